@@ -1,0 +1,208 @@
+"""ctypes loader for the CPU checkers in oracle/ (TEST INFRASTRUCTURE ONLY).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module.  The product (generic-linalg_b200/) never does.
+
+    orc = load("ref")    # oracle/_ref/libref_oracle.so  -- unmodified reference sources
+    orc = load("port")   # oracle/libport_oracle.so      -- our restatement
+    orc = load("best")   # ref if it was built, else port
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+# must mirror oracle/oracle_api.h
+OP = dict(LAPLACE_REAL=0, LAPLACE_IMAG=1, LAPLACE_NC=2, LAPLACE_U1=3, STAG_FREE=4, STAG_U1=5,
+          STAG_GAMMA5_U1=6, STAG_DAGGER_U1=7, STAG_NORMAL_U1=8, GAMMA5=9, STENCIL=10,
+          STENCIL_FROM_STAG=11, STAG_GAMMA5_FREE=12, LAPLACE_REAL_NC=13, STAG_FREE_REAL=14)
+SOLVER = dict(CG=0, CG_RESTART=1, CR=2, CR_RESTART=3, GCR=4, GCR_RESTART=5, BICGSTAB=6,
+              BICGSTAB_RESTART=7, BICGSTAB_L=8, BICGSTAB_L_RESTART=9, GMRES=10, GMRES_RESTART=11)
+
+
+class OpDesc(C.Structure):
+    _fields_ = [("kind", C.c_int), ("X", C.c_int), ("Y", C.c_int), ("Nc", C.c_int),
+                ("mass", C.c_double), ("links", C.c_void_p), ("clover", C.c_void_p),
+                ("hopping", C.c_void_p), ("two_link", C.c_void_p), ("has_two", C.c_int),
+                ("shift", C.c_double * 2), ("eo_shift", C.c_double * 2), ("dof_shift", C.c_double * 2)]
+
+
+class Result(C.Structure):
+    _fields_ = [("resSq", C.c_double), ("iter", C.c_int), ("success", C.c_int), ("ops_count", C.c_int),
+                ("n_rhs", C.c_int), ("resSqmrhs", C.c_double * 32), ("name", C.c_char * 64)]
+
+    def as_dict(self):
+        d = dict(resSq=self.resSq, iter=self.iter, success=bool(self.success), ops_count=self.ops_count,
+                 name=self.name.decode())
+        if self.n_rhs > 0:
+            d["resSqmrhs"] = [self.resSqmrhs[i] for i in range(self.n_rhs)]
+        return d
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Operator:
+    def __init__(self, orc, kind, X, Y, mass=0.0, Nc=1, links=None, clover=None, hopping=None, two_link=None,
+                 shift=0j, eo_shift=0j, dof_shift=0j):
+        self.orc = orc
+        self._keep = (links, clover, hopping, two_link)
+        d = OpDesc()
+        d.kind = OP[kind] if isinstance(kind, str) else kind
+        d.X, d.Y, d.Nc, d.mass = X, Y, Nc, mass
+        d.links, d.clover, d.hopping, d.two_link = _ptr(links), _ptr(clover), _ptr(hopping), _ptr(two_link)
+        d.has_two = 1 if two_link is not None else 0
+        for name, v in (("shift", shift), ("eo_shift", eo_shift), ("dof_shift", dof_shift)):
+            getattr(d, name)[0] = complex(v).real
+            getattr(d, name)[1] = complex(v).imag
+        self.desc = d
+        self.h = orc._f("op_prepare")(C.byref(d))
+        self.is_complex = bool(orc._f("op_is_complex")(self.h))
+        self.size = orc._f("op_size")(self.h)
+        self.dtype = np.complex128 if self.is_complex else np.float64
+
+    def apply(self, rhs):
+        rhs = np.ascontiguousarray(rhs, dtype=self.dtype)
+        out = np.empty_like(rhs)
+        self.orc._f("op_apply")(self.h, _ptr(out), _ptr(rhs))
+        return out
+
+    def __del__(self):
+        try:
+            self.orc._f("op_free")(self.h)
+        except Exception:
+            pass
+
+
+class Oracle:
+    def __init__(self, path, prefix):
+        self.lib = C.CDLL(path)
+        self.prefix = prefix
+        self.path = path
+        L = self.lib
+        vp, ci, cd = C.c_void_p, C.c_int, C.c_double
+        sig = {
+            "kind": (C.c_char_p, []),
+            "rng_new": (vp, [C.c_uint]), "rng_free": (None, [vp]),
+            "gauss_gauge_u1": (None, [vp, vp, ci, ci, cd]), "unit_gauge_u1": (None, [vp, ci, ci]),
+            "gaussian_real": (None, [vp, vp, ci]), "gaussian_complex": (None, [vp, vp, ci]),
+            "read_gauge_u1": (ci, [vp, ci, ci, C.c_char_p]), "plaquette_u1": (None, [vp, ci, ci, vp]),
+            "dot": (None, [ci, vp, vp, ci, vp]), "norm2sq": (cd, [ci, vp, ci]), "diffnorm2sq": (cd, [ci, vp, vp, ci]),
+            "op_prepare": (vp, [C.POINTER(OpDesc)]), "op_free": (None, [vp]), "op_is_complex": (ci, [vp]),
+            "op_size": (ci, [vp]), "op_apply": (None, [vp, vp, vp]),
+            "solve": (ci, [ci, vp, vp, vp, ci, cd, ci, ci, ci, C.POINTER(Result)]),
+            "solve_cg_m": (ci, [vp, C.POINTER(vp), vp, ci, ci, ci, cd, vp, ci, ci, C.POINTER(Result)]),
+        }
+        for name, (res, args) in sig.items():
+            f = getattr(L, prefix + name)
+            f.restype, f.argtypes = res, args
+        self.kind = self._f("kind")().decode()
+
+    def _f(self, name):
+        return getattr(self.lib, self.prefix + name)
+
+    # ---- input generation (same std::mt19937 stream as the reference's tests) ----
+    class Rng:
+        def __init__(self, orc, seed):
+            self.orc, self.h = orc, orc._f("rng_new")(seed)
+
+        def gauss_gauge_u1(self, X, Y, beta):
+            U = np.empty(2 * X * Y, dtype=np.complex128)
+            self.orc._f("gauss_gauge_u1")(self.h, _ptr(U), X, Y, beta)
+            return U
+
+        def gaussian(self, n, dtype=np.complex128):
+            v = np.empty(n, dtype=dtype)
+            self.orc._f("gaussian_complex" if dtype == np.complex128 else "gaussian_real")(self.h, _ptr(v), n)
+            return v
+
+        def __del__(self):
+            try:
+                self.orc._f("rng_free")(self.h)
+            except Exception:
+                pass
+
+    def rng(self, seed=1337):
+        return Oracle.Rng(self, seed)
+
+    def unit_gauge(self, X, Y):
+        U = np.empty(2 * X * Y, dtype=np.complex128)
+        self._f("unit_gauge_u1")(_ptr(U), X, Y)
+        return U
+
+    def read_gauge(self, X, Y, path):
+        U = np.empty(2 * X * Y, dtype=np.complex128)
+        rc = self._f("read_gauge_u1")(_ptr(U), X, Y, path.encode())
+        if rc != 0:
+            raise IOError("cannot read gauge field %s (rc=%d)" % (path, rc))
+        return U
+
+    def plaquette(self, U, X, Y):
+        out = np.zeros(2)
+        self._f("plaquette_u1")(_ptr(U), X, Y, _ptr(out))
+        return complex(out[0], out[1])
+
+    # ---- BLAS-1 ----
+    def dot(self, a, b):
+        isc = int(a.dtype == np.complex128)
+        out = np.zeros(2)
+        self._f("dot")(isc, _ptr(a), _ptr(b), a.size, _ptr(out))
+        return complex(out[0], out[1]) if isc else out[0]
+
+    def norm2sq(self, a):
+        return self._f("norm2sq")(int(a.dtype == np.complex128), _ptr(a), a.size)
+
+    def diffnorm2sq(self, a, b):
+        return self._f("diffnorm2sq")(int(a.dtype == np.complex128), _ptr(a), _ptr(b), a.size)
+
+    # ---- operators / solvers ----
+    def op(self, kind, X, Y, **kw):
+        return Operator(self, kind, X, Y, **kw)
+
+    def solve(self, solver, op, b, x0=None, max_iter=10000, eps=1e-10, restart_freq=0, l=0, verbosity=0):
+        b = np.ascontiguousarray(b, dtype=op.dtype)
+        x = np.zeros_like(b) if x0 is None else np.array(x0, dtype=op.dtype, copy=True)
+        res = Result()
+        s = SOLVER[solver] if isinstance(solver, str) else solver
+        self._f("solve")(s, op.h, _ptr(x), _ptr(b), max_iter, eps, restart_freq, l, verbosity, C.byref(res))
+        return x, res.as_dict()
+
+    def solve_cg_m(self, op, b, shifts, resid_freq_check=10, max_iter=10000, eps=1e-10, worst_first=False,
+                   verbosity=0):
+        b = np.ascontiguousarray(b, dtype=op.dtype)
+        shifts = np.array(shifts, dtype=np.float64, copy=True)
+        n = len(shifts)
+        xs = [np.zeros_like(b) for _ in range(n)]
+        ptrs = (C.c_void_p * n)(*[x.ctypes.data for x in xs])
+        res = Result()
+        self._f("solve_cg_m")(op.h, ptrs, _ptr(b), n, resid_freq_check, max_iter, eps, _ptr(shifts),
+                              int(worst_first), verbosity, C.byref(res))
+        # the solver may have permuted the pointer array; map back by address
+        by_addr = {x.ctypes.data: x for x in xs}
+        xs = [by_addr[ptrs[i]] for i in range(n)]
+        return xs, res.as_dict(), shifts
+
+
+def available():
+    out = []
+    if os.path.exists(os.path.join(HERE, "_ref", "libref_oracle.so")):
+        out.append("ref")
+    if os.path.exists(os.path.join(HERE, "libport_oracle.so")):
+        out.append("port")
+    return out
+
+
+def load(which="best"):
+    if which == "best":
+        av = available()
+        if not av:
+            raise RuntimeError("no oracle library built: run `make -C oracle` (or __graft_entry__.build())")
+        which = av[0]
+    if which == "ref":
+        return Oracle(os.path.join(HERE, "_ref", "libref_oracle.so"), "ref_")
+    if which == "port":
+        return Oracle(os.path.join(HERE, "libport_oracle.so"), "port_")
+    raise ValueError(which)
