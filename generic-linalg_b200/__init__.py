@@ -1,0 +1,428 @@
+"""generic-linalg_b200 -- Python harness over the two in-tree native libraries.
+
+    libglb200.so            CUDA kernels (sm_100a) + runtime + the C ABI of include/glb200.h
+    libglb200_inverters.so  C++ drop-in solver shells with the reference's signatures
+
+The product is the native code; this module is plumbing for tests/ and bench.py (ctypes
+bindings, numpy <-> device copies, torch.distributed bootstrap of the slab communicator).
+It never computes anything itself and there is no CPU fallback: importing works anywhere,
+but creating a Context without the built libraries or without a GPU raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_CUDA = os.path.join(HERE, "libglb200.so")
+LIB_HOST = os.path.join(HERE, "libglb200_inverters.so")
+
+REAL, COMPLEX = 0, 1
+STAG_DAGGER, STAG_GAMMA5, STAG_NORMAL = 1, 2, 4
+
+# operator / solver selectors of host/capi_solvers.cpp (same numbering as oracle/oracle_api.h)
+OP = dict(LAPLACE_REAL=0, LAPLACE_IMAG=1, LAPLACE_NC=2, LAPLACE_U1=3, STAG_FREE=4, STAG_U1=5,
+          STAG_GAMMA5_U1=6, STAG_DAGGER_U1=7, STAG_NORMAL_U1=8, GAMMA5=9, STENCIL=10,
+          STENCIL_FROM_STAG=11, STAG_GAMMA5_FREE=12, LAPLACE_REAL_NC=13)
+SOLVER = dict(CG=0, CG_RESTART=1, CR=2, CR_RESTART=3, GCR=4, GCR_RESTART=5, BICGSTAB=6,
+              BICGSTAB_RESTART=7, BICGSTAB_L=8, BICGSTAB_L_RESTART=9, GMRES=10, GMRES_RESTART=11)
+
+
+class GlbError(RuntimeError):
+    pass
+
+
+class OpDesc(C.Structure):
+    _fields_ = [("kind", C.c_int), ("X", C.c_int), ("Y", C.c_int), ("Nc", C.c_int),
+                ("mass", C.c_double), ("links", C.c_void_p), ("clover", C.c_void_p),
+                ("hopping", C.c_void_p), ("two_link", C.c_void_p), ("has_two", C.c_int),
+                ("shift", C.c_double * 2), ("eo_shift", C.c_double * 2), ("dof_shift", C.c_double * 2)]
+
+
+class Result(C.Structure):
+    _fields_ = [("resSq", C.c_double), ("iter", C.c_int), ("success", C.c_int), ("ops_count", C.c_int),
+                ("n_rhs", C.c_int), ("resSqmrhs", C.c_double * 32), ("name", C.c_char * 64)]
+
+    def as_dict(self):
+        d = dict(resSq=self.resSq, iter=self.iter, success=bool(self.success), ops_count=self.ops_count,
+                 name=self.name.decode())
+        if self.n_rhs > 0:
+            d["resSqmrhs"] = [self.resSqmrhs[i] for i in range(self.n_rhs)]
+        return d
+
+
+class CgReport(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("ops", C.c_int), ("hit_max_iter", C.c_int),
+                ("rsq", C.c_double), ("bnorm", C.c_double)]
+
+
+_libs = None
+
+
+def libs():
+    """Load both native libraries (once).  Raises GlbError when they were not built."""
+    global _libs
+    if _libs is not None:
+        return _libs
+    for p in (LIB_CUDA, LIB_HOST):
+        if not os.path.exists(p):
+            raise GlbError("native library %s is missing: run __graft_entry__.build() "
+                           "(make -C generic-linalg_b200); there is no Python/CPU fallback" % p)
+    # RTLD_LOCAL: the drop-in library exports the reference's own symbol names (minv_vector_cg, ...);
+    # keeping them out of the global scope stops them interposing on the reference-compiled oracle.
+    cu = C.CDLL(LIB_CUDA, mode=C.RTLD_LOCAL)
+    ho = C.CDLL(LIB_HOST, mode=C.RTLD_LOCAL)
+    vp, ci, cd, sz = C.c_void_p, C.c_int, C.c_double, C.c_size_t
+    pd = C.POINTER(C.c_double)
+    sig = {
+        "glb_create": (ci, [ci, C.POINTER(vp)]), "glb_destroy": (ci, [vp]),
+        "glb_last_error": (C.c_char_p, []), "glb_synchronize": (ci, [vp]), "glb_stream": (vp, [vp]),
+        "glb_device": (ci, [vp]), "glb_sm_count": (ci, [vp]), "glb_kernel_launches": (C.c_ulonglong, []),
+        "glb_comm_unique_id": (ci, [C.c_char_p]), "glb_comm_init": (ci, [vp, ci, ci, C.c_char_p]),
+        "glb_comm_rank": (ci, [vp]), "glb_comm_size": (ci, [vp]), "glb_comm_barrier": (ci, [vp]),
+        "glb_vec_alloc": (ci, [vp, ci, sz, C.POINTER(vp)]), "glb_vec_free": (ci, [vp, vp]),
+        "glb_vec_upload": (ci, [vp, ci, sz, vp, vp]), "glb_vec_download": (ci, [vp, ci, sz, vp, vp]),
+        "glb_vec_zero": (ci, [vp, ci, sz, vp]), "glb_vec_copy": (ci, [vp, ci, sz, vp, vp]),
+        "glb_host_alloc": (ci, [vp, sz, C.POINTER(vp)]), "glb_host_free": (ci, [vp, vp]),
+        "glb_op_create_laplace": (ci, [vp, ci, ci, ci, ci, cd, cd, C.POINTER(vp)]),
+        "glb_op_create_laplace_u1": (ci, [vp, vp, ci, ci, cd, C.POINTER(vp)]),
+        "glb_op_create_staggered": (ci, [vp, vp, ci, ci, cd, C.c_uint, C.POINTER(vp)]),
+        "glb_op_create_gamma5": (ci, [vp, ci, ci, C.POINTER(vp)]),
+        "glb_op_create_stencil2d": (ci, [vp, vp, vp, vp, ci, ci, ci, pd, pd, pd, C.POINTER(vp)]),
+        "glb_op_destroy": (ci, [vp]), "glb_op_set_mass": (ci, [vp, cd]), "glb_op_dtype": (ci, [vp]),
+        "glb_op_local_size": (sz, [vp]), "glb_op_global_size": (sz, [vp]),
+        "glb_op_apply": (ci, [vp, vp, vp]), "glb_op_apply_dot": (ci, [vp, vp, vp, vp, ci, pd]),
+        "glb_op_bytes_per_apply": (cd, [vp]),
+        "glb_dot": (ci, [vp, ci, sz, vp, vp, pd]), "glb_norm2sq": (ci, [vp, ci, sz, vp, pd]),
+        "glb_diffnorm2sq": (ci, [vp, ci, sz, vp, vp, pd]), "glb_dot_norm": (ci, [vp, ci, sz, vp, vp, pd]),
+        "glb_multi_dot": (ci, [vp, ci, sz, ci, C.POINTER(vp), vp, pd]),
+        "glb_sub": (ci, [vp, ci, sz, vp, vp, vp]), "glb_add": (ci, [vp, ci, sz, vp, vp, vp]),
+        "glb_axpy": (ci, [vp, ci, sz, pd, vp, vp]), "glb_xpay": (ci, [vp, ci, sz, vp, pd, vp]),
+        "glb_axpyz": (ci, [vp, ci, sz, pd, vp, vp, vp]), "glb_rdiv": (ci, [vp, ci, sz, vp, cd, vp]),
+        "glb_axpy_norm": (ci, [vp, ci, sz, pd, vp, vp, pd]),
+        "glb_lincomb": (ci, [vp, ci, sz, ci, pd, C.POINTER(vp), vp, vp]),
+        "glb_update_xr_norm": (ci, [vp, ci, sz, pd, vp, vp, pd, vp, vp, pd]),
+        "glb_update_p_ap_norm": (ci, [vp, ci, sz, vp, vp, pd, vp, vp, pd]),
+        "glb_bicgstab_update": (ci, [vp, ci, sz, pd, vp, pd, vp, vp, vp, vp, vp, pd]),
+        "glb_bicgstab_pupdate": (ci, [vp, ci, sz, vp, pd, pd, vp, vp]),
+        "glb_cgm_update_x": (ci, [vp, ci, sz, ci, pd, C.POINTER(vp), C.POINTER(vp)]),
+        "glb_cgm_update_p": (ci, [vp, ci, sz, ci, pd, pd, vp, C.POINTER(vp)]),
+        "glb_cg_solve": (ci, [vp, vp, vp, ci, cd, C.POINTER(CgReport), pd, ci]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(cu, name)
+        f.restype, f.argtypes = res, args
+    hsig = {
+        "glbx_default_context": (vp, []), "glbx_set_default_context": (None, [vp]),
+        "glbx_force_host_scalars": (None, [ci]), "glbx_allow_host_callback_shim": (None, [ci]),
+        "glbx_cache_operators": (None, [ci]),
+        "glbx_host_apply": (ci, [C.POINTER(OpDesc), vp, vp]),
+        "glbx_host_solve": (ci, [ci, C.POINTER(OpDesc), vp, vp, ci, cd, ci, ci, ci, C.POINTER(Result)]),
+        "glbx_host_solve_cg_m": (ci, [C.POINTER(OpDesc), C.POINTER(vp), vp, ci, ci, ci, cd, vp, ci, ci,
+                                      C.POINTER(Result)]),
+        "glbx_dev_solve": (ci, [ci, vp, vp, vp, ci, cd, ci, ci, ci, C.POINTER(Result)]),
+        "glbx_dev_solve_cg_m": (ci, [vp, C.POINTER(vp), vp, ci, ci, ci, cd, vp, ci, ci, C.POINTER(Result)]),
+    }
+    for name, (res, args) in hsig.items():
+        f = getattr(ho, name)
+        f.restype, f.argtypes = res, args
+    _libs = (cu, ho)
+    return _libs
+
+
+def exported_symbols():
+    """Names declared in include/glb200.h (used by the CPU test that checks the ABI surface)."""
+    import re
+    hdr = open(os.path.join(HERE, "..", "include", "glb200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(glb_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def _chk(rc, what=""):
+    if rc != 0:
+        cu, _ = libs()
+        raise GlbError("%s failed (code %d): %s" % (what, rc, cu.glb_last_error().decode()))
+
+
+def _dt(arr_or_dtype):
+    d = arr_or_dtype.dtype if hasattr(arr_or_dtype, "dtype") else np.dtype(arr_or_dtype)
+    if d == np.complex128:
+        return COMPLEX
+    if d == np.float64:
+        return REAL
+    raise TypeError("only float64 / complex128 vectors exist on this path")
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _c2(z):
+    z = complex(z)
+    return (C.c_double * 2)(z.real, z.imag)
+
+
+class DeviceVector:
+    """A device-resident vector (slab-local on multi-GPU runs)."""
+
+    def __init__(self, ctx, n, dtype):
+        self.ctx, self.n, self.dtype = ctx, int(n), np.dtype(dtype)
+        self.dt = _dt(self.dtype)
+        p = C.c_void_p()
+        _chk(ctx.cu.glb_vec_alloc(ctx.h, self.dt, self.n, C.byref(p)), "glb_vec_alloc")
+        self.ptr = p.value
+
+    def upload(self, host):
+        host = np.ascontiguousarray(host, dtype=self.dtype)
+        assert host.size == self.n
+        _chk(self.ctx.cu.glb_vec_upload(self.ctx.h, self.dt, self.n, self.ptr, _p(host)), "glb_vec_upload")
+        return self
+
+    def download(self, out=None):
+        out = np.empty(self.n, dtype=self.dtype) if out is None else out
+        _chk(self.ctx.cu.glb_vec_download(self.ctx.h, self.dt, self.n, _p(out), self.ptr), "glb_vec_download")
+        return out
+
+    def zero(self):
+        _chk(self.ctx.cu.glb_vec_zero(self.ctx.h, self.dt, self.n, self.ptr), "glb_vec_zero")
+        return self
+
+    def copy_from(self, other):
+        _chk(self.ctx.cu.glb_vec_copy(self.ctx.h, self.dt, self.n, self.ptr, other.ptr), "glb_vec_copy")
+        return self
+
+    def free(self):
+        if self.ptr:
+            self.ctx.cu.glb_vec_free(self.ctx.h, self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Operator:
+    def __init__(self, ctx, handle, keep=()):
+        self.ctx, self.h, self._keep = ctx, handle, keep
+        cu = ctx.cu
+        self.dtype = np.complex128 if cu.glb_op_dtype(handle) == COMPLEX else np.float64
+        self.local_size = cu.glb_op_local_size(handle)
+        self.global_size = cu.glb_op_global_size(handle)
+        self.bytes_per_apply = cu.glb_op_bytes_per_apply(handle)
+
+    def apply(self, out, inp):
+        _chk(self.ctx.cu.glb_op_apply(self.h, out.ptr, inp.ptr), "glb_op_apply")
+
+    def apply_dot(self, out, inp, w=None, want_norm=False):
+        d = (C.c_double * 3)()
+        _chk(self.ctx.cu.glb_op_apply_dot(self.h, out.ptr, inp.ptr, w.ptr if w is not None else None,
+                                          int(want_norm), d), "glb_op_apply_dot")
+        return complex(d[0], d[1]), d[2]
+
+    def set_mass(self, m):
+        _chk(self.ctx.cu.glb_op_set_mass(self.h, m))
+
+    def apply_host(self, v):
+        """upload -> apply -> download (convenience for tests)"""
+        a = self.ctx.vector(self.local_size, self.dtype).upload(v)
+        b = self.ctx.vector(self.local_size, self.dtype)
+        self.apply(b, a)
+        return b.download()
+
+    def destroy(self):
+        if self.h:
+            self.ctx.cu.glb_op_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+class Context:
+    """One GPU context = one process's view of the library (one per rank)."""
+
+    def __init__(self, device=None, use_default=True):
+        self.cu, self.ho = libs()
+        if use_default:
+            # share the C++ layer's process-wide context so host-pointer and device calls agree
+            if device is not None:
+                os.environ.setdefault("GLB200_DEVICE", str(device))
+            h = self.ho.glbx_default_context()
+            if not h:
+                raise GlbError("no CUDA device / context: " + self.cu.glb_last_error().decode())
+            self.h, self.owned = h, False
+        else:
+            p = C.c_void_p()
+            _chk(self.cu.glb_create(int(device or 0), C.byref(p)), "glb_create")
+            self.h, self.owned = p.value, True
+
+    # ---- communicator bootstrap through torch.distributed (any launcher would do) ----
+    def init_comm_from_torch(self):
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        buf = C.create_string_buffer(128)
+        if rank == 0:
+            _chk(self.cu.glb_comm_unique_id(buf), "glb_comm_unique_id")
+        obj = [bytes(buf.raw)]
+        dist.broadcast_object_list(obj, src=0)
+        _chk(self.cu.glb_comm_init(self.h, rank, world, obj[0]), "glb_comm_init")
+        return rank, world
+
+    @property
+    def rank(self):
+        return self.cu.glb_comm_rank(self.h)
+
+    @property
+    def nranks(self):
+        return self.cu.glb_comm_size(self.h)
+
+    def barrier(self):
+        _chk(self.cu.glb_comm_barrier(self.h), "glb_comm_barrier")
+
+    def sync(self):
+        _chk(self.cu.glb_synchronize(self.h), "glb_synchronize")
+
+    def stream(self):
+        return self.cu.glb_stream(self.h)
+
+    def launches(self):
+        return int(self.cu.glb_kernel_launches())
+
+    def vector(self, n, dtype=np.complex128):
+        return DeviceVector(self, n, dtype)
+
+    def pinned(self, n, dtype=np.complex128):
+        """numpy view of pinned host memory (for end-to-end timing with host buffers)"""
+        dtype = np.dtype(dtype)
+        p = C.c_void_p()
+        _chk(self.cu.glb_host_alloc(self.h, n * dtype.itemsize, C.byref(p)), "glb_host_alloc")
+        arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_byte)), shape=(n * dtype.itemsize,)).view(dtype)
+        return arr
+
+    # ---- operators ----
+    def _op(self, fn, *args, keep=()):
+        p = C.c_void_p()
+        _chk(fn(self.h, *args, C.byref(p)), fn.__name__)
+        return Operator(self, p.value, keep)
+
+    def laplace(self, X, Y, Nc=1, diag=4.01, dtype=np.float64):
+        diag = complex(diag)
+        return self._op(self.cu.glb_op_create_laplace, _dt(dtype), X, Y, Nc, diag.real, diag.imag)
+
+    def laplace_u1(self, links, X, Y, mass):
+        links = np.ascontiguousarray(links, dtype=np.complex128)
+        return self._op(self.cu.glb_op_create_laplace_u1, _p(links), X, Y, mass)
+
+    def staggered(self, links, X, Y, mass, flags=0):
+        if links is not None:
+            links = np.ascontiguousarray(links, dtype=np.complex128)
+        return self._op(self.cu.glb_op_create_staggered, _p(links), X, Y, mass, flags)
+
+    def gamma5(self, X, Y):
+        return self._op(self.cu.glb_op_create_gamma5, X, Y)
+
+    def stencil2d(self, clover, hopping, two_link, X, Y, nc, shift=0j, eo_shift=0j, dof_shift=0j):
+        arrs = [np.ascontiguousarray(a, dtype=np.complex128) if a is not None else None
+                for a in (clover, hopping, two_link)]
+        return self._op(self.cu.glb_op_create_stencil2d, _p(arrs[0]), _p(arrs[1]), _p(arrs[2]), X, Y, nc,
+                        _c2(shift), _c2(eo_shift), _c2(dof_shift))
+
+    # ---- BLAS-1 (thin; used by the parity tests) ----
+    def dot(self, x, y):
+        o = (C.c_double * 2)()
+        _chk(self.cu.glb_dot(self.h, x.dt, x.n, x.ptr, y.ptr, o), "glb_dot")
+        return complex(o[0], o[1]) if x.dt == COMPLEX else o[0]
+
+    def norm2sq(self, x):
+        o = C.c_double()
+        _chk(self.cu.glb_norm2sq(self.h, x.dt, x.n, x.ptr, C.byref(o)), "glb_norm2sq")
+        return o.value
+
+    def diffnorm2sq(self, x, y):
+        o = C.c_double()
+        _chk(self.cu.glb_diffnorm2sq(self.h, x.dt, x.n, x.ptr, y.ptr, C.byref(o)), "glb_diffnorm2sq")
+        return o.value
+
+    # ---- solvers on device vectors (device variant of the callback contract) ----
+    def solve(self, solver, op, x, b, max_iter=10000, eps=1e-10, restart_freq=0, l=0, verbosity=0):
+        res = Result()
+        s = SOLVER[solver] if isinstance(solver, str) else solver
+        _chk(self.ho.glbx_dev_solve(s, op.h, x.ptr, b.ptr, max_iter, eps, restart_freq, l, verbosity,
+                                    C.byref(res)), "glbx_dev_solve")
+        return res.as_dict()
+
+    def solve_cg_m(self, op, xs, b, shifts, resid_freq_check=10, max_iter=10000, eps=1e-10, worst_first=False,
+                   verbosity=0):
+        n = len(xs)
+        shifts = np.array(shifts, dtype=np.float64, copy=True)
+        ptrs = (C.c_void_p * n)(*[x.ptr for x in xs])
+        res = Result()
+        _chk(self.ho.glbx_dev_solve_cg_m(op.h, ptrs, b.ptr, n, resid_freq_check, max_iter, eps, _p(shifts),
+                                         int(worst_first), verbosity, C.byref(res)), "glbx_dev_solve_cg_m")
+        return res.as_dict(), shifts
+
+    def cg_device(self, op, x, b, max_iter=10000, eps=1e-10, want_history=False):
+        """glb_cg_solve: the device-resident CG loop (no final true-residual apply)."""
+        rep = CgReport()
+        hist = np.zeros(max_iter if want_history else 0)
+        _chk(self.cu.glb_cg_solve(op.h, x.ptr, b.ptr, max_iter, eps, C.byref(rep),
+                                  hist.ctypes.data_as(C.POINTER(C.c_double)) if want_history else None,
+                                  max_iter if want_history else 0), "glb_cg_solve")
+        out = dict(iterations=rep.iterations, ops=rep.ops, hit_max_iter=bool(rep.hit_max_iter), rsq=rep.rsq,
+                   bnorm=rep.bnorm)
+        if want_history:
+            out["history"] = hist[:rep.iterations]
+        return out
+
+    # ---- the reference's own calls: HOST vectors + reference-named callbacks ----
+    def _desc(self, kind, X, Y, mass=0.0, Nc=1, links=None, clover=None, hopping=None, two_link=None, shift=0j,
+              eo_shift=0j, dof_shift=0j):
+        d = OpDesc()
+        d.kind = OP[kind] if isinstance(kind, str) else kind
+        d.X, d.Y, d.Nc, d.mass = X, Y, Nc, mass
+        d.links, d.clover, d.hopping, d.two_link = _p(links), _p(clover), _p(hopping), _p(two_link)
+        d.has_two = 1 if two_link is not None else 0
+        for name, v in (("shift", shift), ("eo_shift", eo_shift), ("dof_shift", dof_shift)):
+            getattr(d, name)[0], getattr(d, name)[1] = complex(v).real, complex(v).imag
+        d._keep = (links, clover, hopping, two_link)
+        return d
+
+    def host_apply(self, desc, rhs):
+        out = np.empty_like(rhs)
+        _chk(self.ho.glbx_host_apply(C.byref(desc), _p(out), _p(rhs)), "glbx_host_apply")
+        return out
+
+    def host_solve(self, solver, desc, x, b, max_iter=10000, eps=1e-10, restart_freq=0, l=0, verbosity=0):
+        """x (numpy, in/out) and b (numpy) are HOST arrays: copies are part of the call."""
+        res = Result()
+        s = SOLVER[solver] if isinstance(solver, str) else solver
+        _chk(self.ho.glbx_host_solve(s, C.byref(desc), _p(x), _p(b), max_iter, eps, restart_freq, l, verbosity,
+                                     C.byref(res)), "glbx_host_solve")
+        return res.as_dict()
+
+    def host_solve_cg_m(self, desc, xs, b, shifts, resid_freq_check=10, max_iter=10000, eps=1e-10,
+                        worst_first=False, verbosity=0):
+        n = len(xs)
+        shifts = np.array(shifts, dtype=np.float64, copy=True)
+        ptrs = (C.c_void_p * n)(*[x.ctypes.data for x in xs])
+        res = Result()
+        _chk(self.ho.glbx_host_solve_cg_m(C.byref(desc), ptrs, _p(b), n, resid_freq_check, max_iter, eps,
+                                          _p(shifts), int(worst_first), verbosity, C.byref(res)),
+             "glbx_host_solve_cg_m")
+        return res.as_dict(), shifts
+
+    def force_host_scalars(self, on):
+        self.ho.glbx_force_host_scalars(int(on))
+
+    def cache_operators(self, on):
+        self.ho.glbx_cache_operators(int(on))
+
+    def close(self):
+        if self.owned and self.h:
+            self.cu.glb_destroy(self.h)
+            self.h = None

@@ -1,0 +1,205 @@
+// cg.cu -- device-resident conjugate gradient: the loop of minv_vector_cg
+// (generic_cg.cpp:159-206 real, :307-354 complex) with no host round trip per iteration.
+//
+// Per iteration the stream carries
+//   K3  cg_update_kernel : alpha = rsq/<p,Ap>; x += alpha p; r -= alpha Ap; rsqNew = |r|^2;
+//                          last block: iter++, stopping test, history
+//   K1  direction + apply: beta = rsqNew/rsq; p = r + beta p   fused into the operator apply
+//                          (staggered family, single rank) or a separate xpay kernel
+//   K2  (normal operator): Ap = D^dag (D p) with <p,Ap> accumulated in the apply's epilogue;
+//                          last block publishes <p,Ap> and rsq <- rsqNew
+// Fused minimum traffic (SURVEY 8 d-bytes): 192 B/site for a single-apply Hermitian operator,
+// 272 B/site for D^dag D.  The host enqueues BATCH iterations at a time and polls the state of
+// the previous batch while the next one runs; kernels of iterations past the stopping point
+// return at once, so the iteration count is exactly the reference's.
+#include <vector>
+
+#include "cg_state.cuh"
+#include "runtime.hpp"
+
+namespace glb {
+
+int launch_cg_update(glb_context* ctx, int dtype, void* st, double* hist, const void* p, void* x, const void* Ap,
+                     void* r, size_t n);
+int launch_cg_xpay(glb_context* ctx, int dtype, const void* st, const void* r, void* p, size_t n);
+int op_apply_fused(glb_operator* op, void* out, const void* in, const ApplyFusion& f);
+int allreduce_device(glb_context* ctx, double* d_vals, int n);
+
+static bool can_fuse_direction(const glb_operator* op) {
+  return op->ctx->nranks == 1 && (op->kind == OPK_STAGGERED || op->kind == OPK_LAPLACE_U1) && op->X >= 2;
+}
+
+// p_next = r + beta p_cur ; Ap = A p_next ; <p_next, Ap> -> state.  Returns which buffer holds p.
+static int direction_and_apply(glb_operator* op, CgState* d_st, const void* r, void* p_cur, void* p_alt, void* Ap,
+                               bool* swapped) {
+  glb_context* ctx = op->ctx;
+  const size_t n = glb_op_local_size(op);
+  *swapped = false;
+  if (can_fuse_direction(op)) {
+    ApplyFusion f;
+    f.r = r;
+    f.p_old = p_cur;
+    f.p_new = p_alt;
+    f.cg_state = (const double*)d_st;
+    *swapped = true;
+    if (op->flags & GLB_STAG_NORMAL) {
+      // K1: t = D (r + beta p), p_alt = r + beta p
+      int rc = launch_staggered(op, op->tmp, nullptr, false, f);
+      if (rc) return rc;
+      // K2: Ap = D^dag t, <p_alt, Ap>
+      ApplyFusion g;
+      g.w = p_alt;
+      g.cg_state = (const double*)d_st;
+      g.cg_role = 1;
+      return launch_staggered(op, Ap, op->tmp, true, g);
+    }
+    f.w = p_alt;  // dot partner = the freshly formed direction = the kernel's own input
+    f.w_is_input = true;
+    f.cg_role = 1;
+    return launch_staggered(op, Ap, nullptr, (op->flags & GLB_STAG_DAGGER) != 0, f);
+  }
+  int rc = launch_cg_xpay(ctx, op->dtype, d_st, r, p_cur, n);
+  if (rc) return rc;
+  ApplyFusion g;
+  g.w = p_cur;
+  g.w_is_input = true;
+  g.cg_state = (const double*)d_st;
+  g.cg_role = 1;
+  return op_apply_fused(op, Ap, p_cur, g);
+}
+
+}  // namespace glb
+
+using namespace glb;
+
+extern "C" int glb_cg_solve(glb_operator* op, void* d_x, const void* d_b, int max_iter, double eps,
+                            glb_cg_report* rep, double* rsq_hist, int hist_cap) {
+  if (!op || !d_x || !d_b || !rep) return fail(GLB_ERR_ARG, "glb_cg_solve: null argument");
+  if (max_iter < 1) return fail(GLB_ERR_ARG, "glb_cg_solve: max_iter must be >= 1");
+  glb_context* ctx = op->ctx;
+  if (ctx->nranks > 1) return fail(GLB_ERR_STATE, "glb_cg_solve: slab runs use the host-scalar shell in this build");
+  const int dt = op->dtype;
+  const size_t n = glb_op_local_size(op);
+  int rc;
+  void *r = nullptr, *p0 = nullptr, *p1 = nullptr, *Ap = nullptr;
+  CgState* d_st = nullptr;
+  double* d_hist = nullptr;
+  CgState* h_st = nullptr;
+  const bool fuse = can_fuse_direction(op);
+#define CG_TRY(x) \
+  do {            \
+    rc = (x);     \
+    if (rc) goto done; \
+  } while (0)
+  rc = GLB_OK;
+  CG_TRY(glb_vec_alloc(ctx, dt, n, &r));
+  CG_TRY(glb_vec_alloc(ctx, dt, n, &p0));
+  if (fuse) CG_TRY(glb_vec_alloc(ctx, dt, n, &p1));
+  CG_TRY(glb_vec_alloc(ctx, dt, n, &Ap));
+  if (cudaMallocAsync((void**)&d_st, sizeof(CgState), ctx->stream) != cudaSuccess) {
+    rc = fail(GLB_ERR_CUDA, "cudaMallocAsync(CgState)");
+    goto done;
+  }
+  if (hist_cap > 0 && rsq_hist) {
+    if (cudaMallocAsync((void**)&d_hist, sizeof(double) * hist_cap, ctx->stream) != cudaSuccess) {
+      rc = fail(GLB_ERR_CUDA, "cudaMallocAsync(hist)");
+      goto done;
+    }
+  }
+  h_st = (CgState*)ctx->h_table;  // pinned scratch owned by the context (two slots used)
+  {
+    // --- set-up exactly as generic_cg.cpp:304-321: bnorm, r = b - A x, p = r, Ap = A p, rsq
+    double bsq = 0.0, rsq = 0.0, dots[3];
+    CG_TRY(glb_norm2sq(ctx, dt, n, d_b, &bsq));
+    CG_TRY(glb_op_apply(op, p0, d_x));
+    CG_TRY(glb_sub(ctx, dt, n, d_b, p0, r));
+    CG_TRY(glb_vec_copy(ctx, dt, n, p0, r));
+    CG_TRY(glb_op_apply_dot(op, Ap, p0, p0, 0, dots));
+    CG_TRY(glb_norm2sq(ctx, dt, n, r, &rsq));
+    CgState init{};
+    init.rsq_old = rsq;
+    init.rsq_new = rsq;
+    init.pAp_re = dots[0];
+    init.pAp_im = dots[1];
+    init.bnorm = sqrt(bsq);
+    init.eps = eps;
+    init.iter = 0;
+    init.max_iter = max_iter;
+    init.done = (max_iter <= 0) ? 1 : 0;
+    init.hit_max = 0;
+    init.hist_cap = d_hist ? hist_cap : 0;
+    h_st[0] = init;
+    if (cudaMemcpyAsync(d_st, &h_st[0], sizeof(CgState), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+      rc = fail(GLB_ERR_CUDA, "upload CgState");
+      goto done;
+    }
+    rep->bnorm = init.bnorm;
+
+    // --- the loop: enqueue batches, poll the previous batch's state while the next one runs
+    const int BATCH = 8;
+    void* pc = p0;
+    void* pa = p1;
+    int enq = 0;
+    bool finished = (max_iter <= 0);
+    bool have_pending = false;
+    while (!finished) {
+      for (int b = 0; b < BATCH; b++) {
+        CG_TRY(launch_cg_update(ctx, dt, d_st, d_hist, pc, d_x, Ap, r, n));
+        bool swapped = false;
+        CG_TRY(direction_and_apply(op, d_st, r, pc, pa, Ap, &swapped));
+        if (swapped) std::swap(pc, pa);
+        enq++;
+      }
+      // state after this batch -> pinned slot (enq/BATCH)&1, asynchronously
+      const int slot = (enq / BATCH) & 1;
+      if (have_pending) {
+        // the copy of the PREVIOUS batch was recorded on ev_a: wait for it now (this batch is
+        // already queued behind it, so the GPU stays busy)
+        if (cudaEventSynchronize(ctx->ev_a) != cudaSuccess) {
+          rc = fail(GLB_ERR_CUDA, "cudaEventSynchronize");
+          goto done;
+        }
+        if (h_st[slot ^ 1].done) finished = true;
+      }
+      if (cudaMemcpyAsync(&h_st[slot], d_st, sizeof(CgState), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+          cudaEventRecord(ctx->ev_a, ctx->stream) != cudaSuccess) {
+        rc = fail(GLB_ERR_CUDA, "state readback");
+        goto done;
+      }
+      have_pending = true;
+      if (finished) break;
+      if (enq >= max_iter + BATCH) {  // everything that could run has been enqueued
+        finished = true;
+      }
+    }
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+      rc = fail(GLB_ERR_CUDA, "cudaStreamSynchronize");
+      goto done;
+    }
+    if (cudaMemcpy(&h_st[0], d_st, sizeof(CgState), cudaMemcpyDeviceToHost) != cudaSuccess) {
+      rc = fail(GLB_ERR_CUDA, "final state readback");
+      goto done;
+    }
+    const CgState fin = h_st[0];
+    rep->iterations = fin.iter;
+    rep->ops = 2 + (fin.iter > 0 ? fin.iter - 1 : 0);  // one apply per iteration that did not stop
+    rep->hit_max_iter = fin.hit_max;
+    rep->rsq = fin.rsq_new;
+    if (d_hist) {
+      const int m = fin.iter < hist_cap ? fin.iter : hist_cap;
+      if (m > 0 && cudaMemcpy(rsq_hist, d_hist, sizeof(double) * m, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        rc = fail(GLB_ERR_CUDA, "history readback");
+        goto done;
+      }
+    }
+  }
+done:
+  if (d_hist) cudaFreeAsync(d_hist, ctx->stream);
+  if (d_st) cudaFreeAsync(d_st, ctx->stream);
+  glb_vec_free(ctx, Ap);
+  glb_vec_free(ctx, p1);
+  glb_vec_free(ctx, p0);
+  glb_vec_free(ctx, r);
+  return rc;
+#undef CG_TRY
+}

@@ -1,0 +1,25 @@
+// cg_state.cuh -- device-resident scalar state of the CG recurrence (generic_cg.cpp:324-354).
+//
+// alpha, beta and the stopping test live on the device: kernels read what their predecessors in
+// the stream published here, so a CG iteration needs no host round trip.  Once `done` is set
+// every later kernel of the (speculatively enqueued) batch returns immediately.
+#pragma once
+
+namespace glb {
+
+struct CgState {
+  double rsq_old;   // |r_k|^2 that the current search direction was built with ("rsq")
+  double rsq_new;   // |r_{k+1}|^2 ("rsqNew")
+  double pAp_re;    // <p,Ap>
+  double pAp_im;
+  double bnorm;     // sqrt(|b|^2)
+  double eps;
+  int iter;         // completed x/r updates (k+1)
+  int max_iter;
+  int done;         // stopping test fired
+  int hit_max;      // ... because k == max_iter-1
+  int hist_cap;
+  int pad;
+};
+
+}  // namespace glb

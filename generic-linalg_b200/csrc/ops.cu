@@ -1,0 +1,300 @@
+// ops.cu -- operator objects of include/glb200.h: creation (upload + re-layout of links /
+// stencil matrices, slab extraction), apply, apply with fused inner products.
+#include <vector>
+
+#include "runtime.hpp"
+
+namespace glb {
+
+// AoS links lattice[y*X*2 + x*2 + mu] (operators.cpp:215-224) -> two site-major planes
+__global__ void split_links_kernel(const cplx* aos, cplx* Ux, cplx* Uy, size_t nsites) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nsites; i += (size_t)gridDim.x * blockDim.x) {
+    Ux[i] = aos[2 * i];
+    Uy[i] = aos[2 * i + 1];
+  }
+}
+
+static void slab_of(const glb_context* ctx, int Y, int* y0, int* Yloc) {
+  const long long g = ctx->rank, G = ctx->nranks;
+  const int a = (int)((long long)Y * g / G), b = (int)((long long)Y * (g + 1) / G);
+  *y0 = a;
+  *Yloc = b - a;
+}
+
+static int new_op(glb_context* ctx, int kind, int dtype, int X, int Y, int nc, glb_operator** out) {
+  if (!ctx || !out) return fail(GLB_ERR_ARG, "null context / output");
+  if (X < 1 || Y < 1 || nc < 1) return fail(GLB_ERR_ARG, "bad lattice dimensions");
+  if (Y < ctx->nranks) return fail(GLB_ERR_ARG, "fewer lattice rows than ranks");
+  glb_operator* op = new glb_operator();
+  op->ctx = ctx;
+  op->kind = kind;
+  op->dtype = dtype;
+  op->X = X;
+  op->Y = Y;
+  op->nc = nc;
+  slab_of(ctx, Y, &op->y0, &op->Yloc);
+  *out = op;
+  return GLB_OK;
+}
+
+static int alloc_ghosts(glb_operator* op, int depth) {
+  if (op->ctx->nranks == 1) return GLB_OK;
+  const size_t bytes = (size_t)depth * op->X * op->nc * elem_bytes(op->dtype);
+  GLB_CUDA(cudaMalloc(&op->ghost_lo, bytes));
+  GLB_CUDA(cudaMalloc(&op->ghost_hi, bytes));
+  return GLB_OK;
+}
+
+static int upload_links(glb_operator* op, const void* h_links) {
+  glb_context* ctx = op->ctx;
+  const size_t X = op->X, Vloc = X * op->Yloc;
+  const cplx* h = (const cplx*)h_links;
+  cplx* aos = nullptr;
+  GLB_CUDA(cudaMalloc(&aos, sizeof(cplx) * 2 * Vloc));
+  GLB_CUDA(cudaMalloc(&op->Ux, sizeof(cplx) * Vloc));
+  const bool single = (ctx->nranks == 1);
+  // Uy gets one extra leading row when the slab does not wrap onto itself
+  cplx* uy_store = nullptr;
+  GLB_CUDA(cudaMalloc(&uy_store, sizeof(cplx) * (Vloc + (single ? 0 : X))));
+  op->Uy = single ? uy_store : uy_store + X;
+  op->Uy_lo = single ? op->Uy + (size_t)(op->Yloc - 1) * X : uy_store;
+  GLB_CUDA(cudaMemcpyAsync(aos, h + 2 * (size_t)op->y0 * X, sizeof(cplx) * 2 * Vloc, cudaMemcpyHostToDevice,
+                           ctx->stream));
+  const int grid = blas_grid(ctx, Vloc, 256, 4);
+  split_links_kernel<<<grid, 256, 0, ctx->stream>>>(aos, op->Ux, op->Uy, Vloc);
+  GLB_LAUNCH_CHECK();
+  if (!single) {  // U_y of global row y0-1 (periodic)
+    const int ym = (op->y0 + op->Y - 1) % op->Y;
+    std::vector<cplx> row(X);
+    for (size_t x = 0; x < X; x++) row[x] = h[2 * ((size_t)ym * X + x) + 1];
+    GLB_CUDA(cudaMemcpyAsync(uy_store, row.data(), sizeof(cplx) * X, cudaMemcpyHostToDevice, ctx->stream));
+    GLB_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  GLB_CUDA(cudaStreamSynchronize(ctx->stream));
+  GLB_CUDA(cudaFree(aos));
+  op->has_links = true;
+  return GLB_OK;
+}
+
+}  // namespace glb
+
+using namespace glb;
+
+extern "C" {
+
+int glb_op_create_laplace(glb_context* ctx, int dtype, int X, int Y, int Nc, double diag_re, double diag_im,
+                          glb_operator** out) {
+  if (dtype != GLB_REAL && dtype != GLB_COMPLEX) return fail(GLB_ERR_ARG, "bad dtype");
+  if (dtype == GLB_REAL && diag_im != 0.0) return fail(GLB_ERR_ARG, "real Laplacian with complex diagonal");
+  int rc = new_op(ctx, OPK_LAPLACE, dtype, X, Y, Nc, out);
+  if (rc) return rc;
+  (*out)->diag_re = diag_re;
+  (*out)->diag_im = diag_im;
+  return alloc_ghosts(*out, 1);
+}
+
+int glb_op_create_laplace_u1(glb_context* ctx, const void* h_links, int X, int Y, double mass, glb_operator** out) {
+  if (!h_links) return fail(GLB_ERR_ARG, "gauged Laplacian needs links");
+  int rc = new_op(ctx, OPK_LAPLACE_U1, GLB_COMPLEX, X, Y, 1, out);
+  if (rc) return rc;
+  (*out)->mass = mass;
+  rc = upload_links(*out, h_links);
+  if (rc) return rc;
+  return alloc_ghosts(*out, 1);
+}
+
+int glb_op_create_staggered(glb_context* ctx, const void* h_links, int X, int Y, double mass, unsigned flags,
+                            glb_operator** out) {
+  if ((flags & GLB_STAG_NORMAL) && (flags & (GLB_STAG_DAGGER | GLB_STAG_GAMMA5)))
+    return fail(GLB_ERR_ARG, "NORMAL cannot be combined with DAGGER/GAMMA5");
+  if ((flags & GLB_STAG_DAGGER) && (flags & GLB_STAG_GAMMA5)) return fail(GLB_ERR_ARG, "DAGGER+GAMMA5 unsupported");
+  int rc = new_op(ctx, OPK_STAGGERED, GLB_COMPLEX, X, Y, 1, out);
+  if (rc) return rc;
+  glb_operator* op = *out;
+  op->mass = mass;
+  op->flags = flags;
+  if (h_links) {
+    rc = upload_links(op, h_links);
+    if (rc) return rc;
+  }
+  if (flags & GLB_STAG_NORMAL) GLB_CUDA(cudaMalloc(&op->tmp, sizeof(cplx) * (size_t)X * op->Yloc));
+  return alloc_ghosts(op, 1);
+}
+
+int glb_op_create_gamma5(glb_context* ctx, int X, int Y, glb_operator** out) {
+  return new_op(ctx, OPK_GAMMA5, GLB_COMPLEX, X, Y, 1, out);
+}
+
+int glb_op_create_stencil2d(glb_context* ctx, const void* clover, const void* hopping, const void* two_link, int X,
+                            int Y, int nc, const double shift[2], const double eo_shift[2],
+                            const double dof_shift[2], glb_operator** out) {
+  if (!clover || !hopping) return fail(GLB_ERR_ARG, "stencil2d needs clover and hopping arrays");
+  int rc = new_op(ctx, OPK_STENCIL, GLB_COMPLEX, X, Y, nc, out);
+  if (rc) return rc;
+  glb_operator* op = *out;
+  op->has_two = (two_link != nullptr);
+  for (int i = 0; i < 2; i++) {
+    op->shift[i] = shift ? shift[i] : 0.0;
+    op->eo_shift[i] = eo_shift ? eo_shift[i] : 0.0;
+    op->dof_shift[i] = dof_shift ? dof_shift[i] : 0.0;
+  }
+  // matrices of this slab: per direction plane, rows [y0, y0+Yloc) are contiguous in the reference layout
+  const size_t per_site = (size_t)nc * nc;
+  const size_t Vg = (size_t)X * Y, Vl = (size_t)X * op->Yloc, off = (size_t)X * op->y0 * per_site;
+  GLB_CUDA(cudaMalloc(&op->clover, sizeof(cplx) * Vl * per_site));
+  GLB_CUDA(cudaMemcpyAsync(op->clover, (const cplx*)clover + off, sizeof(cplx) * Vl * per_site,
+                           cudaMemcpyHostToDevice, ctx->stream));
+  GLB_CUDA(cudaMalloc(&op->hopping, sizeof(cplx) * 4 * Vl * per_site));
+  for (int d = 0; d < 4; d++)
+    GLB_CUDA(cudaMemcpyAsync(op->hopping + d * Vl * per_site, (const cplx*)hopping + d * Vg * per_site + off,
+                             sizeof(cplx) * Vl * per_site, cudaMemcpyHostToDevice, ctx->stream));
+  if (op->has_two) {
+    GLB_CUDA(cudaMalloc(&op->two_link, sizeof(cplx) * 8 * Vl * per_site));
+    for (int d = 0; d < 8; d++)
+      GLB_CUDA(cudaMemcpyAsync(op->two_link + d * Vl * per_site, (const cplx*)two_link + d * Vg * per_site + off,
+                               sizeof(cplx) * Vl * per_site, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  GLB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return alloc_ghosts(op, op->has_two ? 2 : 1);
+}
+
+int glb_op_destroy(glb_operator* op) {
+  if (!op) return GLB_OK;
+  cudaStreamSynchronize(op->ctx->stream);
+  cudaFree(op->Ux);
+  if (op->Uy) cudaFree(op->ctx->nranks == 1 ? op->Uy : op->Uy - op->X);
+  cudaFree(op->tmp);
+  cudaFree(op->ghost_lo);
+  cudaFree(op->ghost_hi);
+  cudaFree(op->clover);
+  cudaFree(op->hopping);
+  cudaFree(op->two_link);
+  delete op;
+  return GLB_OK;
+}
+
+int glb_op_set_mass(glb_operator* op, double mass) {
+  op->mass = mass;
+  return GLB_OK;
+}
+int glb_op_dtype(const glb_operator* op) { return op->dtype; }
+size_t glb_op_local_size(const glb_operator* op) { return (size_t)op->X * op->Yloc * op->nc; }
+size_t glb_op_global_size(const glb_operator* op) { return (size_t)op->X * op->Y * op->nc; }
+glb_context* glb_op_context(const glb_operator* op) { return op->ctx; }
+
+double glb_op_bytes_per_apply(const glb_operator* op) {
+  // distinct elements read once / written once
+  const double V = (double)op->X * op->Yloc;
+  const double e = (double)elem_bytes(op->dtype);
+  switch (op->kind) {
+    case OPK_LAPLACE: return V * op->nc * 2 * e;
+    case OPK_LAPLACE_U1: return V * 64.0;
+    case OPK_STAGGERED: {
+      const double one = op->has_links ? 64.0 : 32.0;
+      return V * ((op->flags & GLB_STAG_NORMAL) ? 2 * one : one);
+    }
+    case OPK_GAMMA5: return V * 32.0;
+    case OPK_STENCIL: {
+      const double nc = op->nc;
+      return V * ((op->has_two ? 13.0 : 5.0) * nc * nc + 2 * nc) * 16.0;
+    }
+  }
+  return 0.0;
+}
+
+}  // extern "C"
+
+namespace glb {
+
+// one operator application with optional fused reductions; halo rows exchanged first on slabs
+static int apply_impl(glb_operator* op, void* out, const void* in, const ApplyFusion& f) {
+  glb_context* ctx = op->ctx;
+  const size_t row = (size_t)op->X * op->nc;
+  const int depth = (op->kind == OPK_STENCIL && op->has_two) ? 2 : 1;
+  if (out == in) return fail(GLB_ERR_ARG, "apply: output must not alias input");
+  switch (op->kind) {
+    case OPK_LAPLACE:
+      if (ctx->nranks > 1) {
+        int rc = halo_exchange(op, in, row, op->dtype);
+        if (rc) return rc;
+      }
+      return launch_laplace(op, out, in, f);
+    case OPK_GAMMA5:
+      if (f.w || f.w_is_input) return fail(GLB_ERR_ARG, "gamma5 has no fused reductions");
+      return launch_gamma5(op, out, in);
+    case OPK_STENCIL:
+      if (ctx->nranks > 1) {
+        int rc = halo_exchange(op, in, row * depth, op->dtype);
+        if (rc) return rc;
+      }
+      return launch_stencil2d(op, out, in, f);
+    case OPK_LAPLACE_U1:
+    case OPK_STAGGERED: {
+      if (op->flags & GLB_STAG_NORMAL) {  // operators.cpp:444-453 : tmp = D in ; out = D^dag tmp
+        ApplyFusion none;
+        if (ctx->nranks > 1) {
+          int rc = halo_exchange(op, in, row, op->dtype);
+          if (rc) return rc;
+        }
+        int rc = launch_staggered(op, op->tmp, in, false, none);
+        if (rc) return rc;
+        if (ctx->nranks > 1) {
+          rc = halo_exchange(op, op->tmp, row, op->dtype);
+          if (rc) return rc;
+        }
+        ApplyFusion g = f;
+        if (g.w_is_input) {  // the dot partner is the ORIGINAL input, not tmp
+          g.w_is_input = false;
+          g.w = in;
+        }
+        return launch_staggered(op, out, op->tmp, true, g);
+      }
+      if (ctx->nranks > 1) {
+        int rc = halo_exchange(op, in, row, op->dtype);
+        if (rc) return rc;
+      }
+      return launch_staggered(op, out, in, (op->flags & GLB_STAG_DAGGER) != 0, f);
+    }
+  }
+  return fail(GLB_ERR_ARG, "unknown operator kind");
+}
+
+int op_apply_fused(glb_operator* op, void* out, const void* in, const ApplyFusion& f) { return apply_impl(op, out, in, f); }
+
+}  // namespace glb
+
+extern "C" {
+
+int glb_op_apply(glb_operator* op, void* d_out, const void* d_in) {
+  ApplyFusion none;
+  return apply_impl(op, d_out, d_in, none);
+}
+
+int glb_op_apply_dot(glb_operator* op, void* d_out, const void* d_in, const void* d_w, int want_norm, double dots[3]) {
+  glb_context* ctx = op->ctx;
+  if (op->kind == OPK_GAMMA5) return fail(GLB_ERR_ARG, "gamma5 has no fused reductions");
+  ApplyFusion f;
+  f.w = d_w ? d_w : d_in;
+  f.w_is_input = (d_w == nullptr || d_w == d_in);
+  f.want_norm = want_norm != 0;
+  f.to_host = true;
+  int rc = apply_impl(op, d_out, d_in, f);
+  if (rc) return rc;
+  GLB_CUDA(cudaStreamSynchronize(ctx->stream));
+  const bool cx = (op->dtype == GLB_COMPLEX);
+  double tmp[3] = {0, 0, 0};
+  const int k = (cx ? 2 : 1) + (want_norm ? 1 : 0);
+  for (int i = 0; i < k; i++) tmp[i] = ctx->result_host_ptr[i];
+  if (ctx->nranks > 1) {
+    rc = allreduce_sum(ctx, tmp, k);
+    if (rc) return rc;
+  }
+  if (cx) {
+    dots[0] = tmp[0], dots[1] = tmp[1], dots[2] = want_norm ? tmp[2] : 0.0;
+  } else {
+    dots[0] = tmp[0], dots[1] = 0.0, dots[2] = want_norm ? tmp[1] : 0.0;
+  }
+  return GLB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,129 @@
+// runtime.hpp -- host-side state behind the opaque handles of include/glb200.h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/glb200.h"
+#include "common.cuh"
+
+namespace glb {
+
+// last error text (thread local; glb_last_error())
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+extern std::atomic<unsigned long long> g_launches;
+
+#define GLB_CUDA(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess)                                                                          \
+      return glb::fail(GLB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));           \
+  } while (0)
+
+#define GLB_LAUNCH_CHECK()                                                                          \
+  do {                                                                                              \
+    glb::g_launches.fetch_add(1, std::memory_order_relaxed);                                        \
+    cudaError_t _e = cudaGetLastError();                                                            \
+    if (_e != cudaSuccess) return glb::fail(GLB_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(_e)); \
+  } while (0)
+
+struct Comm;  // comm.cu
+
+}  // namespace glb
+
+struct glb_context {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  // reduction workspace
+  glb::ReduceWs red{};
+  double* result_host_ptr = nullptr;  // host address of the mapped result buffer
+  // small device scratch for pointer/coefficient tables of the multi-vector kernels
+  void* d_table = nullptr;
+  void* h_table = nullptr;  // pinned
+  size_t table_bytes = 0;
+  // slab communicator
+  int rank = 0, nranks = 1;
+  glb::Comm* comm = nullptr;
+};
+
+namespace glb {
+
+enum OpKind {
+  OPK_LAPLACE = 0,      // free Laplacian, Nc colours, real or complex
+  OPK_LAPLACE_U1 = 1,   // gauged Laplacian
+  OPK_STAGGERED = 2,    // staggered family (free or gauged; dagger / gamma5 / normal flags)
+  OPK_GAMMA5 = 3,
+  OPK_STENCIL = 4
+};
+
+}  // namespace glb
+
+struct glb_operator {
+  glb_context* ctx = nullptr;
+  int kind = 0;
+  int dtype = GLB_COMPLEX;
+  int X = 0, Y = 0;          // global lattice
+  int y0 = 0, Yloc = 0;      // this rank's slab: rows [y0, y0+Yloc)
+  int nc = 1;
+  double mass = 0.0;
+  double diag_re = 0.0, diag_im = 0.0;
+  unsigned flags = 0;
+  bool has_links = false;
+  // links as two site-major planes (SoA), slab-local, plus the U_y row below the slab
+  glb::cplx* Ux = nullptr;
+  glb::cplx* Uy = nullptr;     // Yloc rows
+  glb::cplx* Uy_lo = nullptr;  // row y0-1 (points into Uy when single rank)
+  // temporaries
+  void* tmp = nullptr;         // for the normal operator
+  // ghost rows for slab decomposition (rows y0-1 and y0+Yloc of the input), nc*X elements each
+  void* ghost_lo = nullptr;
+  void* ghost_hi = nullptr;
+  // stencil data (slab-local, device)
+  glb::cplx* clover = nullptr;
+  glb::cplx* hopping = nullptr;   // 4 planes of nc*nc*Vloc
+  glb::cplx* two_link = nullptr;  // 8 planes
+  bool has_two = false;
+  double shift[2] = {0, 0}, eo_shift[2] = {0, 0}, dof_shift[2] = {0, 0};
+  // launch geometry chosen at creation
+  int stencil_blocks = 0;
+};
+
+namespace glb {
+
+inline size_t elem_bytes(int dtype) { return dtype == GLB_COMPLEX ? 16 : 8; }
+
+// blas1.cu
+int blas_grid(const glb_context* ctx, size_t n, int threads, int per_thread);
+
+// stencil.cu : launchers.  `w` (optional) is dotted against the output, want_norm adds |out|^2.
+struct ApplyFusion {
+  // pre-op: in = r + beta * p_old, written to p_new (device-resident CG); beta read from device
+  const void* r = nullptr;
+  const void* p_old = nullptr;
+  void* p_new = nullptr;
+  const double* cg_state = nullptr;  // device CgState (see cg.cu), null if unused
+  // post-op reductions
+  const void* w = nullptr;   // <w, out>
+  bool w_is_input = false;   // w == the (possibly fused) input vector
+  bool want_norm = false;    // |out|^2
+  bool to_host = false;      // copy results to the mapped host buffer
+  int cg_role = 0;           // 0 none, 1: epilogue stores <p,Ap> into CgState
+};
+int launch_staggered(glb_operator* op, void* out, const void* in, bool dagger, const ApplyFusion& f);
+int launch_laplace(glb_operator* op, void* out, const void* in, const ApplyFusion& f);
+int launch_gamma5(glb_operator* op, void* out, const void* in);
+int launch_stencil2d(glb_operator* op, void* out, const void* in, const ApplyFusion& f);
+
+// comm.cu : fills op->ghost_lo / ghost_hi from the neighbouring ranks' boundary rows of `in`
+int halo_exchange(glb_operator* op, const void* in, size_t row_elems, int dtype);
+int allreduce_sum(glb_context* ctx, double* host_vals, int n);
+void comm_destroy(glb_context* ctx);
+
+}  // namespace glb

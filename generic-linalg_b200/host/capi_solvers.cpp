@@ -1,0 +1,281 @@
+// capi_solvers.cpp -- plain-C view of the C++ drop-in API, for harnesses that cannot speak C++
+// (tests/ and bench.py load it through ctypes).  Every function here only forwards to the public
+// C++ entry points of generic_inverters.h / glb200_device.h / operators.h -- the calls a C++ user
+// of the reference would make -- and flattens inversion_info into a POD.
+#include <cstring>
+
+#include "coarse_stencil.h"
+#include "dev_internal.hpp"
+#include "operators.h"
+#include "operators_stencil.h"
+
+typedef std::complex<double> zc;
+
+extern "C" {
+
+typedef struct glbx_result {
+  double resSq;
+  int iter;
+  int success;
+  int ops_count;
+  int n_rhs;
+  double resSqmrhs[32];
+  char name[64];
+} glbx_result;
+
+// operator selector (same numbering as oracle/oracle_api.h so the tests can share tables)
+enum {
+  GX_LAPLACE_REAL = 0, GX_LAPLACE_IMAG = 1, GX_LAPLACE_NC = 2, GX_LAPLACE_U1 = 3, GX_STAG_FREE = 4, GX_STAG_U1 = 5,
+  GX_STAG_GAMMA5_U1 = 6, GX_STAG_DAGGER_U1 = 7, GX_STAG_NORMAL_U1 = 8, GX_GAMMA5 = 9, GX_STENCIL = 10,
+  GX_STENCIL_FROM_STAG = 11, GX_STAG_GAMMA5_FREE = 12, GX_LAPLACE_REAL_NC = 13
+};
+enum {
+  GX_CG = 0, GX_CG_RESTART = 1, GX_CR = 2, GX_CR_RESTART = 3, GX_GCR = 4, GX_GCR_RESTART = 5, GX_BICGSTAB = 6,
+  GX_BICGSTAB_RESTART = 7, GX_BICGSTAB_L = 8, GX_BICGSTAB_L_RESTART = 9, GX_GMRES = 10, GX_GMRES_RESTART = 11
+};
+
+typedef struct glbx_opdesc {
+  int kind;
+  int X, Y, Nc;
+  double mass;
+  const void* links;
+  const void* clover;
+  const void* hopping;
+  const void* two_link;
+  int has_two;
+  double shift[2], eo_shift[2], dof_shift[2];
+} glbx_opdesc;
+
+}  // extern "C"
+
+namespace {
+
+void flatten(const inversion_info& inf, glbx_result* out) {
+  std::memset(out, 0, sizeof(*out));
+  out->resSq = inf.resSq;
+  out->iter = inf.iter;
+  out->success = inf.success ? 1 : 0;
+  out->ops_count = inf.ops_count;
+  out->n_rhs = inf.n_rhs;
+  if (inf.resSqmrhs && inf.n_rhs > 0)
+    for (int i = 0; i < inf.n_rhs && i < 32; i++) out->resSqmrhs[i] = inf.resSqmrhs[i];
+  std::strncpy(out->name, inf.name.c_str(), sizeof(out->name) - 1);
+}
+
+void make_verb(int level, inversion_verbose_struct* v) {
+  v->verbosity = (inversion_verbose_level)level;
+  v->verb_prefix = "[glb200] ";
+  v->precond_verbosity = VERB_NONE;
+  v->precond_verb_prefix = "";
+}
+
+// the reference-side objects a user would hold for each operator
+struct HostOp {
+  staggered_u1_op stag;
+  laplace_op lap;
+  Lattice* lat;
+  stencil_2d* st;
+  void (*cz)(zc*, zc*, void*);
+  void (*cd)(double*, double*, void*);
+  void* extra;
+  int size;
+  HostOp() : lat(0), st(0), cz(0), cd(0), extra(0), size(0) {}
+  ~HostOp() {
+    delete st;
+    delete lat;
+  }
+};
+
+bool build_host_op(const glbx_opdesc* d, HostOp* h) {
+  h->stag.lattice = (zc*)d->links;
+  h->stag.mass = d->mass;
+  h->stag.x_fine = d->X;
+  h->stag.y_fine = d->Y;
+  h->stag.Nc = d->Nc > 0 ? d->Nc : 1;
+  h->stag.wilson_coeff = 0.0;
+  h->lap.N = d->X;
+  h->lap.mass_sq = d->mass;
+  h->extra = &h->stag;
+  h->size = d->X * d->Y;
+  switch (d->kind) {
+    case GX_LAPLACE_REAL: h->cd = &square_laplacian; h->extra = &h->lap; break;
+    case GX_LAPLACE_IMAG: h->cz = &square_laplacian; h->extra = &h->lap; break;
+    case GX_LAPLACE_NC: h->cz = &square_laplace; h->size *= h->stag.Nc; break;
+    case GX_LAPLACE_REAL_NC: h->cd = &square_laplace; h->size *= h->stag.Nc; break;
+    case GX_LAPLACE_U1: h->cz = &square_laplace_u1; break;
+    case GX_STAG_FREE: h->cz = &square_staggered; break;
+    case GX_STAG_U1: h->cz = &square_staggered_u1; break;
+    case GX_STAG_GAMMA5_U1: h->cz = &square_staggered_gamma5_u1; break;
+    case GX_STAG_GAMMA5_FREE: h->cz = &square_staggered_gamma5; break;
+    case GX_STAG_DAGGER_U1: h->cz = &square_staggered_dagger_u1; break;
+    case GX_STAG_NORMAL_U1: h->cz = &square_staggered_normal_u1; break;
+    case GX_GAMMA5: h->cz = &gamma_5; break;
+    case GX_STENCIL:
+    case GX_STENCIL_FROM_STAG: {
+      int dims[2] = {d->X, d->Y};
+      const int nc = (d->kind == GX_STENCIL_FROM_STAG) ? 1 : h->stag.Nc;
+      h->lat = new Lattice(2, dims, nc);
+      if (d->kind == GX_STENCIL_FROM_STAG) {
+        h->st = new stencil_2d(h->lat, 1);
+        get_square_staggered_u1_stencil(h->st, &h->stag);
+      } else {
+        h->st = new stencil_2d(h->lat, d->has_two ? 2 : 1, zc(d->shift[0], d->shift[1]),
+                               zc(d->eo_shift[0], d->eo_shift[1]), zc(d->dof_shift[0], d->dof_shift[1]));
+        const size_t m = (size_t)d->X * d->Y * nc * nc;
+        std::memcpy((void*)h->st->clover, d->clover, m * sizeof(zc));
+        std::memcpy((void*)h->st->hopping, d->hopping, 4 * m * sizeof(zc));
+        if (d->has_two) std::memcpy((void*)h->st->two_link, d->two_link, 8 * m * sizeof(zc));
+        h->st->generated = true;
+      }
+      h->cz = &apply_stencil_2d;
+      h->extra = h->st;
+      h->size = d->X * d->Y * nc;
+      break;
+    }
+    default: return false;
+  }
+  return true;
+}
+
+template <typename T>
+inversion_info run_host(int solver, T* phi, T* b, int size, int max_iter, double eps, int rf, int l,
+                        void (*cb)(T*, T*, void*), void* extra, inversion_verbose_struct* v) {
+  switch (solver) {
+    case GX_CG: return minv_vector_cg(phi, b, size, max_iter, eps, cb, extra, v);
+    case GX_CG_RESTART: return minv_vector_cg_restart(phi, b, size, max_iter, eps, rf, cb, extra, v);
+    case GX_CR: return minv_vector_cr(phi, b, size, max_iter, eps, cb, extra, v);
+    case GX_CR_RESTART: return minv_vector_cr_restart(phi, b, size, max_iter, eps, rf, cb, extra, v);
+    case GX_GCR: return minv_vector_gcr(phi, b, size, max_iter, eps, cb, extra, v);
+    case GX_GCR_RESTART: return minv_vector_gcr_restart(phi, b, size, max_iter, eps, rf, cb, extra, v);
+    case GX_BICGSTAB: return minv_vector_bicgstab(phi, b, size, max_iter, eps, cb, extra, v);
+    case GX_BICGSTAB_RESTART: return minv_vector_bicgstab_restart(phi, b, size, max_iter, eps, rf, cb, extra, v);
+    case GX_BICGSTAB_L: return minv_vector_bicgstab_l(phi, b, size, max_iter, eps, l, cb, extra, v);
+    case GX_BICGSTAB_L_RESTART: return minv_vector_bicgstab_l_restart(phi, b, size, max_iter, eps, rf, l, cb, extra, v);
+    case GX_GMRES: return minv_vector_gmres(phi, b, size, max_iter, eps, cb, extra, v);
+    case GX_GMRES_RESTART: return minv_vector_gmres_restart(phi, b, size, max_iter, eps, rf, cb, extra, v);
+  }
+  return inversion_info();
+}
+
+template <typename T>
+inversion_info run_dev(int solver, T* phi, T* b, int size, int max_iter, double eps, int rf, int l, void* op,
+                       inversion_verbose_struct* v) {
+  void (*cb)(T*, T*, void*) = &glb200_apply_dev;
+  switch (solver) {
+    case GX_CG: return minv_vector_cg_dev(phi, b, size, max_iter, eps, cb, op, v);
+    case GX_CG_RESTART: return minv_vector_cg_restart_dev(phi, b, size, max_iter, eps, rf, cb, op, v);
+    case GX_CR: return minv_vector_cr_dev(phi, b, size, max_iter, eps, cb, op, v);
+    case GX_CR_RESTART: return minv_vector_cr_restart_dev(phi, b, size, max_iter, eps, rf, cb, op, v);
+    case GX_GCR: return minv_vector_gcr_dev(phi, b, size, max_iter, eps, cb, op, v);
+    case GX_GCR_RESTART: return minv_vector_gcr_restart_dev(phi, b, size, max_iter, eps, rf, cb, op, v);
+    case GX_BICGSTAB: return minv_vector_bicgstab_dev(phi, b, size, max_iter, eps, cb, op, v);
+    case GX_BICGSTAB_RESTART: return minv_vector_bicgstab_restart_dev(phi, b, size, max_iter, eps, rf, cb, op, v);
+    case GX_BICGSTAB_L: return minv_vector_bicgstab_l_dev(phi, b, size, max_iter, eps, l, cb, op, v);
+    case GX_BICGSTAB_L_RESTART: return minv_vector_bicgstab_l_restart_dev(phi, b, size, max_iter, eps, rf, l, cb, op, v);
+    case GX_GMRES: return minv_vector_gmres_dev(phi, b, size, max_iter, eps, cb, op, v);
+    case GX_GMRES_RESTART: return minv_vector_gmres_restart_dev(phi, b, size, max_iter, eps, rf, cb, op, v);
+  }
+  return inversion_info();
+}
+
+}  // namespace
+
+extern "C" {
+
+void glb200_cache_operators(int on);
+
+// the process-wide context of the C++ layer (so a harness can allocate device vectors on it)
+glb_context* glbx_default_context(void) {
+  try {
+    return glb200_default_context();
+  } catch (const std::exception& e) {
+    std::cerr << "[glb200] " << e.what() << std::endl;
+    return 0;
+  }
+}
+void glbx_set_default_context(glb_context* ctx) { glb200_set_default_context(ctx); }
+void glbx_force_host_scalars(int on) { glb200_force_host_scalars(on != 0); }
+void glbx_allow_host_callback_shim(int on) { glb200_allow_host_callback_shim(on != 0); }
+void glbx_cache_operators(int on) { glb200_cache_operators(on); }
+
+// lhs = A rhs through the reference-named host callback (upload, device apply, download)
+int glbx_host_apply(const glbx_opdesc* d, void* lhs, const void* rhs) {
+  HostOp h;
+  if (!build_host_op(d, &h)) return GLB_ERR_ARG;
+  if (h.cz)
+    h.cz((zc*)lhs, (zc*)rhs, h.extra);
+  else
+    h.cd((double*)lhs, (double*)rhs, h.extra);
+  return GLB_OK;
+}
+
+// the reference's call: solver(phi, phi0, size, ..., callback, extra_info, verbosity) on HOST vectors
+int glbx_host_solve(int solver, const glbx_opdesc* d, void* phi, const void* phi0, int max_iter, double eps,
+                    int restart_freq, int l, int verbosity, glbx_result* out) {
+  HostOp h;
+  if (!build_host_op(d, &h)) return GLB_ERR_ARG;
+  inversion_verbose_struct v;
+  make_verb(verbosity, &v);
+  inversion_info inf;
+  if (h.cz)
+    inf = run_host<zc>(solver, (zc*)phi, (zc*)phi0, h.size, max_iter, eps, restart_freq, l, h.cz, h.extra, &v);
+  else
+    inf = run_host<double>(solver, (double*)phi, (double*)phi0, h.size, max_iter, eps, restart_freq, l, h.cd, h.extra,
+                           &v);
+  flatten(inf, out);
+  return GLB_OK;
+}
+
+int glbx_host_solve_cg_m(const glbx_opdesc* d, void** phi, const void* phi0, int n_shift, int resid_freq_check,
+                         int max_iter, double eps, double* shifts, int worst_first, int verbosity, glbx_result* out) {
+  HostOp h;
+  if (!build_host_op(d, &h)) return GLB_ERR_ARG;
+  inversion_verbose_struct v;
+  make_verb(verbosity, &v);
+  if (h.cz) {
+    inversion_info inf = minv_vector_cg_m((zc**)phi, (zc*)phi0, n_shift, h.size, resid_freq_check, max_iter, eps,
+                                          shifts, h.cz, h.extra, worst_first != 0, &v);
+    flatten(inf, out);
+  } else {
+    inversion_info inf = minv_vector_cg_m((double**)phi, (double*)phi0, n_shift, h.size, resid_freq_check, max_iter,
+                                          eps, shifts, h.cd, h.extra, worst_first != 0, &v);
+    flatten(inf, out);
+  }
+  return GLB_OK;
+}
+
+// device vectors + a glb_operator handle (the device variant of the callback contract)
+int glbx_dev_solve(int solver, glb_operator* op, void* d_phi, void* d_phi0, int max_iter, double eps, int restart_freq,
+                   int l, int verbosity, glbx_result* out) {
+  inversion_verbose_struct v;
+  make_verb(verbosity, &v);
+  const int size = (int)glb_op_local_size(op);
+  inversion_info inf;
+  if (glb_op_dtype(op) == GLB_COMPLEX)
+    inf = run_dev<zc>(solver, (zc*)d_phi, (zc*)d_phi0, size, max_iter, eps, restart_freq, l, op, &v);
+  else
+    inf = run_dev<double>(solver, (double*)d_phi, (double*)d_phi0, size, max_iter, eps, restart_freq, l, op, &v);
+  flatten(inf, out);
+  return GLB_OK;
+}
+
+int glbx_dev_solve_cg_m(glb_operator* op, void** d_phi, void* d_phi0, int n_shift, int resid_freq_check, int max_iter,
+                        double eps, double* shifts, int worst_first, int verbosity, glbx_result* out) {
+  inversion_verbose_struct v;
+  make_verb(verbosity, &v);
+  const int size = (int)glb_op_local_size(op);
+  if (glb_op_dtype(op) == GLB_COMPLEX) {
+    void (*cb)(zc*, zc*, void*) = &glb200_apply_dev;
+    inversion_info inf = minv_vector_cg_m_dev((zc**)d_phi, (zc*)d_phi0, n_shift, size, resid_freq_check, max_iter, eps,
+                                              shifts, cb, (void*)op, worst_first != 0, &v);
+    flatten(inf, out);
+  } else {
+    void (*cb)(double*, double*, void*) = &glb200_apply_dev;
+    inversion_info inf = minv_vector_cg_m_dev((double**)d_phi, (double*)d_phi0, n_shift, size, resid_freq_check,
+                                              max_iter, eps, shifts, cb, (void*)op, worst_first != 0, &v);
+    flatten(inf, out);
+  }
+  return GLB_OK;
+}
+
+}  // extern "C"

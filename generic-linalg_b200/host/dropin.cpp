@@ -1,0 +1,475 @@
+// dropin.cpp -- the reference-facing entry points: solvers called with HOST vectors and the
+// reference's operator callbacks, and those callbacks themselves.
+//
+// A host-pointer solve = recognise the callback -> build (or reuse) the device operator ->
+// upload phi, phi0 -> run the device shell (dev_solvers.cpp) -> download phi.  The callbacks of
+// operators.h / coarse_stencil.h, when called directly, do upload -> device apply -> download.
+// There is no CPU compute path: an unrecognised callback is an error unless the explicit parity
+// shim (glb200_allow_host_callback_shim) is switched on.
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <sstream>
+
+#include "coarse_stencil.h"
+#include "dev_internal.hpp"
+#include "operators.h"
+#include "operators_stencil.h"
+
+using namespace glbx;
+
+namespace {
+
+glb_context* g_default_ctx = 0;
+bool g_allow_shim = false;
+bool g_cache_ops = false;
+
+enum Builtin {
+  B_NONE = 0, B_LAPLACE_NC, B_LAPLACE_NC_REAL, B_LAPLACE_U1, B_STAG_FREE, B_STAG_U1, B_GAMMA5, B_STAG_G5_FREE,
+  B_STAG_G5_U1, B_STAG_DAGGER_U1, B_STAG_NORMAL_U1, B_LAPLACIAN_REAL, B_LAPLACIAN_IMAG, B_STENCIL
+};
+
+Builtin classify(void (*fn)(zcplx*, zcplx*, void*)) {
+  typedef void (*F)(zcplx*, zcplx*, void*);
+  if (fn == (F)&square_laplace) return B_LAPLACE_NC;
+  if (fn == (F)&square_laplace_u1) return B_LAPLACE_U1;
+  if (fn == (F)&square_staggered) return B_STAG_FREE;
+  if (fn == (F)&square_staggered_u1) return B_STAG_U1;
+  if (fn == (F)&gamma_5) return B_GAMMA5;
+  if (fn == (F)&square_staggered_gamma5) return B_STAG_G5_FREE;
+  if (fn == (F)&square_staggered_gamma5_u1) return B_STAG_G5_U1;
+  if (fn == (F)&square_staggered_dagger_u1) return B_STAG_DAGGER_U1;
+  if (fn == (F)&square_staggered_normal_u1) return B_STAG_NORMAL_U1;
+  if (fn == (F)&square_laplacian) return B_LAPLACIAN_IMAG;
+  if (fn == (F)&apply_stencil_2d) return B_STENCIL;
+  return B_NONE;
+}
+Builtin classify(void (*fn)(double*, double*, void*)) {
+  typedef void (*F)(double*, double*, void*);
+  if (fn == (F)&square_laplace) return B_LAPLACE_NC_REAL;
+  if (fn == (F)&square_laplacian) return B_LAPLACIAN_REAL;
+  return B_NONE;
+}
+
+glb_operator* build(Builtin kind, void* extra) {
+  glb_context* ctx = glb200_default_context();
+  glb_operator* op = 0;
+  staggered_u1_op* s = (staggered_u1_op*)extra;
+  switch (kind) {
+    case B_LAPLACE_NC:  // operators.cpp:28 : diag (4+mass)
+      GLBX(glb_op_create_laplace(ctx, GLB_COMPLEX, s->x_fine, s->y_fine, s->Nc, 4 + s->mass, 0.0, &op));
+      break;
+    case B_LAPLACE_NC_REAL:
+      GLBX(glb_op_create_laplace(ctx, GLB_REAL, s->x_fine, s->y_fine, s->Nc, 4 + s->mass, 0.0, &op));
+      break;
+    case B_LAPLACE_U1: GLBX(glb_op_create_laplace_u1(ctx, s->lattice, s->x_fine, s->y_fine, s->mass, &op)); break;
+    case B_STAG_FREE: GLBX(glb_op_create_staggered(ctx, 0, s->x_fine, s->y_fine, s->mass, 0, &op)); break;
+    case B_STAG_U1: GLBX(glb_op_create_staggered(ctx, s->lattice, s->x_fine, s->y_fine, s->mass, 0, &op)); break;
+    case B_GAMMA5: GLBX(glb_op_create_gamma5(ctx, s->x_fine, s->y_fine, &op)); break;
+    case B_STAG_G5_FREE:
+      GLBX(glb_op_create_staggered(ctx, 0, s->x_fine, s->y_fine, s->mass, GLB_STAG_GAMMA5, &op));
+      break;
+    case B_STAG_G5_U1:
+      GLBX(glb_op_create_staggered(ctx, s->lattice, s->x_fine, s->y_fine, s->mass, GLB_STAG_GAMMA5, &op));
+      break;
+    case B_STAG_DAGGER_U1:
+      GLBX(glb_op_create_staggered(ctx, s->lattice, s->x_fine, s->y_fine, s->mass, GLB_STAG_DAGGER, &op));
+      break;
+    case B_STAG_NORMAL_U1:
+      GLBX(glb_op_create_staggered(ctx, s->lattice, s->x_fine, s->y_fine, s->mass, GLB_STAG_NORMAL, &op));
+      break;
+    case B_LAPLACIAN_REAL: {  // square_laplace.cpp:182 : (4+MASS)
+      laplace_op* l = (laplace_op*)extra;
+      GLBX(glb_op_create_laplace(ctx, GLB_REAL, l->N, l->N, 1, 4 + l->mass_sq, 0.0, &op));
+      break;
+    }
+    case B_LAPLACIAN_IMAG: {  // imag_laplace.cpp:126 : (4.0+MASS+i)
+      laplace_op* l = (laplace_op*)extra;
+      GLBX(glb_op_create_laplace(ctx, GLB_COMPLEX, l->N, l->N, 1, 4.0 + l->mass_sq, 1.0, &op));
+      break;
+    }
+    case B_STENCIL: {
+      stencil_2d* st = (stencil_2d*)extra;
+      if (st->sdir != DIR_ALL) throw Error("apply_stencil_2d: only sdir == DIR_ALL is on the accelerated path");
+      if (st->lat->get_nd() != 2) throw Error("apply_stencil_2d: 2-d lattices only");
+      const double sh[2] = {st->shift.real(), st->shift.imag()};
+      const double eo[2] = {st->eo_shift.real(), st->eo_shift.imag()};
+      const double df[2] = {st->dof_shift.real(), st->dof_shift.imag()};
+      GLBX(glb_op_create_stencil2d(ctx, st->clover, st->hopping, st->has_two ? st->two_link : 0,
+                                   st->lat->get_lattice_dimension(0), st->lat->get_lattice_dimension(1),
+                                   st->lat->get_nc(), sh, eo, df, &op));
+      break;
+    }
+    default: break;
+  }
+  return op;
+}
+
+// optional reuse of device operators between calls (off by default: the host arrays may change)
+struct CacheKey {
+  int kind;
+  const void* data;
+  int X, Y, Nc;
+  bool operator<(const CacheKey& o) const {
+    if (kind != o.kind) return kind < o.kind;
+    if (data != o.data) return data < o.data;
+    if (X != o.X) return X < o.X;
+    if (Y != o.Y) return Y < o.Y;
+    return Nc < o.Nc;
+  }
+};
+std::map<CacheKey, glb_operator*> g_cache;
+
+bool cacheable(Builtin k) { return k >= B_LAPLACE_NC && k <= B_STAG_NORMAL_U1; }
+
+struct OpLease {  // operator for the duration of one call
+  glb_operator* op;
+  bool owned;
+  OpLease() : op(0), owned(false) {}
+  ~OpLease() {
+    if (op && owned) glb_op_destroy(op);
+  }
+};
+
+void lease(Builtin kind, void* extra, OpLease* out) {
+  if (g_cache_ops && cacheable(kind)) {
+    staggered_u1_op* s = (staggered_u1_op*)extra;
+    CacheKey key = {(int)kind, (const void*)s->lattice, s->x_fine, s->y_fine, s->Nc};
+    std::map<CacheKey, glb_operator*>::iterator it = g_cache.find(key);
+    if (it == g_cache.end()) it = g_cache.insert(std::make_pair(key, build(kind, extra))).first;
+    glb_op_set_mass(it->second, s->mass);
+    if (kind == B_LAPLACE_NC || kind == B_LAPLACE_NC_REAL) {  // diag depends on the mass
+      glb_op_destroy(it->second);
+      it->second = build(kind, extra);
+    }
+    out->op = it->second;
+    out->owned = false;
+    return;
+  }
+  out->op = build(kind, extra);
+  out->owned = true;
+}
+
+// ---- parity shim for unknown host callbacks: download -> call -> upload
+template <typename T>
+struct Shim {
+  void (*fn)(T*, T*, void*);
+  void* extra;
+  size_t n;
+  std::vector<T> in, out;
+};
+template <typename T>
+void shim_cb(T* d_lhs, T* d_rhs, void* e) {
+  Shim<T>* s = (Shim<T>*)e;
+  glb_context* ctx = glb200_default_context();
+  GLBX(glb_vec_download(ctx, Traits<T>::dtype, s->n, s->in.data(), d_rhs));
+  s->fn(s->out.data(), s->in.data(), s->extra);
+  GLBX(glb_vec_upload(ctx, Traits<T>::dtype, s->n, d_lhs, s->out.data()));
+}
+
+// One host-pointer solve: resolve, upload, run `body(d_phi, d_b, cb, cb_extra)`, download.
+template <typename T, typename Body>
+inversion_info host_solve(const char* alg, T* phi, T* phi0, int size, void (*mv)(T*, T*, void*), void* extra,
+                          Body body) {
+  try {
+    glb_context* ctx = glb200_default_context();
+    const Builtin kind = classify(mv);
+    OpLease L;
+    Shim<T> shim;
+    void (*cb)(T*, T*, void*) = 0;
+    void* cb_extra = 0;
+    if (kind != B_NONE) {
+      lease(kind, extra, &L);
+      if (glb_comm_size(ctx) == 1 && (size_t)size != glb_op_local_size(L.op))
+        throw Error("`size` does not match the operator's lattice");
+      cb = &glb200_apply_dev;
+      cb_extra = L.op;
+    } else if (g_allow_shim) {
+      shim.fn = mv;
+      shim.extra = extra;
+      shim.n = size;
+      shim.in.resize(size);
+      shim.out.resize(size);
+      cb = &shim_cb<T>;
+      cb_extra = &shim;
+    } else {
+      throw Error("operator callback is not a known device operator (operators.h / coarse_stencil.h); "
+                  "this library has no CPU path -- see glb200_device.h");
+    }
+    Blas<T> B = {ctx, (size_t)size};
+    Work<T> W(B);
+    T* d_phi = W.get();
+    T* d_b = W.get();
+    GLBX(glb_vec_upload(ctx, Traits<T>::dtype, size, d_phi, phi));
+    GLBX(glb_vec_upload(ctx, Traits<T>::dtype, size, d_b, phi0));
+    inversion_info inf = body(d_phi, d_b, cb, cb_extra);
+    GLBX(glb_vec_download(ctx, Traits<T>::dtype, size, phi, d_phi));
+    return inf;
+  } catch (const std::exception& e) {
+    std::cerr << "[glb200] " << alg << " aborted: " << e.what() << std::endl;
+    inversion_info inf;
+    inf.name = alg;
+    return inf;
+  }
+}
+
+template <typename T>
+void direct_apply(Builtin kind, T* lhs, T* rhs, void* extra) {
+  try {
+    glb_context* ctx = glb200_default_context();
+    OpLease L;
+    lease(kind, extra, &L);
+    const size_t n = glb_op_local_size(L.op);
+    Blas<T> B = {ctx, n};
+    Work<T> W(B);
+    T* d_in = W.get();
+    T* d_out = W.get();
+    GLBX(glb_vec_upload(ctx, Traits<T>::dtype, n, d_in, rhs));
+    GLBX(glb_op_apply(L.op, d_out, d_in));
+    GLBX(glb_vec_download(ctx, Traits<T>::dtype, n, lhs, d_out));
+  } catch (const std::exception& e) {
+    std::cerr << "[glb200] operator apply failed: " << e.what() << std::endl;
+    std::abort();  // the callback contract has no error channel
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------ context
+glb_context* glb200_default_context() {
+  if (!g_default_ctx) {
+    int dev = 0;
+    if (const char* e = std::getenv("GLB200_DEVICE"))
+      dev = std::atoi(e);
+    else if (const char* e2 = std::getenv("LOCAL_RANK"))
+      dev = std::atoi(e2);
+    glb_context* ctx = 0;
+    if (glb_create(dev, &ctx) != GLB_OK) throw Error(std::string("cannot create device context: ") + glb_last_error());
+    g_default_ctx = ctx;
+  }
+  return g_default_ctx;
+}
+void glb200_set_default_context(glb_context* ctx) { g_default_ctx = ctx; }
+void glb200_allow_host_callback_shim(bool allow) { g_allow_shim = allow; }
+extern "C" void glb200_cache_operators(int on) {
+  g_cache_ops = on != 0;
+  if (!on) {
+    for (std::map<CacheKey, glb_operator*>::iterator it = g_cache.begin(); it != g_cache.end(); ++it)
+      glb_op_destroy(it->second);
+    g_cache.clear();
+  }
+}
+
+void glb200_apply_dev(double* d_lhs, double* d_rhs, void* h) { GLBX(glb_op_apply((glb_operator*)h, d_lhs, d_rhs)); }
+void glb200_apply_dev(zcplx* d_lhs, zcplx* d_rhs, void* h) { GLBX(glb_op_apply((glb_operator*)h, d_lhs, d_rhs)); }
+
+glb_operator* glb200_operator_from_callback(void (*mv)(double*, double*, void*), void* extra) {
+  const Builtin k = classify(mv);
+  return k == B_NONE ? 0 : build(k, extra);
+}
+glb_operator* glb200_operator_from_callback(void (*mv)(zcplx*, zcplx*, void*), void* extra) {
+  const Builtin k = classify(mv);
+  return k == B_NONE ? 0 : build(k, extra);
+}
+
+// ------------------------------------------------------------------------------------------ operator callbacks
+int get_stencil_size(op_type opt) {  // operators.cpp:9-25
+  switch (opt) {
+    case STAGGERED:
+    case LAPLACE:
+    case LAPLACE_NC2:
+    case G5_STAGGERED: return 1;
+    case STAGGERED_INDEX:
+    case STAGGERED_NORMAL: return 2;
+  }
+  return 0;
+}
+void square_laplace(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_LAPLACE_NC, lhs, rhs, e); }
+void square_laplace(double* lhs, double* rhs, void* e) { direct_apply<double>(B_LAPLACE_NC_REAL, lhs, rhs, e); }
+void square_laplace_u1(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_LAPLACE_U1, lhs, rhs, e); }
+void square_staggered(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_STAG_FREE, lhs, rhs, e); }
+void square_staggered_u1(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_STAG_U1, lhs, rhs, e); }
+void gamma_5(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_GAMMA5, lhs, rhs, e); }
+void square_staggered_gamma5(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_STAG_G5_FREE, lhs, rhs, e); }
+void square_staggered_gamma5_u1(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_STAG_G5_U1, lhs, rhs, e); }
+void square_staggered_dagger_u1(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_STAG_DAGGER_U1, lhs, rhs, e); }
+void square_staggered_normal_u1(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_STAG_NORMAL_U1, lhs, rhs, e); }
+void square_laplacian(double* lhs, double* rhs, void* e) { direct_apply<double>(B_LAPLACIAN_REAL, lhs, rhs, e); }
+void square_laplacian(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_LAPLACIAN_IMAG, lhs, rhs, e); }
+void apply_stencil_2d(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_STENCIL, lhs, rhs, e); }
+
+// operators_stencil.cpp:14-63 / :65-118 / :120-170 : hopping[+x] = -U_x/2, [+y] = -eta U_y/2,
+// [-x] = +conj U_x(x-1)/2, [-y] = +eta conj U_y(y-1)/2 ; gamma5 variant carries the site parity
+// sign and moves the mass to eo_shift; dagger variant flips the hopping sign.
+static void fill_stag_stencil(stencil_2d* st, staggered_u1_op* s, double hop, bool g5) {
+  if (st->generated || st->lat->get_nc() != 1) return;
+  const int X = st->lat->get_lattice_dimension(0), Y = st->lat->get_lattice_dimension(1);
+  const int V = X * Y;
+  for (int i = 0; i < V; i++) {
+    const int x = i % X, y = i / X;
+    const int eta1 = 1 - 2 * (x % 2);
+    const int eo = g5 ? (((x + y) % 2 == 0) ? 1 : -1) : 1;
+    const int xm = (x - 1 + X) % X, ym = (y - 1 + Y) % Y;
+    if (g5) {
+      st->hopping[i] = -0.5 * eo * s->lattice[2 * i];
+      st->hopping[i + V] = -0.5 * eo * eta1 * s->lattice[2 * i + 1];
+      st->hopping[i + 2 * V] = 0.5 * eo * conj(s->lattice[2 * (y * X + xm)]);
+      st->hopping[i + 3 * V] = 0.5 * eo * eta1 * conj(s->lattice[2 * (ym * X + x) + 1]);
+    } else {
+      st->hopping[i] = (hop * -0.5) * s->lattice[2 * i];
+      st->hopping[i + V] = (hop * -0.5) * eta1 * s->lattice[2 * i + 1];
+      st->hopping[i + 2 * V] = (hop * 0.5) * conj(s->lattice[2 * (y * X + xm)]);
+      st->hopping[i + 3 * V] = (hop * 0.5) * eta1 * conj(s->lattice[2 * (ym * X + x) + 1]);
+    }
+  }
+  st->shift = g5 ? 0.0 : s->mass;
+  st->eo_shift = g5 ? s->mass : 0.0;
+  st->dof_shift = 0.0;
+  st->generated = true;
+}
+void get_square_staggered_u1_stencil(stencil_2d* st, staggered_u1_op* s) { fill_stag_stencil(st, s, 1.0, false); }
+void get_square_staggered_gamma5_u1_stencil(stencil_2d* st, staggered_u1_op* s) { fill_stag_stencil(st, s, 1.0, true); }
+void get_square_staggered_dagger_u1_stencil(stencil_2d* st, staggered_u1_op* s) { fill_stag_stencil(st, s, -1.0, false); }
+
+// ------------------------------------------------------------------------------------------ solvers, host vectors
+#define GLB200_HOST_BASIC(NAME, DEVNAME, ALG)                                                                      \
+  inversion_info NAME(double* phi, double* phi0, int size, int max_iter, double res,                               \
+                      void (*mv)(double*, double*, void*), void* extra, inversion_verbose_struct* verb) {          \
+    return host_solve<double>(ALG, phi, phi0, size, mv, extra,                                                     \
+                              [&](double* dp, double* db, void (*cb)(double*, double*, void*), void* ce) {         \
+                                return DEVNAME(dp, db, size, max_iter, res, cb, ce, verb);                         \
+                              });                                                                                  \
+  }                                                                                                                \
+  inversion_info NAME(zcplx* phi, zcplx* phi0, int size, int max_iter, double res, void (*mv)(zcplx*, zcplx*, void*), \
+                      void* extra, inversion_verbose_struct* verb) {                                               \
+    return host_solve<zcplx>(ALG, phi, phi0, size, mv, extra,                                                      \
+                             [&](zcplx* dp, zcplx* db, void (*cb)(zcplx*, zcplx*, void*), void* ce) {              \
+                               return DEVNAME(dp, db, size, max_iter, res, cb, ce, verb);                          \
+                             });                                                                                   \
+  }
+#define GLB200_HOST_RESTART(NAME, DEVNAME, ALG)                                                                    \
+  inversion_info NAME(double* phi, double* phi0, int size, int max_iter, double res, int rf,                       \
+                      void (*mv)(double*, double*, void*), void* extra, inversion_verbose_struct* verb) {          \
+    return host_solve<double>(ALG, phi, phi0, size, mv, extra,                                                     \
+                              [&](double* dp, double* db, void (*cb)(double*, double*, void*), void* ce) {         \
+                                return DEVNAME(dp, db, size, max_iter, res, rf, cb, ce, verb);                     \
+                              });                                                                                  \
+  }                                                                                                                \
+  inversion_info NAME(zcplx* phi, zcplx* phi0, int size, int max_iter, double res, int rf,                         \
+                      void (*mv)(zcplx*, zcplx*, void*), void* extra, inversion_verbose_struct* verb) {            \
+    return host_solve<zcplx>(ALG, phi, phi0, size, mv, extra,                                                      \
+                             [&](zcplx* dp, zcplx* db, void (*cb)(zcplx*, zcplx*, void*), void* ce) {              \
+                               return DEVNAME(dp, db, size, max_iter, res, rf, cb, ce, verb);                      \
+                             });                                                                                   \
+  }
+
+GLB200_HOST_BASIC(minv_vector_cg, minv_vector_cg_dev, "CG")
+GLB200_HOST_RESTART(minv_vector_cg_restart, minv_vector_cg_restart_dev, "CG")
+GLB200_HOST_BASIC(minv_vector_cr, minv_vector_cr_dev, "CR")
+GLB200_HOST_RESTART(minv_vector_cr_restart, minv_vector_cr_restart_dev, "CR")
+GLB200_HOST_BASIC(minv_vector_gcr, minv_vector_gcr_dev, "GCR")
+GLB200_HOST_RESTART(minv_vector_gcr_restart, minv_vector_gcr_restart_dev, "GCR")
+GLB200_HOST_BASIC(minv_vector_bicgstab, minv_vector_bicgstab_dev, "BiCGStab")
+GLB200_HOST_RESTART(minv_vector_bicgstab_restart, minv_vector_bicgstab_restart_dev, "BiCGStab")
+GLB200_HOST_BASIC(minv_vector_gmres, minv_vector_gmres_dev, "GMRES")
+GLB200_HOST_RESTART(minv_vector_gmres_restart, minv_vector_gmres_restart_dev, "GMRES")
+
+#define GLB200_HOST_BICGL(T)                                                                                       \
+  inversion_info minv_vector_bicgstab_l(T* phi, T* phi0, int size, int max_iter, double res, int l,                \
+                                        void (*mv)(T*, T*, void*), void* extra, inversion_verbose_struct* verb) {  \
+    return host_solve<T>("BiCGStab-l", phi, phi0, size, mv, extra,                                                 \
+                         [&](T* dp, T* db, void (*cb)(T*, T*, void*), void* ce) {                                  \
+                           return minv_vector_bicgstab_l_dev(dp, db, size, max_iter, res, l, cb, ce, verb);        \
+                         });                                                                                       \
+  }                                                                                                                \
+  inversion_info minv_vector_bicgstab_l_restart(T* phi, T* phi0, int size, int max_iter, double res, int rf, int l, \
+                                                void (*mv)(T*, T*, void*), void* extra,                            \
+                                                inversion_verbose_struct* verb) {                                  \
+    return host_solve<T>("BiCGStab-l", phi, phi0, size, mv, extra,                                                 \
+                         [&](T* dp, T* db, void (*cb)(T*, T*, void*), void* ce) {                                  \
+                           return minv_vector_bicgstab_l_restart_dev(dp, db, size, max_iter, res, rf, l, cb, ce,   \
+                                                                     verb);                                        \
+                         });                                                                                       \
+  }
+GLB200_HOST_BICGL(double)
+GLB200_HOST_BICGL(zcplx)
+
+// multishift: phi[] are n_shift host vectors; the device copies are permuted by the solver exactly
+// like the reference permutes the caller's pointers, and restored before download.
+template <typename T>
+static inversion_info cg_m_host(T** phi, T* phi0, int n_shift, int size, int rfc, int max_iter, double eps,
+                                double* shifts, void (*mv)(T*, T*, void*), void* extra, bool worst_first,
+                                inversion_verbose_struct* verb) {
+  try {
+    glb_context* ctx = glb200_default_context();
+    const Builtin kind = classify(mv);
+    if (kind == B_NONE) throw Error("operator callback is not a known device operator");
+    OpLease L;
+    lease(kind, extra, &L);
+    Blas<T> B = {ctx, (size_t)size};
+    Work<T> W(B);
+    T* d_b = W.get();
+    std::vector<T*> d_phi(n_shift);
+    for (int s = 0; s < n_shift; s++) d_phi[s] = W.get();
+    GLBX(glb_vec_upload(ctx, Traits<T>::dtype, size, d_b, phi0));
+    void (*cb)(T*, T*, void*) = &glb200_apply_dev;
+    inversion_info inf = minv_vector_cg_m_dev(d_phi.data(), d_b, n_shift, size, rfc, max_iter, eps, shifts, cb,
+                                              (void*)L.op, worst_first, verb);
+    for (int s = 0; s < n_shift; s++) GLBX(glb_vec_download(ctx, Traits<T>::dtype, size, phi[s], d_phi[s]));
+    return inf;
+  } catch (const std::exception& e) {
+    std::cerr << "[glb200] CG-M aborted: " << e.what() << std::endl;
+    inversion_info inf;
+    inf.name = "CG-M";
+    return inf;
+  }
+}
+inversion_info minv_vector_cg_m(double** phi, double* phi0, int n_shift, int size, int rfc, int max_iter, double eps,
+                                double* shifts, void (*mv)(double*, double*, void*), void* extra, bool worst_first,
+                                inversion_verbose_struct* verb) {
+  return cg_m_host<double>(phi, phi0, n_shift, size, rfc, max_iter, eps, shifts, mv, extra, worst_first, verb);
+}
+inversion_info minv_vector_cg_m(zcplx** phi, zcplx* phi0, int n_shift, int size, int rfc, int max_iter, double eps,
+                                double* shifts, void (*mv)(zcplx*, zcplx*, void*), void* extra, bool worst_first,
+                                inversion_verbose_struct* verb) {
+  return cg_m_host<zcplx>(phi, phi0, n_shift, size, rfc, max_iter, eps, shifts, mv, extra, worst_first, verb);
+}
+
+// generic_inverter.cpp:18-190 : enum dispatch
+template <typename T>
+static inversion_info dispatch(T* lhs, T* rhs, int size, minv_inverter type, minv_inverter_params& p,
+                               void (*mv)(T*, T*, void*), void* extra, inversion_verbose_struct* verb) {
+  switch (type) {
+    case MINV_CG:
+      return p.restart ? minv_vector_cg_restart(lhs, rhs, size, p.max_iters, p.tol, p.restart_freq, mv, extra, verb)
+                       : minv_vector_cg(lhs, rhs, size, p.max_iters, p.tol, mv, extra, verb);
+    case MINV_CR:
+      return p.restart ? minv_vector_cr_restart(lhs, rhs, size, p.max_iters, p.tol, p.restart_freq, mv, extra, verb)
+                       : minv_vector_cr(lhs, rhs, size, p.max_iters, p.tol, mv, extra, verb);
+    case MINV_GCR:
+      return p.restart ? minv_vector_gcr_restart(lhs, rhs, size, p.max_iters, p.tol, p.restart_freq, mv, extra, verb)
+                       : minv_vector_gcr(lhs, rhs, size, p.max_iters, p.tol, mv, extra, verb);
+    case MINV_BICGSTAB:
+      return p.restart
+                 ? minv_vector_bicgstab_restart(lhs, rhs, size, p.max_iters, p.tol, p.restart_freq, mv, extra, verb)
+                 : minv_vector_bicgstab(lhs, rhs, size, p.max_iters, p.tol, mv, extra, verb);
+    case MINV_BICGSTAB_L:
+      return p.restart ? minv_vector_bicgstab_l_restart(lhs, rhs, size, p.max_iters, p.tol, p.restart_freq,
+                                                        p.bicgstabl_l, mv, extra, verb)
+                       : minv_vector_bicgstab_l(lhs, rhs, size, p.max_iters, p.tol, p.bicgstabl_l, mv, extra, verb);
+    case MINV_GMRES:
+      return p.restart ? minv_vector_gmres_restart(lhs, rhs, size, p.max_iters, p.tol, p.restart_freq, mv, extra, verb)
+                       : minv_vector_gmres(lhs, rhs, size, p.max_iters, p.tol, mv, extra, verb);
+    default:  // SOR / MinRes are outside the accelerated path
+      return inversion_info();
+  }
+}
+inversion_info minv_unpreconditioned(double* lhs, double* rhs, int size, minv_inverter type, minv_inverter_params& p,
+                                     void (*mv)(double*, double*, void*), void* extra,
+                                     inversion_verbose_struct* verb) {
+  return dispatch<double>(lhs, rhs, size, type, p, mv, extra, verb);
+}
+inversion_info minv_unpreconditioned(zcplx* lhs, zcplx* rhs, int size, minv_inverter type, minv_inverter_params& p,
+                                     void (*mv)(zcplx*, zcplx*, void*), void* extra, inversion_verbose_struct* verb) {
+  return dispatch<zcplx>(lhs, rhs, size, type, p, mv, extra, verb);
+}

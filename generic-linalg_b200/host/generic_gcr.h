@@ -1,0 +1,6 @@
+// generic_gcr.h -- kept so that `#include "generic_gcr.h"` in code written against the reference still
+// compiles; every prototype lives in generic_inverters.h.
+#ifndef GLB200_FWD_generic_gcr_H
+#define GLB200_FWD_generic_gcr_H
+#include "generic_inverters.h"
+#endif

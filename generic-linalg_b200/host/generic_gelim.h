@@ -1,0 +1,6 @@
+// generic_gelim.h -- kept so that `#include "generic_gelim.h"` in code written against the reference still
+// compiles; every prototype lives in generic_inverters.h.
+#ifndef GLB200_FWD_generic_gelim_H
+#define GLB200_FWD_generic_gelim_H
+#include "generic_inverters.h"
+#endif

@@ -1,0 +1,61 @@
+// operators.h -- the reference's operator callbacks (operator_utils/operators.h:7-100 and the
+// in-file Laplacians of its examples), same names and signatures, executed on the GPU.
+//
+// Passed to a solver of generic_inverters.h they select the matching device kernel; called
+// directly with host pointers they upload rhs, apply on the device and download lhs.
+#ifndef GLB200_OPERATORS_H
+#define GLB200_OPERATORS_H
+
+#include <complex>
+using namespace std;
+
+// operator_utils/operators.h:7-15
+struct staggered_u1_op {
+  complex<double>* lattice;  // U(1) links, lattice[y*x_fine*2 + x*2 + mu], mu = 0:x, 1:y
+  double mass;
+  int x_fine;
+  int y_fine;
+  int Nc;               // only relevant for square_laplace
+  double wilson_coeff;  // unused on this path
+};
+
+// operator_utils/operators.h:17-25
+enum op_type {
+  STAGGERED = 0,
+  LAPLACE = 1,
+  LAPLACE_NC2 = 2,
+  G5_STAGGERED = 3,
+  STAGGERED_NORMAL = 4,
+  STAGGERED_INDEX = 5,
+};
+int get_stencil_size(op_type opt);  // operators.cpp:9-25
+
+// operators.cpp:28   free Laplacian with Nc colours, diag 4+mass          extra: staggered_u1_op*
+void square_laplace(complex<double>* lhs, complex<double>* rhs, void* extra_data);
+// tests/multishift/multishift.cpp:634   real twin of the above            extra: staggered_u1_op*
+void square_laplace(double* lhs, double* rhs, void* extra_data);
+// operators.cpp:73   gauged Laplacian
+void square_laplace_u1(complex<double>* lhs, complex<double>* rhs, void* extra_data);
+// operators.cpp:127 / :184   staggered D, free and gauged
+void square_staggered(complex<double>* lhs, complex<double>* rhs, void* extra_data);
+void square_staggered_u1(complex<double>* lhs, complex<double>* rhs, void* extra_data);
+// operators.cpp:242   gamma_5 = (-1)^(x+y)
+void gamma_5(complex<double>* lhs, complex<double>* rhs, void* extra_data);
+// operators.cpp:262 / :316   gamma_5 D
+void square_staggered_gamma5(complex<double>* lhs, complex<double>* rhs, void* extra_data);
+void square_staggered_gamma5_u1(complex<double>* lhs, complex<double>* rhs, void* extra_data);
+// operators.cpp:372   D^dagger
+void square_staggered_dagger_u1(complex<double>* lhs, complex<double>* rhs, void* extra_data);
+// operators.cpp:444   D^dagger D
+void square_staggered_normal_u1(complex<double>* lhs, complex<double>* rhs, void* extra_data);
+
+// The examples' in-file Laplacians (square_laplace.cpp:182, unit_test.cpp:573, imag_laplace.cpp:126)
+// take their size from `#define N` / `#define MASS`; here the same numbers travel in extra_data.
+struct laplace_op {
+  int N;          // N x N lattice
+  double mass_sq; // MASS of the examples (diag = 4 + MASS, or 4 + MASS + i for the complex one)
+};
+void square_laplacian(double* lhs, double* rhs, void* extra_data);                    // extra: laplace_op*
+void square_laplacian(complex<double>* lhs, complex<double>* rhs, void* extra_data);  // extra: laplace_op*
+
+#endif

@@ -1,0 +1,209 @@
+/* glb200.h -- C ABI of the B200-native solver hot path of generic-linalg.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ and no torch
+ * types.  It sits one level BELOW the reference's public C++ API
+ * (generic_inverters.h / inverter_struct.h, which return a std::string-bearing
+ * struct by value and therefore cannot be a C ABI): the retained C++ solver
+ * shells in generic-linalg_b200/host/ call ONLY the functions declared here.
+ *
+ * What each group replaces in the reference (paths relative to its root):
+ *   vectors      : the `new T[size]` / `delete[]` work vectors of every solver
+ *                  (e.g. generic_cg.cpp:292-294,370-372) -> device-resident.
+ *   operators    : the `void (*matrix_vector)(T* lhs, T* rhs, void* extra_info)`
+ *                  callbacks  square_laplacian (square_laplace.cpp:182,
+ *                  imag_laplace.cpp:126), square_laplace (operators.cpp:28),
+ *                  square_laplace_u1 (:73), square_staggered(_u1) (:127,:184),
+ *                  gamma5 / dagger / normal variants (:242,:262,:316,:372,:444),
+ *                  apply_stencil_2d (stencil_2d/coarse_stencil.cpp:12).
+ *   BLAS-1       : generic_vector.h:12-169 (zero, copy, dot, norm2sq,
+ *                  diffnorm2sq) and the open-coded axpy loops of each solver.
+ *   fused        : one-pass versions of the loop bodies generic_cg.cpp:326-351,
+ *                  generic_cr.cpp:249-285, generic_bicgstab.cpp:261-303,
+ *                  generic_gcr.cpp:284-292, generic_cg_m.cpp:414-518.
+ *   cg pipeline  : the whole CG loop generic_cg.cpp:324-354 run without any
+ *                  host round trip (scalars and the stopping test on device).
+ *
+ * Conventions
+ *   - every function returns GLB_OK (0) or a non-zero error code; the text of
+ *     the last error is available from glb_last_error().  There is no CPU
+ *     fallback anywhere: without a CUDA device glb_create() fails.
+ *   - `dtype` is GLB_REAL (double) or GLB_COMPLEX (interleaved re,im doubles,
+ *     layout-compatible with std::complex<double>).
+ *   - vector lengths `n` are in ELEMENTS of that dtype (the reference's `size`).
+ *   - device pointers are plain `void*` obtained from glb_vec_alloc.
+ *   - complex scalars cross the boundary as `const double a[2]` = {re, im};
+ *     for GLB_REAL only a[0] is used.
+ *   - all work is enqueued on the context's stream; functions that return a
+ *     scalar to the host synchronise that stream, the others do not.
+ *   - dot products conjugate their FIRST argument (generic_vector.h:102).
+ *   - element-wise updates evaluate exactly the reference's expression (same
+ *     operation order, no fused multiply-add), so given equal scalars they are
+ *     bit-identical to the CPU code; reductions use a fixed tree and are
+ *     run-to-run reproducible.
+ */
+#ifndef GLB200_H
+#define GLB200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLB_OK 0
+#define GLB_ERR_CUDA 1
+#define GLB_ERR_ARG 2
+#define GLB_ERR_COMM 3
+#define GLB_ERR_STATE 4
+
+enum glb_dtype { GLB_REAL = 0, GLB_COMPLEX = 1 };
+
+typedef struct glb_context glb_context;
+typedef struct glb_operator glb_operator;
+
+/* ------------------------------------------------------------------ lifecycle */
+int glb_create(int device, glb_context** ctx);
+int glb_destroy(glb_context* ctx);
+const char* glb_last_error(void);
+int glb_synchronize(glb_context* ctx);
+void* glb_stream(glb_context* ctx);          /* the cudaStream_t all work is enqueued on   */
+int glb_device(glb_context* ctx);
+int glb_sm_count(glb_context* ctx);
+/* number of kernels this library has launched so far in this process (bench.py: gpu_launches) */
+unsigned long long glb_kernel_launches(void);
+
+/* ------------------------------------------------------ slab communicator (y-slabs) */
+/* One process per GPU.  Rank g of G owns rows [g*Y/G, (g+1)*Y/G) of every lattice
+ * vector.  Bootstrapping (exchange of the 128-byte id and of the IPC handles) is done
+ * by the host program (torch.distributed in bench.py/tests; any launcher will do).   */
+#define GLB_COMM_ID_BYTES 128
+#define GLB_IPC_HANDLE_BYTES 64
+int glb_comm_unique_id(char id[GLB_COMM_ID_BYTES]);
+int glb_comm_init(glb_context* ctx, int rank, int nranks, const char id[GLB_COMM_ID_BYTES]);
+int glb_comm_rank(glb_context* ctx);
+int glb_comm_size(glb_context* ctx);
+/* Optional NVLink peer-memory fast path for halos and reductions.  Each rank exports one
+ * handle for its mailbox; all_handles is the rank-ordered concatenation of every rank's. */
+int glb_comm_export_mailbox(glb_context* ctx, char handle[GLB_IPC_HANDLE_BYTES]);
+int glb_comm_attach_mailboxes(glb_context* ctx, const char* all_handles);
+int glb_comm_barrier(glb_context* ctx);
+
+/* ---------------------------------------------------------------------- vectors */
+int glb_vec_alloc(glb_context* ctx, int dtype, size_t n, void** dptr);
+int glb_vec_free(glb_context* ctx, void* dptr);
+int glb_vec_upload(glb_context* ctx, int dtype, size_t n, void* dst_dev, const void* src_host);
+int glb_vec_download(glb_context* ctx, int dtype, size_t n, void* dst_host, const void* src_dev);
+int glb_vec_zero(glb_context* ctx, int dtype, size_t n, void* d);
+int glb_vec_copy(glb_context* ctx, int dtype, size_t n, void* dst, const void* src);
+/* pinned host staging buffers (used by the drop-in shells for host<->device copies) */
+int glb_host_alloc(glb_context* ctx, size_t bytes, void** hptr);
+int glb_host_free(glb_context* ctx, void* hptr);
+
+/* -------------------------------------------------------------------- operators */
+/* flags for glb_op_create_staggered */
+#define GLB_STAG_DAGGER 1u   /* D^dagger : operators.cpp:372                                   */
+#define GLB_STAG_GAMMA5 2u   /* gamma5 D : operators.cpp:262,316                               */
+#define GLB_STAG_NORMAL 4u   /* D^dagger D through a temporary : operators.cpp:444             */
+
+/* 5-point periodic Laplacian, Nc colours per site, out = diag*in - sum of 4 neighbours.
+ * diag = 4+m2 (square_laplace.cpp:182; operators.cpp:28), or 4+m2+i (imag_laplace.cpp:126).
+ * The operator acts on the GLOBAL X x Y lattice; with a communicator each rank holds its slab. */
+int glb_op_create_laplace(glb_context* ctx, int dtype, int X, int Y, int Nc, double diag_re, double diag_im,
+                          glb_operator** op);
+/* gauged Laplacian, operators.cpp:73.  h_links: host array in the reference layout
+ * lattice[y*X*2 + x*2 + mu] (complex), GLOBAL lattice; each rank uploads only its slab. */
+int glb_op_create_laplace_u1(glb_context* ctx, const void* h_links, int X, int Y, double mass, glb_operator** op);
+/* 2-D staggered operator; h_links == NULL gives the free operator (operators.cpp:127,262). */
+int glb_op_create_staggered(glb_context* ctx, const void* h_links, int X, int Y, double mass, unsigned flags,
+                            glb_operator** op);
+/* gamma_5 alone: out = (-1)^(x+y) in  (operators.cpp:242) */
+int glb_op_create_gamma5(glb_context* ctx, int X, int Y, glb_operator** op);
+/* data-driven stencil, stencil_2d/coarse_stencil.h:33 + coarse_stencil.cpp:29-172 (DIR_ALL).
+ * clover: nc*nc*V, hopping: 4 planes, two_link: 8 planes or NULL; host arrays, reference layout. */
+int glb_op_create_stencil2d(glb_context* ctx, const void* clover, const void* hopping, const void* two_link, int X,
+                            int Y, int nc, const double shift[2], const double eo_shift[2],
+                            const double dof_shift[2], glb_operator** op);
+int glb_op_destroy(glb_operator* op);
+int glb_op_set_mass(glb_operator* op, double mass);
+int glb_op_dtype(const glb_operator* op);
+size_t glb_op_local_size(const glb_operator* op);   /* elements held by this rank              */
+size_t glb_op_global_size(const glb_operator* op);
+glb_context* glb_op_context(const glb_operator* op);
+/* how many operator applications one glb_op_apply counts for (1; the reference counts the
+ * normal operator as one callback too) -- kept for ops_count parity */
+/* out = A in.  out is fully overwritten and must not alias in (same contract as the callback). */
+int glb_op_apply(glb_operator* op, void* d_out, const void* d_in);
+/* out = A in, and in the same pass  dots[0..1] = <w,out> (w may be d_in or any vector; NULL skips),
+ * dots[2] = |out|^2 if want_norm.  Host-synchronous. */
+int glb_op_apply_dot(glb_operator* op, void* d_out, const void* d_in, const void* d_w, int want_norm,
+                     double dots[3]);
+/* algorithmic HBM bytes one apply moves (SURVEY section 8 d-bytes); used by bench.py */
+double glb_op_bytes_per_apply(const glb_operator* op);
+
+/* ----------------------------------------------------------------------- BLAS-1 */
+int glb_dot(glb_context* ctx, int dtype, size_t n, const void* x, const void* y, double out[2]);
+int glb_norm2sq(glb_context* ctx, int dtype, size_t n, const void* x, double* out);
+int glb_diffnorm2sq(glb_context* ctx, int dtype, size_t n, const void* x, const void* y, double* out);
+/* out[0..1] = <x,y>, out[2] = |x|^2 in one pass (GCR alpha, generic_gcr.cpp:255) */
+int glb_dot_norm(glb_context* ctx, int dtype, size_t n, const void* x, const void* y, double out[3]);
+/* out[2i..2i+1] = <X[i], y>, i < k, one pass over y (GCR / Gram-Schmidt sweeps) */
+int glb_multi_dot(glb_context* ctx, int dtype, size_t n, int k, const void* const* X, const void* y, double* out);
+
+int glb_sub(glb_context* ctx, int dtype, size_t n, const void* a, const void* b, void* out);        /* out = a - b   */
+int glb_add(glb_context* ctx, int dtype, size_t n, const void* a, const void* b, void* out);        /* out = a + b   */
+int glb_axpy(glb_context* ctx, int dtype, size_t n, const double a[2], const void* x, void* y);     /* y = y + a*x   */
+int glb_xpay(glb_context* ctx, int dtype, size_t n, const void* x, const double a[2], void* y);     /* y = x + a*y   */
+int glb_axpyz(glb_context* ctx, int dtype, size_t n, const double a[2], const void* x, const void* y,
+              void* z);                                                                              /* z = y + a*x   */
+int glb_rdiv(glb_context* ctx, int dtype, size_t n, const void* x, double d, void* out);            /* out = x / d   */
+/* y = y + a*x and |y|^2 in the same pass (generic_cg_m.cpp:423-429) */
+int glb_axpy_norm(glb_context* ctx, int dtype, size_t n, const double a[2], const void* x, void* y, double* nrm);
+/* out = (init ? init : 0) + c[0]*X[0] + c[1]*X[1] + ... accumulated in that order
+ * (generic_gcr.cpp:284-292 with init==out; generic_gmres.cpp:632-648) */
+int glb_lincomb(glb_context* ctx, int dtype, size_t n, int k, const double* coef, const void* const* X,
+                const void* init, void* out);
+
+/* ------------------------------------------------------- fused solver loop bodies */
+/* x = x + a*p ; r = r + b*q ; *rsq = |r|^2   (generic_cg.cpp:328-335 with b = -a, q = Ap) */
+int glb_update_xr_norm(glb_context* ctx, int dtype, size_t n, const double a[2], const void* p, void* x,
+                       const double b[2], const void* q, void* r, double* rsq);
+/* p = r + beta*p ; Ap = Ar + beta*Ap ; *apsq = |Ap|^2   (generic_cr.cpp:279-285) */
+int glb_update_p_ap_norm(glb_context* ctx, int dtype, size_t n, const void* r, const void* Ar, const double beta[2],
+                         void* p, void* Ap, double* apsq);
+/* x = x + alpha*p + omega*s ; r = s - omega*As ; out = {|r|^2, <r0,r>.re, <r0,r>.im}
+ * (generic_bicgstab.cpp:274-295) */
+int glb_bicgstab_update(glb_context* ctx, int dtype, size_t n, const double alpha[2], const void* p,
+                        const double omega[2], const void* s, const void* As, const void* r0, void* x, void* r,
+                        double out[3]);
+/* p = r + beta*(p - omega*Ap)   (generic_bicgstab.cpp:300-303) */
+int glb_bicgstab_pupdate(glb_context* ctx, int dtype, size_t n, const void* r, const double beta[2],
+                         const double omega[2], const void* Ap, void* p);
+/* multishift: for s < ns : x[s] = x[s] - beta_s[s]*p_s[s]   (generic_cg_m.cpp:414-417) */
+int glb_cgm_update_x(glb_context* ctx, int dtype, size_t n, int ns, const double* beta_s, const void* const* p_s,
+                     void* const* x);
+/* multishift: for s < ns : p_s[s] = zeta[s]*r + alpha_s[s]*p_s[s]  (generic_cg_m.cpp:501-512), r read once */
+int glb_cgm_update_p(glb_context* ctx, int dtype, size_t n, int ns, const double* zeta, const double* alpha_s,
+                     const void* r, void* const* p_s);
+
+/* ----------------------------------------------- device-resident CG (no host round trip) */
+/* Runs the loop of minv_vector_cg (generic_cg.cpp:159-206 / :307-354) entirely on the device:
+ * alpha, beta and the stopping test `sqrt(rsqNew) < eps*bnorm || k == max_iter-1` are
+ * evaluated by the kernels themselves; the host only enqueues batches and polls a flag.
+ * Fusion (bytes/site, complex):  [p = r + beta p . Ap = A p . <p,Ap>] + [x,r update . |r|^2].
+ * x is in/out (initial guess), b the rhs.  On return iters/ops follow the reference's counting
+ * (generic_cg.cpp:362,366) EXCLUDING the final true-residual apply, which the shell performs.
+ * rsq_hist (host, may be NULL) receives |r|^2 after each iteration, hist_cap entries at most. */
+typedef struct glb_cg_report {
+  int iterations;      /* value of k+1 at loop exit (what the reference reports as `iter`) */
+  int ops;             /* operator applications performed (initial two + one per continued iteration) */
+  int hit_max_iter;    /* loop ended because k == max_iter-1 */
+  double rsq;          /* last recurrence |r|^2 */
+  double bnorm;        /* sqrt(|b|^2) */
+} glb_cg_report;
+int glb_cg_solve(glb_operator* op, void* d_x, const void* d_b, int max_iter, double eps, glb_cg_report* rep,
+                 double* rsq_hist, int hist_cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLB200_H */

@@ -1,0 +1,89 @@
+"""No-GPU checks of the drop-in boundary: the native libraries exist in-tree, load, export every
+symbol include/glb200.h declares, and refuse to run without a device (no silent CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import ROOT, load_pkg
+
+PKG = os.path.join(ROOT, "generic-linalg_b200")
+
+
+def _built():
+    return os.path.exists(os.path.join(PKG, "libglb200.so")) and os.path.exists(
+        os.path.join(PKG, "libglb200_inverters.so"))
+
+
+needs_build = pytest.mark.skipif(not _built(), reason="native libraries not built (run __graft_entry__.build())")
+
+
+@needs_build
+def test_every_declared_symbol_is_exported():
+    glb = load_pkg()
+    lib = C.CDLL(os.path.join(PKG, "libglb200.so"))
+    names = glb.exported_symbols()
+    assert len(names) > 50
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+@needs_build
+def test_dropin_cxx_symbols_present():
+    """the reference's C++ entry points exist with the reference's (mangled) signatures"""
+    out = subprocess.check_output(["nm", "-DC", os.path.join(PKG, "libglb200_inverters.so")]).decode()
+    for sym in ["minv_vector_cg(std::complex<double>*, std::complex<double>*, int, int, double, "
+                "void (*)(std::complex<double>*, std::complex<double>*, void*), void*, inversion_verbose_struct*)",
+                "minv_vector_cg(double*, double*, int, int, double, void (*)(double*, double*, void*), void*, "
+                "inversion_verbose_struct*)",
+                "minv_vector_bicgstab_l(std::complex<double>*, std::complex<double>*, int, int, double, int,",
+                "minv_vector_gmres_restart(std::complex<double>*, std::complex<double>*, int, int, double, int,",
+                "minv_vector_cg_m(std::complex<double>**, std::complex<double>*, int, int, int, int, double, double*,",
+                "minv_unpreconditioned(std::complex<double>*, std::complex<double>*, int, minv_inverter, "
+                "minv_inverter_params&",
+                "square_staggered_u1(std::complex<double>*, std::complex<double>*, void*)",
+                "square_staggered_normal_u1(std::complex<double>*, std::complex<double>*, void*)",
+                "apply_stencil_2d(std::complex<double>*, std::complex<double>*, void*)",
+                "gaussian_elimination(std::complex<double>*, std::complex<double>*, std::complex<double>**, int)"]:
+        assert sym in out, sym
+
+
+@needs_build
+def test_no_oracle_in_product():
+    """the product libraries must not link or reference anything under oracle/"""
+    for lib in ("libglb200.so", "libglb200_inverters.so"):
+        ldd = subprocess.check_output(["ldd", os.path.join(PKG, lib)]).decode()
+        assert "oracle" not in ldd
+    for dirpath, _, files in os.walk(PKG):
+        if "build" in dirpath:
+            continue
+        for f in files:
+            if f.endswith((".cu", ".cuh", ".cpp", ".hpp", ".h", ".py")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"#include\s+[\"<].*oracle", txt), f
+                assert "oracle_py" not in txt and "libport_oracle" not in txt and "libref_oracle" not in txt, f
+
+
+@needs_build
+def test_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    glb = load_pkg()
+    cu, _ = glb.libs()
+    h = C.c_void_p()
+    rc = cu.glb_create(0, C.byref(h))
+    assert rc != 0
+    assert b"no CUDA device" in cu.glb_last_error() or b"CPU fallback" in cu.glb_last_error()
+    with pytest.raises(glb.GlbError):
+        glb.Context()
+
+
+def test_missing_library_is_an_error(tmp_path, monkeypatch):
+    glb = load_pkg()
+    monkeypatch.setattr(glb, "_libs", None)
+    monkeypatch.setattr(glb, "LIB_CUDA", str(tmp_path / "nope.so"))
+    with pytest.raises(glb.GlbError):
+        glb.libs()
