@@ -87,6 +87,8 @@ def libs():
         "glb_op_create_laplace": (ci, [vp, ci, ci, ci, ci, cd, cd, C.POINTER(vp)]),
         "glb_op_create_laplace_u1": (ci, [vp, vp, ci, ci, cd, C.POINTER(vp)]),
         "glb_op_create_staggered": (ci, [vp, vp, ci, ci, cd, C.c_uint, C.POINTER(vp)]),
+        "glb_op_create_staggered_local": (ci, [vp, vp, ci, ci, cd, C.c_uint, C.POINTER(vp)]),
+        "glb_slab_bounds": (ci, [vp, ci, C.POINTER(ci), C.POINTER(ci)]),
         "glb_op_create_gamma5": (ci, [vp, ci, ci, C.POINTER(vp)]),
         "glb_op_create_stencil2d": (ci, [vp, vp, vp, vp, ci, ci, ci, pd, pd, pd, C.POINTER(vp)]),
         "glb_op_destroy": (ci, [vp]), "glb_op_set_mass": (ci, [vp, cd]), "glb_op_dtype": (ci, [vp]),
@@ -322,6 +324,16 @@ class Context:
         if links is not None:
             links = np.ascontiguousarray(links, dtype=np.complex128)
         return self._op(self.cu.glb_op_create_staggered, _p(links), X, Y, mass, flags)
+
+    def staggered_local(self, links_local, X, Y, mass, flags=0):
+        """links_local: rows y0-1 .. y0+Yloc-1 of the gauge field (this rank's slab + the row below)"""
+        links_local = np.ascontiguousarray(links_local, dtype=np.complex128)
+        return self._op(self.cu.glb_op_create_staggered_local, _p(links_local), X, Y, mass, flags)
+
+    def slab_bounds(self, Y):
+        y0, yl = C.c_int(), C.c_int()
+        _chk(self.cu.glb_slab_bounds(self.h, Y, C.byref(y0), C.byref(yl)), "glb_slab_bounds")
+        return y0.value, yl.value
 
     def gamma5(self, X, Y):
         return self._op(self.cu.glb_op_create_gamma5, X, Y)

@@ -45,7 +45,7 @@ static int alloc_ghosts(glb_operator* op, int depth) {
   return GLB_OK;
 }
 
-static int upload_links(glb_operator* op, const void* h_links) {
+static int upload_links(glb_operator* op, const void* h_links, bool local = false) {
   glb_context* ctx = op->ctx;
   const size_t X = op->X, Vloc = X * op->Yloc;
   const cplx* h = (const cplx*)h_links;
@@ -58,15 +58,16 @@ static int upload_links(glb_operator* op, const void* h_links) {
   GLB_CUDA(cudaMalloc(&uy_store, sizeof(cplx) * (Vloc + (single ? 0 : X))));
   op->Uy = single ? uy_store : uy_store + X;
   op->Uy_lo = single ? op->Uy + (size_t)(op->Yloc - 1) * X : uy_store;
-  GLB_CUDA(cudaMemcpyAsync(aos, h + 2 * (size_t)op->y0 * X, sizeof(cplx) * 2 * Vloc, cudaMemcpyHostToDevice,
-                           ctx->stream));
+  // global array: this rank's rows start at y0; local array: row 0 is y0-1, the slab follows
+  const cplx* slab = local ? h + 2 * X : h + 2 * (size_t)op->y0 * X;
+  GLB_CUDA(cudaMemcpyAsync(aos, slab, sizeof(cplx) * 2 * Vloc, cudaMemcpyHostToDevice, ctx->stream));
   const int grid = blas_grid(ctx, Vloc, 256, 4);
   split_links_kernel<<<grid, 256, 0, ctx->stream>>>(aos, op->Ux, op->Uy, Vloc);
   GLB_LAUNCH_CHECK();
   if (!single) {  // U_y of global row y0-1 (periodic)
     const int ym = (op->y0 + op->Y - 1) % op->Y;
     std::vector<cplx> row(X);
-    for (size_t x = 0; x < X; x++) row[x] = h[2 * ((size_t)ym * X + x) + 1];
+    for (size_t x = 0; x < X; x++) row[x] = local ? h[2 * x + 1] : h[2 * ((size_t)ym * X + x) + 1];
     GLB_CUDA(cudaMemcpyAsync(uy_store, row.data(), sizeof(cplx) * X, cudaMemcpyHostToDevice, ctx->stream));
     GLB_CUDA(cudaStreamSynchronize(ctx->stream));
   }
@@ -121,6 +122,22 @@ int glb_op_create_staggered(glb_context* ctx, const void* h_links, int X, int Y,
   return alloc_ghosts(op, 1);
 }
 
+int glb_op_create_staggered_local(glb_context* ctx, const void* h_links_local, int X, int Y, double mass,
+                                    unsigned flags, glb_operator** out) {
+  if (!h_links_local) return fail(GLB_ERR_ARG, "glb_op_create_staggered_local needs links");
+  if ((flags & GLB_STAG_NORMAL) && (flags & (GLB_STAG_DAGGER | GLB_STAG_GAMMA5)))
+    return fail(GLB_ERR_ARG, "NORMAL cannot be combined with DAGGER/GAMMA5");
+  int rc = new_op(ctx, OPK_STAGGERED, GLB_COMPLEX, X, Y, 1, out);
+  if (rc) return rc;
+  glb_operator* op = *out;
+  op->mass = mass;
+  op->flags = flags;
+  rc = upload_links(op, h_links_local, true);
+  if (rc) return rc;
+  if (flags & GLB_STAG_NORMAL) GLB_CUDA(cudaMalloc(&op->tmp, sizeof(cplx) * (size_t)X * op->Yloc));
+  return alloc_ghosts(op, 1);
+}
+
 int glb_op_create_gamma5(glb_context* ctx, int X, int Y, glb_operator** out) {
   return new_op(ctx, OPK_GAMMA5, GLB_COMPLEX, X, Y, 1, out);
 }
@@ -156,6 +173,12 @@ int glb_op_create_stencil2d(glb_context* ctx, const void* clover, const void* ho
   }
   GLB_CUDA(cudaStreamSynchronize(ctx->stream));
   return alloc_ghosts(op, op->has_two ? 2 : 1);
+}
+
+int glb_slab_bounds(glb_context* ctx, int Y, int* y0, int* Yloc) {
+  if (!ctx || !y0 || !Yloc) return fail(GLB_ERR_ARG, "glb_slab_bounds: null argument");
+  slab_of(ctx, Y, y0, Yloc);
+  return GLB_OK;
 }
 
 int glb_op_destroy(glb_operator* op) {

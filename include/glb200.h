@@ -116,6 +116,13 @@ int glb_op_create_laplace_u1(glb_context* ctx, const void* h_links, int X, int Y
 /* 2-D staggered operator; h_links == NULL gives the free operator (operators.cpp:127,262). */
 int glb_op_create_staggered(glb_context* ctx, const void* h_links, int X, int Y, double mass, unsigned flags,
                             glb_operator** op);
+/* Same, but the host array holds only THIS RANK's rows preceded by the row below the slab:
+ * rows y0-1, y0, ..., y0+Yloc-1 (periodic), i.e. (Yloc+1)*X*2 complex numbers.  Lets a multi-GPU
+ * job build its slabs without any rank ever holding the global gauge field. */
+int glb_op_create_staggered_local(glb_context* ctx, const void* h_links_local, int X, int Y, double mass,
+                                  unsigned flags, glb_operator** op);
+/* rows [y0, y0+Yloc) this rank owns of a Y-row lattice */
+int glb_slab_bounds(glb_context* ctx, int Y, int* y0, int* Yloc);
 /* gamma_5 alone: out = (-1)^(x+y) in  (operators.cpp:242) */
 int glb_op_create_gamma5(glb_context* ctx, int X, int Y, glb_operator** op);
 /* data-driven stencil, stencil_2d/coarse_stencil.h:33 + coarse_stencil.cpp:29-172 (DIR_ALL).

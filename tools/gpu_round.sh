@@ -1,0 +1,28 @@
+#!/bin/bash
+# One GPU-box session: parity tests, smoke, bench, ncu launch list + full capture of the top kernel.
+# Usage (from the repo root on the GPU box):  bash tools/gpu_round.sh [tag]
+TAG=${1:-r01}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/gpu.csv 2>&1
+echo "== smoke" | tee $OUT/summary.txt
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke rc=$?" | tee -a $OUT/summary.txt
+tail -2 $OUT/smoke.log | tee -a $OUT/summary.txt
+echo "== pytest -m gpu" | tee -a $OUT/summary.txt
+timeout 1200 python -m pytest tests -m gpu -q -x --timeout 600 > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/summary.txt
+tail -25 $OUT/pytest_gpu.log | tee -a $OUT/summary.txt
+echo "== bench (default)" | tee -a $OUT/summary.txt
+timeout 900 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?" | tee -a $OUT/summary.txt
+cat $OUT/bench.json | tee -a $OUT/summary.txt; tail -5 $OUT/bench.err | tee -a $OUT/summary.txt
+echo "== bench sizes" | tee -a $OUT/summary.txt
+for L in 256 1024 2048; do
+  timeout 600 python bench.py --L $L --no-cpu >> $OUT/bench_sizes.json 2>> $OUT/bench.err
+done
+cat $OUT/bench_sizes.json | tee -a $OUT/summary.txt
+echo "== ncu launch list" | tee -a $OUT/summary.txt
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/launches.csv \
+   python bench.py --steps 1 --warmup 3 --no-cpu --apply-reps 5 > $OUT/ncu_bench.log 2>&1; echo "ncu list rc=$?" | tee -a $OUT/summary.txt
+echo "== ncu full (stag_kernel, cg_update)" | tee -a $OUT/summary.txt
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"stag_kernel|cg_update_kernel" -s 30 -c 6 \
+   -o $OUT/prof_top python bench.py --steps 1 --warmup 3 --no-cpu --apply-reps 5 > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?" | tee -a $OUT/summary.txt
+ls -la $OUT | tee -a $OUT/summary.txt
