@@ -132,6 +132,14 @@ def libs():
     return _libs
 
 
+def slab_bounds(Y, rank, nranks):
+    """rows [y0, y0+Yloc) of a Y-row lattice owned by `rank` -- the same arithmetic as slab_of() in
+    csrc/ops.cu (pure host logic, testable without a GPU)."""
+    y0 = (Y * rank) // nranks
+    y1 = (Y * (rank + 1)) // nranks
+    return y0, y1 - y0
+
+
 def exported_symbols():
     """Names declared in include/glb200.h (used by the CPU test that checks the ABI surface)."""
     import re
@@ -147,7 +155,7 @@ def _chk(rc, what=""):
 
 
 def _dt(arr_or_dtype):
-    d = arr_or_dtype.dtype if hasattr(arr_or_dtype, "dtype") else np.dtype(arr_or_dtype)
+    d = np.dtype(arr_or_dtype) if isinstance(arr_or_dtype, (type, np.dtype, str)) else arr_or_dtype.dtype
     if d == np.complex128:
         return COMPLEX
     if d == np.float64:

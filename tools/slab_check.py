@@ -1,0 +1,127 @@
+#!/usr/bin/env python
+"""Multi-GPU parity check of the y-slab path (run under torchrun, one rank per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tools/slab_check.py [L]
+
+Every rank holds the same seeded global field on the host (small L), builds its slab operator through
+the C ABI, and the slab results gathered on rank 0 are compared with the CPU oracle: applies bit for
+bit, solves by iteration count (+-2 %) and true residual.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import oracle_py
+    from __graft_entry__ import _load_pkg
+    glb = _load_pkg()
+    L = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = glb.Context(device=local)
+    ctx.init_comm_from_torch()
+    orc = oracle_py.load("best")
+    X, Y = L, L
+    r = orc.rng(1337)
+    U = r.gauss_gauge_u1(X, Y, 6.0)
+    b = r.gaussian(X * Y)
+    y0, Yloc = ctx.slab_bounds(Y)
+    sl = slice(y0 * X, (y0 + Yloc) * X)
+    fails = []
+
+    def gather(local_arr):
+        t = torch.from_numpy(np.ascontiguousarray(local_arr).view(np.float64)).cuda()
+        sizes = [0] * world
+        allsz = [None] * world
+        dist.all_gather_object(allsz, t.numel())
+        outs = [torch.empty(n, dtype=torch.float64, device="cuda") for n in allsz]
+        dist.all_gather(outs, t) if len(set(allsz)) == 1 else [dist.broadcast(outs[i] if i != rank else t, i) for i in range(world)]
+        if len(set(allsz)) != 1:
+            outs[rank] = t
+        return np.concatenate([o.cpu().numpy() for o in outs]).view(np.complex128)
+
+    def check(name, cond, extra=""):
+        if rank == 0:
+            print("%-48s %s %s" % (name, "ok" if cond else "FAIL", extra), flush=True)
+        if not cond:
+            fails.append(name)
+
+    # ---- applies: slab result == global oracle rows, bit for bit
+    for kind, flags in [("STAG_U1", 0), ("STAG_DAGGER_U1", 1), ("STAG_GAMMA5_U1", 2), ("STAG_NORMAL_U1", 4)]:
+        op = ctx.staggered(U, X, Y, 0.1, flags)          # global host array; each rank uploads its slab
+        got = gather(op.apply_host(b[sl]))
+        want = orc.op(kind, X, Y, mass=0.1, links=U).apply(b)
+        check("apply %s" % kind, np.array_equal(got, want), "max diff %.1e" % np.abs(got - want).max())
+    rows = [(y0 - 1 + Y) % Y] + list(range(y0, y0 + Yloc))
+    Uloc = U.reshape(Y, 2 * X)[rows].reshape(-1)
+    got = gather(ctx.staggered_local(Uloc, X, Y, 0.1, 0).apply_host(b[sl]))
+    check("apply STAG_U1 (slab-local links)", np.array_equal(got, orc.op("STAG_U1", X, Y, mass=0.1, links=U).apply(b)))
+    got = gather(ctx.laplace_u1(U, X, Y, 0.3).apply_host(b[sl]))
+    check("apply LAPLACE_U1", np.array_equal(got, orc.op("LAPLACE_U1", X, Y, mass=0.3, links=U).apply(b)))
+    got = gather(ctx.laplace(X, Y, 1, 4.01 + 1j, np.complex128).apply_host(b[sl]))
+    check("apply LAPLACE_IMAG", np.array_equal(got, orc.op("LAPLACE_IMAG", X, Y, mass=0.01).apply(b)))
+    nc = 4
+    rg = np.random.default_rng(3)
+    rc = lambda n: rg.standard_normal(n) + 1j * rg.standard_normal(n)
+    V = X * Y
+    cl, hp, tl, v = rc(V * nc * nc), rc(4 * V * nc * nc), rc(8 * V * nc * nc), rc(V * nc)
+    for two in (None, tl):
+        got = gather(ctx.stencil2d(cl, hp, two, X, Y, nc, shift=0.3, eo_shift=0.2j, dof_shift=0.1).apply_host(
+            v[y0 * X * nc:(y0 + Yloc) * X * nc]))
+        want = orc.op("STENCIL", X, Y, Nc=nc, clover=cl, hopping=hp, two_link=two, shift=0.3, eo_shift=0.2j,
+                      dof_shift=0.1).apply(v)
+        check("apply STENCIL nc=4 two_link=%s" % (two is not None), np.array_equal(got, want))
+
+    # ---- reductions
+    xv = ctx.vector(Yloc * X).upload(b[sl])
+    d = ctx.dot(xv, xv)
+    check("dot over slabs", abs(d - np.vdot(b, b)) <= 1e-12 * abs(np.vdot(b, b)))
+
+    # ---- solves
+    oD = orc.op("STAG_U1", X, Y, mass=0.1, links=U)
+    oN = orc.op("STAG_NORMAL_U1", X, Y, mass=0.1, links=U)
+    bprime = orc.op("STAG_DAGGER_U1", X, Y, mass=0.1, links=U).apply(b)
+    D = ctx.staggered(U, X, Y, 0.1, 0)
+    N = ctx.staggered(U, X, Y, 0.1, glb.STAG_NORMAL)
+    for name, solver, op, oop, rhs, kw in [
+            ("CGNE", "CG", N, oN, bprime, dict(eps=1e-10)), ("CR", "CR", N, oN, bprime, dict(eps=1e-10)),
+            ("BiCGStab", "BICGSTAB", D, oD, b, dict(eps=1e-10)), ("BiCGStab-4", "BICGSTAB_L", D, oD, b, dict(eps=1e-10, l=4)),
+            ("GCR(20)", "GCR_RESTART", D, oD, b, dict(eps=1e-8, restart_freq=20)),
+            ("GMRES(20)", "GMRES_RESTART", D, oD, b, dict(eps=1e-8, restart_freq=20))]:
+        _, want = orc.solve(solver, oop, rhs, max_iter=100000, **kw)
+        x = ctx.vector(Yloc * X).zero()
+        bd = ctx.vector(Yloc * X).upload(rhs[sl])
+        info = ctx.solve(solver, op, x, bd, max_iter=100000, **kw)
+        xg = gather(x.download())
+        rr = np.linalg.norm(oop.apply(xg) - rhs) / np.linalg.norm(rhs)
+        ok = abs(info["iter"] - want["iter"]) <= max(1, round(0.02 * want["iter"])) and rr < kw["eps"] * 1.000001
+        check("solve %s" % name, ok, "iter %d (oracle %d) true rel res %.2e" % (info["iter"], want["iter"], rr))
+    shifts = [0.0, 0.01, 0.05, 0.25]
+    xs = [ctx.vector(Yloc * X) for _ in shifts]
+    info, _ = ctx.solve_cg_m(N, xs, ctx.vector(Yloc * X).upload(bprime[sl]), shifts, max_iter=100000, eps=1e-10)
+    _, want, _ = orc.solve_cg_m(oN, bprime, shifts, max_iter=100000, eps=1e-10)
+    worst = 0.0
+    for s, xd in zip(shifts, xs):
+        xg = gather(xd.download())
+        worst = max(worst, np.linalg.norm(oN.apply(xg) + s * xg - bprime) / np.linalg.norm(bprime))
+    check("solve CG-M", abs(info["iter"] - want["iter"]) <= max(1, round(0.02 * want["iter"])) and worst < 1e-10 * 1.000001,
+          "iter %d (oracle %d) worst rel res %.2e" % (info["iter"], want["iter"], worst))
+    dist.barrier()
+    if rank == 0:
+        print("SLAB CHECK %s (%d ranks, %dx%d)" % ("PASSED" if not fails else "FAILED: %s" % fails, world, X, Y), flush=True)
+    dist.destroy_process_group()
+    sys.exit(1 if fails else 0)
+
+
+if __name__ == "__main__":
+    main()
