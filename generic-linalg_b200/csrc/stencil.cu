@@ -22,6 +22,8 @@
 //     in the epilogue with warp shuffles (generic_cg.cpp:326) -- no extra pass over HBM.
 //   * arithmetic follows the reference's expression order without FMA contraction: the result is
 //     bit-identical to the CPU code.
+#include <cstdlib>
+
 #include "cg_state.cuh"
 #include "runtime.hpp"
 
@@ -66,7 +68,7 @@ struct RowLoad {  // everything fetched one row ahead
   cplx uy[SPT];   // U_y(y)
 };
 
-template <int SPT, bool HAS_U, bool FUSE_XPAY, int NDOT, int FAM>
+template <int SPT, bool HAS_U, bool FUSE_XPAY, int NDOT, int FAM, int PF>
 __global__ void __launch_bounds__(STAG_THREADS) stag_kernel(const StagArgs a) {
   double beta = 0.0;
   if (a.cg != nullptr) {
@@ -143,14 +145,13 @@ __global__ void __launch_bounds__(STAG_THREADS) stag_kernel(const StagArgs a) {
         ldv_nc<SPT>(a.Uy + (size_t)y * X + x0, L.uy);
       }
     };
-    RowLoad<SPT> nxt;
-    fetch(ya, nxt);
+    // PF rows of loads are kept in flight per thread (PF = 1: next row only)
+    RowLoad<SPT> st[PF];
+#pragma unroll
+    for (int k = 0; k < PF; k++)
+      if (ya + k < yb) fetch(ya + k, st[k]);
 
-#pragma unroll 1
-    for (int y = ya; y < yb; y++) {
-      RowLoad<SPT> cur = nxt;
-      if (y + 1 < yb) fetch(y + 1, nxt);  // prefetch while this row is computed
-
+    auto row_body = [&](const int y, const RowLoad<SPT>& cur) {
       // edge lanes: x neighbours that live in another warp / across the periodic seam
       cplx cl, cr, uxl;
       if (edge_l) {
@@ -228,6 +229,19 @@ __global__ void __launch_bounds__(STAG_THREADS) stag_kernel(const StagArgs a) {
         m[s] = c[s];
         c[s] = p[s];
         if (HAS_U) uym[s] = cur.uy[s];
+      }
+    };
+
+#pragma unroll 1
+    for (int y = ya; y < yb; y += PF) {
+#pragma unroll
+      for (int k = 0; k < PF; k++) {
+        const int yy = y + k;
+        if (yy < yb) {
+          const RowLoad<SPT> cur = st[k];
+          if (yy + PF < yb) fetch(yy + PF, st[k]);  // refill this stage while the row is computed
+          row_body(yy, cur);
+        }
       }
     }
   }
@@ -320,16 +334,30 @@ __global__ void __launch_bounds__(256) laplace_kernel(const LapArgs<T> a) {
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
-static int g_stag_blocks_per_sm = 0;
+// tunables (environment, read once): GLB_STAG_PF = rows of loads in flight per thread (1 or 2),
+// GLB_STAG_SPT = sites per thread (1 or 2).  Defaults are the measured-best values.
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+static int stag_pf() {
+  static int v = env_int("GLB_STAG_PF", 1);
+  return v == 2 ? 2 : 1;
+}
+static int stag_spt() {
+  static int v = env_int("GLB_STAG_SPT", 2);
+  return v == 1 ? 1 : 2;
+}
 
-template <int SPT, bool HAS_U, bool FUSE, int NDOT, int FAM>
+template <int SPT, bool HAS_U, bool FUSE, int NDOT, int FAM, int PF>
 static int launch_stag_t(glb_operator* op, const StagArgs& a) {
   glb_context* ctx = op->ctx;
-  auto kern = stag_kernel<SPT, HAS_U, FUSE, NDOT, FAM>;
-  int per_sm = 0;
-  GLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, STAG_THREADS, 0));
-  if (per_sm < 1) per_sm = 1;
-  g_stag_blocks_per_sm = per_sm;
+  auto kern = stag_kernel<SPT, HAS_U, FUSE, NDOT, FAM, PF>;
+  static int per_sm = 0;  // one value per instantiation
+  if (per_sm == 0) {
+    GLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, STAG_THREADS, 0));
+    if (per_sm < 1) per_sm = 1;
+  }
   const int strip_w = STAG_THREADS * SPT;
   const long long nstrips = (a.X + strip_w - 1) / strip_w;
   const long long units = nstrips * a.Yloc;
@@ -344,16 +372,22 @@ static int launch_stag_t(glb_operator* op, const StagArgs& a) {
   return GLB_OK;
 }
 
+template <int SPT, bool HAS_U, int FAM, int PF>
+static int launch_stag_p(glb_operator* op, const StagArgs& a, bool fuse, int ndot) {
+  if (fuse) {
+    if (ndot == 0) return launch_stag_t<SPT, HAS_U, true, 0, FAM, PF>(op, a);
+    if (ndot == 1) return launch_stag_t<SPT, HAS_U, true, 1, FAM, PF>(op, a);
+    return launch_stag_t<SPT, HAS_U, true, 2, FAM, PF>(op, a);
+  }
+  if (ndot == 0) return launch_stag_t<SPT, HAS_U, false, 0, FAM, PF>(op, a);
+  if (ndot == 1) return launch_stag_t<SPT, HAS_U, false, 1, FAM, PF>(op, a);
+  return launch_stag_t<SPT, HAS_U, false, 2, FAM, PF>(op, a);
+}
+
 template <int SPT, bool HAS_U, int FAM>
 static int launch_stag_f(glb_operator* op, const StagArgs& a, bool fuse, int ndot) {
-  if (fuse) {
-    if (ndot == 0) return launch_stag_t<SPT, HAS_U, true, 0, FAM>(op, a);
-    if (ndot == 1) return launch_stag_t<SPT, HAS_U, true, 1, FAM>(op, a);
-    return launch_stag_t<SPT, HAS_U, true, 2, FAM>(op, a);
-  }
-  if (ndot == 0) return launch_stag_t<SPT, HAS_U, false, 0, FAM>(op, a);
-  if (ndot == 1) return launch_stag_t<SPT, HAS_U, false, 1, FAM>(op, a);
-  return launch_stag_t<SPT, HAS_U, false, 2, FAM>(op, a);
+  if (stag_pf() == 2) return launch_stag_p<SPT, HAS_U, FAM, 2>(op, a, fuse, ndot);
+  return launch_stag_p<SPT, HAS_U, FAM, 1>(op, a, fuse, ndot);
 }
 
 int launch_staggered(glb_operator* op, void* out, const void* in, bool dagger, const ApplyFusion& f) {
@@ -399,7 +433,7 @@ int launch_staggered(glb_operator* op, void* out, const void* in, bool dagger, c
   a.cg_role = f.cg_role;
   const int ndot = (f.w != nullptr || f.w_is_input) ? (f.want_norm ? 2 : 1) : 0;
   if (ndot == 0 && f.want_norm) return fail(GLB_ERR_ARG, "want_norm requires a dot partner");
-  const bool spt2 = (op->X % 2 == 0);
+  const bool spt2 = (op->X % 2 == 0) && stag_spt() == 2;
   if (op->kind == OPK_LAPLACE_U1) {
     a.mass = 4 + op->mass;  // operators.cpp:116 : (4+mass), int + double
     if (spt2) return launch_stag_f<2, true, FAM_LAPLACE_U1>(op, a, fuse, ndot);

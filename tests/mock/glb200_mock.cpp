@@ -1,0 +1,271 @@
+// glb200_mock.cpp -- TEST INFRASTRUCTURE: a host-memory implementation of the C ABI
+// (include/glb200.h) so that the C++ solver shells (generic-linalg_b200/host/*.cpp) can be
+// exercised WITHOUT a GPU in `pytest -m "not gpu"`.  "Device" vectors are malloc'ed host arrays,
+// reductions are the serial sums of generic_vector.h and operators are the CPU oracle's
+// (oracle/port_oracle.cpp, included below) -- so the shells running on this mock must reproduce
+// the reference's solvers BIT FOR BIT, which pins every piece of host logic (scalar recurrences,
+// stopping tests, counting, permutations).  Never shipped, never loaded by the product.
+#include "../../oracle/port_oracle.cpp"   // anonymous-namespace helpers: PortOp, apply(), v_dot, ...
+
+#include <cstdlib>
+
+#include "../../include/glb200.h"
+
+struct glb_context {
+  int dummy;
+};
+struct glb_operator {
+  glb_context* ctx;
+  PortOp* op;
+  int dtype;
+  std::vector<cplx> links;
+};
+
+static std::string g_err;
+static unsigned long long g_calls = 0;
+static glb_context g_ctx;
+
+template <typename T>
+static T cf(const double a[2]);
+template <>
+double cf<double>(const double a[2]) { return a[0]; }
+template <>
+cplx cf<cplx>(const double a[2]) { return cplx(a[0], a[1]); }
+
+#define BOTH(dtype, BODY)                      \
+  do {                                         \
+    if ((dtype) == GLB_COMPLEX) {              \
+      typedef cplx T;                          \
+      BODY                                     \
+    } else {                                   \
+      typedef double T;                        \
+      BODY                                     \
+    }                                          \
+  } while (0)
+
+extern "C" {
+int glb_create(int, glb_context** ctx) { *ctx = &g_ctx; return GLB_OK; }
+int glb_destroy(glb_context*) { return GLB_OK; }
+const char* glb_last_error(void) { return g_err.c_str(); }
+int glb_synchronize(glb_context*) { return GLB_OK; }
+void* glb_stream(glb_context*) { return 0; }
+int glb_device(glb_context*) { return -1; }
+int glb_sm_count(glb_context*) { return 0; }
+unsigned long long glb_kernel_launches(void) { return g_calls; }
+int glb_comm_unique_id(char*) { return GLB_ERR_COMM; }
+int glb_comm_init(glb_context*, int, int, const char*) { return GLB_ERR_COMM; }
+int glb_comm_rank(glb_context*) { return 0; }
+int glb_comm_size(glb_context*) { return 1; }
+int glb_comm_export_mailbox(glb_context*, char*) { return GLB_ERR_COMM; }
+int glb_comm_attach_mailboxes(glb_context*, const char*) { return GLB_ERR_COMM; }
+int glb_comm_barrier(glb_context*) { return GLB_OK; }
+int glb_slab_bounds(glb_context*, int Y, int* y0, int* Yloc) { *y0 = 0; *Yloc = Y; return GLB_OK; }
+
+int glb_vec_alloc(glb_context*, int dtype, size_t n, void** p) {
+  *p = std::calloc(n ? n : 1, dtype == GLB_COMPLEX ? 16 : 8);
+  return *p ? GLB_OK : GLB_ERR_CUDA;
+}
+int glb_vec_free(glb_context*, void* p) { std::free(p); return GLB_OK; }
+static size_t eb(int dtype) { return dtype == GLB_COMPLEX ? 16 : 8; }
+int glb_vec_upload(glb_context*, int dt, size_t n, void* d, const void* s) { std::memcpy(d, s, n * eb(dt)); return GLB_OK; }
+int glb_vec_download(glb_context*, int dt, size_t n, void* d, const void* s) { std::memcpy(d, s, n * eb(dt)); return GLB_OK; }
+int glb_vec_zero(glb_context*, int dt, size_t n, void* d) { std::memset(d, 0, n * eb(dt)); return GLB_OK; }
+int glb_vec_copy(glb_context*, int dt, size_t n, void* d, const void* s) { std::memmove(d, s, n * eb(dt)); return GLB_OK; }
+int glb_host_alloc(glb_context*, size_t b, void** p) { *p = std::malloc(b ? b : 1); return GLB_OK; }
+int glb_host_free(glb_context*, void* p) { std::free(p); return GLB_OK; }
+
+static glb_operator* wrap(int kind, int X, int Y, int Nc, double mass, const void* links, int dtype) {
+  glb_operator* o = new glb_operator();
+  o->ctx = &g_ctx;
+  o->dtype = dtype;
+  orc_op_desc d;
+  std::memset(&d, 0, sizeof d);
+  d.kind = kind;
+  d.X = X;
+  d.Y = Y;
+  d.Nc = Nc;
+  d.mass = mass;
+  if (links) {
+    o->links.assign((const cplx*)links, (const cplx*)links + 2 * (size_t)X * Y);
+    d.links = (const double*)o->links.data();
+  }
+  o->op = (PortOp*)port_op_prepare(&d);
+  return o;
+}
+int glb_op_create_laplace(glb_context*, int dtype, int X, int Y, int Nc, double dre, double dim, glb_operator** op) {
+  // mass is recovered from the diagonal exactly as the callers built it (4 + mass)
+  if (dtype == GLB_REAL)
+    *op = wrap(Nc == 1 && X == Y ? ORC_OP_LAPLACE_REAL : ORC_OP_LAPLACE_REAL_NC, X, Y, Nc, dre - 4, 0, dtype);
+  else if (dim != 0.0)
+    *op = wrap(ORC_OP_LAPLACE_IMAG, X, Y, 1, dre - 4.0, 0, dtype);
+  else
+    *op = wrap(ORC_OP_LAPLACE_NC, X, Y, Nc, dre - 4, 0, dtype);
+  return GLB_OK;
+}
+int glb_op_create_laplace_u1(glb_context*, const void* l, int X, int Y, double m, glb_operator** op) {
+  *op = wrap(ORC_OP_LAPLACE_U1, X, Y, 1, m, l, GLB_COMPLEX);
+  return GLB_OK;
+}
+int glb_op_create_staggered(glb_context*, const void* l, int X, int Y, double m, unsigned flags, glb_operator** op) {
+  int kind = l ? ORC_OP_STAG_U1 : ORC_OP_STAG_FREE;
+  if (flags & GLB_STAG_DAGGER) kind = ORC_OP_STAG_DAGGER_U1;
+  if (flags & GLB_STAG_GAMMA5) kind = l ? ORC_OP_STAG_GAMMA5_U1 : ORC_OP_STAG_GAMMA5_FREE;
+  if (flags & GLB_STAG_NORMAL) kind = ORC_OP_STAG_NORMAL_U1;
+  *op = wrap(kind, X, Y, 1, m, l, GLB_COMPLEX);
+  return GLB_OK;
+}
+int glb_op_create_staggered_local(glb_context*, const void*, int, int, double, unsigned, glb_operator**) { return GLB_ERR_ARG; }
+int glb_op_create_gamma5(glb_context*, int X, int Y, glb_operator** op) {
+  *op = wrap(ORC_OP_GAMMA5, X, Y, 1, 0, 0, GLB_COMPLEX);
+  return GLB_OK;
+}
+int glb_op_create_stencil2d(glb_context*, const void* cl, const void* hp, const void* tl, int X, int Y, int nc,
+                            const double sh[2], const double eo[2], const double df[2], glb_operator** op) {
+  glb_operator* o = new glb_operator();
+  o->ctx = &g_ctx;
+  o->dtype = GLB_COMPLEX;
+  orc_op_desc d;
+  std::memset(&d, 0, sizeof d);
+  d.kind = ORC_OP_STENCIL;
+  d.X = X; d.Y = Y; d.Nc = nc;
+  d.clover = (const double*)cl; d.hopping = (const double*)hp; d.two_link = (const double*)tl; d.has_two = tl != 0;
+  for (int i = 0; i < 2; i++) { d.shift[i] = sh[i]; d.eo_shift[i] = eo[i]; d.dof_shift[i] = df[i]; }
+  o->op = (PortOp*)port_op_prepare(&d);
+  *op = o;
+  return GLB_OK;
+}
+int glb_op_destroy(glb_operator* o) { if (o) { port_op_free(o->op); delete o; } return GLB_OK; }
+int glb_op_set_mass(glb_operator* o, double m) { o->op->d.mass = m; return GLB_OK; }
+int glb_op_dtype(const glb_operator* o) { return o->dtype; }
+size_t glb_op_local_size(const glb_operator* o) { return o->op->size; }
+size_t glb_op_global_size(const glb_operator* o) { return o->op->size; }
+glb_context* glb_op_context(const glb_operator* o) { return o->ctx; }
+double glb_op_bytes_per_apply(const glb_operator*) { return 0; }
+int glb_op_apply(glb_operator* o, void* out, const void* in) {
+  g_calls++;
+  port_op_apply(o->op, (double*)out, (const double*)in);
+  return GLB_OK;
+}
+int glb_dot(glb_context*, int dt, size_t n, const void* x, const void* y, double out[2]) {
+  port_dot(dt == GLB_COMPLEX, (const double*)x, (const double*)y, (int)n, out);
+  return GLB_OK;
+}
+int glb_norm2sq(glb_context*, int dt, size_t n, const void* x, double* out) {
+  *out = port_norm2sq(dt == GLB_COMPLEX, (const double*)x, (int)n);
+  return GLB_OK;
+}
+int glb_diffnorm2sq(glb_context*, int dt, size_t n, const void* x, const void* y, double* out) {
+  *out = port_diffnorm2sq(dt == GLB_COMPLEX, (const double*)x, (const double*)y, (int)n);
+  return GLB_OK;
+}
+int glb_op_apply_dot(glb_operator* o, void* out, const void* in, const void* w, int want_norm, double dots[3]) {
+  glb_op_apply(o, out, in);
+  glb_dot(o->ctx, o->dtype, o->op->size, w ? w : in, out, dots);
+  dots[2] = 0.0;
+  if (want_norm) glb_norm2sq(o->ctx, o->dtype, o->op->size, out, &dots[2]);
+  return GLB_OK;
+}
+int glb_dot_norm(glb_context* c, int dt, size_t n, const void* x, const void* y, double out[3]) {
+  glb_dot(c, dt, n, x, y, out);
+  return glb_norm2sq(c, dt, n, x, &out[2]);
+}
+int glb_multi_dot(glb_context* c, int dt, size_t n, int k, const void* const* X, const void* y, double* out) {
+  for (int j = 0; j < k; j++) glb_dot(c, dt, n, X[j], y, out + 2 * j);
+  return GLB_OK;
+}
+int glb_sub(glb_context*, int dt, size_t n, const void* a, const void* b, void* o) {
+  BOTH(dt, { for (size_t i = 0; i < n; i++) ((T*)o)[i] = ((const T*)a)[i] - ((const T*)b)[i]; });
+  return GLB_OK;
+}
+int glb_add(glb_context*, int dt, size_t n, const void* a, const void* b, void* o) {
+  BOTH(dt, { for (size_t i = 0; i < n; i++) ((T*)o)[i] = ((const T*)a)[i] + ((const T*)b)[i]; });
+  return GLB_OK;
+}
+int glb_axpy(glb_context*, int dt, size_t n, const double a[2], const void* x, void* y) {
+  BOTH(dt, { const T c = cf<T>(a); for (size_t i = 0; i < n; i++) ((T*)y)[i] = ((T*)y)[i] + c * ((const T*)x)[i]; });
+  return GLB_OK;
+}
+int glb_xpay(glb_context*, int dt, size_t n, const void* x, const double a[2], void* y) {
+  BOTH(dt, { const T c = cf<T>(a); for (size_t i = 0; i < n; i++) ((T*)y)[i] = ((const T*)x)[i] + c * ((T*)y)[i]; });
+  return GLB_OK;
+}
+int glb_axpyz(glb_context*, int dt, size_t n, const double a[2], const void* x, const void* y, void* z) {
+  BOTH(dt, { const T c = cf<T>(a); for (size_t i = 0; i < n; i++) ((T*)z)[i] = ((const T*)y)[i] + c * ((const T*)x)[i]; });
+  return GLB_OK;
+}
+int glb_rdiv(glb_context*, int dt, size_t n, const void* x, double d, void* o) {
+  BOTH(dt, { for (size_t i = 0; i < n; i++) ((T*)o)[i] = ((const T*)x)[i] / d; });
+  return GLB_OK;
+}
+int glb_axpy_norm(glb_context* c, int dt, size_t n, const double a[2], const void* x, void* y, double* nrm) {
+  glb_axpy(c, dt, n, a, x, y);
+  return glb_norm2sq(c, dt, n, y, nrm);
+}
+int glb_lincomb(glb_context*, int dt, size_t n, int k, const double* coef, const void* const* X, const void* init,
+                void* out) {
+  BOTH(dt, {
+    for (size_t i = 0; i < n; i++) {
+      T v = init ? ((const T*)init)[i] : T(0.0);
+      for (int j = 0; j < k; j++) v = v + cf<T>(coef + 2 * j) * ((const T*)X[j])[i];
+      ((T*)out)[i] = v;
+    }
+  });
+  return GLB_OK;
+}
+int glb_update_xr_norm(glb_context* c, int dt, size_t n, const double a[2], const void* p, void* x, const double b[2],
+                       const void* q, void* r, double* rsq) {
+  glb_axpy(c, dt, n, a, p, x);
+  glb_axpy(c, dt, n, b, q, r);
+  return glb_norm2sq(c, dt, n, r, rsq);
+}
+int glb_update_p_ap_norm(glb_context* c, int dt, size_t n, const void* r, const void* Ar, const double beta[2], void* p,
+                         void* Ap, double* apsq) {
+  glb_xpay(c, dt, n, r, beta, p);
+  glb_xpay(c, dt, n, Ar, beta, Ap);
+  return glb_norm2sq(c, dt, n, Ap, apsq);
+}
+int glb_bicgstab_update(glb_context* c, int dt, size_t n, const double alpha[2], const void* p, const double omega[2],
+                        const void* s, const void* As, const void* r0, void* x, void* r, double out[3]) {
+  BOTH(dt, {
+    const T al = cf<T>(alpha); const T om = cf<T>(omega);
+    for (size_t i = 0; i < n; i++) ((T*)x)[i] = ((T*)x)[i] + al * ((const T*)p)[i] + om * ((const T*)s)[i];
+    for (size_t i = 0; i < n; i++) ((T*)r)[i] = ((const T*)s)[i] - om * ((const T*)As)[i];
+  });
+  glb_norm2sq(c, dt, n, r, &out[0]);
+  out[2] = 0.0;
+  return glb_dot(c, dt, n, r0, r, out + 1);
+}
+int glb_bicgstab_pupdate(glb_context*, int dt, size_t n, const void* r, const double beta[2], const double omega[2],
+                         const void* Ap, void* p) {
+  BOTH(dt, {
+    const T be = cf<T>(beta); const T om = cf<T>(omega);
+    for (size_t i = 0; i < n; i++) ((T*)p)[i] = ((const T*)r)[i] + be * (((T*)p)[i] - om * ((const T*)Ap)[i]);
+  });
+  return GLB_OK;
+}
+int glb_cgm_update_x(glb_context*, int dt, size_t n, int ns, const double* beta_s, const void* const* p_s, void* const* x) {
+  BOTH(dt, {
+    for (int s = 0; s < ns; s++) {
+      const T c = cf<T>(beta_s + 2 * s);
+      for (size_t i = 0; i < n; i++) ((T*)x[s])[i] = ((T*)x[s])[i] - c * ((const T*)p_s[s])[i];
+    }
+  });
+  return GLB_OK;
+}
+int glb_cgm_update_p(glb_context*, int dt, size_t n, int ns, const double* zeta, const double* alpha_s, const void* r,
+                     void* const* p_s) {
+  BOTH(dt, {
+    for (int s = 0; s < ns; s++) {
+      const T z = cf<T>(zeta + 2 * s); const T a = cf<T>(alpha_s + 2 * s);
+      for (size_t i = 0; i < n; i++) ((T*)p_s[s])[i] = z * ((const T*)r)[i] + a * ((T*)p_s[s])[i];
+    }
+  });
+  return GLB_OK;
+}
+// the device-resident CG is a CUDA-only entry point: the shells fall back to the host-scalar loop
+// when forced (glb200_force_host_scalars), which is what the mock tests do.
+int glb_cg_solve(glb_operator*, void*, const void*, int, double, glb_cg_report*, double*, int) {
+  g_err = "glb_cg_solve is not available in the CPU mock";
+  return GLB_ERR_STATE;
+}
+}  // extern "C"

@@ -121,6 +121,8 @@ def test_apply_dot_fusion(ctx, glb, orc):
         assert abs(dot - ref_dot) <= 1e-12 * abs(ref_dot) and abs(nrm - ref_nrm) <= 1e-12 * ref_nrm
         dot2, _ = op.apply_dot(out, x, None)
         assert abs(dot2 - np.vdot(b, y)) <= 1e-12 * abs(np.vdot(b, y))
+        dot3, nrm3 = op.apply_dot(out, x, x, want_norm=True)   # partner == input, with |out|^2 (BiCGStab omega)
+        assert abs(dot3 - np.vdot(b, y)) <= 1e-12 * abs(np.vdot(b, y)) and abs(nrm3 - ref_nrm) <= 1e-12 * ref_nrm
         # reproducible: same call, same bits
         assert op.apply_dot(out, x, w, want_norm=True) == (dot, nrm)
 
