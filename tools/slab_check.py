@@ -104,7 +104,8 @@ def main():
         info = ctx.solve(solver, op, x, bd, max_iter=100000, **kw)
         xg = gather(x.download())
         rr = np.linalg.norm(oop.apply(xg) - rhs) / np.linalg.norm(rhs)
-        ok = abs(info["iter"] - want["iter"]) <= max(1, round(0.02 * want["iter"])) and rr < kw["eps"] * 1.000001
+        tol_it = 0.10 if solver.startswith("BICGSTAB") else 0.02   # BiCGStab is chaotic (see tests/test_solvers_gpu.py)
+        ok = abs(info["iter"] - want["iter"]) <= max(1, round(tol_it * want["iter"])) and rr < kw["eps"] * 1.000001
         check("solve %s" % name, ok, "iter %d (oracle %d) true rel res %.2e" % (info["iter"], want["iter"], rr))
     shifts = [0.0, 0.01, 0.05, 0.25]
     xs = [ctx.vector(Yloc * X) for _ in shifts]
