@@ -42,6 +42,13 @@ static int direction_and_apply(glb_operator* op, CgState* d_st, const void* r, v
     f.p_new = p_alt;
     f.cg_state = (const double*)d_st;
     *swapped = true;
+    if ((op->flags & GLB_STAG_NORMAL) && normal_fused_ok(op)) {
+      // one pass: p_alt = r + beta p ; Ap = D^dag D p_alt ; <p_alt,Ap>   (96 B/site)
+      f.w = p_alt;
+      f.w_is_input = true;
+      f.cg_role = 1;
+      return launch_normal(op, Ap, nullptr, f);
+    }
     if (op->flags & GLB_STAG_NORMAL) {
       // K1: t = D (r + beta p), p_alt = r + beta p
       int rc = launch_staggered(op, op->tmp, nullptr, false, f);

@@ -254,6 +254,7 @@ static int apply_impl(glb_operator* op, void* out, const void* in, const ApplyFu
     case OPK_LAPLACE_U1:
     case OPK_STAGGERED: {
       if (op->flags & GLB_STAG_NORMAL) {  // operators.cpp:444-453 : tmp = D in ; out = D^dag tmp
+        if (normal_fused_ok(op)) return launch_normal(op, out, in, f);  // one pass, tmp stays on the SM
         ApplyFusion none;
         if (ctx->nranks > 1) {
           int rc = halo_exchange(op, in, row, op->dtype);

@@ -119,6 +119,9 @@ struct ApplyFusion {
 int launch_staggered(glb_operator* op, void* out, const void* in, bool dagger, const ApplyFusion& f);
 int launch_laplace(glb_operator* op, void* out, const void* in, const ApplyFusion& f);
 int launch_gamma5(glb_operator* op, void* out, const void* in);
+// normal.cu : D^dag D in one pass (single rank, gauged, even X)
+bool normal_fused_ok(const glb_operator* op);
+int launch_normal(glb_operator* op, void* out, const void* in, const ApplyFusion& f);
 int launch_stencil2d(glb_operator* op, void* out, const void* in, const ApplyFusion& f);
 
 // comm.cu : fills op->ghost_lo / ghost_hi from the neighbouring ranks' boundary rows of `in`

@@ -28,7 +28,12 @@ def iteration_envelope(orc, solver, oop, b, x0=None, nprobe=6, **kw):
     counts over a few 1e-15 perturbations instead of to a single number."""
     its = []
     for s in range(nprobe):
-        bb = b if s == 0 else b * (1 + 1e-15 * np.random.default_rng(s).standard_normal(b.size))
+        if s == 0:
+            bb = b
+        else:  # additive noise at 1e-15 of |b| (a multiplicative one would leave a delta source unperturbed)
+            rg = np.random.default_rng(s)
+            noise = rg.standard_normal(b.size) + (1j * rg.standard_normal(b.size) if np.iscomplexobj(b) else 0.0)
+            bb = b + (1e-15 * np.linalg.norm(b) / np.sqrt(b.size)) * noise
         its.append(orc.solve(solver, oop, bb, x0=x0, **kw)[1]["iter"])
     return min(its), max(its)
 
