@@ -228,9 +228,10 @@ def main():
     X, Y = L, L * world
     y0, Yloc = ctx.slab_bounds(Y)
     V_local, V_global = X * Yloc, X * Y
-    rows = [(y0 - 1 + Y) % Y] + list(range(y0, y0 + Yloc))
+    # this rank's rows plus two periodic ghost rows on each side (glb_op_create_staggered_local)
+    rows = [(y0 - 2 + Y) % Y, (y0 - 1 + Y) % Y] + list(range(y0, y0 + Yloc)) + [(y0 + Yloc) % Y, (y0 + Yloc + 1) % Y]
     links_local = gauge_rows(X, rows)
-    b_local = rhs_rows(X, rows[1:])
+    b_local = rhs_rows(X, rows[2:-2])
     opN = ctx.staggered_local(links_local, X, Y, MASS, glb.STAG_NORMAL)
     opD = ctx.staggered_local(links_local, X, Y, MASS, 0)
     opDd = ctx.staggered_local(links_local, X, Y, MASS, glb.STAG_DAGGER)
@@ -289,7 +290,7 @@ def main():
     e2e_iters = iters
     if world == 1:
         ctx.cache_operators(True)   # gauge field stays resident between solves (it is the "model"); vectors travel
-        desc = ctx._desc("STAG_NORMAL_U1", X, Y, mass=MASS, links=links_local[2 * X:])
+        desc = ctx._desc("STAG_NORMAL_U1", X, Y, mass=MASS, links=links_local[4 * X:4 * X + 2 * X * Y])
 
         def solve_e2e():
             hx[:] = 0
@@ -332,7 +333,7 @@ def main():
         import oracle_py
         orc = oracle_py.load("best")
         Lc = L
-        Uc = links_local[2 * X:] if Lc == L else gauge_rows(Lc, list(range(Lc)))
+        Uc = links_local[4 * X:4 * X + 2 * X * Y] if Lc == L else gauge_rows(Lc, list(range(Lc)))
         bc = hb.copy() if Lc == L else rhs_rows(Lc, list(range(Lc)))
         oop = orc.op("STAG_NORMAL_U1", Lc, Lc, mass=MASS, links=Uc)
         t0 = time.perf_counter()

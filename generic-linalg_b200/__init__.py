@@ -109,6 +109,7 @@ def libs():
         "glb_bicgstab_pupdate": (ci, [vp, ci, sz, vp, pd, pd, vp, vp]),
         "glb_cgm_update_x": (ci, [vp, ci, sz, ci, pd, C.POINTER(vp), C.POINTER(vp)]),
         "glb_cgm_update_p": (ci, [vp, ci, sz, ci, pd, pd, vp, C.POINTER(vp)]),
+        "glb_cg_solve_supported": (ci, [vp]),
         "glb_cg_solve": (ci, [vp, vp, vp, ci, cd, C.POINTER(CgReport), pd, ci]),
     }
     for name, (res, args) in sig.items():
@@ -334,7 +335,8 @@ class Context:
         return self._op(self.cu.glb_op_create_staggered, _p(links), X, Y, mass, flags)
 
     def staggered_local(self, links_local, X, Y, mass, flags=0):
-        """links_local: rows y0-1 .. y0+Yloc-1 of the gauge field (this rank's slab + the row below)"""
+        """links_local: rows y0-2 .. y0+Yloc+1 of the gauge field (this rank's slab + two periodic ghost rows
+        on each side), reference layout [row][x][mu]"""
         links_local = np.ascontiguousarray(links_local, dtype=np.complex128)
         return self._op(self.cu.glb_op_create_staggered_local, _p(links_local), X, Y, mass, flags)
 

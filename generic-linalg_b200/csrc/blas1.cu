@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(256) cgm_p_kernel(MultiArgs<T> a, const T* r, 
 // state, and the stopping test of generic_cg.cpp:339 evaluated by the last block.
 template <typename T, int W>
 __global__ void __launch_bounds__(256)
-cg_update_kernel(CgState* st, double* hist, const T* p, T* x, const T* Ap, T* r, size_t n, ReduceWs red) {
+cg_update_kernel(CgState* st, double* hist, const T* p, T* x, const T* Ap, T* r, size_t n, ReduceWs red, int defer) {
   if (st->done) return;
   T alpha;
   {
@@ -294,6 +294,10 @@ cg_update_kernel(CgState* st, double* hist, const T* p, T* x, const T* Ap, T* r,
   }
   double total[1];
   if (grid_sum<1>(acc, red, total) && threadIdx.x == 0) {
+    if (defer) {  // slab run: the sum over ranks and the recurrence step follow on the stream
+      st->partial[0] = total[0];
+      return;
+    }
     const double rsq_new = total[0];
     st->rsq_new = rsq_new;
     const int k = st->iter;  // 0-based iteration index of the reference loop
@@ -305,6 +309,44 @@ cg_update_kernel(CgState* st, double* hist, const T* p, T* x, const T* Ap, T* r,
       st->done = 1;
       st->hit_max = (k == st->max_iter - 1) ? 1 : 0;  // generic_cg.cpp:356 tests k alone
     }
+  }
+}
+
+// slab runs: fold the rank-summed |r|^2 into the recurrence (what the last block does on one rank)
+__global__ void cg_post_update_kernel(CgState* st, double* hist) {
+  if (st->done) return;
+  const double rsq_new = st->partial[0];
+  st->rsq_new = rsq_new;
+  const int k = st->iter;
+  st->iter = k + 1;
+  if (hist != nullptr && k < st->hist_cap) hist[k] = rsq_new;
+  const bool conv = sqrt(rsq_new) < st->eps * st->bnorm;
+  const bool last = (k == st->max_iter - 1);
+  if (conv || last) {
+    st->done = 1;
+    st->hit_max = last ? 1 : 0;
+  }
+}
+// slab runs: fold the rank-summed <p,Ap> into the recurrence
+__global__ void cg_post_apply_kernel(CgState* st) {
+  if (st->done) return;
+  st->pAp_re = st->partial[1];
+  st->pAp_im = st->partial[2];
+  st->rsq_old = st->rsq_new;
+}
+// slab runs: the new direction p = r + beta p_old on the `nrows` lowest and highest rows of the slab,
+// written to the send buffers that go to the neighbouring ranks' ghost rows
+template <typename T>
+__global__ void cg_boundary_kernel(const CgState* st, const T* r, const T* pold, T* send_lo, T* send_hi,
+                                   size_t row_elems, int nrows, size_t local_elems) {
+  if (st->done) return;
+  const double b = xdiv(st->rsq_new, st->rsq_old);
+  const size_t n = row_elems * nrows;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n; i += (size_t)gridDim.x * blockDim.x) {
+    const bool hi = i >= n;
+    const size_t j = hi ? i - n : i;
+    const size_t src = hi ? local_elems - n + j : j;
+    (hi ? send_hi : send_lo)[j] = fadd(r[src], fscale(b, pold[src]));
   }
 }
 
@@ -324,8 +366,27 @@ __global__ void __launch_bounds__(256) cg_xpay_kernel(const CgState* st, const T
     p[i] = fadd(r[i], fmul(beta, p[i]));
 }
 
+int launch_cg_post_update(glb_context* ctx, void* st, double* hist) {
+  cg_post_update_kernel<<<1, 1, 0, ctx->stream>>>((CgState*)st, hist);
+  GLB_LAUNCH_CHECK();
+  return GLB_OK;
+}
+int launch_cg_post_apply(glb_context* ctx, void* st) {
+  cg_post_apply_kernel<<<1, 1, 0, ctx->stream>>>((CgState*)st);
+  GLB_LAUNCH_CHECK();
+  return GLB_OK;
+}
+int launch_cg_boundary(glb_context* ctx, const void* st, const void* r, const void* pold, void* send_lo, void* send_hi,
+                       size_t row_elems, int nrows, size_t local_elems) {
+  const int grid = blas_grid(ctx, 2 * row_elems * nrows, 256, 1);
+  cg_boundary_kernel<cplx><<<grid, 256, 0, ctx->stream>>>((const CgState*)st, (const cplx*)r, (const cplx*)pold,
+                                                          (cplx*)send_lo, (cplx*)send_hi, row_elems, nrows, local_elems);
+  GLB_LAUNCH_CHECK();
+  return GLB_OK;
+}
+
 int launch_cg_update(glb_context* ctx, int dtype, void* st, double* hist, const void* p, void* x, const void* Ap,
-                     void* r, size_t n) {
+                     void* r, size_t n, int defer) {
   ReduceWs red = ctx->red;
   red.result_host = nullptr;
   if (dtype == GLB_COMPLEX) {
@@ -333,16 +394,16 @@ int launch_cg_update(glb_context* ctx, int dtype, void* st, double* hist, const 
     if (wide) {
       const int grid = blas_grid(ctx, n / 2, 256, 2);
       cg_update_kernel<cplx, 2><<<grid, 256, 0, ctx->stream>>>((CgState*)st, hist, (const cplx*)p, (cplx*)x,
-                                                               (const cplx*)Ap, (cplx*)r, n, red);
+                                                               (const cplx*)Ap, (cplx*)r, n, red, defer);
     } else {
       const int grid = blas_grid(ctx, n, 256, 4);
       cg_update_kernel<cplx, 1><<<grid, 256, 0, ctx->stream>>>((CgState*)st, hist, (const cplx*)p, (cplx*)x,
-                                                               (const cplx*)Ap, (cplx*)r, n, red);
+                                                               (const cplx*)Ap, (cplx*)r, n, red, defer);
     }
   } else {
     const int grid = blas_grid(ctx, n, 256, 4);
     cg_update_kernel<double, 1><<<grid, 256, 0, ctx->stream>>>((CgState*)st, hist, (const double*)p, (double*)x,
-                                                               (const double*)Ap, (double*)r, n, red);
+                                                               (const double*)Ap, (double*)r, n, red, defer);
   }
   GLB_LAUNCH_CHECK();
   return GLB_OK;

@@ -20,13 +20,17 @@
 namespace glb {
 
 int launch_cg_update(glb_context* ctx, int dtype, void* st, double* hist, const void* p, void* x, const void* Ap,
-                     void* r, size_t n);
+                     void* r, size_t n, int defer);
+int launch_cg_post_update(glb_context* ctx, void* st, double* hist);
+int launch_cg_post_apply(glb_context* ctx, void* st);
+int launch_cg_boundary(glb_context* ctx, const void* st, const void* r, const void* pold, void* send_lo, void* send_hi,
+                       size_t row_elems, int nrows, size_t local_elems);
 int launch_cg_xpay(glb_context* ctx, int dtype, const void* st, const void* r, void* p, size_t n);
 int op_apply_fused(glb_operator* op, void* out, const void* in, const ApplyFusion& f);
-int allreduce_device(glb_context* ctx, double* d_vals, int n);
 
 static bool can_fuse_direction(const glb_operator* op) {
-  return op->ctx->nranks == 1 && (op->kind == OPK_STAGGERED || op->kind == OPK_LAPLACE_U1) && op->X >= 2;
+  if (op->ctx->nranks > 1) return normal_fused_ok(op);  // slabs: only the one-pass D^dag D kernel
+  return (op->kind == OPK_STAGGERED || op->kind == OPK_LAPLACE_U1) && op->X >= 2;
 }
 
 // p_next = r + beta p_cur ; Ap = A p_next ; <p_next, Ap> -> state.  Returns which buffer holds p.
@@ -35,6 +39,26 @@ static int direction_and_apply(glb_operator* op, CgState* d_st, const void* r, v
   glb_context* ctx = op->ctx;
   const size_t n = glb_op_local_size(op);
   *swapped = false;
+  if (ctx->nranks > 1) {
+    // slab run: boundary rows of the new direction -> neighbours' ghost rows, then the one-pass
+    // kernel (own rows formed on the fly, ghost rows read as they are), then the rank sum of <p,Ap>
+    const size_t row = (size_t)op->X;
+    int rc = launch_cg_boundary(ctx, d_st, r, p_cur, op->send_lo, op->send_hi, row, 2, n);
+    if (rc) return rc;
+    if ((rc = halo_exchange_ptrs(op, op->send_lo, op->send_hi, 2))) return rc;
+    ApplyFusion f;
+    f.r = r;
+    f.p_old = p_cur;
+    f.p_new = p_alt;
+    f.cg_state = (const double*)d_st;
+    f.w = p_alt;
+    f.w_is_input = true;
+    f.cg_role = 2;
+    *swapped = true;
+    if ((rc = launch_normal(op, Ap, nullptr, f))) return rc;
+    if ((rc = allreduce_device(ctx, d_st->partial + 1, 2))) return rc;
+    return launch_cg_post_apply(ctx, d_st);
+  }
   if (can_fuse_direction(op)) {
     ApplyFusion f;
     f.r = r;
@@ -79,12 +103,18 @@ static int direction_and_apply(glb_operator* op, CgState* d_st, const void* r, v
 
 using namespace glb;
 
+extern "C" int glb_cg_solve_supported(const glb_operator* op) {
+  if (!op) return 0;
+  return (op->ctx->nranks == 1 || normal_fused_ok(op)) ? 1 : 0;
+}
+
 extern "C" int glb_cg_solve(glb_operator* op, void* d_x, const void* d_b, int max_iter, double eps,
                             glb_cg_report* rep, double* rsq_hist, int hist_cap) {
   if (!op || !d_x || !d_b || !rep) return fail(GLB_ERR_ARG, "glb_cg_solve: null argument");
   if (max_iter < 1) return fail(GLB_ERR_ARG, "glb_cg_solve: max_iter must be >= 1");
   glb_context* ctx = op->ctx;
-  if (ctx->nranks > 1) return fail(GLB_ERR_STATE, "glb_cg_solve: slab runs use the host-scalar shell in this build");
+  if (ctx->nranks > 1 && !normal_fused_ok(op))
+    return fail(GLB_ERR_STATE, "glb_cg_solve on slabs needs the one-pass D^dag D operator (see glb_cg_solve_supported)");
   const int dt = op->dtype;
   const size_t n = glb_op_local_size(op);
   int rc;
@@ -151,7 +181,13 @@ extern "C" int glb_cg_solve(glb_operator* op, void* d_x, const void* d_b, int ma
     bool have_pending = false;
     while (!finished) {
       for (int b = 0; b < BATCH; b++) {
-        CG_TRY(launch_cg_update(ctx, dt, d_st, d_hist, pc, d_x, Ap, r, n));
+        if (ctx->nranks > 1) {
+          CG_TRY(launch_cg_update(ctx, dt, d_st, d_hist, pc, d_x, Ap, r, n, 1));
+          CG_TRY(allreduce_device(ctx, d_st->partial, 1));
+          CG_TRY(launch_cg_post_update(ctx, d_st, d_hist));
+        } else {
+          CG_TRY(launch_cg_update(ctx, dt, d_st, d_hist, pc, d_x, Ap, r, n, 0));
+        }
         bool swapped = false;
         CG_TRY(direction_and_apply(op, d_st, r, pc, pa, Ap, &swapped));
         if (swapped) std::swap(pc, pa);

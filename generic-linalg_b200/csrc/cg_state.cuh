@@ -20,6 +20,9 @@ struct CgState {
   int hit_max;      // ... because k == max_iter-1
   int hist_cap;
   int pad;
+  // slab runs: this rank's partial sums, summed over ranks in place (ncclAllReduce on the stream)
+  // before a one-thread kernel folds them into the recurrence: [0] |r|^2, [1..2] <p,Ap>
+  double partial[4];
 };
 
 }  // namespace glb

@@ -77,23 +77,33 @@ void comm_destroy(glb_context* ctx) {
   ctx->comm = nullptr;
 }
 
-int halo_exchange(glb_operator* op, const void* in, size_t elems, int dtype) {
+int halo_exchange_ptrs(glb_operator* op, const void* send_lo, const void* send_hi, int nrows) {
   glb_context* ctx = op->ctx;
   if (ctx->nranks == 1) return GLB_OK;
   if (!ctx->comm) return fail(GLB_ERR_STATE, "slab operator used before glb_comm_init");
+  if (nrows < 1 || nrows > op->ghost_depth) return fail(GLB_ERR_ARG, "halo deeper than the operator's ghost rows");
   const int G = ctx->nranks, g = ctx->rank;
   const int up = (g + 1) % G, down = (g + G - 1) % G;
-  const size_t bytes = elems * elem_bytes(dtype);
-  const size_t local = (size_t)op->X * op->nc * op->Yloc * elem_bytes(dtype);
-  const char* base = (const char*)in;
-  // my lowest rows -> `down`'s ghost_hi ; my highest rows -> `up`'s ghost_lo
+  const size_t rowb = (size_t)op->X * op->nc * elem_bytes(op->dtype);
+  const size_t bytes = rowb * nrows;
+  // my lowest rows -> `down`'s ghost_hi (its rows Yloc ..) ; my highest rows -> `up`'s ghost_lo (its rows -nrows .. -1)
+  char* recv_lo = (char*)op->ghost_lo + rowb * (op->ghost_depth - nrows);
+  char* recv_hi = (char*)op->ghost_hi;
   GLB_NCCL(g_nccl.GroupStart());
-  GLB_NCCL(g_nccl.Send(base, bytes, NCCL_CHAR, down, ctx->comm->nccl, ctx->stream));
-  GLB_NCCL(g_nccl.Send(base + local - bytes, bytes, NCCL_CHAR, up, ctx->comm->nccl, ctx->stream));
-  GLB_NCCL(g_nccl.Recv(op->ghost_lo, bytes, NCCL_CHAR, down, ctx->comm->nccl, ctx->stream));
-  GLB_NCCL(g_nccl.Recv(op->ghost_hi, bytes, NCCL_CHAR, up, ctx->comm->nccl, ctx->stream));
+  GLB_NCCL(g_nccl.Send(send_lo, bytes, NCCL_CHAR, down, ctx->comm->nccl, ctx->stream));
+  GLB_NCCL(g_nccl.Send(send_hi, bytes, NCCL_CHAR, up, ctx->comm->nccl, ctx->stream));
+  GLB_NCCL(g_nccl.Recv(recv_lo, bytes, NCCL_CHAR, down, ctx->comm->nccl, ctx->stream));
+  GLB_NCCL(g_nccl.Recv(recv_hi, bytes, NCCL_CHAR, up, ctx->comm->nccl, ctx->stream));
   GLB_NCCL(g_nccl.GroupEnd());
   return GLB_OK;
+}
+
+int halo_exchange(glb_operator* op, const void* in, int nrows) {
+  if (op->ctx->nranks == 1) return GLB_OK;
+  if (nrows > op->Yloc) return fail(GLB_ERR_ARG, "slab thinner than the halo");
+  const size_t rowb = (size_t)op->X * op->nc * elem_bytes(op->dtype);
+  const char* base = (const char*)in;
+  return halo_exchange_ptrs(op, base, base + rowb * (op->Yloc - nrows), nrows);
 }
 
 int allreduce_sum(glb_context* ctx, double* vals, int n) {
@@ -112,6 +122,7 @@ int allreduce_sum(glb_context* ctx, double* vals, int n) {
 // in-stream sum over ranks of n doubles living in device memory (device-resident CG)
 int allreduce_device(glb_context* ctx, double* d_vals, int n) {
   if (ctx->nranks == 1) return GLB_OK;
+  if (!ctx->comm) return fail(GLB_ERR_STATE, "reduction before glb_comm_init");
   GLB_NCCL(g_nccl.AllReduce(d_vals, d_vals, n, NCCL_FLOAT64, NCCL_SUM, ctx->comm->nccl, ctx->stream));
   return GLB_OK;
 }

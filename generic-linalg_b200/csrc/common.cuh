@@ -146,6 +146,24 @@ __device__ __forceinline__ void stv(cplx* p, const cplx (&v)[SPT]) {
   }
 }
 
+// L2 prefetch of a contiguous byte range by the TMA unit (no registers, no completion tracking):
+// cp.async.bulk.prefetch.L2 (SASS UBLKPF).  addr 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// cp.async (LDGSTS): 16-byte global -> shared copies that bypass the register file; a per-thread
+// queue of commit groups gives deep prefetch without spending registers on staging.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // ------------------------------------------------------------------ warp shuffles of wide values
 __device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 __device__ __forceinline__ cplx shfl_up_c(cplx v, int d) {

@@ -36,8 +36,13 @@ struct NormArgs {
   const cplx* Ux;
   const cplx* Uy;
   const cplx* w;     // dot partner; nullptr = the input itself
-  int X, Y;
+  // slabs: the two input rows below / above the slab (already final values, never fused);
+  // nullptr on a single rank, where rows wrap periodically inside the slab
+  const cplx* g_lo;
+  const cplx* g_hi;
+  int X, Y;          // Y = rows of this slab
   double mass;
+  int pf_rows;  // L2 prefetch distance in rows (0 = off)
   ReduceWs red;
   CgState* cg;
   int cg_role;
@@ -85,8 +90,12 @@ struct NormLoad {  // everything fetched one row ahead: psi(y+2) (raw), U(y+1)
   cplx uy[2];
 };
 
-template <bool FUSE_XPAY, int NDOT>
+// STAGES == 0: the next row is prefetched into registers.  STAGES >= 2: every thread owns a ring of
+// STAGES slots in shared memory filled by cp.async (LDGSTS), STAGES-1 rows in flight per thread and no
+// staging registers -- bytes in flight no longer depend on the register-limited occupancy.
+template <bool FUSE_XPAY, int NDOT, int STAGES>
 __global__ void __launch_bounds__(NORM_THREADS) normal_kernel(const NormArgs a) {
+  extern __shared__ __align__(32) unsigned char ring_raw[];
   double beta = 0.0;
   if (a.cg != nullptr) {
     if (a.cg->done) return;
@@ -105,7 +114,10 @@ __global__ void __launch_bounds__(NORM_THREADS) normal_kernel(const NormArgs a) 
   const long long wid = (long long)blockIdx.x * NORM_WARPS + (threadIdx.x >> 5);
   const long long u_begin = units * wid / nwarps, u_end = units * (wid + 1) / nwarps;
 
+  const bool slab = (a.g_lo != nullptr);
   auto wrap_row = [&](int y) -> size_t { return (size_t)(((y % Y) + Y) % Y) * X; };
+  // links carry periodic ghost rows: U(.,y) is addressable for y in [-2, Y+2)
+  auto link_row = [&](int y) -> ptrdiff_t { return (ptrdiff_t)y * X; };
 
   long long u = u_begin;
   while (u < u_end) {
@@ -120,6 +132,10 @@ __global__ void __launch_bounds__(NORM_THREADS) normal_kernel(const NormArgs a) 
     const bool active = (lane >= 1) && (lane <= 30) && (xs < X);
 
     auto load_psi = [&](int y, cplx(&v)[2]) {  // the (possibly fused) input row y at this lane's pair
+      if (slab && (y < 0 || y >= Y)) {  // ghost rows hold final values
+        ldv<2>((y < 0 ? a.g_lo + (size_t)(y + 2) * X : a.g_hi + (size_t)(y - Y) * X) + x0, v);
+        return;
+      }
       const size_t o = wrap_row(y) + x0;
       if (FUSE_XPAY) {
         cplx rr[2], pp[2];
@@ -132,12 +148,19 @@ __global__ void __launch_bounds__(NORM_THREADS) normal_kernel(const NormArgs a) 
       }
     };
     auto fetch = [&](int y, NormLoad<FUSE_XPAY>& L) {  // for output row y: psi(y+2), U(y+1)
-      const size_t o2 = wrap_row(y + 2) + x0, o1 = wrap_row(y + 1) + x0;
-      if (FUSE_XPAY) {
-        ldv<2>(a.r + o2, L.a);
-        ldv<2>(a.pold + o2, L.b);
+      const ptrdiff_t o1 = link_row(y + 1) + x0;
+      if (slab && y + 2 >= Y) {  // ghost row above the slab: final values; b = 0 makes the fused form a no-op
+        ldv<2>(a.g_hi + (size_t)(y + 2 - Y) * X + x0, L.a);
+        L.b[0] = mk(0.0, 0.0);
+        L.b[1] = mk(0.0, 0.0);
       } else {
-        ldv<2>(a.in + o2, L.a);
+        const size_t o2 = wrap_row(y + 2) + x0;
+        if (FUSE_XPAY) {
+          ldv<2>(a.r + o2, L.a);
+          ldv<2>(a.pold + o2, L.b);
+        } else {
+          ldv<2>(a.in + o2, L.a);
+        }
       }
       ldv_nc<2>(a.Ux + o1, L.ux);
       ldv_nc<2>(a.Uy + o1, L.uy);
@@ -152,23 +175,103 @@ __global__ void __launch_bounds__(NORM_THREADS) normal_kernel(const NormArgs a) 
       load_psi(ya - 1, p_m);
       load_psi(ya, p_c);
       load_psi(ya + 1, p_n);
-      ldv_nc<2>(a.Uy + wrap_row(ya - 2) + x0, uy_mm);
-      ldv_nc<2>(a.Ux + wrap_row(ya - 1) + x0, ux_m);
-      ldv_nc<2>(a.Uy + wrap_row(ya - 1) + x0, uy_m);
-      ldv_nc<2>(a.Ux + wrap_row(ya) + x0, ux_c);
-      ldv_nc<2>(a.Uy + wrap_row(ya) + x0, uy_c);
+      ldv_nc<2>(a.Uy + link_row(ya - 2) + x0, uy_mm);
+      ldv_nc<2>(a.Ux + link_row(ya - 1) + x0, ux_m);
+      ldv_nc<2>(a.Uy + link_row(ya - 1) + x0, uy_m);
+      ldv_nc<2>(a.Ux + link_row(ya) + x0, ux_c);
+      ldv_nc<2>(a.Uy + link_row(ya) + x0, uy_c);
       const cplx uxl_m = shfl_up_c(ux_m[1], 1);
       uxl_c = shfl_up_c(ux_c[1], 1);
       stag_row<false>(t_m, p_mm, p_m, p_c, ux_m, uxl_m, uy_m, uy_mm, a.mass);  // t(ya-1)
       stag_row<false>(t_c, p_m, p_c, p_n, ux_c, uxl_c, uy_c, uy_m, a.mass);    // t(ya)
     }
+    constexpr int NARR = FUSE_XPAY ? 4 : 3;
+    auto slot = [&](int stage, int arr) -> cplx* {  // this thread's 32-byte slot
+      return reinterpret_cast<cplx*>(ring_raw) + ((size_t)(stage * NARR + arr) * NORM_THREADS + threadIdx.x) * 2;
+    };
+    auto issue = [&](int y) {  // asynchronous copies for output row y: psi(y+2), U(y+1); always one commit group
+      if (y < yb) {
+        const int st = y % (STAGES > 0 ? STAGES : 1);
+        const ptrdiff_t o1 = link_row(y + 1) + x0;
+        if (slab && y + 2 >= Y) {
+          const cplx* g = a.g_hi + (size_t)(y + 2 - Y) * X + x0;
+          cp_async16(slot(st, 0), g);
+          cp_async16(slot(st, 0) + 1, g + 1);
+          if (FUSE_XPAY) {
+            slot(st, 3)[0] = mk(0.0, 0.0);
+            slot(st, 3)[1] = mk(0.0, 0.0);
+          }
+        } else {
+          const size_t o2 = wrap_row(y + 2) + x0;
+          const cplx* pa = (FUSE_XPAY ? a.r : a.in) + o2;
+          cp_async16(slot(st, 0), pa);
+          cp_async16(slot(st, 0) + 1, pa + 1);
+          if (FUSE_XPAY) {
+            cp_async16(slot(st, 3), a.pold + o2);
+            cp_async16(slot(st, 3) + 1, a.pold + o2 + 1);
+          }
+        }
+        cp_async16(slot(st, 1), a.Ux + o1);
+        cp_async16(slot(st, 1) + 1, a.Ux + o1 + 1);
+        cp_async16(slot(st, 2), a.Uy + o1);
+        cp_async16(slot(st, 2) + 1, a.Uy + o1 + 1);
+      }
+      cp_async_commit();
+    };
     NormLoad<FUSE_XPAY> nxt;
-    fetch(ya, nxt);
+    if (STAGES == 0) {
+      fetch(ya, nxt);
+    } else {
+#pragma unroll
+      for (int k = 0; k < (STAGES > 0 ? STAGES - 1 : 0); k++) issue(ya + k);
+    }
+    // optional TMA L2 prefetch pf_rows steps ahead: one lane, one request per array (the part of the
+    // 64-site window that does not wrap around the x seam)
+    const int pf_x = (xs - 2 * lane < 0) ? 0 : xs - 2 * lane;
+    const int pf_w = min(X, xs - 2 * lane + 64) - pf_x;
+    auto prefetch_rows = [&](int y) {
+      if (lane == 0 && pf_w > 0) {
+        const unsigned bytes = (unsigned)pf_w * 16u;
+        if (!slab || y + 2 < Y) {
+          const size_t o2 = wrap_row(y + 2) + pf_x;
+          if (FUSE_XPAY) {
+            prefetch_l2_bulk(a.r + o2, bytes);
+            prefetch_l2_bulk(a.pold + o2, bytes);
+          } else {
+            prefetch_l2_bulk(a.in + o2, bytes);
+          }
+        }
+        if (y + 1 < Y + 2) {
+          prefetch_l2_bulk(a.Ux + link_row(y + 1) + pf_x, bytes);
+          prefetch_l2_bulk(a.Uy + link_row(y + 1) + pf_x, bytes);
+        }
+      }
+    };
+    if (a.pf_rows > 0)
+      for (int k = 1; k < a.pf_rows; k++) prefetch_rows(ya + k);
 
 #pragma unroll 1
     for (int y = ya; y < yb; y++) {
-      const NormLoad<FUSE_XPAY> cur = nxt;
-      if (y + 1 < yb) fetch(y + 1, nxt);  // prefetch while this row is computed
+      NormLoad<FUSE_XPAY> cur;
+      if (STAGES == 0) {
+        cur = nxt;
+        if (y + 1 < yb) fetch(y + 1, nxt);  // prefetch while this row is computed
+      } else {
+        issue(y + STAGES - 1);                           // keep STAGES-1 rows in flight
+        cp_async_wait<(STAGES > 0 ? STAGES - 1 : 0)>();  // the group of row y has landed
+        const int st = y % (STAGES > 0 ? STAGES : 1);
+        cur.a[0] = slot(st, 0)[0];
+        cur.a[1] = slot(st, 0)[1];
+        cur.ux[0] = slot(st, 1)[0];
+        cur.ux[1] = slot(st, 1)[1];
+        cur.uy[0] = slot(st, 2)[0];
+        cur.uy[1] = slot(st, 2)[1];
+        if (FUSE_XPAY) {
+          cur.b[0] = slot(st, 3)[0];
+          cur.b[1] = slot(st, 3)[1];
+        }
+      }
+      if (a.pf_rows > 0) prefetch_rows(y + a.pf_rows);
       cplx p_nn[2];
       if (FUSE_XPAY) {
         p_nn[0] = fadd(cur.a[0], fscale(beta, cur.b[0]));
@@ -213,6 +316,7 @@ __global__ void __launch_bounds__(NORM_THREADS) normal_kernel(const NormArgs a) 
       }
       uxl_c = uxl_n;
     }
+    if (STAGES > 0) cp_async_wait<0>();
   }
 
   if (NDOT > 0) {
@@ -222,18 +326,25 @@ __global__ void __launch_bounds__(NORM_THREADS) normal_kernel(const NormArgs a) 
         a.cg->pAp_re = total[0];
         a.cg->pAp_im = total[1];
         a.cg->rsq_old = a.cg->rsq_new;
+      } else if (a.cg != nullptr && a.cg_role == 2) {  // slab run: rank-local part, summed on the stream next
+        a.cg->partial[1] = total[0];
+        a.cg->partial[2] = total[1];
       }
     }
   }
 }
 
-template <bool FUSE, int NDOT>
+template <bool FUSE, int NDOT, int STAGES>
 static int launch_normal_t(glb_operator* op, const NormArgs& a) {
   glb_context* ctx = op->ctx;
-  auto kern = normal_kernel<FUSE, NDOT>;
+  auto kern = normal_kernel<FUSE, NDOT, STAGES>;
+  const size_t smem = (size_t)STAGES * (FUSE ? 4 : 3) * NORM_THREADS * 32;
   static int per_sm = 0;
   if (per_sm == 0) {
-    GLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NORM_THREADS, 0));
+    // static shared memory of the reduction epilogue rides on top of the dynamic ring
+    if (smem + 2048 > 48 * 1024)
+      GLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NORM_THREADS, smem));
     if (per_sm < 1) per_sm = 1;
   }
   const long long nstrips = (a.X + NORM_OUT_PER_WARP - 1) / NORM_OUT_PER_WARP;
@@ -243,20 +354,32 @@ static int launch_normal_t(glb_operator* op, const NormArgs& a) {
   if (blocks > max_useful) blocks = max_useful;
   if (blocks < 1) blocks = 1;
   if (blocks > MAX_PARTIAL_BLOCKS) blocks = MAX_PARTIAL_BLOCKS;
-  kern<<<(unsigned)blocks, NORM_THREADS, 0, ctx->stream>>>(a);
+  kern<<<(unsigned)blocks, NORM_THREADS, smem, ctx->stream>>>(a);
   GLB_LAUNCH_CHECK();
   return GLB_OK;
 }
 
-// can the one-pass kernel serve this operator?  (single rank, gauged, even X)
+template <int STAGES>
+static int launch_normal_s(glb_operator* op, const NormArgs& a, bool fuse, int ndot) {
+  if (fuse) {
+    if (ndot == 0) return launch_normal_t<true, 0, STAGES>(op, a);
+    if (ndot == 1) return launch_normal_t<true, 1, STAGES>(op, a);
+    return launch_normal_t<true, 2, STAGES>(op, a);
+  }
+  if (ndot == 0) return launch_normal_t<false, 0, STAGES>(op, a);
+  if (ndot == 1) return launch_normal_t<false, 1, STAGES>(op, a);
+  return launch_normal_t<false, 2, STAGES>(op, a);
+}
+
+// can the one-pass kernel serve this operator?  (gauged, even X; slabs at least two rows thick)
 bool normal_fused_ok(const glb_operator* op) {
   static int enabled = -1;
   if (enabled < 0) {
     const char* e = getenv("GLB_NORMAL_FUSED");
     enabled = (e && atoi(e) == 0) ? 0 : 1;
   }
-  return enabled && op->ctx->nranks == 1 && op->kind == OPK_STAGGERED && (op->flags & GLB_STAG_NORMAL) &&
-         op->has_links && (op->X % 2 == 0) && op->X >= 2;
+  return enabled && op->kind == OPK_STAGGERED && (op->flags & GLB_STAG_NORMAL) && op->has_links &&
+         (op->X % 2 == 0) && op->X >= 2 && (op->ctx->nranks == 1 || op->Yloc >= 2);
 }
 
 int launch_normal(glb_operator* op, void* out, const void* in, const ApplyFusion& f) {
@@ -275,21 +398,36 @@ int launch_normal(glb_operator* op, void* out, const void* in, const ApplyFusion
   a.Uy = op->Uy;
   a.w = f.w_is_input ? nullptr : (const cplx*)f.w;
   a.X = op->X;
-  a.Y = op->Y;
+  a.Y = op->Yloc;
+  if (ctx->nranks > 1) {
+    a.g_lo = (const cplx*)op->ghost_lo;
+    a.g_hi = (const cplx*)op->ghost_hi;
+  }
   a.mass = op->mass;
+  {
+    static int pf = -1;
+    if (pf < 0) {
+      const char* e = getenv("GLB_PF_L2");
+      pf = e ? atoi(e) : 0;  // measured: L2 bulk prefetch costs bandwidth here (profiles/), off by default
+    }
+    a.pf_rows = pf;
+  }
   a.red = ctx->red;
   if (!f.to_host) a.red.result_host = nullptr;
   a.cg = (CgState*)f.cg_state;
   a.cg_role = f.cg_role;
   const int ndot = (f.w != nullptr || f.w_is_input) ? (f.want_norm ? 2 : 1) : 0;
-  if (fuse) {
-    if (ndot == 0) return launch_normal_t<true, 0>(op, a);
-    if (ndot == 1) return launch_normal_t<true, 1>(op, a);
-    return launch_normal_t<true, 2>(op, a);
+  static int stages = -1;  // GLB_NORMAL_STAGES: 0 = register prefetch, 3/4/6 = cp.async ring depth
+  if (stages < 0) {
+    const char* e = getenv("GLB_NORMAL_STAGES");
+    stages = e ? atoi(e) : 0;
   }
-  if (ndot == 0) return launch_normal_t<false, 0>(op, a);
-  if (ndot == 1) return launch_normal_t<false, 1>(op, a);
-  return launch_normal_t<false, 2>(op, a);
+  switch (stages) {
+    case 3: return launch_normal_s<3>(op, a, fuse, ndot);
+    case 4: return launch_normal_s<4>(op, a, fuse, ndot);
+    case 6: return launch_normal_s<6>(op, a, fuse, ndot);
+    default: return launch_normal_s<0>(op, a, fuse, ndot);
+  }
 }
 
 }  // namespace glb

@@ -38,39 +38,52 @@ static int new_op(glb_context* ctx, int kind, int dtype, int X, int Y, int nc, g
 }
 
 static int alloc_ghosts(glb_operator* op, int depth) {
+  op->ghost_depth = depth;
   if (op->ctx->nranks == 1) return GLB_OK;
+  if (op->Yloc < depth) return fail(GLB_ERR_ARG, "slab thinner than the stencil reach: use fewer ranks");
   const size_t bytes = (size_t)depth * op->X * op->nc * elem_bytes(op->dtype);
   GLB_CUDA(cudaMalloc(&op->ghost_lo, bytes));
   GLB_CUDA(cudaMalloc(&op->ghost_hi, bytes));
+  GLB_CUDA(cudaMalloc(&op->send_lo, bytes));
+  GLB_CUDA(cudaMalloc(&op->send_hi, bytes));
   return GLB_OK;
 }
 
+// Link planes are stored with LINK_GHOST periodic ghost rows below and above the slab, so the
+// kernels address U(x, y) for y in [-LINK_GHOST, Yloc+LINK_GHOST) by plain pointer arithmetic
+// (single rank: wrapped copies of the slab's own rows; slabs: the neighbours' rows, static).
+// h_links is either the GLOBAL reference array lattice[y*X*2 + x*2 + mu], or (local = true) only
+// this rank's rows with the same ghost rows: rows y0-2 .. y0+Yloc+1, (Yloc+4)*X*2 complex.
 static int upload_links(glb_operator* op, const void* h_links, bool local = false) {
   glb_context* ctx = op->ctx;
-  const size_t X = op->X, Vloc = X * op->Yloc;
+  const int G = LINK_GHOST;
+  const size_t X = op->X, rows = (size_t)op->Yloc + 2 * G, n = X * rows;
   const cplx* h = (const cplx*)h_links;
   cplx* aos = nullptr;
-  GLB_CUDA(cudaMalloc(&aos, sizeof(cplx) * 2 * Vloc));
-  GLB_CUDA(cudaMalloc(&op->Ux, sizeof(cplx) * Vloc));
-  const bool single = (ctx->nranks == 1);
-  // Uy gets one extra leading row when the slab does not wrap onto itself
-  cplx* uy_store = nullptr;
-  GLB_CUDA(cudaMalloc(&uy_store, sizeof(cplx) * (Vloc + (single ? 0 : X))));
-  op->Uy = single ? uy_store : uy_store + X;
-  op->Uy_lo = single ? op->Uy + (size_t)(op->Yloc - 1) * X : uy_store;
-  // global array: this rank's rows start at y0; local array: row 0 is y0-1, the slab follows
-  const cplx* slab = local ? h + 2 * X : h + 2 * (size_t)op->y0 * X;
-  GLB_CUDA(cudaMemcpyAsync(aos, slab, sizeof(cplx) * 2 * Vloc, cudaMemcpyHostToDevice, ctx->stream));
-  const int grid = blas_grid(ctx, Vloc, 256, 4);
-  split_links_kernel<<<grid, 256, 0, ctx->stream>>>(aos, op->Ux, op->Uy, Vloc);
-  GLB_LAUNCH_CHECK();
-  if (!single) {  // U_y of global row y0-1 (periodic)
-    const int ym = (op->y0 + op->Y - 1) % op->Y;
-    std::vector<cplx> row(X);
-    for (size_t x = 0; x < X; x++) row[x] = local ? h[2 * x + 1] : h[2 * ((size_t)ym * X + x) + 1];
-    GLB_CUDA(cudaMemcpyAsync(uy_store, row.data(), sizeof(cplx) * X, cudaMemcpyHostToDevice, ctx->stream));
-    GLB_CUDA(cudaStreamSynchronize(ctx->stream));
+  GLB_CUDA(cudaMalloc(&aos, sizeof(cplx) * 2 * n));
+  GLB_CUDA(cudaMalloc(&op->Ux_store, sizeof(cplx) * n));
+  GLB_CUDA(cudaMalloc(&op->Uy_store, sizeof(cplx) * n));
+  op->Ux = op->Ux_store + (size_t)G * X;
+  op->Uy = op->Uy_store + (size_t)G * X;
+  op->Uy_lo = op->Uy - X;
+  if (local) {
+    GLB_CUDA(cudaMemcpyAsync(aos, h, sizeof(cplx) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    // slab rows in one copy, ghost rows one by one (periodic in the global lattice)
+    GLB_CUDA(cudaMemcpyAsync(aos + 2 * (size_t)G * X, h + 2 * (size_t)op->y0 * X, sizeof(cplx) * 2 * X * op->Yloc,
+                             cudaMemcpyHostToDevice, ctx->stream));
+    for (int g = 0; g < G; g++) {
+      const int ylo = ((op->y0 - G + g) % op->Y + op->Y) % op->Y;
+      const int yhi = (op->y0 + op->Yloc + g) % op->Y;
+      GLB_CUDA(cudaMemcpyAsync(aos + 2 * (size_t)g * X, h + 2 * (size_t)ylo * X, sizeof(cplx) * 2 * X,
+                               cudaMemcpyHostToDevice, ctx->stream));
+      GLB_CUDA(cudaMemcpyAsync(aos + 2 * ((size_t)G + op->Yloc + g) * X, h + 2 * (size_t)yhi * X, sizeof(cplx) * 2 * X,
+                               cudaMemcpyHostToDevice, ctx->stream));
+    }
   }
+  const int grid = blas_grid(ctx, n, 256, 4);
+  split_links_kernel<<<grid, 256, 0, ctx->stream>>>(aos, op->Ux_store, op->Uy_store, n);
+  GLB_LAUNCH_CHECK();
   GLB_CUDA(cudaStreamSynchronize(ctx->stream));
   GLB_CUDA(cudaFree(aos));
   op->has_links = true;
@@ -119,7 +132,7 @@ int glb_op_create_staggered(glb_context* ctx, const void* h_links, int X, int Y,
     if (rc) return rc;
   }
   if (flags & GLB_STAG_NORMAL) GLB_CUDA(cudaMalloc(&op->tmp, sizeof(cplx) * (size_t)X * op->Yloc));
-  return alloc_ghosts(op, 1);
+  return alloc_ghosts(op, 2);
 }
 
 int glb_op_create_staggered_local(glb_context* ctx, const void* h_links_local, int X, int Y, double mass,
@@ -135,7 +148,7 @@ int glb_op_create_staggered_local(glb_context* ctx, const void* h_links_local, i
   rc = upload_links(op, h_links_local, true);
   if (rc) return rc;
   if (flags & GLB_STAG_NORMAL) GLB_CUDA(cudaMalloc(&op->tmp, sizeof(cplx) * (size_t)X * op->Yloc));
-  return alloc_ghosts(op, 1);
+  return alloc_ghosts(op, 2);
 }
 
 int glb_op_create_gamma5(glb_context* ctx, int X, int Y, glb_operator** out) {
@@ -184,11 +197,13 @@ int glb_slab_bounds(glb_context* ctx, int Y, int* y0, int* Yloc) {
 int glb_op_destroy(glb_operator* op) {
   if (!op) return GLB_OK;
   cudaStreamSynchronize(op->ctx->stream);
-  cudaFree(op->Ux);
-  if (op->Uy) cudaFree(op->ctx->nranks == 1 ? op->Uy : op->Uy - op->X);
+  cudaFree(op->Ux_store);
+  cudaFree(op->Uy_store);
   cudaFree(op->tmp);
   cudaFree(op->ghost_lo);
   cudaFree(op->ghost_hi);
+  cudaFree(op->send_lo);
+  cudaFree(op->send_hi);
   cudaFree(op->clover);
   cudaFree(op->hopping);
   cudaFree(op->two_link);
@@ -232,40 +247,29 @@ namespace glb {
 // one operator application with optional fused reductions; halo rows exchanged first on slabs
 static int apply_impl(glb_operator* op, void* out, const void* in, const ApplyFusion& f) {
   glb_context* ctx = op->ctx;
-  const size_t row = (size_t)op->X * op->nc;
-  const int depth = (op->kind == OPK_STENCIL && op->has_two) ? 2 : 1;
   if (out == in) return fail(GLB_ERR_ARG, "apply: output must not alias input");
+  int rc;
   switch (op->kind) {
     case OPK_LAPLACE:
-      if (ctx->nranks > 1) {
-        int rc = halo_exchange(op, in, row, op->dtype);
-        if (rc) return rc;
-      }
+      if ((rc = halo_exchange(op, in, 1))) return rc;
       return launch_laplace(op, out, in, f);
     case OPK_GAMMA5:
       if (f.w || f.w_is_input) return fail(GLB_ERR_ARG, "gamma5 has no fused reductions");
       return launch_gamma5(op, out, in);
     case OPK_STENCIL:
-      if (ctx->nranks > 1) {
-        int rc = halo_exchange(op, in, row * depth, op->dtype);
-        if (rc) return rc;
-      }
+      if ((rc = halo_exchange(op, in, op->has_two ? 2 : 1))) return rc;
       return launch_stencil2d(op, out, in, f);
     case OPK_LAPLACE_U1:
     case OPK_STAGGERED: {
       if (op->flags & GLB_STAG_NORMAL) {  // operators.cpp:444-453 : tmp = D in ; out = D^dag tmp
-        if (normal_fused_ok(op)) return launch_normal(op, out, in, f);  // one pass, tmp stays on the SM
+        if (normal_fused_ok(op)) {        // one pass, tmp stays on the SM; slabs exchange two rows once
+          if ((rc = halo_exchange(op, in, 2))) return rc;
+          return launch_normal(op, out, in, f);
+        }
         ApplyFusion none;
-        if (ctx->nranks > 1) {
-          int rc = halo_exchange(op, in, row, op->dtype);
-          if (rc) return rc;
-        }
-        int rc = launch_staggered(op, op->tmp, in, false, none);
-        if (rc) return rc;
-        if (ctx->nranks > 1) {
-          rc = halo_exchange(op, op->tmp, row, op->dtype);
-          if (rc) return rc;
-        }
+        if ((rc = halo_exchange(op, in, 1))) return rc;
+        if ((rc = launch_staggered(op, op->tmp, in, false, none))) return rc;
+        if ((rc = halo_exchange(op, op->tmp, 1))) return rc;
         ApplyFusion g = f;
         if (g.w_is_input) {  // the dot partner is the ORIGINAL input, not tmp
           g.w_is_input = false;
@@ -273,13 +277,11 @@ static int apply_impl(glb_operator* op, void* out, const void* in, const ApplyFu
         }
         return launch_staggered(op, out, op->tmp, true, g);
       }
-      if (ctx->nranks > 1) {
-        int rc = halo_exchange(op, in, row, op->dtype);
-        if (rc) return rc;
-      }
+      if ((rc = halo_exchange(op, in, 1))) return rc;
       return launch_staggered(op, out, in, (op->flags & GLB_STAG_DAGGER) != 0, f);
     }
   }
+  (void)ctx;
   return fail(GLB_ERR_ARG, "unknown operator kind");
 }
 

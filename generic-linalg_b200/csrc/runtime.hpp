@@ -55,6 +55,8 @@ struct glb_context {
 
 namespace glb {
 
+constexpr int LINK_GHOST = 2;
+
 enum OpKind {
   OPK_LAPLACE = 0,      // free Laplacian, Nc colours, real or complex
   OPK_LAPLACE_U1 = 1,   // gauged Laplacian
@@ -77,14 +79,21 @@ struct glb_operator {
   unsigned flags = 0;
   bool has_links = false;
   // links as two site-major planes (SoA), slab-local, plus the U_y row below the slab
+  // Ux/Uy point at row 0 of the slab inside *_store, which carries LINK_GHOST periodic ghost rows
+  // below and above: U(x,y) is addressable for y in [-LINK_GHOST, Yloc+LINK_GHOST)
   glb::cplx* Ux = nullptr;
-  glb::cplx* Uy = nullptr;     // Yloc rows
-  glb::cplx* Uy_lo = nullptr;  // row y0-1 (points into Uy when single rank)
+  glb::cplx* Uy = nullptr;
+  glb::cplx* Uy_lo = nullptr;  // = Uy - X (row y0-1)
+  glb::cplx* Ux_store = nullptr;
+  glb::cplx* Uy_store = nullptr;
   // temporaries
   void* tmp = nullptr;         // for the normal operator
   // ghost rows for slab decomposition (rows y0-1 and y0+Yloc of the input), nc*X elements each
-  void* ghost_lo = nullptr;
-  void* ghost_hi = nullptr;
+  void* ghost_lo = nullptr;    // ghost_depth rows: y0-ghost_depth .. y0-1 (lowest first)
+  void* ghost_hi = nullptr;    // ghost_depth rows: y0+Yloc .. y0+Yloc+ghost_depth-1
+  int ghost_depth = 0;
+  void* send_lo = nullptr;     // staging for boundary rows produced on the fly (device CG)
+  void* send_hi = nullptr;
   // stencil data (slab-local, device)
   glb::cplx* clover = nullptr;
   glb::cplx* hopping = nullptr;   // 4 planes of nc*nc*Vloc
@@ -125,7 +134,10 @@ int launch_normal(glb_operator* op, void* out, const void* in, const ApplyFusion
 int launch_stencil2d(glb_operator* op, void* out, const void* in, const ApplyFusion& f);
 
 // comm.cu : fills op->ghost_lo / ghost_hi from the neighbouring ranks' boundary rows of `in`
-int halo_exchange(glb_operator* op, const void* in, size_t row_elems, int dtype);
+int halo_exchange(glb_operator* op, const void* in, int nrows);
+// same, boundary rows taken from explicit buffers (nrows lowest rows in send_lo, nrows highest in send_hi)
+int halo_exchange_ptrs(glb_operator* op, const void* send_lo, const void* send_hi, int nrows);
+int allreduce_device(glb_context* ctx, double* d_vals, int n);
 int allreduce_sum(glb_context* ctx, double* host_vals, int n);
 void comm_destroy(glb_context* ctx);
 

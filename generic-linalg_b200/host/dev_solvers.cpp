@@ -76,7 +76,7 @@ inversion_info cg_dev(T* x, T* b, int size, int max_iter, double eps, void (*fn)
   int k;
   T* Ap = W.get();
 
-  if (A.native && !g_force_host_scalars && glb_comm_size(A.ctx) == 1 && max_iter >= 1) {
+  if (A.native && !g_force_host_scalars && glb_cg_solve_supported(A.native) && max_iter >= 1) {
     // device-resident loop: alpha, beta and the stopping test never leave the GPU
     std::vector<double> hist;
     const bool detail = (verb != 0 && verb->verbosity == VERB_DETAIL);

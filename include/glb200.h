@@ -116,9 +116,9 @@ int glb_op_create_laplace_u1(glb_context* ctx, const void* h_links, int X, int Y
 /* 2-D staggered operator; h_links == NULL gives the free operator (operators.cpp:127,262). */
 int glb_op_create_staggered(glb_context* ctx, const void* h_links, int X, int Y, double mass, unsigned flags,
                             glb_operator** op);
-/* Same, but the host array holds only THIS RANK's rows preceded by the row below the slab:
- * rows y0-1, y0, ..., y0+Yloc-1 (periodic), i.e. (Yloc+1)*X*2 complex numbers.  Lets a multi-GPU
- * job build its slabs without any rank ever holding the global gauge field. */
+/* Same, but the host array holds only THIS RANK's rows plus two ghost rows on each side:
+ * rows y0-2, y0-1, y0, ..., y0+Yloc-1, y0+Yloc, y0+Yloc+1 (periodic), i.e. (Yloc+4)*X*2 complex
+ * numbers.  Lets a multi-GPU job build its slabs without any rank ever holding the global field. */
 int glb_op_create_staggered_local(glb_context* ctx, const void* h_links_local, int X, int Y, double mass,
                                   unsigned flags, glb_operator** op);
 /* rows [y0, y0+Yloc) this rank owns of a Y-row lattice */
@@ -207,6 +207,9 @@ typedef struct glb_cg_report {
   double rsq;          /* last recurrence |r|^2 */
   double bnorm;        /* sqrt(|b|^2) */
 } glb_cg_report;
+/* 1 if glb_cg_solve can run this operator on this context (always on one rank; on slabs the
+ * one-pass D^dag D staggered operator), else the host-scalar shell must be used */
+int glb_cg_solve_supported(const glb_operator* op);
 int glb_cg_solve(glb_operator* op, void* d_x, const void* d_b, int max_iter, double eps, glb_cg_report* rep,
                  double* rsq_hist, int hist_cap);
 

@@ -62,7 +62,7 @@ def main():
         got = gather(op.apply_host(b[sl]))
         want = orc.op(kind, X, Y, mass=0.1, links=U).apply(b)
         check("apply %s" % kind, np.array_equal(got, want), "max diff %.1e" % np.abs(got - want).max())
-    rows = [(y0 - 1 + Y) % Y] + list(range(y0, y0 + Yloc))
+    rows = [(y0 - 2 + Y) % Y, (y0 - 1 + Y) % Y] + list(range(y0, y0 + Yloc)) + [(y0 + Yloc) % Y, (y0 + Yloc + 1) % Y]
     Uloc = U.reshape(Y, 2 * X)[rows].reshape(-1)
     got = gather(ctx.staggered_local(Uloc, X, Y, 0.1, 0).apply_host(b[sl]))
     check("apply STAG_U1 (slab-local links)", np.array_equal(got, orc.op("STAG_U1", X, Y, mass=0.1, links=U).apply(b)))
