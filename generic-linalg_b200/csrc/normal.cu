@@ -43,6 +43,7 @@ struct NormArgs {
   int X, Y;          // Y = rows of this slab
   double mass;
   int pf_rows;  // L2 prefetch distance in rows (0 = off)
+  int nrb;      // row blocks: work item i -> strip i % nstrips, rows [Y*rb/nrb, Y*(rb+1)/nrb), rb = i / nstrips
   ReduceWs red;
   CgState* cg;
   int cg_role;
@@ -109,22 +110,24 @@ __global__ void __launch_bounds__(NORM_THREADS) normal_kernel(const NormArgs a) 
   const int lane = threadIdx.x & 31;
   const int X = a.X, Y = a.Y;
   const int nstrips = (X + NORM_OUT_PER_WARP - 1) / NORM_OUT_PER_WARP;
-  const long long units = (long long)nstrips * Y;
+  // Work items are laid out so that the warps of a block (and neighbouring blocks) sweep ADJACENT
+  // strips over the SAME rows at the same time: the 2-site overlaps then hit L1/L2 instead of DRAM
+  // and the chip streams whole contiguous rows (DRAM page locality), like a 2-D tiled sweep.
+  const long long nitems = (long long)nstrips * a.nrb;
   const long long nwarps = (long long)gridDim.x * NORM_WARPS;
   const long long wid = (long long)blockIdx.x * NORM_WARPS + (threadIdx.x >> 5);
-  const long long u_begin = units * wid / nwarps, u_end = units * (wid + 1) / nwarps;
 
-  const bool slab = (a.g_lo != nullptr);
   auto wrap_row = [&](int y) -> size_t { return (size_t)(((y % Y) + Y) % Y) * X; };
+  const bool slab = (a.g_lo != nullptr);
   // links carry periodic ghost rows: U(.,y) is addressable for y in [-2, Y+2)
   auto link_row = [&](int y) -> ptrdiff_t { return (ptrdiff_t)y * X; };
 
-  long long u = u_begin;
-  while (u < u_end) {
-    const int strip = (int)(u / Y);
-    const int ya = (int)(u - (long long)strip * Y);
-    const int yb = (int)min((long long)Y, (long long)ya + (u_end - u));
-    u += (yb - ya);
+  for (long long item = wid; item < nitems; item += nwarps) {
+    const int strip = (int)(item % nstrips);
+    const int rb = (int)(item / nstrips);
+    const int ya = (int)((long long)Y * rb / a.nrb);
+    const int yb = (int)((long long)Y * (rb + 1) / a.nrb);
+    if (ya >= yb) continue;
 
     // this lane's pair of sites (periodic in x; pairs never straddle the seam because X is even)
     const int xs = strip * NORM_OUT_PER_WARP - 2 + 2 * lane;
@@ -348,13 +351,19 @@ static int launch_normal_t(glb_operator* op, const NormArgs& a) {
     if (per_sm < 1) per_sm = 1;
   }
   const long long nstrips = (a.X + NORM_OUT_PER_WARP - 1) / NORM_OUT_PER_WARP;
-  const long long units = nstrips * a.Y;
-  long long blocks = (long long)ctx->sm_count * per_sm;
-  const long long max_useful = (units + 8 * NORM_WARPS - 1) / (8 * NORM_WARPS);  // >= 8 rows per warp: 4 halo rows each
-  if (blocks > max_useful) blocks = max_useful;
+  const long long max_warps = (long long)ctx->sm_count * per_sm * NORM_WARPS;
+  // row blocks: as many as there are warps to fill, but at least 8 rows each (4 halo rows per item)
+  long long nrb = max_warps / nstrips;
+  const long long nrb_cap = a.Y >= 16 ? a.Y / 8 : 1;
+  if (nrb > nrb_cap) nrb = nrb_cap;
+  if (nrb < 1) nrb = 1;
+  NormArgs b = a;
+  b.nrb = (int)nrb;
+  long long blocks = (nstrips * nrb + NORM_WARPS - 1) / NORM_WARPS;
+  if (blocks > (long long)ctx->sm_count * per_sm) blocks = (long long)ctx->sm_count * per_sm;
   if (blocks < 1) blocks = 1;
   if (blocks > MAX_PARTIAL_BLOCKS) blocks = MAX_PARTIAL_BLOCKS;
-  kern<<<(unsigned)blocks, NORM_THREADS, smem, ctx->stream>>>(a);
+  kern<<<(unsigned)blocks, NORM_THREADS, smem, ctx->stream>>>(b);
   GLB_LAUNCH_CHECK();
   return GLB_OK;
 }

@@ -57,6 +57,7 @@ struct StagArgs {
   CgState* cg;
   int cg_role;   // 1: epilogue publishes <p,Ap> into the CG state
   int pf_rows;   // L2 prefetch distance in rows (0 = off)
+  int nrb;       // number of row blocks per strip
 };
 
 enum { FAM_STAGGERED = 0, FAM_LAPLACE_U1 = 1 };
@@ -79,9 +80,10 @@ __global__ void __launch_bounds__(STAG_THREADS) stag_kernel(const StagArgs a) {
   const int lane = threadIdx.x & 31;
   const int strip_w = STAG_THREADS * SPT;
   const int nstrips = (a.X + strip_w - 1) / strip_w;
-  const long long units = (long long)nstrips * a.Yloc;
-  const long long u_begin = units * blockIdx.x / gridDim.x;
-  const long long u_end = units * (blockIdx.x + 1) / gridDim.x;
+  // work item i -> strip i % nstrips, row block i / nstrips: neighbouring blocks sweep neighbouring
+  // strips over the same rows at the same time (whole lattice rows stream through DRAM and the
+  // edge-lane loads of a block hit lines its neighbours fetch)
+  const long long nitems = (long long)nstrips * a.nrb;
 
   constexpr int NRED = (NDOT == 0) ? 1 : (NDOT == 1 ? 2 : 3);
   double acc[NRED];
@@ -103,12 +105,12 @@ __global__ void __launch_bounds__(STAG_THREADS) stag_kernel(const StagArgs a) {
     }
   };
 
-  long long u = u_begin;
-  while (u < u_end) {
-    const int strip = (int)(u / Yloc);
-    const int ya = (int)(u - (long long)strip * Yloc);
-    const int yb = (int)min((long long)Yloc, (long long)ya + (u_end - u));
-    u += (yb - ya);
+  for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int strip = (int)(item % nstrips);
+    const int rb = (int)(item / nstrips);
+    const int ya = (int)((long long)Yloc * rb / a.nrb);
+    const int yb = (int)((long long)Yloc * (rb + 1) / a.nrb);
+    if (ya >= yb) continue;
 
     int x0 = strip * strip_w + threadIdx.x * SPT;
     const bool active = x0 < X;
@@ -387,14 +389,19 @@ static int launch_stag_t(glb_operator* op, const StagArgs& a) {
   }
   const int strip_w = STAG_THREADS * SPT;
   const long long nstrips = (a.X + strip_w - 1) / strip_w;
-  const long long units = nstrips * a.Yloc;
-  long long blocks = (long long)ctx->sm_count * per_sm;
-  // at least 4 rows per block so the halo re-reads stay small on little lattices
-  const long long max_useful = (units + 3) / 4;
-  if (blocks > max_useful) blocks = max_useful;
+  const long long cap = (long long)ctx->sm_count * per_sm;
+  // row blocks: enough to fill the resident grid, at least 4 rows each (2 halo rows per item)
+  long long nrb = cap / nstrips;
+  const long long nrb_cap = a.Yloc >= 8 ? a.Yloc / 4 : 1;
+  if (nrb > nrb_cap) nrb = nrb_cap;
+  if (nrb < 1) nrb = 1;
+  StagArgs b = a;
+  b.nrb = (int)nrb;
+  long long blocks = nstrips * nrb;
+  if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   if (blocks > MAX_PARTIAL_BLOCKS) blocks = MAX_PARTIAL_BLOCKS;
-  kern<<<(unsigned)blocks, STAG_THREADS, 0, ctx->stream>>>(a);
+  kern<<<(unsigned)blocks, STAG_THREADS, 0, ctx->stream>>>(b);
   GLB_LAUNCH_CHECK();
   return GLB_OK;
 }
