@@ -241,6 +241,33 @@ def main():
     x = ctx.vector(V_local)
     ctx.sync()
 
+    # ---- roofline leg: the staggered D apply kernel alone, events on the library's stream
+    out = ctx.vector(V_local)
+    stream_evt = stream
+    for _ in range(5):
+        opD.apply(out, b)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.apply_reps):
+        opD.apply(out, b)
+    e1.record(stream)
+    barrier()
+    apply_ms = max_over_ranks(e0.elapsed_time(e1)) / args.apply_reps
+    apply_gbps = 64.0 * V_local / (apply_ms * 1e-3) / 1e9          # per GPU: 16 psi + 32 links + 16 out
+    # the one-pass D^dag D kernel (the CG's dominant kernel without the fused direction update): 64 B/site
+    for _ in range(3):
+        opN.apply(out, b)
+    barrier()
+    n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0.record(stream)
+    for _ in range(args.apply_reps):
+        opN.apply(out, b)
+    n1.record(stream)
+    barrier()
+    normal_ms = max_over_ranks(n0.elapsed_time(n1)) / args.apply_reps
+    normal_gbps = 64.0 * V_local / (normal_ms * 1e-3) / 1e9
+
     def solve_resident():
         x.zero()
         return ctx.solve("CG", opN, x, bp, max_iter=100000, eps=TOL)
@@ -272,31 +299,6 @@ def main():
     true_rel = float(np.sqrt(info["resSq"]))  # |b - A x| (absolute); made relative below
     bnorm = float(np.sqrt(ctx.norm2sq(bp)))
 
-    # ---- roofline leg: the staggered D apply kernel alone, events on the library's stream
-    out = ctx.vector(V_local)
-    for _ in range(5):
-        opD.apply(out, b)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.apply_reps):
-        opD.apply(out, b)
-    e1.record(stream)
-    barrier()
-    apply_ms = max_over_ranks(e0.elapsed_time(e1)) / args.apply_reps
-    apply_gbps = 64.0 * V_local / (apply_ms * 1e-3) / 1e9          # per GPU: 16 psi + 32 links + 16 out
-    # the one-pass D^dag D kernel (the CG's dominant kernel without the fused direction update): 64 B/site
-    for _ in range(3):
-        opN.apply(out, b)
-    barrier()
-    n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n0.record(stream)
-    for _ in range(args.apply_reps):
-        opN.apply(out, b)
-    n1.record(stream)
-    barrier()
-    normal_ms = max_over_ranks(n0.elapsed_time(n1)) / args.apply_reps
-    normal_gbps = 64.0 * V_local / (normal_ms * 1e-3) / 1e9
     sampler.stop_flag = True
     sampler.join(timeout=2)
 

@@ -426,11 +426,16 @@ int launch_normal(glb_operator* op, void* out, const void* in, const ApplyFusion
   a.cg = (CgState*)f.cg_state;
   a.cg_role = f.cg_role;
   const int ndot = (f.w != nullptr || f.w_is_input) ? (f.want_norm ? 2 : 1) : 0;
-  static int stages = -1;  // GLB_NORMAL_STAGES: 0 = register prefetch, 3/4/6 = cp.async ring depth
-  if (stages < 0) {
+  // ring depth (measured at 4096^2, profiles/): the fused-direction variant streams 4 arrays and gains
+  // ~8 % from a 4-deep cp.async ring; the plain variant (3 arrays) is best with register prefetch.
+  static int stages_fused = -1, stages_plain = -1;
+  if (stages_fused < 0) {
     const char* e = getenv("GLB_NORMAL_STAGES");
-    stages = e ? atoi(e) : 0;
+    stages_fused = e ? atoi(e) : 4;
+    const char* e2 = getenv("GLB_NORMAL_STAGES_PLAIN");
+    stages_plain = e2 ? atoi(e2) : 0;
   }
+  const int stages = fuse ? stages_fused : stages_plain;
   switch (stages) {
     case 3: return launch_normal_s<3>(op, a, fuse, ndot);
     case 4: return launch_normal_s<4>(op, a, fuse, ndot);

@@ -105,12 +105,26 @@ __global__ void __launch_bounds__(STAG_THREADS) stag_kernel(const StagArgs a) {
     }
   };
 
-  for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
-    const int strip = (int)(item % nstrips);
-    const int rb = (int)(item / nstrips);
-    const int ya = (int)((long long)Yloc * rb / a.nrb);
-    const int yb = (int)((long long)Yloc * (rb + 1) / a.nrb);
-    if (ya >= yb) continue;
+  // a.nrb == 0 selects the alternative partition: one contiguous run of (strip,row) units per block
+  const bool lockstep = a.nrb > 0;
+  const long long units = (long long)nstrips * Yloc;
+  const long long u_end = lockstep ? nitems : units * (blockIdx.x + 1) / gridDim.x;
+  long long it = lockstep ? (long long)blockIdx.x : units * blockIdx.x / gridDim.x;
+  while (it < u_end) {
+    int strip, ya, yb;
+    if (lockstep) {
+      strip = (int)(it % nstrips);
+      const int rb = (int)(it / nstrips);
+      ya = (int)((long long)Yloc * rb / a.nrb);
+      yb = (int)((long long)Yloc * (rb + 1) / a.nrb);
+      it += gridDim.x;
+      if (ya >= yb) continue;
+    } else {
+      strip = (int)(it / Yloc);
+      ya = (int)(it - (long long)strip * Yloc);
+      yb = (int)min((long long)Yloc, (long long)ya + (u_end - it));
+      it += (yb - ya);
+    }
 
     int x0 = strip * strip_w + threadIdx.x * SPT;
     const bool active = x0 < X;
@@ -396,8 +410,9 @@ static int launch_stag_t(glb_operator* op, const StagArgs& a) {
   if (nrb > nrb_cap) nrb = nrb_cap;
   if (nrb < 1) nrb = 1;
   StagArgs b = a;
-  b.nrb = (int)nrb;
-  long long blocks = nstrips * nrb;
+  static int lockstep = env_int("GLB_STAG_LOCKSTEP", 1);
+  b.nrb = lockstep ? (int)nrb : 0;
+  long long blocks = lockstep ? nstrips * nrb : (nstrips * a.Yloc + 3) / 4;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   if (blocks > MAX_PARTIAL_BLOCKS) blocks = MAX_PARTIAL_BLOCKS;
