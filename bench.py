@@ -270,7 +270,7 @@ def main():
 
     def solve_resident():
         x.zero()
-        return ctx.solve("CG", opN, x, bp, max_iter=100000, eps=TOL)
+        return ctx.solve("CG", opN, x, bp, max_iter=5000, eps=TOL)
 
     # ---- warm-up, then exactly K timed steps bracketed by barrier + synchronize
     for _ in range(args.warmup):
@@ -312,13 +312,13 @@ def main():
 
         def solve_e2e():
             hx[:] = 0
-            return ctx.host_solve("CG", desc, hx, hb, max_iter=100000, eps=TOL)
+            return ctx.host_solve("CG", desc, hx, hb, max_iter=5000, eps=TOL)
     else:
         def solve_e2e():   # slab runs: same copies, device-level call (the host-vector entry point is single-rank)
             hx[:] = 0
             x.upload(hx)
             bp.upload(hb)
-            r = ctx.solve("CG", opN, x, bp, max_iter=100000, eps=TOL)
+            r = ctx.solve("CG", opN, x, bp, max_iter=5000, eps=TOL)
             x.download(hx)
             return r
     for _ in range(2):

@@ -23,7 +23,7 @@ STAG_DAGGER, STAG_GAMMA5, STAG_NORMAL = 1, 2, 4
 # operator / solver selectors of host/capi_solvers.cpp (same numbering as oracle/oracle_api.h)
 OP = dict(LAPLACE_REAL=0, LAPLACE_IMAG=1, LAPLACE_NC=2, LAPLACE_U1=3, STAG_FREE=4, STAG_U1=5,
           STAG_GAMMA5_U1=6, STAG_DAGGER_U1=7, STAG_NORMAL_U1=8, GAMMA5=9, STENCIL=10,
-          STENCIL_FROM_STAG=11, STAG_GAMMA5_FREE=12, LAPLACE_REAL_NC=13)
+          STENCIL_FROM_STAG=11, STAG_GAMMA5_FREE=12, LAPLACE_REAL_NC=13, STAG_FREE_REAL=14)
 SOLVER = dict(CG=0, CG_RESTART=1, CR=2, CR_RESTART=3, GCR=4, GCR_RESTART=5, BICGSTAB=6,
               BICGSTAB_RESTART=7, BICGSTAB_L=8, BICGSTAB_L_RESTART=9, GMRES=10, GMRES_RESTART=11)
 
@@ -86,6 +86,7 @@ def libs():
         "glb_host_alloc": (ci, [vp, sz, C.POINTER(vp)]), "glb_host_free": (ci, [vp, vp]),
         "glb_op_create_laplace": (ci, [vp, ci, ci, ci, ci, cd, cd, C.POINTER(vp)]),
         "glb_op_create_laplace_u1": (ci, [vp, vp, ci, ci, cd, C.POINTER(vp)]),
+        "glb_op_create_staggered_free_real": (ci, [vp, ci, ci, cd, C.POINTER(vp)]),
         "glb_op_create_staggered": (ci, [vp, vp, ci, ci, cd, C.c_uint, C.POINTER(vp)]),
         "glb_op_create_staggered_local": (ci, [vp, vp, ci, ci, cd, C.c_uint, C.POINTER(vp)]),
         "glb_slab_bounds": (ci, [vp, ci, C.POINTER(ci), C.POINTER(ci)]),
@@ -324,6 +325,9 @@ class Context:
     def laplace(self, X, Y, Nc=1, diag=4.01, dtype=np.float64):
         diag = complex(diag)
         return self._op(self.cu.glb_op_create_laplace, _dt(dtype), X, Y, Nc, diag.real, diag.imag)
+
+    def staggered_free_real(self, X, Y, mass):
+        return self._op(self.cu.glb_op_create_staggered_free_real, X, Y, mass)
 
     def laplace_u1(self, links, X, Y, mass):
         links = np.ascontiguousarray(links, dtype=np.complex128)

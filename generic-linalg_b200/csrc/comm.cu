@@ -89,9 +89,11 @@ int halo_exchange_ptrs(glb_operator* op, const void* send_lo, const void* send_h
   // my lowest rows -> `down`'s ghost_hi (its rows Yloc ..) ; my highest rows -> `up`'s ghost_lo (its rows -nrows .. -1)
   char* recv_lo = (char*)op->ghost_lo + rowb * (op->ghost_depth - nrows);
   char* recv_hi = (char*)op->ghost_hi;
+  // Order matters on 2 ranks, where `up` and `down` are the same peer and NCCL pairs the k-th send
+  // with the peer's k-th receive: (hi -> up) must meet the peer's (ghost_lo <- down).
   GLB_NCCL(g_nccl.GroupStart());
-  GLB_NCCL(g_nccl.Send(send_lo, bytes, NCCL_CHAR, down, ctx->comm->nccl, ctx->stream));
   GLB_NCCL(g_nccl.Send(send_hi, bytes, NCCL_CHAR, up, ctx->comm->nccl, ctx->stream));
+  GLB_NCCL(g_nccl.Send(send_lo, bytes, NCCL_CHAR, down, ctx->comm->nccl, ctx->stream));
   GLB_NCCL(g_nccl.Recv(recv_lo, bytes, NCCL_CHAR, down, ctx->comm->nccl, ctx->stream));
   GLB_NCCL(g_nccl.Recv(recv_hi, bytes, NCCL_CHAR, up, ctx->comm->nccl, ctx->stream));
   GLB_NCCL(g_nccl.GroupEnd());

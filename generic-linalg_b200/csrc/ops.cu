@@ -107,6 +107,18 @@ int glb_op_create_laplace(glb_context* ctx, int dtype, int X, int Y, int Nc, dou
   return alloc_ghosts(*out, 1);
 }
 
+// real free staggered operator of tests/multishift/multishift.cpp:677 (served by the simple
+// nearest-neighbour kernel; flag 0x100 selects the staggered signs, diag carries the mass)
+int glb_op_create_staggered_free_real(glb_context* ctx, int X, int Y, double mass, glb_operator** out) {
+  int rc = new_op(ctx, OPK_LAPLACE, GLB_REAL, X, Y, 1, out);
+  if (rc) return rc;
+  (*out)->diag_re = mass;
+  (*out)->diag_im = 0.0;
+  (*out)->mass = mass;
+  (*out)->flags = 0x100u;
+  return alloc_ghosts(*out, 1);
+}
+
 int glb_op_create_laplace_u1(glb_context* ctx, const void* h_links, int X, int Y, double mass, glb_operator** out) {
   if (!h_links) return fail(GLB_ERR_ARG, "gauged Laplacian needs links");
   int rc = new_op(ctx, OPK_LAPLACE_U1, GLB_COMPLEX, X, Y, 1, out);
@@ -213,6 +225,7 @@ int glb_op_destroy(glb_operator* op) {
 
 int glb_op_set_mass(glb_operator* op, double mass) {
   op->mass = mass;
+  if (op->kind == OPK_LAPLACE && (op->flags & 0x100u)) op->diag_re = mass;
   return GLB_OK;
 }
 int glb_op_dtype(const glb_operator* op) { return op->dtype; }

@@ -321,6 +321,7 @@ struct LapArgs {
   const T* w;
   int X, Yloc, Nc;
   T diag;
+  int stag_free;  // 1: free staggered stencil (tests/multishift/multishift.cpp:677), diag carries the mass
   ReduceWs red;
   CgState* cg;
   int cg_role;
@@ -345,12 +346,22 @@ __global__ void __launch_bounds__(256) laplace_kernel(const LapArgs<T> a) {
     const T* rowp = (y + 1 >= a.Yloc) ? a.in_hi : row + RX;
     const T* rowm = (y == 0) ? a.in_lo : row - RX;
     T h = Field<T>::zero();
-    h = fsub(h, row[ep]);   // + e1
-    h = fsub(h, row[em]);   // - e1
-    h = fsub(h, rowp[e]);   // + e2
-    h = fsub(h, rowm[e]);   // - e2
     const T self = row[e];
-    const T res = fadd(h, fmul(a.diag, self));
+    T res;
+    if (a.stag_free) {  // -(x+1) + (x-1) - eta (y+1) + eta (y-1), halved, + m*self ; eta = (-1)^x
+      const bool eta_neg = ((e / a.Nc) & 1);
+      h = fsub(h, row[ep]);
+      h = fadd(h, row[em]);
+      h = eta_neg ? fadd(h, rowp[e]) : fsub(h, rowp[e]);
+      h = eta_neg ? fsub(h, rowm[e]) : fadd(h, rowm[e]);
+      res = fadd(fscale(0.5, h), fmul(a.diag, self));
+    } else {
+      h = fsub(h, row[ep]);   // + e1
+      h = fsub(h, row[em]);   // - e1
+      h = fsub(h, rowp[e]);   // + e2
+      h = fsub(h, rowm[e]);   // - e2
+      res = fadd(h, fmul(a.diag, self));
+    }
     a.out[i] = res;
     if (NDOT >= 1) {
       const T wv = (a.w == nullptr) ? self : a.w[i];
@@ -523,6 +534,7 @@ static int launch_laplace_t(glb_operator* op, void* out, const void* in, const A
   a.Yloc = op->Yloc;
   a.Nc = op->nc;
   a.diag = diag;
+  a.stag_free = (op->flags & 0x100u) ? 1 : 0;
   a.red = ctx->red;
   if (!f.to_host) a.red.result_host = nullptr;
   a.cg = (CgState*)f.cg_state;

@@ -27,7 +27,7 @@ typedef struct glbx_result {
 enum {
   GX_LAPLACE_REAL = 0, GX_LAPLACE_IMAG = 1, GX_LAPLACE_NC = 2, GX_LAPLACE_U1 = 3, GX_STAG_FREE = 4, GX_STAG_U1 = 5,
   GX_STAG_GAMMA5_U1 = 6, GX_STAG_DAGGER_U1 = 7, GX_STAG_NORMAL_U1 = 8, GX_GAMMA5 = 9, GX_STENCIL = 10,
-  GX_STENCIL_FROM_STAG = 11, GX_STAG_GAMMA5_FREE = 12, GX_LAPLACE_REAL_NC = 13
+  GX_STENCIL_FROM_STAG = 11, GX_STAG_GAMMA5_FREE = 12, GX_LAPLACE_REAL_NC = 13, GX_STAG_FREE_REAL = 14
 };
 enum {
   GX_CG = 0, GX_CG_RESTART = 1, GX_CR = 2, GX_CR_RESTART = 3, GX_GCR = 4, GX_GCR_RESTART = 5, GX_BICGSTAB = 6,
@@ -102,6 +102,7 @@ bool build_host_op(const glbx_opdesc* d, HostOp* h) {
     case GX_LAPLACE_IMAG: h->cz = &square_laplacian; h->extra = &h->lap; break;
     case GX_LAPLACE_NC: h->cz = &square_laplace; h->size *= h->stag.Nc; break;
     case GX_LAPLACE_REAL_NC: h->cd = &square_laplace; h->size *= h->stag.Nc; break;
+    case GX_STAG_FREE_REAL: h->cd = &square_staggered; break;
     case GX_LAPLACE_U1: h->cz = &square_laplace_u1; break;
     case GX_STAG_FREE: h->cz = &square_staggered; break;
     case GX_STAG_U1: h->cz = &square_staggered_u1; break;

@@ -26,7 +26,7 @@ bool g_cache_ops = false;
 
 enum Builtin {
   B_NONE = 0, B_LAPLACE_NC, B_LAPLACE_NC_REAL, B_LAPLACE_U1, B_STAG_FREE, B_STAG_U1, B_GAMMA5, B_STAG_G5_FREE,
-  B_STAG_G5_U1, B_STAG_DAGGER_U1, B_STAG_NORMAL_U1, B_LAPLACIAN_REAL, B_LAPLACIAN_IMAG, B_STENCIL
+  B_STAG_G5_U1, B_STAG_DAGGER_U1, B_STAG_NORMAL_U1, B_LAPLACIAN_REAL, B_LAPLACIAN_IMAG, B_STENCIL, B_STAG_FREE_REAL
 };
 
 Builtin classify(void (*fn)(zcplx*, zcplx*, void*)) {
@@ -48,6 +48,7 @@ Builtin classify(void (*fn)(double*, double*, void*)) {
   typedef void (*F)(double*, double*, void*);
   if (fn == (F)&square_laplace) return B_LAPLACE_NC_REAL;
   if (fn == (F)&square_laplacian) return B_LAPLACIAN_REAL;
+  if (fn == (F)&square_staggered) return B_STAG_FREE_REAL;
   return B_NONE;
 }
 
@@ -62,6 +63,7 @@ glb_operator* build(Builtin kind, void* extra) {
     case B_LAPLACE_NC_REAL:
       GLBX(glb_op_create_laplace(ctx, GLB_REAL, s->x_fine, s->y_fine, s->Nc, 4 + s->mass, 0.0, &op));
       break;
+    case B_STAG_FREE_REAL: GLBX(glb_op_create_staggered_free_real(ctx, s->x_fine, s->y_fine, s->mass, &op)); break;
     case B_LAPLACE_U1: GLBX(glb_op_create_laplace_u1(ctx, s->lattice, s->x_fine, s->y_fine, s->mass, &op)); break;
     case B_STAG_FREE: GLBX(glb_op_create_staggered(ctx, 0, s->x_fine, s->y_fine, s->mass, 0, &op)); break;
     case B_STAG_U1: GLBX(glb_op_create_staggered(ctx, s->lattice, s->x_fine, s->y_fine, s->mass, 0, &op)); break;
@@ -288,6 +290,7 @@ void square_laplace(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_LAP
 void square_laplace(double* lhs, double* rhs, void* e) { direct_apply<double>(B_LAPLACE_NC_REAL, lhs, rhs, e); }
 void square_laplace_u1(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_LAPLACE_U1, lhs, rhs, e); }
 void square_staggered(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_STAG_FREE, lhs, rhs, e); }
+void square_staggered(double* lhs, double* rhs, void* e) { direct_apply<double>(B_STAG_FREE_REAL, lhs, rhs, e); }
 void square_staggered_u1(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_STAG_U1, lhs, rhs, e); }
 void gamma_5(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_GAMMA5, lhs, rhs, e); }
 void square_staggered_gamma5(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_STAG_G5_FREE, lhs, rhs, e); }

@@ -38,6 +38,8 @@ void square_laplace(double* lhs, double* rhs, void* extra_data);
 void square_laplace_u1(complex<double>* lhs, complex<double>* rhs, void* extra_data);
 // operators.cpp:127 / :184   staggered D, free and gauged
 void square_staggered(complex<double>* lhs, complex<double>* rhs, void* extra_data);
+// tests/multishift/multishift.cpp:677   real free staggered                  extra: staggered_u1_op*
+void square_staggered(double* lhs, double* rhs, void* extra_data);
 void square_staggered_u1(complex<double>* lhs, complex<double>* rhs, void* extra_data);
 // operators.cpp:242   gamma_5 = (-1)^(x+y)
 void gamma_5(complex<double>* lhs, complex<double>* rhs, void* extra_data);

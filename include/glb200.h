@@ -110,6 +110,8 @@ int glb_host_free(glb_context* ctx, void* hptr);
  * The operator acts on the GLOBAL X x Y lattice; with a communicator each rank holds its slab. */
 int glb_op_create_laplace(glb_context* ctx, int dtype, int X, int Y, int Nc, double diag_re, double diag_im,
                           glb_operator** op);
+/* real free staggered operator, tests/multishift/multishift.cpp:677 (double; out = D_free in + m in) */
+int glb_op_create_staggered_free_real(glb_context* ctx, int X, int Y, double mass, glb_operator** op);
 /* gauged Laplacian, operators.cpp:73.  h_links: host array in the reference layout
  * lattice[y*X*2 + x*2 + mu] (complex), GLOBAL lattice; each rank uploads only its slab. */
 int glb_op_create_laplace_u1(glb_context* ctx, const void* h_links, int X, int Y, double mass, glb_operator** op);

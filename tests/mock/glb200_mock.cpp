@@ -102,6 +102,10 @@ int glb_op_create_laplace(glb_context*, int dtype, int X, int Y, int Nc, double 
     *op = wrap(ORC_OP_LAPLACE_NC, X, Y, Nc, dre - 4, 0, dtype);
   return GLB_OK;
 }
+int glb_op_create_staggered_free_real(glb_context*, int X, int Y, double m, glb_operator** op) {
+  *op = wrap(ORC_OP_STAG_FREE_REAL, X, Y, 1, m, 0, GLB_REAL);
+  return GLB_OK;
+}
 int glb_op_create_laplace_u1(glb_context*, const void* l, int X, int Y, double m, glb_operator** op) {
   *op = wrap(ORC_OP_LAPLACE_U1, X, Y, 1, m, l, GLB_COMPLEX);
   return GLB_OK;

@@ -51,6 +51,9 @@ def test_laplace_family(ctx, glb, orc, X, Y, Nc):
     _check(ctx.laplace(X, Y, Nc, 4 + 0.01, np.complex128).apply_host(v), want)
     want = orc.op("LAPLACE_REAL_NC", X, Y, mass=0.01, Nc=Nc).apply(vr)
     _check(ctx.laplace(X, Y, Nc, 4 + 0.01, np.float64).apply_host(vr), want)
+    if Nc == 1 and X % 2 == 0:  # real free staggered operator of tests/multishift (multishift.cpp:677)
+        want = orc.op("STAG_FREE_REAL", X, Y, mass=0.2).apply(vr)
+        _check(ctx.staggered_free_real(X, Y, 0.2).apply_host(vr), want)
     if X == Y and Nc == 1:
         want = orc.op("LAPLACE_REAL", X, X, mass=0.01).apply(vr)
         _check(ctx.laplace(X, X, 1, 4 + 0.01, np.float64).apply_host(vr), want)

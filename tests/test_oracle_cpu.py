@@ -202,7 +202,8 @@ SOLVES = [("STAG_NORMAL_U1", "CG", {}), ("STAG_NORMAL_U1", "CG_RESTART", dict(re
           ("STAG_U1", "CG", dict(max_iter=7)), ("STAG_U1", "CR", dict(max_iter=7)),
           ("STAG_U1", "GCR", dict(max_iter=7)), ("STAG_U1", "BICGSTAB", dict(max_iter=7)),
           ("STAG_U1", "BICGSTAB_L", dict(max_iter=7, l=2)), ("STAG_U1", "GMRES", dict(max_iter=7)),
-          ("LAPLACE_REAL", "CR", dict(max_iter=7)), ("LAPLACE_REAL", "GMRES", dict(max_iter=7))]
+          ("LAPLACE_REAL", "CR", dict(max_iter=7)), ("LAPLACE_REAL", "GMRES", dict(max_iter=7)),
+          ("STAG_FREE_REAL", "BICGSTAB", {}), ("STAG_FREE_REAL", "GCR", dict(max_iter=200))]
 
 
 @both
