@@ -11,10 +11,10 @@ for n in 1 2 4 8; do
   if [ $n -le $NG ]; then
     echo "== bench N=$n" | tee -a $OUT/summary.txt
     if [ $n -eq 1 ]; then
-      timeout 300 python bench.py --gpus 1 --steps 5 --no-cpu > $OUT/bench_n$n.json 2> $OUT/bench_n$n.err
+      timeout 300 python bench.py --gpus 1 --steps 3 --no-cpu > $OUT/bench_n$n.json 2> $OUT/bench_n$n.err
     else
       timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2952$n \
-        bench.py --gpus $n --steps 5 > $OUT/bench_n$n.json 2> $OUT/bench_n$n.err
+        bench.py --gpus $n --steps 3 > $OUT/bench_n$n.json 2> $OUT/bench_n$n.err
     fi
     echo "rc=$?" | tee -a $OUT/summary.txt
     tail -1 $OUT/bench_n$n.json | tee -a $OUT/summary.txt; tail -3 $OUT/bench_n$n.err | tee -a $OUT/summary.txt
