@@ -5,9 +5,24 @@
 //  * reductions: k doubles summed over ranks.
 // NCCL is bound lazily (dlopen) so that a single-GPU process never needs it; when torch is loaded
 // first its bundled libnccl.so.2 is the one that gets used, otherwise the system one.
+//
+// Fast path over NVLink peer memory (default; GLB_P2P=0 turns it off): every rank owns an "arena" in
+// device memory whose CUDA IPC handle is all-gathered once (through NCCL) at glb_comm_init, so each
+// rank holds a mapped pointer to every peer's arena.  Ghost rows and reduction mailboxes live at
+// IDENTICAL offsets in every arena:
+//   * halo: a small kernel stores this rank's boundary rows straight into the neighbours' ghost rows
+//     (remote 16-byte stores over NVLink), fences, and bumps a sequence flag in the neighbour's arena;
+//     a one-thread kernel spins on the local flags before the stencil kernel runs.  Ghost rows are
+//     double-buffered by exchange parity, so a rank may run one exchange ahead of its neighbour.
+//   * allreduce: one kernel stores the k partial sums into slot [seq%4][rank] of EVERY peer's mailbox,
+//     flags them, waits for the G local flags and adds the G contributions in rank order -- every
+//     rank obtains the bit-identical sum, ~one NVLink store latency, no library launch.
+// NCCL remains the bootstrap and the fallback when peer mapping is unavailable.
 #include <dlfcn.h>
 
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "runtime.hpp"
 
@@ -62,14 +77,34 @@ static int load_nccl() {
     if (_r != NCCL_SUCCESS) return fail(GLB_ERR_COMM, std::string(#expr) + ": " + g_nccl.GetErrorString(_r)); \
   } while (0)
 
+constexpr int P2P_MAX_RANKS = 16;
+constexpr int P2P_RED_SLOTS = 4;
+constexpr int P2P_RED_WIDTH = 40;  // doubles per reduction (multi_dot of 16 complex vectors + slack)
+
+struct Mailbox {  // at offset 0 of every arena
+  double red[P2P_RED_SLOTS][P2P_MAX_RANKS][P2P_RED_WIDTH];
+  unsigned long long red_seq[P2P_RED_SLOTS][P2P_MAX_RANKS];
+};
+
 struct Comm {
   ncclComm_t nccl = nullptr;
   double* d_red = nullptr;  // device staging for host-value reductions
   double* h_red = nullptr;  // pinned
+  // peer-memory fast path
+  bool p2p = false;
+  char* arena = nullptr;
+  size_t arena_bytes = 0, arena_used = 0;
+  char* peer[P2P_MAX_RANKS] = {nullptr};
+  unsigned long long red_seq = 0;
+  unsigned int* ticket = nullptr;
 };
 
 void comm_destroy(glb_context* ctx) {
   if (!ctx->comm) return;
+  for (int g = 0; g < ctx->nranks; g++)
+    if (ctx->comm->p2p && g != ctx->rank && ctx->comm->peer[g]) cudaIpcCloseMemHandle(ctx->comm->peer[g]);
+  cudaFree(ctx->comm->arena);
+  cudaFree(ctx->comm->ticket);
   if (ctx->comm->nccl) g_nccl.CommDestroy(ctx->comm->nccl);
   cudaFree(ctx->comm->d_red);
   cudaFreeHost(ctx->comm->h_red);
@@ -77,11 +112,123 @@ void comm_destroy(glb_context* ctx) {
   ctx->comm = nullptr;
 }
 
+// ------------------------------------------------------------------------------------------ peer-memory kernels
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// boundary rows -> the neighbours' ghost rows (remote stores), then their flags
+__global__ void __launch_bounds__(256) halo_push_kernel(const uint4* send_lo, const uint4* send_hi, uint4* dst_down_hi,
+                                                         uint4* dst_up_lo, size_t n16, unsigned long long* flag_down_hi,
+                                                         unsigned long long* flag_up_lo, unsigned long long seq,
+                                                         unsigned int* ticket) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n16; i += (size_t)gridDim.x * blockDim.x) {
+    if (i < n16)
+      dst_down_hi[i] = send_lo[i];
+    else
+      dst_up_lo[i - n16] = send_hi[i - n16];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicInc(ticket, gridDim.x - 1);
+    if (t == gridDim.x - 1) {  // every block's stores are fenced: publish
+      __threadfence_system();
+      st_release_sys(flag_down_hi, seq);
+      st_release_sys(flag_up_lo, seq);
+    }
+  }
+}
+// Bounded spin: a peer that never shows up (crashed rank) must surface as a CUDA error, not as a hung GPU.
+__device__ __forceinline__ void spin_until(const unsigned long long* flag, unsigned long long seq) {
+  const long long t0 = clock64();
+  while (ld_acquire_sys(flag) < seq) {
+    __nanosleep(64);
+    if (clock64() - t0 > 40000000000LL) __trap();  // ~20 s at 2 GHz
+  }
+}
+// spin until both neighbours have delivered exchange number `seq`
+__global__ void halo_wait_kernel(const unsigned long long* flag_lo, const unsigned long long* flag_hi,
+                                 unsigned long long seq) {
+  spin_until(flag_lo, seq);
+  spin_until(flag_hi, seq);
+}
+// one-shot allreduce of n <= P2P_RED_WIDTH doubles through the peers' mailboxes
+struct PeerPtrs {
+  Mailbox* mb[P2P_MAX_RANKS];
+};
+__global__ void p2p_allreduce_kernel(double* vals, int n, int rank, int nranks, PeerPtrs peers, unsigned long long seq) {
+  const int slot = (int)(seq % P2P_RED_SLOTS);
+  const int t = threadIdx.x;
+  for (int g = 0; g < nranks; g++)
+    if (t < n) peers.mb[g]->red[slot][rank][t] = vals[t];
+  __threadfence_system();
+  __syncthreads();
+  if (t < nranks) st_release_sys(&peers.mb[t]->red_seq[slot][rank], seq);
+  Mailbox* mine = peers.mb[rank];
+  if (t < nranks) spin_until(&mine->red_seq[slot][t], seq);
+  __syncthreads();
+  if (t < n) {
+    double s = 0.0;
+    for (int g = 0; g < nranks; g++) s += __ldcv(&mine->red[slot][g][t]);  // rank order: same bits everywhere
+    vals[t] = s;
+  }
+}
+
+bool comm_p2p(const glb_context* ctx) { return ctx->comm && ctx->comm->p2p; }
+
+// carve `bytes` (256-byte aligned) out of the arena; identical call sequences on all ranks give
+// identical offsets.  Returns nullptr when the arena is exhausted (caller falls back to NCCL buffers).
+void* comm_arena_alloc(glb_context* ctx, size_t bytes, size_t* offset) {
+  Comm* c = ctx->comm;
+  if (!c || !c->p2p) return nullptr;
+  const size_t need = (bytes + 255) & ~(size_t)255;
+  if (c->arena_used + need > c->arena_bytes) return nullptr;
+  *offset = c->arena_used;
+  c->arena_used += need;
+  return c->arena + *offset;
+}
+
+static int halo_exchange_p2p(glb_operator* op, const void* send_lo, const void* send_hi, int nrows) {
+  glb_context* ctx = op->ctx;
+  Comm* c = ctx->comm;
+  const int G = ctx->nranks, g = ctx->rank;
+  const int up = (g + 1) % G, down = (g + G - 1) % G;
+  const size_t rowb = (size_t)op->X * op->nc * elem_bytes(op->dtype);
+  const size_t bytes = rowb * nrows, gbytes = rowb * op->ghost_depth;
+  const unsigned long long seq = ++op->halo_seq;
+  const size_t par = (size_t)(seq & 1);
+  // arena layout of this operator: [parity 0: lo | hi][parity 1: lo | hi][flag_lo][flag_hi]
+  const size_t off_lo = op->ghost_off + par * 2 * gbytes, off_hi = off_lo + gbytes;
+  const size_t off_flag = op->ghost_off + 4 * gbytes;
+  char* dst_down_hi = c->peer[down] + off_hi;                                  // its rows Yloc ..
+  char* dst_up_lo = c->peer[up] + off_lo + rowb * (op->ghost_depth - nrows);   // its rows -nrows .. -1
+  const size_t n16 = bytes / 16;
+  int grid = (int)((2 * n16 + 255) / 256);
+  if (grid > 64) grid = 64;
+  halo_push_kernel<<<grid, 256, 0, ctx->stream>>>(
+      (const uint4*)send_lo, (const uint4*)send_hi, (uint4*)dst_down_hi, (uint4*)dst_up_lo, n16,
+      (unsigned long long*)(c->peer[down] + off_flag + 8), (unsigned long long*)(c->peer[up] + off_flag), seq, c->ticket);
+  GLB_LAUNCH_CHECK();
+  halo_wait_kernel<<<1, 1, 0, ctx->stream>>>((const unsigned long long*)(c->arena + off_flag),
+                                             (const unsigned long long*)(c->arena + off_flag + 8), seq);
+  GLB_LAUNCH_CHECK();
+  op->ghost_lo = c->arena + off_lo;  // the buffers of this parity are what the next kernel reads
+  op->ghost_hi = c->arena + off_hi;
+  return GLB_OK;
+}
+
 int halo_exchange_ptrs(glb_operator* op, const void* send_lo, const void* send_hi, int nrows) {
   glb_context* ctx = op->ctx;
   if (ctx->nranks == 1) return GLB_OK;
   if (!ctx->comm) return fail(GLB_ERR_STATE, "slab operator used before glb_comm_init");
   if (nrows < 1 || nrows > op->ghost_depth) return fail(GLB_ERR_ARG, "halo deeper than the operator's ghost rows");
+  if (op->ghost_p2p) return halo_exchange_p2p(op, send_lo, send_hi, nrows);
   const int G = ctx->nranks, g = ctx->rank;
   const int up = (g + 1) % G, down = (g + G - 1) % G;
   const size_t rowb = (size_t)op->X * op->nc * elem_bytes(op->dtype);
@@ -108,13 +255,18 @@ int halo_exchange(glb_operator* op, const void* in, int nrows) {
   return halo_exchange_ptrs(op, base, base + rowb * (op->Yloc - nrows), nrows);
 }
 
+int allreduce_device(glb_context* ctx, double* d_vals, int n);
+
 int allreduce_sum(glb_context* ctx, double* vals, int n) {
   if (ctx->nranks == 1) return GLB_OK;
   if (!ctx->comm) return fail(GLB_ERR_STATE, "reduction before glb_comm_init");
   if (n > 64) return fail(GLB_ERR_ARG, "allreduce_sum: too many values");
   std::memcpy(ctx->comm->h_red, vals, sizeof(double) * n);
   GLB_CUDA(cudaMemcpyAsync(ctx->comm->d_red, ctx->comm->h_red, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
-  GLB_NCCL(g_nccl.AllReduce(ctx->comm->d_red, ctx->comm->d_red, n, NCCL_FLOAT64, NCCL_SUM, ctx->comm->nccl, ctx->stream));
+  {
+    int rc = allreduce_device(ctx, ctx->comm->d_red, n);
+    if (rc) return rc;
+  }
   GLB_CUDA(cudaMemcpyAsync(ctx->comm->h_red, ctx->comm->d_red, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
   GLB_CUDA(cudaStreamSynchronize(ctx->stream));
   std::memcpy(vals, ctx->comm->h_red, sizeof(double) * n);
@@ -125,6 +277,14 @@ int allreduce_sum(glb_context* ctx, double* vals, int n) {
 int allreduce_device(glb_context* ctx, double* d_vals, int n) {
   if (ctx->nranks == 1) return GLB_OK;
   if (!ctx->comm) return fail(GLB_ERR_STATE, "reduction before glb_comm_init");
+  Comm* c = ctx->comm;
+  if (c->p2p && n <= P2P_RED_WIDTH) {
+    PeerPtrs pp;
+    for (int g = 0; g < ctx->nranks; g++) pp.mb[g] = (Mailbox*)c->peer[g];
+    p2p_allreduce_kernel<<<1, 64, 0, ctx->stream>>>(d_vals, n, ctx->rank, ctx->nranks, pp, ++c->red_seq);
+    GLB_LAUNCH_CHECK();
+    return GLB_OK;
+  }
   GLB_NCCL(g_nccl.AllReduce(d_vals, d_vals, n, NCCL_FLOAT64, NCCL_SUM, ctx->comm->nccl, ctx->stream));
   return GLB_OK;
 }
@@ -160,6 +320,66 @@ int glb_comm_init(glb_context* ctx, int rank, int nranks, const char id[GLB_COMM
   GLB_CUDA(cudaMalloc(&c->d_red, sizeof(double) * 64));
   GLB_CUDA(cudaHostAlloc((void**)&c->h_red, sizeof(double) * 64, cudaHostAllocDefault));
   ctx->comm = c;
+  // ---- peer-memory arena: export, all-gather the IPC handles through NCCL, map every peer
+  const char* e = getenv("GLB_P2P");
+  const bool want = !(e && atoi(e) == 0) && nranks <= P2P_MAX_RANKS;
+  int ok = 0;
+  if (want) {
+    const char* es = getenv("GLB_P2P_ARENA_MB");
+    c->arena_bytes = (size_t)(es ? atoi(es) : 96) << 20;
+    ok = (cudaMalloc((void**)&c->arena, c->arena_bytes) == cudaSuccess) &&
+         (cudaMemset(c->arena, 0, c->arena_bytes) == cudaSuccess) &&
+         (cudaMalloc((void**)&c->ticket, sizeof(unsigned int)) == cudaSuccess) &&
+         (cudaMemset(c->ticket, 0, sizeof(unsigned int)) == cudaSuccess);
+  }
+  cudaIpcMemHandle_t mine;
+  std::memset(&mine, 0, sizeof mine);
+  if (ok) ok = (cudaIpcGetMemHandle(&mine, c->arena) == cudaSuccess);
+  // gather [ok flag | handle] from everybody (fixed-size record so a failing rank cannot desynchronise)
+  const size_t rec = 8 + sizeof(cudaIpcMemHandle_t);
+  char* d_all = nullptr;
+  GLB_CUDA(cudaMalloc((void**)&d_all, rec * nranks));
+  std::vector<char> h_all(rec * nranks, 0);
+  long long okl = ok;
+  std::memcpy(&h_all[rec * rank], &okl, 8);
+  std::memcpy(&h_all[rec * rank + 8], &mine, sizeof mine);
+  GLB_CUDA(cudaMemcpy(d_all + rec * rank, &h_all[rec * rank], rec, cudaMemcpyHostToDevice));
+  typedef int (*AllGatherFn)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t);
+  AllGatherFn all_gather = (AllGatherFn)dlsym(g_nccl.lib, "ncclAllGather");
+  if (!all_gather) return fail(GLB_ERR_COMM, "libnccl lacks ncclAllGather");
+  GLB_NCCL(all_gather(d_all + rec * rank, d_all, rec, NCCL_CHAR, c->nccl, ctx->stream));
+  GLB_CUDA(cudaStreamSynchronize(ctx->stream));
+  GLB_CUDA(cudaMemcpy(h_all.data(), d_all, rec * nranks, cudaMemcpyDeviceToHost));
+  GLB_CUDA(cudaFree(d_all));
+  bool all_ok = want;
+  for (int g = 0; g < nranks && all_ok; g++) {
+    long long v;
+    std::memcpy(&v, &h_all[rec * g], 8);
+    all_ok = (v != 0);
+  }
+  int mapped = all_ok ? 1 : 0;
+  if (all_ok) {
+    for (int g = 0; g < nranks && mapped; g++) {
+      if (g == rank) {
+        c->peer[g] = c->arena;
+        continue;
+      }
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, &h_all[rec * g + 8], sizeof h);
+      if (cudaIpcOpenMemHandle((void**)&c->peer[g], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        mapped = 0;
+      }
+    }
+  }
+  // everybody must agree, otherwise nobody uses the fast path
+  double agree = mapped ? 0.0 : 1.0;
+  c->p2p = false;
+  int rc2 = allreduce_sum(ctx, &agree, 1);
+  if (rc2) return rc2;
+  c->p2p = (agree == 0.0);
+  c->arena_used = (sizeof(Mailbox) + 255) & ~(size_t)255;
+  if (!c->p2p && getenv("GLB_VERBOSE")) fprintf(stderr, "[glb200] rank %d: peer-memory path unavailable, using NCCL\n", rank);
   return GLB_OK;
 }
 

@@ -42,10 +42,20 @@ static int alloc_ghosts(glb_operator* op, int depth) {
   if (op->ctx->nranks == 1) return GLB_OK;
   if (op->Yloc < depth) return fail(GLB_ERR_ARG, "slab thinner than the stencil reach: use fewer ranks");
   const size_t bytes = (size_t)depth * op->X * op->nc * elem_bytes(op->dtype);
-  GLB_CUDA(cudaMalloc(&op->ghost_lo, bytes));
-  GLB_CUDA(cudaMalloc(&op->ghost_hi, bytes));
   GLB_CUDA(cudaMalloc(&op->send_lo, bytes));
   GLB_CUDA(cudaMalloc(&op->send_hi, bytes));
+  // peer-memory path: [parity 0: lo|hi][parity 1: lo|hi][flag_lo, flag_hi] at the same offset on every rank
+  size_t off = 0;
+  char* area = (char*)comm_arena_alloc(op->ctx, 4 * bytes + 256, &off);
+  if (area) {
+    op->ghost_p2p = true;
+    op->ghost_off = off;
+    op->ghost_lo = area;
+    op->ghost_hi = area + bytes;
+    return GLB_OK;
+  }
+  GLB_CUDA(cudaMalloc(&op->ghost_lo, bytes));
+  GLB_CUDA(cudaMalloc(&op->ghost_hi, bytes));
   return GLB_OK;
 }
 
@@ -212,8 +222,10 @@ int glb_op_destroy(glb_operator* op) {
   cudaFree(op->Ux_store);
   cudaFree(op->Uy_store);
   cudaFree(op->tmp);
-  cudaFree(op->ghost_lo);
-  cudaFree(op->ghost_hi);
+  if (!op->ghost_p2p) {
+    cudaFree(op->ghost_lo);
+    cudaFree(op->ghost_hi);
+  }
   cudaFree(op->send_lo);
   cudaFree(op->send_hi);
   cudaFree(op->clover);

@@ -92,6 +92,9 @@ struct glb_operator {
   void* ghost_lo = nullptr;    // ghost_depth rows: y0-ghost_depth .. y0-1 (lowest first)
   void* ghost_hi = nullptr;    // ghost_depth rows: y0+Yloc .. y0+Yloc+ghost_depth-1
   int ghost_depth = 0;
+  bool ghost_p2p = false;      // ghost rows live in the peer-mapped arena (NVLink stores + flags)
+  size_t ghost_off = 0;        // offset of this operator's ghost area inside every rank's arena
+  unsigned long long halo_seq = 0;
   void* send_lo = nullptr;     // staging for boundary rows produced on the fly (device CG)
   void* send_hi = nullptr;
   // stencil data (slab-local, device)
@@ -140,5 +143,7 @@ int halo_exchange_ptrs(glb_operator* op, const void* send_lo, const void* send_h
 int allreduce_device(glb_context* ctx, double* d_vals, int n);
 int allreduce_sum(glb_context* ctx, double* host_vals, int n);
 void comm_destroy(glb_context* ctx);
+bool comm_p2p(const glb_context* ctx);
+void* comm_arena_alloc(glb_context* ctx, size_t bytes, size_t* offset);
 
 }  // namespace glb
