@@ -378,6 +378,9 @@ def main():
                    "lattice": [X, Y], "iterations": iters, "true_rel_residual": true_rel / bnorm,
                    "l2": "working set %.1f GB per GPU >> 126 MB L2: no flush needed" % (V_local * 16 * 9 / 1e9),
                    "gauge": "gauss U(1), beta=6, per-row numpy seed %d" % SEED,
+                   "comm": ("single GPU" if world == 1 else
+                            ("NVLink peer memory: halo rows and rank sums written by the kernels themselves"
+                             if ctx.p2p else "NCCL send/recv + allreduce on the compute stream")),
                    "bytes_model": "SURVEY 8 d-bytes fused minimum: 368 + 272*(it-1) + 96 + 160 B/site; the one-pass "
                                   "D^dag D kernel actually moves 192 B/site/iteration, so value/peak may exceed 1",
                    "actual_traffic_frac_of_peak": (192.0 * V_local * iters * args.steps / (ms_total * 1e-3) / 1e9) / peak_early},

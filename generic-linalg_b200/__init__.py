@@ -79,7 +79,7 @@ def libs():
         "glb_last_error": (C.c_char_p, []), "glb_synchronize": (ci, [vp]), "glb_stream": (vp, [vp]),
         "glb_device": (ci, [vp]), "glb_sm_count": (ci, [vp]), "glb_kernel_launches": (C.c_ulonglong, []),
         "glb_comm_unique_id": (ci, [C.c_char_p]), "glb_comm_init": (ci, [vp, ci, ci, C.c_char_p]),
-        "glb_comm_rank": (ci, [vp]), "glb_comm_size": (ci, [vp]), "glb_comm_barrier": (ci, [vp]),
+        "glb_comm_p2p_enabled": (ci, [vp]), "glb_comm_rank": (ci, [vp]), "glb_comm_size": (ci, [vp]), "glb_comm_barrier": (ci, [vp]),
         "glb_vec_alloc": (ci, [vp, ci, sz, C.POINTER(vp)]), "glb_vec_free": (ci, [vp, vp]),
         "glb_vec_upload": (ci, [vp, ci, sz, vp, vp]), "glb_vec_download": (ci, [vp, ci, sz, vp, vp]),
         "glb_vec_zero": (ci, [vp, ci, sz, vp]), "glb_vec_copy": (ci, [vp, ci, sz, vp, vp]),
@@ -292,6 +292,10 @@ class Context:
     @property
     def nranks(self):
         return self.cu.glb_comm_size(self.h)
+
+    @property
+    def p2p(self):
+        return bool(self.cu.glb_comm_p2p_enabled(self.h))
 
     def barrier(self):
         _chk(self.cu.glb_comm_barrier(self.h), "glb_comm_barrier")

@@ -262,7 +262,8 @@ __global__ void __launch_bounds__(256) cgm_p_kernel(MultiArgs<T> a, const T* r, 
 // state, and the stopping test of generic_cg.cpp:339 evaluated by the last block.
 template <typename T, int W>
 __global__ void __launch_bounds__(256)
-cg_update_kernel(CgState* st, double* hist, const T* p, T* x, const T* Ap, T* r, size_t n, ReduceWs red, int defer) {
+cg_update_kernel(CgState* st, double* hist, const T* p, T* x, const T* Ap, T* r, size_t n, ReduceWs red, int defer,
+                 P2PRed pr) {
   if (st->done) return;
   T alpha;
   {
@@ -294,10 +295,11 @@ cg_update_kernel(CgState* st, double* hist, const T* p, T* x, const T* Ap, T* r,
   }
   double total[1];
   if (grid_sum<1>(acc, red, total) && threadIdx.x == 0) {
-    if (defer) {  // slab run: the sum over ranks and the recurrence step follow on the stream
+    if (defer == 1) {  // slab run over NCCL: the sum over ranks and the recurrence step follow on the stream
       st->partial[0] = total[0];
       return;
     }
+    if (defer == 2) p2p_allreduce_thread(pr, total, 1);  // slab run over peer memory: finish the sum here
     const double rsq_new = total[0];
     st->rsq_new = rsq_new;
     const int k = st->iter;  // 0-based iteration index of the reference loop
@@ -350,6 +352,37 @@ __global__ void cg_boundary_kernel(const CgState* st, const T* r, const T* pold,
   }
 }
 
+// same, but the rows go straight into the neighbours' ghost rows over NVLink and the last block raises
+// their flags (compute + halo push in one kernel)
+template <typename T>
+__global__ void cg_boundary_push_kernel(const CgState* st, const T* r, const T* pold, T* dst_down_hi, T* dst_up_lo,
+                                        size_t row_elems, int nrows, size_t local_elems,
+                                        unsigned long long* flag_down_hi, unsigned long long* flag_up_lo,
+                                        unsigned long long seq, unsigned int* ticket) {
+  // NB: no early exit on st->done -- the neighbours' kernels wait for these flags
+  const bool done = st->done != 0;
+  const double b = done ? 0.0 : xdiv(st->rsq_new, st->rsq_old);
+  const size_t n = row_elems * nrows;
+  if (!done) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n; i += (size_t)gridDim.x * blockDim.x) {
+      const bool hi = i >= n;
+      const size_t j = hi ? i - n : i;
+      const size_t src = hi ? local_elems - n + j : j;
+      (hi ? dst_up_lo : dst_down_hi)[j] = fadd(r[src], fscale(b, pold[src]));
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicInc(ticket, gridDim.x - 1);
+    if (t == gridDim.x - 1) {
+      __threadfence_system();
+      st_release_sys(flag_down_hi, seq);
+      st_release_sys(flag_up_lo, seq);
+    }
+  }
+}
+
 // p = r + beta p with beta = rsqNew/rsq from the CG state (for operators without the fused input)
 template <typename T>
 __global__ void __launch_bounds__(256) cg_xpay_kernel(const CgState* st, const T* r, T* p, size_t n) {
@@ -385,8 +418,20 @@ int launch_cg_boundary(glb_context* ctx, const void* st, const void* r, const vo
   return GLB_OK;
 }
 
+int launch_cg_boundary_push(glb_context* ctx, const void* st, const void* r, const void* pold, size_t row_elems, int nrows,
+                            size_t local_elems, const HaloTargets& t) {
+  const int grid = blas_grid(ctx, 2 * row_elems * nrows, 256, 1);
+  cg_boundary_push_kernel<cplx><<<grid, 256, 0, ctx->stream>>>(
+      (const CgState*)st, (const cplx*)r, (const cplx*)pold, (cplx*)t.dst_down_hi, (cplx*)t.dst_up_lo, row_elems, nrows,
+      local_elems, t.flag_down_hi, t.flag_up_lo, t.wait.seq, t.ticket);
+  GLB_LAUNCH_CHECK();
+  return GLB_OK;
+}
+
 int launch_cg_update(glb_context* ctx, int dtype, void* st, double* hist, const void* p, void* x, const void* Ap,
                      void* r, size_t n, int defer) {
+  P2PRed pr{};
+  if (defer == 2) pr = comm_p2p_red(ctx);
   ReduceWs red = ctx->red;
   red.result_host = nullptr;
   if (dtype == GLB_COMPLEX) {
@@ -394,16 +439,16 @@ int launch_cg_update(glb_context* ctx, int dtype, void* st, double* hist, const 
     if (wide) {
       const int grid = blas_grid(ctx, n / 2, 256, 2);
       cg_update_kernel<cplx, 2><<<grid, 256, 0, ctx->stream>>>((CgState*)st, hist, (const cplx*)p, (cplx*)x,
-                                                               (const cplx*)Ap, (cplx*)r, n, red, defer);
+                                                               (const cplx*)Ap, (cplx*)r, n, red, defer, pr);
     } else {
       const int grid = blas_grid(ctx, n, 256, 4);
       cg_update_kernel<cplx, 1><<<grid, 256, 0, ctx->stream>>>((CgState*)st, hist, (const cplx*)p, (cplx*)x,
-                                                               (const cplx*)Ap, (cplx*)r, n, red, defer);
+                                                               (const cplx*)Ap, (cplx*)r, n, red, defer, pr);
     }
   } else {
     const int grid = blas_grid(ctx, n, 256, 4);
     cg_update_kernel<double, 1><<<grid, 256, 0, ctx->stream>>>((CgState*)st, hist, (const double*)p, (double*)x,
-                                                               (const double*)Ap, (double*)r, n, red, defer);
+                                                               (const double*)Ap, (double*)r, n, red, defer, pr);
   }
   GLB_LAUNCH_CHECK();
   return GLB_OK;

@@ -23,6 +23,8 @@ int launch_cg_update(glb_context* ctx, int dtype, void* st, double* hist, const 
                      void* r, size_t n, int defer);
 int launch_cg_post_update(glb_context* ctx, void* st, double* hist);
 int launch_cg_post_apply(glb_context* ctx, void* st);
+int launch_cg_boundary_push(glb_context* ctx, const void* st, const void* r, const void* pold, size_t row_elems, int nrows,
+                            size_t local_elems, const HaloTargets& t);
 int launch_cg_boundary(glb_context* ctx, const void* st, const void* r, const void* pold, void* send_lo, void* send_hi,
                        size_t row_elems, int nrows, size_t local_elems);
 int launch_cg_xpay(glb_context* ctx, int dtype, const void* st, const void* r, void* p, size_t n);
@@ -43,8 +45,27 @@ static int direction_and_apply(glb_operator* op, CgState* d_st, const void* r, v
     // slab run: boundary rows of the new direction -> neighbours' ghost rows, then the one-pass
     // kernel (own rows formed on the fly, ghost rows read as they are), then the rank sum of <p,Ap>
     const size_t row = (size_t)op->X;
-    int rc = launch_cg_boundary(ctx, d_st, r, p_cur, op->send_lo, op->send_hi, row, 2, n);
-    if (rc) return rc;
+    int rc;
+    if (comm_p2p(ctx) && op->ghost_p2p) {
+      // peer memory: boundary rows are computed straight into the neighbours' ghost rows, the one-pass
+      // kernel waits for its own ghost flags in its prologue and its last block sums <p,Ap> over ranks
+      HaloTargets t;
+      if ((rc = halo_p2p_begin(op, 2, &t))) return rc;
+      if ((rc = launch_cg_boundary_push(ctx, d_st, r, p_cur, row, 2, n, t))) return rc;
+      ApplyFusion f;
+      f.r = r;
+      f.p_old = p_cur;
+      f.p_new = p_alt;
+      f.cg_state = (const double*)d_st;
+      f.w = p_alt;
+      f.w_is_input = true;
+      f.cg_role = 3;
+      f.pr = comm_p2p_red(ctx);
+      f.wait = t.wait;
+      *swapped = true;
+      return launch_normal(op, Ap, nullptr, f);
+    }
+    if ((rc = launch_cg_boundary(ctx, d_st, r, p_cur, op->send_lo, op->send_hi, row, 2, n))) return rc;
     if ((rc = halo_exchange_ptrs(op, op->send_lo, op->send_hi, 2))) return rc;
     ApplyFusion f;
     f.r = r;
@@ -181,7 +202,9 @@ extern "C" int glb_cg_solve(glb_operator* op, void* d_x, const void* d_b, int ma
     bool have_pending = false;
     while (!finished) {
       for (int b = 0; b < BATCH; b++) {
-        if (ctx->nranks > 1) {
+        if (ctx->nranks > 1 && comm_p2p(ctx)) {
+          CG_TRY(launch_cg_update(ctx, dt, d_st, d_hist, pc, d_x, Ap, r, n, 2));  // last block sums over ranks
+        } else if (ctx->nranks > 1) {
           CG_TRY(launch_cg_update(ctx, dt, d_st, d_hist, pc, d_x, Ap, r, n, 1));
           CG_TRY(allreduce_device(ctx, d_st->partial, 1));
           CG_TRY(launch_cg_post_update(ctx, d_st, d_hist));

@@ -43,10 +43,29 @@ template <int NC>
 __device__ __forceinline__ cplx row_times(cplx acc, const cplx* __restrict__ M, const cplx* __restrict__ v, int nc) {
   if (NC > 0) {
     cplx mm[NC > 0 ? NC : 1], vv[NC > 0 ? NC : 1];
+    if (NC % 2 == 0) {
+      // rows of an even nc start 32-byte aligned: LDG.256 halves the L1 wavefronts of this
+      // row-per-thread pattern (lanes 16*nc bytes apart), which is what bounded the kernel at nc = 8
 #pragma unroll
-    for (int c = 0; c < NC; c++) mm[c] = __ldg(M + c);
+      for (int c = 0; c < NC; c += 2) {
+        cplx pr[2];
+        ldv_nc<2>(M + c, pr);
+        mm[c] = pr[0];
+        mm[c + (NC > 1 ? 1 : 0)] = pr[1];
+      }
 #pragma unroll
-    for (int c = 0; c < NC; c++) vv[c] = v[c];
+      for (int c = 0; c < NC; c += 2) {
+        cplx pr[2];
+        ldv<2>(v + c, pr);
+        vv[c] = pr[0];
+        vv[c + (NC > 1 ? 1 : 0)] = pr[1];
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < NC; c++) mm[c] = __ldg(M + c);
+#pragma unroll
+      for (int c = 0; c < NC; c++) vv[c] = v[c];
+    }
 #pragma unroll
     for (int c = 0; c < NC; c++) acc = fadd(acc, fmul(mm[c], vv[c]));
   } else {

@@ -24,6 +24,7 @@
 #include <cstring>
 #include <vector>
 
+#include "p2p.cuh"
 #include "runtime.hpp"
 
 namespace glb {
@@ -77,15 +78,6 @@ static int load_nccl() {
     if (_r != NCCL_SUCCESS) return fail(GLB_ERR_COMM, std::string(#expr) + ": " + g_nccl.GetErrorString(_r)); \
   } while (0)
 
-constexpr int P2P_MAX_RANKS = 16;
-constexpr int P2P_RED_SLOTS = 4;
-constexpr int P2P_RED_WIDTH = 40;  // doubles per reduction (multi_dot of 16 complex vectors + slack)
-
-struct Mailbox {  // at offset 0 of every arena
-  double red[P2P_RED_SLOTS][P2P_MAX_RANKS][P2P_RED_WIDTH];
-  unsigned long long red_seq[P2P_RED_SLOTS][P2P_MAX_RANKS];
-};
-
 struct Comm {
   ncclComm_t nccl = nullptr;
   double* d_red = nullptr;  // device staging for host-value reductions
@@ -113,15 +105,6 @@ void comm_destroy(glb_context* ctx) {
 }
 
 // ------------------------------------------------------------------------------------------ peer-memory kernels
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-
 // boundary rows -> the neighbours' ghost rows (remote stores), then their flags
 __global__ void __launch_bounds__(256) halo_push_kernel(const uint4* send_lo, const uint4* send_hi, uint4* dst_down_hi,
                                                          uint4* dst_up_lo, size_t n16, unsigned long long* flag_down_hi,
@@ -144,43 +127,57 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const uint4* send_lo, co
     }
   }
 }
-// Bounded spin: a peer that never shows up (crashed rank) must surface as a CUDA error, not as a hung GPU.
-__device__ __forceinline__ void spin_until(const unsigned long long* flag, unsigned long long seq) {
-  const long long t0 = clock64();
-  while (ld_acquire_sys(flag) < seq) {
-    __nanosleep(64);
-    if (clock64() - t0 > 40000000000LL) __trap();  // ~20 s at 2 GHz
-  }
-}
 // spin until both neighbours have delivered exchange number `seq`
 __global__ void halo_wait_kernel(const unsigned long long* flag_lo, const unsigned long long* flag_hi,
                                  unsigned long long seq) {
   spin_until(flag_lo, seq);
   spin_until(flag_hi, seq);
 }
-// one-shot allreduce of n <= P2P_RED_WIDTH doubles through the peers' mailboxes
-struct PeerPtrs {
-  Mailbox* mb[P2P_MAX_RANKS];
-};
-__global__ void p2p_allreduce_kernel(double* vals, int n, int rank, int nranks, PeerPtrs peers, unsigned long long seq) {
-  const int slot = (int)(seq % P2P_RED_SLOTS);
-  const int t = threadIdx.x;
-  for (int g = 0; g < nranks; g++)
-    if (t < n) peers.mb[g]->red[slot][rank][t] = vals[t];
-  __threadfence_system();
-  __syncthreads();
-  if (t < nranks) st_release_sys(&peers.mb[t]->red_seq[slot][rank], seq);
-  Mailbox* mine = peers.mb[rank];
-  if (t < nranks) spin_until(&mine->red_seq[slot][t], seq);
-  __syncthreads();
-  if (t < n) {
-    double s = 0.0;
-    for (int g = 0; g < nranks; g++) s += __ldcv(&mine->red[slot][g][t]);  // rank order: same bits everywhere
-    vals[t] = s;
-  }
-}
+// stand-alone one-shot allreduce (used when no producing kernel can finish the sum itself)
+__global__ void p2p_allreduce_kernel(double* vals, int n, P2PRed pr) { p2p_allreduce_thread(pr, vals, n); }
 
 bool comm_p2p(const glb_context* ctx) { return ctx->comm && ctx->comm->p2p; }
+
+// descriptor of the NEXT rank-wide reduction (bumps the sequence number: one per reduction, same order on all ranks)
+P2PRed comm_p2p_red(glb_context* ctx) {
+  P2PRed pr;
+  Comm* c = ctx->comm;
+  for (int g = 0; g < P2P_MAX_RANKS; g++) pr.mb[g] = (g < ctx->nranks) ? (Mailbox*)c->peer[g] : nullptr;
+  pr.rank = ctx->rank;
+  pr.nranks = ctx->nranks;
+  pr.seq = ++c->red_seq;
+  return pr;
+}
+
+// Start halo exchange number op->halo_seq+1 on the peer-memory path: where this rank's boundary rows go
+// (remote pointers), which flags to raise there, which local flags to wait on.  Also points
+// op->ghost_lo/hi at the buffers of this exchange's parity.
+int halo_p2p_begin(glb_operator* op, int nrows, HaloTargets* t) {
+  glb_context* ctx = op->ctx;
+  Comm* c = ctx->comm;
+  if (!c || !c->p2p || !op->ghost_p2p) return fail(GLB_ERR_STATE, "operator is not on the peer-memory path");
+  const int G = ctx->nranks, g = ctx->rank;
+  const int up = (g + 1) % G, down = (g + G - 1) % G;
+  const size_t rowb = (size_t)op->X * op->nc * elem_bytes(op->dtype);
+  const size_t gbytes = rowb * op->ghost_depth;
+  const unsigned long long seq = ++op->halo_seq;
+  const size_t par = (size_t)(seq & 1);
+  // arena layout of this operator: [parity 0: lo | hi][parity 1: lo | hi][flag_lo][flag_hi]
+  const size_t off_lo = op->ghost_off + par * 2 * gbytes, off_hi = off_lo + gbytes;
+  const size_t off_flag = op->ghost_off + 4 * gbytes;
+  t->dst_down_hi = c->peer[down] + off_hi;                                 // its rows Yloc ..
+  t->dst_up_lo = c->peer[up] + off_lo + rowb * (op->ghost_depth - nrows);  // its rows -nrows .. -1
+  t->flag_down_hi = (unsigned long long*)(c->peer[down] + off_flag + 8);
+  t->flag_up_lo = (unsigned long long*)(c->peer[up] + off_flag);
+  t->wait.flag_lo = (const unsigned long long*)(c->arena + off_flag);
+  t->wait.flag_hi = (const unsigned long long*)(c->arena + off_flag + 8);
+  t->wait.seq = seq;
+  t->ticket = c->ticket;
+  t->bytes = rowb * nrows;
+  op->ghost_lo = c->arena + off_lo;
+  op->ghost_hi = c->arena + off_hi;
+  return GLB_OK;
+}
 
 // carve `bytes` (256-byte aligned) out of the arena; identical call sequences on all ranks give
 // identical offsets.  Returns nullptr when the arena is exhausted (caller falls back to NCCL buffers).
@@ -196,30 +193,18 @@ void* comm_arena_alloc(glb_context* ctx, size_t bytes, size_t* offset) {
 
 static int halo_exchange_p2p(glb_operator* op, const void* send_lo, const void* send_hi, int nrows) {
   glb_context* ctx = op->ctx;
-  Comm* c = ctx->comm;
-  const int G = ctx->nranks, g = ctx->rank;
-  const int up = (g + 1) % G, down = (g + G - 1) % G;
-  const size_t rowb = (size_t)op->X * op->nc * elem_bytes(op->dtype);
-  const size_t bytes = rowb * nrows, gbytes = rowb * op->ghost_depth;
-  const unsigned long long seq = ++op->halo_seq;
-  const size_t par = (size_t)(seq & 1);
-  // arena layout of this operator: [parity 0: lo | hi][parity 1: lo | hi][flag_lo][flag_hi]
-  const size_t off_lo = op->ghost_off + par * 2 * gbytes, off_hi = off_lo + gbytes;
-  const size_t off_flag = op->ghost_off + 4 * gbytes;
-  char* dst_down_hi = c->peer[down] + off_hi;                                  // its rows Yloc ..
-  char* dst_up_lo = c->peer[up] + off_lo + rowb * (op->ghost_depth - nrows);   // its rows -nrows .. -1
-  const size_t n16 = bytes / 16;
+  HaloTargets t;
+  int rc = halo_p2p_begin(op, nrows, &t);
+  if (rc) return rc;
+  const size_t n16 = t.bytes / 16;
   int grid = (int)((2 * n16 + 255) / 256);
   if (grid > 64) grid = 64;
-  halo_push_kernel<<<grid, 256, 0, ctx->stream>>>(
-      (const uint4*)send_lo, (const uint4*)send_hi, (uint4*)dst_down_hi, (uint4*)dst_up_lo, n16,
-      (unsigned long long*)(c->peer[down] + off_flag + 8), (unsigned long long*)(c->peer[up] + off_flag), seq, c->ticket);
+  halo_push_kernel<<<grid, 256, 0, ctx->stream>>>((const uint4*)send_lo, (const uint4*)send_hi, (uint4*)t.dst_down_hi,
+                                                  (uint4*)t.dst_up_lo, n16, t.flag_down_hi, t.flag_up_lo, t.wait.seq,
+                                                  t.ticket);
   GLB_LAUNCH_CHECK();
-  halo_wait_kernel<<<1, 1, 0, ctx->stream>>>((const unsigned long long*)(c->arena + off_flag),
-                                             (const unsigned long long*)(c->arena + off_flag + 8), seq);
+  halo_wait_kernel<<<1, 1, 0, ctx->stream>>>(t.wait.flag_lo, t.wait.flag_hi, t.wait.seq);
   GLB_LAUNCH_CHECK();
-  op->ghost_lo = c->arena + off_lo;  // the buffers of this parity are what the next kernel reads
-  op->ghost_hi = c->arena + off_hi;
   return GLB_OK;
 }
 
@@ -279,9 +264,7 @@ int allreduce_device(glb_context* ctx, double* d_vals, int n) {
   if (!ctx->comm) return fail(GLB_ERR_STATE, "reduction before glb_comm_init");
   Comm* c = ctx->comm;
   if (c->p2p && n <= P2P_RED_WIDTH) {
-    PeerPtrs pp;
-    for (int g = 0; g < ctx->nranks; g++) pp.mb[g] = (Mailbox*)c->peer[g];
-    p2p_allreduce_kernel<<<1, 64, 0, ctx->stream>>>(d_vals, n, ctx->rank, ctx->nranks, pp, ++c->red_seq);
+    p2p_allreduce_kernel<<<1, 1, 0, ctx->stream>>>(d_vals, n, comm_p2p_red(ctx));
     GLB_LAUNCH_CHECK();
     return GLB_OK;
   }
@@ -383,6 +366,7 @@ int glb_comm_init(glb_context* ctx, int rank, int nranks, const char id[GLB_COMM
   return GLB_OK;
 }
 
+int glb_comm_p2p_enabled(glb_context* ctx) { return comm_p2p(ctx) ? 1 : 0; }
 int glb_comm_rank(glb_context* ctx) { return ctx->rank; }
 int glb_comm_size(glb_context* ctx) { return ctx->nranks; }
 
@@ -390,17 +374,6 @@ int glb_comm_barrier(glb_context* ctx) {
   double z = 0.0;
   GLB_CUDA(cudaStreamSynchronize(ctx->stream));
   return allreduce_sum(ctx, &z, 1);
-}
-
-int glb_comm_export_mailbox(glb_context* ctx, char handle[GLB_IPC_HANDLE_BYTES]) {
-  (void)ctx;
-  (void)handle;
-  return fail(GLB_ERR_STATE, "peer-memory mailboxes are not enabled in this build");
-}
-int glb_comm_attach_mailboxes(glb_context* ctx, const char* all_handles) {
-  (void)ctx;
-  (void)all_handles;
-  return fail(GLB_ERR_STATE, "peer-memory mailboxes are not enabled in this build");
 }
 
 }  // extern "C"

@@ -44,6 +44,8 @@ struct NormArgs {
   double mass;
   int pf_rows;  // L2 prefetch distance in rows (0 = off)
   int nrb;      // row blocks: work item i -> strip i % nstrips, rows [Y*rb/nrb, Y*(rb+1)/nrb), rb = i / nstrips
+  P2PRed pr;    // cg_role 3: the last block finishes the sum over ranks itself (peer memory)
+  HaloWait wait;  // peer-memory slabs: ghost-row flags to wait for before touching g_lo / g_hi
   ReduceWs red;
   CgState* cg;
   int cg_role;
@@ -102,6 +104,7 @@ __global__ void __launch_bounds__(NORM_THREADS) normal_kernel(const NormArgs a) 
     if (a.cg->done) return;
     if (FUSE_XPAY) beta = xdiv(a.cg->rsq_new, a.cg->rsq_old);  // generic_cg.cpp:344
   }
+  halo_wait_block(a.wait);  // slabs over peer memory: the neighbours' rows must have landed
   constexpr int NRED = (NDOT == 0) ? 1 : (NDOT == 1 ? 2 : 3);
   double acc[NRED];
 #pragma unroll
@@ -332,6 +335,11 @@ __global__ void __launch_bounds__(NORM_THREADS) normal_kernel(const NormArgs a) 
       } else if (a.cg != nullptr && a.cg_role == 2) {  // slab run: rank-local part, summed on the stream next
         a.cg->partial[1] = total[0];
         a.cg->partial[2] = total[1];
+      } else if (a.cg != nullptr && a.cg_role == 3) {  // slab run over peer memory: finish the sum here
+        p2p_allreduce_thread(a.pr, total, 2);
+        a.cg->pAp_re = total[0];
+        a.cg->pAp_im = total[1];
+        a.cg->rsq_old = a.cg->rsq_new;
       }
     }
   }
@@ -425,6 +433,8 @@ int launch_normal(glb_operator* op, void* out, const void* in, const ApplyFusion
   if (!f.to_host) a.red.result_host = nullptr;
   a.cg = (CgState*)f.cg_state;
   a.cg_role = f.cg_role;
+  a.pr = f.pr;
+  a.wait = f.wait;
   const int ndot = (f.w != nullptr || f.w_is_input) ? (f.want_norm ? 2 : 1) : 0;
   // ring depth (measured at 4096^2, profiles/): the fused-direction variant streams 4 arrays and gains
   // ~8 % from a 4-deep cp.async ring; the plain variant (3 arrays) is best with register prefetch.

@@ -9,6 +9,7 @@
 
 #include "../../include/glb200.h"
 #include "common.cuh"
+#include "p2p.cuh"
 
 namespace glb {
 
@@ -126,7 +127,10 @@ struct ApplyFusion {
   bool w_is_input = false;   // w == the (possibly fused) input vector
   bool want_norm = false;    // |out|^2
   bool to_host = false;      // copy results to the mapped host buffer
-  int cg_role = 0;           // 0 none, 1: epilogue stores <p,Ap> into CgState
+  int cg_role = 0;           // 0 none, 1: epilogue stores <p,Ap> into CgState, 2: rank-local partial (summed on the
+                             // stream next), 3: the last block sums over ranks itself (peer memory) and publishes
+  P2PRed pr{};               // cg_role 3: descriptor of that reduction
+  HaloWait wait{};           // slabs on the peer-memory path: ghost-row flags to wait for in the prologue
 };
 int launch_staggered(glb_operator* op, void* out, const void* in, bool dagger, const ApplyFusion& f);
 int launch_laplace(glb_operator* op, void* out, const void* in, const ApplyFusion& f);
@@ -144,6 +148,17 @@ int allreduce_device(glb_context* ctx, double* d_vals, int n);
 int allreduce_sum(glb_context* ctx, double* host_vals, int n);
 void comm_destroy(glb_context* ctx);
 bool comm_p2p(const glb_context* ctx);
+P2PRed comm_p2p_red(glb_context* ctx);
+struct HaloTargets {
+  char* dst_down_hi;
+  char* dst_up_lo;
+  unsigned long long* flag_down_hi;
+  unsigned long long* flag_up_lo;
+  HaloWait wait;
+  unsigned int* ticket;
+  size_t bytes;
+};
+int halo_p2p_begin(glb_operator* op, int nrows, HaloTargets* t);
 void* comm_arena_alloc(glb_context* ctx, size_t bytes, size_t* offset);
 
 }  // namespace glb

@@ -77,15 +77,14 @@ unsigned long long glb_kernel_launches(void);
  * vector.  Bootstrapping (exchange of the 128-byte id and of the IPC handles) is done
  * by the host program (torch.distributed in bench.py/tests; any launcher will do).   */
 #define GLB_COMM_ID_BYTES 128
-#define GLB_IPC_HANDLE_BYTES 64
 int glb_comm_unique_id(char id[GLB_COMM_ID_BYTES]);
 int glb_comm_init(glb_context* ctx, int rank, int nranks, const char id[GLB_COMM_ID_BYTES]);
 int glb_comm_rank(glb_context* ctx);
 int glb_comm_size(glb_context* ctx);
-/* Optional NVLink peer-memory fast path for halos and reductions.  Each rank exports one
- * handle for its mailbox; all_handles is the rank-ordered concatenation of every rank's. */
-int glb_comm_export_mailbox(glb_context* ctx, char handle[GLB_IPC_HANDLE_BYTES]);
-int glb_comm_attach_mailboxes(glb_context* ctx, const char* all_handles);
+/* NVLink peer-memory fast path for halos and reductions: glb_comm_init exports this rank's
+ * arena (CUDA IPC), all-gathers the handles through NCCL and maps every peer; 1 if that worked on
+ * every rank (else NCCL send/recv + allreduce are used).  GLB_P2P=0 in the environment disables it. */
+int glb_comm_p2p_enabled(glb_context* ctx);
 int glb_comm_barrier(glb_context* ctx);
 
 /* ---------------------------------------------------------------------- vectors */

@@ -56,8 +56,7 @@ int glb_comm_unique_id(char*) { return GLB_ERR_COMM; }
 int glb_comm_init(glb_context*, int, int, const char*) { return GLB_ERR_COMM; }
 int glb_comm_rank(glb_context*) { return 0; }
 int glb_comm_size(glb_context*) { return 1; }
-int glb_comm_export_mailbox(glb_context*, char*) { return GLB_ERR_COMM; }
-int glb_comm_attach_mailboxes(glb_context*, const char*) { return GLB_ERR_COMM; }
+int glb_comm_p2p_enabled(glb_context*) { return 0; }
 int glb_comm_barrier(glb_context*) { return GLB_OK; }
 int glb_slab_bounds(glb_context*, int Y, int* y0, int* Yloc) { *y0 = 0; *Yloc = Y; return GLB_OK; }
 
