@@ -14,7 +14,9 @@ L x (L*N) lattice, y-slab-sharded over N GPUs (weak scaling: L x L sites per GPU
            (bytes = SURVEY section 8 d-bytes accounting, see algorithmic_bytes()).
   e2e    : same metric through the reference-facing call with HOST (pinned) buffers:
            upload phi, phi0 -> solve -> download phi inside the timed region.
-  roofline : the staggered D apply kernel alone (64 B/site), CUDA events on the library's stream.
+  roofline : the step's dominant kernel (one-pass D^dag D with the fused CG direction update, 96 B/site),
+           every launch timed with CUDA events on the library's stream; the x/r update, the staggered D
+           apply alone (64 B/site) and the plain one-pass D^dag D are listed beside it.
   cpu_baseline : the reference's CPU code (oracle/_ref, else the port) on a bounded sample, 1 core.
 
 --impl reference times the reference's own CPU implementation (same metric/unit/config).
@@ -60,6 +62,17 @@ def algorithmic_bytes(V, iterations):
     the last iteration only does the x,r update                                               =  96
     true residual  apply 128 + diffnorm 32                                                    = 160"""
     return float(V) * (368.0 + 272.0 * max(iterations - 1, 0) + 96.0 + 160.0)
+
+
+def ncu_traffic(kernel, L):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json, written by tools/ncu_summary.py), or None when there is no capture of this
+    kernel at this lattice size"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        return t.get(str(L), {}).get(kernel, {}).get("bytes")
+    except Exception:
+        return None
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -302,6 +315,24 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
+    # ---- roofline leg: the step's own kernels, each launch bracketed by CUDA events on the library's
+    # stream (glb_prof_*), on one more solve of the same workload right after the timed region.  The CG
+    # loop launches [x/r update][direction + D^dag D] per iteration; launches enqueued past the stopping
+    # point return at once and are not counted.
+    ctx.prof_enable(True)
+    info_p = solve_resident()
+    ctx.prof_enable(False)
+    it_p = info_p["iter"]
+    t_fused = ctx.prof_read(1)[:max(it_p - 1, 0)]
+    t_upd = ctx.prof_read(3)[:it_p]
+    fused_ms = max_over_ranks(sum(t_fused) / max(len(t_fused), 1))
+    upd_ms = max_over_ranks(sum(t_upd) / max(len(t_upd), 1))
+    fused_gbps = 96.0 * V_local / (fused_ms * 1e-3) / 1e9 if t_fused else 0.0   # R r,p,U 64 + W p,Ap 32
+    upd_gbps = 96.0 * V_local / (upd_ms * 1e-3) / 1e9 if t_upd else 0.0         # R x,p,r,Ap 64 + W x,r 32
+    step_ms = ms_total / args.steps
+    fused_share = sum(t_fused) / step_ms if step_ms > 0 else 0.0
+    upd_share = sum(t_upd) / step_ms if step_ms > 0 else 0.0
+
     # ---- end to end: the reference-facing call with host (pinned) buffers
     hx, hb = ctx.pinned(V_local), ctx.pinned(V_local)
     hb[:] = bp.download()
@@ -389,13 +420,26 @@ def main():
         "frac_of_hbm_peak": value / world / peak,
         "clocks": sampler.summary(),
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "stag_kernel (staggered D apply, 64 B/site)", "achieved": apply_gbps,
-                     "peak": peak, "unit": "GB/s", "frac": apply_gbps / peak, "traffic": None,
-                     "ms_per_launch": apply_ms, "peak_source": peak_src, "per_gpu": True,
+        "roofline": {"bound": "hbm",
+                     "kernel": "normal_kernel<fused> (p = r + beta p ; Ap = D^dag D p ; <p,Ap> in one pass, 96 B/site): "
+                               "the step's dominant kernel",
+                     "achieved": fused_gbps, "peak": peak, "unit": "GB/s", "frac": fused_gbps / peak,
+                     "traffic": ncu_traffic("normal_kernel_fused", L), "ms_per_launch": fused_ms,
+                     "algorithmic_bytes_per_launch": 96.0 * V_local, "launches_timed": len(t_fused),
+                     "share_of_step": fused_share, "peak_source": peak_src, "per_gpu": True,
+                     "how": "CUDA events around every launch inside one more solve right after the timed region "
+                            "(slab runs: includes waiting for the neighbours' halo rows)",
                      "other_kernels": [
-                         {"kernel": "normal_kernel (D^dag D in one pass, 64 B/site; CG adds the fused p update: 96 B/site)",
+                         {"kernel": "cg_update_kernel (x += alpha p ; r -= alpha Ap ; |r|^2, 96 B/site)",
+                          "achieved": upd_gbps, "frac": upd_gbps / peak, "ms_per_launch": upd_ms,
+                          "traffic": ncu_traffic("cg_update_kernel", L), "share_of_step": upd_share,
+                          "launches_timed": len(t_upd)},
+                         {"kernel": "stag_kernel (staggered D apply alone, 64 B/site; the metric's 'Dirac apply GB/s')",
+                          "achieved": apply_gbps, "frac": apply_gbps / peak, "ms_per_launch": apply_ms,
+                          "traffic": ncu_traffic("stag_kernel", L), "how": "loop of %d applies" % args.apply_reps},
+                         {"kernel": "normal_kernel (D^dag D alone in one pass, 64 B/site)",
                           "achieved": normal_gbps, "frac": normal_gbps / peak, "ms_per_launch": normal_ms,
-                          "note": "slab runs include the 2-row halo exchange"}]},
+                          "traffic": ncu_traffic("normal_kernel", L), "how": "loop of %d applies" % args.apply_reps}]},
         "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": int(2 * 16 * V_local),
                 "d2h_bytes_per_step": int(16 * V_local), "s_per_step": e2e_s / args.steps, "iterations": e2e_iters,
                 "note": "host vectors travel every step (pinned); the gauge field is uploaded once and stays resident"},

@@ -78,6 +78,7 @@ def libs():
         "glb_create": (ci, [ci, C.POINTER(vp)]), "glb_destroy": (ci, [vp]),
         "glb_last_error": (C.c_char_p, []), "glb_synchronize": (ci, [vp]), "glb_stream": (vp, [vp]),
         "glb_device": (ci, [vp]), "glb_sm_count": (ci, [vp]), "glb_kernel_launches": (C.c_ulonglong, []),
+        "glb_prof_enable": (ci, [vp, ci]), "glb_prof_read": (ci, [vp, ci, ci, C.POINTER(C.c_float), C.POINTER(ci)]),
         "glb_comm_unique_id": (ci, [C.c_char_p]), "glb_comm_init": (ci, [vp, ci, ci, C.c_char_p]),
         "glb_comm_p2p_enabled": (ci, [vp]), "glb_comm_rank": (ci, [vp]), "glb_comm_size": (ci, [vp]), "glb_comm_barrier": (ci, [vp]),
         "glb_vec_alloc": (ci, [vp, ci, sz, C.POINTER(vp)]), "glb_vec_free": (ci, [vp, vp]),
@@ -308,6 +309,18 @@ class Context:
 
     def launches(self):
         return int(self.cu.glb_kernel_launches())
+
+    def prof_enable(self, on=True):
+        """per-kernel CUDA-event timing of the classified kernels (include/glb200.h: glb_prof_*)"""
+        _chk(self.cu.glb_prof_enable(self.h, 1 if on else 0), "glb_prof_enable")
+
+    def prof_read(self, cls):
+        """durations (ms) of every launch of kernel class `cls` recorded since prof_enable, in launch order"""
+        n = C.c_int(0)
+        _chk(self.cu.glb_prof_read(self.h, cls, 0, None, C.byref(n)), "glb_prof_read")
+        buf = (C.c_float * max(n.value, 1))()
+        _chk(self.cu.glb_prof_read(self.h, cls, n.value, buf, C.byref(n)), "glb_prof_read")
+        return [float(buf[i]) for i in range(n.value)]
 
     def vector(self, n, dtype=np.complex128):
         return DeviceVector(self, n, dtype)

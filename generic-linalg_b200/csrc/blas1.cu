@@ -434,6 +434,7 @@ int launch_cg_update(glb_context* ctx, int dtype, void* st, double* hist, const 
   if (defer == 2) pr = comm_p2p_red(ctx);
   ReduceWs red = ctx->red;
   red.result_host = nullptr;
+  ProfScope prof(ctx, PROF_CG_UPDATE);
   if (dtype == GLB_COMPLEX) {
     const bool wide = (n % 2 == 0) && ((((uintptr_t)p | (uintptr_t)x | (uintptr_t)Ap | (uintptr_t)r) & 31u) == 0);
     if (wide) {

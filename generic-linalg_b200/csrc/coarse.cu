@@ -8,6 +8,9 @@
 //   lines of matrix data, each element touched once (5*nc^2+2*nc complex per site, HBM-bound).
 // One thread owns one output dof and accumulates clover, +x, +y, -x, -y, (two-link), shifts in
 // exactly the reference's order without FMA contraction -> bit-identical results.
+#include <cstdint>
+#include <cstdlib>
+
 #include "cg_state.cuh"
 #include "runtime.hpp"
 
@@ -138,9 +141,300 @@ __global__ void __launch_bounds__(256) coarse_kernel(const CoarseArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// nc = 1 (the fine-level stencil of get_square_staggered_u1_stencil, operators_stencil.cpp:14-63),
+// five-point, even X: one thread per PAIR of adjacent sites.  The five matrix planes, the input pair
+// and the rows above / below arrive as 32-byte LDG.256 (10 loads for two sites instead of 22 16-byte
+// ones); the two outer x neighbours are 16-byte loads that hit L1.  112 B/site.
+template <int NDOT>
+__global__ void __launch_bounds__(256) stencil1_pair_kernel(const CoarseArgs a) {
+  if (a.cg != nullptr && a.cg->done) return;
+  constexpr int NRED = (NDOT == 0) ? 1 : (NDOT == 1 ? 2 : 3);
+  double acc[NRED];
+#pragma unroll
+  for (int i = 0; i < NRED; i++) acc[i] = 0.0;
+  const int X = a.X, HX = X / 2;
+  const size_t L = (size_t)X * a.Yloc;
+  const size_t npairs = L / 2;
+  for (size_t pi = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pi < npairs; pi += (size_t)gridDim.x * blockDim.x) {
+    const int y = (int)(pi / HX);
+    const int x = 2 * (int)(pi % HX);
+    const size_t i = (size_t)y * X + x;
+    cplx cl[2], hxp[2], hyp[2], hxm[2], hym[2], c[2], up[2], dn[2];
+    ldv_nc<2>(a.clover + i, cl);
+    ldv_nc<2>(a.hopping + i, hxp);
+    ldv_nc<2>(a.hopping + L + i, hyp);
+    ldv_nc<2>(a.hopping + 2 * L + i, hxm);
+    ldv_nc<2>(a.hopping + 3 * L + i, hym);
+    ldv<2>(a.in + i, c);
+    ldv<2>(site_ptr(a, x, y + 1), up);
+    ldv<2>(site_ptr(a, x, y - 1), dn);
+    const cplx left = a.in[(size_t)y * X + (x == 0 ? X - 1 : x - 1)];
+    const cplx right = a.in[(size_t)y * X + (x + 2 == X ? 0 : x + 2)];
+    cplx s[2];
+    s[0] = fadd(mk(0.0, 0.0), fmul(cl[0], c[0]));
+    s[1] = fadd(mk(0.0, 0.0), fmul(cl[1], c[1]));
+    s[0] = fadd(s[0], fmul(hxp[0], c[1]));
+    s[1] = fadd(s[1], fmul(hxp[1], right));
+    s[0] = fadd(s[0], fmul(hyp[0], up[0]));
+    s[1] = fadd(s[1], fmul(hyp[1], up[1]));
+    s[0] = fadd(s[0], fmul(hxm[0], left));
+    s[1] = fadd(s[1], fmul(hxm[1], c[0]));
+    s[0] = fadd(s[0], fmul(hym[0], dn[0]));
+    s[1] = fadd(s[1], fmul(hym[1], dn[1]));
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      if (a.use_shift) s[k] = fadd(s[k], fmul(a.shift, c[k]));  // coarse_stencil.cpp:153-156
+      if (a.use_eo) {                                           // coarse_stencil.cpp:159-162
+        const bool odd = ((x + k + y + a.y0) & 1);
+        s[k] = fadd(s[k], fmul(odd ? fneg(a.eo_shift) : a.eo_shift, c[k]));
+      }
+      // dof_shift: row < nc/2 is never true at nc = 1 (coarse_stencil.cpp:165-169)
+      if (a.use_dof) s[k] = fadd(s[k], fmul(fneg(a.dof_shift), c[k]));
+    }
+    stv<2>(a.out + i, s);
+    if (NDOT >= 1) {
+      cplx wv[2];
+      if (a.w == nullptr) {
+        wv[0] = c[0];
+        wv[1] = c[1];
+      } else {
+        ldv<2>(a.w + i, wv);
+      }
+      Field<cplx>::dot_acc(acc, wv[0], s[0]);
+      Field<cplx>::dot_acc(acc, wv[1], s[1]);
+    }
+    if (NDOT >= 2) {
+      acc[2] += fnorm(s[0]);
+      acc[2] += fnorm(s[1]);
+    }
+  }
+  if (NDOT > 0) {
+    double total[NRED];
+    if (grid_sum<NRED>(acc, a.red, total) && threadIdx.x == 0) {
+      if (a.cg != nullptr && a.cg_role == 1) {
+        a.cg->pAp_re = total[0];
+        a.cg->pAp_im = total[1];
+        a.cg->rsq_old = a.cg->rsq_new;
+      }
+    }
+  }
+}
+
+static int launch_stencil1_pair(glb_context* ctx, const CoarseArgs& a, int ndot, size_t L) {
+  const int grid = blas_grid(ctx, L / 2, 256, 1);
+  ProfScope prof(ctx, PROF_COARSE);
+  if (ndot == 0)
+    stencil1_pair_kernel<0><<<grid, 256, 0, ctx->stream>>>(a);
+  else if (ndot == 1)
+    stencil1_pair_kernel<1><<<grid, 256, 0, ctx->stream>>>(a);
+  else
+    stencil1_pair_kernel<2><<<grid, 256, 0, ctx->stream>>>(a);
+  GLB_LAUNCH_CHECK();
+  return GLB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// nc = 8 / 16: matrices streamed through a per-warp cp.async ring.
+//
+// With one output row per thread the direct kernel above makes every lane read its own 128-byte
+// line (nc = 8): each LDG touches 32 lines and the L1 tag stage, not HBM, bounds it (63 % of peak,
+// profiles/r01_configs.jsonl).  Here a warp owns a tile of 32 consecutive rows (= 32/nc sites); one
+// pipeline stage is ONE direction's matrices of that tile, a contiguous 32*nc*16-byte run of the
+// plane, copied by LDGSTS with consecutive lanes on consecutive 16-byte chunks (4 lines per request)
+// together with the 512 bytes of neighbour-site input the stage multiplies.  Chunks are XOR-swizzled
+// by row so that the row-per-thread LDS.128 reads are bank-conflict free.  RING_STAGES-1 stages per
+// warp stay in flight; the warps never meet at a block barrier.  The accumulation runs clover, +x,
+// +y, -x, -y, (two-link), shifts over c = 0..nc-1 inside one thread exactly as the direct kernel:
+// bit-identical results.
+constexpr int RING_THREADS = 128;
+constexpr int RING_WARPS = RING_THREADS / 32;
+
+__device__ __forceinline__ cplx lds_c(const cplx* p) {
+  cplx r;
+  const unsigned s = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(s));
+  return r;
+}
+
+template <int NC, int NDOT, bool HAS_TWO, int STAGES>
+__global__ void __launch_bounds__(RING_THREADS) coarse_ring_kernel(const CoarseArgs a, const long long ntiles) {
+  extern __shared__ __align__(128) unsigned char ring_raw[];
+  if (a.cg != nullptr && a.cg->done) return;
+  constexpr int NRED = (NDOT == 0) ? 1 : (NDOT == 1 ? 2 : 3);
+  constexpr int NDIR = HAS_TWO ? 13 : 5;
+  constexpr int SITES = 32 / NC;                    // sites per tile
+  constexpr int STAGE_ELEMS = 32 * NC + 32;         // matrices + 32 chunks of input
+  double acc[NRED];
+#pragma unroll
+  for (int i = 0; i < NRED; i++) acc[i] = 0.0;
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int X = a.X;
+  const size_t L = (size_t)X * a.Yloc * NC;
+  const size_t plane = L * NC;
+  cplx* ring = reinterpret_cast<cplx*>(ring_raw) + (size_t)warp * STAGES * STAGE_ELEMS;
+  const long long nwarps = (long long)gridDim.x * RING_WARPS;
+  const long long first = (long long)blockIdx.x * RING_WARPS + warp;
+  const long long mine = (first < ntiles) ? (ntiles - first + nwarps - 1) / nwarps : 0;
+
+  // neighbour of direction d (order of apply_stencil_2d: clover, +x, +y, -x, -y, then the eight
+  // two-link corners +2x, +x+y, +2y, -x+y, -2x, -x-y, -2y, +x-y)
+  auto nbr = [&](int d, int x, int y, int& xn, int& yn) {
+    int dx = 0, dy = 0;
+    switch (d) {
+      case 1: dx = 1; break;
+      case 2: dy = 1; break;
+      case 3: dx = -1; break;
+      case 4: dy = -1; break;
+      case 5: dx = 2; break;
+      case 6: dx = 1; dy = 1; break;
+      case 7: dy = 2; break;
+      case 8: dx = -1; dy = 1; break;
+      case 9: dx = -2; break;
+      case 10: dx = -1; dy = -1; break;
+      case 11: dy = -2; break;
+      case 12: dx = 1; dy = -1; break;
+      default: break;
+    }
+    xn = x + dx;
+    if (xn >= X) xn -= X;
+    if (xn < 0) xn += X;
+    yn = y + dy;
+  };
+
+  // producer side: stage (tile, d) into ring slot `st`
+  long long is_tile = first;  // tile / direction of the next stage to issue
+  int is_d = 0;
+  long long is_left = mine * NDIR;
+  int is_slot = 0;
+  auto issue = [&]() {
+    if (is_left > 0) {
+      cplx* dst = ring + (size_t)is_slot * STAGE_ELEMS;
+      const cplx* M = (is_d == 0) ? a.clover : (is_d < 5 ? a.hopping + (size_t)(is_d - 1) * plane
+                                                         : a.two_link + (size_t)(is_d - 5) * plane);
+      M += (size_t)is_tile * 32 * NC;
+#pragma unroll
+      for (int k = 0; k < NC; k++) {
+        const int e = lane + 32 * k;
+        const int row = e / NC, col = e % NC;
+        cp_async16(dst + row * NC + (col ^ (row & 7)), M + e);
+      }
+      // input of the neighbour sites: lane -> (site of the tile, chunk)
+      const size_t site = (size_t)is_tile * SITES + lane / NC;
+      const int x = (int)(site % X), y = (int)(site / X);
+      int xn, yn;
+      nbr(is_d, x, y, xn, yn);
+      cp_async16(dst + 32 * NC + lane, site_ptr(a, xn, yn) + (lane % NC));
+      is_left--;
+      if (++is_d == NDIR) {
+        is_d = 0;
+        is_tile += nwarps;
+      }
+      if (++is_slot == STAGES) is_slot = 0;
+    }
+    cp_async_commit();
+  };
+
+#pragma unroll
+  for (int k = 0; k < STAGES - 1; k++) issue();
+
+  int slot = 0;
+  long long tile = first;
+#pragma unroll 1
+  for (long long t = 0; t < mine; t++, tile += nwarps) {
+    cplx s = mk(0.0, 0.0);
+    cplx self = mk(0.0, 0.0);
+#pragma unroll 1
+    for (int d = 0; d < NDIR; d++) {
+      __syncwarp();  // every lane is done with the slot the next copy overwrites
+      issue();
+      cp_async_wait<STAGES - 1>();
+      __syncwarp();  // ... and sees the chunks its neighbours copied
+      const cplx* st = ring + (size_t)slot * STAGE_ELEMS;
+      const cplx* mrow = st + lane * NC;
+      const cplx* vrow = st + 32 * NC + (lane / NC) * NC;
+      if (d == 0) self = lds_c(vrow + (lane % NC));
+#pragma unroll
+      for (int c = 0; c < NC; c++) s = fadd(s, fmul(lds_c(mrow + (c ^ (lane & 7))), lds_c(vrow + c)));
+      if (++slot == STAGES) slot = 0;
+    }
+    const size_t i = (size_t)tile * 32 + lane;
+    const int row = lane % NC;
+    if (a.use_shift) s = fadd(s, fmul(a.shift, self));  // coarse_stencil.cpp:153-156
+    if (a.use_eo) {                                     // coarse_stencil.cpp:159-162
+      const size_t site = i / NC;
+      const int x = (int)(site % X), y = (int)(site / X);
+      const bool odd = ((x + y + a.y0) & 1);
+      s = fadd(s, fmul(odd ? fneg(a.eo_shift) : a.eo_shift, self));
+    }
+    if (a.use_dof) s = fadd(s, fmul(row < NC / 2 ? a.dof_shift : fneg(a.dof_shift), self));  // :165-169
+    a.out[i] = s;
+    if (NDOT >= 1) {
+      const cplx wv = (a.w == nullptr) ? self : a.w[i];
+      Field<cplx>::dot_acc(acc, wv, s);
+    }
+    if (NDOT >= 2) acc[2] += fnorm(s);
+  }
+  cp_async_wait<0>();
+  if (NDOT > 0) {
+    double total[NRED];
+    if (grid_sum<NRED>(acc, a.red, total) && threadIdx.x == 0) {
+      if (a.cg != nullptr && a.cg_role == 1) {
+        a.cg->pAp_re = total[0];
+        a.cg->pAp_im = total[1];
+        a.cg->rsq_old = a.cg->rsq_new;
+      }
+    }
+  }
+}
+
+template <int NC, int NDOT, bool HAS_TWO, int STAGES>
+static int launch_ring_t(glb_context* ctx, const CoarseArgs& a, size_t L) {
+  auto kern = coarse_ring_kernel<NC, NDOT, HAS_TWO, STAGES>;
+  const size_t smem = (size_t)RING_WARPS * STAGES * (32 * NC + 32) * sizeof(cplx);
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    GLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RING_THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+  }
+  const long long ntiles = (long long)(L / 32);
+  long long blocks = (ntiles + RING_WARPS - 1) / RING_WARPS;
+  if (blocks > (long long)ctx->sm_count * per_sm) blocks = (long long)ctx->sm_count * per_sm;
+  if (blocks > MAX_PARTIAL_BLOCKS) blocks = MAX_PARTIAL_BLOCKS;
+  if (blocks < 1) blocks = 1;
+  ProfScope prof(ctx, PROF_COARSE);
+  kern<<<(unsigned)blocks, RING_THREADS, smem, ctx->stream>>>(a, ntiles);
+  GLB_LAUNCH_CHECK();
+  return GLB_OK;
+}
+
+template <int NC, int STAGES>
+static int launch_ring(glb_context* ctx, const CoarseArgs& a, int ndot, size_t L) {
+  if (a.has_two) {
+    if (ndot == 0) return launch_ring_t<NC, 0, true, STAGES>(ctx, a, L);
+    if (ndot == 1) return launch_ring_t<NC, 1, true, STAGES>(ctx, a, L);
+    return launch_ring_t<NC, 2, true, STAGES>(ctx, a, L);
+  }
+  if (ndot == 0) return launch_ring_t<NC, 0, false, STAGES>(ctx, a, L);
+  if (ndot == 1) return launch_ring_t<NC, 1, false, STAGES>(ctx, a, L);
+  return launch_ring_t<NC, 2, false, STAGES>(ctx, a, L);
+}
+
+static bool ring_enabled() {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("GLB_COARSE_RING");
+    enabled = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return enabled != 0;
+}
+
 template <int NC>
 static int launch_coarse_nc(glb_context* ctx, const CoarseArgs& a, int ndot, size_t L) {
   const int grid = blas_grid(ctx, L, 256, 1);
+  ProfScope prof(ctx, PROF_COARSE);
   if (ndot == 0)
     coarse_kernel<NC, 0><<<grid, 256, 0, ctx->stream>>>(a);
   else if (ndot == 1)
@@ -184,6 +478,23 @@ int launch_stencil2d(glb_operator* op, void* out, const void* in, const ApplyFus
   a.cg_role = f.cg_role;
   const int ndot = (f.w != nullptr || f.w_is_input) ? (f.want_norm ? 2 : 1) : 0;
   const size_t L = rowlen * op->Yloc;
+  // pairs need 32-byte aligned rows in every array (even X) and the ghost rows to be rows of X sites
+  if (op->nc == 1 && !op->has_two && op->X % 2 == 0 && op->X >= 4 && ring_enabled() &&
+      ((((uintptr_t)a.in | (uintptr_t)a.in_lo | (uintptr_t)a.in_hi | (uintptr_t)a.out | (uintptr_t)a.w) & 31u) == 0))
+    return launch_stencil1_pair(ctx, a, ndot, L);
+  if (ring_enabled() && L % 32 == 0 && L >= 32) {
+    static int stages8 = -1;
+    if (stages8 < 0) {
+      const char* e = getenv("GLB_COARSE_STAGES");
+      stages8 = e ? atoi(e) : 3;  // measured (gpurun t06): 3 stages 96.9 %, 4: 95.0 %, 6: 90.6 % of HBM peak at 512^2
+    }
+    if (op->nc == 8) {
+      if (stages8 == 3) return launch_ring<8, 3>(ctx, a, ndot, L);
+      if (stages8 == 6) return launch_ring<8, 6>(ctx, a, ndot, L);
+      return launch_ring<8, 4>(ctx, a, ndot, L);
+    }
+    if (op->nc == 16) return launch_ring<16, 3>(ctx, a, ndot, L);
+  }
   switch (op->nc) {
     case 1: return launch_coarse_nc<1>(ctx, a, ndot, L);
     case 2: return launch_coarse_nc<2>(ctx, a, ndot, L);

@@ -17,6 +17,7 @@
 //     square_staggered_normal_u1.
 //   * fused epilogue reductions <w,out>, |out|^2 and the device-resident CG hooks as in stencil.cu.
 #include <cstdlib>
+#include <type_traits>
 
 #include "cg_state.cuh"
 #include "runtime.hpp"
@@ -42,7 +43,6 @@ struct NormArgs {
   const cplx* g_hi;
   int X, Y;          // Y = rows of this slab
   double mass;
-  int pf_rows;  // L2 prefetch distance in rows (0 = off)
   int nrb;      // row blocks: work item i -> strip i % nstrips, rows [Y*rb/nrb, Y*(rb+1)/nrb), rb = i / nstrips
   P2PRed pr;    // cg_role 3: the last block finishes the sum over ranks itself (peer memory)
   HaloWait wait;  // peer-memory slabs: ghost-row flags to wait for before touching g_lo / g_hi
@@ -93,11 +93,11 @@ struct NormLoad {  // everything fetched one row ahead: psi(y+2) (raw), U(y+1)
   cplx uy[2];
 };
 
-// STAGES == 0: the next row is prefetched into registers.  STAGES >= 2: every thread owns a ring of
-// STAGES slots in shared memory filled by cp.async (LDGSTS), STAGES-1 rows in flight per thread and no
+// STAGES == 0: the next row is prefetched into registers.  STAGES >= 2: every warp owns a ring of
+// STAGES slots in shared memory filled by cp.async (LDGSTS), STAGES-1 rows in flight per warp and no
 // staging registers -- bytes in flight no longer depend on the register-limited occupancy.
-template <bool FUSE_XPAY, int NDOT, int STAGES>
-__global__ void __launch_bounds__(NORM_THREADS) normal_kernel(const NormArgs a) {
+template <bool FUSE_XPAY, int NDOT, int STAGES, bool UNROLL3, int LAYOUT>
+__global__ void __launch_bounds__(NORM_THREADS, 3) normal_kernel(const NormArgs a) {
   extern __shared__ __align__(32) unsigned char ring_raw[];
   double beta = 0.0;
   if (a.cg != nullptr) {
@@ -172,55 +172,83 @@ __global__ void __launch_bounds__(NORM_THREADS) normal_kernel(const NormArgs a) 
       ldv_nc<2>(a.Uy + o1, L.uy);
     };
 
-    // ---- prologue: t(ya-1), t(ya) from psi(ya-2 .. ya+1)
-    cplx p_c[2], p_n[2], t_m[2], t_c[2], ux_c[2], uy_m[2], uy_c[2];
-    cplx uxl_c;
-    {
+    // ---- register windows: three-slot rings indexed by (row - ya) % 3, so that unrolling the row
+    // loop by three renames registers instead of moving them.  At row y (k = (y - ya) % 3):
+    //   psi(y), psi(y+1), psi(y+2) = p[k], p[k+1], p[k+2];  t(y-1), t(y), t(y+1) = t[k], t[k+1], t[k+2]
+    //   U_y(y-1), U_y(y), U_y(y+1) = uy[k], uy[k+1], uy[k+2];  U_x(y), U_x(y+1) = ux[k+1], ux[k+2]
+    // (slot indices mod 3; uxl = U_x of the site to the left of the pair)
+    cplx p[3][2], t[3][2], ux[3][2], uy[3][2];
+    cplx uxl[3];
+    {  // prologue: t(ya-1), t(ya) from psi(ya-2 .. ya+1)
       cplx p_mm[2], p_m[2], ux_m[2], uy_mm[2];
       load_psi(ya - 2, p_mm);
       load_psi(ya - 1, p_m);
-      load_psi(ya, p_c);
-      load_psi(ya + 1, p_n);
+      load_psi(ya, p[0]);
+      load_psi(ya + 1, p[1]);
       ldv_nc<2>(a.Uy + link_row(ya - 2) + x0, uy_mm);
       ldv_nc<2>(a.Ux + link_row(ya - 1) + x0, ux_m);
-      ldv_nc<2>(a.Uy + link_row(ya - 1) + x0, uy_m);
-      ldv_nc<2>(a.Ux + link_row(ya) + x0, ux_c);
-      ldv_nc<2>(a.Uy + link_row(ya) + x0, uy_c);
+      ldv_nc<2>(a.Uy + link_row(ya - 1) + x0, uy[0]);
+      ldv_nc<2>(a.Ux + link_row(ya) + x0, ux[1]);
+      ldv_nc<2>(a.Uy + link_row(ya) + x0, uy[1]);
       const cplx uxl_m = shfl_up_c(ux_m[1], 1);
-      uxl_c = shfl_up_c(ux_c[1], 1);
-      stag_row<false>(t_m, p_mm, p_m, p_c, ux_m, uxl_m, uy_m, uy_mm, a.mass);  // t(ya-1)
-      stag_row<false>(t_c, p_m, p_c, p_n, ux_c, uxl_c, uy_c, uy_m, a.mass);    // t(ya)
+      uxl[1] = shfl_up_c(ux[1][1], 1);
+      stag_row<false>(t[0], p_mm, p_m, p[0], ux_m, uxl_m, uy[0], uy_mm, a.mass);     // t(ya-1)
+      stag_row<false>(t[1], p_m, p[0], p[1], ux[1], uxl[1], uy[1], uy[0], a.mass);  // t(ya)
     }
     constexpr int NARR = FUSE_XPAY ? 4 : 3;
-    auto slot = [&](int stage, int arr) -> cplx* {  // this thread's 32-byte slot
-      return reinterpret_cast<cplx*>(ring_raw) + ((size_t)(stage * NARR + arr) * NORM_THREADS + threadIdx.x) * 2;
-    };
-    auto issue = [&](int y) {  // asynchronous copies for output row y: psi(y+2), U(y+1); always one commit group
-      if (y < yb) {
-        const int st = y % (STAGES > 0 ? STAGES : 1);
-        const ptrdiff_t o1 = link_row(y + 1) + x0;
-        if (slab && y + 2 >= Y) {
-          const cplx* g = a.g_hi + (size_t)(y + 2 - Y) * X + x0;
-          cp_async16(slot(st, 0), g);
-          cp_async16(slot(st, 0) + 1, g + 1);
+    constexpr int NST = STAGES > 0 ? STAGES : 1;
+    // Ring slot of (stage, array).
+    //  LAYOUT 0: every thread owns a private 32-byte slot and copies its own pair of sites (two 16-byte
+    //            LDGSTS to adjacent addresses: each warp request touches all 32 sectors of the window).
+    //  LAYOUT 1: the warp's 64-site window is stored line by line: lane l copies window sites l and l+32
+    //            (consecutive lanes on consecutive 16-byte chunks: 4 whole lines per LDGSTS request, every
+    //            sector requested once), each 128-byte line stays one shared-memory row, and odd rows swap
+    //            neighbouring chunks (c ^ 1) so that the pair reads (lane l: sites 2l, 2l+1) are
+    //            conflict-free LDS.128.
+    auto phys = [](int j) -> int { return (j & ~7) | ((j & 7) ^ ((j >> 3) & 1)); };
+    cplx* const ring_w = reinterpret_cast<cplx*>(ring_raw) +
+                         (LAYOUT == 0 ? (size_t)threadIdx.x * 2 : (size_t)(threadIdx.x >> 5) * 64);
+    auto slot = [&](int stage, int arr) -> cplx* { return ring_w + (size_t)(stage * NARR + arr) * (NORM_THREADS * 2); };
+    const int win0 = strip * NORM_OUT_PER_WARP - 2;
+    // copy c (0/1) of this lane: ring index and x coordinate
+    const int ia0 = (LAYOUT == 0) ? 0 : phys(lane), ia1 = (LAYOUT == 0) ? 1 : phys(lane + 32);
+    const int xa = (LAYOUT == 0) ? x0 : (((win0 + lane) % X) + X) % X;
+    const int xb = (LAYOUT == 0) ? x0 + 1 : (((win0 + 32 + lane) % X) + X) % X;
+    // reads: this lane's pair
+    const int ir0 = (LAYOUT == 0) ? 0 : phys(2 * lane), ir1 = (LAYOUT == 0) ? 1 : phys(2 * lane + 1);
+    // running state of the producer: output row of the next stage, its ring slot, and the (wrapped)
+    // input row y+2 it reads -- incremented, never divided
+    int is_y = ya, is_st = 0;
+    int is_row2 = ya + 2;
+    if (!slab && is_row2 >= Y) is_row2 -= Y;
+    auto issue = [&]() {  // asynchronous copies for output row is_y: psi(is_y+2), U(is_y+1); always one commit group
+      if (is_y < yb) {
+        const ptrdiff_t o1 = link_row(is_y + 1);
+        if (slab && is_row2 >= Y) {
+          const cplx* g = a.g_hi + (size_t)(is_row2 - Y) * X;
+          cp_async16(slot(is_st, 0) + ia0, g + xa);
+          cp_async16(slot(is_st, 0) + ia1, g + xb);
           if (FUSE_XPAY) {
-            slot(st, 3)[0] = mk(0.0, 0.0);
-            slot(st, 3)[1] = mk(0.0, 0.0);
+            slot(is_st, 3)[ia0] = mk(0.0, 0.0);
+            slot(is_st, 3)[ia1] = mk(0.0, 0.0);
           }
         } else {
-          const size_t o2 = wrap_row(y + 2) + x0;
+          const size_t o2 = (size_t)is_row2 * X;
           const cplx* pa = (FUSE_XPAY ? a.r : a.in) + o2;
-          cp_async16(slot(st, 0), pa);
-          cp_async16(slot(st, 0) + 1, pa + 1);
+          cp_async16(slot(is_st, 0) + ia0, pa + xa);
+          cp_async16(slot(is_st, 0) + ia1, pa + xb);
           if (FUSE_XPAY) {
-            cp_async16(slot(st, 3), a.pold + o2);
-            cp_async16(slot(st, 3) + 1, a.pold + o2 + 1);
+            cp_async16(slot(is_st, 3) + ia0, a.pold + o2 + xa);
+            cp_async16(slot(is_st, 3) + ia1, a.pold + o2 + xb);
           }
         }
-        cp_async16(slot(st, 1), a.Ux + o1);
-        cp_async16(slot(st, 1) + 1, a.Ux + o1 + 1);
-        cp_async16(slot(st, 2), a.Uy + o1);
-        cp_async16(slot(st, 2) + 1, a.Uy + o1 + 1);
+        cp_async16(slot(is_st, 1) + ia0, a.Ux + o1 + xa);
+        cp_async16(slot(is_st, 1) + ia1, a.Ux + o1 + xb);
+        cp_async16(slot(is_st, 2) + ia0, a.Uy + o1 + xa);
+        cp_async16(slot(is_st, 2) + ia1, a.Uy + o1 + xb);
+        is_y++;
+        if (++is_row2 == Y && !slab) is_row2 = 0;
+        if (++is_st == NST) is_st = 0;
       }
       cp_async_commit();
     };
@@ -229,76 +257,61 @@ __global__ void __launch_bounds__(NORM_THREADS) normal_kernel(const NormArgs a) 
       fetch(ya, nxt);
     } else {
 #pragma unroll
-      for (int k = 0; k < (STAGES > 0 ? STAGES - 1 : 0); k++) issue(ya + k);
+      for (int k = 0; k < (STAGES > 0 ? STAGES - 1 : 0); k++) issue();
     }
-    // optional TMA L2 prefetch pf_rows steps ahead: one lane, one request per array (the part of the
-    // 64-site window that does not wrap around the x seam)
-    const int pf_x = (xs - 2 * lane < 0) ? 0 : xs - 2 * lane;
-    const int pf_w = min(X, xs - 2 * lane + 64) - pf_x;
-    auto prefetch_rows = [&](int y) {
-      if (lane == 0 && pf_w > 0) {
-        const unsigned bytes = (unsigned)pf_w * 16u;
-        if (!slab || y + 2 < Y) {
-          const size_t o2 = wrap_row(y + 2) + pf_x;
-          if (FUSE_XPAY) {
-            prefetch_l2_bulk(a.r + o2, bytes);
-            prefetch_l2_bulk(a.pold + o2, bytes);
-          } else {
-            prefetch_l2_bulk(a.in + o2, bytes);
-          }
-        }
-        if (y + 1 < Y + 2) {
-          prefetch_l2_bulk(a.Ux + link_row(y + 1) + pf_x, bytes);
-          prefetch_l2_bulk(a.Uy + link_row(y + 1) + pf_x, bytes);
-        }
-      }
-    };
-    if (a.pf_rows > 0)
-      for (int k = 1; k < a.pf_rows; k++) prefetch_rows(ya + k);
 
-#pragma unroll 1
-    for (int y = ya; y < yb; y++) {
-      NormLoad<FUSE_XPAY> cur;
+    int rd_st = 0;  // consumer's ring slot
+    // one output row; K = (y - ya) % 3 selects the register slots at compile time
+    auto row_step = [&](auto Kc, const int y) {
+      constexpr int K0 = decltype(Kc)::value % 3, K1 = (K0 + 1) % 3, K2 = (K0 + 2) % 3;
+      cplx la[2], lb[2];
       if (STAGES == 0) {
-        cur = nxt;
+        la[0] = nxt.a[0];
+        la[1] = nxt.a[1];
+        lb[0] = nxt.b[0];
+        lb[1] = nxt.b[1];
+        ux[K2][0] = nxt.ux[0];
+        ux[K2][1] = nxt.ux[1];
+        uy[K2][0] = nxt.uy[0];
+        uy[K2][1] = nxt.uy[1];
         if (y + 1 < yb) fetch(y + 1, nxt);  // prefetch while this row is computed
       } else {
-        issue(y + STAGES - 1);                           // keep STAGES-1 rows in flight
-        cp_async_wait<(STAGES > 0 ? STAGES - 1 : 0)>();  // the group of row y has landed
-        const int st = y % (STAGES > 0 ? STAGES : 1);
-        cur.a[0] = slot(st, 0)[0];
-        cur.a[1] = slot(st, 0)[1];
-        cur.ux[0] = slot(st, 1)[0];
-        cur.ux[1] = slot(st, 1)[1];
-        cur.uy[0] = slot(st, 2)[0];
-        cur.uy[1] = slot(st, 2)[1];
+        if (LAYOUT != 0) __syncwarp();                   // all lanes are done with the slot refilled next
+        issue();                                         // keep STAGES-1 rows in flight
+        cp_async_wait<(STAGES > 0 ? STAGES - 1 : 0)>();  // this lane's copies of row y have landed
+        if (LAYOUT != 0) __syncwarp();                   // ... and so have the other lanes'
+        la[0] = slot(rd_st, 0)[ir0];
+        la[1] = slot(rd_st, 0)[ir1];
+        ux[K2][0] = slot(rd_st, 1)[ir0];
+        ux[K2][1] = slot(rd_st, 1)[ir1];
+        uy[K2][0] = slot(rd_st, 2)[ir0];
+        uy[K2][1] = slot(rd_st, 2)[ir1];
         if (FUSE_XPAY) {
-          cur.b[0] = slot(st, 3)[0];
-          cur.b[1] = slot(st, 3)[1];
+          lb[0] = slot(rd_st, 3)[ir0];
+          lb[1] = slot(rd_st, 3)[ir1];
         }
+        if (++rd_st == NST) rd_st = 0;
       }
-      if (a.pf_rows > 0) prefetch_rows(y + a.pf_rows);
-      cplx p_nn[2];
       if (FUSE_XPAY) {
-        p_nn[0] = fadd(cur.a[0], fscale(beta, cur.b[0]));
-        p_nn[1] = fadd(cur.a[1], fscale(beta, cur.b[1]));
+        p[K2][0] = fadd(la[0], fscale(beta, lb[0]));
+        p[K2][1] = fadd(la[1], fscale(beta, lb[1]));
       } else {
-        p_nn[0] = cur.a[0];
-        p_nn[1] = cur.a[1];
+        p[K2][0] = la[0];
+        p[K2][1] = la[1];
       }
-      const cplx uxl_n = shfl_up_c(cur.ux[1], 1);
-      cplx t_n[2], res[2];
-      stag_row<false>(t_n, p_c, p_n, p_nn, cur.ux, uxl_n, cur.uy, uy_c, a.mass);  // t(y+1) = D psi
-      stag_row<true>(res, t_m, t_c, t_n, ux_c, uxl_c, uy_c, uy_m, a.mass);        // out(y) = D^dag t
+      uxl[K2] = shfl_up_c(ux[K2][1], 1);
+      cplx res[2];
+      stag_row<false>(t[K2], p[K0], p[K1], p[K2], ux[K2], uxl[K2], uy[K2], uy[K1], a.mass);  // t(y+1) = D psi
+      stag_row<true>(res, t[K0], t[K1], t[K2], ux[K1], uxl[K1], uy[K1], uy[K0], a.mass);     // out(y) = D^dag t
       if (active) {
         const size_t o = (size_t)y * X + x0;
         stv<2>(a.out + o, res);
-        if (FUSE_XPAY) stv<2>(a.pnew + o, p_c);
+        if (FUSE_XPAY) stv<2>(a.pnew + o, p[K0]);
         if (NDOT >= 1) {
           cplx wv[2];
           if (a.w == nullptr) {
-            wv[0] = p_c[0];
-            wv[1] = p_c[1];
+            wv[0] = p[K0][0];
+            wv[1] = p[K0][1];
           } else {
             ldv<2>(a.w + o, wv);
           }
@@ -310,19 +323,38 @@ __global__ void __launch_bounds__(NORM_THREADS) normal_kernel(const NormArgs a) 
           acc[2] += fnorm(res[1]);
         }
       }
-#pragma unroll
-      for (int s = 0; s < 2; s++) {  // roll the windows
-        p_c[s] = p_n[s];
-        p_n[s] = p_nn[s];
-        t_m[s] = t_c[s];
-        t_c[s] = t_n[s];
-        ux_c[s] = cur.ux[s];
-        uy_m[s] = uy_c[s];
-        uy_c[s] = cur.uy[s];
+    };
+    if (UNROLL3) {
+      int y = ya;
+#pragma unroll 1
+      for (; y + 3 <= yb; y += 3) {
+        row_step(std::integral_constant<int, 0>(), y);
+        row_step(std::integral_constant<int, 1>(), y + 1);
+        row_step(std::integral_constant<int, 2>(), y + 2);
       }
-      uxl_c = uxl_n;
+      if (y < yb) row_step(std::integral_constant<int, 0>(), y);
+      if (y + 1 < yb) row_step(std::integral_constant<int, 1>(), y + 1);
+    } else {
+#pragma unroll 1
+      for (int y = ya; y < yb; y++) {
+        row_step(std::integral_constant<int, 0>(), y);
+#pragma unroll
+        for (int s2 = 0; s2 < 2; s2++) {  // roll the windows
+          p[0][s2] = p[1][s2];
+          p[1][s2] = p[2][s2];
+          t[0][s2] = t[1][s2];
+          t[1][s2] = t[2][s2];
+          uy[0][s2] = uy[1][s2];
+          uy[1][s2] = uy[2][s2];
+          ux[1][s2] = ux[2][s2];
+        }
+        uxl[1] = uxl[2];
+      }
     }
-    if (STAGES > 0) cp_async_wait<0>();
+    if (STAGES > 0) {
+      cp_async_wait<0>();
+      __syncwarp();  // the next item's prologue refills slots other lanes may still be reading
+    }
   }
 
   if (NDOT > 0) {
@@ -345,11 +377,11 @@ __global__ void __launch_bounds__(NORM_THREADS) normal_kernel(const NormArgs a) 
   }
 }
 
-template <bool FUSE, int NDOT, int STAGES>
+template <bool FUSE, int NDOT, int STAGES, bool UNROLL3, int LAYOUT>
 static int launch_normal_t(glb_operator* op, const NormArgs& a) {
   glb_context* ctx = op->ctx;
-  auto kern = normal_kernel<FUSE, NDOT, STAGES>;
-  const size_t smem = (size_t)STAGES * (FUSE ? 4 : 3) * NORM_THREADS * 32;
+  auto kern = normal_kernel<FUSE, NDOT, STAGES, UNROLL3, LAYOUT>;
+  const size_t smem = (size_t)STAGES * (FUSE ? 4 : 3) * NORM_THREADS * 2 * sizeof(cplx);
   static int per_sm = 0;
   if (per_sm == 0) {
     // static shared memory of the reduction epilogue rides on top of the dynamic ring
@@ -371,21 +403,22 @@ static int launch_normal_t(glb_operator* op, const NormArgs& a) {
   if (blocks > (long long)ctx->sm_count * per_sm) blocks = (long long)ctx->sm_count * per_sm;
   if (blocks < 1) blocks = 1;
   if (blocks > MAX_PARTIAL_BLOCKS) blocks = MAX_PARTIAL_BLOCKS;
+  ProfScope prof(ctx, FUSE ? PROF_NORMAL_FUSED : PROF_NORMAL);
   kern<<<(unsigned)blocks, NORM_THREADS, smem, ctx->stream>>>(b);
   GLB_LAUNCH_CHECK();
   return GLB_OK;
 }
 
-template <int STAGES>
+template <int STAGES, bool UNROLL3, int LAYOUT>
 static int launch_normal_s(glb_operator* op, const NormArgs& a, bool fuse, int ndot) {
   if (fuse) {
-    if (ndot == 0) return launch_normal_t<true, 0, STAGES>(op, a);
-    if (ndot == 1) return launch_normal_t<true, 1, STAGES>(op, a);
-    return launch_normal_t<true, 2, STAGES>(op, a);
+    if (ndot == 0) return launch_normal_t<true, 0, STAGES, UNROLL3, LAYOUT>(op, a);
+    if (ndot == 1) return launch_normal_t<true, 1, STAGES, UNROLL3, LAYOUT>(op, a);
+    return launch_normal_t<true, 2, STAGES, UNROLL3, LAYOUT>(op, a);
   }
-  if (ndot == 0) return launch_normal_t<false, 0, STAGES>(op, a);
-  if (ndot == 1) return launch_normal_t<false, 1, STAGES>(op, a);
-  return launch_normal_t<false, 2, STAGES>(op, a);
+  if (ndot == 0) return launch_normal_t<false, 0, STAGES, UNROLL3, LAYOUT>(op, a);
+  if (ndot == 1) return launch_normal_t<false, 1, STAGES, UNROLL3, LAYOUT>(op, a);
+  return launch_normal_t<false, 2, STAGES, UNROLL3, LAYOUT>(op, a);
 }
 
 // can the one-pass kernel serve this operator?  (gauged, even X; slabs at least two rows thick)
@@ -421,14 +454,6 @@ int launch_normal(glb_operator* op, void* out, const void* in, const ApplyFusion
     a.g_hi = (const cplx*)op->ghost_hi;
   }
   a.mass = op->mass;
-  {
-    static int pf = -1;
-    if (pf < 0) {
-      const char* e = getenv("GLB_PF_L2");
-      pf = e ? atoi(e) : 0;  // measured: L2 bulk prefetch costs bandwidth here (profiles/), off by default
-    }
-    a.pf_rows = pf;
-  }
   a.red = ctx->red;
   if (!f.to_host) a.red.result_host = nullptr;
   a.cg = (CgState*)f.cg_state;
@@ -438,20 +463,32 @@ int launch_normal(glb_operator* op, void* out, const void* in, const ApplyFusion
   const int ndot = (f.w != nullptr || f.w_is_input) ? (f.want_norm ? 2 : 1) : 0;
   // ring depth (measured at 4096^2, profiles/): the fused-direction variant streams 4 arrays and gains
   // ~8 % from a 4-deep cp.async ring; the plain variant (3 arrays) is best with register prefetch.
-  static int stages_fused = -1, stages_plain = -1;
+  static int stages_fused = -1, stages_plain = -1, unroll3 = -1, layout = -1;
   if (stages_fused < 0) {
     const char* e = getenv("GLB_NORMAL_STAGES");
     stages_fused = e ? atoi(e) : 4;
     const char* e2 = getenv("GLB_NORMAL_STAGES_PLAIN");
     stages_plain = e2 ? atoi(e2) : 0;
+    const char* e3 = getenv("GLB_NORMAL_UNROLL");  // 3: row loop unrolled by the window period (no register moves)
+    unroll3 = (e3 && atoi(e3) == 1) ? 0 : 1;
+    const char* e4 = getenv("GLB_NORMAL_LAYOUT");  // ring layout: 0 private slots, 1 line-contiguous (coalesced copies)
+    layout = e4 ? atoi(e4) : 1;
   }
   const int stages = fuse ? stages_fused : stages_plain;
-  switch (stages) {
-    case 3: return launch_normal_s<3>(op, a, fuse, ndot);
-    case 4: return launch_normal_s<4>(op, a, fuse, ndot);
-    case 6: return launch_normal_s<6>(op, a, fuse, ndot);
-    default: return launch_normal_s<0>(op, a, fuse, ndot);
+  if (stages == 4 || stages == 3) {
+    const int key = (stages == 4 ? 4 : 0) | (unroll3 ? 2 : 0) | (layout ? 1 : 0);
+    switch (key) {
+      case 7: return launch_normal_s<4, true, 1>(op, a, fuse, ndot);
+      case 6: return launch_normal_s<4, true, 0>(op, a, fuse, ndot);
+      case 5: return launch_normal_s<4, false, 1>(op, a, fuse, ndot);
+      case 4: return launch_normal_s<4, false, 0>(op, a, fuse, ndot);
+      case 3: return launch_normal_s<3, true, 1>(op, a, fuse, ndot);
+      case 2: return launch_normal_s<3, true, 0>(op, a, fuse, ndot);
+      case 1: return launch_normal_s<3, false, 1>(op, a, fuse, ndot);
+      default: return launch_normal_s<3, false, 0>(op, a, fuse, ndot);
+    }
   }
+  return launch_normal_s<0, false, 0>(op, a, fuse, ndot);  // register prefetch (unrolling it spills)
 }
 
 }  // namespace glb

@@ -66,6 +66,7 @@ int glb_destroy(glb_context* ctx) {
   if (!ctx) return GLB_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  glb_prof_enable(ctx, 1);  // drops recorded events
   comm_destroy(ctx);
   cudaFree(ctx->red.partials);
   cudaFree(ctx->red.ticket);
@@ -87,6 +88,31 @@ int glb_synchronize(glb_context* ctx) {
 void* glb_stream(glb_context* ctx) { return (void*)ctx->stream; }
 int glb_device(glb_context* ctx) { return ctx->device; }
 int glb_sm_count(glb_context* ctx) { return ctx->sm_count; }
+
+int glb_prof_enable(glb_context* ctx, int on) {
+  if (!ctx) return fail(GLB_ERR_ARG, "glb_prof_enable: null context");
+  if (on) {
+    for (auto& r : ctx->prof) {
+      cudaEventDestroy(r.a);
+      cudaEventDestroy(r.b);
+    }
+    ctx->prof.clear();
+  }
+  ctx->prof_on = (on != 0);
+  return GLB_OK;
+}
+int glb_prof_read(glb_context* ctx, int cls, int cap, float* ms, int* n) {
+  if (!ctx || !n) return fail(GLB_ERR_ARG, "glb_prof_read: null argument");
+  GLB_CUDA(cudaStreamSynchronize(ctx->stream));
+  int k = 0;
+  for (auto& r : ctx->prof) {
+    if (r.cls != cls) continue;
+    if (ms && k < cap) GLB_CUDA(cudaEventElapsedTime(&ms[k], r.a, r.b));
+    k++;
+  }
+  *n = k;
+  return GLB_OK;
+}
 
 int glb_vec_alloc(glb_context* ctx, int dtype, size_t n, void** dptr) {
   if (!dptr) return fail(GLB_ERR_ARG, "glb_vec_alloc: null output");

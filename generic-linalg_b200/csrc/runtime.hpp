@@ -34,6 +34,21 @@ extern std::atomic<unsigned long long> g_launches;
 
 struct Comm;  // comm.cu
 
+// per-kernel timing for bench.py's roofline leg (glb_prof_*): while enabled, the launchers of the
+// classified kernels bracket each launch with a pair of CUDA events on the context's stream
+enum ProfClass {
+  PROF_NORMAL_FUSED = 1,  // normal_kernel with the fused CG direction update (96 B/site)
+  PROF_NORMAL = 2,        // normal_kernel, plain D^dag D (64 B/site)
+  PROF_CG_UPDATE = 3,     // cg_update_kernel (96 B/site)
+  PROF_STAG = 4,          // stag_kernel, any flavour
+  PROF_COARSE = 5,        // coarse_kernel / coarse_ring_kernel
+  PROF_LAPLACE = 6
+};
+struct ProfRec {
+  cudaEvent_t a, b;
+  int cls;
+};
+
 }  // namespace glb
 
 struct glb_context {
@@ -52,6 +67,9 @@ struct glb_context {
   // slab communicator
   int rank = 0, nranks = 1;
   glb::Comm* comm = nullptr;
+  // kernel timing (off by default)
+  bool prof_on = false;
+  std::vector<glb::ProfRec> prof;
 };
 
 namespace glb {
@@ -109,6 +127,24 @@ struct glb_operator {
 };
 
 namespace glb {
+
+// RAII bracket around one classified launch; a no-op unless glb_prof_enable(ctx, 1) was called
+struct ProfScope {
+  glb_context* ctx;
+  cudaEvent_t b = nullptr;
+  ProfScope(glb_context* c, int cls) : ctx(c) {
+    if (!c->prof_on) return;
+    ProfRec r{};
+    r.cls = cls;
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    cudaEventRecord(r.a, c->stream);
+    b = r.b;
+    c->prof.push_back(r);
+  }
+  ~ProfScope() {
+    if (b) cudaEventRecord(b, ctx->stream);
+  }
+};
 
 inline size_t elem_bytes(int dtype) { return dtype == GLB_COMPLEX ? 16 : 8; }
 

@@ -427,6 +427,7 @@ static int launch_stag_t(glb_operator* op, const StagArgs& a) {
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   if (blocks > MAX_PARTIAL_BLOCKS) blocks = MAX_PARTIAL_BLOCKS;
+  ProfScope prof(ctx, PROF_STAG);
   kern<<<(unsigned)blocks, STAG_THREADS, 0, ctx->stream>>>(b);
   GLB_LAUNCH_CHECK();
   return GLB_OK;
@@ -541,6 +542,7 @@ static int launch_laplace_t(glb_operator* op, void* out, const void* in, const A
   a.cg_role = f.cg_role;
   const int ndot = (f.w != nullptr || f.w_is_input) ? (f.want_norm ? 2 : 1) : 0;
   const int grid = blas_grid(ctx, RX * op->Yloc, 256, 1);
+  ProfScope prof(ctx, PROF_LAPLACE);
   if (ndot == 0)
     laplace_kernel<T, 0><<<grid, 256, 0, ctx->stream>>>(a);
   else if (ndot == 1)

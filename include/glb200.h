@@ -71,6 +71,14 @@ int glb_device(glb_context* ctx);
 int glb_sm_count(glb_context* ctx);
 /* number of kernels this library has launched so far in this process (bench.py: gpu_launches) */
 unsigned long long glb_kernel_launches(void);
+/* Per-kernel timing (measurement aid, bench.py roofline leg).  While enabled, every launch of a
+   classified kernel is bracketed by two CUDA events on the context's stream.  Classes: 1 one-pass
+   D^dag D with the fused CG direction update, 2 one-pass D^dag D, 3 CG x/r update, 4 staggered /
+   gauged-Laplace stencil, 5 coarse stencil, 6 Laplace.  glb_prof_enable(ctx,1) clears and starts,
+   (ctx,0) stops; glb_prof_read synchronises and returns the durations (ms) of class `cls` in launch
+   order (at most cap of them; *n = how many were recorded). */
+int glb_prof_enable(glb_context* ctx, int on);
+int glb_prof_read(glb_context* ctx, int cls, int cap, float* ms, int* n);
 
 /* ------------------------------------------------------ slab communicator (y-slabs) */
 /* One process per GPU.  Rank g of G owns rows [g*Y/G, (g+1)*Y/G) of every lattice

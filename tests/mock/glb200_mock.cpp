@@ -52,6 +52,8 @@ void* glb_stream(glb_context*) { return 0; }
 int glb_device(glb_context*) { return -1; }
 int glb_sm_count(glb_context*) { return 0; }
 unsigned long long glb_kernel_launches(void) { return g_calls; }
+int glb_prof_enable(glb_context*, int) { return GLB_OK; }
+int glb_prof_read(glb_context*, int, int, float*, int* n) { if (n) *n = 0; return GLB_OK; }
 int glb_comm_unique_id(char*) { return GLB_ERR_COMM; }
 int glb_comm_init(glb_context*, int, int, const char*) { return GLB_ERR_COMM; }
 int glb_comm_rank(glb_context*) { return 0; }

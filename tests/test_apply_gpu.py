@@ -62,7 +62,14 @@ def test_laplace_family(ctx, glb, orc, X, Y, Nc):
 
 
 @pytest.mark.parametrize("X,Y,nc,two", [(4, 4, 1, False), (6, 8, 2, True), (16, 16, 4, False), (32, 16, 8, False),
-                                         (8, 8, 8, True), (5, 7, 3, True), (64, 64, 8, False)])
+                                         (8, 8, 8, True), (5, 7, 3, True), (64, 64, 8, False),
+                                         # cp.async-ring kernel (nc = 8, 16; dofs a multiple of 32): tiles that
+                                         # straddle rows, more tiles than resident warps, and the ragged
+                                         # volumes that must fall back to the direct kernel
+                                         (6, 6, 8, False), (5, 6, 8, True), (12, 10, 16, False), (8, 6, 16, True),
+                                         (256, 192, 8, False), (96, 64, 8, True),
+                                         # nc = 1: pair-per-thread kernel (even X), generic kernel otherwise
+                                         (64, 48, 1, False), (7, 6, 1, False), (10, 4, 1, True)])
 def test_coarse_stencil(ctx, glb, orc, X, Y, nc, two):
     V = X * Y
     rg = np.random.default_rng(nc + 10 * two)
@@ -128,6 +135,29 @@ def test_apply_dot_fusion(ctx, glb, orc):
         assert abs(dot3 - np.vdot(b, y)) <= 1e-12 * abs(np.vdot(b, y)) and abs(nrm3 - ref_nrm) <= 1e-12 * ref_nrm
         # reproducible: same call, same bits
         assert op.apply_dot(out, x, w, want_norm=True) == (dot, nrm)
+
+
+@pytest.mark.parametrize("nc,two", [(8, False), (8, True), (16, False), (4, False)])
+def test_coarse_apply_dot_fusion(ctx, glb, orc, nc, two):
+    """apply_stencil_2d with the fused <w,out>, |out|^2 epilogue (ring kernel for nc = 8/16): the output is
+    bit-identical to the oracle, the sums agree with numpy and are run-to-run reproducible"""
+    X, Y = 48, 40
+    V = X * Y
+    rg = np.random.default_rng(77 + nc)
+    rc = lambda n: rg.standard_normal(n) + 1j * rg.standard_normal(n)
+    cl, hp, tl = rc(V * nc * nc), rc(4 * V * nc * nc), (rc(8 * V * nc * nc) if two else None)
+    v, w_host = rc(V * nc), rc(V * nc)
+    op = ctx.stencil2d(cl, hp, tl, X, Y, nc, shift=0.25)
+    want = orc.op("STENCIL", X, Y, Nc=nc, clover=cl, hopping=hp, two_link=tl, shift=0.25).apply(v)
+    x, w, out = ctx.vector(V * nc).upload(v), ctx.vector(V * nc).upload(w_host), ctx.vector(V * nc)
+    dot, nrm = op.apply_dot(out, x, w, want_norm=True)
+    y = out.download()
+    assert np.array_equal(y, want)
+    ref_dot, ref_nrm = np.vdot(w_host, y), np.vdot(y, y).real
+    assert abs(dot - ref_dot) <= 1e-12 * abs(ref_dot) and abs(nrm - ref_nrm) <= 1e-12 * ref_nrm
+    dot2, _ = op.apply_dot(out, x, None)
+    assert abs(dot2 - np.vdot(v, y)) <= 1e-12 * abs(np.vdot(v, y))
+    assert op.apply_dot(out, x, w, want_norm=True) == (dot, nrm)
 
 
 @pytest.mark.parametrize("L", [1024, 4096])
