@@ -129,7 +129,8 @@ def main():
 
     # ---- 3. config 5 pieces: coarse stencil apply (512^2, nc = 8) and the nc = 1 fine stencil at 2048^2
     rg = np.random.default_rng(0)
-    for X, nc, two in ([(256, 8, False)] if quick else [(512, 8, False), (512, 8, True), (2048, 1, False), (512, 4, False)]):
+    for X, nc, two in ([(256, 8, False)] if quick else [(512, 8, False), (512, 8, True), (256, 16, False), (2048, 1, False),
+                                                        (512, 4, False)]):
         Vc = X * X
         m = Vc * nc * nc
         cl = (rg.standard_normal(m) + 1j * rg.standard_normal(m))
@@ -144,6 +145,68 @@ def main():
              bytes_per_site=bps, GBps=bps * Vc / ms / 1e6, frac_of_measured_hbm_peak=bps * Vc / ms / 1e6 / PEAK)
         op.destroy()
         del v, w, cl, hp, tl
+
+    # ---- 3b. config 5, gated solves: unpreconditioned minv_vector_gcr_restart(..., 64, ...) on the fine level
+    # (nc = 1 stencil of the 2048^2 staggered operator, built as get_square_staggered_u1_stencil does,
+    # operators_stencil.cpp:14-63; tol 5e-7 = the outer precision of input_params.cpp:638) and on a
+    # 512^2 x 8 coarse level (synthetic diagonally dominant stencil -- the MG set-up that would produce
+    # the real one is SURVEY 8f-2; tol 1e-2 = the coarse precision, input_params.cpp:790)
+    if not quick:
+        L = 2048
+        V = L * L
+        rows = list(range(L))
+        U = bench.gauge_rows(L, rows).reshape(L, L, 2)
+        eta = (1.0 - 2.0 * (np.arange(L) % 2))[None, :]
+        hop = np.empty((4, L, L), dtype=np.complex128)
+        hop[0] = -0.5 * U[:, :, 0]
+        hop[1] = -0.5 * eta * U[:, :, 1]
+        hop[2] = 0.5 * np.conj(np.roll(U[:, :, 0], 1, axis=1))
+        hop[3] = 0.5 * eta * np.conj(np.roll(U[:, :, 1], 1, axis=0))
+        op = ctx.stencil2d(np.zeros(V, dtype=np.complex128), hop.reshape(-1), None, L, L, 1, shift=0.1)
+        Dref = ctx.staggered(U.reshape(-1), L, L, 0.1, 0)
+        bh = bench.rhs_rows(L, rows)
+        b, x, chk = ctx.vector(V).upload(bh), ctx.vector(V), ctx.vector(V)
+        op.apply(x, b)
+        Dref.apply(chk, b)
+        xs_, cs_ = x.download(), chk.download()   # staggered_stencil.cpp:232: function operator vs stencil operator
+        same = float(np.linalg.norm(xs_ - cs_) / np.linalg.norm(cs_))
+        del xs_, cs_
+        for _ in range(2):
+            x.zero()
+            ctx.sync()
+            t0 = time.perf_counter()
+            info = ctx.solve("GCR_RESTART", op, x, b, max_iter=100000, eps=5e-7, restart_freq=64)
+            dt = time.perf_counter() - t0
+        gb = (288.0 + 48.0 * 31.5 + (112.0 - 64.0)) * info["iter"] * V / 1e9   # d-bytes GCR, stencil apply 112 B/site
+        emit(kind="solve", L=L, solver="config 5 fine level: minv_vector_gcr_restart(64) on the nc=1 stencil, tol 5e-7",
+             seconds=dt, iterations=info["iter"], ops=info["ops_count"], success=info["success"],
+             iterations_per_s=info["iter"] / dt, stencil_vs_function_operator_rel_diff=same,
+             true_rel_residual=float(np.sqrt(info["resSq"]) / np.sqrt(ctx.norm2sq(b))),
+             algorithmic_GB=gb, GBps=gb / dt, frac_of_measured_hbm_peak=gb / dt / PEAK)
+        op.destroy()
+        Dref.destroy()
+        del b, x, chk, hop, U
+        Xc, nc = 512, 8
+        Vc = Xc * Xc
+        m = Vc * nc * nc
+        cl = 0.1 * (rg.standard_normal(m) + 1j * rg.standard_normal(m))
+        cl.reshape(Vc, nc, nc)[:, np.arange(nc), np.arange(nc)] += 1.0
+        hp = 0.2 * (rg.standard_normal(4 * m) + 1j * rg.standard_normal(4 * m)) / np.sqrt(nc)
+        op = ctx.stencil2d(cl, hp, None, Xc, Xc, nc)
+        b = ctx.vector(Vc * nc).upload(rg.standard_normal(Vc * nc) + 1j * rg.standard_normal(Vc * nc))
+        x = ctx.vector(Vc * nc)
+        for _ in range(2):
+            x.zero()
+            ctx.sync()
+            t0 = time.perf_counter()
+            info = ctx.solve("GCR_RESTART", op, x, b, max_iter=1024, eps=1e-2, restart_freq=64)
+            dt = time.perf_counter() - t0
+        emit(kind="solve", L=Xc, solver="config 5 coarse level: minv_vector_gcr_restart(64) on a 512^2 x 8 stencil, tol 1e-2",
+             seconds=dt, iterations=info["iter"], ops=info["ops_count"], success=info["success"],
+             iterations_per_s=info["iter"] / dt,
+             true_rel_residual=float(np.sqrt(info["resSq"]) / np.sqrt(ctx.norm2sq(b))))
+        op.destroy()
+        del b, x, cl, hp
 
     # ---- 4. config 1: real 64^2 Laplace, CG to 1e-10 (launch/latency-bound: 32 KiB vectors)
     N = 64

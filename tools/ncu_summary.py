@@ -17,10 +17,27 @@ def short(name):
     m = re.search(r"normal_kernel<[^>]*>", name)
     if m:
         return m.group(0)
+    m = re.search(r"coarse_ring_kernel<[^>]*>", name)
+    if m:
+        return m.group(0)
     m = re.search(r"ew_kernel<[^,]*, *(?:glb::)?(\w+)", name)
     if m:
         return "ew_kernel<" + m.group(1) + ">"
     return re.sub(r"\(.*", "", name).replace("void ", "").replace("glb::", "")
+
+
+def traffic_key(name):
+    """bench.py's name for the kernels whose DRAM traffic it reports (profiles/ncu_traffic.json)"""
+    m = re.match(r"normal_kernel<([01]),", name)
+    if m:
+        return "normal_kernel_fused" if m.group(1) == "1" else "normal_kernel"
+    if name.startswith("cg_update_kernel"):
+        return "cg_update_kernel"
+    if name.startswith("stag_kernel"):
+        return "stag_kernel"
+    if name.startswith("coarse_ring_kernel"):
+        return "coarse_ring_kernel"
+    return None
 
 
 def launches(path):
@@ -79,6 +96,9 @@ def main():
             md.append("| `%s` | %d | %.2f | %.1f | %.1f %% |" % (k, v[0], v[1] / 1e3, v[1] / v[0], 100 * v[1] / tot))
         md.append("")
     rp = os.path.join(src, "prof_top.ncu-rep")
+    tpath = os.path.join("profiles", "ncu_traffic.json")
+    traffic = json.load(open(tpath)) if os.path.exists(tpath) else {}
+    lattice = int(sys.argv[3]) if len(sys.argv) > 3 else 4096   # lattice extent of the captured command
     if os.path.exists(rp):
         md.append("## `ncu --set full --clock-control none --import-source on` (per launch)\n")
         md.append("| kernel | time | DRAM read | DRAM write | traffic GB | GB/s | DRAM %% of ncu peak | warps active %% | regs | grid x block | L2 hit %% |\n|---|---|---|---|---:|---:|---|---|---|---|---|")
@@ -92,6 +112,10 @@ def main():
             if d["gpu__time_duration.sum"].split()[1] == "ms":
                 t_us *= 1e3
             tr = gb(d["dram__bytes_read.sum"]) + gb(d["dram__bytes_write.sum"])
+            tkey = traffic_key(key)
+            if tkey:
+                traffic.setdefault(str(lattice), {})[tkey] = {"bytes": tr * 1e9, "kernel": key, "capture": tag,
+                                                               "ncu_time_us": t_us}
             md.append("| `%s` | %s | %s | %s | %.3f | %.0f | %s | %s | %s | %s x %s | %s |" % (
                 key, d["gpu__time_duration.sum"], d["dram__bytes_read.sum"], d["dram__bytes_write.sum"], tr,
                 tr / (t_us * 1e-6), d.get("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "").split()[0],
@@ -120,6 +144,7 @@ def main():
             md.append("")
             with open(os.path.join("profiles", "%s_%s" % (tag, name)), "w") as f:
                 f.write(open(bp).read())
+    json.dump(traffic, open(tpath, "w"), indent=1, sort_keys=True)
     open(os.path.join("profiles", "%s_summary.md" % tag), "w").write("\n".join(md) + "\n")
     print("\n".join(md))
 
