@@ -222,6 +222,24 @@ int glb_cg_solve_supported(const glb_operator* op);
 int glb_cg_solve(glb_operator* op, void* d_x, const void* d_b, int max_iter, double eps, glb_cg_report* rep,
                  double* rsq_hist, int hist_cap);
 
+/* ----------------------------------------------- multigrid grid transfers */
+/* prolong / restrict of multigrid/aa_mg/mg_complex.cpp:372-467 on device vectors.  A transfer
+ * couples a fine level (Xf x Yf sites, dof_f values per site, vector index (y*Xf + x)*dof_f + d) to
+ * the coarse level of bx x by blocks with nvec values per coarse site (index (yc*Xc + xc)*nvec + v).
+ * null_vectors: nvec HOST pointers to complex arrays of Xf*Yf*dof_f elements each -- the reference's
+ * mg_operator_struct_complex::null_vectors[level] (mg_complex.h:164) -- copied to the device once.
+ * On y-slabs pass the local extent (the transfers are block-local; Yf must be a multiple of by).
+ *   prolong : fine   = P coarse            (fine fully overwritten;  mg_complex.cpp:372-418)
+ *   restrict: coarse = P^dagger fine       (coarse fully overwritten; mg_complex.cpp:422-467)   */
+typedef struct glb_mg_transfer glb_mg_transfer;
+int glb_mg_transfer_create(glb_context* ctx, int Xf, int Yf, int dof_f, int bx, int by, int nvec,
+                           const void* const* null_vectors, glb_mg_transfer** out);
+int glb_mg_transfer_destroy(glb_mg_transfer* t);
+size_t glb_mg_fine_size(const glb_mg_transfer* t);
+size_t glb_mg_coarse_size(const glb_mg_transfer* t);
+int glb_mg_prolong(glb_mg_transfer* t, void* d_fine, const void* d_coarse);
+int glb_mg_restrict(glb_mg_transfer* t, void* d_coarse, const void* d_fine);
+
 #ifdef __cplusplus
 }
 #endif

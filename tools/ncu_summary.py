@@ -134,11 +134,16 @@ def main():
                 j = json.loads(line)
                 r = j.get("roofline", {})
                 md.append("* lattice %s: value %.0f GB/s (%.1f %% of measured HBM peak), %.2f ms/solve, %d iterations, "
-                          "apply %.0f GB/s (frac %.3f, %.4f ms), e2e %.0f GB/s, launches %d, clocks %s" % (
+                          "roofline kernel %.0f GB/s (frac %.3f, %.4f ms/launch), e2e %.0f GB/s, launches %d, clocks %s" % (
                               j["config"].get("lattice"), j["value"], 100 * j.get("frac_of_hbm_peak", 0), j["ms_per_step"],
                               j["config"].get("iterations", 0), r.get("achieved", 0), r.get("frac", 0),
                               r.get("ms_per_launch", 0), j.get("e2e", {}).get("value", 0), j.get("gpu_launches", 0),
                               json.dumps(j.get("clocks"))))
+                for o in [r] + r.get("other_kernels", []):
+                    if "kernel" in o:
+                        md.append("  * `%s`: %.0f GB/s, frac %.3f, %.4f ms/launch%s" % (
+                            o["kernel"].split(" (")[0], o.get("achieved", 0), o.get("frac", 0), o.get("ms_per_launch", 0),
+                            (", share of step %.3f" % o["share_of_step"]) if "share_of_step" in o else ""))
                 if "cpu_baseline" in j:
                     md.append("  * cpu_baseline: %s" % json.dumps(j["cpu_baseline"]))
             md.append("")
