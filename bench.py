@@ -199,6 +199,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--L", type=int, default=4096)
+    ap.add_argument("--Y", type=int, default=0, help="total rows of the lattice (strong scaling: fixed L x Y "
+                                                      "split over the GPUs); default L rows per GPU (weak)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--apply-reps", type=int, default=50)
     args = ap.parse_args()
@@ -238,7 +240,9 @@ def main():
         return float(t.item())
 
     L = args.L
-    X, Y = L, L * world
+    X, Y = L, (args.Y if args.Y > 0 else L * world)
+    if Y % world != 0:
+        raise SystemExit("--Y must be a multiple of the number of GPUs")
     y0, Yloc = ctx.slab_bounds(Y)
     V_local, V_global = X * Yloc, X * Y
     # this rank's rows plus two periodic ghost rows on each side (glb_op_create_staggered_local)
@@ -377,7 +381,7 @@ def main():
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
 
     cpu = None
-    if not args.no_cpu and world == 1:
+    if not args.no_cpu and world == 1 and Y == L:
         # bounded sample of the same workload on the host: minv_vector_cg(max_iter=3), same arrays
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import oracle_py
@@ -402,11 +406,11 @@ def main():
     line = {
         "metric": "staggered_cgne_solve_algorithmic_GBps", "value": value, "unit": "GB/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "complex<f64>",
-        "data": "synthetic",
+        "higher_is_better": True, "scaling": ("strong" if args.Y > 0 else "weak"), "vs_baseline": None,
+        "dtype": "complex<f64>", "data": "synthetic",
         "config": {"workload": "CGNE solve: minv_vector_cg on square_staggered_normal_u1 (D^dag D), 2-D U(1) staggered, "
                                "%dx%d per GPU (global %dx%d, y-slabs), complex<double>, m=0.1, tol 1e-10, zero guess"
-                               % (L, L, X, Y),
+                               % (X, Y // world, X, Y),
                    "lattice": [X, Y], "iterations": iters, "true_rel_residual": true_rel / bnorm,
                    "l2": "working set %.1f GB per GPU >> 126 MB L2: no flush needed" % (V_local * 16 * 9 / 1e9),
                    "gauge": "gauss U(1), beta=6, per-row numpy seed %d" % SEED,
