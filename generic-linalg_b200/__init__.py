@@ -113,6 +113,9 @@ def libs():
         "glb_cgm_update_p": (ci, [vp, ci, sz, ci, pd, pd, vp, C.POINTER(vp)]),
         "glb_cg_solve_supported": (ci, [vp]),
         "glb_cg_solve": (ci, [vp, vp, vp, ci, cd, C.POINTER(CgReport), pd, ci]),
+        "glb_mg_transfer_create": (ci, [vp, ci, ci, ci, ci, ci, ci, C.POINTER(vp), C.POINTER(vp)]),
+        "glb_mg_transfer_destroy": (ci, [vp]), "glb_mg_fine_size": (sz, [vp]), "glb_mg_coarse_size": (sz, [vp]),
+        "glb_mg_prolong": (ci, [vp, vp, vp]), "glb_mg_restrict": (ci, [vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(cu, name)
@@ -127,6 +130,11 @@ def libs():
                                       C.POINTER(Result)]),
         "glbx_dev_solve": (ci, [ci, vp, vp, vp, ci, cd, ci, ci, ci, C.POINTER(Result)]),
         "glbx_dev_solve_cg_m": (ci, [vp, C.POINTER(vp), vp, ci, ci, ci, cd, vp, ci, ci, C.POINTER(Result)]),
+        "glbx_mg_create": (vp, [ci, C.POINTER(vp), C.POINTER(vp)]), "glbx_mg_destroy": (None, [vp]),
+        "glbx_mg_set": (None, [vp, ci, ci, ci, ci, ci, ci, cd, ci, ci]),
+        "glbx_mg_vcycle": (ci, [vp, vp, vp]),
+        "glbx_mg_vpgcr": (ci, [vp, vp, vp, ci, cd, ci, ci, C.POINTER(Result)]),
+        "glbx_mg_counts": (None, [vp, C.POINTER(ci)]),
     }
     for name, (res, args) in hsig.items():
         f = getattr(ho, name)
@@ -256,6 +264,88 @@ class Operator:
             pass
 
 
+class MgTransfer:
+    """prolong / restrict between two multigrid levels (include/glb200.h: glb_mg_*; mg_complex.cpp:372-467)"""
+
+    def __init__(self, ctx, Xf, Yf, dof_f, bx, by, null_vectors):
+        self.ctx = ctx
+        self._null = [np.ascontiguousarray(v, dtype=np.complex128) for v in null_vectors]
+        n = len(self._null)
+        ptrs = (C.c_void_p * n)(*[v.ctypes.data for v in self._null])
+        h = C.c_void_p()
+        _chk(ctx.cu.glb_mg_transfer_create(ctx.h, Xf, Yf, dof_f, bx, by, n, ptrs, C.byref(h)), "glb_mg_transfer_create")
+        self.h = h
+        self.fine_size = int(ctx.cu.glb_mg_fine_size(h))
+        self.coarse_size = int(ctx.cu.glb_mg_coarse_size(h))
+
+    def prolong(self, fine, coarse):
+        _chk(self.ctx.cu.glb_mg_prolong(self.h, fine.ptr, coarse.ptr), "glb_mg_prolong")
+
+    def restrict(self, coarse, fine):
+        _chk(self.ctx.cu.glb_mg_restrict(self.h, coarse.ptr, fine.ptr), "glb_mg_restrict")
+
+    def destroy(self):
+        if self.h:
+            self.ctx.cu.glb_mg_transfer_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+class Multigrid:
+    """The device multigrid preconditioner (host/mg_complex.h): ops[0] fine ... ops[n_refine] coarsest,
+    transfers[l] couples level l to l+1.  Defaults are the reference's (input_params.cpp:751-800)."""
+    INNER = dict(NONE=0, MINRES=1, CG=2, GCR=3, BICGSTAB=4, CR=5, BICGSTAB_L=6)
+    SMOOTH = dict(CG=0, CR=1, GCR=2, BICGSTAB=3, BICGSTAB_L=4, GMRES=5, SOR=6, MINRES=7, INVALID=-1)
+
+    def __init__(self, ctx, ops, transfers):
+        assert len(ops) == len(transfers) + 1
+        self.ctx, self.ops, self.transfers = ctx, list(ops), list(transfers)
+        n = len(transfers)
+        op_p = (C.c_void_p * (n + 1))(*[o.h.value if hasattr(o.h, "value") else o.h for o in ops])
+        tr_p = (C.c_void_p * n)(*[t.h.value for t in transfers])
+        self.h = ctx.ho.glbx_mg_create(n, op_p, tr_p)
+        if not self.h:
+            raise GlbError("glbx_mg_create failed")
+        self.n_refine = n
+
+    def set(self, smooth="GCR", n_pre=6, n_post=6, inner="GCR", n_max=1024, n_restart=64, rel_res=1e-2,
+            recursive=False, quiet=True):
+        self.ctx.ho.glbx_mg_set(self.h, self.SMOOTH[smooth], n_pre, n_post, self.INNER[inner], n_max, n_restart,
+                                rel_res, 1 if recursive else 0, 1 if quiet else 0)
+
+    def vcycle(self, out, rhs):
+        _chk(self.ctx.ho.glbx_mg_vcycle(self.h, out.ptr, rhs.ptr), "glbx_mg_vcycle")
+
+    def vpgcr(self, x, b, max_iter=1000, eps=5e-7, restart_freq=64, verbosity=0):
+        res = Result()
+        _chk(self.ctx.ho.glbx_mg_vpgcr(self.h, x.ptr, b.ptr, max_iter, eps, restart_freq, verbosity, C.byref(res)),
+             "glbx_mg_vpgcr")
+        return res.as_dict()
+
+    def counts(self):
+        n = self.n_refine + 1
+        buf = (C.c_int * (5 * n))()
+        self.ctx.ho.glbx_mg_counts(self.h, buf)
+        names = ("krylov", "presmooth", "postsmooth", "residual", "nullvectors")
+        return {nm: [buf[i * n + l] for l in range(n)] for i, nm in enumerate(names)}
+
+    def destroy(self):
+        if self.h:
+            self.ctx.ho.glbx_mg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
 class Context:
     """One GPU context = one process's view of the library (one per rank)."""
 
@@ -374,6 +464,12 @@ class Context:
                 for a in (clover, hopping, two_link)]
         return self._op(self.cu.glb_op_create_stencil2d, _p(arrs[0]), _p(arrs[1]), _p(arrs[2]), X, Y, nc,
                         _c2(shift), _c2(eo_shift), _c2(dof_shift))
+
+    def mg_transfer(self, Xf, Yf, dof_f, bx, by, null_vectors):
+        return MgTransfer(self, Xf, Yf, dof_f, bx, by, null_vectors)
+
+    def multigrid(self, ops, transfers):
+        return Multigrid(self, ops, transfers)
 
     # ---- BLAS-1 (thin; used by the parity tests) ----
     def dot(self, x, y):

@@ -294,12 +294,13 @@ cg_update_kernel(CgState* st, double* hist, const T* p, T* x, const T* Ap, T* r,
     *reinterpret_cast<Pack<T, W>*>(r + i) = vr;
   }
   double total[1];
-  if (grid_sum<1>(acc, red, total) && threadIdx.x == 0) {
+  if (!grid_sum<1>(acc, red, total)) return;  // only the block that arrived last goes on
+  if (defer == 2 && threadIdx.x < 32) p2p_allreduce_warp(pr, total, 1);  // slabs over peer memory: finish the sum here
+  if (threadIdx.x == 0) {
     if (defer == 1) {  // slab run over NCCL: the sum over ranks and the recurrence step follow on the stream
       st->partial[0] = total[0];
       return;
     }
-    if (defer == 2) p2p_allreduce_thread(pr, total, 1);  // slab run over peer memory: finish the sum here
     const double rsq_new = total[0];
     st->rsq_new = rsq_new;
     const int k = st->iter;  // 0-based iteration index of the reference loop

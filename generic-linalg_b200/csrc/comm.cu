@@ -134,7 +134,13 @@ __global__ void halo_wait_kernel(const unsigned long long* flag_lo, const unsign
   spin_until(flag_hi, seq);
 }
 // stand-alone one-shot allreduce (used when no producing kernel can finish the sum itself)
-__global__ void p2p_allreduce_kernel(double* vals, int n, P2PRed pr) { p2p_allreduce_thread(pr, vals, n); }
+__global__ void p2p_allreduce_kernel(double* vals, int n, P2PRed pr) {  // one warp
+  for (int t = 0; t < n; t++) {
+    double v[1] = {vals[t]};
+    p2p_allreduce_warp(pr, v, 1, t);
+    if (threadIdx.x == 0) vals[t] = v[0];
+  }
+}
 
 bool comm_p2p(const glb_context* ctx) { return ctx->comm && ctx->comm->p2p; }
 
@@ -264,7 +270,7 @@ int allreduce_device(glb_context* ctx, double* d_vals, int n) {
   if (!ctx->comm) return fail(GLB_ERR_STATE, "reduction before glb_comm_init");
   Comm* c = ctx->comm;
   if (c->p2p && n <= P2P_RED_WIDTH) {
-    p2p_allreduce_kernel<<<1, 1, 0, ctx->stream>>>(d_vals, n, comm_p2p_red(ctx));
+    p2p_allreduce_kernel<<<1, 32, 0, ctx->stream>>>(d_vals, n, comm_p2p_red(ctx));
     GLB_LAUNCH_CHECK();
     return GLB_OK;
   }

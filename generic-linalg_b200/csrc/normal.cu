@@ -359,19 +359,18 @@ __global__ void __launch_bounds__(NORM_THREADS, 3) normal_kernel(const NormArgs 
 
   if (NDOT > 0) {
     double total[NRED];
-    if (grid_sum<NRED>(acc, a.red, total) && threadIdx.x == 0) {
-      if (a.cg != nullptr && a.cg_role == 1) {  // <p,Ap> ready: generic_cg.cpp:326 / :345
-        a.cg->pAp_re = total[0];
-        a.cg->pAp_im = total[1];
-        a.cg->rsq_old = a.cg->rsq_new;
-      } else if (a.cg != nullptr && a.cg_role == 2) {  // slab run: rank-local part, summed on the stream next
-        a.cg->partial[1] = total[0];
-        a.cg->partial[2] = total[1];
-      } else if (a.cg != nullptr && a.cg_role == 3) {  // slab run over peer memory: finish the sum here
-        p2p_allreduce_thread(a.pr, total, 2);
-        a.cg->pAp_re = total[0];
-        a.cg->pAp_im = total[1];
-        a.cg->rsq_old = a.cg->rsq_new;
+    if (grid_sum<NRED>(acc, a.red, total)) {  // the block that arrived last
+      // slab run over peer memory: its first warp finishes the sum over ranks
+      if (a.cg != nullptr && a.cg_role == 3 && threadIdx.x < 32) p2p_allreduce_warp(a.pr, total, 2);
+      if (threadIdx.x == 0 && a.cg != nullptr) {
+        if (a.cg_role == 1 || a.cg_role == 3) {  // <p,Ap> ready: generic_cg.cpp:326 / :345
+          a.cg->pAp_re = total[0];
+          a.cg->pAp_im = total[1];
+          a.cg->rsq_old = a.cg->rsq_new;
+        } else if (a.cg_role == 2) {  // slab run over NCCL: rank-local part, summed on the stream next
+          a.cg->partial[1] = total[0];
+          a.cg->partial[2] = total[1];
+        }
       }
     }
   }

@@ -1,10 +1,12 @@
 // p2p.cuh -- device side of the NVLink peer-memory communication (see comm.cu).
 //
 // Every rank maps every peer's arena; a Mailbox sits at offset 0 of each.  A kernel whose last block
-// has just finished this rank's partial sums can complete the sum over ranks ITSELF: one thread
-// stores the values into slot [seq % 4][rank] of every peer's mailbox, releases a sequence flag on
-// each, waits for the G flags in its own mailbox and adds the G contributions in rank order.  All
-// ranks obtain the bit-identical result; no library call, no extra kernel.
+// has just finished this rank's partial sums can complete the sum over ranks ITSELF: lane g of one warp
+// stores the values into slot [seq % 4][rank] of peer g's mailbox and polls the words rank g sent here,
+// then the warp adds the G contributions in rank order.  All ranks obtain the bit-identical result; no
+// library call, no extra kernel.  The words travel NCCL-LL style: every 8-byte store carries 32 bits of
+// payload and a 32-bit tag derived from the sequence number, so data and flag arrive in one atomic
+// store -- no fence, no second round trip, and the G peers are served in parallel by G lanes.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -15,8 +17,8 @@ constexpr int P2P_RED_SLOTS = 4;
 constexpr int P2P_RED_WIDTH = 40;  // doubles per reduction (multi_dot of 16 complex vectors + slack)
 
 struct Mailbox {  // at offset 0 of every arena
-  double red[P2P_RED_SLOTS][P2P_MAX_RANKS][P2P_RED_WIDTH];
-  unsigned long long red_seq[P2P_RED_SLOTS][P2P_MAX_RANKS];
+  // [slot][sending rank][2*t], [2*t+1] : low / high half of value t, each tagged in the upper 32 bits
+  unsigned long long ll[P2P_RED_SLOTS][P2P_MAX_RANKS][2 * P2P_RED_WIDTH];
 };
 
 struct P2PRed {  // by-value kernel argument; seq == 0 means "not used"
@@ -48,18 +50,47 @@ __device__ __forceinline__ void spin_until(const unsigned long long* flag, unsig
     if (clock64() - t0 > 40000000000LL) __trap();  // ~20 s at 2 GHz
   }
 }
-// Sum vals[0..n) over all ranks, in place.  Call from exactly ONE thread of ONE block per rank.
-__device__ __forceinline__ void p2p_allreduce_thread(const P2PRed& pr, double* vals, int n) {
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// Sum vals[0..n) over all ranks, in place.  Call from all 32 lanes of exactly ONE warp per rank; vals is
+// read from lane 0 and valid in every lane on return.  `base` offsets the word index when one reduction
+// (one seq) is fed through several calls.
+__device__ __forceinline__ void p2p_allreduce_warp(const P2PRed& pr, double* vals, int n, int base = 0) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
   const int slot = (int)(pr.seq % P2P_RED_SLOTS);
-  for (int g = 0; g < pr.nranks; g++)
-    for (int t = 0; t < n; t++) pr.mb[g]->red[slot][pr.rank][t] = vals[t];
-  __threadfence_system();
-  for (int g = 0; g < pr.nranks; g++) st_release_sys(&pr.mb[g]->red_seq[slot][pr.rank], pr.seq);
+  const unsigned long long tag = ((pr.seq % 0xffffffffull) + 1ull) << 32;  // never 0: fresh mailboxes are zero
   Mailbox* mine = pr.mb[pr.rank];
-  for (int g = 0; g < pr.nranks; g++) spin_until(&mine->red_seq[slot][g], pr.seq);
+  Mailbox* peer = pr.mb[lane < pr.nranks ? lane : pr.rank];
   for (int t = 0; t < n; t++) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(__shfl_sync(full, vals[t], 0));
+    if (lane < pr.nranks) {
+      st_relaxed_sys(&peer->ll[slot][pr.rank][2 * (base + t)], tag | (bits & 0xffffffffull));
+      st_relaxed_sys(&peer->ll[slot][pr.rank][2 * (base + t) + 1], tag | (bits >> 32));
+    }
+  }
+  for (int t = 0; t < n; t++) {
+    double got = 0.0;
+    if (lane < pr.nranks) {
+      const unsigned long long* w = &mine->ll[slot][lane][2 * (base + t)];
+      const long long t0 = clock64();
+      unsigned long long lo, hi;
+      for (;;) {
+        lo = ld_relaxed_sys(w);
+        hi = ld_relaxed_sys(w + 1);
+        if ((lo & 0xffffffff00000000ull) == tag && (hi & 0xffffffff00000000ull) == tag) break;
+        if (clock64() - t0 > 40000000000LL) __trap();  // a peer that never shows up must not hang the GPU
+      }
+      got = __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
+    }
     double s = 0.0;
-    for (int g = 0; g < pr.nranks; g++) s += __ldcv(&mine->red[slot][g][t]);  // rank order: same bits everywhere
+    for (int g = 0; g < pr.nranks; g++) s += __shfl_sync(full, got, g);  // rank order: same bits everywhere
     vals[t] = s;
   }
 }

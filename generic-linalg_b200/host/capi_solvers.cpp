@@ -3,9 +3,11 @@
 // C++ entry points of generic_inverters.h / glb200_device.h / operators.h -- the calls a C++ user
 // of the reference would make -- and flattens inversion_info into a POD.
 #include <cstring>
+#include <vector>
 
 #include "coarse_stencil.h"
 #include "dev_internal.hpp"
+#include "mg_complex.h"
 #include "operators.h"
 #include "operators_stencil.h"
 
@@ -277,6 +279,110 @@ int glbx_dev_solve_cg_m(glb_operator* op, void** d_phi, void* d_phi0, int n_shif
     flatten(inf, out);
   }
   return GLB_OK;
+}
+
+
+// ---- multigrid-preconditioned solves (mg_complex.h): the hierarchy is handed over as device objects
+typedef struct glbx_mg {
+  mg_operator_struct_complex_dev mg;
+  mg_precond_struct_complex_dev pc;
+  std::vector<glb_operator*> ops;
+  std::vector<glb_mg_transfer*> trs;
+  std::vector<int> n_pre, n_post;
+  std::vector<double> rel_res;
+} glbx_mg;
+
+glbx_mg* glbx_mg_create(int n_refine, glb_operator** level_ops, glb_mg_transfer** transfers) {
+  if (n_refine < 1 || !level_ops || !transfers) return 0;
+  glbx_mg* h = new glbx_mg();
+  h->ops.assign(level_ops, level_ops + n_refine + 1);
+  h->trs.assign(transfers, transfers + n_refine);
+  h->mg.n_refine = n_refine;
+  h->mg.stencils = h->ops.data();
+  h->mg.transfers = h->trs.data();
+  h->mg.curr_level = 0;
+  h->mg.dslash_count = new dslash_tracker(n_refine);
+  // defaults of multigrid/aa_mg/input_params.cpp:751-800
+  h->n_pre.assign(n_refine, 6);
+  h->n_post.assign(n_refine, 6);
+  h->rel_res.assign(n_refine, 1e-2);
+  h->pc.in_smooth_type = MINV_GCR;
+  h->pc.omega_smooth = 0.67;
+  h->pc.n_pre_smooth = h->n_pre.data();
+  h->pc.n_post_smooth = h->n_post.data();
+  h->pc.normal_eqn_mg = false;
+  h->pc.normal_eqn_smooth = false;
+  h->pc.mlevel_type = MLEVEL_SMOOTH;
+  h->pc.in_solve_type = GCR;
+  h->pc.n_max = 1024;
+  h->pc.n_restart = 64;
+  h->pc.rel_res = h->rel_res.data();
+  h->pc.mgstruct = &h->mg;
+  h->pc.quiet = true;
+  return h;
+}
+
+void glbx_mg_destroy(glbx_mg* h) {
+  if (!h) return;
+  delete h->mg.dslash_count;
+  delete h;
+}
+
+void glbx_mg_set(glbx_mg* h, int in_smooth_type, int n_pre, int n_post, int in_solve_type, int n_max, int n_restart,
+                 double rel_res, int mlevel_type, int quiet) {
+  h->pc.in_smooth_type = (minv_inverter)in_smooth_type;
+  h->pc.in_solve_type = (inner_solver)in_solve_type;
+  h->pc.n_max = n_max;
+  h->pc.n_restart = n_restart;
+  h->pc.mlevel_type = (mg_multilevel_type)mlevel_type;
+  h->pc.quiet = (quiet != 0);
+  for (int i = 0; i < h->mg.n_refine; i++) {
+    h->n_pre[i] = n_pre;
+    h->n_post[i] = n_post;
+    h->rel_res[i] = rel_res;
+  }
+}
+
+// one cycle on the top level: d_lhs = M^-1 d_rhs
+int glbx_mg_vcycle(glbx_mg* h, void* d_lhs, void* d_rhs) {
+  h->mg.curr_level = 0;
+  const int size = (int)glb_op_local_size(h->ops[0]);
+  if (glb_vec_zero(glb_op_context(h->ops[0]), GLB_COMPLEX, size, d_lhs) != GLB_OK) return GLB_ERR_CUDA;
+  mg_preconditioner_dev((zc*)d_lhs, (zc*)d_rhs, size, (void*)&h->pc, 0);
+  return GLB_OK;
+}
+
+// minv_vector_gcr_var_precond(_restart) on the level-0 operator with mg_preconditioner_dev
+int glbx_mg_vpgcr(glbx_mg* h, void* d_phi, void* d_phi0, int max_iter, double res, int restart_freq, int verbosity,
+                  glbx_result* out) {
+  h->mg.curr_level = 0;
+  inversion_verbose_struct v;
+  make_verb(verbosity, &v);
+  const int size = (int)glb_op_local_size(h->ops[0]);
+  void (*cb)(zc*, zc*, void*) = &glb200_apply_dev;
+  void (*pcb)(zc*, zc*, int, void*, inversion_verbose_struct*) = &mg_preconditioner_dev;
+  inversion_info inf;
+  if (restart_freq > 0)
+    inf = minv_vector_gcr_var_precond_restart_dev((zc*)d_phi, (zc*)d_phi0, size, max_iter, res, restart_freq, cb,
+                                                  (void*)h->ops[0], pcb, (void*)&h->pc, &v);
+  else
+    inf = minv_vector_gcr_var_precond_dev((zc*)d_phi, (zc*)d_phi0, size, max_iter, res, cb, (void*)h->ops[0], pcb,
+                                          (void*)&h->pc, &v);
+  flatten(inf, out);
+  return GLB_OK;
+}
+
+// dslash counters (mg_complex.h:104-136): out[5*(n_refine+1)] = krylov, presmooth, postsmooth, residual, nullvectors
+void glbx_mg_counts(glbx_mg* h, int* out) {
+  const int n = h->mg.n_refine + 1;
+  const dslash_tracker* d = h->mg.dslash_count;
+  for (int i = 0; i < n; i++) {
+    out[i] = d->krylov[i];
+    out[n + i] = d->presmooth[i];
+    out[2 * n + i] = d->postsmooth[i];
+    out[3 * n + i] = d->residual[i];
+    out[4 * n + i] = d->nullvectors[i];
+  }
 }
 
 }  // extern "C"

@@ -223,6 +223,75 @@ inversion_info gcr_dev(T* x, T* b, int size, int max_iter, double eps, void (*fn
   return inf;
 }
 
+// ------------------------------------------------------------------------------------------ VPGCR
+// generic_gcr_var_precond.cpp:28-195 (real) / :220-365 (complex): GCR whose search direction is the
+// variably preconditioned residual z = M^-1 r.  As in gcr_dev the coefficients
+// beta_ij = -<Ap_i,Az>/|Ap_i|^2 (:310) all use the same Az, so they come from one batched pass.
+// The preconditioner follows the device variant of the reference's precond contract
+// (generic_gcr_var_precond.h:16-23): void(T* d_lhs, T* d_rhs, int size, void* extra, verbosity*), lhs
+// zeroed by the caller before every call but the first (:245 / :296).
+template <typename T>
+inversion_info gcr_var_precond_dev(T* x, T* b, int size, int max_iter, double eps, void (*fn)(T*, T*, void*), void* extra,
+                                   void (*precond)(T*, T*, int, void*, inversion_verbose_struct*), void* precond_info,
+                                   inversion_verbose_struct* verb) {
+  inversion_info inf;
+  DevOp<T> A = make_op<T>(fn, extra, size);
+  Blas<T> B = {A.ctx, (size_t)size};
+  Work<T> W(B);
+  inversion_verbose_struct verb_prec;
+  shuffle_verbosity_precond(&verb_prec, verb);
+  T *r = W.get(), *z = W.get(), *Az = W.get();
+  std::vector<const void*> ps, Aps;
+  std::vector<double> Apnorm;
+  T* p = W.get();
+  T* Ap = W.get();
+  const double bsqrt = sqrt(B.norm2sq(b));
+  A.apply(p, x);
+  B.sub(b, p, r);
+  B.zero(z);
+  precond(z, r, size, precond_info, &verb_prec);
+  B.copy(p, z);
+  A.apply(Ap, p);
+  double rsq = 0.0;
+  int k;
+  std::vector<double> dots, coef;
+  for (k = 0; k < max_iter; k++) {
+    ps.push_back(p);
+    Aps.push_back(Ap);
+    double dn[3];
+    GLBX(glb_dot_norm(A.ctx, Traits<T>::dtype, size, Ap, r, dn));  // <Ap,r>, |Ap|^2
+    Apnorm.push_back(dn[2]);
+    const T alpha = Traits<T>::unpack(dn) / dn[2];
+    rsq = B.update_xr_norm(alpha, p, x, -alpha, Ap, r);
+    print_verbosity_resid(verb, "VPGCR", k + 1, A.ops, sqrt(rsq) / bsqrt);
+    if (sqrt(rsq) < eps * bsqrt || k == max_iter - 1) break;
+    B.zero(z);
+    precond(z, r, size, precond_info, &verb_prec);
+    A.apply(Az, z);
+    dots.resize(2 * (k + 1));
+    coef.resize(2 * (k + 1));
+    GLBX(glb_multi_dot(A.ctx, Traits<T>::dtype, size, k + 1, Aps.data(), Az, dots.data()));
+    for (int ii = 0; ii <= k; ii++) {
+      const T beta = -Traits<T>::unpack(&dots[2 * ii]) / Apnorm[ii];
+      Traits<T>::pack(beta, &coef[2 * ii]);
+    }
+    p = W.get();
+    Ap = W.get();
+    GLBX(glb_lincomb(A.ctx, Traits<T>::dtype, size, k + 1, coef.data(), ps.data(), z, p));
+    GLBX(glb_lincomb(A.ctx, Traits<T>::dtype, size, k + 1, coef.data(), Aps.data(), Az, Ap));
+  }
+  inf.success = !(k == max_iter - 1);
+  k++;
+  A.apply(Az, x);
+  const double truersq = B.diffnorm2sq(Az, b);
+  inf.ops_count = A.ops;
+  print_verbosity_summary(verb, "VPGCR", inf.success, k, inf.ops_count, sqrt(truersq) / bsqrt);
+  inf.resSq = truersq;
+  inf.iter = k;
+  inf.name = "Variably Preconditioned GCR";
+  return inf;
+}
+
 // ------------------------------------------------------------------------------------------ BiCGStab
 // generic_bicgstab.cpp:22-158 / :205-341
 template <typename T>
@@ -691,3 +760,71 @@ GLB200_DEF_RESTART(minv_vector_gmres_restart_dev, gmres_dev, "GMRES", true)
   }
 GLB200_DEF_BICGL(double)
 GLB200_DEF_BICGL(zcplx)
+
+// ------------------------------------------------------------------------------------------ VPGCR exports
+#define GLB200_DEF_VPGCR(T)                                                                                        \
+  inversion_info minv_vector_gcr_var_precond_dev(T* phi, T* phi0, int size, int max_iter, double res,              \
+                                                 void (*mv)(T*, T*, void*), void* extra,                           \
+                                                 void (*pc)(T*, T*, int, void*, inversion_verbose_struct*),        \
+                                                 void* pc_info, inversion_verbose_struct* verb) {                  \
+    try {                                                                                                          \
+      return gcr_var_precond_dev<T>(phi, phi0, size, max_iter, res, mv, extra, pc, pc_info, verb);                 \
+    } catch (const std::exception& e) {                                                                            \
+      return failed("VPGCR", e);                                                                                   \
+    }                                                                                                              \
+  }                                                                                                                \
+  inversion_info minv_vector_gcr_var_precond_restart_dev(T* phi, T* phi0, int size, int max_iter, double res,      \
+                                                         int rf, void (*mv)(T*, T*, void*), void* extra,           \
+                                                         void (*pc)(T*, T*, int, void*, inversion_verbose_struct*), \
+                                                         void* pc_info, inversion_verbose_struct* verb) {          \
+    try {                                                                                                          \
+      return restarted<T>(label("Variably Preconditioned Restarted GCR", rf), phi0, size, max_iter, res,           \
+                          ctx_of<T>(mv, extra), verb, false, [&](inversion_verbose_struct* v) {                    \
+                            return gcr_var_precond_dev<T>(phi, phi0, size, rf, res, mv, extra, pc, pc_info, v);    \
+                          });                                                                                      \
+    } catch (const std::exception& e) {                                                                            \
+      return failed("VPGCR", e);                                                                                   \
+    }                                                                                                              \
+  }
+GLB200_DEF_VPGCR(double)
+GLB200_DEF_VPGCR(zcplx)
+
+// generic_inverter.cpp:18-190 on device vectors: the enum dispatch the MG smoother uses
+template <typename T>
+static inversion_info dispatch_dev(T* lhs, T* rhs, int size, minv_inverter type, minv_inverter_params& p,
+                                   void (*mv)(T*, T*, void*), void* extra, inversion_verbose_struct* verb) {
+  switch (type) {
+    case MINV_CG:
+      return p.restart ? minv_vector_cg_restart_dev(lhs, rhs, size, p.max_iters, p.tol, p.restart_freq, mv, extra, verb)
+                       : minv_vector_cg_dev(lhs, rhs, size, p.max_iters, p.tol, mv, extra, verb);
+    case MINV_CR:
+      return p.restart ? minv_vector_cr_restart_dev(lhs, rhs, size, p.max_iters, p.tol, p.restart_freq, mv, extra, verb)
+                       : minv_vector_cr_dev(lhs, rhs, size, p.max_iters, p.tol, mv, extra, verb);
+    case MINV_GCR:
+      return p.restart ? minv_vector_gcr_restart_dev(lhs, rhs, size, p.max_iters, p.tol, p.restart_freq, mv, extra, verb)
+                       : minv_vector_gcr_dev(lhs, rhs, size, p.max_iters, p.tol, mv, extra, verb);
+    case MINV_BICGSTAB:
+      return p.restart
+                 ? minv_vector_bicgstab_restart_dev(lhs, rhs, size, p.max_iters, p.tol, p.restart_freq, mv, extra, verb)
+                 : minv_vector_bicgstab_dev(lhs, rhs, size, p.max_iters, p.tol, mv, extra, verb);
+    case MINV_BICGSTAB_L:
+      return p.restart ? minv_vector_bicgstab_l_restart_dev(lhs, rhs, size, p.max_iters, p.tol, p.restart_freq,
+                                                            p.bicgstabl_l, mv, extra, verb)
+                       : minv_vector_bicgstab_l_dev(lhs, rhs, size, p.max_iters, p.tol, p.bicgstabl_l, mv, extra, verb);
+    case MINV_GMRES:
+      return p.restart ? minv_vector_gmres_restart_dev(lhs, rhs, size, p.max_iters, p.tol, p.restart_freq, mv, extra, verb)
+                       : minv_vector_gmres_dev(lhs, rhs, size, p.max_iters, p.tol, mv, extra, verb);
+    default:  // SOR / MinRes are outside the accelerated path
+      return inversion_info();
+  }
+}
+inversion_info minv_unpreconditioned_dev(double* lhs, double* rhs, int size, minv_inverter type, minv_inverter_params& p,
+                                         void (*mv)(double*, double*, void*), void* extra,
+                                         inversion_verbose_struct* verb) {
+  return dispatch_dev<double>(lhs, rhs, size, type, p, mv, extra, verb);
+}
+inversion_info minv_unpreconditioned_dev(zcplx* lhs, zcplx* rhs, int size, minv_inverter type, minv_inverter_params& p,
+                                         void (*mv)(zcplx*, zcplx*, void*), void* extra,
+                                         inversion_verbose_struct* verb) {
+  return dispatch_dev<zcplx>(lhs, rhs, size, type, p, mv, extra, verb);
+}

@@ -90,4 +90,28 @@ inversion_info minv_vector_cg_m_dev(std::complex<double>** d_phi, std::complex<d
                                     void* extra_info, bool worst_first = false,
                                     inversion_verbose_struct* verbosity = 0);
 
+// Variably preconditioned GCR (generic_gcr_var_precond.h:16-23) on device vectors.  The preconditioner is
+// the device variant of the reference's precond contract: d_lhs = M^-1 d_rhs on the context's stream.
+#define GLB200_DECL_VPGCR(T)                                                                                       \
+  inversion_info minv_vector_gcr_var_precond_dev(                                                                  \
+      T* d_phi, T* d_phi0, int size, int max_iter, double res, void (*matrix_vector_dev)(T*, T*, void*),           \
+      void* extra_info, void (*precond_matrix_vector_dev)(T*, T*, int, void*, inversion_verbose_struct*),          \
+      void* precond_info, inversion_verbose_struct* verbosity = 0);                                                \
+  inversion_info minv_vector_gcr_var_precond_restart_dev(                                                          \
+      T* d_phi, T* d_phi0, int size, int max_iter, double res, int restart_freq,                                   \
+      void (*matrix_vector_dev)(T*, T*, void*), void* extra_info,                                                  \
+      void (*precond_matrix_vector_dev)(T*, T*, int, void*, inversion_verbose_struct*), void* precond_info,        \
+      inversion_verbose_struct* verbosity = 0);
+GLB200_DECL_VPGCR(double)
+GLB200_DECL_VPGCR(std::complex<double>)
+
+// minv_unpreconditioned (generic_inverters.h:109-111) on device vectors
+inversion_info minv_unpreconditioned_dev(double* d_lhs, double* d_rhs, int size, minv_inverter type,
+                                         minv_inverter_params& params, void (*matrix_vector_dev)(double*, double*, void*),
+                                         void* extra_info, inversion_verbose_struct* verbosity = 0);
+inversion_info minv_unpreconditioned_dev(std::complex<double>* d_lhs, std::complex<double>* d_rhs, int size,
+                                         minv_inverter type, minv_inverter_params& params,
+                                         void (*matrix_vector_dev)(std::complex<double>*, std::complex<double>*, void*),
+                                         void* extra_info, inversion_verbose_struct* verbosity = 0);
+
 #endif

@@ -1,0 +1,195 @@
+// mg_dev.cpp -- mg_preconditioner on device vectors (multigrid/aa_mg/mg_complex.cpp:514-822).
+//
+// The control flow, the parameters handed to the smoother and the inner solvers, the printed lines and
+// the dslash bookkeeping follow the reference statement by statement; vectors are device arrays and
+// every operation is a C-ABI call (operator applies, BLAS-1, glb_mg_prolong / glb_mg_restrict).
+#include <cmath>
+#include <cstdio>
+#include <iostream>
+
+#include "dev_internal.hpp"
+#include "mg_complex.h"
+
+using namespace glbx;
+
+dslash_tracker::dslash_tracker(int refine) : n_refine(refine) {
+  krylov = new int[refine + 1];
+  presmooth = new int[refine + 1];
+  postsmooth = new int[refine + 1];
+  residual = new int[refine + 1];
+  nullvectors = new int[refine + 1];
+  for (int i = 0; i < refine + 1; i++) krylov[i] = presmooth[i] = postsmooth[i] = residual[i] = nullvectors[i] = 0;
+}
+dslash_tracker::~dslash_tracker() {
+  delete[] krylov;
+  delete[] presmooth;
+  delete[] postsmooth;
+  delete[] residual;
+  delete[] nullvectors;
+}
+
+// mg_complex.cpp:469-510 : only the level index is state here (sizes come from the operators)
+void level_down(mg_operator_struct_complex_dev* mg) {
+  if (mg->curr_level < mg->n_refine - 1) mg->curr_level++;
+}
+void level_up(mg_operator_struct_complex_dev* mg) {
+  if (mg->curr_level > 0) mg->curr_level--;
+}
+
+namespace {
+
+void cycle(zcplx* lhs, zcplx* rhs, int size, mg_precond_struct_complex_dev* pc, inversion_verbose_struct* verb) {
+  mg_operator_struct_complex_dev* mg = pc->mgstruct;
+  const int lvl = mg->curr_level;
+  const bool say = !pc->quiet;
+  if (pc->normal_eqn_smooth || pc->normal_eqn_mg)
+    throw Error("mg_preconditioner_dev: the normal-equation variants are not on the accelerated path");
+  if (say) std::cout << "[MG]: Entered mg_preconditioner.\n";
+  glb_operator* fine = mg->stencils[lvl];
+  glb_operator* coarse = mg->stencils[lvl + 1];
+  glb_mg_transfer* tr = mg->transfers[lvl];
+  const int fine_size = (int)glb_op_local_size(fine);
+  const int coarse_length = (int)glb_op_local_size(coarse);
+  if (fine_size != size) throw Error("mg_preconditioner_dev: vector size does not match the current level");
+  if ((size_t)fine_size != glb_mg_fine_size(tr) || (size_t)coarse_length != glb_mg_coarse_size(tr))
+    throw Error("mg_preconditioner_dev: transfer and operators disagree on the level sizes");
+  void (*apply)(zcplx*, zcplx*, void*) = &glb200_apply_dev;
+  glb_context* ctx = glb_op_context(fine);
+  Blas<zcplx> B = {ctx, (size_t)fine_size};
+  Blas<zcplx> Bc = {ctx, (size_t)coarse_length};
+  Work<zcplx> W(B);
+  Work<zcplx> Wc(Bc);
+  inversion_info invif;
+
+  // 1. pre-smooth: z1 ~ A^-1 rhs from a zero guess, r1 = rhs - A z1   (mg_complex.cpp:548-595)
+  zcplx* z1 = W.get();
+  zcplx* r1 = W.get();
+  B.zero(z1);
+  if (pc->n_pre_smooth[lvl] > 0 && pc->in_smooth_type != MINV_INVALID) {
+    minv_inverter_params pre_solve;
+    pre_solve.tol = 1e-20;
+    pre_solve.max_iters = pc->n_pre_smooth[lvl];
+    pre_solve.restart = false;
+    pre_solve.restart_freq = -1;
+    pre_solve.sor_omega = 1.0;
+    pre_solve.minres_omega = 1.0;
+    pre_solve.bicgstabl_l = pc->n_pre_smooth[lvl];
+    invif = minv_unpreconditioned_dev(z1, rhs, fine_size, pc->in_smooth_type, pre_solve, apply, (void*)fine);
+    if (say) {
+      printf("[L%d Presmooth]: Iterations %d Res %.8e Err N Algorithm %s\n", lvl + 1, invif.iter, sqrt(invif.resSq),
+             invif.name.c_str());
+      fflush(stdout);
+    }
+    mg->dslash_count->presmooth[lvl] += invif.ops_count;
+    GLBX(glb_op_apply(fine, r1, z1));
+    mg->dslash_count->residual[lvl]++;
+    B.sub(rhs, r1, r1);
+  } else {
+    B.copy(r1, rhs);
+  }
+
+  // 2. coarse correction z2 = P (P^dag A P)^-1 P^dag r1, lhs = z1 + z2   (mg_complex.cpp:598-758)
+  const bool coarsest = (lvl + 1 == mg->n_refine);
+  if (pc->in_solve_type != NONE || !coarsest) {
+    zcplx* z2 = W.get();
+    zcplx* rhs_coarse = Wc.get();
+    zcplx* lhs_coarse = Wc.get();
+    GLBX(glb_mg_restrict(tr, rhs_coarse, r1));
+    Bc.zero(lhs_coarse);
+    if (pc->in_solve_type != NONE && coarsest) {
+      const double tol = pc->rel_res[lvl];
+      switch (pc->in_solve_type) {
+        case CG:
+          invif = minv_vector_cg_dev(lhs_coarse, rhs_coarse, coarse_length, pc->n_max, tol, apply, (void*)coarse, verb);
+          break;
+        case GCR:
+          invif = minv_vector_gcr_restart_dev(lhs_coarse, rhs_coarse, coarse_length, pc->n_max, tol, pc->n_restart, apply,
+                                              (void*)coarse, verb);
+          break;
+        case BICGSTAB:
+        case BICGSTAB_L:
+          invif = minv_vector_bicgstab_dev(lhs_coarse, rhs_coarse, coarse_length, pc->n_max, tol, apply, (void*)coarse,
+                                           verb);
+          break;
+        case CR:
+          invif = minv_vector_cr_restart_dev(lhs_coarse, rhs_coarse, coarse_length, pc->n_max, tol, pc->n_restart, apply,
+                                             (void*)coarse, verb);
+          break;
+        default:
+          throw Error("mg_preconditioner_dev: MinRes is not on the accelerated path (use CG, GCR, BiCGStab or CR)");
+      }
+      if (say)
+        printf("[L%d]: Iterations %d RelRes %.8e Err N Algorithm %s\n", lvl + 2, invif.iter,
+               sqrt(invif.resSq) / sqrt(Bc.norm2sq(rhs_coarse)), invif.name.c_str());
+      mg->dslash_count->krylov[lvl + 1] += invif.ops_count;
+    } else {
+      // not on the coarsest level: the level below is preconditioned by its own cycle
+      if (say) {
+        printf(pc->in_solve_type != NONE ? "About to enter coarser solve.\n" : "[L%d]: About to enter coarser solve.\n",
+               lvl + 1);
+        fflush(stdout);
+      }
+      level_down(mg);
+      if (pc->in_solve_type == NONE || pc->mlevel_type == MLEVEL_SMOOTH || pc->in_solve_type == MINRES) {
+        cycle(lhs_coarse, rhs_coarse, coarse_length, pc, verb);
+      } else {
+        if (pc->in_solve_type != GCR && pc->in_solve_type != CR)
+          throw Error("mg_preconditioner_dev: the recursive cycle is accelerated for GCR / CR (VPGCR) only");
+        void (*self)(zcplx*, zcplx*, int, void*, inversion_verbose_struct*) = &mg_preconditioner_dev;
+        invif = minv_vector_gcr_var_precond_restart_dev(lhs_coarse, rhs_coarse, coarse_length, pc->n_max,
+                                                        pc->rel_res[mg->curr_level - 1], pc->n_restart, apply,
+                                                        (void*)coarse, self, (void*)pc, verb);
+        if (say)
+          printf("[L%d]: Iterations %d RelRes %.8e Err N Algorithm %s\n", mg->curr_level + 1, invif.iter,
+                 sqrt(invif.resSq) / sqrt(Bc.norm2sq(rhs_coarse)), invif.name.c_str());
+        mg->dslash_count->krylov[mg->curr_level] += invif.ops_count;
+      }
+      level_up(mg);
+      if (say) {
+        printf(pc->in_solve_type != NONE ? "Exited coarser solve.\n" : "[L%d]: Exited coarse solve.\n", lvl + 1);
+        fflush(stdout);
+      }
+    }
+    GLBX(glb_mg_prolong(tr, z2, lhs_coarse));
+    B.add(z1, z2, lhs);
+  } else {
+    B.copy(lhs, z1);  // no inner solver on the coarsest level: lhs = z1
+  }
+
+  // 3. post-smooth on the residual equation: lhs += z3, z3 ~ A^-1 (rhs - A lhs)   (mg_complex.cpp:760-806)
+  if (pc->n_post_smooth[lvl] > 0 && pc->in_smooth_type != MINV_INVALID) {
+    zcplx* r2 = W.get();
+    zcplx* z3 = W.get();
+    GLBX(glb_op_apply(fine, r2, lhs));
+    mg->dslash_count->residual[lvl]++;
+    B.sub(rhs, r2, r2);
+    minv_inverter_params post_solve;
+    post_solve.tol = 1e-20;
+    post_solve.max_iters = pc->n_post_smooth[lvl];
+    post_solve.restart = false;
+    post_solve.restart_freq = -1;
+    post_solve.sor_omega = 1.0;
+    post_solve.minres_omega = 1.0;
+    post_solve.bicgstabl_l = pc->n_post_smooth[lvl];
+    B.zero(z3);
+    invif = minv_unpreconditioned_dev(z3, r2, fine_size, pc->in_smooth_type, post_solve, apply, (void*)fine);
+    if (say)
+      printf("[L%d Postsmooth]: Iterations %d Res %.8e Err N Algorithm %s\n", lvl + 1, invif.iter, sqrt(invif.resSq),
+             invif.name.c_str());
+    mg->dslash_count->postsmooth[lvl] += invif.ops_count;
+    B.add(lhs, z3, lhs);
+  }
+  if (say) std::cout << "[MG]: Exited mg_preconditioner.\n";
+}
+
+}  // namespace
+
+void mg_preconditioner_dev(zcplx* d_lhs, zcplx* d_rhs, int size, void* extra_data, inversion_verbose_struct* verb) {
+  mg_precond_struct_complex_dev* pc = (mg_precond_struct_complex_dev*)extra_data;
+  try {
+    cycle(d_lhs, d_rhs, size, pc, verb);
+  } catch (const std::exception& e) {
+    // the preconditioner contract has no error channel (generic_gcr_var_precond.h:16): report and leave lhs as is
+    std::cerr << "[glb200] mg_preconditioner aborted: " << e.what() << std::endl;
+  }
+}

@@ -186,6 +186,102 @@ class Oracle:
         return xs, res.as_dict(), shifts
 
 
+class RefMg:
+    """The reference's own adaptive multigrid (oracle/ref_mg_shim.cpp; `ref` library only): two or more levels on
+    the 2-D U(1) staggered operator, built from caller-supplied null vectors.  null[l] = list of nvec[l] arrays."""
+    # mg.h:4-13 inner_solver, generic_inverters.h minv_inverter, mg_complex.h:17-21 mg_multilevel_type
+    INNER = dict(NONE=0, MINRES=1, CG=2, GCR=3, BICGSTAB=4, CR=5, BICGSTAB_L=6)
+    SMOOTH = dict(CG=0, CR=1, GCR=2, BICGSTAB=3, BICGSTAB_L=4, GMRES=5, SOR=6, MINRES=7, INVALID=-1)
+
+    def __init__(self, orc, X, Y, links, mass, blocks, nvecs, null):
+        if orc.kind != "reference":
+            raise RuntimeError("RefMg needs oracle/_ref/libref_oracle.so (the reference-compiled checker)")
+        L = orc.lib
+        vp, ci, cd = C.c_void_p, C.c_int, C.c_double
+        for name, res, args in (("refmg_create", vp, [ci, ci, vp, cd, ci, vp, vp, vp]),
+                                ("refmg_level_dims", None, [vp, ci, vp, vp, vp]),
+                                ("refmg_get_null", None, [vp, ci, ci, vp]),
+                                ("refmg_get_stencil", None, [vp, ci, vp, vp, vp]),
+                                ("refmg_prolong", None, [vp, ci, vp, vp]), ("refmg_restrict", None, [vp, ci, vp, vp]),
+                                ("refmg_apply_level", None, [vp, ci, vp, vp]),
+                                ("refmg_set_precond", None, [vp, ci, ci, ci, ci, ci, ci, cd, ci]),
+                                ("refmg_vcycle", None, [vp, vp, vp]),
+                                ("refmg_vpgcr", None, [vp, vp, vp, ci, cd, ci, ci, vp])):
+            f = getattr(L, name)
+            f.restype, f.argtypes = res, args
+        self.L = L
+        self.n_refine = len(blocks)
+        self.links = np.ascontiguousarray(links, dtype=np.complex128)
+        blocks_a = np.array(blocks, dtype=np.int32)
+        nvecs_a = np.array(nvecs, dtype=np.int32)
+        self._null = [[np.ascontiguousarray(v, dtype=np.complex128) for v in lvl] for lvl in null]
+        lvl_ptrs = []
+        for lvl in self._null:
+            lvl_ptrs.append((C.c_void_p * len(lvl))(*[v.ctypes.data for v in lvl]))
+        top = (C.c_void_p * len(lvl_ptrs))(*[C.cast(a, C.c_void_p).value for a in lvl_ptrs])
+        self._keep = (lvl_ptrs, top, blocks_a, nvecs_a)
+        self.h = L.refmg_create(X, Y, _ptr(self.links), mass, self.n_refine, _ptr(blocks_a), _ptr(nvecs_a),
+                                C.cast(top, C.c_void_p))
+
+    def dims(self, level):
+        x, y, n = C.c_int(), C.c_int(), C.c_int()
+        self.L.refmg_level_dims(self.h, level, C.byref(x), C.byref(y), C.byref(n))
+        return x.value, y.value, n.value
+
+    def size(self, level):
+        x, y, n = self.dims(level)
+        return x * y * n
+
+    def null(self, level, v):
+        out = np.empty(self.size(level), dtype=np.complex128)
+        self.L.refmg_get_null(self.h, level, v, _ptr(out))
+        return out
+
+    def stencil(self, level):
+        x, y, n = self.dims(level)
+        cl = np.empty(x * y * n * n, dtype=np.complex128)
+        hp = np.empty(4 * x * y * n * n, dtype=np.complex128)
+        sh = np.empty(3, dtype=np.complex128)
+        self.L.refmg_get_stencil(self.h, level, _ptr(cl), _ptr(hp), _ptr(sh))
+        return cl, hp, sh
+
+    def prolong(self, level, coarse):
+        coarse = np.ascontiguousarray(coarse, dtype=np.complex128)
+        fine = np.empty(self.size(level), dtype=np.complex128)
+        self.L.refmg_prolong(self.h, level, _ptr(fine), _ptr(coarse))
+        return fine
+
+    def restrict(self, level, fine):
+        fine = np.ascontiguousarray(fine, dtype=np.complex128)
+        coarse = np.empty(self.size(level + 1), dtype=np.complex128)
+        self.L.refmg_restrict(self.h, level, _ptr(coarse), _ptr(fine))
+        return coarse
+
+    def apply_level(self, level, v):
+        v = np.ascontiguousarray(v, dtype=np.complex128)
+        out = np.zeros_like(v)
+        self.L.refmg_apply_level(self.h, level, _ptr(out), _ptr(v))
+        return out
+
+    def set_precond(self, smooth="GCR", n_pre=6, n_post=6, inner="GCR", n_max=1024, n_restart=64, rel_res=1e-2,
+                    recursive=False):
+        self.L.refmg_set_precond(self.h, self.SMOOTH[smooth], n_pre, n_post, self.INNER[inner], n_max, n_restart,
+                                 rel_res, 1 if recursive else 0)
+
+    def vcycle(self, rhs):
+        rhs = np.ascontiguousarray(rhs, dtype=np.complex128)
+        out = np.zeros_like(rhs)
+        self.L.refmg_vcycle(self.h, _ptr(out), _ptr(rhs))
+        return out
+
+    def vpgcr(self, b, x0=None, max_iter=1000, eps=5e-7, restart_freq=64, verbosity=0):
+        b = np.ascontiguousarray(b, dtype=np.complex128)
+        x = np.zeros_like(b) if x0 is None else np.array(x0, dtype=np.complex128, copy=True)
+        out = np.zeros(4)
+        self.L.refmg_vpgcr(self.h, _ptr(x), _ptr(b), max_iter, eps, restart_freq, verbosity, _ptr(out))
+        return x, dict(resSq=out[0], iter=int(out[1]), success=bool(out[2]), ops_count=int(out[3]))
+
+
 def available():
     out = []
     if os.path.exists(os.path.join(HERE, "_ref", "libref_oracle.so")):

@@ -274,4 +274,57 @@ int glb_cg_solve(glb_operator*, void*, const void*, int, double, glb_cg_report*,
   g_err = "glb_cg_solve is not available in the CPU mock";
   return GLB_ERR_STATE;
 }
+
+// multigrid grid transfers: host loops in the reference's accumulation order (mg_complex.cpp:372-467)
+struct glb_mg_transfer {
+  int Xf, Yf, dof_f, bx, by, nvec, Xc, Yc;
+  std::vector<std::vector<cplx> > null;
+};
+int glb_mg_transfer_create(glb_context*, int Xf, int Yf, int dof_f, int bx, int by, int nvec,
+                           const void* const* null_vectors, glb_mg_transfer** out) {
+  if (Xf % bx != 0 || Yf % by != 0) return GLB_ERR_ARG;
+  glb_mg_transfer* t = new glb_mg_transfer();
+  t->Xf = Xf; t->Yf = Yf; t->dof_f = dof_f; t->bx = bx; t->by = by; t->nvec = nvec;
+  t->Xc = Xf / bx; t->Yc = Yf / by;
+  const size_t nf = (size_t)Xf * Yf * dof_f;
+  for (int v = 0; v < nvec; v++) t->null.push_back(std::vector<cplx>((const cplx*)null_vectors[v], (const cplx*)null_vectors[v] + nf));
+  *out = t;
+  return GLB_OK;
+}
+int glb_mg_transfer_destroy(glb_mg_transfer* t) { delete t; return GLB_OK; }
+size_t glb_mg_fine_size(const glb_mg_transfer* t) { return (size_t)t->Xf * t->Yf * t->dof_f; }
+size_t glb_mg_coarse_size(const glb_mg_transfer* t) { return (size_t)t->Xc * t->Yc * t->nvec; }
+int glb_mg_prolong(glb_mg_transfer* t, void* d_fine, const void* d_coarse) {
+  g_calls++;
+  cplx* fine = (cplx*)d_fine; const cplx* coarse = (const cplx*)d_coarse;
+  const size_t nf = glb_mg_fine_size(t);
+  for (size_t f = 0; f < nf; f++) {
+    const size_t site = f / t->dof_f;
+    const int x = (int)(site % t->Xf), y = (int)(site / t->Xf);
+    const size_t cs = (size_t)(y / t->by) * t->Xc + x / t->bx;
+    cplx acc = 0.0;
+    for (int v = 0; v < t->nvec; v++) acc += t->null[v][f] * coarse[cs * t->nvec + v];
+    fine[f] = acc;
+  }
+  return GLB_OK;
+}
+int glb_mg_restrict(glb_mg_transfer* t, void* d_coarse, const void* d_fine) {
+  g_calls++;
+  cplx* coarse = (cplx*)d_coarse; const cplx* fine = (const cplx*)d_fine;
+  const size_t nc = glb_mg_coarse_size(t);
+  for (size_t i = 0; i < nc; i++) {
+    const int v = (int)(i % t->nvec);
+    const size_t cs = i / t->nvec;
+    const int xc = (int)(cs % t->Xc), yc = (int)(cs / t->Xc);
+    cplx acc = 0.0;
+    for (int y = yc * t->by; y < (yc + 1) * t->by; y++)
+      for (int x = xc * t->bx; x < (xc + 1) * t->bx; x++)
+        for (int d = 0; d < t->dof_f; d++) {
+          const size_t f = ((size_t)y * t->Xf + x) * t->dof_f + d;
+          acc += std::conj(t->null[v][f]) * fine[f];
+        }
+    coarse[i] = acc;
+  }
+  return GLB_OK;
+}
 }  // extern "C"
