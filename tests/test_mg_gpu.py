@@ -54,14 +54,18 @@ def test_transfers_bit_exact(ctx, glb, L, nvec):
 
 
 @pytest.mark.parametrize("L,nvec,cfg", [(16, 2, dict()), (32, 4, dict()),
-                                         (32, 4, dict(smooth="BICGSTAB", n_pre=3, n_post=2, inner="CG", rel_res=1e-3)),
-                                         (32, 2, dict(n_pre=0, n_post=4, inner="BICGSTAB"))])
+                                         (32, 4, dict(smooth="BICGSTAB", n_pre=3, n_post=2, inner="CG")),
+                                         (32, 2, dict(n_pre=0, n_post=4, inner="BICGSTAB")),
+                                         (32, 2, dict(n_pre=2, n_post=0, inner="CR", n_restart=16))])
 def test_vcycle_matches_reference(ctx, glb, L, nvec, cfg):
+    """one cycle with the coarse system solved to 1e-11: a coarse solve stopped at the reference's default 1e-2
+    may take one iteration more or less on the device (reduction order), which changes the cycle's output at the
+    1e-2 level -- that case is covered by the outer-solve test below, where only iteration counts matter"""
     orc = oracle_py.load("ref")
     mg, U, b = build_reference_mg(orc, L=L, nvec=nvec)
     ops, tr = device_hierarchy(ctx, mg)
     dmg = ctx.multigrid(ops, [tr])
-    full = dict(smooth="GCR", n_pre=6, n_post=6, inner="GCR", n_max=1024, n_restart=64, rel_res=1e-2)
+    full = dict(smooth="GCR", n_pre=6, n_post=6, inner="GCR", n_max=4096, n_restart=64, rel_res=1e-11)
     full.update(cfg)
     mg.set_precond(**full)
     dmg.set(**full)
@@ -70,7 +74,7 @@ def test_vcycle_matches_reference(ctx, glb, L, nvec, cfg):
     out, rhs = ctx.vector(b.size), ctx.vector(b.size).upload(b)
     dmg.vcycle(out, rhs)
     # Krylov smoothers amplify the reduction-order rounding (BiCGStab most): measured 1e-12 .. 4e-9
-    assert rel_err(out.download(), want) < 1e-7
+    assert rel_err(out.download(), want) < 1e-6
     cnt = dmg.counts()
     assert cnt["presmooth"][0] == (full["n_pre"] + 2 if full["n_pre"] else 0) or full["smooth"] != "GCR"
     assert cnt["krylov"][1] > 0
@@ -90,6 +94,7 @@ def test_vpgcr_mg_solve(ctx, glb, L, nvec, restart, native):
     with quiet_stdout():
         xo, want = mg.vpgcr(b, max_iter=1000, eps=5e-7, restart_freq=restart)
     x, rhs = ctx.vector(b.size), ctx.vector(b.size).upload(b)
+    x.zero()   # pool memory is not cleared: the initial guess is the caller's business, as in the reference
     got = dmg.vpgcr(x, rhs, max_iter=1000, eps=5e-7, restart_freq=restart)
     assert got["success"] and want["success"]
     assert abs(got["iter"] - want["iter"]) <= max(1, int(0.02 * want["iter"]))
@@ -98,5 +103,7 @@ def test_vpgcr_mg_solve(ctx, glb, L, nvec, restart, native):
     assert np.linalg.norm(b - D.apply(xs)) / np.linalg.norm(b) < 5e-7 * 1.0001
     assert rel_err(xs, xo) < 1e-4
     # against the unpreconditioned solver the reference's own tests compare with: an order of magnitude fewer applies
-    plain = ctx.solve("GCR_RESTART", ops[0], ctx.vector(b.size), rhs, max_iter=100000, eps=5e-7, restart_freq=64)
+    x0 = ctx.vector(b.size)
+    x0.zero()
+    plain = ctx.solve("GCR_RESTART", ops[0], x0, rhs, max_iter=100000, eps=5e-7, restart_freq=64)
     assert plain["iter"] > 5 * got["iter"]
