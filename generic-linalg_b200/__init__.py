@@ -109,6 +109,7 @@ def libs():
         "glb_update_p_ap_norm": (ci, [vp, ci, sz, vp, vp, pd, vp, vp, pd]),
         "glb_bicgstab_update": (ci, [vp, ci, sz, pd, vp, pd, vp, vp, vp, vp, vp, pd]),
         "glb_bicgstab_pupdate": (ci, [vp, ci, sz, vp, pd, pd, vp, vp]),
+        "glb_conj": (ci, [vp, ci, sz, vp, vp]), "glb_bicgstabm_update_s": (ci, [vp, ci, sz, pd, vp, vp, vp, vp]),
         "glb_cgm_update_x": (ci, [vp, ci, sz, ci, pd, C.POINTER(vp), C.POINTER(vp)]),
         "glb_cgm_update_p": (ci, [vp, ci, sz, ci, pd, pd, vp, C.POINTER(vp)]),
         "glb_cg_solve_supported": (ci, [vp]),
@@ -130,6 +131,9 @@ def libs():
                                       C.POINTER(Result)]),
         "glbx_dev_solve": (ci, [ci, vp, vp, vp, ci, cd, ci, ci, ci, C.POINTER(Result)]),
         "glbx_dev_solve_cg_m": (ci, [vp, C.POINTER(vp), vp, ci, ci, ci, cd, vp, ci, ci, C.POINTER(Result)]),
+        "glbx_host_solve_multi": (ci, [ci, C.POINTER(OpDesc), C.POINTER(vp), vp, ci, ci, ci, cd, vp, ci, ci,
+                                       C.POINTER(Result)]),
+        "glbx_host_solve_precond": (ci, [ci, C.POINTER(OpDesc), vp, vp, ci, cd, ci, ci, ci, cd, ci, C.POINTER(Result)]),
         "glbx_mg_create": (vp, [ci, C.POINTER(vp), C.POINTER(vp)]), "glbx_mg_destroy": (None, [vp]),
         "glbx_mg_set": (None, [vp, ci, ci, ci, ci, ci, ci, cd, ci, ci]),
         "glbx_mg_vcycle": (ci, [vp, vp, vp]),
@@ -554,6 +558,32 @@ class Context:
                                           _p(shifts), int(worst_first), verbosity, C.byref(res)),
              "glbx_host_solve_cg_m")
         return res.as_dict(), shifts
+
+    MULTI = dict(CG_M=0, CR_M=1, BICGSTAB_M=2)
+    PRECOND_SOLVER = dict(PCG=0, FPCG=1, FPCG_RESTART=2, VPGCR=3, VPGCR_RESTART=4, PBICGSTAB=5, PBICGSTAB_RESTART=6)
+    PRECOND = dict(IDENTITY=0, GCR=1)
+
+    def host_solve_multi(self, which, desc, xs, b, shifts, resid_freq_check=10, max_iter=10000, eps=1e-10,
+                         worst_first=False, verbosity=0):
+        """minv_vector_{cg,cr,bicgstab}_m with HOST vectors (generic_cg_m.h, generic_cr_m.h, generic_bicgstab_m.h)"""
+        n = len(xs)
+        shifts = np.array(shifts, dtype=np.float64, copy=True)
+        ptrs = (C.c_void_p * n)(*[x.ctypes.data for x in xs])
+        res = Result()
+        _chk(self.ho.glbx_host_solve_multi(self.MULTI[which], C.byref(desc), ptrs, _p(b), n, resid_freq_check, max_iter,
+                                           eps, _p(shifts), int(worst_first), verbosity, C.byref(res)),
+             "glbx_host_solve_multi")
+        return res.as_dict(), shifts
+
+    def host_solve_precond(self, solver, desc, x, b, max_iter=10000, eps=1e-10, restart_freq=0, precond="IDENTITY",
+                           n_step=4, rel_res=1e-20, verbosity=0):
+        """the preconditioned family (generic_inverters_precond.h) with HOST vectors and the stock preconditioners
+        of generic_precond.h: identity_preconditioner, or gcr_preconditioner (n_step iterations on the same operator)"""
+        res = Result()
+        _chk(self.ho.glbx_host_solve_precond(self.PRECOND_SOLVER[solver], C.byref(desc), _p(x), _p(b), max_iter, eps,
+                                             restart_freq, self.PRECOND[precond], n_step, rel_res, verbosity,
+                                             C.byref(res)), "glbx_host_solve_precond")
+        return res.as_dict()
 
     def force_host_scalars(self, on):
         self.ho.glbx_force_host_scalars(int(on))

@@ -191,6 +191,22 @@ struct FBicgP {  // p = r + beta*(p - omega*Ap)     vectors: r, Ap, p    (generi
   T beta, omega;
   __device__ void elem(T (&e)[NV], double*) const { e[2] = fadd(e[0], fmul(beta, fsub(e[2], fmul(omega, e[1])))); }
 };
+template <typename T>
+struct FConj {  // out = conj(x)   (a copy for real fields)     vectors: x, out    (generic_vector.h conj<>)
+  static constexpr int NV = 2, RD = 1, WR = 2, NRED = 0;
+  __device__ static double cj(double a) { return a; }
+  __device__ static cplx cj(cplx a) { return mk(a.x, -a.y); }
+  __device__ void elem(T (&e)[NV], double*) const { e[1] = cj(e[0]); }
+};
+template <typename T>
+struct FBicgMS {  // s_n = c0 r + c1 (s_n - c2 (c3 w - c4 r_prev))   vectors: r, w, r_prev, s_n  (generic_bicgstab_m.cpp:705)
+  static constexpr int NV = 4, RD = 15, WR = 8, NRED = 0;
+  T c0, c1, c2, c3, c4;
+  __device__ void elem(T (&e)[NV], double*) const {
+    const T inner = fsub(fmul(c3, e[1]), fmul(c4, e[2]));
+    e[3] = fadd(fmul(c0, e[0]), fmul(c1, fsub(e[3], fmul(c2, inner))));
+  }
+};
 
 template <typename T>
 static T coef(const double a[2]);
@@ -588,6 +604,23 @@ int glb_bicgstab_pupdate(glb_context* ctx, int dtype, size_t n, const void* r, c
   return ew_call<FBicgP, 3>(ctx, dtype, n, false, v, [&](auto& f) {
     f.beta = coef<decltype(f.beta)>(beta);
     f.omega = coef<decltype(f.omega)>(omega);
+  });
+}
+
+int glb_conj(glb_context* ctx, int dtype, size_t n, const void* x, void* out) {
+  VecPtrs<2> v{{(void*)x, out}};
+  return ew_call<FConj, 2>(ctx, dtype, n, false, v, NoInit());
+}
+
+int glb_bicgstabm_update_s(glb_context* ctx, int dtype, size_t n, const double c[10], const void* r, const void* w,
+                           const void* r_prev, void* s_n) {
+  VecPtrs<4> v{{(void*)r, (void*)w, (void*)r_prev, s_n}};
+  return ew_call<FBicgMS, 4>(ctx, dtype, n, false, v, [&](auto& f) {
+    f.c0 = coef<decltype(f.c0)>(c);
+    f.c1 = coef<decltype(f.c1)>(c + 2);
+    f.c2 = coef<decltype(f.c2)>(c + 4);
+    f.c3 = coef<decltype(f.c3)>(c + 6);
+    f.c4 = coef<decltype(f.c4)>(c + 8);
   });
 }
 

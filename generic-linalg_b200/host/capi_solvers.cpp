@@ -7,6 +7,7 @@
 
 #include "coarse_stencil.h"
 #include "dev_internal.hpp"
+#include "generic_inverters_precond.h"
 #include "mg_complex.h"
 #include "operators.h"
 #include "operators_stencil.h"
@@ -281,6 +282,80 @@ int glbx_dev_solve_cg_m(glb_operator* op, void** d_phi, void* d_phi0, int n_shif
   return GLB_OK;
 }
 
+
+// ---- multishift CR / BiCGStab and the preconditioned family through the reference's own calls
+// which: 0 minv_vector_cg_m, 1 minv_vector_cr_m, 2 minv_vector_bicgstab_m   (HOST vectors)
+int glbx_host_solve_multi(int which, const glbx_opdesc* d, void** phi, const void* phi0, int n_shift, int resid_freq_check,
+                          int max_iter, double eps, double* shifts, int worst_first, int verbosity, glbx_result* out) {
+  HostOp h;
+  if (!build_host_op(d, &h)) return GLB_ERR_ARG;
+  inversion_verbose_struct v;
+  make_verb(verbosity, &v);
+  inversion_info inf(n_shift);
+  if (h.cz) {
+    zc** p = (zc**)phi;
+    zc* b = (zc*)phi0;
+    if (which == 0) inf = minv_vector_cg_m(p, b, n_shift, h.size, resid_freq_check, max_iter, eps, shifts, h.cz, h.extra, worst_first != 0, &v);
+    if (which == 1) inf = minv_vector_cr_m(p, b, n_shift, h.size, resid_freq_check, max_iter, eps, shifts, h.cz, h.extra, worst_first != 0, &v);
+    if (which == 2) inf = minv_vector_bicgstab_m(p, b, n_shift, h.size, resid_freq_check, max_iter, eps, shifts, h.cz, h.extra, worst_first != 0, &v);
+  } else {
+    double** p = (double**)phi;
+    double* b = (double*)phi0;
+    if (which == 0) inf = minv_vector_cg_m(p, b, n_shift, h.size, resid_freq_check, max_iter, eps, shifts, h.cd, h.extra, worst_first != 0, &v);
+    if (which == 1) inf = minv_vector_cr_m(p, b, n_shift, h.size, resid_freq_check, max_iter, eps, shifts, h.cd, h.extra, worst_first != 0, &v);
+    if (which == 2) inf = minv_vector_bicgstab_m(p, b, n_shift, h.size, resid_freq_check, max_iter, eps, shifts, h.cd, h.extra, worst_first != 0, &v);
+  }
+  flatten(inf, out);
+  return GLB_OK;
+}
+}  // extern "C"
+
+namespace {
+// solver: 0 PCG, 1 FPCG, 2 FPCG restart, 3 VPGCR, 4 VPGCR restart, 5 PBiCGStab, 6 PBiCGStab restart
+// precond: 0 identity_preconditioner, 1 gcr_preconditioner (n_step iterations to rel_res on the same operator)
+template <typename T, typename G>
+inversion_info run_host_precond(int solver, T* phi, T* b, int size, int max_iter, double eps, int rf,
+                                void (*cb)(T*, T*, void*), void* extra, int precond, int n_step, double rel_res,
+                                inversion_verbose_struct* v) {
+  G g;
+  g.n_step = n_step;
+  g.rel_res = rel_res;
+  g.matrix_vector = cb;
+  g.matrix_extra_data = extra;
+  typedef void (*pfn)(T*, T*, int, void*, inversion_verbose_struct*);
+  pfn pc_gcr = &gcr_preconditioner, pc_id = &identity_preconditioner;
+  pfn pc = (precond == 1) ? pc_gcr : pc_id;
+  void* pci = (precond == 1) ? (void*)&g : 0;
+  switch (solver) {
+    case 0: return minv_vector_cg_precond(phi, b, size, max_iter, eps, cb, extra, pc, pci, v);
+    case 1: return minv_vector_cg_flex_precond(phi, b, size, max_iter, eps, cb, extra, pc, pci, v);
+    case 2: return minv_vector_cg_flex_precond_restart(phi, b, size, max_iter, eps, rf, cb, extra, pc, pci, v);
+    case 3: return minv_vector_gcr_var_precond(phi, b, size, max_iter, eps, cb, extra, pc, pci, v);
+    case 4: return minv_vector_gcr_var_precond_restart(phi, b, size, max_iter, eps, rf, cb, extra, pc, pci, v);
+    case 5: return minv_vector_bicgstab_precond(phi, b, size, max_iter, eps, cb, extra, pc, pci, v);
+    case 6: return minv_vector_bicgstab_precond_restart(phi, b, size, max_iter, eps, rf, cb, extra, pc, pci, v);
+  }
+  return inversion_info();
+}
+}  // namespace
+
+extern "C" {
+int glbx_host_solve_precond(int solver, const glbx_opdesc* d, void* phi, const void* phi0, int max_iter, double eps,
+                            int restart_freq, int precond, int n_step, double rel_res, int verbosity, glbx_result* out) {
+  HostOp h;
+  if (!build_host_op(d, &h)) return GLB_ERR_ARG;
+  inversion_verbose_struct v;
+  make_verb(verbosity, &v);
+  inversion_info inf;
+  if (h.cz)
+    inf = run_host_precond<zc, gcr_precond_struct_complex>(solver, (zc*)phi, (zc*)phi0, h.size, max_iter, eps, restart_freq,
+                                                          h.cz, h.extra, precond, n_step, rel_res, &v);
+  else
+    inf = run_host_precond<double, gcr_precond_struct_real>(solver, (double*)phi, (double*)phi0, h.size, max_iter, eps,
+                                                           restart_freq, h.cd, h.extra, precond, n_step, rel_res, &v);
+  flatten(inf, out);
+  return GLB_OK;
+}
 
 // ---- multigrid-preconditioned solves (mg_complex.h): the hierarchy is handed over as device objects
 typedef struct glbx_mg {

@@ -828,3 +828,626 @@ inversion_info minv_unpreconditioned_dev(zcplx* lhs, zcplx* rhs, int size, minv_
                                          inversion_verbose_struct* verb) {
   return dispatch_dev<zcplx>(lhs, rhs, size, type, p, mv, extra, verb);
 }
+
+// =====================================================================================================
+// the rest of the solver family on the same kernels -- preconditioned CG / flexible CG /
+// BiCGStab (generic_cg_precond.cpp, generic_cg_flex_precond.cpp, generic_bicgstab_precond.cpp), the
+// multishift CR and BiCGStab (generic_cr_m.cpp, generic_bicgstab_m.cpp), the enum dispatch
+// (generic_inverter_precond.cpp) and the stock preconditioners of generic_precond.cpp.  Pure host-shell
+// work: every vector operation is an existing C-ABI call.
+// =====================================================================================================
+namespace {
+
+// ------------------------------------------------------------------------------------------ PCG
+// generic_cg_precond.cpp:23-145 / :150-275
+template <typename T>
+inversion_info cg_precond_dev(T* x, T* b, int size, int max_iter, double eps, void (*fn)(T*, T*, void*), void* extra,
+                              void (*precond)(T*, T*, int, void*, inversion_verbose_struct*), void* precond_info,
+                              inversion_verbose_struct* verb) {
+  inversion_info inf;
+  DevOp<T> A = make_op<T>(fn, extra, size);
+  Blas<T> B = {A.ctx, (size_t)size};
+  Work<T> W(B);
+  inversion_verbose_struct verb_prec;
+  shuffle_verbosity_precond(&verb_prec, verb);
+  T *r = W.get(), *p = W.get(), *Ap = W.get(), *z = W.get();
+  const double bsqrt = sqrt(B.norm2sq(b));
+  A.apply(p, x);
+  B.sub(b, p, r);
+  B.zero(z);
+  precond(z, r, size, precond_info, &verb_prec);
+  B.copy(p, z);
+  A.apply(Ap, p);
+  T zdotr = B.dot(z, r);
+  if (IsComplex<T>::value) {  // generic_cg_precond.cpp:199 : the complex overload announces its loop
+    printf("Starting loop!\n");
+    fflush(stdout);
+  }
+  double rsq = 0.0;
+  int k;
+  for (k = 0; k < max_iter; k++) {
+    const T alpha = zdotr / B.dot(p, Ap);
+    rsq = B.update_xr_norm(alpha, p, x, -alpha, Ap, r);
+    print_verbosity_resid(verb, "PCG", k + 1, A.ops, sqrt(rsq) / bsqrt);
+    if (sqrt(rsq) < eps * bsqrt || k == max_iter - 1) break;
+    B.zero(z);
+    precond(z, r, size, precond_info, &verb_prec);
+    const T zdotr_new = B.dot(r, z);
+    const T beta = zdotr_new / zdotr;
+    zdotr = zdotr_new;
+    B.xpay(z, beta, p);  // p = z + beta p
+    A.apply(Ap, p);
+  }
+  inf.success = !(k == max_iter - 1);
+  k++;
+  A.apply(Ap, x);
+  const double truersq = B.diffnorm2sq(Ap, b);
+  inf.ops_count = A.ops;
+  print_verbosity_summary(verb, "PCG", inf.success, k, inf.ops_count, sqrt(truersq) / bsqrt);
+  inf.resSq = truersq;
+  inf.iter = k;
+  inf.name = "Preconditioned CG";
+  return inf;
+}
+
+// ------------------------------------------------------------------------------------------ FPCG
+// generic_cg_flex_precond.cpp:26-166 / :223-362.  Like VPGCR every direction is kept; the coefficients
+// beta_ij = -<Ap_i, z>/<p_i, Ap_i> (:310) all use the same z: one batched pass.
+template <typename T>
+inversion_info cg_flex_precond_dev(T* x, T* b, int size, int max_iter, double eps, void (*fn)(T*, T*, void*), void* extra,
+                                   void (*precond)(T*, T*, int, void*, inversion_verbose_struct*), void* precond_info,
+                                   inversion_verbose_struct* verb) {
+  inversion_info inf;
+  DevOp<T> A = make_op<T>(fn, extra, size);
+  Blas<T> B = {A.ctx, (size_t)size};
+  Work<T> W(B);
+  inversion_verbose_struct verb_prec;
+  shuffle_verbosity_precond(&verb_prec, verb);
+  T *r = W.get(), *z = W.get(), *Az = W.get();
+  std::vector<const void*> ps, Aps;
+  std::vector<T> pAp;
+  T* p = W.get();
+  T* Ap = W.get();
+  const double bsqrt = sqrt(B.norm2sq(b));
+  A.apply(p, x);
+  B.sub(b, p, r);
+  B.zero(z);
+  precond(z, r, size, precond_info, &verb_prec);
+  B.copy(p, z);
+  A.apply(Ap, p);
+  double rsq = 0.0;
+  int k;
+  std::vector<double> dots, coef;
+  for (k = 0; k < max_iter; k++) {
+    ps.push_back(p);
+    Aps.push_back(Ap);
+    pAp.push_back(B.dot(p, Ap));
+    const T alpha = B.dot(p, r) / pAp.back();
+    rsq = B.update_xr_norm(alpha, p, x, -alpha, Ap, r);
+    print_verbosity_resid(verb, "FPCG", k + 1, A.ops, sqrt(rsq) / bsqrt);
+    if (sqrt(rsq) < eps * bsqrt || k == max_iter - 1) break;
+    B.zero(z);
+    precond(z, r, size, precond_info, &verb_prec);
+    A.apply(Az, z);
+    dots.resize(2 * (k + 1));
+    coef.resize(2 * (k + 1));
+    GLBX(glb_multi_dot(A.ctx, Traits<T>::dtype, size, k + 1, Aps.data(), z, dots.data()));
+    for (int ii = 0; ii <= k; ii++) {
+      const T beta = -Traits<T>::unpack(&dots[2 * ii]) / pAp[ii];
+      Traits<T>::pack(beta, &coef[2 * ii]);
+    }
+    p = W.get();
+    Ap = W.get();
+    GLBX(glb_lincomb(A.ctx, Traits<T>::dtype, size, k + 1, coef.data(), ps.data(), z, p));
+    GLBX(glb_lincomb(A.ctx, Traits<T>::dtype, size, k + 1, coef.data(), Aps.data(), Az, Ap));
+  }
+  inf.success = !(k == max_iter - 1);
+  k++;
+  A.apply(Az, x);
+  const double truersq = B.diffnorm2sq(Az, b);
+  inf.ops_count = A.ops;
+  print_verbosity_summary(verb, "FPCG", inf.success, k, inf.ops_count, sqrt(truersq) / bsqrt);
+  inf.resSq = truersq;
+  inf.iter = k;
+  inf.name = "Flexibly Preconditioned CG";
+  return inf;
+}
+
+// generic_cg_flex_precond.cpp:171-218 / :367-415 : the restart loop spends one more apply on the true residual
+template <typename T>
+inversion_info cg_flex_precond_restart_dev(T* x, T* b, int size, int max_iter, double res, int rf,
+                                           void (*fn)(T*, T*, void*), void* extra,
+                                           void (*precond)(T*, T*, int, void*, inversion_verbose_struct*),
+                                           void* precond_info, inversion_verbose_struct* verb) {
+  glb_context* ctx = ctx_of<T>(fn, extra);
+  Blas<T> B = {ctx, (size_t)size};
+  const double bsqrt = sqrt(B.norm2sq(b));
+  const std::string name = label("Flexibly Preconditioned Restarted CG", rf);
+  inversion_verbose_struct verb_rest;
+  shuffle_verbosity_restart(&verb_rest, verb);
+  inversion_info inf;
+  int iter = 0, ops = 0;
+  do {
+    inf = cg_flex_precond_dev<T>(x, b, size, rf, res, fn, extra, precond, precond_info, &verb_rest);
+    iter += inf.iter;
+    ops += inf.ops_count;
+    print_verbosity_restart(verb, name, iter, ops, sqrt(inf.resSq) / bsqrt);
+  } while (iter < max_iter && inf.success == false && sqrt(inf.resSq) / bsqrt > res);
+  DevOp<T> A = make_op<T>(fn, extra, size);
+  Work<T> W(B);
+  T* Ax = W.get();
+  A.apply(Ax, x);
+  ops++;
+  const double truersq = B.diffnorm2sq(Ax, b);
+  inf.resSq = truersq;
+  if (IsComplex<T>::value) {  // :398 prints before, the real overload (:209-211) after the counts are stored
+    print_verbosity_summary(verb, name, inf.success, iter, inf.ops_count, sqrt(truersq) / bsqrt);
+    inf.iter = iter;
+    inf.ops_count = ops;
+  } else {
+    inf.iter = iter;
+    inf.ops_count = ops;
+    print_verbosity_summary(verb, name, inf.success, iter, inf.ops_count, sqrt(truersq) / bsqrt);
+  }
+  inf.name = name;
+  inf.success = !(sqrt(inf.resSq) / bsqrt > res);
+  return inf;
+}
+
+// ------------------------------------------------------------------------------------------ PBiCGStab
+// generic_bicgstab_precond.cpp:22-176 / :226-380 (flexible BiCGStab).  Quirks kept: the loop has no
+// k == max_iter-1 exit, failure is k == max_iter and then k is NOT incremented; name "BiCGStab".
+template <typename T>
+inversion_info bicgstab_precond_dev(T* x, T* b, int size, int max_iter, double eps, void (*fn)(T*, T*, void*),
+                                    void* extra, void (*precond)(T*, T*, int, void*, inversion_verbose_struct*),
+                                    void* precond_info, inversion_verbose_struct* verb) {
+  inversion_info inf;
+  DevOp<T> A = make_op<T>(fn, extra, size);
+  Blas<T> B = {A.ctx, (size_t)size};
+  Work<T> W(B);
+  inversion_verbose_struct verb_prec;
+  shuffle_verbosity_precond(&verb_prec, verb);
+  T *r = W.get(), *r0 = W.get(), *p = W.get(), *s = W.get(), *pt = W.get(), *Apt = W.get(), *st = W.get(),
+    *Ast = W.get();
+  const double bsqrt = sqrt(B.norm2sq(b));
+  A.apply(Apt, x);
+  B.sub(b, Apt, r);
+  B.copy(r0, r);
+  B.copy(p, r);
+  T rho = B.dot(r0, r);
+  double rsq = 0.0;
+  int k;
+  for (k = 0; k < max_iter; k++) {
+    B.zero(pt);
+    precond(pt, p, size, precond_info, &verb_prec);
+    const T r0Apt = A.apply_dot(Apt, pt, r0);
+    const T alpha = rho / r0Apt;
+    B.axpyz(-alpha, Apt, r, s);  // s = r - alpha A ptilde
+    B.zero(st);
+    precond(st, s, size, precond_info, &verb_prec);
+    double AsAs = 0.0;
+    const T sAst = A.apply_dot_norm(Ast, st, s, &AsAs);  // <s, A stilde>, |A stilde|^2
+    const T omega = sAst / T(AsAs);                      // :316 dot(s,Astilde)/dot(Astilde,Astilde)
+    // x = x + alpha ptilde + omega stilde  (:319-322: one expression, left to right) ; r = s - omega A stilde
+    B.axpy(alpha, pt, x);
+    B.axpy(omega, st, x);
+    B.axpyz(-omega, Ast, s, r);
+    rsq = B.norm2sq(r);
+    print_verbosity_resid(verb, "Preconditioned BiCGStab", k + 1, A.ops, sqrt(rsq) / bsqrt);
+    if (sqrt(rsq) < eps * bsqrt) break;
+    const T rhoNew = B.dot(r0, r);
+    const T beta = rhoNew / rho * (alpha / omega);
+    rho = rhoNew;
+    // p = r + beta (p - omega A ptilde)
+    double cb[2], cmo[2];
+    Traits<T>::pack(beta, cb);
+    Traits<T>::pack(omega, cmo);
+    GLBX(glb_bicgstab_pupdate(A.ctx, Traits<T>::dtype, size, r, cb, cmo, Apt, p));
+  }
+  if (k == max_iter) {
+    inf.success = false;
+  } else {
+    k++;
+    inf.success = true;
+  }
+  A.apply(Apt, x);
+  const double truersq = B.diffnorm2sq(Apt, b);
+  inf.ops_count = A.ops;
+  print_verbosity_summary(verb, "Preconditioned BiCGStab", inf.success, k, inf.ops_count, sqrt(truersq) / bsqrt);
+  inf.resSq = truersq;
+  inf.iter = k;
+  inf.name = "BiCGStab";
+  return inf;
+}
+
+}  // namespace
+
+namespace {
+
+// shared tail of the multishift solvers: undo the permutation of phi[] / shifts[] (generic_cg_m.cpp:533-558)
+template <typename T>
+void undo_shift_permutation(T** phi, double* shifts, std::vector<int>& mapping, int n_shift) {
+  for (int s = 0; s < n_shift; s++) {
+    if (mapping[s] != s) {
+      for (int m = s + 1; m < n_shift; m++) {
+        if (mapping[m] == s) {
+          std::swap(phi[m], phi[s]);
+          std::swap(shifts[m], shifts[s]);
+          mapping[m] = mapping[s];
+          mapping[s] = s;
+          s--;
+          break;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ CR-M
+// generic_cr_m.cpp:24-318 / :323-622.  Same shifted recurrences as CG-M (zeta, beta_s, alpha_s) on top of the
+// CR base iteration; both overloads test abs(zeta).
+template <typename T>
+inversion_info cr_m_dev(T** phi, T* b, int n_shift, int size, int check_every, int max_iter, double eps, double* shifts,
+                        void (*fn)(T*, T*, void*), void* extra, bool worst_first, inversion_verbose_struct* verb) {
+  inversion_info inf(n_shift);
+  DevOp<T> A = make_op<T>(fn, extra, size);
+  Blas<T> B = {A.ctx, (size_t)size};
+  Work<T> W(B);
+  std::vector<T> alpha_s(n_shift, T(0.0)), beta_s(n_shift, T(1.0)), zeta_s(n_shift, T(1.0)), zeta_prev(n_shift, T(1.0));
+  std::vector<T*> p_s(n_shift);
+  std::vector<int> mapping(n_shift);
+  for (int s = 0; s < n_shift; s++) {
+    p_s[s] = W.get();
+    mapping[s] = s;
+  }
+  T *r = W.get(), *Ar = W.get(), *p = W.get(), *Ap = W.get();
+  int live = n_shift;
+  T beta = 1.0, alpha = 0.0, beta_prev;
+  const double bsqrt = sqrt(B.norm2sq(b));
+  for (int s = 0; s < n_shift; s++) {
+    B.copy(p_s[s], b);
+    B.zero(phi[s]);
+  }
+  B.copy(p, b);
+  B.copy(r, b);
+  A.apply(Ap, p);
+  B.copy(Ar, Ap);
+  double Apsq = B.norm2sq(Ap);
+  double rsq = B.norm2sq(r);
+  std::vector<double> c0, c1;
+  int k;
+  for (k = 0; k < max_iter; k++) {
+    beta_prev = beta;
+    beta = -B.dot(Ap, r) / Apsq;
+    c0.resize(2 * live);
+    for (int s = 0; s < live; s++) {
+      const T z_old = zeta_s[s];
+      zeta_s[s] = (zeta_s[s] * zeta_prev[s] * beta_prev) /
+                  (beta * alpha * (zeta_prev[s] - zeta_s[s]) + zeta_prev[s] * beta_prev * (1.0 - shifts[s] * beta));
+      zeta_prev[s] = z_old;
+      beta_s[s] = beta * zeta_s[s] / zeta_prev[s];
+      Traits<T>::pack(beta_s[s], &c0[2 * s]);
+    }
+    if (live > 0)
+      GLBX(glb_cgm_update_x(A.ctx, Traits<T>::dtype, size, live, c0.data(), (const void* const*)p_s.data(),
+                            (void* const*)phi));
+    rsq = B.axpy_norm(beta, Ap, r);  // r = r + beta Ap ; |r|^2
+    print_verbosity_resid(verb, "CR-M", k + 1, A.ops, sqrt(rsq) / bsqrt);
+    if (k % check_every == 0) {
+      for (int s = 0; s < live; s++) {
+        if (std::abs(zeta_s[s]) * sqrt(rsq) < eps * bsqrt) {
+          live--;
+          if (live != s) {
+            std::swap(mapping[live], mapping[s]);
+            std::swap(phi[live], phi[s]);
+            std::swap(p_s[live], p_s[s]);
+            std::swap(alpha_s[live], alpha_s[s]);
+            std::swap(beta_s[live], beta_s[s]);
+            std::swap(zeta_s[live], zeta_s[s]);
+            std::swap(zeta_prev[live], zeta_prev[s]);
+            std::swap(shifts[live], shifts[s]);
+            s--;
+          }
+        }
+      }
+    }
+    if ((worst_first && std::abs(zeta_s[0]) * sqrt(rsq) < eps * bsqrt) || live == 0 || k == max_iter - 1) break;
+    const T ApAr = A.apply_dot(Ar, r, Ap);  // Ar = A r, <Ap, Ar>
+    alpha = -ApAr / Apsq;
+    c0.resize(2 * live);
+    c1.resize(2 * live);
+    for (int s = 0; s < live; s++) {
+      alpha_s[s] = alpha * zeta_s[s] * beta_s[s] / (zeta_prev[s] * beta);
+      Traits<T>::pack(zeta_s[s], &c0[2 * s]);
+      Traits<T>::pack(alpha_s[s], &c1[2 * s]);
+    }
+    if (live > 0)
+      GLBX(glb_cgm_update_p(A.ctx, Traits<T>::dtype, size, live, c0.data(), c1.data(), r, (void* const*)p_s.data()));
+    double ca[2];
+    Traits<T>::pack(alpha, ca);
+    // p = r + alpha p ; Ap = Ar + alpha Ap ; |Ap|^2
+    GLBX(glb_update_p_ap_norm(A.ctx, Traits<T>::dtype, size, r, Ar, ca, p, Ap, &Apsq));
+  }
+  inf.success = !(k == max_iter - 1);
+  k++;
+  undo_shift_permutation(phi, shifts, mapping, n_shift);
+  std::vector<double> relres(n_shift);
+  for (int s = 0; s < n_shift; s++) {
+    A.apply(Ap, phi[s]);
+    B.axpy(T(shifts[s]), phi[s], Ap);
+    inf.resSqmrhs[s] = B.diffnorm2sq(Ap, b);
+    relres[s] = sqrt(inf.resSqmrhs[s]) / bsqrt;
+  }
+  inf.ops_count = A.ops;
+  print_verbosity_summary_multi(verb, "CR-M", inf.success, k, inf.ops_count, relres.data(), n_shift);
+  inf.resSq = 0.0;  // truersq is never assigned (generic_cr_m.cpp:617)
+  inf.iter = k;
+  inf.name = "CR-M";
+  return inf;
+}
+
+inline bool is_nan_d(double v) { return v != v; }
+
+// ------------------------------------------------------------------------------------------ BiCGStab-M
+// generic_bicgstab_m.cpp:26-397 / :402-774 (Jegerlehner's shifted BiCGStab).  w^dag = conj(r_0) in the complex
+// overload (:494), r_0 in the real one; dot() conjugates its first argument, so <w^dag, v> = sum r_0 v.
+template <typename T>
+inversion_info bicgstab_m_dev(T** phi, T* b, int n_shift, int size, int check_every, int max_iter, double eps,
+                              double* shifts, void (*fn)(T*, T*, void*), void* extra, bool worst_first,
+                              inversion_verbose_struct* verb) {
+  inversion_info inf(n_shift);
+  DevOp<T> A = make_op<T>(fn, extra, size);
+  Blas<T> B = {A.ctx, (size_t)size};
+  Work<T> W(B);
+  const T one = 1.0, zero = 0.0;
+  std::vector<T> alpha_s(n_shift, zero), beta_s(n_shift, one), zeta_s(n_shift, one), zeta_prev(n_shift, one),
+      chi_s(n_shift, zero), rho_s(n_shift, one), rho_prev(n_shift, one);
+  std::vector<T*> s_s(n_shift);
+  std::vector<int> mapping(n_shift);
+  for (int n = 0; n < n_shift; n++) {
+    s_s[n] = W.get();
+    mapping[n] = n;
+  }
+  T *r = W.get(), *r_prev = W.get(), *s = W.get(), *As = W.get(), *w = W.get(), *Aw = W.get(), *wdag = W.get();
+  int live = n_shift;
+  T beta = 1.0, alpha = 0.0, beta_prev, chi = 0.0;
+  bool breakdown = false;
+  const double bsqrt = sqrt(B.norm2sq(b));
+  for (int n = 0; n < n_shift; n++) {
+    B.copy(s_s[n], b);
+    B.zero(phi[n]);
+  }
+  B.copy(s, b);
+  B.copy(r, b);
+  B.copy(r_prev, r);
+  A.apply(As, s);
+  GLBX(glb_conj(A.ctx, Traits<T>::dtype, size, r, wdag));  // wdag = conj(r)  (a copy for real fields)
+  T delta = B.dot(wdag, r), delta_prev = delta;
+  T psi = B.dot(wdag, As) / delta;
+  double rsqNew = 0.0;
+  int k;
+  for (k = 0; k < max_iter; k++) {
+    beta_prev = beta;
+    beta = -1.0 / psi;
+    B.axpyz(beta, As, r, w);  // w = r + beta As
+    double AwAw = 0.0;
+    const T wAw = A.apply_dot_norm(Aw, w, w, &AwAw);  // <w, Aw>, |Aw|^2
+    chi = conj_of(wAw) / AwAw;                        // :521 dot(Aw, w)/norm2sq(Aw)
+    B.copy(r_prev, r);
+    B.axpyz(-chi, Aw, w, r);  // r = w - chi Aw
+    for (int n = 0; n < live; n++) {
+      const T z_old = zeta_s[n];
+      zeta_s[n] = (zeta_s[n] * zeta_prev[n] * beta_prev) /
+                  (beta * alpha * (zeta_prev[n] - zeta_s[n]) + zeta_prev[n] * beta_prev * (1.0 - shifts[n] * beta));
+      zeta_prev[n] = z_old;
+      beta_s[n] = beta * zeta_s[n] / zeta_prev[n];
+      chi_s[n] = chi / (1.0 + chi * shifts[n]);
+      const T rho_old = rho_s[n];
+      rho_s[n] = rho_s[n] / (1.0 + chi * shifts[n]);
+      rho_prev[n] = rho_old;
+      // x_n = x_n - beta_n s_n + (chi_n rho_n^prev zeta_n) w   (:552, left to right)
+      B.axpy(-beta_s[n], s_s[n], phi[n]);
+      B.axpy(chi_s[n] * rho_prev[n] * zeta_s[n], w, phi[n]);
+    }
+    rsqNew = B.norm2sq(r);
+    print_verbosity_resid(verb, "BICGSTAB-M", k + 1, A.ops, sqrt(rsqNew) / bsqrt);
+    if (k % check_every == 0) {
+      for (int n = 0; n < live; n++) {
+        if (std::abs(zeta_s[n] * rho_s[n]) * sqrt(rsqNew) < eps * bsqrt) {
+          live--;
+          if (live != n) {
+            std::swap(mapping[live], mapping[n]);
+            std::swap(phi[live], phi[n]);
+            std::swap(s_s[live], s_s[n]);
+            std::swap(alpha_s[live], alpha_s[n]);
+            std::swap(beta_s[live], beta_s[n]);
+            std::swap(zeta_s[live], zeta_s[n]);
+            std::swap(zeta_prev[live], zeta_prev[n]);
+            std::swap(chi_s[live], chi_s[n]);
+            std::swap(rho_s[live], rho_s[n]);
+            std::swap(rho_prev[live], rho_prev[n]);
+            std::swap(shifts[live], shifts[n]);
+            n--;
+          }
+        }
+      }
+    }
+    if ((worst_first && (std::abs(zeta_s[0] * rho_s[0]) * sqrt(rsqNew) < eps * bsqrt)) || is_nan_d(rsqNew) || live == 0 ||
+        k == max_iter - 1)
+      break;
+    delta_prev = delta;
+    delta = B.dot(wdag, r);
+    alpha = -beta * delta / (delta_prev * chi);
+    for (int n = 0; n < live; n++) alpha_s[n] = alpha * zeta_s[n] * beta_s[n] / (zeta_prev[n] * beta);
+    // s = r + alpha (s - chi As)
+    double ca[2], cc[2];
+    Traits<T>::pack(alpha, ca);
+    Traits<T>::pack(chi, cc);
+    GLBX(glb_bicgstab_pupdate(A.ctx, Traits<T>::dtype, size, r, ca, cc, As, s));
+    for (int n = 0; n < live; n++) {
+      if (std::abs(shifts[n]) != 0.0) {
+        // s_n = (zeta_n rho_n) r + alpha_n (s_n - (chi_n/beta_n) ((zeta_n rho_n^prev) w - (zeta_n^prev rho_n^prev) r_prev))
+        double c[10];
+        Traits<T>::pack(zeta_s[n] * rho_s[n], c);
+        Traits<T>::pack(alpha_s[n], c + 2);
+        Traits<T>::pack(chi_s[n] / beta_s[n], c + 4);
+        Traits<T>::pack(zeta_s[n] * rho_prev[n], c + 6);
+        Traits<T>::pack(zeta_prev[n] * rho_prev[n], c + 8);
+        GLBX(glb_bicgstabm_update_s(A.ctx, Traits<T>::dtype, size, c, r, w, r_prev, s_s[n]));
+      } else {
+        B.copy(s_s[n], s);
+      }
+    }
+    A.apply(As, s);
+    psi = B.dot(wdag, As) / delta;
+    if (std::abs(psi) == 0) {
+      breakdown = true;
+      break;
+    }
+  }
+  inf.success = !(k == max_iter - 1 || breakdown);
+  k++;
+  undo_shift_permutation(phi, shifts, mapping, n_shift);
+  std::vector<double> relres(n_shift);
+  for (int n = 0; n < n_shift; n++) {
+    A.apply(As, phi[n]);
+    B.axpy(T(shifts[n]), phi[n], As);
+    inf.resSqmrhs[n] = B.diffnorm2sq(As, b);
+    relres[n] = sqrt(inf.resSqmrhs[n]) / bsqrt;
+  }
+  inf.ops_count = A.ops;
+  print_verbosity_summary_multi(verb, "BICGSTAB-M", inf.success, k, inf.ops_count, relres.data(), n_shift);
+  inf.resSq = 0.0;
+  inf.iter = k;
+  inf.name = "BICGSTAB-M";
+  return inf;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------ 8f-4 exports
+#define GLB200_DEF_PRECOND_FAMILY(T)                                                                               \
+  inversion_info minv_vector_cg_precond_dev(T* phi, T* phi0, int size, int max_iter, double eps,                   \
+                                            void (*mv)(T*, T*, void*), void* extra,                                \
+                                            void (*pc)(T*, T*, int, void*, inversion_verbose_struct*), void* pci,  \
+                                            inversion_verbose_struct* verb) {                                      \
+    try {                                                                                                          \
+      return cg_precond_dev<T>(phi, phi0, size, max_iter, eps, mv, extra, pc, pci, verb);                          \
+    } catch (const std::exception& e) {                                                                            \
+      return failed("PCG", e);                                                                                     \
+    }                                                                                                              \
+  }                                                                                                                \
+  inversion_info minv_vector_cg_flex_precond_dev(T* phi, T* phi0, int size, int max_iter, double eps,              \
+                                                 void (*mv)(T*, T*, void*), void* extra,                           \
+                                                 void (*pc)(T*, T*, int, void*, inversion_verbose_struct*),        \
+                                                 void* pci, inversion_verbose_struct* verb) {                      \
+    try {                                                                                                          \
+      return cg_flex_precond_dev<T>(phi, phi0, size, max_iter, eps, mv, extra, pc, pci, verb);                     \
+    } catch (const std::exception& e) {                                                                            \
+      return failed("FPCG", e);                                                                                    \
+    }                                                                                                              \
+  }                                                                                                                \
+  inversion_info minv_vector_cg_flex_precond_restart_dev(T* phi, T* phi0, int size, int max_iter, double res,      \
+                                                         int rf, void (*mv)(T*, T*, void*), void* extra,           \
+                                                         void (*pc)(T*, T*, int, void*, inversion_verbose_struct*), \
+                                                         void* pci, inversion_verbose_struct* verb) {              \
+    try {                                                                                                          \
+      return cg_flex_precond_restart_dev<T>(phi, phi0, size, max_iter, res, rf, mv, extra, pc, pci, verb);         \
+    } catch (const std::exception& e) {                                                                            \
+      return failed("FPCG", e);                                                                                    \
+    }                                                                                                              \
+  }                                                                                                                \
+  inversion_info minv_vector_bicgstab_precond_dev(T* phi, T* phi0, int size, int max_iter, double eps,             \
+                                                  void (*mv)(T*, T*, void*), void* extra,                          \
+                                                  void (*pc)(T*, T*, int, void*, inversion_verbose_struct*),       \
+                                                  void* pci, inversion_verbose_struct* verb) {                     \
+    try {                                                                                                          \
+      return bicgstab_precond_dev<T>(phi, phi0, size, max_iter, eps, mv, extra, pc, pci, verb);                    \
+    } catch (const std::exception& e) {                                                                            \
+      return failed("Preconditioned BiCGStab", e);                                                                 \
+    }                                                                                                              \
+  }                                                                                                                \
+  inversion_info minv_vector_bicgstab_precond_restart_dev(T* phi, T* phi0, int size, int max_iter, double res,     \
+                                                          int rf, void (*mv)(T*, T*, void*), void* extra,          \
+                                                          void (*pc)(T*, T*, int, void*, inversion_verbose_struct*), \
+                                                          void* pci, inversion_verbose_struct* verb) {             \
+    try {                                                                                                          \
+      return restarted<T>(label("Preconditioned Restarted BiCGStab", rf), phi0, size, max_iter, res,               \
+                          ctx_of<T>(mv, extra), verb, false, [&](inversion_verbose_struct* v) {                    \
+                            return bicgstab_precond_dev<T>(phi, phi0, size, rf, res, mv, extra, pc, pci, v);       \
+                          });                                                                                      \
+    } catch (const std::exception& e) {                                                                            \
+      return failed("Preconditioned BiCGStab", e);                                                                 \
+    }                                                                                                              \
+  }                                                                                                                \
+  inversion_info minv_vector_cr_m_dev(T** phi, T* phi0, int n_shift, int size, int rfc, int max_iter, double eps,  \
+                                      double* shifts, void (*mv)(T*, T*, void*), void* extra, bool worst_first,    \
+                                      inversion_verbose_struct* verb) {                                            \
+    try {                                                                                                          \
+      return cr_m_dev<T>(phi, phi0, n_shift, size, rfc, max_iter, eps, shifts, mv, extra, worst_first, verb);      \
+    } catch (const std::exception& e) {                                                                            \
+      return failed("CR-M", e);                                                                                    \
+    }                                                                                                              \
+  }                                                                                                                \
+  inversion_info minv_vector_bicgstab_m_dev(T** phi, T* phi0, int n_shift, int size, int rfc, int max_iter,        \
+                                            double eps, double* shifts, void (*mv)(T*, T*, void*), void* extra,    \
+                                            bool worst_first, inversion_verbose_struct* verb) {                    \
+    try {                                                                                                          \
+      return bicgstab_m_dev<T>(phi, phi0, n_shift, size, rfc, max_iter, eps, shifts, mv, extra, worst_first, verb); \
+    } catch (const std::exception& e) {                                                                            \
+      return failed("BICGSTAB-M", e);                                                                              \
+    }                                                                                                              \
+  }                                                                                                                \
+  void identity_preconditioner_dev(T* lhs, T* rhs, int size, void*, inversion_verbose_struct*) {                   \
+    glb_vec_copy(glb200_default_context(), Traits<T>::dtype, size, lhs, rhs);                                      \
+  }
+GLB200_DEF_PRECOND_FAMILY(double)
+GLB200_DEF_PRECOND_FAMILY(zcplx)
+
+// generic_precond.cpp:62-77 : n_step GCR iterations on the operator named by the struct
+void gcr_preconditioner_dev(double* lhs, double* rhs, int size, void* extra_data, inversion_verbose_struct* verb) {
+  gcr_precond_struct_real* g = (gcr_precond_struct_real*)extra_data;
+  minv_vector_gcr_dev(lhs, rhs, size, g->n_step, g->rel_res, g->matrix_vector, g->matrix_extra_data, verb);
+}
+void gcr_preconditioner_dev(zcplx* lhs, zcplx* rhs, int size, void* extra_data, inversion_verbose_struct* verb) {
+  gcr_precond_struct_complex* g = (gcr_precond_struct_complex*)extra_data;
+  minv_vector_gcr_dev(lhs, rhs, size, g->n_step, g->rel_res, g->matrix_vector, g->matrix_extra_data, verb);
+}
+
+// generic_inverter_precond.cpp:18-114
+template <typename T>
+static inversion_info dispatch_precond_dev(T* lhs, T* rhs, int size, minv_inverter_precond type,
+                                           minv_inverter_precond_params& p, void (*mv)(T*, T*, void*), void* extra,
+                                           void (*pc)(T*, T*, int, void*, inversion_verbose_struct*), void* pci,
+                                           inversion_verbose_struct* verb) {
+  switch (type) {
+    case MINV_PRE_CG:  // there is no restarted preconditioned CG (generic_inverter_precond.cpp:22)
+      return minv_vector_cg_precond_dev(lhs, rhs, size, p.max_iters, p.tol, mv, extra, pc, pci, verb);
+    case MINV_PRE_FPCG:
+      return p.restart ? minv_vector_cg_flex_precond_restart_dev(lhs, rhs, size, p.max_iters, p.tol, p.restart_freq, mv,
+                                                                 extra, pc, pci, verb)
+                       : minv_vector_cg_flex_precond_dev(lhs, rhs, size, p.max_iters, p.tol, mv, extra, pc, pci, verb);
+    case MINV_PRE_VPGCR:
+      return p.restart ? minv_vector_gcr_var_precond_restart_dev(lhs, rhs, size, p.max_iters, p.tol, p.restart_freq, mv,
+                                                                 extra, pc, pci, verb)
+                       : minv_vector_gcr_var_precond_dev(lhs, rhs, size, p.max_iters, p.tol, mv, extra, pc, pci, verb);
+    case MINV_PRE_BICGSTAB:
+      return p.restart ? minv_vector_bicgstab_precond_restart_dev(lhs, rhs, size, p.max_iters, p.tol, p.restart_freq,
+                                                                  mv, extra, pc, pci, verb)
+                       : minv_vector_bicgstab_precond_dev(lhs, rhs, size, p.max_iters, p.tol, mv, extra, pc, pci, verb);
+    default:
+      return inversion_info();
+  }
+}
+inversion_info minv_preconditioned_dev(double* lhs, double* rhs, int size, minv_inverter_precond type,
+                                       minv_inverter_precond_params& p, void (*mv)(double*, double*, void*), void* extra,
+                                       void (*pc)(double*, double*, int, void*, inversion_verbose_struct*), void* pci,
+                                       inversion_verbose_struct* verb) {
+  return dispatch_precond_dev<double>(lhs, rhs, size, type, p, mv, extra, pc, pci, verb);
+}
+inversion_info minv_preconditioned_dev(zcplx* lhs, zcplx* rhs, int size, minv_inverter_precond type,
+                                       minv_inverter_precond_params& p, void (*mv)(zcplx*, zcplx*, void*), void* extra,
+                                       void (*pc)(zcplx*, zcplx*, int, void*, inversion_verbose_struct*), void* pci,
+                                       inversion_verbose_struct* verb) {
+  return dispatch_precond_dev<zcplx>(lhs, rhs, size, type, p, mv, extra, pc, pci, verb);
+}

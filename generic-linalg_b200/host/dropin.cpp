@@ -13,6 +13,7 @@
 
 #include "coarse_stencil.h"
 #include "dev_internal.hpp"
+#include "generic_inverters_precond.h"
 #include "operators.h"
 #include "operators_stencil.h"
 
@@ -400,9 +401,14 @@ GLB200_HOST_BICGL(zcplx)
 // multishift: phi[] are n_shift host vectors; the device copies are permuted by the solver exactly
 // like the reference permutes the caller's pointers, and restored before download.
 template <typename T>
-static inversion_info cg_m_host(T** phi, T* phi0, int n_shift, int size, int rfc, int max_iter, double eps,
-                                double* shifts, void (*mv)(T*, T*, void*), void* extra, bool worst_first,
-                                inversion_verbose_struct* verb) {
+struct MultiDev {  // signature shared by minv_vector_{cg,cr,bicgstab}_m_dev
+  typedef inversion_info (*fn)(T**, T*, int, int, int, int, double, double*, void (*)(T*, T*, void*), void*, bool,
+                               inversion_verbose_struct*);
+};
+template <typename T>
+static inversion_info multi_host(const char* alg, typename MultiDev<T>::fn dev, T** phi, T* phi0, int n_shift, int size,
+                                 int rfc, int max_iter, double eps, double* shifts, void (*mv)(T*, T*, void*),
+                                 void* extra, bool worst_first, inversion_verbose_struct* verb) {
   try {
     glb_context* ctx = glb200_default_context();
     const Builtin kind = classify(mv);
@@ -416,16 +422,191 @@ static inversion_info cg_m_host(T** phi, T* phi0, int n_shift, int size, int rfc
     for (int s = 0; s < n_shift; s++) d_phi[s] = W.get();
     GLBX(glb_vec_upload(ctx, Traits<T>::dtype, size, d_b, phi0));
     void (*cb)(T*, T*, void*) = &glb200_apply_dev;
-    inversion_info inf = minv_vector_cg_m_dev(d_phi.data(), d_b, n_shift, size, rfc, max_iter, eps, shifts, cb,
-                                              (void*)L.op, worst_first, verb);
+    inversion_info inf = dev(d_phi.data(), d_b, n_shift, size, rfc, max_iter, eps, shifts, cb, (void*)L.op, worst_first,
+                             verb);
     for (int s = 0; s < n_shift; s++) GLBX(glb_vec_download(ctx, Traits<T>::dtype, size, phi[s], d_phi[s]));
     return inf;
   } catch (const std::exception& e) {
-    std::cerr << "[glb200] CG-M aborted: " << e.what() << std::endl;
+    std::cerr << "[glb200] " << alg << " aborted: " << e.what() << std::endl;
     inversion_info inf;
-    inf.name = "CG-M";
+    inf.name = alg;
     return inf;
   }
+}
+template <typename T>
+static inversion_info cg_m_host(T** phi, T* phi0, int n_shift, int size, int rfc, int max_iter, double eps,
+                                double* shifts, void (*mv)(T*, T*, void*), void* extra, bool worst_first,
+                                inversion_verbose_struct* verb) {
+  typename MultiDev<T>::fn dev = &minv_vector_cg_m_dev;
+  return multi_host<T>("CG-M", dev, phi, phi0, n_shift, size, rfc, max_iter, eps, shifts, mv, extra, worst_first, verb);
+}
+#define GLB200_HOST_MULTI(T)                                                                                        \
+  inversion_info minv_vector_cr_m(T** phi, T* phi0, int n_shift, int size, int rfc, int max_iter, double eps,       \
+                                  double* shifts, void (*mv)(T*, T*, void*), void* extra, bool worst_first,         \
+                                  inversion_verbose_struct* verb) {                                                 \
+    MultiDev<T>::fn dev = &minv_vector_cr_m_dev;                                                                    \
+    return multi_host<T>("CR-M", dev, phi, phi0, n_shift, size, rfc, max_iter, eps, shifts, mv, extra, worst_first, \
+                         verb);                                                                                     \
+  }                                                                                                                 \
+  inversion_info minv_vector_bicgstab_m(T** phi, T* phi0, int n_shift, int size, int rfc, int max_iter, double eps, \
+                                        double* shifts, void (*mv)(T*, T*, void*), void* extra, bool worst_first,   \
+                                        inversion_verbose_struct* verb) {                                           \
+    MultiDev<T>::fn dev = &minv_vector_bicgstab_m_dev;                                                              \
+    return multi_host<T>("BICGSTAB-M", dev, phi, phi0, n_shift, size, rfc, max_iter, eps, shifts, mv, extra,        \
+                         worst_first, verb);                                                                        \
+  }
+GLB200_HOST_MULTI(double)
+GLB200_HOST_MULTI(zcplx)
+
+// ------------------------------------------------------------------------------------------ preconditioned family
+// A host preconditioner callback is mapped to its device form: the stock ones of generic_precond.h are
+// recognised (identity_preconditioner; gcr_preconditioner on a known operator); anything else is an error
+// unless the parity shim is on (download -> host callback -> upload around every application).
+template <typename T>
+struct GcrStruct;
+template <>
+struct GcrStruct<double> {
+  typedef gcr_precond_struct_real type;
+};
+template <>
+struct GcrStruct<zcplx> {
+  typedef gcr_precond_struct_complex type;
+};
+template <typename T>
+struct PrecondShim {
+  void (*fn)(T*, T*, int, void*, inversion_verbose_struct*);
+  void* extra;
+  std::vector<T> in, out;
+};
+template <typename T>
+void precond_shim_cb(T* d_lhs, T* d_rhs, int size, void* e, inversion_verbose_struct* verb) {
+  PrecondShim<T>* s = (PrecondShim<T>*)e;
+  glb_context* ctx = glb200_default_context();
+  s->in.resize(size);
+  s->out.resize(size);
+  GLBX(glb_vec_download(ctx, Traits<T>::dtype, size, s->in.data(), d_rhs));
+  GLBX(glb_vec_download(ctx, Traits<T>::dtype, size, s->out.data(), d_lhs));
+  s->fn(s->out.data(), s->in.data(), size, s->extra, verb);
+  GLBX(glb_vec_upload(ctx, Traits<T>::dtype, size, d_lhs, s->out.data()));
+}
+template <typename T>
+struct PrecondMap {
+  typedef void (*pfn)(T*, T*, int, void*, inversion_verbose_struct*);
+  pfn dev;
+  void* info;
+  OpLease L;
+  typename GcrStruct<T>::type gcr;
+  PrecondShim<T> shim;
+  PrecondMap(pfn host, void* host_info) : dev(0), info(0) {
+    pfn ident = &identity_preconditioner;
+    pfn gcrp = &gcr_preconditioner;
+    if (host == ident) {
+      dev = &identity_preconditioner_dev;
+    } else if (host == gcrp) {
+      typename GcrStruct<T>::type* g = (typename GcrStruct<T>::type*)host_info;
+      const Builtin kind = classify(g->matrix_vector);
+      if (kind == B_NONE) throw Error("gcr_preconditioner: its operator callback is not a known device operator");
+      lease(kind, g->matrix_extra_data, &L);
+      gcr.n_step = g->n_step;
+      gcr.rel_res = g->rel_res;
+      gcr.matrix_vector = &glb200_apply_dev;
+      gcr.matrix_extra_data = L.op;
+      dev = &gcr_preconditioner_dev;
+      info = &gcr;
+    } else if (g_allow_shim) {
+      shim.fn = host;
+      shim.extra = host_info;
+      dev = &precond_shim_cb<T>;
+      info = &shim;
+    } else {
+      throw Error("preconditioner callback is not one of generic_precond.h (identity_preconditioner, gcr_preconditioner); "
+                  "use the _dev entry points with a device preconditioner");
+    }
+  }
+};
+
+#define GLB200_HOST_PRECOND(T, NAME, DEVNAME, ALG)                                                                  \
+  inversion_info NAME(T* phi, T* phi0, int size, int max_iter, double eps, void (*mv)(T*, T*, void*), void* extra,  \
+                      void (*pc)(T*, T*, int, void*, inversion_verbose_struct*), void* pci,                         \
+                      inversion_verbose_struct* verb) {                                                             \
+    return host_solve<T>(ALG, phi, phi0, size, mv, extra, [&](T* dp, T* db, void (*cb)(T*, T*, void*), void* ce) {  \
+      PrecondMap<T> pm(pc, pci);                                                                                    \
+      return DEVNAME(dp, db, size, max_iter, eps, cb, ce, pm.dev, pm.info, verb);                                   \
+    });                                                                                                             \
+  }
+#define GLB200_HOST_PRECOND_RESTART(T, NAME, DEVNAME, ALG)                                                          \
+  inversion_info NAME(T* phi, T* phi0, int size, int max_iter, double res, int rf, void (*mv)(T*, T*, void*),       \
+                      void* extra, void (*pc)(T*, T*, int, void*, inversion_verbose_struct*), void* pci,            \
+                      inversion_verbose_struct* verb) {                                                             \
+    return host_solve<T>(ALG, phi, phi0, size, mv, extra, [&](T* dp, T* db, void (*cb)(T*, T*, void*), void* ce) {  \
+      PrecondMap<T> pm(pc, pci);                                                                                    \
+      return DEVNAME(dp, db, size, max_iter, res, rf, cb, ce, pm.dev, pm.info, verb);                               \
+    });                                                                                                             \
+  }
+#define GLB200_HOST_PRECOND_ALL(T)                                                                                  \
+  GLB200_HOST_PRECOND(T, minv_vector_cg_precond, minv_vector_cg_precond_dev, "PCG")                                 \
+  GLB200_HOST_PRECOND(T, minv_vector_cg_flex_precond, minv_vector_cg_flex_precond_dev, "FPCG")                      \
+  GLB200_HOST_PRECOND_RESTART(T, minv_vector_cg_flex_precond_restart, minv_vector_cg_flex_precond_restart_dev, "FPCG") \
+  GLB200_HOST_PRECOND(T, minv_vector_gcr_var_precond, minv_vector_gcr_var_precond_dev, "VPGCR")                     \
+  GLB200_HOST_PRECOND_RESTART(T, minv_vector_gcr_var_precond_restart, minv_vector_gcr_var_precond_restart_dev, "VPGCR") \
+  GLB200_HOST_PRECOND(T, minv_vector_bicgstab_precond, minv_vector_bicgstab_precond_dev, "Preconditioned BiCGStab") \
+  GLB200_HOST_PRECOND_RESTART(T, minv_vector_bicgstab_precond_restart, minv_vector_bicgstab_precond_restart_dev,    \
+                              "Preconditioned BiCGStab")
+GLB200_HOST_PRECOND_ALL(double)
+GLB200_HOST_PRECOND_ALL(zcplx)
+
+// the stock preconditioners called directly with host vectors (generic_precond.cpp:23-77)
+void identity_preconditioner(double* lhs, double* rhs, int size, void*, inversion_verbose_struct*) {
+  std::memcpy(lhs, rhs, sizeof(double) * (size_t)size);
+}
+void identity_preconditioner(zcplx* lhs, zcplx* rhs, int size, void*, inversion_verbose_struct*) {
+  std::memcpy((void*)lhs, (const void*)rhs, sizeof(zcplx) * (size_t)size);
+}
+void gcr_preconditioner(double* lhs, double* rhs, int size, void* extra_data, inversion_verbose_struct* verb) {
+  gcr_precond_struct_real* g = (gcr_precond_struct_real*)extra_data;
+  minv_vector_gcr(lhs, rhs, size, g->n_step, g->rel_res, g->matrix_vector, g->matrix_extra_data, verb);
+}
+void gcr_preconditioner(zcplx* lhs, zcplx* rhs, int size, void* extra_data, inversion_verbose_struct* verb) {
+  gcr_precond_struct_complex* g = (gcr_precond_struct_complex*)extra_data;
+  minv_vector_gcr(lhs, rhs, size, g->n_step, g->rel_res, g->matrix_vector, g->matrix_extra_data, verb);
+}
+
+// generic_inverter_precond.cpp:18-114
+template <typename T>
+static inversion_info dispatch_precond(T* lhs, T* rhs, int size, minv_inverter_precond type,
+                                       minv_inverter_precond_params& p, void (*mv)(T*, T*, void*), void* extra,
+                                       void (*pc)(T*, T*, int, void*, inversion_verbose_struct*), void* pci,
+                                       inversion_verbose_struct* verb) {
+  switch (type) {
+    case MINV_PRE_CG:
+      return minv_vector_cg_precond(lhs, rhs, size, p.max_iters, p.tol, mv, extra, pc, pci, verb);
+    case MINV_PRE_FPCG:
+      return p.restart ? minv_vector_cg_flex_precond_restart(lhs, rhs, size, p.max_iters, p.tol, p.restart_freq, mv, extra,
+                                                             pc, pci, verb)
+                       : minv_vector_cg_flex_precond(lhs, rhs, size, p.max_iters, p.tol, mv, extra, pc, pci, verb);
+    case MINV_PRE_VPGCR:
+      return p.restart ? minv_vector_gcr_var_precond_restart(lhs, rhs, size, p.max_iters, p.tol, p.restart_freq, mv, extra,
+                                                             pc, pci, verb)
+                       : minv_vector_gcr_var_precond(lhs, rhs, size, p.max_iters, p.tol, mv, extra, pc, pci, verb);
+    case MINV_PRE_BICGSTAB:
+      return p.restart ? minv_vector_bicgstab_precond_restart(lhs, rhs, size, p.max_iters, p.tol, p.restart_freq, mv,
+                                                              extra, pc, pci, verb)
+                       : minv_vector_bicgstab_precond(lhs, rhs, size, p.max_iters, p.tol, mv, extra, pc, pci, verb);
+    default:
+      return inversion_info();
+  }
+}
+inversion_info minv_preconditioned(double* lhs, double* rhs, int size, minv_inverter_precond type,
+                                   minv_inverter_precond_params& p, void (*mv)(double*, double*, void*), void* extra,
+                                   void (*pc)(double*, double*, int, void*, inversion_verbose_struct*), void* pci,
+                                   inversion_verbose_struct* verb) {
+  return dispatch_precond<double>(lhs, rhs, size, type, p, mv, extra, pc, pci, verb);
+}
+inversion_info minv_preconditioned(zcplx* lhs, zcplx* rhs, int size, minv_inverter_precond type,
+                                   minv_inverter_precond_params& p, void (*mv)(zcplx*, zcplx*, void*), void* extra,
+                                   void (*pc)(zcplx*, zcplx*, int, void*, inversion_verbose_struct*), void* pci,
+                                   inversion_verbose_struct* verb) {
+  return dispatch_precond<zcplx>(lhs, rhs, size, type, p, mv, extra, pc, pci, verb);
 }
 inversion_info minv_vector_cg_m(double** phi, double* phi0, int n_shift, int size, int rfc, int max_iter, double eps,
                                 double* shifts, void (*mv)(double*, double*, void*), void* extra, bool worst_first,

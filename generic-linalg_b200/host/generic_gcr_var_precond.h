@@ -1,0 +1,6 @@
+// generic_gcr_var_precond.h -- kept so that `#include "generic_gcr_var_precond.h"` in code written against the reference still
+// compiles; every prototype lives in generic_inverters_precond.h.
+#ifndef GLB200_FWD_generic_gcr_var_precond_H
+#define GLB200_FWD_generic_gcr_var_precond_H
+#include "generic_inverters_precond.h"
+#endif

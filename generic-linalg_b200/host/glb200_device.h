@@ -13,6 +13,7 @@
 #include <complex>
 
 #include "generic_inverters.h"
+#include "generic_inverters_precond.h"
 #include "glb200.h"
 
 // Process-wide context used by the host-pointer entry points and by direct operator calls.
@@ -104,6 +105,44 @@ inversion_info minv_vector_cg_m_dev(std::complex<double>** d_phi, std::complex<d
       inversion_verbose_struct* verbosity = 0);
 GLB200_DECL_VPGCR(double)
 GLB200_DECL_VPGCR(std::complex<double>)
+
+// The rest of the preconditioned family and the multishift CR / BiCGStab on device vectors
+// (generic_cg_precond.h, generic_cg_flex_precond.h, generic_bicgstab_precond.h, generic_cr_m.h, generic_bicgstab_m.h)
+#define GLB200_DEV_PRECOND_ARGS(T)                                                                                  \
+  void (*matrix_vector_dev)(T*, T*, void*), void* extra_info,                                                       \
+      void (*precond_matrix_vector_dev)(T*, T*, int, void*, inversion_verbose_struct*), void* precond_info,         \
+      inversion_verbose_struct* verbosity = 0
+#define GLB200_DECL_DEV_PRECOND(T)                                                                                  \
+  inversion_info minv_vector_cg_precond_dev(T* d_phi, T* d_phi0, int size, int max_iter, double eps,                \
+                                            GLB200_DEV_PRECOND_ARGS(T));                                            \
+  inversion_info minv_vector_cg_flex_precond_dev(T* d_phi, T* d_phi0, int size, int max_iter, double eps,           \
+                                                 GLB200_DEV_PRECOND_ARGS(T));                                       \
+  inversion_info minv_vector_cg_flex_precond_restart_dev(T* d_phi, T* d_phi0, int size, int max_iter, double res,   \
+                                                         int restart_freq, GLB200_DEV_PRECOND_ARGS(T));             \
+  inversion_info minv_vector_bicgstab_precond_dev(T* d_phi, T* d_phi0, int size, int max_iter, double eps,          \
+                                                  GLB200_DEV_PRECOND_ARGS(T));                                      \
+  inversion_info minv_vector_bicgstab_precond_restart_dev(T* d_phi, T* d_phi0, int size, int max_iter, double res,  \
+                                                          int restart_freq, GLB200_DEV_PRECOND_ARGS(T));            \
+  inversion_info minv_vector_cr_m_dev(T** d_phi, T* d_phi0, int n_shift, int size, int resid_freq_check, int max_iter, \
+                                      double eps, double* shifts, void (*matrix_vector_dev)(T*, T*, void*),         \
+                                      void* extra_info, bool worst_first = false,                                   \
+                                      inversion_verbose_struct* verbosity = 0);                                     \
+  inversion_info minv_vector_bicgstab_m_dev(T** d_phi, T* d_phi0, int n_shift, int size, int resid_freq_check,      \
+                                            int max_iter, double eps, double* shifts,                               \
+                                            void (*matrix_vector_dev)(T*, T*, void*), void* extra_info,             \
+                                            bool worst_first = false, inversion_verbose_struct* verbosity = 0);     \
+  /* generic_precond.cpp:23-77 on device vectors: lhs = rhs; n_step GCR iterations on gps->matrix_vector (a device   \
+     callback with its extra_info) from the lhs handed in */                                                        \
+  void identity_preconditioner_dev(T* d_lhs, T* d_rhs, int size, void* extra_data, inversion_verbose_struct* verb = 0); \
+  void gcr_preconditioner_dev(T* d_lhs, T* d_rhs, int size, void* extra_data, inversion_verbose_struct* verb = 0);
+GLB200_DECL_DEV_PRECOND(double)
+GLB200_DECL_DEV_PRECOND(std::complex<double>)
+
+inversion_info minv_preconditioned_dev(double* d_lhs, double* d_rhs, int size, minv_inverter_precond type,
+                                       minv_inverter_precond_params& params, GLB200_DEV_PRECOND_ARGS(double));
+inversion_info minv_preconditioned_dev(std::complex<double>* d_lhs, std::complex<double>* d_rhs, int size,
+                                       minv_inverter_precond type, minv_inverter_precond_params& params,
+                                       GLB200_DEV_PRECOND_ARGS(std::complex<double>));
 
 // minv_unpreconditioned (generic_inverters.h:109-111) on device vectors
 inversion_info minv_unpreconditioned_dev(double* d_lhs, double* d_rhs, int size, minv_inverter type,

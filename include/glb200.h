@@ -194,6 +194,12 @@ int glb_bicgstab_update(glb_context* ctx, int dtype, size_t n, const double alph
 /* p = r + beta*(p - omega*Ap)   (generic_bicgstab.cpp:300-303) */
 int glb_bicgstab_pupdate(glb_context* ctx, int dtype, size_t n, const void* r, const double beta[2],
                          const double omega[2], const void* Ap, void* p);
+/* out = conj(x) (complex) / out = x (real)   (generic_vector.h conj<>; generic_bicgstab_m.cpp:494) */
+int glb_conj(glb_context* ctx, int dtype, size_t n, const void* x, void* out);
+/* multishift BiCGStab, one shift: s_n = c0*r + c1*(s_n - c2*(c3*w - c4*r_prev)) with c = {c0..c4} complex pairs
+ * (generic_bicgstab_m.cpp:705: c0 = zeta rho, c1 = alpha_n, c2 = chi_n/beta_n, c3 = zeta rho_prev, c4 = zeta_prev rho_prev) */
+int glb_bicgstabm_update_s(glb_context* ctx, int dtype, size_t n, const double c[10], const void* r, const void* w,
+                           const void* r_prev, void* s_n);
 /* multishift: for s < ns : x[s] = x[s] - beta_s[s]*p_s[s]   (generic_cg_m.cpp:414-417) */
 int glb_cgm_update_x(glb_context* ctx, int dtype, size_t n, int ns, const double* beta_s, const void* const* p_s,
                      void* const* x);

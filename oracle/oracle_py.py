@@ -282,6 +282,44 @@ class RefMg:
         return x, dict(resSq=out[0], iter=int(out[1]), success=bool(out[2]), ops_count=int(out[3]))
 
 
+MULTI = dict(CG_M=0, CR_M=1, BICGSTAB_M=2)
+PRECOND_SOLVER = dict(PCG=0, FPCG=1, FPCG_RESTART=2, VPGCR=3, VPGCR_RESTART=4, PBICGSTAB=5, PBICGSTAB_RESTART=6)
+PRECOND = dict(IDENTITY=0, GCR=1)
+
+
+def ref_solve_multi(orc, which, op, b, shifts, resid_freq_check=10, max_iter=10000, eps=1e-10, worst_first=False):
+    """minv_vector_{cg,cr,bicgstab}_m of the reference (`ref` library only)"""
+    f = orc.lib.ref_solve_multi
+    f.restype = C.c_int
+    f.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double,
+                  C.c_void_p, C.c_int, C.c_int, C.POINTER(Result)]
+    b = np.ascontiguousarray(b, dtype=op.dtype)
+    shifts = np.array(shifts, dtype=np.float64, copy=True)
+    n = len(shifts)
+    xs = [np.zeros_like(b) for _ in range(n)]
+    ptrs = (C.c_void_p * n)(*[x.ctypes.data for x in xs])
+    res = Result()
+    f(MULTI[which], op.h, ptrs, _ptr(b), n, resid_freq_check, max_iter, eps, _ptr(shifts), int(worst_first), 0,
+      C.byref(res))
+    by_addr = {x.ctypes.data: x for x in xs}
+    return [by_addr[ptrs[i]] for i in range(n)], res.as_dict(), shifts
+
+
+def ref_solve_precond(orc, solver, op, b, x0=None, max_iter=10000, eps=1e-10, restart_freq=0, precond="IDENTITY",
+                      n_step=4, rel_res=1e-20):
+    """the reference's preconditioned family with its stock preconditioners (`ref` library only)"""
+    f = orc.lib.ref_solve_precond
+    f.restype = C.c_int
+    f.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
+                  C.c_double, C.c_int, C.POINTER(Result)]
+    b = np.ascontiguousarray(b, dtype=op.dtype)
+    x = np.zeros_like(b) if x0 is None else np.array(x0, dtype=op.dtype, copy=True)
+    res = Result()
+    f(PRECOND_SOLVER[solver], op.h, _ptr(x), _ptr(b), max_iter, eps, restart_freq, PRECOND[precond], n_step, rel_res, 0,
+      C.byref(res))
+    return x, res.as_dict()
+
+
 def available():
     out = []
     if os.path.exists(os.path.join(HERE, "_ref", "libref_oracle.so")):

@@ -20,6 +20,9 @@
 // Reference headers (include paths supplied by the Makefile).
 #include "generic_inverters.h"
 #include "generic_cg_m.h"
+#include "generic_cr_m.h"
+#include "generic_bicgstab_m.h"
+#include "generic_inverters_precond.h"
 #include "generic_vector.h"
 #include "u1_utils.h"
 #include "operators.h"
@@ -263,6 +266,76 @@ int ref_solve_cg_m(void* opv, double** phi, const double* phi0, int n_shift, int
                                            shifts, cb_r, opv, worst_first != 0, &verb);
     fill_result(info, out);
   }
+  return 0;
+}
+
+
+// ---- SURVEY 8f-4 (reference library only, no port): multishift CR / BiCGStab and the preconditioned family
+// which: 0 minv_vector_cg_m, 1 minv_vector_cr_m (generic_cr_m.cpp:24,323), 2 minv_vector_bicgstab_m (generic_bicgstab_m.cpp:26,402)
+int ref_solve_multi(int which, void* opv, double** phi, const double* phi0, int n_shift, int resid_freq_check,
+                    int max_iter, double eps, double* shifts, int worst_first, int verbosity, orc_result* out) {
+  RefOp* op = (RefOp*)opv;
+  inversion_verbose_struct verb;
+  make_verb(verbosity, &verb);
+  inversion_info info(n_shift);
+  if (op->is_complex) {
+    cplx** p = (cplx**)phi;
+    cplx* b = (cplx*)phi0;
+    if (which == 0) info = minv_vector_cg_m(p, b, n_shift, op->size, resid_freq_check, max_iter, eps, shifts, cb_c, opv, worst_first != 0, &verb);
+    if (which == 1) info = minv_vector_cr_m(p, b, n_shift, op->size, resid_freq_check, max_iter, eps, shifts, cb_c, opv, worst_first != 0, &verb);
+    if (which == 2) info = minv_vector_bicgstab_m(p, b, n_shift, op->size, resid_freq_check, max_iter, eps, shifts, cb_c, opv, worst_first != 0, &verb);
+  } else {
+    double* b = (double*)phi0;
+    if (which == 0) info = minv_vector_cg_m(phi, b, n_shift, op->size, resid_freq_check, max_iter, eps, shifts, cb_r, opv, worst_first != 0, &verb);
+    if (which == 1) info = minv_vector_cr_m(phi, b, n_shift, op->size, resid_freq_check, max_iter, eps, shifts, cb_r, opv, worst_first != 0, &verb);
+    if (which == 2) info = minv_vector_bicgstab_m(phi, b, n_shift, op->size, resid_freq_check, max_iter, eps, shifts, cb_r, opv, worst_first != 0, &verb);
+  }
+  fill_result(info, out);
+  return 0;
+}
+
+}  // extern "C"
+
+// solver: 0 PCG, 1 FPCG, 2 FPCG restart, 3 VPGCR, 4 VPGCR restart, 5 PBiCGStab, 6 PBiCGStab restart
+// precond: 0 identity_preconditioner, 1 gcr_preconditioner (n_step iterations to rel_res on the same operator)
+template <typename T, typename G>
+static inversion_info run_precond(int solver, T* phi, T* b, int size, int max_iter, double eps, int rf,
+                                  void (*cb)(T*, T*, void*), void* opv, int precond, int n_step, double rel_res,
+                                  inversion_verbose_struct* verb) {
+  G g;
+  g.n_step = n_step;
+  g.rel_res = rel_res;
+  g.matrix_vector = cb;
+  g.matrix_extra_data = opv;
+  typedef void (*pfn)(T*, T*, int, void*, inversion_verbose_struct*);
+  pfn pc_gcr = &gcr_preconditioner, pc_id = &identity_preconditioner;
+  pfn pc = (precond == 1) ? pc_gcr : pc_id;
+  void* pci = (precond == 1) ? (void*)&g : 0;
+  switch (solver) {
+    case 0: return minv_vector_cg_precond(phi, b, size, max_iter, eps, cb, opv, pc, pci, verb);
+    case 1: return minv_vector_cg_flex_precond(phi, b, size, max_iter, eps, cb, opv, pc, pci, verb);
+    case 2: return minv_vector_cg_flex_precond_restart(phi, b, size, max_iter, eps, rf, cb, opv, pc, pci, verb);
+    case 3: return minv_vector_gcr_var_precond(phi, b, size, max_iter, eps, cb, opv, pc, pci, verb);
+    case 4: return minv_vector_gcr_var_precond_restart(phi, b, size, max_iter, eps, rf, cb, opv, pc, pci, verb);
+    case 5: return minv_vector_bicgstab_precond(phi, b, size, max_iter, eps, cb, opv, pc, pci, verb);
+    case 6: return minv_vector_bicgstab_precond_restart(phi, b, size, max_iter, eps, rf, cb, opv, pc, pci, verb);
+  }
+  return inversion_info();
+}
+extern "C" {
+int ref_solve_precond(int solver, void* opv, double* phi, const double* phi0, int max_iter, double eps, int restart_freq,
+                      int precond, int n_step, double rel_res, int verbosity, orc_result* out) {
+  RefOp* op = (RefOp*)opv;
+  inversion_verbose_struct verb;
+  make_verb(verbosity, &verb);
+  inversion_info info;
+  if (op->is_complex)
+    info = run_precond<cplx, gcr_precond_struct_complex>(solver, (cplx*)phi, (cplx*)phi0, op->size, max_iter, eps,
+                                                        restart_freq, cb_c, opv, precond, n_step, rel_res, &verb);
+  else
+    info = run_precond<double, gcr_precond_struct_real>(solver, phi, (double*)phi0, op->size, max_iter, eps, restart_freq,
+                                                       cb_r, opv, precond, n_step, rel_res, &verb);
+  fill_result(info, out);
   return 0;
 }
 

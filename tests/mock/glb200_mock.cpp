@@ -248,6 +248,23 @@ int glb_bicgstab_pupdate(glb_context*, int dt, size_t n, const void* r, const do
   });
   return GLB_OK;
 }
+int glb_conj(glb_context*, int dt, size_t n, const void* x, void* out) {
+  if (dt == GLB_COMPLEX) {
+    for (size_t i = 0; i < n; i++) ((cplx*)out)[i] = std::conj(((const cplx*)x)[i]);
+  } else {
+    for (size_t i = 0; i < n; i++) ((double*)out)[i] = ((const double*)x)[i];
+  }
+  return GLB_OK;
+}
+int glb_bicgstabm_update_s(glb_context*, int dt, size_t n, const double c[10], const void* r, const void* w,
+                           const void* rp, void* sn) {
+  BOTH(dt, {
+    const T c0 = cf<T>(c); const T c1 = cf<T>(c + 2); const T c2 = cf<T>(c + 4); const T c3 = cf<T>(c + 6); const T c4 = cf<T>(c + 8);
+    for (size_t i = 0; i < n; i++)
+      ((T*)sn)[i] = c0 * ((const T*)r)[i] + c1 * (((T*)sn)[i] - c2 * (c3 * ((const T*)w)[i] - c4 * ((const T*)rp)[i]));
+  });
+  return GLB_OK;
+}
 int glb_cgm_update_x(glb_context*, int dt, size_t n, int ns, const double* beta_s, const void* const* p_s, void* const* x) {
   BOTH(dt, {
     for (int s = 0; s < ns; s++) {
