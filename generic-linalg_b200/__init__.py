@@ -19,11 +19,13 @@ LIB_HOST = os.path.join(HERE, "libglb200_inverters.so")
 
 REAL, COMPLEX = 0, 1
 STAG_DAGGER, STAG_GAMMA5, STAG_NORMAL = 1, 2, 4
+STAG_DEO, STAG_DOE, STAG_M2MDEODOE = 8, 16, 32   # even/odd pieces (operators.cpp:456-571)
 
 # operator / solver selectors of host/capi_solvers.cpp (same numbering as oracle/oracle_api.h)
 OP = dict(LAPLACE_REAL=0, LAPLACE_IMAG=1, LAPLACE_NC=2, LAPLACE_U1=3, STAG_FREE=4, STAG_U1=5,
           STAG_GAMMA5_U1=6, STAG_DAGGER_U1=7, STAG_NORMAL_U1=8, GAMMA5=9, STENCIL=10,
-          STENCIL_FROM_STAG=11, STAG_GAMMA5_FREE=12, LAPLACE_REAL_NC=13, STAG_FREE_REAL=14)
+          STENCIL_FROM_STAG=11, STAG_GAMMA5_FREE=12, LAPLACE_REAL_NC=13, STAG_FREE_REAL=14,
+          STAG_DEO_U1=15, STAG_DOE_U1=16, STAG_M2MDEODOE_U1=17)
 SOLVER = dict(CG=0, CG_RESTART=1, CR=2, CR_RESTART=3, GCR=4, GCR_RESTART=5, BICGSTAB=6,
               BICGSTAB_RESTART=7, BICGSTAB_L=8, BICGSTAB_L_RESTART=9, GMRES=10, GMRES_RESTART=11)
 
@@ -114,6 +116,7 @@ def libs():
         "glb_cgm_update_p": (ci, [vp, ci, sz, ci, pd, pd, vp, C.POINTER(vp)]),
         "glb_cg_solve_supported": (ci, [vp]),
         "glb_cg_solve": (ci, [vp, vp, vp, ci, cd, C.POINTER(CgReport), pd, ci]),
+        "glb_stag_eoprec_prepare": (ci, [vp, vp, vp]), "glb_stag_eoprec_reconstruct": (ci, [vp, vp, vp, vp]),
         "glb_mg_transfer_create": (ci, [vp, ci, ci, ci, ci, ci, ci, C.POINTER(vp), C.POINTER(vp)]),
         "glb_mg_transfer_destroy": (ci, [vp]), "glb_mg_fine_size": (sz, [vp]), "glb_mg_coarse_size": (sz, [vp]),
         "glb_mg_prolong": (ci, [vp, vp, vp]), "glb_mg_restrict": (ci, [vp, vp, vp]),
@@ -131,6 +134,8 @@ def libs():
                                       C.POINTER(Result)]),
         "glbx_dev_solve": (ci, [ci, vp, vp, vp, ci, cd, ci, ci, ci, C.POINTER(Result)]),
         "glbx_dev_solve_cg_m": (ci, [vp, C.POINTER(vp), vp, ci, ci, ci, cd, vp, ci, ci, C.POINTER(Result)]),
+        "glbx_host_eoprec_prepare": (ci, [C.POINTER(OpDesc), vp, vp]),
+        "glbx_host_eoprec_reconstruct": (ci, [C.POINTER(OpDesc), vp, vp, vp]),
         "glbx_host_solve_multi": (ci, [ci, C.POINTER(OpDesc), C.POINTER(vp), vp, ci, ci, ci, cd, vp, ci, ci,
                                        C.POINTER(Result)]),
         "glbx_host_solve_precond": (ci, [ci, C.POINTER(OpDesc), vp, vp, ci, cd, ci, ci, ci, cd, ci, C.POINTER(Result)]),
@@ -245,6 +250,15 @@ class Operator:
         _chk(self.ctx.cu.glb_op_apply_dot(self.h, out.ptr, inp.ptr, w.ptr if w is not None else None,
                                           int(want_norm), d), "glb_op_apply_dot")
         return complex(d[0], d[1]), d[2]
+
+    def eoprec_prepare(self, rhs_e, rhs_orig):
+        """glb_stag_eoprec_prepare: rhs_e = m rhs - D_eo rhs on even sites, 0 on odd (operators.cpp:528)"""
+        _chk(self.ctx.cu.glb_stag_eoprec_prepare(self.h, rhs_e.ptr, rhs_orig.ptr), "glb_stag_eoprec_prepare")
+
+    def eoprec_reconstruct(self, lhs_full, lhs_e, rhs_o):
+        """glb_stag_eoprec_reconstruct: even sites lhs_e, odd sites (rhs_o - D_oe lhs_e)/m (operators.cpp:574)"""
+        _chk(self.ctx.cu.glb_stag_eoprec_reconstruct(self.h, lhs_full.ptr, lhs_e.ptr, rhs_o.ptr),
+             "glb_stag_eoprec_reconstruct")
 
     def set_mass(self, m):
         _chk(self.ctx.cu.glb_op_set_mass(self.h, m))
@@ -538,6 +552,17 @@ class Context:
     def host_apply(self, desc, rhs):
         out = np.empty_like(rhs)
         _chk(self.ho.glbx_host_apply(C.byref(desc), _p(out), _p(rhs)), "glbx_host_apply")
+        return out
+
+    def host_eoprec_prepare(self, desc, rhs_orig):
+        out = np.empty_like(rhs_orig)
+        _chk(self.ho.glbx_host_eoprec_prepare(C.byref(desc), _p(out), _p(rhs_orig)), "glbx_host_eoprec_prepare")
+        return out
+
+    def host_eoprec_reconstruct(self, desc, lhs_e, rhs_o):
+        out = np.empty_like(lhs_e)
+        _chk(self.ho.glbx_host_eoprec_reconstruct(C.byref(desc), _p(out), _p(lhs_e), _p(rhs_o)),
+             "glbx_host_eoprec_reconstruct")
         return out
 
     def host_solve(self, solver, desc, x, b, max_iter=10000, eps=1e-10, restart_freq=0, l=0, verbosity=0):

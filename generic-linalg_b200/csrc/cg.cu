@@ -32,6 +32,7 @@ int op_apply_fused(glb_operator* op, void* out, const void* in, const ApplyFusio
 
 static bool can_fuse_direction(const glb_operator* op) {
   if (op->ctx->nranks > 1) return normal_fused_ok(op);  // slabs: only the one-pass D^dag D kernel
+  if (op->kind == OPK_STAGGERED && (op->flags & (GLB_STAG_DEO | GLB_STAG_DOE | GLB_STAG_M2MDEODOE))) return false;
   return (op->kind == OPK_STAGGERED || op->kind == OPK_LAPLACE_U1) && op->X >= 2;
 }
 

@@ -144,6 +144,9 @@ int glb_op_create_staggered(glb_context* ctx, const void* h_links, int X, int Y,
   if ((flags & GLB_STAG_NORMAL) && (flags & (GLB_STAG_DAGGER | GLB_STAG_GAMMA5)))
     return fail(GLB_ERR_ARG, "NORMAL cannot be combined with DAGGER/GAMMA5");
   if ((flags & GLB_STAG_DAGGER) && (flags & GLB_STAG_GAMMA5)) return fail(GLB_ERR_ARG, "DAGGER+GAMMA5 unsupported");
+  const unsigned eo = flags & (GLB_STAG_DEO | GLB_STAG_DOE | GLB_STAG_M2MDEODOE);
+  if (eo && ((eo & (eo - 1)) || (flags & ~eo) || !h_links))
+    return fail(GLB_ERR_ARG, "DEO / DOE / M2MDEODOE are exclusive, gauged-only flags");
   int rc = new_op(ctx, OPK_STAGGERED, GLB_COMPLEX, X, Y, 1, out);
   if (rc) return rc;
   glb_operator* op = *out;
@@ -153,7 +156,7 @@ int glb_op_create_staggered(glb_context* ctx, const void* h_links, int X, int Y,
     rc = upload_links(op, h_links);
     if (rc) return rc;
   }
-  if (flags & GLB_STAG_NORMAL) GLB_CUDA(cudaMalloc(&op->tmp, sizeof(cplx) * (size_t)X * op->Yloc));
+  if (flags & (GLB_STAG_NORMAL | GLB_STAG_M2MDEODOE)) GLB_CUDA(cudaMalloc(&op->tmp, sizeof(cplx) * (size_t)X * op->Yloc));
   return alloc_ghosts(op, 2);
 }
 
@@ -162,6 +165,8 @@ int glb_op_create_staggered_local(glb_context* ctx, const void* h_links_local, i
   if (!h_links_local) return fail(GLB_ERR_ARG, "glb_op_create_staggered_local needs links");
   if ((flags & GLB_STAG_NORMAL) && (flags & (GLB_STAG_DAGGER | GLB_STAG_GAMMA5)))
     return fail(GLB_ERR_ARG, "NORMAL cannot be combined with DAGGER/GAMMA5");
+  const unsigned eo = flags & (GLB_STAG_DEO | GLB_STAG_DOE | GLB_STAG_M2MDEODOE);
+  if (eo && ((eo & (eo - 1)) || (flags & ~eo))) return fail(GLB_ERR_ARG, "DEO / DOE / M2MDEODOE are exclusive flags");
   int rc = new_op(ctx, OPK_STAGGERED, GLB_COMPLEX, X, Y, 1, out);
   if (rc) return rc;
   glb_operator* op = *out;
@@ -169,7 +174,7 @@ int glb_op_create_staggered_local(glb_context* ctx, const void* h_links_local, i
   op->flags = flags;
   rc = upload_links(op, h_links_local, true);
   if (rc) return rc;
-  if (flags & GLB_STAG_NORMAL) GLB_CUDA(cudaMalloc(&op->tmp, sizeof(cplx) * (size_t)X * op->Yloc));
+  if (flags & (GLB_STAG_NORMAL | GLB_STAG_M2MDEODOE)) GLB_CUDA(cudaMalloc(&op->tmp, sizeof(cplx) * (size_t)X * op->Yloc));
   return alloc_ghosts(op, 2);
 }
 
@@ -254,6 +259,7 @@ double glb_op_bytes_per_apply(const glb_operator* op) {
     case OPK_LAPLACE_U1: return V * 64.0;
     case OPK_STAGGERED: {
       const double one = op->has_links ? 64.0 : 32.0;
+      if (op->flags & GLB_STAG_M2MDEODOE) return V * (2 * one + 16.0);  // two hopping passes + the m^2 in term
       return V * ((op->flags & GLB_STAG_NORMAL) ? 2 * one : one);
     }
     case OPK_GAMMA5: return V * 32.0;
@@ -302,7 +308,21 @@ static int apply_impl(glb_operator* op, void* out, const void* in, const ApplyFu
         }
         return launch_staggered(op, out, op->tmp, true, g);
       }
+      if (op->flags & GLB_STAG_M2MDEODOE) {  // operators.cpp:549-571 : tmp = D_oe in ; out = m^2 in - D_eo tmp | 0
+        ApplyFusion none;
+        if ((rc = halo_exchange(op, in, 1))) return rc;
+        if ((rc = launch_staggered_eo(op, op->tmp, in, 1, 0, 0.0, nullptr, none))) return rc;
+        if ((rc = halo_exchange(op, op->tmp, 1))) return rc;
+        ApplyFusion g = f;
+        if (g.w_is_input) {
+          g.w_is_input = false;
+          g.w = in;
+        }
+        return launch_staggered_eo(op, out, op->tmp, 0, 1, op->mass * op->mass, in, g);
+      }
       if ((rc = halo_exchange(op, in, 1))) return rc;
+      if (op->flags & GLB_STAG_DEO) return launch_staggered_eo(op, out, in, 0, 0, 0.0, nullptr, f);
+      if (op->flags & GLB_STAG_DOE) return launch_staggered_eo(op, out, in, 1, 0, 0.0, nullptr, f);
       return launch_staggered(op, out, in, (op->flags & GLB_STAG_DAGGER) != 0, f);
     }
   }
@@ -319,6 +339,24 @@ extern "C" {
 int glb_op_apply(glb_operator* op, void* d_out, const void* d_in) {
   ApplyFusion none;
   return apply_impl(op, d_out, d_in, none);
+}
+
+int glb_stag_eoprec_prepare(glb_operator* op, void* d_rhs_e, const void* d_rhs_orig) {
+  if (!op || op->kind != OPK_STAGGERED || !op->has_links) return fail(GLB_ERR_ARG, "eoprec_prepare needs a gauged staggered operator");
+  if (d_rhs_e == d_rhs_orig) return fail(GLB_ERR_ARG, "eoprec_prepare: output must not alias input");
+  ApplyFusion none;
+  int rc = halo_exchange(op, d_rhs_orig, 1);
+  if (rc) return rc;
+  return launch_staggered_eo(op, d_rhs_e, d_rhs_orig, 0, 1, op->mass, d_rhs_orig, none);
+}
+
+int glb_stag_eoprec_reconstruct(glb_operator* op, void* d_lhs_full, const void* d_lhs_e, const void* d_rhs_o) {
+  if (!op || op->kind != OPK_STAGGERED || !op->has_links) return fail(GLB_ERR_ARG, "eoprec_reconstruct needs a gauged staggered operator");
+  if (d_lhs_full == d_lhs_e || d_lhs_full == d_rhs_o) return fail(GLB_ERR_ARG, "eoprec_reconstruct: output must not alias an input");
+  ApplyFusion none;
+  int rc = halo_exchange(op, d_lhs_e, 1);
+  if (rc) return rc;
+  return launch_staggered_eo(op, d_lhs_full, d_lhs_e, 1, 2, 1.0 / op->mass, d_rhs_o, none);
 }
 
 int glb_op_apply_dot(glb_operator* op, void* d_out, const void* d_in, const void* d_w, int want_norm, double dots[3]) {

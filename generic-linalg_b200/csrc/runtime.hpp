@@ -169,6 +169,10 @@ struct ApplyFusion {
   HaloWait wait{};           // slabs on the peer-memory path: ghost-row flags to wait for in the prologue
 };
 int launch_staggered(glb_operator* op, void* out, const void* in, bool dagger, const ApplyFusion& f);
+// even/odd pieces of the staggered operator (operators.cpp:456-616): parity 0 updates even sites, 1 odd sites;
+// post 0: h/2 | 0, post 1: coef*aux - h/2 | 0, post 2: coef*(aux - h/2) | in
+int launch_staggered_eo(glb_operator* op, void* out, const void* in, int parity, int post, double coef, const void* aux,
+                        const ApplyFusion& f);
 int launch_laplace(glb_operator* op, void* out, const void* in, const ApplyFusion& f);
 int launch_gamma5(glb_operator* op, void* out, const void* in);
 // normal.cu : D^dag D in one pass (single rank, gauged, even X)

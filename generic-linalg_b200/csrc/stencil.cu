@@ -58,9 +58,16 @@ struct StagArgs {
   int cg_role;   // 1: epilogue publishes <p,Ap> into the CG state
   int pf_rows;   // L2 prefetch distance in rows (0 = off)
   int nrb;       // number of row blocks per strip
+  // FAM_STAG_EO: the even/odd pieces of operators.cpp:456-616
+  int eo_parity;    // 0: update even sites (D_eo), 1: update odd sites (D_oe); the other parity gets the `else` value
+  int eo_post;      // 0: out = h/2 | 0          (square_staggered_deo_u1 / _doe_u1)
+                    // 1: out = coef*aux - h/2 | 0          (m2mdeodoe: coef = m^2; eoprec_prepare: coef = m)
+                    // 2: out = coef*(aux - h/2) | in       (eoprec_reconstruct: coef = 1/m)
+  double eo_coef;
+  const cplx* aux;  // second input of eo_post 1 / 2 (same layout as out)
 };
 
-enum { FAM_STAGGERED = 0, FAM_LAPLACE_U1 = 1 };
+enum { FAM_STAGGERED = 0, FAM_LAPLACE_U1 = 1, FAM_STAG_EO = 2 };
 
 template <int SPT>
 struct RowLoad {  // everything fetched one row ahead
@@ -221,7 +228,7 @@ __global__ void __launch_bounds__(STAG_THREADS) stag_kernel(const StagArgs a) {
         const int x = x0 + s;
         cplx h = mk(0.0, 0.0);
         cplx res;
-        if (FAM == FAM_STAGGERED) {
+        if (FAM == FAM_STAGGERED || FAM == FAM_STAG_EO) {
           const bool eta_neg = (x & 1);  // eta1 = 1 - 2*(x%2), operators.cpp:212
           if (HAS_U) {
             const cplx ux_m = (s > 0) ? cur.ux[s - 1] : uxl;
@@ -237,10 +244,26 @@ __global__ void __launch_bounds__(STAG_THREADS) stag_kernel(const StagArgs a) {
             h = eta_neg ? fadd(h, p[s]) : fsub(h, p[s]);
             h = eta_neg ? fsub(h, m[s]) : fadd(h, m[s]);
           }
+          if (FAM == FAM_STAG_EO) {
+            // operators.cpp:456-616: hopping term only, on one parity; the other parity is zeroed (deo/doe,
+            // m2mdeodoe, prepare) or copied from the input (reconstruct)
+            h = fscale(0.5, h);                                       // :486 / :521
+            const bool upd = (((x + yg) & 1) == a.eo_parity);
+            if (a.eo_post == 0) {
+              res = upd ? h : mk(0.0, 0.0);
+            } else {
+              const cplx ax = a.aux[(size_t)y * X + x];
+              if (a.eo_post == 1)
+                res = upd ? fsub(fscale(a.eo_coef, ax), h) : mk(0.0, 0.0);   // :541, :564
+              else
+                res = upd ? fscale(a.eo_coef, fsub(ax, h)) : c[s];          // :589-595
+            }
+          } else {
           if (a.dagger) h = fneg(h);               // operators.cpp:405-414: every hop changes sign
           h = fscale(0.5, h);                      // operators.cpp:227
           res = fadd(h, fscale(a.mass, c[s]));     // operators.cpp:231
           if (a.gamma5 && ((x + yg) & 1)) res = fneg(res);  // operators.cpp:345 eo_sign on every term
+          }
         } else {  // gauged Laplacian, operators.cpp:103-116
           const cplx ux_m = (s > 0) ? cur.ux[s - 1] : uxl;
           h = fsub(h, fmul(cur.ux[s], psi_xp));
@@ -509,6 +532,49 @@ int launch_staggered(glb_operator* op, void* out, const void* in, bool dagger, c
   }
   if (spt2) return launch_stag_f<2, false, FAM_STAGGERED>(op, a, fuse, ndot);
   return launch_stag_f<1, false, FAM_STAGGERED>(op, a, fuse, ndot);
+}
+
+// even/odd pieces (operators.cpp:456-616): hopping term on one parity with an optional second input
+int launch_staggered_eo(glb_operator* op, void* out, const void* in, int parity, int post, double coef, const void* aux,
+                        const ApplyFusion& f) {
+  glb_context* ctx = op->ctx;
+  if (op->X < 2 || op->Yloc < 1 || !op->has_links) return fail(GLB_ERR_ARG, "even/odd staggered pieces need links and X >= 2");
+  if (f.r != nullptr) return fail(GLB_ERR_ARG, "even/odd staggered pieces have no fused direction update");
+  if (post != 0 && aux == nullptr) return fail(GLB_ERR_ARG, "even/odd post-operation needs its second input");
+  StagArgs a{};
+  const size_t X = op->X;
+  const bool single = (ctx->nranks == 1);
+  a.in = (const cplx*)in;
+  a.in_lo = single ? (const cplx*)in + (size_t)(op->Yloc - 1) * X : (const cplx*)op->ghost_lo + (size_t)(op->ghost_depth - 1) * X;
+  a.in_hi = single ? (const cplx*)in : (const cplx*)op->ghost_hi;
+  a.out = (cplx*)out;
+  a.Ux = op->Ux;
+  a.Uy = op->Uy;
+  a.Uy_lo = op->Uy_lo;
+  a.w = f.w_is_input ? nullptr : (const cplx*)f.w;
+  a.X = op->X;
+  a.Yloc = op->Yloc;
+  a.y0 = op->y0;
+  a.mass = op->mass;
+  a.red = ctx->red;
+  if (!f.to_host) a.red.result_host = nullptr;
+  a.cg = (CgState*)f.cg_state;
+  a.cg_role = f.cg_role;
+  a.pf_rows = 0;
+  a.eo_parity = parity;
+  a.eo_post = post;
+  a.eo_coef = coef;
+  a.aux = (const cplx*)aux;
+  const int ndot = (f.w != nullptr || f.w_is_input) ? (f.want_norm ? 2 : 1) : 0;
+  const bool spt2 = (op->X % 2 == 0) && stag_spt() == 2;
+  if (spt2) {
+    if (ndot == 0) return launch_stag_t<2, true, false, 0, FAM_STAG_EO, 1>(op, a);
+    if (ndot == 1) return launch_stag_t<2, true, false, 1, FAM_STAG_EO, 1>(op, a);
+    return launch_stag_t<2, true, false, 2, FAM_STAG_EO, 1>(op, a);
+  }
+  if (ndot == 0) return launch_stag_t<1, true, false, 0, FAM_STAG_EO, 1>(op, a);
+  if (ndot == 1) return launch_stag_t<1, true, false, 1, FAM_STAG_EO, 1>(op, a);
+  return launch_stag_t<1, true, false, 2, FAM_STAG_EO, 1>(op, a);
 }
 
 int launch_gamma5(glb_operator* op, void* out, const void* in) {

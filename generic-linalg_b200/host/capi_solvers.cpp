@@ -30,7 +30,8 @@ typedef struct glbx_result {
 enum {
   GX_LAPLACE_REAL = 0, GX_LAPLACE_IMAG = 1, GX_LAPLACE_NC = 2, GX_LAPLACE_U1 = 3, GX_STAG_FREE = 4, GX_STAG_U1 = 5,
   GX_STAG_GAMMA5_U1 = 6, GX_STAG_DAGGER_U1 = 7, GX_STAG_NORMAL_U1 = 8, GX_GAMMA5 = 9, GX_STENCIL = 10,
-  GX_STENCIL_FROM_STAG = 11, GX_STAG_GAMMA5_FREE = 12, GX_LAPLACE_REAL_NC = 13, GX_STAG_FREE_REAL = 14
+  GX_STENCIL_FROM_STAG = 11, GX_STAG_GAMMA5_FREE = 12, GX_LAPLACE_REAL_NC = 13, GX_STAG_FREE_REAL = 14,
+  GX_STAG_DEO_U1 = 15, GX_STAG_DOE_U1 = 16, GX_STAG_M2MDEODOE_U1 = 17
 };
 enum {
   GX_CG = 0, GX_CG_RESTART = 1, GX_CR = 2, GX_CR_RESTART = 3, GX_GCR = 4, GX_GCR_RESTART = 5, GX_BICGSTAB = 6,
@@ -114,6 +115,9 @@ bool build_host_op(const glbx_opdesc* d, HostOp* h) {
     case GX_STAG_DAGGER_U1: h->cz = &square_staggered_dagger_u1; break;
     case GX_STAG_NORMAL_U1: h->cz = &square_staggered_normal_u1; break;
     case GX_GAMMA5: h->cz = &gamma_5; break;
+    case GX_STAG_DEO_U1: h->cz = &square_staggered_deo_u1; break;
+    case GX_STAG_DOE_U1: h->cz = &square_staggered_doe_u1; break;
+    case GX_STAG_M2MDEODOE_U1: h->cz = &square_staggered_m2mdeodoe_u1; break;
     case GX_STENCIL:
     case GX_STENCIL_FROM_STAG: {
       int dims[2] = {d->X, d->Y};
@@ -210,6 +214,20 @@ int glbx_host_apply(const glbx_opdesc* d, void* lhs, const void* rhs) {
     h.cz((zc*)lhs, (zc*)rhs, h.extra);
   else
     h.cd((double*)lhs, (double*)rhs, h.extra);
+  return GLB_OK;
+}
+
+// operators.cpp:528 / :574 through the reference-named host functions (d: any gauged staggered descriptor)
+int glbx_host_eoprec_prepare(const glbx_opdesc* d, void* rhs_e, const void* rhs_orig) {
+  HostOp h;
+  if (!build_host_op(d, &h)) return GLB_ERR_ARG;
+  square_staggered_eoprec_prepare((zc*)rhs_e, (zc*)rhs_orig, &h.stag);
+  return GLB_OK;
+}
+int glbx_host_eoprec_reconstruct(const glbx_opdesc* d, void* lhs_full, const void* lhs_e, const void* rhs_o) {
+  HostOp h;
+  if (!build_host_op(d, &h)) return GLB_ERR_ARG;
+  square_staggered_eoprec_reconstruct((zc*)lhs_full, (zc*)lhs_e, (zc*)rhs_o, &h.stag);
   return GLB_OK;
 }
 

@@ -27,7 +27,8 @@ bool g_cache_ops = false;
 
 enum Builtin {
   B_NONE = 0, B_LAPLACE_NC, B_LAPLACE_NC_REAL, B_LAPLACE_U1, B_STAG_FREE, B_STAG_U1, B_GAMMA5, B_STAG_G5_FREE,
-  B_STAG_G5_U1, B_STAG_DAGGER_U1, B_STAG_NORMAL_U1, B_LAPLACIAN_REAL, B_LAPLACIAN_IMAG, B_STENCIL, B_STAG_FREE_REAL
+  B_STAG_G5_U1, B_STAG_DAGGER_U1, B_STAG_NORMAL_U1, B_STAG_DEO_U1, B_STAG_DOE_U1, B_STAG_M2MDEODOE_U1, B_LAPLACIAN_REAL,
+  B_LAPLACIAN_IMAG, B_STENCIL, B_STAG_FREE_REAL
 };
 
 Builtin classify(void (*fn)(zcplx*, zcplx*, void*)) {
@@ -41,6 +42,9 @@ Builtin classify(void (*fn)(zcplx*, zcplx*, void*)) {
   if (fn == (F)&square_staggered_gamma5_u1) return B_STAG_G5_U1;
   if (fn == (F)&square_staggered_dagger_u1) return B_STAG_DAGGER_U1;
   if (fn == (F)&square_staggered_normal_u1) return B_STAG_NORMAL_U1;
+  if (fn == (F)&square_staggered_deo_u1) return B_STAG_DEO_U1;
+  if (fn == (F)&square_staggered_doe_u1) return B_STAG_DOE_U1;
+  if (fn == (F)&square_staggered_m2mdeodoe_u1) return B_STAG_M2MDEODOE_U1;
   if (fn == (F)&square_laplacian) return B_LAPLACIAN_IMAG;
   if (fn == (F)&apply_stencil_2d) return B_STENCIL;
   return B_NONE;
@@ -80,6 +84,15 @@ glb_operator* build(Builtin kind, void* extra) {
       break;
     case B_STAG_NORMAL_U1:
       GLBX(glb_op_create_staggered(ctx, s->lattice, s->x_fine, s->y_fine, s->mass, GLB_STAG_NORMAL, &op));
+      break;
+    case B_STAG_DEO_U1:
+      GLBX(glb_op_create_staggered(ctx, s->lattice, s->x_fine, s->y_fine, s->mass, GLB_STAG_DEO, &op));
+      break;
+    case B_STAG_DOE_U1:
+      GLBX(glb_op_create_staggered(ctx, s->lattice, s->x_fine, s->y_fine, s->mass, GLB_STAG_DOE, &op));
+      break;
+    case B_STAG_M2MDEODOE_U1:
+      GLBX(glb_op_create_staggered(ctx, s->lattice, s->x_fine, s->y_fine, s->mass, GLB_STAG_M2MDEODOE, &op));
       break;
     case B_LAPLACIAN_REAL: {  // square_laplace.cpp:182 : (4+MASS)
       laplace_op* l = (laplace_op*)extra;
@@ -123,7 +136,7 @@ struct CacheKey {
 };
 std::map<CacheKey, glb_operator*> g_cache;
 
-bool cacheable(Builtin k) { return k >= B_LAPLACE_NC && k <= B_STAG_NORMAL_U1; }
+bool cacheable(Builtin k) { return k >= B_LAPLACE_NC && k <= B_STAG_M2MDEODOE_U1; }
 
 struct OpLease {  // operator for the duration of one call
   glb_operator* op;
@@ -298,6 +311,47 @@ void square_staggered_gamma5(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcp
 void square_staggered_gamma5_u1(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_STAG_G5_U1, lhs, rhs, e); }
 void square_staggered_dagger_u1(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_STAG_DAGGER_U1, lhs, rhs, e); }
 void square_staggered_normal_u1(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_STAG_NORMAL_U1, lhs, rhs, e); }
+void square_staggered_deo_u1(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_STAG_DEO_U1, lhs, rhs, e); }
+void square_staggered_doe_u1(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_STAG_DOE_U1, lhs, rhs, e); }
+void square_staggered_m2mdeodoe_u1(zcplx* lhs, zcplx* rhs, void* e) {
+  direct_apply<zcplx>(B_STAG_M2MDEODOE_U1, lhs, rhs, e);
+}
+// operators.cpp:528-545 / :574-598 with host vectors: upload, one device pass each, download
+void square_staggered_eoprec_prepare(zcplx* rhs_e, zcplx* rhs_orig, void* e) {
+  try {
+    glb_context* ctx = glb200_default_context();
+    OpLease L;
+    lease(B_STAG_U1, e, &L);
+    const size_t n = glb_op_local_size(L.op);
+    Blas<zcplx> B = {ctx, n};
+    Work<zcplx> W(B);
+    zcplx *d_in = W.get(), *d_out = W.get();
+    GLBX(glb_vec_upload(ctx, GLB_COMPLEX, n, d_in, rhs_orig));
+    GLBX(glb_stag_eoprec_prepare(L.op, d_out, d_in));
+    GLBX(glb_vec_download(ctx, GLB_COMPLEX, n, rhs_e, d_out));
+  } catch (const std::exception& ex) {
+    std::cerr << "[glb200] square_staggered_eoprec_prepare failed: " << ex.what() << std::endl;
+    std::abort();
+  }
+}
+void square_staggered_eoprec_reconstruct(zcplx* lhs_full, zcplx* lhs_e, zcplx* rhs_o, void* e) {
+  try {
+    glb_context* ctx = glb200_default_context();
+    OpLease L;
+    lease(B_STAG_U1, e, &L);
+    const size_t n = glb_op_local_size(L.op);
+    Blas<zcplx> B = {ctx, n};
+    Work<zcplx> W(B);
+    zcplx *d_e = W.get(), *d_o = W.get(), *d_out = W.get();
+    GLBX(glb_vec_upload(ctx, GLB_COMPLEX, n, d_e, lhs_e));
+    GLBX(glb_vec_upload(ctx, GLB_COMPLEX, n, d_o, rhs_o));
+    GLBX(glb_stag_eoprec_reconstruct(L.op, d_out, d_e, d_o));
+    GLBX(glb_vec_download(ctx, GLB_COMPLEX, n, lhs_full, d_out));
+  } catch (const std::exception& ex) {
+    std::cerr << "[glb200] square_staggered_eoprec_reconstruct failed: " << ex.what() << std::endl;
+    std::abort();
+  }
+}
 void square_laplacian(double* lhs, double* rhs, void* e) { direct_apply<double>(B_LAPLACIAN_REAL, lhs, rhs, e); }
 void square_laplacian(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_LAPLACIAN_IMAG, lhs, rhs, e); }
 void apply_stencil_2d(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_STENCIL, lhs, rhs, e); }

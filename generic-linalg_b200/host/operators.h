@@ -51,6 +51,16 @@ void square_staggered_dagger_u1(complex<double>* lhs, complex<double>* rhs, void
 // operators.cpp:444   D^dagger D
 void square_staggered_normal_u1(complex<double>* lhs, complex<double>* rhs, void* extra_data);
 
+// operators.cpp:456 / :494   even/odd pieces: the hopping term on even (odd) sites, the other parity zeroed
+void square_staggered_deo_u1(complex<double>* lhs, complex<double>* rhs, void* extra_data);
+void square_staggered_doe_u1(complex<double>* lhs, complex<double>* rhs, void* extra_data);
+// operators.cpp:549   m^2 - D_eo D_oe on even sites (odd sites zeroed): the e/o preconditioned, Hermitian system
+void square_staggered_m2mdeodoe_u1(complex<double>* lhs, complex<double>* rhs, void* extra_data);
+// operators.cpp:528 / :574   rhs_e = m rhs - D_eo rhs (even) ; lhs_full = lhs_e (even), (rhs_o - D_oe lhs_e)/m (odd)
+void square_staggered_eoprec_prepare(complex<double>* rhs_e, complex<double>* rhs_orig, void* extra_data);
+void square_staggered_eoprec_reconstruct(complex<double>* lhs_full, complex<double>* lhs_e, complex<double>* rhs_o,
+                                         void* extra_data);
+
 // The examples' in-file Laplacians (square_laplace.cpp:182, unit_test.cpp:573, imag_laplace.cpp:126)
 // take their size from `#define N` / `#define MASS`; here the same numbers travel in extra_data.
 struct laplace_op {

@@ -111,6 +111,10 @@ int glb_host_free(glb_context* ctx, void* hptr);
 #define GLB_STAG_DAGGER 1u   /* D^dagger : operators.cpp:372                                   */
 #define GLB_STAG_GAMMA5 2u   /* gamma5 D : operators.cpp:262,316                               */
 #define GLB_STAG_NORMAL 4u   /* D^dagger D through a temporary : operators.cpp:444             */
+/* even/odd pieces (gauged only; not combinable with the flags above) */
+#define GLB_STAG_DEO 8u      /* D_eo: hopping term on even sites, odd sites zeroed : operators.cpp:456   */
+#define GLB_STAG_DOE 16u     /* D_oe: hopping term on odd sites, even sites zeroed : operators.cpp:494   */
+#define GLB_STAG_M2MDEODOE 32u /* m^2 - D_eo D_oe on even sites, odd sites zeroed  : operators.cpp:549   */
 
 /* 5-point periodic Laplacian, Nc colours per site, out = diag*in - sum of 4 neighbours.
  * diag = 4+m2 (square_laplace.cpp:182; operators.cpp:28), or 4+m2+i (imag_laplace.cpp:126).
@@ -227,6 +231,14 @@ typedef struct glb_cg_report {
 int glb_cg_solve_supported(const glb_operator* op);
 int glb_cg_solve(glb_operator* op, void* d_x, const void* d_b, int max_iter, double eps, glb_cg_report* rep,
                  double* rsq_hist, int hist_cap);
+
+/* ----------------------------------------------- even/odd preconditioning */
+/* square_staggered_eoprec_prepare (operators.cpp:528-545): rhs_e = m rhs_orig - D_eo rhs_orig on even sites, 0 on
+ * odd sites.  `op` is any gauged staggered operator (its links and mass are used). */
+int glb_stag_eoprec_prepare(glb_operator* op, void* d_rhs_e, const void* d_rhs_orig);
+/* square_staggered_eoprec_reconstruct (operators.cpp:574-598): lhs_full = lhs_e on even sites,
+ * (rhs_o - D_oe lhs_e)/m on odd sites. */
+int glb_stag_eoprec_reconstruct(glb_operator* op, void* d_lhs_full, const void* d_lhs_e, const void* d_rhs_o);
 
 /* ----------------------------------------------- multigrid grid transfers */
 /* prolong / restrict of multigrid/aa_mg/mg_complex.cpp:372-467 on device vectors.  A transfer

@@ -44,7 +44,10 @@ enum orc_op_kind {
   ORC_OP_STENCIL_FROM_STAG = 11,/* operators_stencil.cpp:14 get_square_staggered_u1_stencil + apply         */
   ORC_OP_STAG_GAMMA5_FREE = 12, /* operators.cpp:262  square_staggered_gamma5                               */
   ORC_OP_LAPLACE_REAL_NC = 13,  /* tests/multishift/multishift.cpp:634 square_laplace (double, Nc colours)  */
-  ORC_OP_STAG_FREE_REAL = 14    /* tests/multishift/multishift.cpp:677 square_staggered (double)            */
+  ORC_OP_STAG_FREE_REAL = 14,   /* tests/multishift/multishift.cpp:677 square_staggered (double)            */
+  ORC_OP_STAG_DEO_U1 = 15,      /* operators.cpp:456  square_staggered_deo_u1   (hop term, even sites)      */
+  ORC_OP_STAG_DOE_U1 = 16,      /* operators.cpp:494  square_staggered_doe_u1   (hop term, odd sites)       */
+  ORC_OP_STAG_M2MDEODOE_U1 = 17 /* operators.cpp:549  square_staggered_m2mdeodoe_u1 (m^2 - D_eo D_oe)       */
 };
 
 /* Description of one operator.  Arrays are host pointers owned by the caller
@@ -106,6 +109,11 @@ void ORC(op_free)(void* op);
 int ORC(op_is_complex)(void* op);
 int ORC(op_size)(void* op);
 void ORC(op_apply)(void* op, double* lhs, const double* rhs);
+
+/* Even/odd preconditioning of the staggered operator described by `op` (any gauged staggered kind):
+ * operators.cpp:528 square_staggered_eoprec_prepare, :574 square_staggered_eoprec_reconstruct. */
+void ORC(eoprec_prepare)(void* op, double* rhs_e, const double* rhs_orig);
+void ORC(eoprec_reconstruct)(void* op, double* lhs_full, const double* lhs_e, const double* rhs_o);
 
 /* Solvers: phi is in/out (initial guess -> solution), phi0 the rhs.  verbosity:
  * 0 none .. 3 detail (verbosity.h:9-16), printed to stdout exactly as the reference does. */

@@ -17,7 +17,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # must mirror oracle/oracle_api.h
 OP = dict(LAPLACE_REAL=0, LAPLACE_IMAG=1, LAPLACE_NC=2, LAPLACE_U1=3, STAG_FREE=4, STAG_U1=5,
           STAG_GAMMA5_U1=6, STAG_DAGGER_U1=7, STAG_NORMAL_U1=8, GAMMA5=9, STENCIL=10,
-          STENCIL_FROM_STAG=11, STAG_GAMMA5_FREE=12, LAPLACE_REAL_NC=13, STAG_FREE_REAL=14)
+          STENCIL_FROM_STAG=11, STAG_GAMMA5_FREE=12, LAPLACE_REAL_NC=13, STAG_FREE_REAL=14,
+          STAG_DEO_U1=15, STAG_DOE_U1=16, STAG_M2MDEODOE_U1=17)
 SOLVER = dict(CG=0, CG_RESTART=1, CR=2, CR_RESTART=3, GCR=4, GCR_RESTART=5, BICGSTAB=6,
               BICGSTAB_RESTART=7, BICGSTAB_L=8, BICGSTAB_L_RESTART=9, GMRES=10, GMRES_RESTART=11)
 
@@ -70,6 +71,21 @@ class Operator:
         self.orc._f("op_apply")(self.h, _ptr(out), _ptr(rhs))
         return out
 
+    def eoprec_prepare(self, rhs_orig):
+        """operators.cpp:528 square_staggered_eoprec_prepare with this operator's links and mass"""
+        rhs_orig = np.ascontiguousarray(rhs_orig, dtype=np.complex128)
+        out = np.empty_like(rhs_orig)
+        self.orc._f("eoprec_prepare")(self.h, _ptr(out), _ptr(rhs_orig))
+        return out
+
+    def eoprec_reconstruct(self, lhs_e, rhs_o):
+        """operators.cpp:574 square_staggered_eoprec_reconstruct"""
+        lhs_e = np.ascontiguousarray(lhs_e, dtype=np.complex128)
+        rhs_o = np.ascontiguousarray(rhs_o, dtype=np.complex128)
+        out = np.empty_like(lhs_e)
+        self.orc._f("eoprec_reconstruct")(self.h, _ptr(out), _ptr(lhs_e), _ptr(rhs_o))
+        return out
+
     def __del__(self):
         try:
             self.orc._f("op_free")(self.h)
@@ -93,6 +109,7 @@ class Oracle:
             "dot": (None, [ci, vp, vp, ci, vp]), "norm2sq": (cd, [ci, vp, ci]), "diffnorm2sq": (cd, [ci, vp, vp, ci]),
             "op_prepare": (vp, [C.POINTER(OpDesc)]), "op_free": (None, [vp]), "op_is_complex": (ci, [vp]),
             "op_size": (ci, [vp]), "op_apply": (None, [vp, vp, vp]),
+            "eoprec_prepare": (None, [vp, vp, vp]), "eoprec_reconstruct": (None, [vp, vp, vp, vp]),
             "solve": (ci, [ci, vp, vp, vp, ci, cd, ci, ci, ci, C.POINTER(Result)]),
             "solve_cg_m": (ci, [vp, C.POINTER(vp), vp, ci, ci, ci, cd, vp, ci, ci, C.POINTER(Result)]),
         }

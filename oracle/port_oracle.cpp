@@ -182,6 +182,51 @@ void op_staggered_free_real(double* out, const double* in, int X, int Y, double 
   }
 }
 
+// operators.cpp:456-525 square_staggered_deo_u1 / _doe_u1: the hopping term on one parity, the other zeroed
+void op_staggered_eo(cplx* out, const cplx* in, const cplx* U, int X, int Y, int parity) {
+  for (int i = 0; i < X * Y; i++) {
+    const int x = i % X, y = i / X;
+    out[i] = 0.0;
+    const double eta1 = 1 - 2 * (x % 2);
+    if ((x + y) % 2 != parity) continue;
+    const int xp = wrap_up(x, X), xm = wrap_dn(x, X), yp = wrap_up(y, Y), ym = wrap_dn(y, Y);
+    out[i] = out[i] - U[y * X * 2 + x * 2] * in[y * X + xp];
+    out[i] = out[i] + std::conj(U[y * X * 2 + xm * 2]) * in[y * X + xm];
+    out[i] = out[i] - eta1 * U[y * X * 2 + x * 2 + 1] * in[yp * X + x];
+    out[i] = out[i] + eta1 * std::conj(U[ym * X * 2 + x * 2 + 1]) * in[ym * X + x];
+    out[i] = 0.5 * out[i];
+  }
+}
+// operators.cpp:549-571 square_staggered_m2mdeodoe_u1
+void op_staggered_m2mdeodoe(cplx* out, const cplx* in, const cplx* U, int X, int Y, double mass) {
+  std::vector<cplx> tmp((size_t)X * Y);
+  op_staggered_eo(tmp.data(), in, U, X, Y, 1);
+  op_staggered_eo(out, tmp.data(), U, X, Y, 0);
+  for (int i = 0; i < X * Y; i++) {
+    const int x = i % X, y = i / X;
+    if ((x + y) % 2 == 0) out[i] = mass * mass * in[i] - out[i];
+  }
+}
+// operators.cpp:528-545 / :574-598
+void op_eoprec_prepare(cplx* rhs_e, const cplx* rhs_orig, const cplx* U, int X, int Y, double mass) {
+  op_staggered_eo(rhs_e, rhs_orig, U, X, Y, 0);
+  for (int i = 0; i < X * Y; i++) {
+    const int x = i % X, y = i / X;
+    if ((x + y) % 2 == 0) rhs_e[i] = mass * rhs_orig[i] - rhs_e[i];
+  }
+}
+void op_eoprec_reconstruct(cplx* lhs_full, const cplx* lhs_e, const cplx* rhs_o, const cplx* U, int X, int Y, double mass) {
+  const double inv_mass = 1.0 / mass;
+  op_staggered_eo(lhs_full, lhs_e, U, X, Y, 1);
+  for (int i = 0; i < X * Y; i++) {
+    const int x = i % X, y = i / X;
+    if ((x + y) % 2 == 1)
+      lhs_full[i] = inv_mass * (rhs_o[i] - lhs_full[i]);
+    else
+      lhs_full[i] = lhs_e[i];
+  }
+}
+
 // operators.cpp:242-259 gamma_5
 void op_gamma5(cplx* out, const cplx* in, int X, int Y) {
   for (int i = 0; i < X * Y; i++) {
@@ -266,6 +311,9 @@ void apply_c(PortOp* op, cplx* out, const cplx* in) {
     case ORC_OP_GAMMA5: op_gamma5(out, in, d.X, d.Y); break;
     case ORC_OP_STENCIL:
     case ORC_OP_STENCIL_FROM_STAG: op_stencil(*op, out, in); break;
+    case ORC_OP_STAG_DEO_U1: op_staggered_eo(out, in, U, d.X, d.Y, 0); break;
+    case ORC_OP_STAG_DOE_U1: op_staggered_eo(out, in, U, d.X, d.Y, 1); break;
+    case ORC_OP_STAG_M2MDEODOE_U1: op_staggered_m2mdeodoe(out, in, U, d.X, d.Y, d.mass); break;
     default: break;
   }
 }
@@ -1021,6 +1069,16 @@ void port_op_apply(void* opv, double* lhs, const double* rhs) {
     apply_c(op, (cplx*)lhs, (const cplx*)rhs);
   else
     apply_r(op, lhs, rhs);
+}
+
+void port_eoprec_prepare(void* opv, double* rhs_e, const double* rhs_orig) {
+  PortOp* op = (PortOp*)opv;
+  op_eoprec_prepare((cplx*)rhs_e, (const cplx*)rhs_orig, (const cplx*)op->d.links, op->d.X, op->d.Y, op->d.mass);
+}
+void port_eoprec_reconstruct(void* opv, double* lhs_full, const double* lhs_e, const double* rhs_o) {
+  PortOp* op = (PortOp*)opv;
+  op_eoprec_reconstruct((cplx*)lhs_full, (const cplx*)lhs_e, (const cplx*)rhs_o, (const cplx*)op->d.links, op->d.X,
+                        op->d.Y, op->d.mass);
 }
 
 int port_solve(int solver, void* opv, double* phi, const double* phi0, int max_iter, double eps, int restart_freq,

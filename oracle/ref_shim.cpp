@@ -82,6 +82,9 @@ void apply_c(RefOp* op, cplx* lhs, cplx* rhs) {
     case ORC_OP_STAG_DAGGER_U1: square_staggered_dagger_u1(lhs, rhs, e); break;
     case ORC_OP_STAG_NORMAL_U1: square_staggered_normal_u1(lhs, rhs, e); break;
     case ORC_OP_GAMMA5: gamma_5(lhs, rhs, e); break;
+    case ORC_OP_STAG_DEO_U1: square_staggered_deo_u1(lhs, rhs, e); break;
+    case ORC_OP_STAG_DOE_U1: square_staggered_doe_u1(lhs, rhs, e); break;
+    case ORC_OP_STAG_M2MDEODOE_U1: square_staggered_m2mdeodoe_u1(lhs, rhs, e); break;
     case ORC_OP_STENCIL:
     case ORC_OP_STENCIL_FROM_STAG: apply_stencil_2d(lhs, rhs, (void*)op->stenc); break;
     default: break;
@@ -234,6 +237,15 @@ void ref_op_apply(void* opv, double* lhs, const double* rhs) {
     apply_c(op, (cplx*)lhs, (cplx*)rhs);
   else
     apply_r(op, lhs, (double*)rhs);
+}
+
+void ref_eoprec_prepare(void* opv, double* rhs_e, const double* rhs_orig) {
+  RefOp* op = (RefOp*)opv;
+  square_staggered_eoprec_prepare((cplx*)rhs_e, (cplx*)rhs_orig, (void*)&op->stagif);
+}
+void ref_eoprec_reconstruct(void* opv, double* lhs_full, const double* lhs_e, const double* rhs_o) {
+  RefOp* op = (RefOp*)opv;
+  square_staggered_eoprec_reconstruct((cplx*)lhs_full, (cplx*)lhs_e, (cplx*)rhs_o, (void*)&op->stagif);
 }
 
 int ref_solve(int solver, void* opv, double* phi, const double* phi0, int max_iter, double eps, int restart_freq,

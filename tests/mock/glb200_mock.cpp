@@ -116,6 +116,9 @@ int glb_op_create_staggered(glb_context*, const void* l, int X, int Y, double m,
   if (flags & GLB_STAG_DAGGER) kind = ORC_OP_STAG_DAGGER_U1;
   if (flags & GLB_STAG_GAMMA5) kind = l ? ORC_OP_STAG_GAMMA5_U1 : ORC_OP_STAG_GAMMA5_FREE;
   if (flags & GLB_STAG_NORMAL) kind = ORC_OP_STAG_NORMAL_U1;
+  if (flags & GLB_STAG_DEO) kind = ORC_OP_STAG_DEO_U1;
+  if (flags & GLB_STAG_DOE) kind = ORC_OP_STAG_DOE_U1;
+  if (flags & GLB_STAG_M2MDEODOE) kind = ORC_OP_STAG_M2MDEODOE_U1;
   *op = wrap(kind, X, Y, 1, m, l, GLB_COMPLEX);
   return GLB_OK;
 }
@@ -146,6 +149,16 @@ size_t glb_op_local_size(const glb_operator* o) { return o->op->size; }
 size_t glb_op_global_size(const glb_operator* o) { return o->op->size; }
 glb_context* glb_op_context(const glb_operator* o) { return o->ctx; }
 double glb_op_bytes_per_apply(const glb_operator*) { return 0; }
+int glb_stag_eoprec_prepare(glb_operator* o, void* rhs_e, const void* rhs_orig) {
+  g_calls++;
+  port_eoprec_prepare(o->op, (double*)rhs_e, (const double*)rhs_orig);
+  return GLB_OK;
+}
+int glb_stag_eoprec_reconstruct(glb_operator* o, void* lhs_full, const void* lhs_e, const void* rhs_o) {
+  g_calls++;
+  port_eoprec_reconstruct(o->op, (double*)lhs_full, (const double*)lhs_e, (const double*)rhs_o);
+  return GLB_OK;
+}
 int glb_op_apply(glb_operator* o, void* out, const void* in) {
   g_calls++;
   port_op_apply(o->op, (double*)out, (const double*)in);
