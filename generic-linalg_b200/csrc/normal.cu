@@ -19,8 +19,7 @@
 #include <cstdlib>
 #include <type_traits>
 
-#include "cg_state.cuh"
-#include "runtime.hpp"
+#include "normal_args.cuh"
 
 namespace glb {
 
@@ -28,28 +27,6 @@ constexpr int NORM_THREADS = 128;
 constexpr int NORM_WARPS = NORM_THREADS / 32;
 constexpr int NORM_OUT_PER_WARP = 60;  // 64 loaded - 2 halo sites on each side
 
-struct NormArgs {
-  const cplx* in;    // plain input, or nullptr when fused
-  const cplx* r;     // fused direction update: input := r + beta * pold
-  const cplx* pold;
-  cplx* pnew;
-  cplx* out;
-  const cplx* Ux;
-  const cplx* Uy;
-  const cplx* w;     // dot partner; nullptr = the input itself
-  // slabs: the two input rows below / above the slab (already final values, never fused);
-  // nullptr on a single rank, where rows wrap periodically inside the slab
-  const cplx* g_lo;
-  const cplx* g_hi;
-  int X, Y;          // Y = rows of this slab
-  double mass;
-  int nrb;      // row blocks: work item i -> strip i % nstrips, rows [Y*rb/nrb, Y*(rb+1)/nrb), rb = i / nstrips
-  P2PRed pr;    // cg_role 3: the last block finishes the sum over ranks itself (peer memory)
-  HaloWait wait;  // peer-memory slabs: ghost-row flags to wait for before touching g_lo / g_hi
-  ReduceWs red;
-  CgState* cg;
-  int cg_role;
-};
 
 // hopping part of the staggered stencil at one site, reference order (operators.cpp:215-224):
 //   h = -U_x(x) psi(x+1) + conj U_x(x-1) psi(x-1) - eta U_y(x,y) psi(y+1) + eta conj U_y(x,y-1) psi(y-1)
@@ -468,6 +445,15 @@ int launch_normal(glb_operator* op, void* out, const void* in, const ApplyFusion
     stages_fused = e ? atoi(e) : 4;
     const char* e2 = getenv("GLB_NORMAL_STAGES_PLAIN");
     stages_plain = e2 ? atoi(e2) : 0;
+  }
+  {
+    // one site per thread (normal1.cu): GLB_NORMAL_SPT1 = 10*stages + min blocks per SM, 0 = off
+    static int spt1 = -1;
+    if (spt1 < 0) {
+      const char* e = getenv("GLB_NORMAL_SPT1");
+      spt1 = e ? atoi(e) : 0;
+    }
+    if (spt1 > 0) return launch_normal_spt1(op, a, fuse, ndot, spt1);
   }
   const int stages = fuse ? stages_fused : stages_plain;
   // Measured at 4096^2 (gpurun t07): ring depth 3 vs 4, rolled vs unrolled row loop and private vs
