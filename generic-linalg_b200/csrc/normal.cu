@@ -448,12 +448,18 @@ int launch_normal(glb_operator* op, void* out, const void* in, const ApplyFusion
   }
   {
     // one site per thread (normal1.cu): GLB_NORMAL_SPT1 = 10*stages + min blocks per SM, 0 = off
-    static int spt1 = -1;
-    if (spt1 < 0) {
+    // Measured at 4096^2 (gpurun t08): the plain kernel runs at 0.183 ms = 5850 GB/s (89 % of the copy peak)
+    // in this shape against 0.209 ms with two sites per thread; the variant with the fused CG direction update
+    // is slower in it (0.330 vs 0.312 ms: twice the shuffles per site on top of a fourth input stream), so the
+    // default is one site per thread for the plain kernel only.  GLB_NORMAL_SPT1: 0 = never, 34/44/... = variant
+    // for both, unset = 34 for the plain kernel.
+    static int spt1 = -2;
+    if (spt1 == -2) {
       const char* e = getenv("GLB_NORMAL_SPT1");
-      spt1 = e ? atoi(e) : 0;
+      spt1 = e ? atoi(e) : -1;
     }
     if (spt1 > 0) return launch_normal_spt1(op, a, fuse, ndot, spt1);
+    if (spt1 == -1 && !fuse) return launch_normal_spt1(op, a, fuse, ndot, 34);
   }
   const int stages = fuse ? stages_fused : stages_plain;
   // Measured at 4096^2 (gpurun t07): ring depth 3 vs 4, rolled vs unrolled row loop and private vs

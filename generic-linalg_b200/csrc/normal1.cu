@@ -234,16 +234,11 @@ static int launch_n1_s(glb_operator* op, const NormArgs& a, bool fuse, int ndot)
   return launch_n1_t<false, 2, STAGES, MINB>(op, a);
 }
 
-// variant: 10*STAGES + min blocks per SM (GLB_NORMAL_SPT1), e.g. 44 = 4 stages, >= 4 blocks (<= 128 registers)
+// variant: 10*STAGES + min blocks per SM (GLB_NORMAL_SPT1): 34 = 3 stages, 4 blocks per SM (<= 128 registers).
+// Five or six blocks per SM force spills and measured slower (gpurun t08); they are not instantiated.
 int launch_normal_spt1(glb_operator* op, const NormArgs& a, bool fuse, int ndot, int variant) {
-  switch (variant) {
-    case 34: return launch_n1_s<3, 4>(op, a, fuse, ndot);
-    case 35: return launch_n1_s<3, 5>(op, a, fuse, ndot);
-    case 36: return launch_n1_s<3, 6>(op, a, fuse, ndot);
-    case 45: return launch_n1_s<4, 5>(op, a, fuse, ndot);
-    case 46: return launch_n1_s<4, 6>(op, a, fuse, ndot);
-    default: return launch_n1_s<4, 4>(op, a, fuse, ndot);
-  }
+  if (variant == 44) return launch_n1_s<4, 4>(op, a, fuse, ndot);
+  return launch_n1_s<3, 4>(op, a, fuse, ndot);
 }
 
 }  // namespace glb
