@@ -116,6 +116,7 @@ def libs():
         "glb_cgm_update_p": (ci, [vp, ci, sz, ci, pd, pd, vp, C.POINTER(vp)]),
         "glb_cg_solve_supported": (ci, [vp]),
         "glb_cg_solve": (ci, [vp, vp, vp, ci, cd, C.POINTER(CgReport), pd, ci]),
+        "glb_op_apply_part": (ci, [vp, vp, vp, ci]),
         "glb_stag_eoprec_prepare": (ci, [vp, vp, vp]), "glb_stag_eoprec_reconstruct": (ci, [vp, vp, vp, vp]),
         "glb_mg_transfer_create": (ci, [vp, ci, ci, ci, ci, ci, ci, C.POINTER(vp), C.POINTER(vp)]),
         "glb_mg_transfer_destroy": (ci, [vp]), "glb_mg_fine_size": (sz, [vp]), "glb_mg_coarse_size": (sz, [vp]),
@@ -134,6 +135,7 @@ def libs():
                                       C.POINTER(Result)]),
         "glbx_dev_solve": (ci, [ci, vp, vp, vp, ci, cd, ci, ci, ci, C.POINTER(Result)]),
         "glbx_dev_solve_cg_m": (ci, [vp, C.POINTER(vp), vp, ci, ci, ci, cd, vp, ci, ci, C.POINTER(Result)]),
+        "glbx_host_stencil_part": (ci, [C.POINTER(OpDesc), ci, vp, vp]),
         "glbx_host_eoprec_prepare": (ci, [C.POINTER(OpDesc), vp, vp]),
         "glbx_host_eoprec_reconstruct": (ci, [C.POINTER(OpDesc), vp, vp, vp]),
         "glbx_host_solve_multi": (ci, [ci, C.POINTER(OpDesc), C.POINTER(vp), vp, ci, ci, ci, cd, vp, ci, ci,
@@ -250,6 +252,12 @@ class Operator:
         _chk(self.ctx.cu.glb_op_apply_dot(self.h, out.ptr, inp.ptr, w.ptr if w is not None else None,
                                           int(want_norm), d), "glb_op_apply_dot")
         return complex(d[0], d[1]), d[2]
+
+    PART = dict(EO=1, OE=2, TB=3, BT=4)
+
+    def apply_part(self, part, out, inp):
+        """glb_op_apply_part: apply_stencil_2d_{eo,oe,tb,bt} on a stencil2d operator (coarse_stencil.cpp:395-1512)"""
+        _chk(self.ctx.cu.glb_op_apply_part(self.h, out.ptr, inp.ptr, self.PART[part]), "glb_op_apply_part")
 
     def eoprec_prepare(self, rhs_e, rhs_orig):
         """glb_stag_eoprec_prepare: rhs_e = m rhs - D_eo rhs on even sites, 0 on odd (operators.cpp:528)"""
@@ -552,6 +560,11 @@ class Context:
     def host_apply(self, desc, rhs):
         out = np.empty_like(rhs)
         _chk(self.ho.glbx_host_apply(C.byref(desc), _p(out), _p(rhs)), "glbx_host_apply")
+        return out
+
+    def host_stencil_part(self, desc, part, rhs):
+        out = np.empty_like(rhs)
+        _chk(self.ho.glbx_host_stencil_part(C.byref(desc), Operator.PART[part], _p(out), _p(rhs)), "glbx_host_stencil_part")
         return out
 
     def host_eoprec_prepare(self, desc, rhs_orig):

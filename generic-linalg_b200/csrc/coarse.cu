@@ -431,6 +431,90 @@ static bool ring_enabled() {
   return enabled != 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// The partial applies of the preconditioned paths (coarse_stencil.cpp:395-1512, DIR_ALL):
+//   EO / OE : hopping term only, output on even / odd sites, the other parity zeroed        (:395, :560)
+//   TB / BT : clover + hopping (+ two-link) restricted to the top<-bottom / bottom<-top halves of the
+//             colour index: rows < nc/2 summed over c >= nc/2, or the mirror; other rows zeroed (:725, :1120)
+// No shifts.  One thread per output dof, reference accumulation order (bit-identical); these serve the e/o and
+// t/b preconditioned solves, not the headline path.
+__global__ void __launch_bounds__(256) coarse_part_kernel(const CoarseArgs a, const int part) {
+  const int nc = a.nc;
+  const int X = a.X;
+  const size_t L = (size_t)X * a.Yloc * nc;
+  const size_t plane = L * nc;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < L; i += (size_t)gridDim.x * blockDim.x) {
+    const int row = (int)(i % nc);
+    const size_t site = i / nc;
+    const int x = (int)(site % X), y = (int)(site / X);
+    cplx s = mk(0.0, 0.0);
+    int c0 = 0, c1 = nc;
+    bool live;
+    if (part == GLB_PART_EO || part == GLB_PART_OE) {
+      const bool even = (((x + y + a.y0) & 1) == 0);
+      live = (part == GLB_PART_EO) ? even : !even;
+    } else {
+      const bool top = row < nc / 2;
+      live = (part == GLB_PART_TB) ? top : !top;
+      c0 = (part == GLB_PART_TB) ? nc / 2 : 0;
+      c1 = (part == GLB_PART_TB) ? nc : nc / 2;
+    }
+    if (live) {
+      const int xp = (x + 1 == X) ? 0 : x + 1, xm = (x == 0) ? X - 1 : x - 1;
+      auto term = [&](const cplx* M, const cplx* v) {
+        for (int c = c0; c < c1; c++) s = fadd(s, fmul(__ldg(M + c), v[c]));
+      };
+      if (part == GLB_PART_TB || part == GLB_PART_BT) term(a.clover + i * nc, site_ptr(a, x, y));
+      const cplx* H = a.hopping + i * nc;
+      term(H, site_ptr(a, xp, y));
+      term(H + plane, site_ptr(a, x, y + 1));
+      term(H + 2 * plane, site_ptr(a, xm, y));
+      term(H + 3 * plane, site_ptr(a, x, y - 1));
+      if (a.has_two && (part == GLB_PART_TB || part == GLB_PART_BT)) {
+        const int xpp = (x + 2) % X, xmm = (x - 2 + 2 * X) % X;
+        const cplx* T = a.two_link + i * nc;
+        term(T, site_ptr(a, xpp, y));
+        term(T + plane, site_ptr(a, xp, y + 1));
+        term(T + 2 * plane, site_ptr(a, x, y + 2));
+        term(T + 3 * plane, site_ptr(a, xm, y + 1));
+        term(T + 4 * plane, site_ptr(a, xmm, y));
+        term(T + 5 * plane, site_ptr(a, xm, y - 1));
+        term(T + 6 * plane, site_ptr(a, x, y - 2));
+        term(T + 7 * plane, site_ptr(a, xp, y - 1));
+      }
+    }
+    a.out[i] = s;
+  }
+}
+
+int launch_stencil2d_part(glb_operator* op, void* out, const void* in, int part) {
+  glb_context* ctx = op->ctx;
+  if (part < GLB_PART_EO || part > GLB_PART_BT) return fail(GLB_ERR_ARG, "stencil2d: unknown partial apply");
+  CoarseArgs a{};
+  const size_t rowlen = (size_t)op->X * op->nc;
+  const bool single = (ctx->nranks == 1);
+  const int depth = op->has_two ? 2 : 1;
+  if (op->Yloc < depth) return fail(GLB_ERR_ARG, "stencil2d: slab thinner than the stencil reach");
+  a.in = (const cplx*)in;
+  a.in_lo = single ? (const cplx*)in + (size_t)(op->Yloc - depth) * rowlen : (const cplx*)op->ghost_lo;
+  a.in_hi = single ? (const cplx*)in : (const cplx*)op->ghost_hi;
+  a.out = (cplx*)out;
+  a.clover = op->clover;
+  a.hopping = op->hopping;
+  a.two_link = op->two_link;
+  a.X = op->X;
+  a.Yloc = op->Yloc;
+  a.y0 = op->y0;
+  a.nc = op->nc;
+  a.has_two = op->has_two ? 1 : 0;
+  const size_t L = rowlen * op->Yloc;
+  const int grid = blas_grid(ctx, L, 256, 1);
+  ProfScope prof(ctx, PROF_COARSE);
+  coarse_part_kernel<<<grid, 256, 0, ctx->stream>>>(a, part);
+  GLB_LAUNCH_CHECK();
+  return GLB_OK;
+}
+
 template <int NC>
 static int launch_coarse_nc(glb_context* ctx, const CoarseArgs& a, int ndot, size_t L) {
   const int grid = blas_grid(ctx, L, 256, 1);

@@ -22,7 +22,8 @@ namespace glb {
 
 constexpr int N1_THREADS = 128;
 constexpr int N1_WARPS = N1_THREADS / 32;
-constexpr int N1_OUT = 28;  // 32 loaded - 2 halo sites on each side
+// outputs per warp row = 32 - 2*HALO: HALO = 2 is the minimum (28 outputs); HALO = 4 makes every warp's stores whole
+// 128-byte lines (24 outputs = 384 bytes, line-aligned when X is a multiple of 8) at the price of more redundant loads
 
 // hopping term at this lane's site, reference order (operators.cpp:215-224); eta = -1 on odd x
 __device__ __forceinline__ cplx hop1(bool eta_neg, cplx ux, cplx ux_m, cplx uy, cplx uy_m, cplx psi_xp, cplx psi_xm,
@@ -49,8 +50,9 @@ __device__ __forceinline__ cplx row1(bool eta_neg, cplx below, cplx centre, cplx
   return fadd(fscale(0.5, h), fscale(mass, centre));
 }
 
-template <bool FUSE_XPAY, int NDOT, int STAGES, int MINB>
+template <bool FUSE_XPAY, int NDOT, int STAGES, int MINB, int HALO>
 __global__ void __launch_bounds__(N1_THREADS, MINB) normal1_kernel(const NormArgs a) {
+  constexpr int N1_OUT = 32 - 2 * HALO;
   extern __shared__ __align__(16) unsigned char ring_raw[];
   double beta = 0.0;
   if (a.cg != nullptr) {
@@ -64,7 +66,7 @@ __global__ void __launch_bounds__(N1_THREADS, MINB) normal1_kernel(const NormArg
   for (int i = 0; i < NRED; i++) acc[i] = 0.0;
 
   const int lane = threadIdx.x & 31;
-  const bool eta_neg = (lane & 1);  // windows start on even x (28*strip - 2)
+  const bool eta_neg = (lane & 1);  // windows start on even x (N1_OUT*strip - HALO, both even)
   const int X = a.X, Y = a.Y;
   const int nstrips = (X + N1_OUT - 1) / N1_OUT;
   const long long nitems = (long long)nstrips * a.nrb;
@@ -81,9 +83,9 @@ __global__ void __launch_bounds__(N1_THREADS, MINB) normal1_kernel(const NormArg
     const int ya = (int)((long long)Y * rb / a.nrb);
     const int yb = (int)((long long)Y * (rb + 1) / a.nrb);
     if (ya >= yb) continue;
-    const int xs = strip * N1_OUT - 2 + lane;
+    const int xs = strip * N1_OUT - HALO + lane;
     const int x0 = ((xs % X) + X) % X;
-    const bool active = (lane >= 2) && (lane <= 29) && (xs < X);
+    const bool active = (lane >= HALO) && (lane < 32 - HALO) && (xs < X);
 
     auto load_psi = [&](int y) -> cplx {  // the (possibly fused) input at row y, this lane's site
       if (slab && (y < 0 || y >= Y)) return (y < 0 ? a.g_lo + (size_t)(y + 2) * X : a.g_hi + (size_t)(y - Y) * X)[x0];
@@ -193,10 +195,11 @@ __global__ void __launch_bounds__(N1_THREADS, MINB) normal1_kernel(const NormArg
   }
 }
 
-template <bool FUSE, int NDOT, int STAGES, int MINB>
+template <bool FUSE, int NDOT, int STAGES, int MINB, int HALO>
 static int launch_n1_t(glb_operator* op, const NormArgs& a) {
   glb_context* ctx = op->ctx;
-  auto kern = normal1_kernel<FUSE, NDOT, STAGES, MINB>;
+  constexpr int N1_OUT = 32 - 2 * HALO;
+  auto kern = normal1_kernel<FUSE, NDOT, STAGES, MINB, HALO>;
   const size_t smem = (size_t)N1_WARPS * STAGES * (FUSE ? 4 : 3) * 32 * sizeof(cplx);
   static int per_sm = 0;
   if (per_sm == 0) {
@@ -222,23 +225,25 @@ static int launch_n1_t(glb_operator* op, const NormArgs& a) {
   return GLB_OK;
 }
 
-template <int STAGES, int MINB>
+template <int STAGES, int MINB, int HALO>
 static int launch_n1_s(glb_operator* op, const NormArgs& a, bool fuse, int ndot) {
   if (fuse) {
-    if (ndot == 0) return launch_n1_t<true, 0, STAGES, MINB>(op, a);
-    if (ndot == 1) return launch_n1_t<true, 1, STAGES, MINB>(op, a);
-    return launch_n1_t<true, 2, STAGES, MINB>(op, a);
+    if (ndot == 0) return launch_n1_t<true, 0, STAGES, MINB, HALO>(op, a);
+    if (ndot == 1) return launch_n1_t<true, 1, STAGES, MINB, HALO>(op, a);
+    return launch_n1_t<true, 2, STAGES, MINB, HALO>(op, a);
   }
-  if (ndot == 0) return launch_n1_t<false, 0, STAGES, MINB>(op, a);
-  if (ndot == 1) return launch_n1_t<false, 1, STAGES, MINB>(op, a);
-  return launch_n1_t<false, 2, STAGES, MINB>(op, a);
+  if (ndot == 0) return launch_n1_t<false, 0, STAGES, MINB, HALO>(op, a);
+  if (ndot == 1) return launch_n1_t<false, 1, STAGES, MINB, HALO>(op, a);
+  return launch_n1_t<false, 2, STAGES, MINB, HALO>(op, a);
 }
 
-// variant: 10*STAGES + min blocks per SM (GLB_NORMAL_SPT1): 34 = 3 stages, 4 blocks per SM (<= 128 registers).
-// Five or six blocks per SM force spills and measured slower (gpurun t08); they are not instantiated.
+// variant (GLB_NORMAL_SPT1): 10*STAGES + min blocks per SM.  34 = 3 stages, 4 blocks per SM (<= 128 registers).
+// Measured and not instantiated (gpurun t08, t09): five or six blocks per SM force spills (0.189 / 0.216 ms against
+// 0.184 ms for the plain kernel at 4096^2); HALO = 4 (24 outputs per warp row, every store a whole 128-byte line)
+// costs more in redundant loads than the aligned stores give back (0.219 ms).
 int launch_normal_spt1(glb_operator* op, const NormArgs& a, bool fuse, int ndot, int variant) {
-  if (variant == 44) return launch_n1_s<4, 4>(op, a, fuse, ndot);
-  return launch_n1_s<3, 4>(op, a, fuse, ndot);
+  if (variant == 44) return launch_n1_s<4, 4, 2>(op, a, fuse, ndot);
+  return launch_n1_s<3, 4, 2>(op, a, fuse, ndot);
 }
 
 }  // namespace glb

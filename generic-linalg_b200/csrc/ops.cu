@@ -341,6 +341,14 @@ int glb_op_apply(glb_operator* op, void* d_out, const void* d_in) {
   return apply_impl(op, d_out, d_in, none);
 }
 
+int glb_op_apply_part(glb_operator* op, void* d_out, const void* d_in, int part) {
+  if (!op || op->kind != OPK_STENCIL) return fail(GLB_ERR_ARG, "glb_op_apply_part needs a stencil2d operator");
+  if (d_out == d_in) return fail(GLB_ERR_ARG, "apply: output must not alias input");
+  int rc = halo_exchange(op, d_in, op->has_two ? 2 : 1);
+  if (rc) return rc;
+  return launch_stencil2d_part(op, d_out, d_in, part);
+}
+
 int glb_stag_eoprec_prepare(glb_operator* op, void* d_rhs_e, const void* d_rhs_orig) {
   if (!op || op->kind != OPK_STAGGERED || !op->has_links) return fail(GLB_ERR_ARG, "eoprec_prepare needs a gauged staggered operator");
   if (d_rhs_e == d_rhs_orig) return fail(GLB_ERR_ARG, "eoprec_prepare: output must not alias input");

@@ -179,6 +179,7 @@ int launch_gamma5(glb_operator* op, void* out, const void* in);
 bool normal_fused_ok(const glb_operator* op);
 int launch_normal(glb_operator* op, void* out, const void* in, const ApplyFusion& f);
 int launch_stencil2d(glb_operator* op, void* out, const void* in, const ApplyFusion& f);
+int launch_stencil2d_part(glb_operator* op, void* out, const void* in, int part);  // GLB_PART_*
 
 // comm.cu : fills op->ghost_lo / ghost_hi from the neighbouring ranks' boundary rows of `in`
 int halo_exchange(glb_operator* op, const void* in, int nrows);

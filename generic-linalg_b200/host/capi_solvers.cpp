@@ -217,6 +217,18 @@ int glbx_host_apply(const glbx_opdesc* d, void* lhs, const void* rhs) {
   return GLB_OK;
 }
 
+// apply_stencil_2d_{eo,oe,tb,bt} through the reference-named host functions (d: a stencil descriptor); part 1..4
+int glbx_host_stencil_part(const glbx_opdesc* d, int part, void* lhs, const void* rhs) {
+  HostOp h;
+  if (!build_host_op(d, &h) || !h.st) return GLB_ERR_ARG;
+  if (part == GLB_PART_EO) apply_stencil_2d_eo((zc*)lhs, (zc*)rhs, h.st);
+  else if (part == GLB_PART_OE) apply_stencil_2d_oe((zc*)lhs, (zc*)rhs, h.st);
+  else if (part == GLB_PART_TB) apply_stencil_2d_tb((zc*)lhs, (zc*)rhs, h.st);
+  else if (part == GLB_PART_BT) apply_stencil_2d_bt((zc*)lhs, (zc*)rhs, h.st);
+  else return GLB_ERR_ARG;
+  return GLB_OK;
+}
+
 // operators.cpp:528 / :574 through the reference-named host functions (d: any gauged staggered descriptor)
 int glbx_host_eoprec_prepare(const glbx_opdesc* d, void* rhs_e, const void* rhs_orig) {
   HostOp h;

@@ -74,5 +74,11 @@ struct stencil_2d {
 
 // stencil_2d/coarse_stencil.cpp:12   extra_data: stencil_2d*
 void apply_stencil_2d(complex<double>* lhs, complex<double>* rhs, void* extra_data);
+// coarse_stencil.cpp:395 / :560 / :725 / :1120 (sdir == DIR_ALL): hopping term between the site parities, and the
+// clover + hopping (+ two-link) blocks between the halves of the colour index; extra_data: stencil_2d*
+void apply_stencil_2d_eo(complex<double>* lhs, complex<double>* rhs, void* extra_data);
+void apply_stencil_2d_oe(complex<double>* lhs, complex<double>* rhs, void* extra_data);
+void apply_stencil_2d_tb(complex<double>* lhs, complex<double>* rhs, void* extra_data);
+void apply_stencil_2d_bt(complex<double>* lhs, complex<double>* rhs, void* extra_data);
 
 #endif

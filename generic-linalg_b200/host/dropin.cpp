@@ -355,6 +355,27 @@ void square_staggered_eoprec_reconstruct(zcplx* lhs_full, zcplx* lhs_e, zcplx* r
 void square_laplacian(double* lhs, double* rhs, void* e) { direct_apply<double>(B_LAPLACIAN_REAL, lhs, rhs, e); }
 void square_laplacian(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_LAPLACIAN_IMAG, lhs, rhs, e); }
 void apply_stencil_2d(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_STENCIL, lhs, rhs, e); }
+static void stencil_part(zcplx* lhs, zcplx* rhs, void* e, int part) {
+  try {
+    glb_context* ctx = glb200_default_context();
+    OpLease L;
+    lease(B_STENCIL, e, &L);
+    const size_t n = glb_op_local_size(L.op);
+    Blas<zcplx> B = {ctx, n};
+    Work<zcplx> W(B);
+    zcplx *d_in = W.get(), *d_out = W.get();
+    GLBX(glb_vec_upload(ctx, GLB_COMPLEX, n, d_in, rhs));
+    GLBX(glb_op_apply_part(L.op, d_out, d_in, part));
+    GLBX(glb_vec_download(ctx, GLB_COMPLEX, n, lhs, d_out));
+  } catch (const std::exception& ex) {
+    std::cerr << "[glb200] partial stencil apply failed: " << ex.what() << std::endl;
+    std::abort();
+  }
+}
+void apply_stencil_2d_eo(zcplx* lhs, zcplx* rhs, void* e) { stencil_part(lhs, rhs, e, GLB_PART_EO); }
+void apply_stencil_2d_oe(zcplx* lhs, zcplx* rhs, void* e) { stencil_part(lhs, rhs, e, GLB_PART_OE); }
+void apply_stencil_2d_tb(zcplx* lhs, zcplx* rhs, void* e) { stencil_part(lhs, rhs, e, GLB_PART_TB); }
+void apply_stencil_2d_bt(zcplx* lhs, zcplx* rhs, void* e) { stencil_part(lhs, rhs, e, GLB_PART_BT); }
 
 // operators_stencil.cpp:14-63 / :65-118 / :120-170 : hopping[+x] = -U_x/2, [+y] = -eta U_y/2,
 // [-x] = +conj U_x(x-1)/2, [-y] = +eta conj U_y(y-1)/2 ; gamma5 variant carries the site parity

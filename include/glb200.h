@@ -232,6 +232,17 @@ int glb_cg_solve_supported(const glb_operator* op);
 int glb_cg_solve(glb_operator* op, void* d_x, const void* d_b, int max_iter, double eps, glb_cg_report* rep,
                  double* rsq_hist, int hist_cap);
 
+/* ----------------------------------------------- partial stencil applies */
+/* apply_stencil_2d_eo / _oe / _tb / _bt (coarse_stencil.cpp:395, 560, 725, 1120; DIR_ALL) on a stencil2d operator:
+ *   EO, OE: hopping term only, output on even / odd sites, the other parity zeroed;
+ *   TB, BT: clover + hopping (+ two-link) from the bottom to the top half of the colour index (rows < nc/2 summed
+ *           over c >= nc/2) or the mirror, the other rows zeroed.  No shifts are applied. */
+#define GLB_PART_EO 1
+#define GLB_PART_OE 2
+#define GLB_PART_TB 3
+#define GLB_PART_BT 4
+int glb_op_apply_part(glb_operator* op, void* d_out, const void* d_in, int part);
+
 /* ----------------------------------------------- even/odd preconditioning */
 /* square_staggered_eoprec_prepare (operators.cpp:528-545): rhs_e = m rhs_orig - D_eo rhs_orig on even sites, 0 on
  * odd sites.  `op` is any gauged staggered operator (its links and mass are used). */

@@ -115,6 +115,10 @@ void ORC(op_apply)(void* op, double* lhs, const double* rhs);
 void ORC(eoprec_prepare)(void* op, double* rhs_e, const double* rhs_orig);
 void ORC(eoprec_reconstruct)(void* op, double* lhs_full, const double* lhs_e, const double* rhs_o);
 
+/* Partial stencil applies on an ORC_OP_STENCIL(_FROM_STAG) operator: part 1 apply_stencil_2d_eo, 2 _oe, 3 _tb,
+ * 4 _bt (coarse_stencil.cpp:395, 560, 725, 1120; DIR_ALL path). */
+void ORC(stencil_apply_part)(void* op, int part, double* lhs, const double* rhs);
+
 /* Solvers: phi is in/out (initial guess -> solution), phi0 the rhs.  verbosity:
  * 0 none .. 3 detail (verbosity.h:9-16), printed to stdout exactly as the reference does. */
 int ORC(solve)(int solver, void* op, double* phi, const double* phi0, int max_iter, double eps,

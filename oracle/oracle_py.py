@@ -71,6 +71,15 @@ class Operator:
         self.orc._f("op_apply")(self.h, _ptr(out), _ptr(rhs))
         return out
 
+    PART = dict(EO=1, OE=2, TB=3, BT=4)
+
+    def apply_part(self, part, rhs):
+        """apply_stencil_2d_{eo,oe,tb,bt} (coarse_stencil.cpp:395-1512) on a STENCIL operator"""
+        rhs = np.ascontiguousarray(rhs, dtype=np.complex128)
+        out = np.empty_like(rhs)
+        self.orc._f("stencil_apply_part")(self.h, self.PART[part], _ptr(out), _ptr(rhs))
+        return out
+
     def eoprec_prepare(self, rhs_orig):
         """operators.cpp:528 square_staggered_eoprec_prepare with this operator's links and mass"""
         rhs_orig = np.ascontiguousarray(rhs_orig, dtype=np.complex128)
@@ -110,6 +119,7 @@ class Oracle:
             "op_prepare": (vp, [C.POINTER(OpDesc)]), "op_free": (None, [vp]), "op_is_complex": (ci, [vp]),
             "op_size": (ci, [vp]), "op_apply": (None, [vp, vp, vp]),
             "eoprec_prepare": (None, [vp, vp, vp]), "eoprec_reconstruct": (None, [vp, vp, vp, vp]),
+            "stencil_apply_part": (None, [vp, ci, vp, vp]),
             "solve": (ci, [ci, vp, vp, vp, ci, cd, ci, ci, ci, C.POINTER(Result)]),
             "solve_cg_m": (ci, [vp, C.POINTER(vp), vp, ci, ci, ci, cd, vp, ci, ci, C.POINTER(Result)]),
         }

@@ -1071,6 +1071,47 @@ void port_op_apply(void* opv, double* lhs, const double* rhs) {
     apply_r(op, lhs, rhs);
 }
 
+// coarse_stencil.cpp:395-1512 (DIR_ALL): eo / oe = hopping on one parity; tb / bt = clover + hopping (+ two-link)
+// between the halves of the colour index.  Same accumulation order as op_stencil, no shifts.
+void port_stencil_apply_part(void* opv, int part, double* lhs_, const double* rhs_) {
+  PortOp& op = *(PortOp*)opv;
+  cplx* out = (cplx*)lhs_;
+  const cplx* in = (const cplx*)rhs_;
+  const int X = op.d.X, Y = op.d.Y, nc = op.nc;
+  const int L = X * Y * nc;
+  static const int hop_dx[4] = {1, 0, -1, 0}, hop_dy[4] = {0, 1, 0, -1};
+  static const int two_dx[8] = {2, 1, 0, -1, -2, -1, 0, 1}, two_dy[8] = {0, 1, 2, 1, 0, -1, -2, -1};
+  for (int i = 0; i < L; i++) {
+    out[i] = 0.0;
+    const int row = i % nc, site = i / nc, x = site % X, y = site / X;
+    int c0 = 0, c1 = nc;
+    bool live;
+    const bool colour_split = (part == 3 || part == 4);
+    if (!colour_split) {
+      const bool even = ((x + y) % 2 == 0);
+      live = (part == 1) ? even : !even;
+    } else {
+      const bool top = row < nc / 2;
+      live = (part == 3) ? top : !top;
+      c0 = (part == 3) ? nc / 2 : 0;
+      c1 = (part == 3) ? nc : nc / 2;
+    }
+    if (!live) continue;
+    if (colour_split)
+      for (int c = c0; c < c1; c++) out[i] += op.clover[c + nc * i] * in[site * nc + c];
+    for (int d = 0; d < 4; d++) {
+      const int xn = (x + hop_dx[d] + X) % X, yn = (y + hop_dy[d] + Y) % Y;
+      for (int c = c0; c < c1; c++) out[i] += op.hopping[c + nc * i + d * nc * L] * in[(yn * X + xn) * nc + c];
+    }
+    if (colour_split && op.has_two) {
+      for (int d = 0; d < 8; d++) {
+        const int xn = (x + two_dx[d] + 2 * X) % X, yn = (y + two_dy[d] + 2 * Y) % Y;
+        for (int c = c0; c < c1; c++) out[i] += op.two_link[c + nc * i + d * nc * L] * in[(yn * X + xn) * nc + c];
+      }
+    }
+  }
+}
+
 void port_eoprec_prepare(void* opv, double* rhs_e, const double* rhs_orig) {
   PortOp* op = (PortOp*)opv;
   op_eoprec_prepare((cplx*)rhs_e, (const cplx*)rhs_orig, (const cplx*)op->d.links, op->d.X, op->d.Y, op->d.mass);

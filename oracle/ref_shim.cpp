@@ -239,6 +239,13 @@ void ref_op_apply(void* opv, double* lhs, const double* rhs) {
     apply_r(op, lhs, (double*)rhs);
 }
 
+void ref_stencil_apply_part(void* opv, int part, double* lhs, const double* rhs) {
+  RefOp* op = (RefOp*)opv;
+  if (part == 1) apply_stencil_2d_eo((cplx*)lhs, (cplx*)rhs, (void*)op->stenc);
+  if (part == 2) apply_stencil_2d_oe((cplx*)lhs, (cplx*)rhs, (void*)op->stenc);
+  if (part == 3) apply_stencil_2d_tb((cplx*)lhs, (cplx*)rhs, (void*)op->stenc);
+  if (part == 4) apply_stencil_2d_bt((cplx*)lhs, (cplx*)rhs, (void*)op->stenc);
+}
 void ref_eoprec_prepare(void* opv, double* rhs_e, const double* rhs_orig) {
   RefOp* op = (RefOp*)opv;
   square_staggered_eoprec_prepare((cplx*)rhs_e, (cplx*)rhs_orig, (void*)&op->stagif);

@@ -98,3 +98,41 @@ def test_shells_on_mock_bit_identical():
     x = np.empty_like(b)
     assert lib.glbx_host_eoprec_reconstruct(C.byref(desc("STAG_U1")), p(x), p(xe), p(b)) == 0
     assert np.array_equal(x, D.eoprec_reconstruct(xo, b))
+
+
+@pytest.mark.skipif("ref" not in oracle_py.available(), reason="needs oracle/_ref")
+@pytest.mark.parametrize("X,Y,nc,two", [(6, 8, 4, False), (8, 6, 2, True), (5, 7, 3, True), (4, 4, 1, False), (8, 8, 8, False)])
+def test_partial_stencil_applies_port_equals_reference(X, Y, nc, two):
+    """apply_stencil_2d_{eo,oe,tb,bt} (coarse_stencil.cpp:395-1512): port == reference, bit for bit"""
+    ref, port = oracle_py.load("ref"), oracle_py.load("port")
+    rg = np.random.default_rng(X * 100 + nc)
+    rc = lambda n: rg.standard_normal(n) + 1j * rg.standard_normal(n)
+    V = X * Y
+    cl, hp, tl, v = rc(V * nc * nc), rc(4 * V * nc * nc), (rc(8 * V * nc * nc) if two else None), rc(V * nc)
+    kw = dict(Nc=nc, clover=cl, hopping=hp, two_link=tl, shift=0.3, eo_shift=0.1j, dof_shift=0.2)
+    a, b = ref.op("STENCIL", X, Y, **kw), port.op("STENCIL", X, Y, **kw)
+    for part in ("EO", "OE", "TB", "BT"):
+        assert np.array_equal(a.apply_part(part, v), b.apply_part(part, v))
+
+
+def test_partial_stencil_identities(orc):
+    """on the staggered stencil: D = m + D_eo + D_oe, and the function operators' even/odd pieces equal the stencil's
+    (tests/staggered_pieces/staggered_pieces.cpp TEST 9-10); on any stencil the four colour blocks add up:
+    (tt + bb) + tb + bt = clover + hopping, checked through linearity"""
+    L, m = 8, 0.2
+    U, b = synthetic(orc, L)
+    S = orc.op("STENCIL_FROM_STAG", L, L, mass=m, links=U)
+    assert np.allclose(S.apply(b), m * b + S.apply_part("EO", b) + S.apply_part("OE", b), rtol=0, atol=1e-14)
+    assert np.allclose(S.apply_part("EO", b), orc.op("STAG_DEO_U1", L, L, mass=m, links=U).apply(b), rtol=0, atol=1e-15)
+    assert np.allclose(S.apply_part("OE", b), orc.op("STAG_DOE_U1", L, L, mass=m, links=U).apply(b), rtol=0, atol=1e-15)
+    rg = np.random.default_rng(5)
+    nc, V = 4, L * L
+    rc = lambda n: rg.standard_normal(n) + 1j * rg.standard_normal(n)
+    T = orc.op("STENCIL", L, L, Nc=nc, clover=rc(V * nc * nc), hopping=rc(4 * V * nc * nc))
+    v = rc(V * nc)
+    top = (np.arange(V * nc) % nc) < nc // 2
+    vt, vb = np.where(top, v, 0), np.where(~top, v, 0)
+    full = T.apply(v)
+    # rows of the top half: T v = (T vt)_top + tb(v);  rows of the bottom half likewise with bt
+    assert np.allclose(np.where(top, full, 0), np.where(top, T.apply(vt), 0) + T.apply_part("TB", v), rtol=0, atol=1e-13)
+    assert np.allclose(np.where(~top, full, 0), np.where(~top, T.apply(vb), 0) + T.apply_part("BT", v), rtol=0, atol=1e-13)

@@ -56,3 +56,22 @@ def test_even_odd_preconditioned_solve(ctx, glb, orc, L, m):
     plain = ctx.solve("CG", N, xn, bp, max_iter=20000, eps=1e-10)
     assert got["iter"] <= plain["iter"] + 1
     assert rel_err(xs, xn.download()) < 1e-6
+
+
+@pytest.mark.parametrize("X,Y,nc,two", [(6, 8, 4, False), (8, 6, 2, True), (5, 7, 3, True), (64, 64, 8, False), (32, 48, 8, True)])
+def test_partial_stencil_applies_bit_exact(ctx, glb, orc, X, Y, nc, two):
+    """glb_op_apply_part and the reference-named host entry points apply_stencil_2d_{eo,oe,tb,bt}"""
+    rg = np.random.default_rng(X * 100 + nc)
+    rc = lambda n: rg.standard_normal(n) + 1j * rg.standard_normal(n)
+    V = X * Y
+    cl, hp, tl, v = rc(V * nc * nc), rc(4 * V * nc * nc), (rc(8 * V * nc * nc) if two else None), rc(V * nc)
+    kw = dict(shift=0.3, eo_shift=0.1j, dof_shift=0.2)
+    oop = orc.op("STENCIL", X, Y, Nc=nc, clover=cl, hopping=hp, two_link=tl, **kw)
+    op = ctx.stencil2d(cl, hp, tl, X, Y, nc, **kw)
+    dv, out = ctx.vector(V * nc).upload(v), ctx.vector(V * nc)
+    d = ctx._desc("STENCIL", X, Y, Nc=nc, clover=cl, hopping=hp, two_link=tl, **kw)
+    for part in ("EO", "OE", "TB", "BT"):
+        want = oop.apply_part(part, v)
+        op.apply_part(part, out, dv)
+        assert np.array_equal(out.download(), want)
+        assert np.array_equal(ctx.host_stencil_part(d, part, v), want)
