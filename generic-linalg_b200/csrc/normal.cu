@@ -28,40 +28,6 @@ constexpr int NORM_WARPS = NORM_THREADS / 32;
 constexpr int NORM_OUT_PER_WARP = 60;  // 64 loaded - 2 halo sites on each side
 
 
-// hopping part of the staggered stencil at one site, reference order (operators.cpp:215-224):
-//   h = -U_x(x) psi(x+1) + conj U_x(x-1) psi(x-1) - eta U_y(x,y) psi(y+1) + eta conj U_y(x,y-1) psi(y-1)
-template <bool ETA_NEG>
-__device__ __forceinline__ cplx stag_hop(cplx ux, cplx ux_m, cplx uy, cplx uy_m, cplx psi_xp, cplx psi_xm, cplx psi_yp,
-                                         cplx psi_ym) {
-  cplx h = mk(0.0, 0.0);
-  h = fsub(h, fmul(ux, psi_xp));
-  h = fadd(h, fcmul(ux_m, psi_xm));
-  const cplx t3 = fmul(uy, psi_yp);
-  h = ETA_NEG ? fadd(h, t3) : fsub(h, t3);
-  const cplx t4 = fcmul(uy_m, psi_ym);
-  h = ETA_NEG ? fsub(h, t4) : fadd(h, t4);
-  return h;
-}
-
-// one full row of D (DAGGER=false) or D^dag (DAGGER=true) on this lane's pair of sites.
-// below/centre/above: the three input rows; the x neighbours of `centre` come from the warp.
-template <bool DAGGER>
-__device__ __forceinline__ void stag_row(cplx (&res)[2], const cplx (&below)[2], const cplx (&centre)[2],
-                                         const cplx (&above)[2], const cplx (&ux)[2], cplx ux_left,
-                                         const cplx (&uy)[2], const cplx (&uy_below)[2], double mass) {
-  const cplx left = shfl_up_c(centre[1], 1);     // psi(x0-1)
-  const cplx right = shfl_down_c(centre[0], 1);  // psi(x0+2)
-  // site 0 sits on an even x (eta = +1), site 1 on an odd x (eta = -1): pairs start on even sites
-  cplx h0 = stag_hop<false>(ux[0], ux_left, uy[0], uy_below[0], centre[1], left, above[0], below[0]);
-  cplx h1 = stag_hop<true>(ux[1], ux[0], uy[1], uy_below[1], right, centre[0], above[1], below[1]);
-  if (DAGGER) {
-    h0 = fneg(h0);
-    h1 = fneg(h1);
-  }
-  res[0] = fadd(fscale(0.5, h0), fscale(mass, centre[0]));
-  res[1] = fadd(fscale(0.5, h1), fscale(mass, centre[1]));
-}
-
 template <bool FUSE>
 struct NormLoad {  // everything fetched one row ahead: psi(y+2) (raw), U(y+1)
   cplx a[2];
@@ -445,6 +411,15 @@ int launch_normal(glb_operator* op, void* out, const void* in, const ApplyFusion
     stages_fused = e ? atoi(e) : 4;
     const char* e2 = getenv("GLB_NORMAL_STAGES_PLAIN");
     stages_plain = e2 ? atoi(e2) : 0;
+  }
+  {
+    // chunked self-scheduling (normal_ws.cu): GLB_NORMAL_WS = 1 for the fused kernel, 2 for the plain one too
+    static int wsm = -1;
+    if (wsm < 0) {
+      const char* e = getenv("GLB_NORMAL_WS");
+      wsm = e ? atoi(e) : 0;
+    }
+    if ((wsm >= 1 && fuse) || wsm >= 2) return launch_normal_ws(op, a, fuse, ndot);
   }
   {
     // one site per thread (normal1.cu): GLB_NORMAL_SPT1 = 10*stages + min blocks per SM, 0 = off
