@@ -413,15 +413,6 @@ int launch_normal(glb_operator* op, void* out, const void* in, const ApplyFusion
     stages_plain = e2 ? atoi(e2) : 0;
   }
   {
-    // chunked self-scheduling (normal_ws.cu): GLB_NORMAL_WS = 1 for the fused kernel, 2 for the plain one too
-    static int wsm = -1;
-    if (wsm < 0) {
-      const char* e = getenv("GLB_NORMAL_WS");
-      wsm = e ? atoi(e) : 0;
-    }
-    if ((wsm >= 1 && fuse) || wsm >= 2) return launch_normal_ws(op, a, fuse, ndot);
-  }
-  {
     // one site per thread (normal1.cu): GLB_NORMAL_SPT1 = 10*stages + min blocks per SM, 0 = off
     // Measured at 4096^2 (gpurun t08): the plain kernel runs at 0.183 ms = 5850 GB/s (89 % of the copy peak)
     // in this shape against 0.209 ms with two sites per thread; the variant with the fused CG direction update

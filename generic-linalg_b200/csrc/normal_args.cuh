@@ -29,9 +29,6 @@ struct NormArgs {
   int cg_role;
 };
 
-// normal_ws.cu: the two-sites-per-thread shape with chunked self-scheduling (work stealing)
-int launch_normal_ws(glb_operator* op, const NormArgs& a, bool fuse, int ndot);
-
 #ifdef __CUDACC__
 // hopping part of the staggered stencil at one site, reference order (operators.cpp:215-224):
 //   h = -U_x(x) psi(x+1) + conj U_x(x-1) psi(x-1) - eta U_y(x,y) psi(y+1) + eta conj U_y(x,y-1) psi(y-1)

@@ -68,9 +68,6 @@ int glb_destroy(glb_context* ctx) {
   cudaStreamSynchronize(ctx->stream);
   glb_prof_enable(ctx, 1);  // drops recorded events
   comm_destroy(ctx);
-  cudaFree(ctx->ws_cnt);
-  cudaFree(ctx->ws_part);
-  cudaFree(ctx->ws_ticket);
   cudaFree(ctx->red.partials);
   cudaFree(ctx->red.ticket);
   cudaFree(ctx->red.result_dev);

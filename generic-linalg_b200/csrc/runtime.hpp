@@ -67,11 +67,6 @@ struct glb_context {
   // slab communicator
   int rank = 0, nranks = 1;
   glb::Comm* comm = nullptr;
-  // workspace of the self-scheduling one-pass kernel (normal_ws.cu): claim counters, per-chunk partials, ticket
-  int* ws_cnt = nullptr;
-  double* ws_part = nullptr;
-  unsigned int* ws_ticket = nullptr;
-  size_t ws_cnt_n = 0, ws_part_n = 0;
   // kernel timing (off by default)
   bool prof_on = false;
   std::vector<glb::ProfRec> prof;

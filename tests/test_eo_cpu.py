@@ -136,3 +136,27 @@ def test_partial_stencil_identities(orc):
     # rows of the top half: T v = (T vt)_top + tb(v);  rows of the bottom half likewise with bt
     assert np.allclose(np.where(top, full, 0), np.where(top, T.apply(vt), 0) + T.apply_part("TB", v), rtol=0, atol=1e-13)
     assert np.allclose(np.where(~top, full, 0), np.where(~top, T.apply(vb), 0) + T.apply_part("BT", v), rtol=0, atol=1e-13)
+
+
+def test_partial_stencil_host_entry_points_on_mock():
+    """apply_stencil_2d_{eo,oe,tb,bt} of host/coarse_stencil.h on the CPU mock == the oracle"""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "mock")], stdout=subprocess.DEVNULL)
+    glb = load_pkg()
+    lib = C.CDLL(MOCK, mode=C.RTLD_LOCAL)
+    vp, ci = C.c_void_p, C.c_int
+    lib.glbx_host_stencil_part.argtypes = [C.POINTER(glb.OpDesc), ci, vp, vp]
+    orc = oracle_py.load("best")
+    X, Y, nc = 6, 8, 4
+    V = X * Y
+    rg = np.random.default_rng(8)
+    rc = lambda n: rg.standard_normal(n) + 1j * rg.standard_normal(n)
+    cl, hp, tl, v = rc(V * nc * nc), rc(4 * V * nc * nc), rc(8 * V * nc * nc), rc(V * nc)
+    p = lambda a: a.ctypes.data_as(vp)
+    d = glb.OpDesc()
+    d.kind, d.X, d.Y, d.Nc, d.mass = glb.OP["STENCIL"], X, Y, nc, 0.0
+    d.clover, d.hopping, d.two_link, d.has_two = p(cl), p(hp), p(tl), 1
+    oop = orc.op("STENCIL", X, Y, Nc=nc, clover=cl, hopping=hp, two_link=tl)
+    for part, code in (("EO", 1), ("OE", 2), ("TB", 3), ("BT", 4)):
+        out = np.empty_like(v)
+        assert lib.glbx_host_stencil_part(C.byref(d), code, p(out), p(v)) == 0
+        assert np.array_equal(out, oop.apply_part(part, v))
