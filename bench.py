@@ -441,7 +441,7 @@ def main():
                          {"kernel": "stag_kernel (staggered D apply alone, 64 B/site; the metric's 'Dirac apply GB/s')",
                           "achieved": apply_gbps, "frac": apply_gbps / peak, "ms_per_launch": apply_ms,
                           "traffic": ncu_traffic("stag_kernel", L), "how": "loop of %d applies" % args.apply_reps},
-                         {"kernel": "normal_kernel (D^dag D alone in one pass, 64 B/site)",
+                         {"kernel": "normal1_kernel (D^dag D alone in one pass, one site per thread, 64 B/site)",
                           "achieved": normal_gbps, "frac": normal_gbps / peak, "ms_per_launch": normal_ms,
                           "traffic": ncu_traffic("normal_kernel", L), "how": "loop of %d applies" % args.apply_reps}]},
         "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": int(2 * 16 * V_local),

@@ -24,6 +24,6 @@ echo "== ncu launch list" | tee -a $OUT/summary.txt
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/launches.csv \
    python bench.py --steps 1 --warmup 3 --no-cpu --apply-reps 5 > $OUT/ncu_bench.log 2>&1; echo "ncu list rc=$?" | tee -a $OUT/summary.txt
 echo "== ncu full (normal_kernel, cg_update, stag_kernel)" | tee -a $OUT/summary.txt
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"normal_kernel|cg_update_kernel|stag_kernel" -s 10 -c 16 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"normal_kernel|normal1_kernel|cg_update_kernel|stag_kernel" -s 10 -c 16 \
    -o $OUT/prof_top python bench.py --steps 1 --warmup 3 --no-cpu --apply-reps 5 > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?" | tee -a $OUT/summary.txt
 ls -la $OUT | tee -a $OUT/summary.txt

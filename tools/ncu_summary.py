@@ -17,6 +17,9 @@ def short(name):
     m = re.search(r"normal_kernel<[^>]*>", name)
     if m:
         return m.group(0)
+    m = re.search(r"normal1_kernel<[^>]*>", name)
+    if m:
+        return m.group(0)
     m = re.search(r"coarse_ring_kernel<[^>]*>", name)
     if m:
         return m.group(0)
@@ -28,7 +31,7 @@ def short(name):
 
 def traffic_key(name):
     """bench.py's name for the kernels whose DRAM traffic it reports (profiles/ncu_traffic.json)"""
-    m = re.match(r"normal_kernel<([01]),", name)
+    m = re.match(r"normal1?_kernel<([01]),", name)
     if m:
         return "normal_kernel_fused" if m.group(1) == "1" else "normal_kernel"
     if name.startswith("cg_update_kernel"):
