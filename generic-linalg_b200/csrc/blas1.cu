@@ -192,6 +192,12 @@ struct FBicgP {  // p = r + beta*(p - omega*Ap)     vectors: r, Ap, p    (generi
   __device__ void elem(T (&e)[NV], double*) const { e[2] = fadd(e[0], fmul(beta, fsub(e[2], fmul(omega, e[1])))); }
 };
 template <typename T>
+struct FRscale {  // out = s*x, real s       vectors: x, out   (generic_vector.h normalize)
+  static constexpr int NV = 2, RD = 1, WR = 2, NRED = 0;
+  double s;
+  __device__ void elem(T (&e)[NV], double*) const { e[1] = fscale(s, e[0]); }
+};
+template <typename T>
 struct FConj {  // out = conj(x)   (a copy for real fields)     vectors: x, out    (generic_vector.h conj<>)
   static constexpr int NV = 2, RD = 1, WR = 2, NRED = 0;
   __device__ static double cj(double a) { return a; }
@@ -605,6 +611,11 @@ int glb_bicgstab_pupdate(glb_context* ctx, int dtype, size_t n, const void* r, c
     f.beta = coef<decltype(f.beta)>(beta);
     f.omega = coef<decltype(f.omega)>(omega);
   });
+}
+
+int glb_rscale(glb_context* ctx, int dtype, size_t n, const void* x, double sc, void* out) {
+  VecPtrs<2> v{{(void*)x, out}};
+  return ew_call<FRscale, 2>(ctx, dtype, n, false, v, [&](auto& f) { f.s = sc; });
 }
 
 int glb_conj(glb_context* ctx, int dtype, size_t n, const void* x, void* out) {

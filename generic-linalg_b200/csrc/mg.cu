@@ -77,6 +77,120 @@ __global__ void __launch_bounds__(256) mg_restrict_kernel(const MgArgs a, cplx* 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Set-up on the device.
+//
+// block_orthonormalize + block_normalize (mg_complex.cpp:191-370): one thread owns one block and runs the
+// reference's loops in its order (normalise vector v-1, project v against 0..v-1, ..., final normalisation), so the
+// result is bit-identical to the CPU code.  The null vectors are nvec separate device arrays (the reference layout).
+struct MgNullPtrs {
+  cplx* v[32];
+};
+__global__ void __launch_bounds__(128) mg_block_orthonormalize_kernel(const MgNullPtrs n, int Xf, int dof_f, int bx, int by,
+                                                                      int nvec, int Xc, int Yc) {
+  const size_t nb = (size_t)Xc * Yc;
+  for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (size_t)gridDim.x * blockDim.x) {
+    const int x_lo = (int)(b % Xc) * bx, y_lo = (int)(b / Xc) * by;
+    auto for_sites = [&](auto fn) {
+      for (int y = y_lo; y < y_lo + by; y++)
+        for (int x = x_lo; x < x_lo + bx; x++)
+          for (int d = 0; d < dof_f; d++) fn(((size_t)y * Xf + x) * dof_f + d);
+    };
+    auto normalise = [&](cplx* v) {
+      double nrm = 0.0;
+      for_sites([&](size_t f) { nrm = xadd(nrm, fnorm(v[f])); });
+      nrm = sqrt(nrm);
+      for_sites([&](size_t f) { v[f] = frdiv(v[f], nrm); });
+    };
+    for (int c = 1; c < nvec; c++) {
+      normalise(n.v[c - 1]);
+      for (int m = 0; m < c; m++) {
+        cplx dot = mk(0.0, 0.0);
+        for_sites([&](size_t f) { dot = fadd(dot, fcmul(n.v[m][f], n.v[c][f])); });
+        for_sites([&](size_t f) { n.v[c][f] = fsub(n.v[c][f], fmul(dot, n.v[m][f])); });
+      }
+    }
+    for (int c = 0; c < nvec; c++) normalise(n.v[c]);  // block_normalize (mg_complex.cpp:191-256)
+  }
+}
+
+// null_partition_staggered / null_partition_coarse, BLOCK_EO (null_gen.cpp:26-35, :109-126): the odd part of `even_io`
+// (odd sites on the top level, upper half of the colour index below it) moves to `odd_out` and is zeroed in place.
+__global__ void mg_partition_kernel(cplx* __restrict__ even_io, cplx* __restrict__ odd_out, size_t n, int X, int dof, int y0,
+                                    int by_colour) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    bool odd;
+    if (by_colour) {
+      odd = (int)(i % dof) >= dof / 2;
+    } else {
+      const size_t site = i / dof;
+      odd = ((site % X + site / X + y0) & 1) != 0;
+    }
+    if (odd) {
+      odd_out[i] = even_io[i];
+      even_io[i] = mk(0.0, 0.0);
+    }
+  }
+}
+
+// Galerkin coarse operator P^dag A P of a five-point fine stencil (what generate_coarse_from_fine_stencil,
+// mg_complex.cpp:827-1026, assembles by probing; ignore_shifts = false: the fine shifts end up in the coarse clover).
+// One thread per (coarse site, i, j): sums conj(n_i[f,a]) M[f][a,b] n_j[g,b] over the fine dofs of the block; a hop
+// that stays inside the block feeds the coarse clover, one that leaves it the coarse hopping term of that direction.
+struct MgFine {
+  const cplx* clover;
+  const cplx* hopping;
+  cplx shift, eo_shift, dof_shift;
+  int use_shift, use_eo, use_dof;
+};
+__global__ void __launch_bounds__(128) mg_galerkin_kernel(const MgArgs a, const MgFine fs, cplx* __restrict__ cl_c,
+                                                          cplx* __restrict__ hp_c) {
+  const int nv = a.nvec, df = a.dof_f;
+  const size_t nc_sites = (size_t)a.Xc * a.Yc;
+  const size_t total = nc_sites * nv * nv;
+  const size_t Lf = (size_t)a.Xf * a.Yf * df;     // fine dofs
+  const size_t Lc = nc_sites * nv;                // coarse dofs
+  for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(id % nv), i = (int)((id / nv) % nv);
+    const size_t cs = id / ((size_t)nv * nv);
+    const int xc = (int)(cs % a.Xc), yc = (int)(cs / a.Xc);
+    cplx acc_c = mk(0.0, 0.0), acc_h[4] = {mk(0.0, 0.0), mk(0.0, 0.0), mk(0.0, 0.0), mk(0.0, 0.0)};
+    for (int y = yc * a.by; y < (yc + 1) * a.by; y++) {
+      for (int x = xc * a.bx; x < (xc + 1) * a.bx; x++) {
+        const size_t site = (size_t)y * a.Xf + x;
+        const int xn[4] = {(x + 1 == a.Xf) ? 0 : x + 1, x, (x == 0) ? a.Xf - 1 : x - 1, x};
+        const int yn[4] = {y, (y + 1 == a.Yf) ? 0 : y + 1, y, (y == 0) ? a.Yf - 1 : y - 1};
+        const bool inside[4] = {(x + 1) % a.bx != 0, (y + 1) % a.by != 0, x % a.bx != 0, y % a.by != 0};
+        for (int r = 0; r < df; r++) {
+          const size_t f = site * df + r;
+          const cplx ci = a.null[f * nv + i];
+          // diagonal part: clover row + the shifts (coarse_stencil.cpp:153-169)
+          cplx row = mk(0.0, 0.0);
+          for (int c = 0; c < df; c++) row = fadd(row, fmul(fs.clover[c + df * f], a.null[(site * df + c) * nv + j]));
+          const cplx self = a.null[f * nv + j];
+          if (fs.use_shift) row = fadd(row, fmul(fs.shift, self));
+          if (fs.use_eo) row = fadd(row, fmul(((x + y) & 1) ? fneg(fs.eo_shift) : fs.eo_shift, self));
+          if (fs.use_dof) row = fadd(row, fmul(r < df / 2 ? fs.dof_shift : fneg(fs.dof_shift), self));
+          acc_c = fadd(acc_c, fcmul(ci, row));
+          for (int d = 0; d < 4; d++) {
+            const size_t g = ((size_t)yn[d] * a.Xf + xn[d]) * df;
+            cplx h = mk(0.0, 0.0);
+            for (int c = 0; c < df; c++) h = fadd(h, fmul(fs.hopping[c + df * f + d * df * Lf], a.null[(g + c) * nv + j]));
+            if (inside[d])
+              acc_c = fadd(acc_c, fcmul(ci, h));
+            else
+              acc_h[d] = fadd(acc_h[d], fcmul(ci, h));
+          }
+        }
+      }
+    }
+    const size_t o = (cs * nv + i) * nv + j;  // clover[c + nc*i'] with i' = cs*nc + i (coarse_stencil.h:41)
+    cl_c[o] = acc_c;
+#pragma unroll
+    for (int d = 0; d < 4; d++) hp_c[o + (size_t)d * nv * Lc] = acc_h[d];
+  }
+}
+
 // host arrays null_vectors[v][f] -> device null[f*nvec + v]
 __global__ void mg_interleave_kernel(cplx* __restrict__ dst, const cplx* __restrict__ src, size_t nf, int nvec, int v) {
   for (size_t f = (size_t)blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += (size_t)gridDim.x * blockDim.x)
@@ -86,6 +200,20 @@ __global__ void mg_interleave_kernel(cplx* __restrict__ dst, const cplx* __restr
 }  // namespace glb
 
 using namespace glb;
+
+static MgArgs mg_args(const glb_mg_transfer* t) {
+  MgArgs a;
+  a.null = t->null;
+  a.Xf = t->Xf;
+  a.Yf = t->Yf;
+  a.dof_f = t->dof_f;
+  a.bx = t->bx;
+  a.by = t->by;
+  a.nvec = t->nvec;
+  a.Xc = t->Xc;
+  a.Yc = t->Yc;
+  return a;
+}
 
 extern "C" {
 
@@ -137,6 +265,94 @@ int glb_mg_transfer_create(glb_context* ctx, int Xf, int Yf, int dof_f, int bx, 
   return GLB_OK;
 }
 
+// the same from DEVICE-resident null vectors (after glb_mg_block_orthonormalize)
+int glb_mg_transfer_create_dev(glb_context* ctx, int Xf, int Yf, int dof_f, int bx, int by, int nvec,
+                               const void* const* d_null_vectors, glb_mg_transfer** out) {
+  if (!ctx || !d_null_vectors || !out) return fail(GLB_ERR_ARG, "glb_mg_transfer_create_dev: null argument");
+  if (Xf < 1 || Yf < 1 || dof_f < 1 || bx < 1 || by < 1 || nvec < 1 || Xf % bx != 0 || Yf % by != 0)
+    return fail(GLB_ERR_ARG, "glb_mg_transfer_create_dev: bad extents");
+  GLB_CUDA(cudaSetDevice(ctx->device));
+  glb_mg_transfer* t = new glb_mg_transfer();
+  t->ctx = ctx;
+  t->Xf = Xf;
+  t->Yf = Yf;
+  t->dof_f = dof_f;
+  t->bx = bx;
+  t->by = by;
+  t->nvec = nvec;
+  t->Xc = Xf / bx;
+  t->Yc = Yf / by;
+  const size_t nf = (size_t)Xf * Yf * dof_f;
+  if (cudaMalloc(&t->null, nf * nvec * sizeof(cplx)) != cudaSuccess) {
+    delete t;
+    return fail(GLB_ERR_CUDA, "glb_mg_transfer_create_dev: out of device memory");
+  }
+  const int grid = blas_grid(ctx, nf, 256, 1);
+  for (int v = 0; v < nvec; v++)
+    mg_interleave_kernel<<<grid, 256, 0, ctx->stream>>>(t->null, (const cplx*)d_null_vectors[v], nf, nvec, v);
+  GLB_LAUNCH_CHECK();
+  *out = t;
+  return GLB_OK;
+}
+
+int glb_mg_block_orthonormalize(glb_context* ctx, int Xf, int Yf, int dof_f, int bx, int by, int nvec,
+                                void* const* d_null_vectors) {
+  if (!ctx || !d_null_vectors) return fail(GLB_ERR_ARG, "glb_mg_block_orthonormalize: null argument");
+  if (nvec < 1 || nvec > 32) return fail(GLB_ERR_ARG, "glb_mg_block_orthonormalize: 1..32 null vectors");
+  if (Xf % bx != 0 || Yf % by != 0) return fail(GLB_ERR_ARG, "glb_mg_block_orthonormalize: the block size must divide the lattice");
+  MgNullPtrs n{};
+  for (int v = 0; v < nvec; v++) n.v[v] = (cplx*)d_null_vectors[v];
+  const size_t nb = (size_t)(Xf / bx) * (Yf / by);
+  const int grid = blas_grid(ctx, nb, 128, 1);
+  mg_block_orthonormalize_kernel<<<grid, 128, 0, ctx->stream>>>(n, Xf, dof_f, bx, by, nvec, Xf / bx, Yf / by);
+  GLB_LAUNCH_CHECK();
+  return GLB_OK;
+}
+
+int glb_mg_partition(glb_context* ctx, int X, int Y, int dof, int by_colour, void* d_even_io, void* d_odd_out) {
+  if (!ctx || !d_even_io || !d_odd_out) return fail(GLB_ERR_ARG, "glb_mg_partition: null argument");
+  const size_t n = (size_t)X * Y * dof;
+  const int grid = blas_grid(ctx, n, 256, 1);
+  mg_partition_kernel<<<grid, 256, 0, ctx->stream>>>((cplx*)d_even_io, (cplx*)d_odd_out, n, X, dof, 0, by_colour);
+  GLB_LAUNCH_CHECK();
+  return GLB_OK;
+}
+
+int glb_mg_galerkin(glb_mg_transfer* t, glb_operator* fine, glb_operator** coarse) {
+  if (!t || !fine || !coarse) return fail(GLB_ERR_ARG, "glb_mg_galerkin: null argument");
+  glb_context* ctx = t->ctx;
+  if (fine->kind != OPK_STENCIL || fine->has_two)
+    return fail(GLB_ERR_ARG, "glb_mg_galerkin: the fine operator must be a five-point stencil2d operator");
+  if (fine->X != t->Xf || fine->Yloc != t->Yf || fine->nc != t->dof_f || ctx->nranks != 1)
+    return fail(GLB_ERR_ARG, "glb_mg_galerkin: transfer and fine operator disagree (single rank only)");
+  if (t->Xc < 2 || t->Yc < 2) return fail(GLB_ERR_ARG, "glb_mg_galerkin: the coarse lattice needs at least 2 sites per direction");
+  const int nv = t->nvec;
+  const size_t per = (size_t)t->Xc * t->Yc * nv * nv;
+  cplx *cl = nullptr, *hp = nullptr;
+  if (cudaMalloc(&cl, per * sizeof(cplx)) != cudaSuccess || cudaMalloc(&hp, 4 * per * sizeof(cplx)) != cudaSuccess) {
+    cudaFree(cl);
+    return fail(GLB_ERR_CUDA, "glb_mg_galerkin: out of device memory");
+  }
+  MgFine fs;
+  fs.clover = fine->clover;
+  fs.hopping = fine->hopping;
+  fs.shift = make_double2(fine->shift[0], fine->shift[1]);
+  fs.eo_shift = make_double2(fine->eo_shift[0], fine->eo_shift[1]);
+  fs.dof_shift = make_double2(fine->dof_shift[0], fine->dof_shift[1]);
+  fs.use_shift = (fine->shift[0] != 0.0 || fine->shift[1] != 0.0);
+  fs.use_eo = (fine->eo_shift[0] != 0.0 || fine->eo_shift[1] != 0.0);
+  fs.use_dof = (fine->dof_shift[0] != 0.0 || fine->dof_shift[1] != 0.0);
+  const int grid = blas_grid(ctx, per, 128, 1);
+  mg_galerkin_kernel<<<grid, 128, 0, ctx->stream>>>(mg_args(t), fs, cl, hp);
+  GLB_LAUNCH_CHECK();
+  int rc = op_adopt_stencil2d(ctx, t->Xc, t->Yc, nv, cl, hp, coarse);
+  if (rc) {
+    cudaFree(cl);
+    cudaFree(hp);
+  }
+  return rc;
+}
+
 int glb_mg_transfer_destroy(glb_mg_transfer* t) {
   if (!t) return GLB_OK;
   cudaStreamSynchronize(t->ctx->stream);
@@ -148,19 +364,6 @@ int glb_mg_transfer_destroy(glb_mg_transfer* t) {
 size_t glb_mg_fine_size(const glb_mg_transfer* t) { return t ? (size_t)t->Xf * t->Yf * t->dof_f : 0; }
 size_t glb_mg_coarse_size(const glb_mg_transfer* t) { return t ? (size_t)t->Xc * t->Yc * t->nvec : 0; }
 
-static MgArgs mg_args(const glb_mg_transfer* t) {
-  MgArgs a;
-  a.null = t->null;
-  a.Xf = t->Xf;
-  a.Yf = t->Yf;
-  a.dof_f = t->dof_f;
-  a.bx = t->bx;
-  a.by = t->by;
-  a.nvec = t->nvec;
-  a.Xc = t->Xc;
-  a.Yc = t->Yc;
-  return a;
-}
 
 int glb_mg_prolong(glb_mg_transfer* t, void* d_fine, const void* d_coarse) {
   if (!t || !d_fine || !d_coarse) return fail(GLB_ERR_ARG, "glb_mg_prolong: null argument");

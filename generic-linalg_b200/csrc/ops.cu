@@ -215,6 +215,25 @@ int glb_op_create_stencil2d(glb_context* ctx, const void* clover, const void* ho
   return alloc_ghosts(op, op->has_two ? 2 : 1);
 }
 
+}  // extern "C"
+
+namespace glb {
+// a five-point stencil2d operator around matrices that already live on the device (ownership passes to the
+// operator): used by the Galerkin set-up in mg.cu.  Single rank only.
+int op_adopt_stencil2d(glb_context* ctx, int X, int Y, int nc, cplx* d_clover, cplx* d_hopping, glb_operator** out) {
+  if (ctx->nranks != 1) return fail(GLB_ERR_STATE, "device-side stencil set-up is single-rank");
+  int rc = new_op(ctx, OPK_STENCIL, GLB_COMPLEX, X, Y, nc, out);
+  if (rc) return rc;
+  glb_operator* op = *out;
+  op->has_two = false;
+  op->clover = d_clover;
+  op->hopping = d_hopping;
+  return alloc_ghosts(op, 1);
+}
+}  // namespace glb
+
+extern "C" {
+
 int glb_slab_bounds(glb_context* ctx, int Y, int* y0, int* Yloc) {
   if (!ctx || !y0 || !Yloc) return fail(GLB_ERR_ARG, "glb_slab_bounds: null argument");
   slab_of(ctx, Y, y0, Yloc);

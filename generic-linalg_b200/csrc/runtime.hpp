@@ -181,6 +181,9 @@ int launch_normal(glb_operator* op, void* out, const void* in, const ApplyFusion
 int launch_stencil2d(glb_operator* op, void* out, const void* in, const ApplyFusion& f);
 int launch_stencil2d_part(glb_operator* op, void* out, const void* in, int part);  // GLB_PART_*
 
+// ops.cu : stencil2d operator around device-resident matrices (ownership passes to the operator)
+int op_adopt_stencil2d(glb_context* ctx, int X, int Y, int nc, cplx* d_clover, cplx* d_hopping, glb_operator** out);
+
 // comm.cu : fills op->ghost_lo / ghost_hi from the neighbouring ranks' boundary rows of `in`
 int halo_exchange(glb_operator* op, const void* in, int nrows);
 // same, boundary rows taken from explicit buffers (nrows lowest rows in send_lo, nrows highest in send_hi)

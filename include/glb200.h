@@ -198,6 +198,8 @@ int glb_bicgstab_update(glb_context* ctx, int dtype, size_t n, const double alph
 /* p = r + beta*(p - omega*Ap)   (generic_bicgstab.cpp:300-303) */
 int glb_bicgstab_pupdate(glb_context* ctx, int dtype, size_t n, const void* r, const double beta[2],
                          const double omega[2], const void* Ap, void* p);
+/* out = s*x with a real s (generic_vector.h:173-203 normalize: v *= 1/sqrt(|v|^2)) */
+int glb_rscale(glb_context* ctx, int dtype, size_t n, const void* x, double s, void* out);
 /* out = conj(x) (complex) / out = x (real)   (generic_vector.h conj<>; generic_bicgstab_m.cpp:494) */
 int glb_conj(glb_context* ctx, int dtype, size_t n, const void* x, void* out);
 /* multishift BiCGStab, one shift: s_n = c0*r + c1*(s_n - c2*(c3*w - c4*r_prev)) with c = {c0..c4} complex pairs
@@ -264,6 +266,20 @@ typedef struct glb_mg_transfer glb_mg_transfer;
 int glb_mg_transfer_create(glb_context* ctx, int Xf, int Yf, int dof_f, int bx, int by, int nvec,
                            const void* const* null_vectors, glb_mg_transfer** out);
 int glb_mg_transfer_destroy(glb_mg_transfer* t);
+/* ---- set-up on the device ---- */
+/* the transfer from DEVICE-resident null vectors (nvec device pointers, reference layout null_vectors[v][f]) */
+int glb_mg_transfer_create_dev(glb_context* ctx, int Xf, int Yf, int dof_f, int bx, int by, int nvec,
+                               const void* const* d_null_vectors, glb_mg_transfer** out);
+/* block_orthonormalize + block_normalize (mg_complex.cpp:191-370) in place on nvec device vectors */
+int glb_mg_block_orthonormalize(glb_context* ctx, int Xf, int Yf, int dof_f, int bx, int by, int nvec,
+                                void* const* d_null_vectors);
+/* BLOCK_EO partition of one null vector (null_gen.cpp:26-35 top level: by_colour = 0, odd SITES move to odd_out;
+ * :109-126 coarser levels: by_colour = 1, the upper half of the colour index moves); even_io keeps the rest */
+int glb_mg_partition(glb_context* ctx, int X, int Y, int dof, int by_colour, void* d_even_io, void* d_odd_out);
+/* Galerkin coarse operator P^dag A P of a five-point stencil2d fine operator (what generate_coarse_from_fine_stencil,
+ * mg_complex.cpp:827-1026, assembles by probing; fine shifts are folded into the coarse clover): a new stencil2d
+ * operator on the coarse lattice of the transfer, nc = nvec.  Single rank. */
+int glb_mg_galerkin(glb_mg_transfer* t, glb_operator* fine, glb_operator** coarse);
 size_t glb_mg_fine_size(const glb_mg_transfer* t);
 size_t glb_mg_coarse_size(const glb_mg_transfer* t);
 int glb_mg_prolong(glb_mg_transfer* t, void* d_fine, const void* d_coarse);

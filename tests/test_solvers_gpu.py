@@ -188,7 +188,10 @@ def test_device_cg_equals_host_scalar_cg(ctx, glb, orc):
     x2, i2 = run_dev(ctx, Nrm, "CG", b, max_iter=100000, eps=1e-10)
     ctx.force_host_scalars(False)
     assert i1["iter"] == i2["iter"] and i1["ops_count"] == i2["ops_count"] and i1["success"] == i2["success"]
-    assert rel_err(x1, x2) < 1e-12
+    # same recurrences; the inner products come from differently shaped kernels (the device loop's fused one-pass
+    # kernel sums two sites per thread, the shell's plain one one site per thread), so the iterates agree to
+    # rounding amplified over ~170 iterations (measured 1e-12), not bit for bit
+    assert rel_err(x1, x2) < 1e-10
     # history returned by the device loop is the recurrence residual of every iteration
     x = ctx.vector(L * L).zero()
     rep = ctx.cg_device(Nrm, x, ctx.vector(L * L).upload(b), max_iter=100000, eps=1e-10, want_history=True)
