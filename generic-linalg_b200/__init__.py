@@ -121,6 +121,13 @@ def libs():
         "glb_mg_transfer_create": (ci, [vp, ci, ci, ci, ci, ci, ci, C.POINTER(vp), C.POINTER(vp)]),
         "glb_mg_transfer_destroy": (ci, [vp]), "glb_mg_fine_size": (sz, [vp]), "glb_mg_coarse_size": (sz, [vp]),
         "glb_mg_prolong": (ci, [vp, vp, vp]), "glb_mg_restrict": (ci, [vp, vp, vp]),
+        "glb_rscale": (ci, [vp, ci, sz, vp, cd, vp]),
+        "glb_op_set_shifts": (ci, [vp, pd, pd, pd]), "glb_op_get_shifts": (ci, [vp, pd, pd, pd]),
+        "glb_op_stencil_download": (ci, [vp, vp, vp]),
+        "glb_mg_transfer_create_dev": (ci, [vp, ci, ci, ci, ci, ci, ci, C.POINTER(vp), C.POINTER(vp)]),
+        "glb_mg_block_orthonormalize": (ci, [vp, ci, ci, ci, ci, ci, ci, C.POINTER(vp)]),
+        "glb_mg_partition": (ci, [vp, ci, ci, ci, ci, vp, vp]),
+        "glb_mg_galerkin": (ci, [vp, vp, ci, C.POINTER(vp)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(cu, name)
@@ -146,6 +153,10 @@ def libs():
         "glbx_mg_vcycle": (ci, [vp, vp, vp]),
         "glbx_mg_vpgcr": (ci, [vp, vp, vp, ci, cd, ci, ci, C.POINTER(Result)]),
         "glbx_mg_counts": (None, [vp, C.POINTER(ci)]),
+        "glbx_mg_setup": (vp, [vp, ci, ci, ci, C.POINTER(ci), C.POINTER(ci), ci, cd, ci, pd, C.POINTER(ci), ci, ci, ci,
+                               ci, C.c_uint, ci]),
+        "glbx_mg_level_op": (vp, [vp, ci]), "glbx_mg_level_transfer": (vp, [vp, ci]),
+        "glbx_mg_null_vector": (vp, [vp, ci, ci]), "glbx_mg_setup_seconds": (None, [vp, pd]),
     }
     for name, (res, args) in hsig.items():
         f = getattr(ho, name)
@@ -271,6 +282,23 @@ class Operator:
     def set_mass(self, m):
         _chk(self.ctx.cu.glb_op_set_mass(self.h, m))
 
+    def set_shifts(self, shift=None, eo_shift=None, dof_shift=None):
+        """stencil2d operators: stencil_2d::shift / eo_shift / dof_shift (coarse_stencil.h:62-71); None keeps one"""
+        a = [_c2(v) if v is not None else None for v in (shift, eo_shift, dof_shift)]
+        _chk(self.ctx.cu.glb_op_set_shifts(self.h, a[0], a[1], a[2]), "glb_op_set_shifts")
+
+    def get_shifts(self):
+        a = [(C.c_double * 2)() for _ in range(3)]
+        _chk(self.ctx.cu.glb_op_get_shifts(self.h, a[0], a[1], a[2]), "glb_op_get_shifts")
+        return tuple(complex(v[0], v[1]) for v in a)
+
+    def stencil_download(self, X, Y, nc):
+        """(clover, hopping) of a single-rank stencil2d operator in the reference layout"""
+        cl = np.empty(X * Y * nc * nc, dtype=np.complex128)
+        hp = np.empty(4 * X * Y * nc * nc, dtype=np.complex128)
+        _chk(self.ctx.cu.glb_op_stencil_download(self.h, _p(cl), _p(hp)), "glb_op_stencil_download")
+        return cl, hp
+
     def apply_host(self, v):
         """upload -> apply -> download (convenience for tests)"""
         a = self.ctx.vector(self.local_size, self.dtype).upload(v)
@@ -294,12 +322,21 @@ class MgTransfer:
     """prolong / restrict between two multigrid levels (include/glb200.h: glb_mg_*; mg_complex.cpp:372-467)"""
 
     def __init__(self, ctx, Xf, Yf, dof_f, bx, by, null_vectors):
+        """null_vectors: host arrays, or DeviceVectors (e.g. after Context.mg_block_orthonormalize)"""
         self.ctx = ctx
-        self._null = [np.ascontiguousarray(v, dtype=np.complex128) for v in null_vectors]
-        n = len(self._null)
-        ptrs = (C.c_void_p * n)(*[v.ctypes.data for v in self._null])
+        self.dims = (Xf, Yf, dof_f, bx, by)
+        n = len(null_vectors)
         h = C.c_void_p()
-        _chk(ctx.cu.glb_mg_transfer_create(ctx.h, Xf, Yf, dof_f, bx, by, n, ptrs, C.byref(h)), "glb_mg_transfer_create")
+        if n and isinstance(null_vectors[0], DeviceVector):
+            ptrs = (C.c_void_p * n)(*[v.ptr for v in null_vectors])
+            _chk(ctx.cu.glb_mg_transfer_create_dev(ctx.h, Xf, Yf, dof_f, bx, by, n, ptrs, C.byref(h)),
+                 "glb_mg_transfer_create_dev")
+        else:
+            self._null = [np.ascontiguousarray(v, dtype=np.complex128) for v in null_vectors]
+            ptrs = (C.c_void_p * n)(*[v.ctypes.data for v in self._null])
+            _chk(ctx.cu.glb_mg_transfer_create(ctx.h, Xf, Yf, dof_f, bx, by, n, ptrs, C.byref(h)),
+                 "glb_mg_transfer_create")
+        self.nvec = n
         self.h = h
         self.fine_size = int(ctx.cu.glb_mg_fine_size(h))
         self.coarse_size = int(ctx.cu.glb_mg_coarse_size(h))
@@ -309,6 +346,13 @@ class MgTransfer:
 
     def restrict(self, coarse, fine):
         _chk(self.ctx.cu.glb_mg_restrict(self.h, coarse.ptr, fine.ptr), "glb_mg_restrict")
+
+    def galerkin(self, fine_op, ignore_shifts=False):
+        """glb_mg_galerkin: the coarse stencil2d operator P^dag A P (generate_coarse_from_fine_stencil,
+        mg_complex.cpp:827-1026) of a five-point stencil2d fine operator"""
+        h = C.c_void_p()
+        _chk(self.ctx.cu.glb_mg_galerkin(self.h, fine_op.h, int(ignore_shifts), C.byref(h)), "glb_mg_galerkin")
+        return Operator(self.ctx, h)
 
     def destroy(self):
         if self.h:
@@ -338,6 +382,63 @@ class Multigrid:
         if not self.h:
             raise GlbError("glbx_mg_create failed")
         self.n_refine = n
+
+    @classmethod
+    def setup(cls, ctx, fine_op, X, Y, blocks, nvecs, bstrat=1, null_mass=1e-2, null_gen="BICGSTAB", tol=5e-5,
+              max_iter=500, restart_freq=0, bicgstab_l=-1, do_ortho_eo=False, do_global_ortho_conj=False, seed=1337,
+              verbosity=0):
+        """glbx_mg_setup: the reference driver's set-up sequence on the device (null_generate_random_smooth_dev,
+        block_orthonormalize_dev, generate_coarse_from_fine_stencil_dev; aa_mg_square_staggered_u1.cpp:716-1143).
+        fine_op: the level-0 stencil2d operator with the mass in its shift.  nvecs[l]: vectors of refinement l after
+        the partition; bstrat 0 = BLOCK_NONE, 1 = BLOCK_EO."""
+        n = len(blocks)
+        self = cls.__new__(cls)
+        self.ctx, self.n_refine = ctx, n
+        bl = (C.c_int * n)(*blocks)
+        nv = (C.c_int * n)(*nvecs)
+        tl = (C.c_double * n)(*([tol] * n if np.isscalar(tol) else tol))
+        mi = (C.c_int * n)(*([max_iter] * n if np.isscalar(max_iter) else max_iter))
+        self.h = ctx.ho.glbx_mg_setup(fine_op.h, X, Y, n, bl, nv, bstrat, null_mass, cls.SMOOTH[null_gen], tl, mi,
+                                      restart_freq, bicgstab_l, int(do_ortho_eo), int(do_global_ortho_conj), seed,
+                                      verbosity)
+        if not self.h:
+            raise GlbError("glbx_mg_setup failed (see stderr)")
+        self.ops, self.transfers = [fine_op], []
+        self.blocks, self.nvecs, self.top = list(blocks), list(nvecs), (X, Y)
+        return self
+
+    def level_dims(self, level):
+        X, Y = self.top
+        dof = 1
+        for l in range(level):
+            X, Y, dof = X // self.blocks[l], Y // self.blocks[l], self.nvecs[l]
+        return X, Y, dof
+
+    def level_stencil(self, level):
+        """(clover, hopping, shifts) of level `level` of a hierarchy built by setup()"""
+        X, Y, nc = self.level_dims(level)
+        h = self.ctx.ho.glbx_mg_level_op(self.h, level)
+        cl = np.empty(X * Y * nc * nc, dtype=np.complex128)
+        hp = np.empty(4 * X * Y * nc * nc, dtype=np.complex128)
+        _chk(self.ctx.cu.glb_op_stencil_download(h, _p(cl), _p(hp)), "glb_op_stencil_download")
+        a = [(C.c_double * 2)() for _ in range(3)]
+        _chk(self.ctx.cu.glb_op_get_shifts(h, a[0], a[1], a[2]), "glb_op_get_shifts")
+        return cl, hp, tuple(complex(v[0], v[1]) for v in a)
+
+    def null_vector(self, level, v):
+        """block-orthonormalised null vector v of refinement `level` (downloaded)"""
+        X, Y, dof = self.level_dims(level)
+        out = np.empty(X * Y * dof, dtype=np.complex128)
+        p = self.ctx.ho.glbx_mg_null_vector(self.h, level, v)
+        if not p:
+            raise GlbError("no such null vector")
+        _chk(self.ctx.cu.glb_vec_download(self.ctx.h, COMPLEX, out.size, _p(out), p), "glb_vec_download")
+        return out
+
+    def setup_seconds(self):
+        a = (C.c_double * 4)()
+        self.ctx.ho.glbx_mg_setup_seconds(self.h, a)
+        return dict(null_vectors=a[0], block_orthonormalize=a[1], galerkin=a[2], total=a[3])
 
     def set(self, smooth="GCR", n_pre=6, n_post=6, inner="GCR", n_max=1024, n_restart=64, rel_res=1e-2,
             recursive=False, quiet=True):
@@ -496,6 +597,20 @@ class Context:
 
     def multigrid(self, ops, transfers):
         return Multigrid(self, ops, transfers)
+
+    def multigrid_setup(self, fine_op, X, Y, blocks, nvecs, **kw):
+        return Multigrid.setup(self, fine_op, X, Y, blocks, nvecs, **kw)
+
+    def mg_block_orthonormalize(self, Xf, Yf, dof_f, bx, by, dev_vectors):
+        """block_orthonormalize + block_normalize (mg_complex.cpp:191-370) in place on DeviceVectors"""
+        n = len(dev_vectors)
+        ptrs = (C.c_void_p * n)(*[v.ptr for v in dev_vectors])
+        _chk(self.cu.glb_mg_block_orthonormalize(self.h, Xf, Yf, dof_f, bx, by, n, ptrs), "glb_mg_block_orthonormalize")
+
+    def mg_partition(self, X, Y, dof, colour_period, even_io, odd_out):
+        """BLOCK_EO partition of one null vector: colour_period 0 = odd sites (null_gen.cpp:26-35), m > 0 = elements
+        with index % m >= m/2 (null_gen.cpp:109-126)"""
+        _chk(self.cu.glb_mg_partition(self.h, X, Y, dof, int(colour_period), even_io.ptr, odd_out.ptr), "glb_mg_partition")
 
     # ---- BLAS-1 (thin; used by the parity tests) ----
     def dot(self, x, y):

@@ -115,13 +115,14 @@ __global__ void __launch_bounds__(128) mg_block_orthonormalize_kernel(const MgNu
 }
 
 // null_partition_staggered / null_partition_coarse, BLOCK_EO (null_gen.cpp:26-35, :109-126): the odd part of `even_io`
-// (odd sites on the top level, upper half of the colour index below it) moves to `odd_out` and is zeroed in place.
+// (odd sites on the top level; below it the elements whose index modulo colour_period lies in the upper half of the
+// period) moves to `odd_out` and is zeroed in place.
 __global__ void mg_partition_kernel(cplx* __restrict__ even_io, cplx* __restrict__ odd_out, size_t n, int X, int dof, int y0,
-                                    int by_colour) {
+                                    int colour_period) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     bool odd;
-    if (by_colour) {
-      odd = (int)(i % dof) >= dof / 2;
+    if (colour_period > 0) {
+      odd = (int)(i % colour_period) >= colour_period / 2;
     } else {
       const size_t site = i / dof;
       odd = ((site % X + site / X + y0) & 1) != 0;
@@ -309,23 +310,25 @@ int glb_mg_block_orthonormalize(glb_context* ctx, int Xf, int Yf, int dof_f, int
   return GLB_OK;
 }
 
-int glb_mg_partition(glb_context* ctx, int X, int Y, int dof, int by_colour, void* d_even_io, void* d_odd_out) {
+int glb_mg_partition(glb_context* ctx, int X, int Y, int dof, int colour_period, void* d_even_io, void* d_odd_out) {
   if (!ctx || !d_even_io || !d_odd_out) return fail(GLB_ERR_ARG, "glb_mg_partition: null argument");
+  if (X < 1 || Y < 1 || dof < 1 || colour_period < 0) return fail(GLB_ERR_ARG, "glb_mg_partition: bad extents");
   const size_t n = (size_t)X * Y * dof;
   const int grid = blas_grid(ctx, n, 256, 1);
-  mg_partition_kernel<<<grid, 256, 0, ctx->stream>>>((cplx*)d_even_io, (cplx*)d_odd_out, n, X, dof, 0, by_colour);
+  mg_partition_kernel<<<grid, 256, 0, ctx->stream>>>((cplx*)d_even_io, (cplx*)d_odd_out, n, X, dof, 0, colour_period);
   GLB_LAUNCH_CHECK();
   return GLB_OK;
 }
 
-int glb_mg_galerkin(glb_mg_transfer* t, glb_operator* fine, glb_operator** coarse) {
+int glb_mg_galerkin(glb_mg_transfer* t, glb_operator* fine, int ignore_shifts, glb_operator** coarse) {
   if (!t || !fine || !coarse) return fail(GLB_ERR_ARG, "glb_mg_galerkin: null argument");
   glb_context* ctx = t->ctx;
   if (fine->kind != OPK_STENCIL || fine->has_two)
     return fail(GLB_ERR_ARG, "glb_mg_galerkin: the fine operator must be a five-point stencil2d operator");
   if (fine->X != t->Xf || fine->Yloc != t->Yf || fine->nc != t->dof_f || ctx->nranks != 1)
     return fail(GLB_ERR_ARG, "glb_mg_galerkin: transfer and fine operator disagree (single rank only)");
-  if (t->Xc < 2 || t->Yc < 2) return fail(GLB_ERR_ARG, "glb_mg_galerkin: the coarse lattice needs at least 2 sites per direction");
+  if (t->Xc < 2 || t->Yc < 2 || (t->Xc & 1) || (t->Yc & 1))
+    return fail(GLB_ERR_ARG, "glb_mg_galerkin: the coarse lattice needs an even number (>= 2) of sites per direction");
   const int nv = t->nvec;
   const size_t per = (size_t)t->Xc * t->Yc * nv * nv;
   cplx *cl = nullptr, *hp = nullptr;
@@ -339,9 +342,9 @@ int glb_mg_galerkin(glb_mg_transfer* t, glb_operator* fine, glb_operator** coars
   fs.shift = make_double2(fine->shift[0], fine->shift[1]);
   fs.eo_shift = make_double2(fine->eo_shift[0], fine->eo_shift[1]);
   fs.dof_shift = make_double2(fine->dof_shift[0], fine->dof_shift[1]);
-  fs.use_shift = (fine->shift[0] != 0.0 || fine->shift[1] != 0.0);
-  fs.use_eo = (fine->eo_shift[0] != 0.0 || fine->eo_shift[1] != 0.0);
-  fs.use_dof = (fine->dof_shift[0] != 0.0 || fine->dof_shift[1] != 0.0);
+  fs.use_shift = !ignore_shifts && (fine->shift[0] != 0.0 || fine->shift[1] != 0.0);
+  fs.use_eo = !ignore_shifts && (fine->eo_shift[0] != 0.0 || fine->eo_shift[1] != 0.0);
+  fs.use_dof = !ignore_shifts && (fine->dof_shift[0] != 0.0 || fine->dof_shift[1] != 0.0);
   const int grid = blas_grid(ctx, per, 128, 1);
   mg_galerkin_kernel<<<grid, 128, 0, ctx->stream>>>(mg_args(t), fs, cl, hp);
   GLB_LAUNCH_CHECK();

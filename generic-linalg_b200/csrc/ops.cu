@@ -264,6 +264,34 @@ int glb_op_set_mass(glb_operator* op, double mass) {
   if (op->kind == OPK_LAPLACE && (op->flags & 0x100u)) op->diag_re = mass;
   return GLB_OK;
 }
+int glb_op_set_shifts(glb_operator* op, const double shift[2], const double eo_shift[2], const double dof_shift[2]) {
+  if (!op || op->kind != OPK_STENCIL) return fail(GLB_ERR_ARG, "glb_op_set_shifts: not a stencil2d operator");
+  for (int i = 0; i < 2; i++) {
+    if (shift) op->shift[i] = shift[i];
+    if (eo_shift) op->eo_shift[i] = eo_shift[i];
+    if (dof_shift) op->dof_shift[i] = dof_shift[i];
+  }
+  return GLB_OK;
+}
+int glb_op_get_shifts(const glb_operator* op, double shift[2], double eo_shift[2], double dof_shift[2]) {
+  if (!op || op->kind != OPK_STENCIL) return fail(GLB_ERR_ARG, "glb_op_get_shifts: not a stencil2d operator");
+  for (int i = 0; i < 2; i++) {
+    if (shift) shift[i] = op->shift[i];
+    if (eo_shift) eo_shift[i] = op->eo_shift[i];
+    if (dof_shift) dof_shift[i] = op->dof_shift[i];
+  }
+  return GLB_OK;
+}
+int glb_op_stencil_download(glb_operator* op, void* h_clover, void* h_hopping) {
+  if (!op || op->kind != OPK_STENCIL) return fail(GLB_ERR_ARG, "glb_op_stencil_download: not a stencil2d operator");
+  if (op->ctx->nranks != 1) return fail(GLB_ERR_STATE, "glb_op_stencil_download: single rank only");
+  GLB_CUDA(cudaSetDevice(op->ctx->device));
+  const size_t per = (size_t)op->X * op->Y * op->nc * op->nc * sizeof(cplx);
+  if (h_clover) GLB_CUDA(cudaMemcpyAsync(h_clover, op->clover, per, cudaMemcpyDeviceToHost, op->ctx->stream));
+  if (h_hopping) GLB_CUDA(cudaMemcpyAsync(h_hopping, op->hopping, 4 * per, cudaMemcpyDeviceToHost, op->ctx->stream));
+  GLB_CUDA(cudaStreamSynchronize(op->ctx->stream));
+  return GLB_OK;
+}
 int glb_op_dtype(const glb_operator* op) { return op->dtype; }
 size_t glb_op_local_size(const glb_operator* op) { return (size_t)op->X * op->Yloc * op->nc; }
 size_t glb_op_global_size(const glb_operator* op) { return (size_t)op->X * op->Y * op->nc; }

@@ -2,13 +2,18 @@
 // (tests/ and bench.py load it through ctypes).  Every function here only forwards to the public
 // C++ entry points of generic_inverters.h / glb200_device.h / operators.h -- the calls a C++ user
 // of the reference would make -- and flattens inversion_info into a POD.
+#include <chrono>
 #include <cstring>
+#include <iostream>
+#include <random>
+#include <string>
 #include <vector>
 
 #include "coarse_stencil.h"
 #include "dev_internal.hpp"
 #include "generic_inverters_precond.h"
 #include "mg_complex.h"
+#include "null_gen.h"
 #include "operators.h"
 #include "operators_stencil.h"
 
@@ -395,13 +400,17 @@ typedef struct glbx_mg {
   std::vector<glb_mg_transfer*> trs;
   std::vector<int> n_pre, n_post;
   std::vector<double> rel_res;
+  // set-up on the device (glbx_mg_setup): this handle then owns the coarse operators, the transfers and the
+  // device null vectors; the level-0 operator stays the caller's
+  bool owns_hierarchy;
+  std::vector<int> bx, by, nvec;
+  std::vector<std::vector<zc*> > null_dev;
+  std::vector<zc**> null_tab;
+  double setup_seconds[4];  // null vectors, block orthonormalisation, transfers + Galerkin products, total
+  glbx_mg() : owns_hierarchy(false) { setup_seconds[0] = setup_seconds[1] = setup_seconds[2] = setup_seconds[3] = 0.0; }
 } glbx_mg;
 
-glbx_mg* glbx_mg_create(int n_refine, glb_operator** level_ops, glb_mg_transfer** transfers) {
-  if (n_refine < 1 || !level_ops || !transfers) return 0;
-  glbx_mg* h = new glbx_mg();
-  h->ops.assign(level_ops, level_ops + n_refine + 1);
-  h->trs.assign(transfers, transfers + n_refine);
+static void mg_defaults(glbx_mg* h, int n_refine) {
   h->mg.n_refine = n_refine;
   h->mg.stencils = h->ops.data();
   h->mg.transfers = h->trs.data();
@@ -424,13 +433,147 @@ glbx_mg* glbx_mg_create(int n_refine, glb_operator** level_ops, glb_mg_transfer*
   h->pc.rel_res = h->rel_res.data();
   h->pc.mgstruct = &h->mg;
   h->pc.quiet = true;
+}
+
+glbx_mg* glbx_mg_create(int n_refine, glb_operator** level_ops, glb_mg_transfer** transfers) {
+  if (n_refine < 1 || !level_ops || !transfers) return 0;
+  glbx_mg* h = new glbx_mg();
+  h->ops.assign(level_ops, level_ops + n_refine + 1);
+  h->trs.assign(transfers, transfers + n_refine);
+  mg_defaults(h, n_refine);
   return h;
 }
 
 void glbx_mg_destroy(glbx_mg* h) {
   if (!h) return;
+  if (h->owns_hierarchy) {
+    glb_context* ctx = h->ops[0] ? glb_op_context(h->ops[0]) : 0;
+    for (size_t i = 1; i < h->ops.size(); i++)
+      if (h->ops[i]) glb_op_destroy(h->ops[i]);
+    for (size_t i = 0; i < h->trs.size(); i++)
+      if (h->trs[i]) glb_mg_transfer_destroy(h->trs[i]);
+    for (size_t l = 0; l < h->null_dev.size(); l++)
+      for (size_t v = 0; v < h->null_dev[l].size(); v++)
+        if (h->null_dev[l][v] && ctx) glb_vec_free(ctx, h->null_dev[l][v]);
+  }
   delete h->mg.dslash_count;
   delete h;
+}
+
+// The set-up sequence of the reference's driver for --operator staggered --null-operator staggered
+// (multigrid/aa_mg/aa_mg_square_staggered_u1.cpp:716-1143) on the device.  `fine` is the level-0 stencil2d operator
+// (get_square_staggered_u1_stencil with the mass in the shift, :986-996); it stays the caller's.  Per refinement:
+// null_generate_random_smooth_dev with the shift set to null_mass, block_orthonormalize_dev,
+// generate_coarse_from_fine_stencil_dev(ignore_shifts = true) and the shift copied down; at the end every level's
+// shift is the true mass again (the Galerkin products do not depend on it, so the reference's second "final" build
+// :1066-1093 gives the same matrices).
+//   nvec[l]   total null vectors of refinement l (after the partition);  bstrat: 0 none, 1 even/odd
+//   null_gen  minv_inverter;  tol[l], max_iter[l] per refinement;  seed of the std::mt19937 behind the sources
+glbx_mg* glbx_mg_setup(glb_operator* fine, int X, int Y, int n_refine, const int* block, const int* nvec, int bstrat,
+                       double null_mass, int null_gen, const double* tol, const int* max_iter, int restart_freq,
+                       int bicgstab_l, int do_ortho_eo, int do_global_ortho_conj, unsigned seed, int verbosity) {
+  if (!fine || n_refine < 1 || !block || !nvec || !tol || !max_iter) return 0;
+  glbx_mg* h = new glbx_mg();
+  double mass_shift[2] = {0.0, 0.0};
+  bool shifted = false;
+  try {
+    glb_context* ctx = glb_op_context(fine);
+    h->owns_hierarchy = true;
+    h->ops.assign(n_refine + 1, (glb_operator*)0);
+    h->ops[0] = fine;
+    h->trs.assign(n_refine, (glb_mg_transfer*)0);
+    mg_defaults(h, n_refine);
+    h->bx.assign(block, block + n_refine);
+    h->by.assign(block, block + n_refine);
+    h->nvec.assign(nvec, nvec + n_refine);
+    h->mg.x_fine = X;
+    h->mg.y_fine = Y;
+    h->mg.blocksize_x = h->bx.data();
+    h->mg.blocksize_y = h->by.data();
+    h->mg.n_vectors = h->nvec.data();
+    h->null_dev.resize(n_refine);
+    h->null_tab.resize(n_refine);
+    for (int l = 0; l < n_refine; l++) {  // aa_mg_square_staggered_u1.cpp:607-616: allocated and zeroed
+      int lx, ly, ld;
+      mg_level_dims(&h->mg, l, &lx, &ly, &ld);
+      const size_t sz = (size_t)lx * ly * ld;
+      h->null_dev[l].assign(nvec[l], (zc*)0);
+      for (int v = 0; v < nvec[l]; v++) {
+        void* p = 0;
+        GLBX(glb_vec_alloc(ctx, GLB_COMPLEX, sz, &p));
+        h->null_dev[l][v] = (zc*)p;
+        GLBX(glb_vec_zero(ctx, GLB_COMPLEX, sz, p));
+      }
+      h->null_tab[l] = h->null_dev[l].data();
+    }
+    h->mg.null_vectors = h->null_tab.data();
+
+    null_vector_params nv;
+    nv.null_gen = (minv_inverter)null_gen;
+    nv.null_restart = restart_freq > 0;
+    nv.null_restart_freq = restart_freq;
+    nv.null_bicgstab_l = bicgstab_l;
+    nv.null_mass = null_mass;
+    nv.bstrat = (blocking_strategy)bstrat;
+    nv.null_partitions = (bstrat == BLOCK_EO) ? 2 : 1;  // :412-427
+    nv.do_ortho_eo = do_ortho_eo != 0;
+    nv.do_global_ortho_conj = do_global_ortho_conj != 0;
+    nv.quiet = verbosity == 0;
+    for (int l = 0; l < n_refine; l++) {
+      nv.n_null_vectors.push_back(nvec[l] / nv.null_partitions);
+      nv.null_precisions.push_back(tol[l]);
+      nv.null_max_iters.push_back(max_iter[l]);
+    }
+    std::mt19937 generator(seed);
+    inversion_verbose_struct verb;
+    make_verb(verbosity, &verb);
+
+    double null_shift[2] = {null_mass, 0.0};
+    GLBX(glb_op_get_shifts(fine, mass_shift, 0, 0));
+    GLBX(glb_op_set_shifts(fine, null_shift, 0, 0));  // :757
+    shifted = true;
+    typedef std::chrono::steady_clock clk;
+    const clk::time_point t_all = clk::now();
+    for (int n = 0; n < n_refine; n++) {
+      verb.verb_prefix = "[L" + std::to_string(h->mg.curr_level + 1) + "_NULLVEC]: ";
+      clk::time_point t0 = clk::now();
+      null_generate_random_smooth_dev(&h->mg, &nv, &verb, &generator);
+      GLBX(glb_synchronize(ctx));
+      clk::time_point t1 = clk::now();
+      block_orthonormalize_dev(&h->mg);
+      GLBX(glb_synchronize(ctx));
+      clk::time_point t2 = clk::now();
+      generate_coarse_from_fine_stencil_dev(&h->mg, true);
+      GLBX(glb_op_set_shifts(h->ops[n + 1], null_shift, 0, 0));  // :933
+      GLBX(glb_synchronize(ctx));
+      clk::time_point t3 = clk::now();
+      h->setup_seconds[0] += std::chrono::duration<double>(t1 - t0).count();
+      h->setup_seconds[1] += std::chrono::duration<double>(t2 - t1).count();
+      h->setup_seconds[2] += std::chrono::duration<double>(t3 - t2).count();
+      if (n != n_refine - 1) level_down(&h->mg);
+    }
+    h->mg.curr_level = 0;
+    for (int n = 0; n <= n_refine; n++) GLBX(glb_op_set_shifts(h->ops[n], mass_shift, 0, 0));  // :996, :1086
+    h->setup_seconds[3] = std::chrono::duration<double>(clk::now() - t_all).count();
+  } catch (const std::exception& e) {
+    std::cerr << "glbx_mg_setup: " << e.what() << "\n";
+    if (shifted) glb_op_set_shifts(fine, mass_shift, 0, 0);
+    glbx_mg_destroy(h);
+    return 0;
+  }
+  return h;
+}
+
+// what the set-up produced: the operator of level l (l >= 1: owned by the handle), the transfer of refinement l,
+// device null vector v of refinement l, wall-clock seconds {null vectors, orthonormalisation, Galerkin, total}
+glb_operator* glbx_mg_level_op(glbx_mg* h, int level) { return (h && level >= 0 && level < (int)h->ops.size()) ? h->ops[level] : 0; }
+glb_mg_transfer* glbx_mg_level_transfer(glbx_mg* h, int level) { return (h && level >= 0 && level < (int)h->trs.size()) ? h->trs[level] : 0; }
+void* glbx_mg_null_vector(glbx_mg* h, int level, int v) {
+  if (!h || level < 0 || level >= (int)h->null_dev.size() || v < 0 || v >= (int)h->null_dev[level].size()) return 0;
+  return h->null_dev[level][v];
+}
+void glbx_mg_setup_seconds(glbx_mg* h, double out[4]) {
+  for (int i = 0; i < 4; i++) out[i] = h->setup_seconds[i];
 }
 
 void glbx_mg_set(glbx_mg* h, int in_smooth_type, int n_pre, int n_post, int in_solve_type, int n_max, int n_restart,

@@ -6,9 +6,10 @@
 // K cycle through VPGCR), prolong, post-smooth -- its printed progress lines and its dslash counters.
 // What changes: every level's operator is a device operator (include/glb200.h: the fine staggered
 // stencil or a coarse stencil_2d uploaded once with glb_op_create_stencil2d), the grid transfers are the
-// device kernels of glb_mg_prolong / glb_mg_restrict, and all work vectors live in HBM.  The set-up
-// (null vectors, block_orthonormalize, generate_coarse_from_fine_stencil) stays with the caller: the
-// hierarchy is handed over as arrays (SURVEY 8f-2 is the next row).
+// device kernels of glb_mg_prolong / glb_mg_restrict, and all work vectors live in HBM.  The hierarchy is
+// either handed over as arrays (null vectors + per-level stencils built elsewhere) or set up on the device:
+// null_generate_random_smooth_dev (null_gen.h), block_orthonormalize_dev and
+// generate_coarse_from_fine_stencil_dev below.
 #ifndef GLB200_MG_COMPLEX_H
 #define GLB200_MG_COMPLEX_H
 
@@ -42,7 +43,25 @@ struct mg_operator_struct_complex_dev {
   glb_mg_transfer** transfers;
   int curr_level;
   dslash_tracker* dslash_count;
+  // ---- set-up state (needed by the *_dev set-up routines only; names of mg_complex.h:139-182)
+  int x_fine, y_fine;                      // top-level lattice; Nc = 1
+  int* blocksize_x;                        // [n_refine]
+  int* blocksize_y;                        // [n_refine]
+  int* n_vectors;                          // [n_refine] null vectors per refinement = coarse dofs per site
+  std::complex<double>*** null_vectors;    // DEVICE arrays null_vectors[level][v], level-l lattice size each
 };
+
+// lattice of level l (mg_complex.h: latt[l]): sites and dofs per site
+void mg_level_dims(const mg_operator_struct_complex_dev* mgstruct, int level, int* X, int* Y, int* dof);
+
+// block_orthonormalize + block_normalize (mg_complex.cpp:191-370) of null_vectors[curr_level], in place on the device.
+void block_orthonormalize_dev(mg_operator_struct_complex_dev* mgstruct);
+
+// generate_coarse_from_fine_stencil (mg_complex.cpp:827-1026) at curr_level: builds transfers[curr_level] from
+// null_vectors[curr_level] (replacing an existing one) and stencils[curr_level+1] = P^dag stencils[curr_level] P
+// (replacing an existing one) as a device stencil2d operator.  ignore_shifts as in the reference: true leaves the
+// fine shifts out of the coarse clover (the caller copies the shift down, aa_mg_square_staggered_u1.cpp:1080-1093).
+void generate_coarse_from_fine_stencil_dev(mg_operator_struct_complex_dev* mgstruct, bool ignore_shifts);
 
 // mg_precond_struct_complex (mg_complex.h:185-236) without the function pointers: the operators are
 // the device operators of the hierarchy.  normal_eqn_smooth / normal_eqn_mg must be false.

@@ -1,0 +1,79 @@
+// null_gen.h -- null-vector generation of the adaptive multigrid on DEVICE-resident vectors: counterpart of
+// multigrid/aa_mg/null_gen.h.  Same enums, same parameter struct, same routines with a _dev suffix;
+// the vectors of mgstruct->null_vectors are device arrays, the smoothing solve is the device solver family, and
+// the partition / normalise / orthogonalise steps are C-ABI calls.  The gaussian sources are drawn on the host from
+// the caller's std::mt19937 exactly as generic_vector.h:48-60 draws them (so the reference and this code see the
+// same random numbers) and uploaded.
+#ifndef GLB200_NULL_GEN_H
+#define GLB200_NULL_GEN_H
+
+#include <random>
+#include <vector>
+
+#include "generic_inverters.h"
+#include "inverter_struct.h"
+#include "mg_complex.h"
+
+// null_gen.h:14-21
+enum blocking_strategy {
+  BLOCK_NONE = 0,    // block fully
+  BLOCK_EO = 1,      // even/odd
+  BLOCK_CORNER = 2,  // corners        (not on the accelerated path)
+  BLOCK_TOPO = 3     // taste singlet  (not on the accelerated path)
+};
+
+// null_gen.h:24-29
+enum null_precond_strategy {
+  NULL_PRECOND_NONE = 0,
+  NULL_PRECOND_EO = 1,      // not on the accelerated path
+  NULL_PRECOND_NORMAL = 2,  // not on the accelerated path
+};
+
+// null_gen.h:31-64 (opt_null dropped: the operator is whatever stencils[curr_level] holds)
+struct null_vector_params {
+  std::vector<int> n_null_vectors;  // per refinement, BEFORE the partition doubles them
+  minv_inverter null_gen;
+  null_precond_strategy null_prec;
+  std::vector<double> null_precisions;
+  std::vector<int> null_max_iters;
+  bool null_restart;
+  int null_restart_freq;
+  int null_bicgstab_l;
+  double null_relaxation;
+  double null_mass;
+  int null_partitions;
+  blocking_strategy bstrat;
+  bool do_global_ortho_conj;
+  bool do_ortho_eo;
+  bool quiet;  // true: skip the reference's "[L*_NULLVEC]: Pre-orthog cosines ..." lines (and their three reductions each)
+
+  null_vector_params() {
+    null_gen = MINV_BICGSTAB;
+    null_prec = NULL_PRECOND_NONE;
+    null_restart = false;
+    null_restart_freq = -1;
+    null_bicgstab_l = -1;
+    null_relaxation = 1.0;
+    null_mass = 0.0;
+    null_partitions = 0;
+    bstrat = BLOCK_NONE;
+    do_global_ortho_conj = false;
+    do_ortho_eo = false;
+    quiet = false;
+  }
+};
+
+// null_gen.cpp:13-103: partition null vector `num_null_vec` of the top level (BLOCK_EO: its odd sites move to vector
+// num_null_vec + n_vectors[0]/2).  BLOCK_NONE: nothing.  Other strategies throw.
+void null_partition_staggered_dev(mg_operator_struct_complex_dev* mgstruct, int num_null_vec, blocking_strategy bstrat);
+
+// null_gen.cpp:106-160: the same below the top level (BLOCK_EO: the upper half of the colour index moves).
+void null_partition_coarse_dev(mg_operator_struct_complex_dev* mgstruct, int num_null_vec, blocking_strategy bstrat);
+
+// null_gen.cpp:193-400: for each of n_vectors[curr_level]/null_partitions vectors draw a gaussian x0, orthogonalise it
+// against the vectors found so far, solve A x = -A x0 from a zero guess with `null_gen` on stencils[curr_level]
+// (tolerance / iteration cap of this level), keep x + x0, partition, normalise, orthogonalise, normalise.
+void null_generate_random_smooth_dev(mg_operator_struct_complex_dev* mgstruct, null_vector_params* nvec_params,
+                                     inversion_verbose_struct* verb, std::mt19937* generator);
+
+#endif

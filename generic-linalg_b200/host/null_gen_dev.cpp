@@ -1,0 +1,225 @@
+// null_gen_dev.cpp -- multigrid set-up on device vectors: null_partition_*, null_generate_random_smooth
+// (multigrid/aa_mg/null_gen.cpp:13-400), block_orthonormalize (mg_complex.cpp:259-370) and
+// generate_coarse_from_fine_stencil (mg_complex.cpp:827-1026).
+//
+// The statements follow the reference one by one; vectors are device arrays and every operation is a C-ABI call:
+// operator applies, BLAS-1 (glb_dot / glb_norm2sq / glb_axpy / glb_rscale / glb_conj), glb_mg_partition,
+// glb_mg_block_orthonormalize, glb_mg_transfer_create_dev and glb_mg_galerkin.  The one thing that stays on the
+// host is the random source: it is drawn from the caller's std::mt19937 exactly as generic_vector.h:48-60 draws it
+// and uploaded, so the reference and this code start from the same numbers.
+#include <cmath>
+#include <iostream>
+
+#include "dev_internal.hpp"
+#include "null_gen.h"
+
+using namespace glbx;
+
+void mg_level_dims(const mg_operator_struct_complex_dev* mg, int level, int* X, int* Y, int* dof) {
+  int x = mg->x_fine, y = mg->y_fine, d = 1;
+  for (int l = 0; l < level; l++) {
+    x /= mg->blocksize_x[l];
+    y /= mg->blocksize_y[l];
+    d = mg->n_vectors[l];
+  }
+  *X = x;
+  *Y = y;
+  *dof = d;
+}
+
+namespace {
+
+struct Level {
+  glb_context* ctx;
+  int X, Y, dof, size;
+};
+
+Level level_of(const mg_operator_struct_complex_dev* mg) {
+  if (!mg || !mg->stencils || !mg->blocksize_x || !mg->blocksize_y || !mg->n_vectors || !mg->null_vectors)
+    throw Error("multigrid set-up: the set-up fields of mg_operator_struct_complex_dev are not filled in");
+  glb_operator* op = mg->stencils[mg->curr_level];
+  if (!op) throw Error("multigrid set-up: no operator on the current level");
+  Level L;
+  L.ctx = glb_op_context(op);
+  mg_level_dims(mg, mg->curr_level, &L.X, &L.Y, &L.dof);
+  L.size = L.X * L.Y * L.dof;
+  if ((size_t)L.size != glb_op_local_size(op)) throw Error("multigrid set-up: operator and level sizes disagree");
+  return L;
+}
+
+// generic_vector.h:173-203 normalize: res = 1/sqrt(|v|^2); if (res > 0) v *= res
+void normalize_dev(const Blas<zcplx>& B, zcplx* v) {
+  const double res = 1.0 / sqrt(B.norm2sq(v));
+  if (res > 0.0) GLBX(glb_rscale(B.ctx, GLB_COMPLEX, B.n, v, res, v));
+}
+
+// generic_vector.h:236-249 orthogonal: v1 += (-<v2,v1>/|v2|^2) v2
+void orthogonal_dev(const Blas<zcplx>& B, zcplx* v1, const zcplx* v2) {
+  const zcplx alpha = -B.dot(v2, v1) / B.norm2sq(v2);
+  B.axpy(alpha, v2, v1);
+}
+
+void conj_dev(const Blas<zcplx>& B, zcplx* v) { GLBX(glb_conj(B.ctx, GLB_COMPLEX, B.n, v, v)); }
+
+// generic_vector.h:48-60: g++ evaluates the two constructor arguments right to left, so the reference draws the
+// imaginary part first (pinned against the reference build in tests/test_oracle_cpu.py)
+void gaussian_host(std::vector<zcplx>& v, std::mt19937& generator) {
+  std::normal_distribution<> dist(0.0, 1.0);
+  for (size_t i = 0; i < v.size(); i++) {
+    const double im = dist(generator);
+    const double re = dist(generator);
+    v[i] = zcplx(re, im);
+  }
+}
+
+void partition(mg_operator_struct_complex_dev* mg, int num_null_vec, blocking_strategy bstrat, bool by_colour) {
+  const Level L = level_of(mg);
+  const int lvl = mg->curr_level;
+  switch (bstrat) {
+    case BLOCK_NONE:
+      return;
+    case BLOCK_EO:
+      // null_gen.cpp:114: below the top level the colour index is taken modulo n_vectors[curr_level] (the number
+      // of vectors being built on this level, not the dofs per site of this level -- kept as the reference has it)
+      GLBX(glb_mg_partition(L.ctx, L.X, L.Y, L.dof, by_colour ? mg->n_vectors[lvl] : 0, mg->null_vectors[lvl][num_null_vec],
+                            mg->null_vectors[lvl][num_null_vec + mg->n_vectors[lvl] / 2]));
+      return;
+    default:
+      throw Error("null_partition: only BLOCK_NONE and BLOCK_EO are on the accelerated path");
+  }
+}
+
+}  // namespace
+
+void null_partition_staggered_dev(mg_operator_struct_complex_dev* mg, int num_null_vec, blocking_strategy bstrat) {
+  partition(mg, num_null_vec, bstrat, false);
+}
+
+void null_partition_coarse_dev(mg_operator_struct_complex_dev* mg, int num_null_vec, blocking_strategy bstrat) {
+  // null_gen.cpp:112: BLOCK_TOPO partitions the coarse levels like BLOCK_EO
+  partition(mg, num_null_vec, bstrat == BLOCK_TOPO ? BLOCK_EO : bstrat, true);
+}
+
+void null_generate_random_smooth_dev(mg_operator_struct_complex_dev* mg, null_vector_params* nv,
+                                     inversion_verbose_struct* verb, std::mt19937* generator) {
+  const Level L = level_of(mg);
+  const int lvl = mg->curr_level;
+  if (nv->null_prec != NULL_PRECOND_NONE)
+    throw Error("null_generate_random_smooth_dev: preconditioned null-vector solves are not on the accelerated path");
+  if (nv->null_partitions < 1 || mg->n_vectors[lvl] % nv->null_partitions != 0)
+    throw Error("null_generate_random_smooth_dev: n_vectors must be a multiple of null_partitions");
+  glb_operator* op = mg->stencils[lvl];
+  zcplx** null = mg->null_vectors[lvl];
+  const int n_gen = mg->n_vectors[lvl] / nv->null_partitions;
+  const int stride = nv->n_null_vectors[lvl];
+  const int n_split = nv->do_ortho_eo ? nv->null_partitions : 1;
+  void (*apply)(zcplx*, zcplx*, void*) = &glb200_apply_dev;
+
+  // null_gen.cpp:199-206
+  minv_inverter_params solve;
+  solve.tol = nv->null_precisions[lvl];
+  solve.max_iters = nv->null_max_iters[lvl];
+  solve.restart = nv->null_restart;
+  solve.restart_freq = nv->null_restart_freq;
+  solve.minres_omega = nv->null_relaxation;
+  solve.sor_omega = nv->null_relaxation;
+  solve.bicgstabl_l = nv->null_bicgstab_l;
+
+  Blas<zcplx> B = {L.ctx, (size_t)L.size};
+  Work<zcplx> W(B);
+  zcplx* rand_guess = W.get();
+  zcplx* Arand_guess = W.get();
+  std::vector<zcplx> host(L.size);
+
+  for (int i = 0; i < n_gen; i++) {
+    // a gaussian source (:219), orthogonal to the vectors found so far (:222-238)
+    gaussian_host(host, *generator);
+    GLBX(glb_vec_upload(L.ctx, GLB_COMPLEX, B.n, rand_guess, host.data()));
+    for (int j = 0; j < i; j++) {
+      for (int k = 0; k < n_split; k++) {
+        zcplx* prev = null[j + k * stride];
+        orthogonal_dev(B, rand_guess, prev);
+        if (nv->do_global_ortho_conj) {
+          conj_dev(B, prev);
+          orthogonal_dev(B, rand_guess, prev);
+          conj_dev(B, prev);
+        }
+      }
+    }
+
+    // the residual equation A x = -A x0 (:241-250)
+    B.zero(Arand_guess);
+    GLBX(glb_op_apply(op, Arand_guess, rand_guess));
+    mg->dslash_count->nullvectors[lvl]++;
+    GLBX(glb_rscale(L.ctx, GLB_COMPLEX, B.n, Arand_guess, -1.0, Arand_guess));
+
+    // :252-258 (the initial guess is whatever null[i] holds: zero after allocation)
+    inversion_info invif = minv_unpreconditioned_dev(null[i], Arand_guess, L.size, nv->null_gen, solve, apply, (void*)op, verb);
+    mg->dslash_count->nullvectors[lvl] += invif.ops_count;
+
+    // undo the residual equation (:316-319)
+    B.add(null[i], rand_guess, null[i]);
+
+    // split now if asked to (:322-335)
+    if (nv->do_ortho_eo) {
+      if (lvl == 0)
+        null_partition_staggered_dev(mg, i, nv->bstrat);
+      else
+        null_partition_coarse_dev(mg, i, nv->bstrat);
+    }
+    for (int k = 0; k < n_split; k++) normalize_dev(B, null[i + k * stride]);  // :338-341
+
+    // orthogonalise against the previous vectors (:344-366)
+    for (int j = 0; j < i; j++) {
+      if (!nv->quiet) std::cout << "[L" << lvl + 1 << "_NULLVEC]: Pre-orthog cosines of " << j << "," << i << " are: ";
+      for (int k = 0; k < n_split; k++) {
+        zcplx* vi = null[i + k * stride];
+        zcplx* vj = null[j + k * stride];
+        if (!nv->quiet) std::cout << std::abs(B.dot(vi, vj) / sqrt(B.norm2sq(vi) * B.norm2sq(vj))) << " ";
+        orthogonal_dev(B, vi, vj);
+        if (nv->do_global_ortho_conj) {
+          conj_dev(B, vj);
+          orthogonal_dev(B, vi, vj);
+          conj_dev(B, vj);
+        }
+      }
+      if (!nv->quiet) std::cout << "\n";
+    }
+    for (int k = 0; k < n_split; k++) normalize_dev(B, null[i + k * stride]);  // :369-372
+  }
+
+  // split afterwards otherwise (:376-397)
+  if (!nv->do_ortho_eo) {
+    for (int i = 0; i < n_gen; i++) {
+      if (lvl == 0)
+        null_partition_staggered_dev(mg, i, nv->bstrat);
+      else
+        null_partition_coarse_dev(mg, i, nv->bstrat);
+      for (int k = 0; k < nv->null_partitions; k++) normalize_dev(B, null[i + k * stride]);
+    }
+  }
+}
+
+void block_orthonormalize_dev(mg_operator_struct_complex_dev* mg) {
+  const Level L = level_of(mg);
+  const int lvl = mg->curr_level;
+  GLBX(glb_mg_block_orthonormalize(L.ctx, L.X, L.Y, L.dof, mg->blocksize_x[lvl], mg->blocksize_y[lvl], mg->n_vectors[lvl],
+                                   (void* const*)mg->null_vectors[lvl]));
+}
+
+void generate_coarse_from_fine_stencil_dev(mg_operator_struct_complex_dev* mg, bool ignore_shifts) {
+  const Level L = level_of(mg);
+  const int lvl = mg->curr_level;
+  if (!mg->transfers) throw Error("generate_coarse_from_fine_stencil_dev: no transfer table");
+  if (mg->transfers[lvl]) {
+    glb_mg_transfer_destroy(mg->transfers[lvl]);
+    mg->transfers[lvl] = 0;
+  }
+  GLBX(glb_mg_transfer_create_dev(L.ctx, L.X, L.Y, L.dof, mg->blocksize_x[lvl], mg->blocksize_y[lvl], mg->n_vectors[lvl],
+                                  (const void* const*)mg->null_vectors[lvl], &mg->transfers[lvl]));
+  if (mg->stencils[lvl + 1]) {
+    glb_op_destroy(mg->stencils[lvl + 1]);
+    mg->stencils[lvl + 1] = 0;
+  }
+  GLBX(glb_mg_galerkin(mg->transfers[lvl], mg->stencils[lvl], ignore_shifts ? 1 : 0, &mg->stencils[lvl + 1]));
+}

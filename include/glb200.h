@@ -145,6 +145,14 @@ int glb_op_create_stencil2d(glb_context* ctx, const void* clover, const void* ho
                             const double dof_shift[2], glb_operator** op);
 int glb_op_destroy(glb_operator* op);
 int glb_op_set_mass(glb_operator* op, double mass);
+/* stencil2d operators: the three diagonal shifts of stencil_2d (coarse_stencil.h:62-71: shift, eo_shift, dof_shift;
+ * applied by coarse_stencil.cpp:153-169).  The reference's set-up changes them in place between the null-vector
+ * generation and the final build (aa_mg_square_staggered_u1.cpp:757, :933, :996, :1086); NULL leaves one unchanged. */
+int glb_op_set_shifts(glb_operator* op, const double shift[2], const double eo_shift[2], const double dof_shift[2]);
+int glb_op_get_shifts(const glb_operator* op, double shift[2], double eo_shift[2], double dof_shift[2]);
+/* stencil2d operators, single rank: copy the matrices back to host arrays in the reference layout
+ * (clover nc*nc*V, hopping 4*nc*nc*V complex; either may be NULL) -- what stencil_2d::clover / ::hopping hold */
+int glb_op_stencil_download(glb_operator* op, void* h_clover, void* h_hopping);
 int glb_op_dtype(const glb_operator* op);
 size_t glb_op_local_size(const glb_operator* op);   /* elements held by this rank              */
 size_t glb_op_global_size(const glb_operator* op);
@@ -273,13 +281,18 @@ int glb_mg_transfer_create_dev(glb_context* ctx, int Xf, int Yf, int dof_f, int 
 /* block_orthonormalize + block_normalize (mg_complex.cpp:191-370) in place on nvec device vectors */
 int glb_mg_block_orthonormalize(glb_context* ctx, int Xf, int Yf, int dof_f, int bx, int by, int nvec,
                                 void* const* d_null_vectors);
-/* BLOCK_EO partition of one null vector (null_gen.cpp:26-35 top level: by_colour = 0, odd SITES move to odd_out;
- * :109-126 coarser levels: by_colour = 1, the upper half of the colour index moves); even_io keeps the rest */
-int glb_mg_partition(glb_context* ctx, int X, int Y, int dof, int by_colour, void* d_even_io, void* d_odd_out);
+/* BLOCK_EO partition of one null vector of X*Y*dof elements: its "odd" part moves to odd_out (only those elements
+ * of odd_out are written) and is zeroed in even_io.  colour_period = 0: odd SITES (x+y odd; top level,
+ * null_partition_staggered, null_gen.cpp:26-35).  colour_period = m > 0: elements with (index % m) >= m/2
+ * (null_partition_coarse, null_gen.cpp:109-126, where m = n_vectors[curr_level]). */
+int glb_mg_partition(glb_context* ctx, int X, int Y, int dof, int colour_period, void* d_even_io, void* d_odd_out);
 /* Galerkin coarse operator P^dag A P of a five-point stencil2d fine operator (what generate_coarse_from_fine_stencil,
- * mg_complex.cpp:827-1026, assembles by probing; fine shifts are folded into the coarse clover): a new stencil2d
- * operator on the coarse lattice of the transfer, nc = nvec.  Single rank. */
-int glb_mg_galerkin(glb_mg_transfer* t, glb_operator* fine, glb_operator** coarse);
+ * mg_complex.cpp:827-1026, assembles by probing with 1 + 8 applies per coarse colour): a new stencil2d operator on
+ * the coarse lattice of the transfer, nc = nvec, all three coarse shifts zero.  ignore_shifts = 0: the fine shifts
+ * are folded into the coarse clover; != 0: they are left out (the caller then sets the coarse shifts with
+ * glb_op_set_shifts, aa_mg_square_staggered_u1.cpp:1080-1093).  Single rank; the coarse lattice needs an even
+ * number (>= 2) of sites per direction, as the reference's even/odd probing does. */
+int glb_mg_galerkin(glb_mg_transfer* t, glb_operator* fine, int ignore_shifts, glb_operator** coarse);
 size_t glb_mg_fine_size(const glb_mg_transfer* t);
 size_t glb_mg_coarse_size(const glb_mg_transfer* t);
 int glb_mg_prolong(glb_mg_transfer* t, void* d_fine, const void* d_coarse);

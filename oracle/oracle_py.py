@@ -220,12 +220,32 @@ class RefMg:
     INNER = dict(NONE=0, MINRES=1, CG=2, GCR=3, BICGSTAB=4, CR=5, BICGSTAB_L=6)
     SMOOTH = dict(CG=0, CR=1, GCR=2, BICGSTAB=3, BICGSTAB_L=4, GMRES=5, SOR=6, MINRES=7, INVALID=-1)
 
-    def __init__(self, orc, X, Y, links, mass, blocks, nvecs, null):
+    def __init__(self, orc, X, Y, links, mass, blocks, nvecs, null, ignore_shifts=False):
+        """ignore_shifts: build the stencils the way the reference's driver does (mass in the shift of every level,
+        generate_coarse_from_fine_stencil(..., true)); default: shifts folded into the coarse clover."""
+        self._bind(orc)
+        self.n_refine = len(blocks)
+        self.links = np.ascontiguousarray(links, dtype=np.complex128)
+        blocks_a = np.array(blocks, dtype=np.int32)
+        nvecs_a = np.array(nvecs, dtype=np.int32)
+        self._null = [[np.ascontiguousarray(v, dtype=np.complex128) for v in lvl] for lvl in null]
+        lvl_ptrs = []
+        for lvl in self._null:
+            lvl_ptrs.append((C.c_void_p * len(lvl))(*[v.ctypes.data for v in lvl]))
+        top = (C.c_void_p * len(lvl_ptrs))(*[C.cast(a, C.c_void_p).value for a in lvl_ptrs])
+        self._keep = (lvl_ptrs, top, blocks_a, nvecs_a)
+        self.h = self.L.refmg_create2(X, Y, _ptr(self.links), mass, self.n_refine, _ptr(blocks_a), _ptr(nvecs_a),
+                                      C.cast(top, C.c_void_p), int(ignore_shifts))
+
+    def _bind(self, orc):
         if orc.kind != "reference":
             raise RuntimeError("RefMg needs oracle/_ref/libref_oracle.so (the reference-compiled checker)")
         L = orc.lib
         vp, ci, cd = C.c_void_p, C.c_int, C.c_double
-        for name, res, args in (("refmg_create", vp, [ci, ci, vp, cd, ci, vp, vp, vp]),
+        for name, res, args in (("refmg_create2", vp, [ci, ci, vp, cd, ci, vp, vp, vp, ci]),
+                                ("refmg_setup", vp, [ci, ci, vp, cd, ci, vp, vp, ci, cd, ci, vp, vp, ci, ci, ci, ci,
+                                                     C.c_uint, ci]),
+                                ("refmg_null_counts", None, [vp, vp]),
                                 ("refmg_level_dims", None, [vp, ci, vp, vp, vp]),
                                 ("refmg_get_null", None, [vp, ci, ci, vp]),
                                 ("refmg_get_stencil", None, [vp, ci, vp, vp, vp]),
@@ -237,18 +257,33 @@ class RefMg:
             f = getattr(L, name)
             f.restype, f.argtypes = res, args
         self.L = L
+
+    @classmethod
+    def setup(cls, orc, X, Y, links, mass, blocks, nvecs, bstrat=1, null_mass=1e-2, null_gen="BICGSTAB", tol=5e-5,
+              max_iter=500, restart_freq=0, bicgstab_l=-1, do_ortho_eo=False, do_global_ortho_conj=False, seed=1337,
+              verbosity=0):
+        """The reference driver's complete set-up (aa_mg_square_staggered_u1.cpp:716-1143; oracle/ref_mg_shim.cpp
+        refmg_setup): null vectors from null_generate_random_smooth with a std::mt19937(seed), block_orthonormalize,
+        generate_coarse_from_fine_stencil(ignore_shifts=true) with the shift copied down.  nvecs[l] = total vectors
+        of refinement l (after the partition); bstrat 0 = BLOCK_NONE, 1 = BLOCK_EO."""
+        self = cls.__new__(cls)
+        self._bind(orc)
         self.n_refine = len(blocks)
         self.links = np.ascontiguousarray(links, dtype=np.complex128)
         blocks_a = np.array(blocks, dtype=np.int32)
         nvecs_a = np.array(nvecs, dtype=np.int32)
-        self._null = [[np.ascontiguousarray(v, dtype=np.complex128) for v in lvl] for lvl in null]
-        lvl_ptrs = []
-        for lvl in self._null:
-            lvl_ptrs.append((C.c_void_p * len(lvl))(*[v.ctypes.data for v in lvl]))
-        top = (C.c_void_p * len(lvl_ptrs))(*[C.cast(a, C.c_void_p).value for a in lvl_ptrs])
-        self._keep = (lvl_ptrs, top, blocks_a, nvecs_a)
-        self.h = L.refmg_create(X, Y, _ptr(self.links), mass, self.n_refine, _ptr(blocks_a), _ptr(nvecs_a),
-                                C.cast(top, C.c_void_p))
+        tol_a = np.array([tol] * self.n_refine if np.isscalar(tol) else tol, dtype=np.float64)
+        it_a = np.array([max_iter] * self.n_refine if np.isscalar(max_iter) else max_iter, dtype=np.int32)
+        self._keep = (blocks_a, nvecs_a, tol_a, it_a)
+        self.h = self.L.refmg_setup(X, Y, _ptr(self.links), mass, self.n_refine, _ptr(blocks_a), _ptr(nvecs_a), bstrat,
+                                    null_mass, self.SMOOTH[null_gen], _ptr(tol_a), _ptr(it_a), restart_freq, bicgstab_l,
+                                    int(do_ortho_eo), int(do_global_ortho_conj), seed, verbosity)
+        return self
+
+    def null_counts(self):
+        out = np.zeros(self.n_refine + 1, dtype=np.int32)
+        self.L.refmg_null_counts(self.h, _ptr(out))
+        return [int(v) for v in out]
 
     def dims(self, level):
         x, y, n = C.c_int(), C.c_int(), C.c_int()

@@ -25,6 +25,8 @@ using namespace std;
 #include "operators.h"
 #include "operators_stencil.h"
 #include "coarse_stencil.h"
+#include "null_gen.h"
+#include <random>
 
 namespace {
 
@@ -47,8 +49,8 @@ extern "C" {
 // links: reference layout, 2*X*Y complex.  block[l], nvec[l] for l < n_refine.  null[l][v]: host arrays of the
 // level-l lattice size (level 0: X*Y; level l: Vol_l * nvec[l-1]).  Levels below the first are set up after the
 // coarse stencils above them exist, exactly in the driver's order.
-void* refmg_create(int X, int Y, const double* links, double mass, int n_refine, const int* block, const int* nvec,
-                   const double* const* const* null_in) {
+static RefMg* make_struct(int X, int Y, const double* links, double mass, int n_refine, const int* block, const int* nvec,
+                          const double* const* const* null_in) {
   RefMg* h = new RefMg();
   h->n_refine = n_refine;
   h->links.assign((const zc*)links, (const zc*)links + 2 * (size_t)X * Y);
@@ -100,21 +102,16 @@ void* refmg_create(int X, int Y, const double* links, double mass, int n_refine,
     const int sz = mg.latt[i]->get_lattice_size();
     for (int j = 0; j < mg.n_vectors[i]; j++) {
       mg.null_vectors[i][j] = new zc[sz];
-      memcpy(mg.null_vectors[i][j], null_in[i][j], sizeof(zc) * sz);
+      if (null_in)
+        memcpy(mg.null_vectors[i][j], null_in[i][j], sizeof(zc) * sz);
+      else
+        zero<double>(mg.null_vectors[i][j], sz);  // aa_mg_square_staggered_u1.cpp:613-614
     }
   }
   mg.stencils = new stencil_2d*[n_refine + 1];
   for (int i = 0; i <= n_refine; i++) mg.stencils[i] = new stencil_2d(mg.latt[i], 1);
   mg.have_dagger_stencil = false;
   mg.dagger_stencils = 0;
-  get_square_staggered_u1_stencil(mg.stencils[0], &h->stagif);
-  // level by level: orthonormalise this level's null vectors, build the next stencil, step down
-  for (int n = 0; n < n_refine; n++) {
-    block_orthonormalize(&mg);
-    generate_coarse_from_fine_stencil(mg.stencils[n + 1], mg.stencils[n], &mg, false);
-    if (n != n_refine - 1) level_down(&mg);
-  }
-  for (int n = n_refine - 1; n > 0; n--) level_up(&mg);
 
   mg_precond_struct_complex& p = h->pre;
   p.in_smooth_type = MINV_GCR;
@@ -140,6 +137,111 @@ void* refmg_create(int X, int Y, const double* links, double mass, int n_refine,
   p.coarse_matrix_vector_normal = coarse_square_staggered_normal;
   p.fine_matrix_vector_normal = fine_square_staggered_normal;
   return h;
+}
+
+// links: reference layout, 2*X*Y complex.  block[l], nvec[l] for l < n_refine.  null[l][v]: host arrays of the
+// level-l lattice size (level 0: X*Y; level l: Vol_l * nvec[l-1]).  ignore_shifts: the flag handed to
+// generate_coarse_from_fine_stencil; when set the coarse shift is copied from the fine one as the driver does
+// (aa_mg_square_staggered_u1.cpp:1080-1086).
+void* refmg_create2(int X, int Y, const double* links, double mass, int n_refine, const int* block, const int* nvec,
+                    const double* const* const* null_in, int ignore_shifts) {
+  RefMg* h = make_struct(X, Y, links, mass, n_refine, block, nvec, null_in);
+  mg_operator_struct_complex& mg = h->mg;
+  if (ignore_shifts) {  // the driver's way: mass in the shift, not in the stencil (:986-996)
+    h->stagif.mass = 0.0;
+    get_square_staggered_u1_stencil(mg.stencils[0], &h->stagif);
+    h->stagif.mass = mass;
+    mg.stencils[0]->shift = mass;
+  } else {
+    get_square_staggered_u1_stencil(mg.stencils[0], &h->stagif);
+  }
+  // level by level: orthonormalise this level's null vectors, build the next stencil, step down
+  for (int n = 0; n < n_refine; n++) {
+    block_orthonormalize(&mg);
+    generate_coarse_from_fine_stencil(mg.stencils[n + 1], mg.stencils[n], &mg, ignore_shifts != 0);
+    if (ignore_shifts) mg.stencils[n + 1]->shift = mg.stencils[n]->shift;
+    if (n != n_refine - 1) level_down(&mg);
+  }
+  for (int n = n_refine - 1; n > 0; n--) level_up(&mg);
+  return h;
+}
+void* refmg_create(int X, int Y, const double* links, double mass, int n_refine, const int* block, const int* nvec,
+                   const double* const* const* null_in) {
+  return refmg_create2(X, Y, links, mass, n_refine, block, nvec, null_in, 0);
+}
+
+// The complete set-up of the reference's driver for --operator staggered --null-operator staggered
+// (aa_mg_square_staggered_u1.cpp:716-1143): null vectors from null_generate_random_smooth (null_gen.cpp:193) on the
+// null-generation stencils (mass = null_mass in the shift), block_orthonormalize, coarse null-generation stencil with
+// ignore_shifts = true and the shift copied down, level_down; afterwards the final stencils with the true mass.
+//   nvec[l]       total null vectors of refinement l (= n_null[l] * partitions)
+//   bstrat        blocking_strategy (null_gen.h:15-21): 0 none (1 partition), 1 even/odd (2 partitions)
+//   null_gen      minv_inverter of the smoothing solve; tol[l], max_iter[l] per refinement
+//   restart_freq  > 0: restarted solver;  bicgstab_l: l of BiCGStab-l
+//   seed          std::mt19937 seed of the gaussian sources
+void* refmg_setup(int X, int Y, const double* links, double mass, int n_refine, const int* block, const int* nvec,
+                  int bstrat, double null_mass, int null_gen, const double* tol, const int* max_iter, int restart_freq,
+                  int bicgstab_l, int do_ortho_eo, int do_global_ortho_conj, unsigned seed, int verbosity) {
+  RefMg* h = make_struct(X, Y, links, mass, n_refine, block, nvec, 0);
+  mg_operator_struct_complex& mg = h->mg;
+  null_vector_params nv;
+  nv.opt_null = STAGGERED;
+  nv.null_gen = (minv_inverter)null_gen;
+  nv.null_prec = NULL_PRECOND_NONE;
+  nv.null_restart = restart_freq > 0;
+  nv.null_restart_freq = restart_freq;
+  nv.null_bicgstab_l = bicgstab_l;
+  nv.null_mass = null_mass;
+  nv.bstrat = (blocking_strategy)bstrat;
+  nv.null_partitions = (bstrat == BLOCK_EO) ? 2 : 1;  // aa_mg_square_staggered_u1.cpp:412-427
+  nv.do_global_ortho_conj = do_global_ortho_conj != 0;
+  nv.do_ortho_eo = do_ortho_eo != 0;
+  for (int i = 0; i < n_refine; i++) {
+    nv.n_null_vectors.push_back(nvec[i] / nv.null_partitions);
+    nv.null_precisions.push_back(tol[i]);
+    nv.null_max_iters.push_back(max_iter[i]);
+  }
+  std::mt19937 generator(seed);
+  inversion_verbose_struct verb;
+  verb.verbosity = (inversion_verbose_level)verbosity;
+  verb.verb_prefix = "";
+  verb.precond_verbosity = VERB_NONE;
+  verb.precond_verb_prefix = "";
+  // null-generation stencils (:724-757): mass encoded in the shift
+  h->stagif.mass = 0.0;
+  get_square_staggered_u1_stencil(mg.stencils[0], &h->stagif);
+  h->stagif.mass = mass;
+  mg.stencils[0]->shift = null_mass;
+  for (int n = 0; n < n_refine; n++) {
+    verb.verb_prefix = "[L" + to_string(mg.curr_level + 1) + "_NULLVEC]: ";
+    null_generate_random_smooth(&mg, &nv, &verb, &generator);
+    block_orthonormalize(&mg);
+    if (n != n_refine - 1) {
+      generate_coarse_from_fine_stencil(mg.stencils[mg.curr_level + 1], mg.stencils[mg.curr_level], &mg, true);
+      mg.stencils[mg.curr_level + 1]->shift = mg.stencils[mg.curr_level]->shift;
+      level_down(&mg);
+    }
+  }
+  for (int n = 1; n < n_refine; n++) level_up(&mg);
+  // final stencils with the true mass (:982-1143)
+  for (int n = 0; n <= n_refine; n++) mg.stencils[n]->clear_stencils();
+  h->stagif.mass = 0.0;
+  get_square_staggered_u1_stencil(mg.stencils[0], &h->stagif);
+  h->stagif.mass = mass;
+  mg.stencils[0]->shift = mass;
+  for (int n = 0; n < n_refine; n++) {
+    generate_coarse_from_fine_stencil(mg.stencils[n + 1], mg.stencils[n], &mg, true);
+    mg.stencils[n + 1]->shift = mg.stencils[n]->shift;
+    if (n != n_refine - 1) level_down(&mg);
+  }
+  for (int n = 1; n < n_refine; n++) level_up(&mg);
+  return h;
+}
+
+// dslash_tracker::nullvectors per level (mg_complex.h:104-136)
+void refmg_null_counts(void* hv, int* out) {
+  RefMg* h = (RefMg*)hv;
+  for (int i = 0; i <= h->n_refine; i++) out[i] = h->mg.dslash_count->nullvectors[i];
 }
 
 void refmg_free(void* hv) {

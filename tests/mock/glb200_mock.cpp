@@ -362,4 +362,125 @@ int glb_mg_restrict(glb_mg_transfer* t, void* d_coarse, const void* d_fine) {
   }
   return GLB_OK;
 }
+// ---- multigrid set-up: host loops in the reference's order
+int glb_rscale(glb_context*, int dt, size_t n, const void* x, double sc, void* out) {
+  BOTH(dt, { for (size_t i = 0; i < n; i++) { T v = ((const T*)x)[i]; v *= sc; ((T*)out)[i] = v; } });
+  return GLB_OK;
+}
+int glb_op_set_shifts(glb_operator* o, const double sh[2], const double eo[2], const double df[2]) {
+  if (sh) o->op->shift = cplx(sh[0], sh[1]);
+  if (eo) o->op->eo_shift = cplx(eo[0], eo[1]);
+  if (df) o->op->dof_shift = cplx(df[0], df[1]);
+  return GLB_OK;
+}
+int glb_op_get_shifts(const glb_operator* o, double sh[2], double eo[2], double df[2]) {
+  if (sh) { sh[0] = o->op->shift.real(); sh[1] = o->op->shift.imag(); }
+  if (eo) { eo[0] = o->op->eo_shift.real(); eo[1] = o->op->eo_shift.imag(); }
+  if (df) { df[0] = o->op->dof_shift.real(); df[1] = o->op->dof_shift.imag(); }
+  return GLB_OK;
+}
+int glb_op_stencil_download(glb_operator* o, void* cl, void* hp) {
+  if (cl) std::memcpy(cl, o->op->clover.data(), o->op->clover.size() * sizeof(cplx));
+  if (hp) std::memcpy(hp, o->op->hopping.data(), o->op->hopping.size() * sizeof(cplx));
+  return GLB_OK;
+}
+int glb_mg_transfer_create_dev(glb_context* c, int Xf, int Yf, int dof_f, int bx, int by, int nvec,
+                               const void* const* d_null_vectors, glb_mg_transfer** out) {
+  return glb_mg_transfer_create(c, Xf, Yf, dof_f, bx, by, nvec, d_null_vectors, out);
+}
+// mg_complex.cpp:259-370 block_orthonormalize followed by block_normalize (:191-256)
+int glb_mg_block_orthonormalize(glb_context*, int Xf, int Yf, int dof_f, int bx, int by, int nvec, void* const* nulls) {
+  g_calls++;
+  cplx** nv = (cplx**)nulls;
+  const int Xc = Xf / bx, Yc = Yf / by;
+  for (int b = 0; b < Xc * Yc; b++) {
+    const int x0 = (b % Xc) * bx, y0 = (b / Xc) * by;
+    std::vector<size_t> idx;
+    for (int y = y0; y < y0 + by; y++)
+      for (int x = x0; x < x0 + bx; x++)
+        for (int d = 0; d < dof_f; d++) idx.push_back(((size_t)y * Xf + x) * dof_f + d);
+    for (int c = 1; c < nvec; c++) {
+      double norm = 0.0;
+      for (size_t k = 0; k < idx.size(); k++) norm += real(conj(nv[c - 1][idx[k]]) * nv[c - 1][idx[k]]);
+      norm = sqrt(norm);
+      for (size_t k = 0; k < idx.size(); k++) nv[c - 1][idx[k]] /= norm;
+      for (int m = 0; m < c; m++) {
+        cplx dot_prod = 0.0;
+        for (size_t k = 0; k < idx.size(); k++) dot_prod += conj(nv[m][idx[k]]) * nv[c][idx[k]];
+        for (size_t k = 0; k < idx.size(); k++) nv[c][idx[k]] -= dot_prod * nv[m][idx[k]];
+      }
+    }
+    for (int c = 0; c < nvec; c++) {
+      double norm = 0.0;
+      for (size_t k = 0; k < idx.size(); k++) norm += real(conj(nv[c][idx[k]]) * nv[c][idx[k]]);
+      norm = sqrt(norm);
+      for (size_t k = 0; k < idx.size(); k++) nv[c][idx[k]] /= norm;
+    }
+  }
+  return GLB_OK;
+}
+// null_gen.cpp:26-35 (by_colour = 0) / :109-126 (by_colour = 1)
+int glb_mg_partition(glb_context*, int X, int Y, int dof, int colour_period, void* even_io, void* odd_out) {
+  g_calls++;
+  cplx* e = (cplx*)even_io; cplx* o = (cplx*)odd_out;
+  const size_t n = (size_t)X * Y * dof;
+  for (size_t i = 0; i < n; i++) {
+    bool odd;
+    if (colour_period > 0) {
+      odd = (int)(i % colour_period) >= colour_period / 2;
+    } else {
+      const size_t site = i / dof;
+      odd = ((site % X + site / X) % 2) != 0;
+    }
+    if (odd) { o[i] = e[i]; e[i] = 0.0; }
+  }
+  return GLB_OK;
+}
+// P^dag A P summed directly (the device kernel's formulation of mg_complex.cpp:827-1026)
+int glb_mg_galerkin(glb_mg_transfer* t, glb_operator* fine, int ignore_shifts, glb_operator** coarse) {
+  g_calls++;
+  const PortOp& f = *fine->op;
+  const int nv = t->nvec, df = t->dof_f, Xf = t->Xf, Yf = t->Yf, Xc = t->Xc, Yc = t->Yc;
+  if (f.has_two || (Xc & 1) || (Yc & 1) || Xc < 2 || Yc < 2) return GLB_ERR_ARG;
+  const size_t Lf = (size_t)Xf * Yf * df, per = (size_t)Xc * Yc * nv * nv;
+  std::vector<cplx> cl(per, 0.0), hp(4 * per, 0.0);
+  const bool us = !ignore_shifts && std::abs(f.shift) != 0.0, ue = !ignore_shifts && std::abs(f.eo_shift) != 0.0,
+             ud = !ignore_shifts && std::abs(f.dof_shift) != 0.0;
+  for (size_t cs = 0; cs < (size_t)Xc * Yc; cs++) {
+    const int xc = (int)(cs % Xc), yc = (int)(cs / Xc);
+    for (int i = 0; i < nv; i++)
+      for (int j = 0; j < nv; j++) {
+        cplx acc_c = 0.0, acc_h[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int y = yc * t->by; y < (yc + 1) * t->by; y++)
+          for (int x = xc * t->bx; x < (xc + 1) * t->bx; x++) {
+            const size_t site = (size_t)y * Xf + x;
+            const int xn[4] = {(x + 1) % Xf, x, (x + Xf - 1) % Xf, x};
+            const int yn[4] = {y, (y + 1) % Yf, y, (y + Yf - 1) % Yf};
+            const bool inside[4] = {(x + 1) % t->bx != 0, (y + 1) % t->by != 0, x % t->bx != 0, y % t->by != 0};
+            for (int r = 0; r < df; r++) {
+              const size_t fi = site * df + r;
+              const cplx ci = t->null[i][fi];
+              cplx row = 0.0;
+              for (int c = 0; c < df; c++) row += f.clover[c + df * fi] * t->null[j][site * df + c];
+              const cplx self = t->null[j][fi];
+              if (us) row += f.shift * self;
+              if (ue) row += (((x + y) & 1) ? -f.eo_shift : f.eo_shift) * self;
+              if (ud) row += (r < df / 2 ? f.dof_shift : -f.dof_shift) * self;
+              acc_c += conj(ci) * row;
+              for (int d = 0; d < 4; d++) {
+                const size_t g = ((size_t)yn[d] * Xf + xn[d]) * df;
+                cplx h = 0.0;
+                for (int c = 0; c < df; c++) h += f.hopping[c + df * fi + d * df * Lf] * t->null[j][g + c];
+                if (inside[d]) acc_c += conj(ci) * h; else acc_h[d] += conj(ci) * h;
+              }
+            }
+          }
+        const size_t o = (cs * nv + i) * nv + j;
+        cl[o] = acc_c;
+        for (int d = 0; d < 4; d++) hp[o + d * per] = acc_h[d];
+      }
+  }
+  const double z[2] = {0.0, 0.0};
+  return glb_op_create_stencil2d(fine->ctx, cl.data(), hp.data(), 0, Xc, Yc, nv, z, z, z, coarse);
+}
 }  // extern "C"
