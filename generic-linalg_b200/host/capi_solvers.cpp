@@ -403,11 +403,12 @@ typedef struct glbx_mg {
   // set-up on the device (glbx_mg_setup): this handle then owns the coarse operators, the transfers and the
   // device null vectors; the level-0 operator stays the caller's
   bool owns_hierarchy;
+  glb_context* ctx;  // of the set-up (the level-0 operator may be destroyed by its owner before this handle)
   std::vector<int> bx, by, nvec;
   std::vector<std::vector<zc*> > null_dev;
   std::vector<zc**> null_tab;
   double setup_seconds[4];  // null vectors, block orthonormalisation, transfers + Galerkin products, total
-  glbx_mg() : owns_hierarchy(false) { setup_seconds[0] = setup_seconds[1] = setup_seconds[2] = setup_seconds[3] = 0.0; }
+  glbx_mg() : owns_hierarchy(false), ctx(0) { setup_seconds[0] = setup_seconds[1] = setup_seconds[2] = setup_seconds[3] = 0.0; }
 } glbx_mg;
 
 static void mg_defaults(glbx_mg* h, int n_refine) {
@@ -447,7 +448,7 @@ glbx_mg* glbx_mg_create(int n_refine, glb_operator** level_ops, glb_mg_transfer*
 void glbx_mg_destroy(glbx_mg* h) {
   if (!h) return;
   if (h->owns_hierarchy) {
-    glb_context* ctx = h->ops[0] ? glb_op_context(h->ops[0]) : 0;
+    glb_context* ctx = h->ctx;
     for (size_t i = 1; i < h->ops.size(); i++)
       if (h->ops[i]) glb_op_destroy(h->ops[i]);
     for (size_t i = 0; i < h->trs.size(); i++)
@@ -478,6 +479,7 @@ glbx_mg* glbx_mg_setup(glb_operator* fine, int X, int Y, int n_refine, const int
   bool shifted = false;
   try {
     glb_context* ctx = glb_op_context(fine);
+    h->ctx = ctx;
     h->owns_hierarchy = true;
     h->ops.assign(n_refine + 1, (glb_operator*)0);
     h->ops[0] = fine;

@@ -789,6 +789,111 @@ GLB200_DEF_BICGL(zcplx)
 GLB200_DEF_VPGCR(double)
 GLB200_DEF_VPGCR(zcplx)
 
+namespace {
+// ------------------------------------------------------------------------------------------ SOR, MinRes
+// generic_sor.cpp:24-117 / :122-209.  x_{n+1} = x_n + omega (b - A x_n); the convergence test looks at the residual
+// of x_n, and on convergence the reference returns x_n (its xnew is dropped), so x is advanced after the test.
+template <typename T>
+inversion_info sor_dev(T* x, T* b, int size, int max_iter, double eps, double omega, void (*fn)(T*, T*, void*),
+                       void* extra, inversion_verbose_struct* verb) {
+  inversion_info inf;
+  DevOp<T> A = make_op<T>(fn, extra, size);
+  Blas<T> B = {A.ctx, (size_t)size};
+  Work<T> W(B);
+  T *Ax = W.get(), *t = W.get();
+  std::ostringstream ss;
+  ss << "SOR_" << omega;
+  const double bsqrt = sqrt(B.norm2sq(b));
+  double rsq = 0.0;
+  int k;
+  for (k = 0; k < max_iter; k++) {
+    A.apply(Ax, x);
+    rsq = B.diffnorm2sq(Ax, b);  // |check|^2 with check = Ax - b
+    print_verbosity_resid(verb, ss.str(), k + 1, A.ops, sqrt(rsq) / bsqrt);
+    if (sqrt(rsq) < eps * bsqrt) break;
+    B.sub(b, Ax, t);
+    B.axpy(T(omega), t, x);  // x = x + omega (b - Ax)
+  }
+  inf.success = (k != max_iter);
+  if (inf.success && !IsComplex<T>::value) k++;  // only the real overload counts the last iteration (:83 vs :180)
+  A.apply(Ax, x);
+  const double truersq = B.diffnorm2sq(Ax, b);
+  inf.ops_count = A.ops;
+  // generic_sor.cpp:104: the summary line is printed from invif.resSq before it is assigned (0)
+  print_verbosity_summary(verb, ss.str(), inf.success, k, inf.ops_count, sqrt(inf.resSq) / bsqrt);
+  inf.resSq = truersq;
+  inf.iter = k;
+  std::ostringstream ss2;
+  ss2 << "SOR omega=" << omega;
+  inf.name = ss2.str();
+  return inf;
+}
+
+// generic_minres.cpp:22-117 / :128-232 (Saad 5.3.2 with a relaxation factor): p = A r, alpha = omega <p,r>/|p|^2,
+// x += alpha r, r -= alpha p.  <p,r> and |p|^2 come from one pass, the update and |r|^2 from another.
+template <typename T>
+inversion_info minres_dev(T* x, T* b, int size, int max_iter, double eps, double omega, void (*fn)(T*, T*, void*),
+                          void* extra, inversion_verbose_struct* verb) {
+  inversion_info inf;
+  DevOp<T> A = make_op<T>(fn, extra, size);
+  Blas<T> B = {A.ctx, (size_t)size};
+  Work<T> W(B);
+  T *p = W.get(), *r = W.get();
+  std::ostringstream ss;
+  ss << "MR_" << omega;
+  const double bsqrt = sqrt(B.norm2sq(b));
+  A.apply(p, x);
+  B.sub(b, p, r);
+  double rsq = 0.0;
+  int k;
+  for (k = 0; k < max_iter; k++) {
+    A.apply(p, r);
+    double dn[3];
+    GLBX(glb_dot_norm(A.ctx, Traits<T>::dtype, size, p, r, dn));  // <p,r>, |p|^2
+    T alpha = Traits<T>::unpack(dn) / dn[2];
+    alpha *= omega;
+    rsq = B.update_xr_norm(alpha, r, x, -alpha, p, r);
+    print_verbosity_resid(verb, ss.str(), k + 1, A.ops, sqrt(rsq) / bsqrt);
+    if (sqrt(rsq) < eps * bsqrt) break;
+  }
+  inf.success = (k != max_iter);
+  if (inf.success && !IsComplex<T>::value) k++;  // :91 vs :204
+  A.apply(p, x);
+  const double truersq = B.diffnorm2sq(p, b);
+  inf.ops_count = A.ops;
+  print_verbosity_summary(verb, ss.str(), inf.success, k, inf.ops_count, sqrt(truersq) / bsqrt);
+  inf.resSq = truersq;
+  inf.iter = k;
+  inf.name = "Minimum Residual (MinRes)";
+  return inf;
+}
+
+}  // namespace
+
+#define GLB200_DEF_RELAX(T)                                                                                       \
+  inversion_info minv_vector_sor_dev(T* phi, T* phi0, int size, int max_iter, double eps, double omega,           \
+                                     void (*mv)(T*, T*, void*), void* extra, inversion_verbose_struct* verb) {    \
+    try {                                                                                                         \
+      return sor_dev<T>(phi, phi0, size, max_iter, eps, omega, mv, extra, verb);                                  \
+    } catch (const std::exception& e) {                                                                           \
+      return failed("SOR", e);                                                                                    \
+    }                                                                                                             \
+  }                                                                                                               \
+  inversion_info minv_vector_minres_dev(T* phi, T* phi0, int size, int max_iter, double eps, double omega,        \
+                                        void (*mv)(T*, T*, void*), void* extra, inversion_verbose_struct* verb) { \
+    try {                                                                                                         \
+      return minres_dev<T>(phi, phi0, size, max_iter, eps, omega, mv, extra, verb);                               \
+    } catch (const std::exception& e) {                                                                           \
+      return failed("MinRes", e);                                                                                 \
+    }                                                                                                             \
+  }                                                                                                               \
+  inversion_info minv_vector_minres_dev(T* phi, T* phi0, int size, int max_iter, double eps,                      \
+                                        void (*mv)(T*, T*, void*), void* extra, inversion_verbose_struct* verb) { \
+    return minv_vector_minres_dev(phi, phi0, size, max_iter, eps, 1.0, mv, extra, verb);                          \
+  }
+GLB200_DEF_RELAX(double)
+GLB200_DEF_RELAX(zcplx)
+
 // generic_inverter.cpp:18-190 on device vectors: the enum dispatch the MG smoother uses
 template <typename T>
 static inversion_info dispatch_dev(T* lhs, T* rhs, int size, minv_inverter type, minv_inverter_params& p,
@@ -814,7 +919,11 @@ static inversion_info dispatch_dev(T* lhs, T* rhs, int size, minv_inverter type,
     case MINV_GMRES:
       return p.restart ? minv_vector_gmres_restart_dev(lhs, rhs, size, p.max_iters, p.tol, p.restart_freq, mv, extra, verb)
                        : minv_vector_gmres_dev(lhs, rhs, size, p.max_iters, p.tol, mv, extra, verb);
-    default:  // SOR / MinRes are outside the accelerated path
+    case MINV_SOR:     // restarting makes no sense for these two (generic_inverter.cpp:86-95)
+      return minv_vector_sor_dev(lhs, rhs, size, p.max_iters, p.tol, p.sor_omega, mv, extra, verb);
+    case MINV_MINRES:
+      return minv_vector_minres_dev(lhs, rhs, size, p.max_iters, p.tol, p.minres_omega, mv, extra, verb);
+    default:
       return inversion_info();
   }
 }

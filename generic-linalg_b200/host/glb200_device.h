@@ -64,6 +64,20 @@ GLB200_DECL_DEV_RESTART(minv_vector_bicgstab_restart_dev)
 GLB200_DECL_DEV(minv_vector_gmres_dev)
 GLB200_DECL_DEV_RESTART(minv_vector_gmres_restart_dev)
 
+// generic_sor.h:14-18, generic_minres.h:16-23 (relaxation parameter omega; MinRes also without it)
+#define GLB200_DECL_DEV_RELAX(T)                                                                                   \
+  inversion_info minv_vector_sor_dev(T* d_phi, T* d_phi0, int size, int max_iter, double eps, double omega,        \
+                                     void (*matrix_vector_dev)(T*, T*, void*), void* extra_info,                   \
+                                     inversion_verbose_struct* verbosity = 0);                                     \
+  inversion_info minv_vector_minres_dev(T* d_phi, T* d_phi0, int size, int max_iter, double eps, double omega,     \
+                                        void (*matrix_vector_dev)(T*, T*, void*), void* extra_info,                \
+                                        inversion_verbose_struct* verbosity = 0);                                  \
+  inversion_info minv_vector_minres_dev(T* d_phi, T* d_phi0, int size, int max_iter, double eps,                   \
+                                        void (*matrix_vector_dev)(T*, T*, void*), void* extra_info,                \
+                                        inversion_verbose_struct* verbosity = 0);
+GLB200_DECL_DEV_RELAX(double)
+GLB200_DECL_DEV_RELAX(std::complex<double>)
+
 inversion_info minv_vector_bicgstab_l_dev(double* d_phi, double* d_phi0, int size, int max_iter, double res, int l,
                                           void (*matrix_vector_dev)(double*, double*, void*), void* extra_info,
                                           inversion_verbose_struct* verbosity = 0);
