@@ -148,6 +148,8 @@ def libs():
         "glbx_host_solve_multi": (ci, [ci, C.POINTER(OpDesc), C.POINTER(vp), vp, ci, ci, ci, cd, vp, ci, ci,
                                        C.POINTER(Result)]),
         "glbx_host_solve_precond": (ci, [ci, C.POINTER(OpDesc), vp, vp, ci, cd, ci, ci, ci, cd, ci, C.POINTER(Result)]),
+        "glbx_host_solve_relax": (ci, [ci, C.POINTER(OpDesc), vp, vp, ci, cd, cd, ci, C.POINTER(Result)]),
+        "glbx_dev_solve_relax": (ci, [ci, vp, vp, vp, ci, cd, cd, ci, C.POINTER(Result)]),
         "glbx_mg_create": (vp, [ci, C.POINTER(vp), C.POINTER(vp)]), "glbx_mg_destroy": (None, [vp]),
         "glbx_mg_set": (None, [vp, ci, ci, ci, ci, ci, ci, cd, ci, ci]),
         "glbx_mg_vcycle": (ci, [vp, vp, vp]),
@@ -634,6 +636,22 @@ class Context:
         s = SOLVER[solver] if isinstance(solver, str) else solver
         _chk(self.ho.glbx_dev_solve(s, op.h, x.ptr, b.ptr, max_iter, eps, restart_freq, l, verbosity,
                                     C.byref(res)), "glbx_dev_solve")
+        return res.as_dict()
+
+    RELAX = dict(SOR=0, MINRES=1)
+
+    def solve_relax(self, which, op, x, b, max_iter=10000, eps=1e-10, omega=1.0, verbosity=0):
+        """minv_vector_sor_dev / minv_vector_minres_dev (generic_sor.cpp, generic_minres.cpp) on device vectors"""
+        res = Result()
+        _chk(self.ho.glbx_dev_solve_relax(self.RELAX[which], op.h, x.ptr, b.ptr, max_iter, eps, omega, verbosity,
+                                          C.byref(res)), "glbx_dev_solve_relax")
+        return res.as_dict()
+
+    def host_solve_relax(self, which, desc, x, b, max_iter=10000, eps=1e-10, omega=1.0, verbosity=0):
+        """minv_vector_sor / minv_vector_minres with host vectors (x in/out)"""
+        res = Result()
+        _chk(self.ho.glbx_host_solve_relax(self.RELAX[which], C.byref(desc), _p(x), _p(b), max_iter, eps, omega,
+                                           verbosity, C.byref(res)), "glbx_host_solve_relax")
         return res.as_dict()
 
     def solve_cg_m(self, op, xs, b, shifts, resid_freq_check=10, max_iter=10000, eps=1e-10, worst_first=False,

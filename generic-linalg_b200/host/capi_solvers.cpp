@@ -283,6 +283,43 @@ int glbx_host_solve_cg_m(const glbx_opdesc* d, void** phi, const void* phi0, int
   return GLB_OK;
 }
 
+// minv_vector_sor (which = 0) / minv_vector_minres (which = 1) with their relaxation parameter, host vectors
+int glbx_host_solve_relax(int which, const glbx_opdesc* d, void* phi, const void* phi0, int max_iter, double eps,
+                          double omega, int verbosity, glbx_result* out) {
+  HostOp h;
+  if (!build_host_op(d, &h)) return GLB_ERR_ARG;
+  inversion_verbose_struct v;
+  make_verb(verbosity, &v);
+  inversion_info inf;
+  if (h.cz)
+    inf = which == 0 ? minv_vector_sor((zc*)phi, (zc*)phi0, h.size, max_iter, eps, omega, h.cz, h.extra, &v)
+                     : minv_vector_minres((zc*)phi, (zc*)phi0, h.size, max_iter, eps, omega, h.cz, h.extra, &v);
+  else
+    inf = which == 0 ? minv_vector_sor((double*)phi, (double*)phi0, h.size, max_iter, eps, omega, h.cd, h.extra, &v)
+                     : minv_vector_minres((double*)phi, (double*)phi0, h.size, max_iter, eps, omega, h.cd, h.extra, &v);
+  flatten(inf, out);
+  return GLB_OK;
+}
+// the same on device vectors
+int glbx_dev_solve_relax(int which, glb_operator* op, void* d_phi, void* d_phi0, int max_iter, double eps, double omega,
+                         int verbosity, glbx_result* out) {
+  inversion_verbose_struct v;
+  make_verb(verbosity, &v);
+  const int size = (int)glb_op_local_size(op);
+  inversion_info inf;
+  if (glb_op_dtype(op) == GLB_COMPLEX) {
+    void (*cb)(zc*, zc*, void*) = &glb200_apply_dev;
+    inf = which == 0 ? minv_vector_sor_dev((zc*)d_phi, (zc*)d_phi0, size, max_iter, eps, omega, cb, op, &v)
+                     : minv_vector_minres_dev((zc*)d_phi, (zc*)d_phi0, size, max_iter, eps, omega, cb, op, &v);
+  } else {
+    void (*cb)(double*, double*, void*) = &glb200_apply_dev;
+    inf = which == 0 ? minv_vector_sor_dev((double*)d_phi, (double*)d_phi0, size, max_iter, eps, omega, cb, op, &v)
+                     : minv_vector_minres_dev((double*)d_phi, (double*)d_phi0, size, max_iter, eps, omega, cb, op, &v);
+  }
+  flatten(inf, out);
+  return GLB_OK;
+}
+
 // device vectors + a glb_operator handle (the device variant of the callback contract)
 int glbx_dev_solve(int solver, glb_operator* op, void* d_phi, void* d_phi0, int max_iter, double eps, int restart_freq,
                    int l, int verbosity, glbx_result* out) {

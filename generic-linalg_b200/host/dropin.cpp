@@ -442,6 +442,28 @@ void get_square_staggered_dagger_u1_stencil(stencil_2d* st, staggered_u1_op* s) 
                              });                                                                                   \
   }
 
+// generic_sor.cpp:24,122; generic_minres.cpp:22,120,128,236
+#define GLB200_HOST_RELAX(T)                                                                                       \
+  inversion_info minv_vector_sor(T* phi, T* phi0, int size, int max_iter, double eps, double omega,                \
+                                 void (*mv)(T*, T*, void*), void* extra, inversion_verbose_struct* verb) {         \
+    return host_solve<T>("SOR", phi, phi0, size, mv, extra, [&](T* dp, T* db, void (*cb)(T*, T*, void*), void* ce) { \
+      return minv_vector_sor_dev(dp, db, size, max_iter, eps, omega, cb, ce, verb);                                \
+    });                                                                                                            \
+  }                                                                                                                \
+  inversion_info minv_vector_minres(T* phi, T* phi0, int size, int max_iter, double eps, double omega,             \
+                                    void (*mv)(T*, T*, void*), void* extra, inversion_verbose_struct* verb) {      \
+    return host_solve<T>("MinRes", phi, phi0, size, mv, extra,                                                     \
+                         [&](T* dp, T* db, void (*cb)(T*, T*, void*), void* ce) {                                  \
+                           return minv_vector_minres_dev(dp, db, size, max_iter, eps, omega, cb, ce, verb);        \
+                         });                                                                                       \
+  }                                                                                                                \
+  inversion_info minv_vector_minres(T* phi, T* phi0, int size, int max_iter, double eps, void (*mv)(T*, T*, void*), \
+                                    void* extra, inversion_verbose_struct* verb) {                                 \
+    return minv_vector_minres(phi, phi0, size, max_iter, eps, 1.0, mv, extra, verb);                               \
+  }
+GLB200_HOST_RELAX(double)
+GLB200_HOST_RELAX(zcplx)
+
 GLB200_HOST_BASIC(minv_vector_cg, minv_vector_cg_dev, "CG")
 GLB200_HOST_RESTART(minv_vector_cg_restart, minv_vector_cg_restart_dev, "CG")
 GLB200_HOST_BASIC(minv_vector_cr, minv_vector_cr_dev, "CR")
@@ -719,7 +741,11 @@ static inversion_info dispatch(T* lhs, T* rhs, int size, minv_inverter type, min
     case MINV_GMRES:
       return p.restart ? minv_vector_gmres_restart(lhs, rhs, size, p.max_iters, p.tol, p.restart_freq, mv, extra, verb)
                        : minv_vector_gmres(lhs, rhs, size, p.max_iters, p.tol, mv, extra, verb);
-    default:  // SOR / MinRes are outside the accelerated path
+    case MINV_SOR:  // generic_inverter.cpp:86-95: no restarts for these two
+      return minv_vector_sor(lhs, rhs, size, p.max_iters, p.tol, p.sor_omega, mv, extra, verb);
+    case MINV_MINRES:
+      return minv_vector_minres(lhs, rhs, size, p.max_iters, p.tol, p.minres_omega, mv, extra, verb);
+    default:
       return inversion_info();
   }
 }

@@ -83,6 +83,27 @@ inversion_info minv_vector_cg_m(complex<double>** phi, complex<double>* phi0, in
                                 void (*matrix_vector)(complex<double>*, complex<double>*, void*), void* extra_info,
                                 bool worst_first = false, inversion_verbose_struct* verbosity = 0);
 
+// Successive over-relaxation x <- x + omega (b - A x)          generic_sor.h:14-18
+inversion_info minv_vector_sor(double* phi, double* phi0, int size, int max_iter, double eps, double omega,
+                               void (*matrix_vector)(double*, double*, void*), void* extra_info,
+                               inversion_verbose_struct* verb = 0);
+inversion_info minv_vector_sor(complex<double>* phi, complex<double>* phi0, int size, int max_iter, double eps,
+                               double omega, void (*matrix_vector)(complex<double>*, complex<double>*, void*),
+                               void* extra_info, inversion_verbose_struct* verb = 0);
+// Minimum residual (Saad 5.3.2), with and without relaxation    generic_minres.h:16-23
+inversion_info minv_vector_minres(double* phi, double* phi0, int size, int max_iter, double eps,
+                                  void (*matrix_vector)(double*, double*, void*), void* extra_info,
+                                  inversion_verbose_struct* verbosity = 0);
+inversion_info minv_vector_minres(double* phi, double* phi0, int size, int max_iter, double eps, double omega,
+                                  void (*matrix_vector)(double*, double*, void*), void* extra_info,
+                                  inversion_verbose_struct* verbosity = 0);
+inversion_info minv_vector_minres(complex<double>* phi, complex<double>* phi0, int size, int max_iter, double eps,
+                                  void (*matrix_vector)(complex<double>*, complex<double>*, void*), void* extra_info,
+                                  inversion_verbose_struct* verbosity = 0);
+inversion_info minv_vector_minres(complex<double>* phi, complex<double>* phi0, int size, int max_iter, double eps,
+                                  double omega, void (*matrix_vector)(complex<double>*, complex<double>*, void*),
+                                  void* extra_info, inversion_verbose_struct* verbosity = 0);
+
 // Gauss-Jordan elimination used by GMRES; stays on the host (generic_gelim.h)
 int gaussian_elimination(double* x, double* b, double** matrix, int size);
 int gaussian_elimination(complex<double>* x, complex<double>* b, complex<double>** matrix, int size);
@@ -95,8 +116,8 @@ enum minv_inverter {
   MINV_BICGSTAB = 3,
   MINV_BICGSTAB_L = 4,
   MINV_GMRES = 5,
-  MINV_SOR = 6,      // not on the accelerated path: returns an empty inversion_info
-  MINV_MINRES = 7,   // not on the accelerated path: returns an empty inversion_info
+  MINV_SOR = 6,
+  MINV_MINRES = 7,
   MINV_INVALID = -1,
 };
 

@@ -367,6 +367,18 @@ def ref_solve_multi(orc, which, op, b, shifts, resid_freq_check=10, max_iter=100
     return [by_addr[ptrs[i]] for i in range(n)], res.as_dict(), shifts
 
 
+def ref_solve_relax(orc, which, op, b, x0=None, max_iter=10000, eps=1e-10, omega=1.0):
+    """minv_vector_sor / minv_vector_minres of the reference (`ref` library only); which = "SOR" | "MINRES" """
+    f = orc.lib.ref_solve_relax
+    f.restype = C.c_int
+    f.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.POINTER(Result)]
+    b = np.ascontiguousarray(b, dtype=op.dtype)
+    x = np.zeros_like(b) if x0 is None else np.array(x0, dtype=op.dtype, copy=True)
+    res = Result()
+    f(dict(SOR=0, MINRES=1)[which], op.h, _ptr(x), _ptr(b), max_iter, eps, omega, 0, C.byref(res))
+    return x, res.as_dict()
+
+
 def ref_solve_precond(orc, solver, op, b, x0=None, max_iter=10000, eps=1e-10, restart_freq=0, precond="IDENTITY",
                       n_step=4, rel_res=1e-20):
     """the reference's preconditioned family with its stock preconditioners (`ref` library only)"""

@@ -271,6 +271,23 @@ int ref_solve(int solver, void* opv, double* phi, const double* phi0, int max_it
   return 0;
 }
 
+// minv_vector_sor (which = 0, generic_sor.cpp:24,122) / minv_vector_minres (which = 1, generic_minres.cpp:22,128)
+int ref_solve_relax(int which, void* opv, double* phi, const double* phi0, int max_iter, double eps, double omega,
+                    int verbosity, orc_result* out) {
+  RefOp* op = (RefOp*)opv;
+  inversion_verbose_struct verb;
+  make_verb(verbosity, &verb);
+  inversion_info info;
+  if (op->is_complex)
+    info = which == 0 ? minv_vector_sor((cplx*)phi, (cplx*)phi0, op->size, max_iter, eps, omega, cb_c, opv, &verb)
+                      : minv_vector_minres((cplx*)phi, (cplx*)phi0, op->size, max_iter, eps, omega, cb_c, opv, &verb);
+  else
+    info = which == 0 ? minv_vector_sor(phi, (double*)phi0, op->size, max_iter, eps, omega, cb_r, opv, &verb)
+                      : minv_vector_minres(phi, (double*)phi0, op->size, max_iter, eps, omega, cb_r, opv, &verb);
+  fill_result(info, out);
+  return 0;
+}
+
 int ref_solve_cg_m(void* opv, double** phi, const double* phi0, int n_shift, int resid_freq_check, int max_iter,
                    double eps, double* shifts, int worst_first, int verbosity, orc_result* out) {
   RefOp* op = (RefOp*)opv;

@@ -98,3 +98,45 @@ def test_preconditioned_family(ctx, glb, solver, kind, kw):
         assert close_iters(got["iter"], want["iter"])
     assert np.linalg.norm(op.apply(x) - bb) / np.linalg.norm(bb) < 1e-9 * 1.0001
     assert rel_err(x, xo) < 1e-6
+
+
+@pytest.mark.parametrize("which,kind,kw", [
+    ("SOR", "LAPLACE_REAL", dict(omega=0.2, eps=1e-6)),
+    ("SOR", "LAPLACE_NC", dict(omega=0.15, eps=1e-5)),
+    ("MINRES", "LAPLACE_REAL", dict(omega=1.0, eps=1e-8)),
+    ("MINRES", "STAG_U1", dict(omega=1.0, eps=1e-7)),
+    ("MINRES", "STAG_U1", dict(omega=0.67, eps=1e-7)),
+    ("MINRES", "STAG_NORMAL_U1", dict(omega=0.85, eps=1e-9, max_iter=40)),      # hits max_iter
+])
+def test_sor_minres(ctx, glb, which, kind, kw):
+    """minv_vector_sor / minv_vector_minres through the reference's own calls with host vectors: one-term recurrences
+    without the chaos of the BiCG family, so iteration counts are held to +-2 % and the iterates to 1e-9"""
+    orc = oracle_py.load("ref")
+    L = 64
+    U, b = synthetic(orc, L)
+    Nc = 2 if kind == "LAPLACE_NC" else 1
+    op = orc.op(kind, L, L, mass=0.1, links=U, Nc=Nc) if Nc > 1 else orc.op(kind, L, L, mass=0.1, links=U)
+    rg = np.random.default_rng(3)
+    n = op.size
+    bb = (rg.standard_normal(n) + 1j * rg.standard_normal(n)) if op.is_complex else rg.standard_normal(n)
+    x0 = 0.1 * ((rg.standard_normal(n) + 1j * rg.standard_normal(n)) if op.is_complex else rg.standard_normal(n))
+    args = dict(max_iter=5000, eps=1e-8, omega=1.0)
+    args.update(kw)
+    xo, want = oracle_py.ref_solve_relax(orc, which, op, bb, x0=x0, **args)
+    x = np.array(x0, copy=True)
+    d = ctx._desc(kind, L, L, mass=0.1, Nc=Nc, links=U)
+    got = ctx.host_solve_relax(which, d, x, bb, **args)
+    assert got["success"] == want["success"] and got["name"] == want["name"]
+    assert close_iters(got["iter"], want["iter"]) and close_iters(got["ops_count"], want["ops_count"])
+    # the same number of steps: the same iterate to rounding; one step more or less at the threshold: to the tolerance
+    assert rel_err(x, xo) < (1e-9 if got["iter"] == want["iter"] else 100 * args["eps"])
+    if want["success"]:
+        assert np.linalg.norm(op.apply(x) - bb) / np.linalg.norm(bb) < args["eps"] * 1.0001
+    # the device variant of the call on a native operator
+    dop = ctx.laplace(L, L, Nc=Nc, diag=4.1, dtype=op.dtype) if kind.startswith("LAPLACE") else \
+        ctx.staggered(U, L, L, 0.1, glb.STAG_NORMAL if kind == "STAG_NORMAL_U1" else 0)
+    dx, db = ctx.vector(n, op.dtype).upload(x0), ctx.vector(n, op.dtype).upload(bb)
+    got_d = ctx.solve_relax(which, dop, dx, db, **args)
+    assert (got_d["iter"], got_d["ops_count"], got_d["success"], got_d["name"]) == (
+        got["iter"], got["ops_count"], got["success"], got["name"])
+    assert rel_err(dx.download(), x) < 1e-12

@@ -32,6 +32,7 @@ def mock():
                                           C.POINTER(glb.Result)]
     lib.glbx_host_solve_precond.argtypes = [ci, C.POINTER(glb.OpDesc), vp, vp, ci, cd, ci, ci, ci, cd, ci,
                                             C.POINTER(glb.Result)]
+    lib.glbx_host_solve_relax.argtypes = [ci, C.POINTER(glb.OpDesc), vp, vp, ci, cd, cd, ci, C.POINTER(glb.Result)]
     lib.glbx_force_host_scalars.argtypes = [ci]
     lib.glbx_force_host_scalars(1)
     return glb, lib
@@ -115,5 +116,45 @@ def test_preconditioned_family_bit_identical(mock, solver, kind, kw):
     assert lib.glbx_host_solve_precond(oracle_py.PRECOND_SOLVER[solver], C.byref(d), _p(x), _p(bb), args["max_iter"],
                                        args["eps"], args["restart_freq"], oracle_py.PRECOND[args["precond"]],
                                        args["n_step"], args["rel_res"], 0, C.byref(res)) == 0
+    assert res.as_dict() == want
+    assert np.array_equal(x, xo)
+
+
+RELAX_CASES = [
+    # SOR only converges when |1 - omega lambda| < 1 for the whole spectrum: the (massive) Laplacians qualify
+    ("SOR", "LAPLACE_REAL", dict(omega=0.2, eps=1e-6)),
+    ("SOR", "LAPLACE_NC", dict(omega=0.15, eps=1e-5)),                       # complex overload: iter is not bumped
+    ("SOR", "LAPLACE_REAL", dict(omega=0.2, eps=1e-12, max_iter=25)),         # hits max_iter
+    ("SOR", "STAG_U1", dict(omega=0.3, eps=1e-8, max_iter=12)),               # diverges; the shell must follow it
+    ("MINRES", "LAPLACE_REAL", dict(omega=1.0, eps=1e-8)),
+    ("MINRES", "STAG_U1", dict(omega=1.0, eps=1e-7)),
+    ("MINRES", "STAG_U1", dict(omega=0.67, eps=1e-7)),                        # the multigrid smoother's relaxation
+    ("MINRES", "STAG_NORMAL_U1", dict(omega=0.85, eps=1e-9, max_iter=40)),    # hits max_iter
+]
+
+
+@pytest.mark.parametrize("which,kind,kw", RELAX_CASES)
+def test_sor_minres_bit_identical(mock, which, kind, kw):
+    """minv_vector_sor / minv_vector_minres (generic_sor.cpp, generic_minres.cpp): solution, counts, success flag,
+    name (it carries omega) and residual equal the reference's, including the overload differences (the real
+    versions count the last iteration, the complex ones do not) and a non-zero initial guess"""
+    glb, lib = mock
+    orc = oracle_py.load("ref")
+    L = 16
+    U, b = synthetic(orc, L)
+    Nc = 2 if kind == "LAPLACE_NC" else 1
+    op = orc.op(kind, L, L, mass=0.1, links=U, Nc=Nc) if Nc > 1 else orc.op(kind, L, L, mass=0.1, links=U)
+    rg = np.random.default_rng(3)
+    n = op.size
+    bb = (rg.standard_normal(n) + 1j * rg.standard_normal(n)) if op.is_complex else rg.standard_normal(n)
+    x0 = 0.1 * ((rg.standard_normal(n) + 1j * rg.standard_normal(n)) if op.is_complex else rg.standard_normal(n))
+    args = dict(max_iter=3000, eps=1e-8, omega=1.0)
+    args.update(kw)
+    xo, want = oracle_py.ref_solve_relax(orc, which, op, bb, x0=x0, **args)
+    x = np.array(x0, copy=True)
+    res = glb.Result()
+    d = desc(glb, kind, L, L, mass=0.1, Nc=Nc, links=U)
+    assert lib.glbx_host_solve_relax(dict(SOR=0, MINRES=1)[which], C.byref(d), _p(x), _p(bb), args["max_iter"],
+                                     args["eps"], args["omega"], 0, C.byref(res)) == 0
     assert res.as_dict() == want
     assert np.array_equal(x, xo)

@@ -56,7 +56,8 @@ def test_transfers_bit_exact(ctx, glb, L, nvec):
 @pytest.mark.parametrize("L,nvec,cfg", [(16, 2, dict()), (32, 4, dict()),
                                          (32, 4, dict(smooth="BICGSTAB", n_pre=3, n_post=2, inner="CG")),
                                          (32, 2, dict(n_pre=0, n_post=4, inner="BICGSTAB")),
-                                         (32, 2, dict(n_pre=2, n_post=0, inner="CR", n_restart=16))])
+                                         (32, 2, dict(n_pre=2, n_post=0, inner="CR", n_restart=16)),
+                                         (32, 4, dict(smooth="MINRES", n_pre=4, n_post=4))])
 def test_vcycle_matches_reference(ctx, glb, L, nvec, cfg):
     """one cycle with the coarse system solved to 1e-11: a coarse solve stopped at the reference's default 1e-2
     may take one iteration more or less on the device (reduction order), which changes the cycle's output at the
