@@ -18,6 +18,8 @@ LIB_CUDA = os.path.join(HERE, "libglb200.so")
 LIB_HOST = os.path.join(HERE, "libglb200_inverters.so")
 
 REAL, COMPLEX = 0, 1
+# composite operators on a stencil2d operator (include/glb200.h GLB_SV_*)
+STENCIL_VIEW = dict(NONE=0, M2MDEODOE=1, M2MDTBDBT=2, NORMAL_EO=3, NORMAL_TB=4, DAGGER_EO=5, DAGGER_TB=6)
 STAG_DAGGER, STAG_GAMMA5, STAG_NORMAL = 1, 2, 4
 STAG_DEO, STAG_DOE, STAG_M2MDEODOE = 8, 16, 32   # even/odd pieces (operators.cpp:456-571)
 
@@ -38,7 +40,8 @@ class OpDesc(C.Structure):
     _fields_ = [("kind", C.c_int), ("X", C.c_int), ("Y", C.c_int), ("Nc", C.c_int),
                 ("mass", C.c_double), ("links", C.c_void_p), ("clover", C.c_void_p),
                 ("hopping", C.c_void_p), ("two_link", C.c_void_p), ("has_two", C.c_int),
-                ("shift", C.c_double * 2), ("eo_shift", C.c_double * 2), ("dof_shift", C.c_double * 2)]
+                ("shift", C.c_double * 2), ("eo_shift", C.c_double * 2), ("dof_shift", C.c_double * 2),
+                ("view", C.c_int)]
 
 
 class Result(C.Structure):
@@ -122,6 +125,8 @@ def libs():
         "glb_mg_transfer_destroy": (ci, [vp]), "glb_mg_fine_size": (sz, [vp]), "glb_mg_coarse_size": (sz, [vp]),
         "glb_mg_prolong": (ci, [vp, vp, vp]), "glb_mg_restrict": (ci, [vp, vp, vp]),
         "glb_rscale": (ci, [vp, ci, sz, vp, cd, vp]),
+        "glb_op_create_stencil_view": (ci, [vp, ci, ci, C.POINTER(vp)]),
+        "glb_stencil_prec_prepare": (ci, [vp, ci, vp, vp]), "glb_stencil_prec_reconstruct": (ci, [vp, ci, vp, vp, vp]),
         "glb_op_set_shifts": (ci, [vp, pd, pd, pd]), "glb_op_get_shifts": (ci, [vp, pd, pd, pd]),
         "glb_op_stencil_download": (ci, [vp, vp, vp]),
         "glb_mg_transfer_create_dev": (ci, [vp, ci, ci, ci, ci, ci, ci, C.POINTER(vp), C.POINTER(vp)]),
@@ -148,6 +153,7 @@ def libs():
         "glbx_host_solve_multi": (ci, [ci, C.POINTER(OpDesc), C.POINTER(vp), vp, ci, ci, ci, cd, vp, ci, ci,
                                        C.POINTER(Result)]),
         "glbx_host_solve_precond": (ci, [ci, C.POINTER(OpDesc), vp, vp, ci, cd, ci, ci, ci, cd, ci, C.POINTER(Result)]),
+        "glbx_host_stencil_prec": (ci, [C.POINTER(OpDesc), ci, ci, vp, vp, vp]),
         "glbx_host_solve_relax": (ci, [ci, C.POINTER(OpDesc), vp, vp, ci, cd, cd, ci, C.POINTER(Result)]),
         "glbx_dev_solve_relax": (ci, [ci, vp, vp, vp, ci, cd, cd, ci, C.POINTER(Result)]),
         "glbx_mg_create": (vp, [ci, C.POINTER(vp), C.POINTER(vp)]), "glbx_mg_destroy": (None, [vp]),
@@ -156,7 +162,7 @@ def libs():
         "glbx_mg_vpgcr": (ci, [vp, vp, vp, ci, cd, ci, ci, C.POINTER(Result)]),
         "glbx_mg_counts": (None, [vp, C.POINTER(ci)]),
         "glbx_mg_setup": (vp, [vp, ci, ci, ci, C.POINTER(ci), C.POINTER(ci), ci, cd, ci, pd, C.POINTER(ci), ci, ci, ci,
-                               ci, C.c_uint, ci]),
+                               ci, C.c_uint, ci, ci]),
         "glbx_mg_level_op": (vp, [vp, ci]), "glbx_mg_level_transfer": (vp, [vp, ci]),
         "glbx_mg_null_vector": (vp, [vp, ci, ci]), "glbx_mg_setup_seconds": (None, [vp, pd]),
     }
@@ -284,6 +290,23 @@ class Operator:
     def set_mass(self, m):
         _chk(self.ctx.cu.glb_op_set_mass(self.h, m))
 
+    def view(self, kind):
+        """glb_op_create_stencil_view: a composite operator (STENCIL_VIEW name) sharing this stencil2d operator's
+        matrices and shifts; it must not outlive this operator"""
+        h = C.c_void_p()
+        _chk(self.ctx.cu.glb_op_create_stencil_view(self.h, STENCIL_VIEW[kind], 0, C.byref(h)), "glb_op_create_stencil_view")
+        return Operator(self.ctx, h, keep=(self,))
+
+    def prec_prepare(self, top_bottom, rhs_part, rhs_orig):
+        """glb_stencil_prec_prepare: apply_square_staggered_{eo,tb}prec_prepare_stencil"""
+        _chk(self.ctx.cu.glb_stencil_prec_prepare(self.h, int(top_bottom), rhs_part.ptr, rhs_orig.ptr),
+             "glb_stencil_prec_prepare")
+
+    def prec_reconstruct(self, top_bottom, lhs_full, lhs_part, rhs_other):
+        """glb_stencil_prec_reconstruct: apply_square_staggered_{eo,tb}prec_reconstruct_stencil"""
+        _chk(self.ctx.cu.glb_stencil_prec_reconstruct(self.h, int(top_bottom), lhs_full.ptr, lhs_part.ptr, rhs_other.ptr),
+             "glb_stencil_prec_reconstruct")
+
     def set_shifts(self, shift=None, eo_shift=None, dof_shift=None):
         """stencil2d operators: stencil_2d::shift / eo_shift / dof_shift (coarse_stencil.h:62-71); None keeps one"""
         a = [_c2(v) if v is not None else None for v in (shift, eo_shift, dof_shift)]
@@ -388,11 +411,12 @@ class Multigrid:
     @classmethod
     def setup(cls, ctx, fine_op, X, Y, blocks, nvecs, bstrat=1, null_mass=1e-2, null_gen="BICGSTAB", tol=5e-5,
               max_iter=500, restart_freq=0, bicgstab_l=-1, do_ortho_eo=False, do_global_ortho_conj=False, seed=1337,
-              verbosity=0):
+              verbosity=0, null_prec=0):
         """glbx_mg_setup: the reference driver's set-up sequence on the device (null_generate_random_smooth_dev,
         block_orthonormalize_dev, generate_coarse_from_fine_stencil_dev; aa_mg_square_staggered_u1.cpp:716-1143).
         fine_op: the level-0 stencil2d operator with the mass in its shift.  nvecs[l]: vectors of refinement l after
-        the partition; bstrat 0 = BLOCK_NONE, 1 = BLOCK_EO."""
+        the partition; bstrat 0 = BLOCK_NONE, 1 = BLOCK_EO; null_prec 0 = plain solves, 1 = even/odd (top/bottom below the
+        top level), 2 = normal equations (null_gen.h:24-29)."""
         n = len(blocks)
         self = cls.__new__(cls)
         self.ctx, self.n_refine = ctx, n
@@ -402,7 +426,7 @@ class Multigrid:
         mi = (C.c_int * n)(*([max_iter] * n if np.isscalar(max_iter) else max_iter))
         self.h = ctx.ho.glbx_mg_setup(fine_op.h, X, Y, n, bl, nv, bstrat, null_mass, cls.SMOOTH[null_gen], tl, mi,
                                       restart_freq, bicgstab_l, int(do_ortho_eo), int(do_global_ortho_conj), seed,
-                                      verbosity)
+                                      verbosity, null_prec)
         if not self.h:
             raise GlbError("glbx_mg_setup failed (see stderr)")
         self.ops, self.transfers = [fine_op], []
@@ -647,6 +671,13 @@ class Context:
                                           C.byref(res)), "glbx_dev_solve_relax")
         return res.as_dict()
 
+    def host_stencil_prec(self, desc, top_bottom, a, b=None):
+        """the reference-named prepare (b is None) / reconstruct wrappers with host vectors"""
+        out = np.empty_like(a)
+        _chk(self.ho.glbx_host_stencil_prec(C.byref(desc), int(top_bottom), 0 if b is None else 1, _p(out), _p(a),
+                                            _p(b) if b is not None else None), "glbx_host_stencil_prec")
+        return out
+
     def host_solve_relax(self, which, desc, x, b, max_iter=10000, eps=1e-10, omega=1.0, verbosity=0):
         """minv_vector_sor / minv_vector_minres with host vectors (x in/out)"""
         res = Result()
@@ -679,8 +710,9 @@ class Context:
 
     # ---- the reference's own calls: HOST vectors + reference-named callbacks ----
     def _desc(self, kind, X, Y, mass=0.0, Nc=1, links=None, clover=None, hopping=None, two_link=None, shift=0j,
-              eo_shift=0j, dof_shift=0j):
+              eo_shift=0j, dof_shift=0j, view=0):
         d = OpDesc()
+        d.view = STENCIL_VIEW[view] if isinstance(view, str) else view
         d.kind = OP[kind] if isinstance(kind, str) else kind
         d.X, d.Y, d.Nc, d.mass = X, Y, Nc, mass
         d.links, d.clover, d.hopping, d.two_link = _p(links), _p(clover), _p(hopping), _p(two_link)

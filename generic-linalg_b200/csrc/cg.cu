@@ -127,6 +127,7 @@ using namespace glb;
 
 extern "C" int glb_cg_solve_supported(const glb_operator* op) {
   if (!op) return 0;
+  if (op->composite) return 0;  // multi-pass stencil views: no fused epilogue, the host-scalar shell runs them
   return (op->ctx->nranks == 1 || normal_fused_ok(op)) ? 1 : 0;
 }
 

@@ -438,7 +438,16 @@ static bool ring_enabled() {
 //             colour index: rows < nc/2 summed over c >= nc/2, or the mirror; other rows zeroed (:725, :1120)
 // No shifts.  One thread per output dof, reference accumulation order (bit-identical); these serve the e/o and
 // t/b preconditioned solves, not the headline path.
-__global__ void __launch_bounds__(256) coarse_part_kernel(const CoarseArgs a, const int part) {
+//
+// post selects what is stored (the even/odd and top/bottom preconditioned stencil paths, operators_stencil.cpp:179-236,
+// mg_complex.cpp:1211-1330, fused into the pass that produces the hopping term s):
+//   0: s | 0                              apply_stencil_2d_{eo,oe,tb,bt}
+//   1: coef*aux - s | 0                   *prec_prepare (coef = shift), second pass of m^2 - D_ab D_ba (coef = shift^2)
+//   2: coef.re*(aux - s) | in             *prec_reconstruct (coef.re = 1/Re shift; the other half is copied from in)
+//   3: coef*aux - s on EVERY dof          first half of m^2 - D_ab D_ba - D_ba D_ab (s = 0 off the live half)
+//   4: out - s on EVERY dof               second half of the same (out is read and rewritten)
+__global__ void __launch_bounds__(256) coarse_part_kernel(const CoarseArgs a, const int part, const int post, const cplx coef,
+                                                          const cplx* __restrict__ aux) {
   const int nc = a.nc;
   const int X = a.X;
   const size_t L = (size_t)X * a.Yloc * nc;
@@ -483,13 +492,49 @@ __global__ void __launch_bounds__(256) coarse_part_kernel(const CoarseArgs a, co
         term(T + 7 * plane, site_ptr(a, xp, y - 1));
       }
     }
-    a.out[i] = s;
+    cplx r;
+    switch (post) {
+      case 1: r = live ? fsub(fmul(coef, aux[i]), s) : mk(0.0, 0.0); break;
+      case 2: r = live ? fscale(coef.x, fsub(aux[i], s)) : a.in[i]; break;
+      case 3: r = fsub(fmul(coef, aux[i]), s); break;
+      case 4: r = fsub(a.out[i], s); break;
+      default: r = s; break;
+    }
+    a.out[i] = r;
   }
 }
 
-int launch_stencil2d_part(glb_operator* op, void* out, const void* in, int part) {
+// lattice_epsilon / lattice_sigma3 (lattice/lattice_functions.h:11-53): out = +-in by site parity (mode 0) or by
+// colour half (mode 1; a copy when nc is odd)
+__global__ void __launch_bounds__(256) coarse_sign_kernel(cplx* __restrict__ out, const cplx* __restrict__ in, size_t n, int X,
+                                                          int nc, int y0, int mode) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    bool flip;
+    if (mode == 0) {
+      const size_t site = i / nc;
+      flip = (((site % X) + (site / X) + y0) & 1) != 0;
+    } else {
+      flip = (nc % 2 == 0) && ((int)(i % nc) >= nc / 2);
+    }
+    const cplx v = in[i];
+    out[i] = flip ? fneg(v) : v;
+  }
+}
+
+int launch_stencil2d_sign(glb_operator* op, void* out, const void* in, int mode) {
+  glb_context* ctx = op->ctx;
+  const size_t n = (size_t)op->X * op->Yloc * op->nc;
+  const int grid = blas_grid(ctx, n, 256, 1);
+  coarse_sign_kernel<<<grid, 256, 0, ctx->stream>>>((cplx*)out, (const cplx*)in, n, op->X, op->nc, op->y0, mode);
+  GLB_LAUNCH_CHECK();
+  return GLB_OK;
+}
+
+int launch_stencil2d_part(glb_operator* op, void* out, const void* in, int part, int post, const double coef[2],
+                          const void* aux) {
   glb_context* ctx = op->ctx;
   if (part < GLB_PART_EO || part > GLB_PART_BT) return fail(GLB_ERR_ARG, "stencil2d: unknown partial apply");
+  if (post < 0 || post > 4 || ((post >= 1 && post <= 3) && !aux)) return fail(GLB_ERR_ARG, "stencil2d: bad post-operation");
   CoarseArgs a{};
   const size_t rowlen = (size_t)op->X * op->nc;
   const bool single = (ctx->nranks == 1);
@@ -510,7 +555,8 @@ int launch_stencil2d_part(glb_operator* op, void* out, const void* in, int part)
   const size_t L = rowlen * op->Yloc;
   const int grid = blas_grid(ctx, L, 256, 1);
   ProfScope prof(ctx, PROF_COARSE);
-  coarse_part_kernel<<<grid, 256, 0, ctx->stream>>>(a, part);
+  coarse_part_kernel<<<grid, 256, 0, ctx->stream>>>(a, part, post, coef ? make_double2(coef[0], coef[1]) : make_double2(0.0, 0.0),
+                                                    (const cplx*)aux);
   GLB_LAUNCH_CHECK();
   return GLB_OK;
 }

@@ -252,9 +252,14 @@ int glb_op_destroy(glb_operator* op) {
   }
   cudaFree(op->send_lo);
   cudaFree(op->send_hi);
-  cudaFree(op->clover);
-  cudaFree(op->hopping);
-  cudaFree(op->two_link);
+  cudaFree(op->tmp2);
+  if (op->base) {  // a view: the matrices are the base's
+    if (op->owns_base) glb_op_destroy(op->base);
+  } else {
+    cudaFree(op->clover);
+    cudaFree(op->hopping);
+    cudaFree(op->two_link);
+  }
   delete op;
   return GLB_OK;
 }
@@ -266,6 +271,7 @@ int glb_op_set_mass(glb_operator* op, double mass) {
 }
 int glb_op_set_shifts(glb_operator* op, const double shift[2], const double eo_shift[2], const double dof_shift[2]) {
   if (!op || op->kind != OPK_STENCIL) return fail(GLB_ERR_ARG, "glb_op_set_shifts: not a stencil2d operator");
+  if (op->base) return glb_op_set_shifts(op->base, shift, eo_shift, dof_shift);
   for (int i = 0; i < 2; i++) {
     if (shift) op->shift[i] = shift[i];
     if (eo_shift) op->eo_shift[i] = eo_shift[i];
@@ -275,6 +281,7 @@ int glb_op_set_shifts(glb_operator* op, const double shift[2], const double eo_s
 }
 int glb_op_get_shifts(const glb_operator* op, double shift[2], double eo_shift[2], double dof_shift[2]) {
   if (!op || op->kind != OPK_STENCIL) return fail(GLB_ERR_ARG, "glb_op_get_shifts: not a stencil2d operator");
+  if (op->base) return glb_op_get_shifts(op->base, shift, eo_shift, dof_shift);
   for (int i = 0; i < 2; i++) {
     if (shift) shift[i] = op->shift[i];
     if (eo_shift) eo_shift[i] = op->eo_shift[i];
@@ -323,6 +330,64 @@ double glb_op_bytes_per_apply(const glb_operator* op) {
 namespace glb {
 
 // one operator application with optional fused reductions; halo rows exchanged first on slabs
+// A view shares the base's matrices and shifts; they are read at apply time so that glb_op_set_shifts on the base is seen.
+static void sync_view(glb_operator* v) {
+  const glb_operator* b = v->base;
+  v->clover = b->clover;
+  v->hopping = b->hopping;
+  v->two_link = b->two_link;
+  v->has_two = b->has_two;
+  for (int i = 0; i < 2; i++) {
+    v->shift[i] = b->shift[i];
+    v->eo_shift[i] = b->eo_shift[i];
+    v->dof_shift[i] = b->dof_shift[i];
+  }
+}
+
+static int part_apply(glb_operator* op, void* out, const void* in, int part, int post = 0, const double coef[2] = nullptr,
+                      const void* aux = nullptr) {
+  int rc = halo_exchange(op, in, op->has_two ? 2 : 1);
+  if (rc) return rc;
+  return launch_stencil2d_part(op, out, in, part, post, coef, aux);
+}
+
+// the composite stencil operators of operators_stencil.cpp:196-214 and mg_complex.cpp:1228-1372
+static int apply_composite(glb_operator* op, void* out, const void* in) {
+  sync_view(op);
+  // shift*shift as std::complex multiplies it (operators_stencil.cpp:209: stenc->shift*stenc->shift*rhs[i])
+  const double s2[2] = {op->shift[0] * op->shift[0] - op->shift[1] * op->shift[1],
+                        op->shift[0] * op->shift[1] + op->shift[1] * op->shift[0]};
+  int rc;
+  switch (op->composite) {
+    case GLB_SV_M2MDEODOE:  // tmp = D_oe in ; out = m^2 in - D_eo tmp on even sites, 0 on odd
+      if ((rc = part_apply(op, op->tmp, in, GLB_PART_OE))) return rc;
+      return part_apply(op, out, op->tmp, GLB_PART_EO, 1, s2, in);
+    case GLB_SV_M2MDTBDBT:
+      if ((rc = part_apply(op, op->tmp, in, GLB_PART_BT))) return rc;
+      return part_apply(op, out, op->tmp, GLB_PART_TB, 1, s2, in);
+    case GLB_SV_NORMAL_EO:  // out = m^2 in - D_oe D_eo in - D_eo D_oe in
+      if ((rc = part_apply(op, op->tmp, in, GLB_PART_EO))) return rc;
+      if ((rc = part_apply(op, out, op->tmp, GLB_PART_OE, 3, s2, in))) return rc;
+      if ((rc = part_apply(op, op->tmp, in, GLB_PART_OE))) return rc;
+      return part_apply(op, out, op->tmp, GLB_PART_EO, 4);
+    case GLB_SV_NORMAL_TB:
+      if ((rc = part_apply(op, op->tmp, in, GLB_PART_TB))) return rc;
+      if ((rc = part_apply(op, out, op->tmp, GLB_PART_BT, 3, s2, in))) return rc;
+      if ((rc = part_apply(op, op->tmp, in, GLB_PART_BT))) return rc;
+      return part_apply(op, out, op->tmp, GLB_PART_TB, 4);
+    case GLB_SV_DAGGER_EO:  // epsilon D epsilon
+    case GLB_SV_DAGGER_TB: {  // sigma_3 D sigma_3
+      const int mode = (op->composite == GLB_SV_DAGGER_EO) ? 0 : 1;
+      ApplyFusion none;
+      if ((rc = launch_stencil2d_sign(op, op->tmp, in, mode))) return rc;
+      if ((rc = halo_exchange(op, op->tmp, op->has_two ? 2 : 1))) return rc;
+      if ((rc = launch_stencil2d(op, op->tmp2, op->tmp, none))) return rc;
+      return launch_stencil2d_sign(op, out, op->tmp2, mode);
+    }
+  }
+  return fail(GLB_ERR_ARG, "unknown composite stencil operator");
+}
+
 static int apply_impl(glb_operator* op, void* out, const void* in, const ApplyFusion& f) {
   glb_context* ctx = op->ctx;
   if (out == in) return fail(GLB_ERR_ARG, "apply: output must not alias input");
@@ -335,6 +400,11 @@ static int apply_impl(glb_operator* op, void* out, const void* in, const ApplyFu
       if (f.w || f.w_is_input) return fail(GLB_ERR_ARG, "gamma5 has no fused reductions");
       return launch_gamma5(op, out, in);
     case OPK_STENCIL:
+      if (op->composite) {
+        if (f.w || f.w_is_input || f.want_norm || f.p_new || f.cg_role)
+          return fail(GLB_ERR_ARG, "composite stencil operators have no fused reductions");
+        return apply_composite(op, out, in);
+      }
       if ((rc = halo_exchange(op, in, op->has_two ? 2 : 1))) return rc;
       return launch_stencil2d(op, out, in, f);
     case OPK_LAPLACE_U1:
@@ -391,9 +461,57 @@ int glb_op_apply(glb_operator* op, void* d_out, const void* d_in) {
 int glb_op_apply_part(glb_operator* op, void* d_out, const void* d_in, int part) {
   if (!op || op->kind != OPK_STENCIL) return fail(GLB_ERR_ARG, "glb_op_apply_part needs a stencil2d operator");
   if (d_out == d_in) return fail(GLB_ERR_ARG, "apply: output must not alias input");
-  int rc = halo_exchange(op, d_in, op->has_two ? 2 : 1);
+  if (op->base) sync_view(op);
+  return part_apply(op, d_out, d_in, part);
+}
+
+int glb_op_create_stencil_view(glb_operator* base, int kind, int adopt_base, glb_operator** out) {
+  if (!base || !out || base->kind != OPK_STENCIL || base->base)
+    return fail(GLB_ERR_ARG, "glb_op_create_stencil_view: the base must be a plain stencil2d operator");
+  if (kind < GLB_SV_M2MDEODOE || kind > GLB_SV_DAGGER_TB) return fail(GLB_ERR_ARG, "glb_op_create_stencil_view: unknown kind");
+  if ((kind == GLB_SV_M2MDTBDBT || kind == GLB_SV_NORMAL_TB) && base->nc % 2 != 0)
+    return fail(GLB_ERR_ARG, "glb_op_create_stencil_view: top/bottom operators need an even number of colours");
+  glb_context* ctx = base->ctx;
+  GLB_CUDA(cudaSetDevice(ctx->device));
+  int rc = new_op(ctx, OPK_STENCIL, GLB_COMPLEX, base->X, base->Y, base->nc, out);
   if (rc) return rc;
-  return launch_stencil2d_part(op, d_out, d_in, part);
+  glb_operator* v = *out;
+  v->composite = kind;
+  v->base = base;
+  v->owns_base = false;  // set last: a failed creation must not take the base with it
+  sync_view(v);
+  const size_t bytes = sizeof(cplx) * (size_t)v->X * v->Yloc * v->nc;
+  if (cudaMalloc(&v->tmp, bytes) != cudaSuccess ||
+      ((kind == GLB_SV_DAGGER_EO || kind == GLB_SV_DAGGER_TB) && cudaMalloc(&v->tmp2, bytes) != cudaSuccess)) {
+    glb_op_destroy(v);
+    *out = nullptr;
+    return fail(GLB_ERR_CUDA, "glb_op_create_stencil_view: out of device memory");
+  }
+  rc = alloc_ghosts(v, v->has_two ? 2 : 1);
+  if (rc) {
+    glb_op_destroy(v);
+    *out = nullptr;
+    return rc;
+  }
+  v->owns_base = adopt_base != 0;
+  return GLB_OK;
+}
+
+int glb_stencil_prec_prepare(glb_operator* op, int top_bottom, void* d_rhs_part, const void* d_rhs_orig) {
+  if (!op || op->kind != OPK_STENCIL || op->composite) return fail(GLB_ERR_ARG, "glb_stencil_prec_prepare needs a plain stencil2d operator");
+  if (d_rhs_part == d_rhs_orig) return fail(GLB_ERR_ARG, "glb_stencil_prec_prepare: output must not alias input");
+  if (top_bottom && op->nc % 2 != 0) return fail(GLB_ERR_ARG, "glb_stencil_prec_prepare: top/bottom needs an even number of colours");
+  return part_apply(op, d_rhs_part, d_rhs_orig, top_bottom ? GLB_PART_TB : GLB_PART_EO, 1, op->shift, d_rhs_orig);
+}
+
+int glb_stencil_prec_reconstruct(glb_operator* op, int top_bottom, void* d_lhs_full, const void* d_lhs_part,
+                                 const void* d_rhs_other) {
+  if (!op || op->kind != OPK_STENCIL || op->composite) return fail(GLB_ERR_ARG, "glb_stencil_prec_reconstruct needs a plain stencil2d operator");
+  if (d_lhs_full == d_lhs_part || d_lhs_full == d_rhs_other)
+    return fail(GLB_ERR_ARG, "glb_stencil_prec_reconstruct: output must not alias an input");
+  if (top_bottom && op->nc % 2 != 0) return fail(GLB_ERR_ARG, "glb_stencil_prec_reconstruct: top/bottom needs an even number of colours");
+  const double inv[2] = {1.0 / op->shift[0], 0.0};  // operators_stencil.cpp:222: inv_mass = 1.0/real(stenc->shift)
+  return part_apply(op, d_lhs_full, d_lhs_part, top_bottom ? GLB_PART_BT : GLB_PART_OE, 2, inv, d_rhs_other);
 }
 
 int glb_stag_eoprec_prepare(glb_operator* op, void* d_rhs_e, const void* d_rhs_orig) {
@@ -417,6 +535,15 @@ int glb_stag_eoprec_reconstruct(glb_operator* op, void* d_lhs_full, const void* 
 int glb_op_apply_dot(glb_operator* op, void* d_out, const void* d_in, const void* d_w, int want_norm, double dots[3]) {
   glb_context* ctx = op->ctx;
   if (op->kind == OPK_GAMMA5) return fail(GLB_ERR_ARG, "gamma5 has no fused reductions");
+  if (op->composite) {  // several passes: the reductions follow as their own passes
+    int rc0 = apply_composite(op, d_out, d_in);
+    if (rc0) return rc0;
+    const size_t n = glb_op_local_size(op);
+    rc0 = glb_dot(ctx, op->dtype, n, d_w ? d_w : d_in, d_out, dots);
+    if (rc0) return rc0;
+    dots[2] = 0.0;
+    return want_norm ? glb_norm2sq(ctx, op->dtype, n, d_out, &dots[2]) : GLB_OK;
+  }
   ApplyFusion f;
   f.w = d_w ? d_w : d_in;
   f.w_is_input = (d_w == nullptr || d_w == d_in);

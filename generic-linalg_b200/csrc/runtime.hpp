@@ -122,6 +122,11 @@ struct glb_operator {
   glb::cplx* two_link = nullptr;  // 8 planes
   bool has_two = false;
   double shift[2] = {0, 0}, eo_shift[2] = {0, 0}, dof_shift[2] = {0, 0};
+  // composite views of a stencil2d operator (GLB_SV_*): matrices and shifts are the base's, read at apply time
+  int composite = 0;
+  glb_operator* base = nullptr;
+  bool owns_base = false;
+  void* tmp2 = nullptr;
   // launch geometry chosen at creation
   int stencil_blocks = 0;
 };
@@ -179,7 +184,10 @@ int launch_gamma5(glb_operator* op, void* out, const void* in);
 bool normal_fused_ok(const glb_operator* op);
 int launch_normal(glb_operator* op, void* out, const void* in, const ApplyFusion& f);
 int launch_stencil2d(glb_operator* op, void* out, const void* in, const ApplyFusion& f);
-int launch_stencil2d_part(glb_operator* op, void* out, const void* in, int part);  // GLB_PART_*
+// GLB_PART_* with a fused post-operation (see coarse_part_kernel)
+int launch_stencil2d_part(glb_operator* op, void* out, const void* in, int part, int post = 0, const double coef[2] = nullptr,
+                          const void* aux = nullptr);
+int launch_stencil2d_sign(glb_operator* op, void* out, const void* in, int mode);  // 0: epsilon(x), 1: sigma_3
 
 // ops.cu : stencil2d operator around device-resident matrices (ownership passes to the operator)
 int op_adopt_stencil2d(glb_context* ctx, int X, int Y, int nc, cplx* d_clover, cplx* d_hopping, glb_operator** out);

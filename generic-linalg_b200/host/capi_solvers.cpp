@@ -53,6 +53,7 @@ typedef struct glbx_opdesc {
   const void* two_link;
   int has_two;
   double shift[2], eo_shift[2], dof_shift[2];
+  int view;  // stencil kinds: 0 apply_stencil_2d, GLB_SV_* the composite callback on the stencil
 } glbx_opdesc;
 
 }  // extern "C"
@@ -140,7 +141,16 @@ bool build_host_op(const glbx_opdesc* d, HostOp* h) {
         if (d->has_two) std::memcpy((void*)h->st->two_link, d->two_link, 8 * m * sizeof(zc));
         h->st->generated = true;
       }
-      h->cz = &apply_stencil_2d;
+      switch (d->view) {
+        case 0: h->cz = &apply_stencil_2d; break;
+        case GLB_SV_M2MDEODOE: h->cz = &apply_square_staggered_m2mdeodoe_stencil; break;
+        case GLB_SV_M2MDTBDBT: h->cz = &apply_square_staggered_m2mdtbdbt_stencil; break;
+        case GLB_SV_NORMAL_EO: h->cz = &apply_square_staggered_normal_eo_stencil; break;
+        case GLB_SV_NORMAL_TB: h->cz = &apply_square_staggered_normal_tb_stencil; break;
+        case GLB_SV_DAGGER_EO: h->cz = &apply_square_staggered_dagger_eo_stencil; break;
+        case GLB_SV_DAGGER_TB: h->cz = &apply_square_staggered_dagger_tb_stencil; break;
+        default: return false;
+      }
       h->extra = h->st;
       h->size = d->X * d->Y * nc;
       break;
@@ -279,6 +289,24 @@ int glbx_host_solve_cg_m(const glbx_opdesc* d, void** phi, const void* phi0, int
     inversion_info inf = minv_vector_cg_m((double**)phi, (double*)phi0, n_shift, h.size, resid_freq_check, max_iter,
                                           eps, shifts, h.cd, h.extra, worst_first != 0, &v);
     flatten(inf, out);
+  }
+  return GLB_OK;
+}
+
+// apply_square_staggered_{eo,tb}prec_{prepare,reconstruct}_stencil with host vectors (operators_stencil.h:31-38)
+int glbx_host_stencil_prec(const glbx_opdesc* d, int top_bottom, int reconstruct, void* out, void* a, void* b) {
+  HostOp h;
+  if (!build_host_op(d, &h) || !h.st) return GLB_ERR_ARG;
+  if (!reconstruct) {
+    if (top_bottom)
+      apply_square_staggered_tbprec_prepare_stencil((zc*)out, (zc*)a, h.st);
+    else
+      apply_square_staggered_eoprec_prepare_stencil((zc*)out, (zc*)a, h.st);
+  } else {
+    if (top_bottom)
+      apply_square_staggered_tbprec_reconstruct_stencil((zc*)out, (zc*)a, (zc*)b, h.st);
+    else
+      apply_square_staggered_eoprec_reconstruct_stencil((zc*)out, (zc*)a, (zc*)b, h.st);
   }
   return GLB_OK;
 }
@@ -507,9 +535,11 @@ void glbx_mg_destroy(glbx_mg* h) {
 // :1066-1093 gives the same matrices).
 //   nvec[l]   total null vectors of refinement l (after the partition);  bstrat: 0 none, 1 even/odd
 //   null_gen  minv_inverter;  tol[l], max_iter[l] per refinement;  seed of the std::mt19937 behind the sources
+//   null_prec null_precond_strategy: 0 plain solve, 1 even/odd (top/bottom below the top level), 2 normal equations
 glbx_mg* glbx_mg_setup(glb_operator* fine, int X, int Y, int n_refine, const int* block, const int* nvec, int bstrat,
                        double null_mass, int null_gen, const double* tol, const int* max_iter, int restart_freq,
-                       int bicgstab_l, int do_ortho_eo, int do_global_ortho_conj, unsigned seed, int verbosity) {
+                       int bicgstab_l, int do_ortho_eo, int do_global_ortho_conj, unsigned seed, int verbosity,
+                       int null_prec) {
   if (!fine || n_refine < 1 || !block || !nvec || !tol || !max_iter) return 0;
   glbx_mg* h = new glbx_mg();
   double mass_shift[2] = {0.0, 0.0};
@@ -549,6 +579,7 @@ glbx_mg* glbx_mg_setup(glb_operator* fine, int X, int Y, int n_refine, const int
 
     null_vector_params nv;
     nv.null_gen = (minv_inverter)null_gen;
+    nv.null_prec = (null_precond_strategy)null_prec;
     nv.null_restart = restart_freq > 0;
     nv.null_restart_freq = restart_freq;
     nv.null_bicgstab_l = bicgstab_l;

@@ -28,7 +28,9 @@ bool g_cache_ops = false;
 enum Builtin {
   B_NONE = 0, B_LAPLACE_NC, B_LAPLACE_NC_REAL, B_LAPLACE_U1, B_STAG_FREE, B_STAG_U1, B_GAMMA5, B_STAG_G5_FREE,
   B_STAG_G5_U1, B_STAG_DAGGER_U1, B_STAG_NORMAL_U1, B_STAG_DEO_U1, B_STAG_DOE_U1, B_STAG_M2MDEODOE_U1, B_LAPLACIAN_REAL,
-  B_LAPLACIAN_IMAG, B_STENCIL, B_STAG_FREE_REAL
+  B_LAPLACIAN_IMAG, B_STENCIL, B_STAG_FREE_REAL,
+  // composite views of a stencil_2d (include/glb200.h GLB_SV_*), in that order
+  B_SV_M2MDEODOE, B_SV_M2MDTBDBT, B_SV_NORMAL_EO, B_SV_NORMAL_TB, B_SV_DAGGER_EO, B_SV_DAGGER_TB
 };
 
 Builtin classify(void (*fn)(zcplx*, zcplx*, void*)) {
@@ -47,6 +49,12 @@ Builtin classify(void (*fn)(zcplx*, zcplx*, void*)) {
   if (fn == (F)&square_staggered_m2mdeodoe_u1) return B_STAG_M2MDEODOE_U1;
   if (fn == (F)&square_laplacian) return B_LAPLACIAN_IMAG;
   if (fn == (F)&apply_stencil_2d) return B_STENCIL;
+  if (fn == (F)&apply_square_staggered_m2mdeodoe_stencil) return B_SV_M2MDEODOE;
+  if (fn == (F)&apply_square_staggered_m2mdtbdbt_stencil) return B_SV_M2MDTBDBT;
+  if (fn == (F)&apply_square_staggered_normal_eo_stencil) return B_SV_NORMAL_EO;
+  if (fn == (F)&apply_square_staggered_normal_tb_stencil) return B_SV_NORMAL_TB;
+  if (fn == (F)&apply_square_staggered_dagger_eo_stencil) return B_SV_DAGGER_EO;
+  if (fn == (F)&apply_square_staggered_dagger_tb_stencil) return B_SV_DAGGER_TB;
   return B_NONE;
 }
 Builtin classify(void (*fn)(double*, double*, void*)) {
@@ -114,6 +122,20 @@ glb_operator* build(Builtin kind, void* extra) {
       GLBX(glb_op_create_stencil2d(ctx, st->clover, st->hopping, st->has_two ? st->two_link : 0,
                                    st->lat->get_lattice_dimension(0), st->lat->get_lattice_dimension(1),
                                    st->lat->get_nc(), sh, eo, df, &op));
+      break;
+    }
+    case B_SV_M2MDEODOE:
+    case B_SV_M2MDTBDBT:
+    case B_SV_NORMAL_EO:
+    case B_SV_NORMAL_TB:
+    case B_SV_DAGGER_EO:
+    case B_SV_DAGGER_TB: {  // the stencil itself, then the view on it (which adopts it)
+      glb_operator* base = build(B_STENCIL, extra);
+      const int sv = GLB_SV_M2MDEODOE + ((int)kind - (int)B_SV_M2MDEODOE);
+      if (glb_op_create_stencil_view(base, sv, 1, &op) != GLB_OK) {
+        glb_op_destroy(base);
+        throw Error(std::string("stencil view: ") + glb_last_error());
+      }
       break;
     }
     default: break;
@@ -355,6 +377,47 @@ void square_staggered_eoprec_reconstruct(zcplx* lhs_full, zcplx* lhs_e, zcplx* r
 void square_laplacian(double* lhs, double* rhs, void* e) { direct_apply<double>(B_LAPLACIAN_REAL, lhs, rhs, e); }
 void square_laplacian(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_LAPLACIAN_IMAG, lhs, rhs, e); }
 void apply_stencil_2d(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_STENCIL, lhs, rhs, e); }
+void apply_square_staggered_m2mdeodoe_stencil(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_SV_M2MDEODOE, lhs, rhs, e); }
+void apply_square_staggered_m2mdtbdbt_stencil(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_SV_M2MDTBDBT, lhs, rhs, e); }
+void apply_square_staggered_normal_eo_stencil(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_SV_NORMAL_EO, lhs, rhs, e); }
+void apply_square_staggered_normal_tb_stencil(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_SV_NORMAL_TB, lhs, rhs, e); }
+void apply_square_staggered_dagger_eo_stencil(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_SV_DAGGER_EO, lhs, rhs, e); }
+void apply_square_staggered_dagger_tb_stencil(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_SV_DAGGER_TB, lhs, rhs, e); }
+// operators_stencil.cpp:179-193, :217-236; mg_complex.cpp:1211-1225, :1252-1272 with host vectors: one device pass each
+static void stencil_prec(int tb, bool reconstruct, zcplx* out, zcplx* a, zcplx* b, stencil_2d* st) {
+  try {
+    glb_context* ctx = glb200_default_context();
+    OpLease L;
+    lease(B_STENCIL, (void*)st, &L);
+    const size_t n = glb_op_local_size(L.op);
+    Blas<zcplx> B = {ctx, n};
+    Work<zcplx> W(B);
+    zcplx *d_a = W.get(), *d_b = W.get(), *d_out = W.get();
+    GLBX(glb_vec_upload(ctx, GLB_COMPLEX, n, d_a, a));
+    if (reconstruct) {
+      GLBX(glb_vec_upload(ctx, GLB_COMPLEX, n, d_b, b));
+      GLBX(glb_stencil_prec_reconstruct(L.op, tb, d_out, d_a, d_b));
+    } else {
+      GLBX(glb_stencil_prec_prepare(L.op, tb, d_out, d_a));
+    }
+    GLBX(glb_vec_download(ctx, GLB_COMPLEX, n, out, d_out));
+  } catch (const std::exception& ex) {
+    std::cerr << "[glb200] preconditioned stencil prepare / reconstruct failed: " << ex.what() << std::endl;
+    std::abort();
+  }
+}
+void apply_square_staggered_eoprec_prepare_stencil(zcplx* rhs_e, zcplx* rhs_orig, stencil_2d* st) {
+  stencil_prec(0, false, rhs_e, rhs_orig, 0, st);
+}
+void apply_square_staggered_eoprec_reconstruct_stencil(zcplx* lhs_full, zcplx* lhs_e, zcplx* rhs_o, stencil_2d* st) {
+  stencil_prec(0, true, lhs_full, lhs_e, rhs_o, st);
+}
+void apply_square_staggered_tbprec_prepare_stencil(zcplx* rhs_t, zcplx* rhs_orig, stencil_2d* st) {
+  stencil_prec(1, false, rhs_t, rhs_orig, 0, st);
+}
+void apply_square_staggered_tbprec_reconstruct_stencil(zcplx* lhs_full, zcplx* lhs_t, zcplx* rhs_b, stencil_2d* st) {
+  stencil_prec(1, true, lhs_full, lhs_t, rhs_b, st);
+}
 static void stencil_part(zcplx* lhs, zcplx* rhs, void* e, int part) {
   try {
     glb_context* ctx = glb200_default_context();

@@ -72,6 +72,15 @@ void gaussian_host(std::vector<zcplx>& v, std::mt19937& generator) {
   }
 }
 
+// a composite view of a stencil2d operator for the duration of one solve
+struct StencilView {
+  glb_operator* view;
+  StencilView(glb_operator* base, int kind) : view(0) { GLBX(glb_op_create_stencil_view(base, kind, 0, &view)); }
+  ~StencilView() {
+    if (view) glb_op_destroy(view);
+  }
+};
+
 void partition(mg_operator_struct_complex_dev* mg, int num_null_vec, blocking_strategy bstrat, bool by_colour) {
   const Level L = level_of(mg);
   const int lvl = mg->curr_level;
@@ -104,8 +113,6 @@ void null_generate_random_smooth_dev(mg_operator_struct_complex_dev* mg, null_ve
                                      inversion_verbose_struct* verb, std::mt19937* generator) {
   const Level L = level_of(mg);
   const int lvl = mg->curr_level;
-  if (nv->null_prec != NULL_PRECOND_NONE)
-    throw Error("null_generate_random_smooth_dev: preconditioned null-vector solves are not on the accelerated path");
   if (nv->null_partitions < 1 || mg->n_vectors[lvl] % nv->null_partitions != 0)
     throw Error("null_generate_random_smooth_dev: n_vectors must be a multiple of null_partitions");
   glb_operator* op = mg->stencils[lvl];
@@ -129,6 +136,9 @@ void null_generate_random_smooth_dev(mg_operator_struct_complex_dev* mg, null_ve
   Work<zcplx> W(B);
   zcplx* rand_guess = W.get();
   zcplx* Arand_guess = W.get();
+  zcplx* prep = (nv->null_prec != NULL_PRECOND_NONE) ? W.get() : 0;      // Arand_guess_prep (:213)
+  zcplx* prec_soln = (nv->null_prec == NULL_PRECOND_EO) ? W.get() : 0;   // Arand_guess_prec_soln (:214)
+  if (prec_soln) B.zero(prec_soln);  // the reference hands this new[]-ed array to the solver as its initial guess
   std::vector<zcplx> host(L.size);
 
   for (int i = 0; i < n_gen; i++) {
@@ -153,9 +163,31 @@ void null_generate_random_smooth_dev(mg_operator_struct_complex_dev* mg, null_ve
     mg->dslash_count->nullvectors[lvl]++;
     GLBX(glb_rscale(L.ctx, GLB_COMPLEX, B.n, Arand_guess, -1.0, Arand_guess));
 
-    // :252-258 (the initial guess is whatever null[i] holds: zero after allocation)
-    inversion_info invif = minv_unpreconditioned_dev(null[i], Arand_guess, L.size, nv->null_gen, solve, apply, (void*)op, verb);
-    mg->dslash_count->nullvectors[lvl] += invif.ops_count;
+    if (nv->null_prec == NULL_PRECOND_NONE) {
+      // :252-258 (the initial guess is whatever null[i] holds: zero after allocation)
+      inversion_info invif = minv_unpreconditioned_dev(null[i], Arand_guess, L.size, nv->null_gen, solve, apply, (void*)op, verb);
+      mg->dslash_count->nullvectors[lvl] += invif.ops_count;
+    } else if (nv->null_prec == NULL_PRECOND_EO) {
+      // :259-289: even/odd preconditioned on the top level, top/bottom (colour halves) below it.  The prepare is
+      // half an apply and is counted with the reconstruct.
+      const int tb = (lvl == 0) ? 0 : 1;
+      StencilView M(op, tb ? GLB_SV_M2MDTBDBT : GLB_SV_M2MDEODOE);
+      GLBX(glb_stencil_prec_prepare(op, tb, prep, Arand_guess));
+      inversion_info invif = minv_unpreconditioned_dev(prec_soln, prep, L.size, nv->null_gen, solve, apply, (void*)M.view, verb);
+      mg->dslash_count->nullvectors[lvl] += invif.ops_count;
+      GLBX(glb_stencil_prec_reconstruct(op, tb, null[i], prec_soln, Arand_guess));
+      mg->dslash_count->nullvectors[lvl]++;
+    } else {
+      // :290-313 NULL_PRECOND_NORMAL: D^dag rhs through epsilon D epsilon (sigma_3 D sigma_3 below the top level),
+      // then the non-Galerkin normal operator m^2 - D_eo D_oe - D_oe D_eo; every solver step counts two applies
+      const int tb = (lvl == 0) ? 0 : 1;
+      StencilView Dd(op, tb ? GLB_SV_DAGGER_TB : GLB_SV_DAGGER_EO);
+      StencilView N(op, tb ? GLB_SV_NORMAL_TB : GLB_SV_NORMAL_EO);
+      GLBX(glb_op_apply(Dd.view, prep, Arand_guess));
+      mg->dslash_count->nullvectors[lvl]++;
+      inversion_info invif = minv_unpreconditioned_dev(null[i], prep, L.size, nv->null_gen, solve, apply, (void*)N.view, verb);
+      mg->dslash_count->nullvectors[lvl] += 2 * invif.ops_count;
+    }
 
     // undo the residual equation (:316-319)
     B.add(null[i], rand_guess, null[i]);

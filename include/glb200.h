@@ -253,6 +253,33 @@ int glb_cg_solve(glb_operator* op, void* d_x, const void* d_b, int max_iter, dou
 #define GLB_PART_BT 4
 int glb_op_apply_part(glb_operator* op, void* d_out, const void* d_in, int part);
 
+/* ----------------------------------------------- preconditioned stencil paths */
+/* The composite operators the reference builds from the partial applies of a stencil_2d, as device operators that
+ * plug into every solver (glb_op_apply; no fused reductions, several passes through a temporary):
+ *   M2MDEODOE  m^2 - D_eo D_oe on even sites, 0 on odd     apply_square_staggered_m2mdeodoe_stencil  operators_stencil.cpp:196
+ *   M2MDTBDBT  m^2 - D_tb D_bt on the top colours, 0 below apply_square_staggered_m2mdtbdbt_stencil  mg_complex.cpp:1228
+ *   NORMAL_EO  m^2 - D_eo D_oe - D_oe D_eo                 apply_square_staggered_normal_eo_stencil  mg_complex.cpp:1278
+ *   NORMAL_TB  m^2 - D_tb D_bt - D_bt D_tb                 apply_square_staggered_normal_tb_stencil  mg_complex.cpp:1306
+ *   DAGGER_EO  epsilon(x) D epsilon(x)                      apply_square_staggered_dagger_eo_stencil  mg_complex.cpp:1336
+ *   DAGGER_TB  sigma_3 D sigma_3                            apply_square_staggered_dagger_tb_stencil  mg_complex.cpp:1355
+ * (m = the stencil's `shift`).  A view shares the matrices and shifts of `base` (read at apply time; set_shifts on
+ * either is seen by both) and must not outlive it, unless adopt_base != 0: then destroying the view destroys the base. */
+#define GLB_SV_M2MDEODOE 1
+#define GLB_SV_M2MDTBDBT 2
+#define GLB_SV_NORMAL_EO 3
+#define GLB_SV_NORMAL_TB 4
+#define GLB_SV_DAGGER_EO 5
+#define GLB_SV_DAGGER_TB 6
+int glb_op_create_stencil_view(glb_operator* base, int kind, int adopt_base, glb_operator** view);
+/* apply_square_staggered_{eo,tb}prec_prepare_stencil (operators_stencil.cpp:179, mg_complex.cpp:1211):
+ * rhs_part = shift*rhs_orig - D_eo rhs_orig on even sites (top_bottom = 0) / - D_tb rhs_orig on the top colours (1),
+ * 0 on the other half.  One pass. */
+int glb_stencil_prec_prepare(glb_operator* op, int top_bottom, void* d_rhs_part, const void* d_rhs_orig);
+/* apply_square_staggered_{eo,tb}prec_reconstruct_stencil (operators_stencil.cpp:217, mg_complex.cpp:1252):
+ * lhs_full = lhs_part on the solved half, (rhs_other - D_oe lhs_part)/Re(shift) on the other half.  One pass. */
+int glb_stencil_prec_reconstruct(glb_operator* op, int top_bottom, void* d_lhs_full, const void* d_lhs_part,
+                                 const void* d_rhs_other);
+
 /* ----------------------------------------------- even/odd preconditioning */
 /* square_staggered_eoprec_prepare (operators.cpp:528-545): rhs_e = m rhs_orig - D_eo rhs_orig on even sites, 0 on
  * odd sites.  `op` is any gauged staggered operator (its links and mass are used). */

@@ -62,6 +62,10 @@ typedef struct orc_op_desc {
   const double* two_link;/* stencil: 8 planes, only if has_two                                           */
   int has_two;
   double shift[2], eo_shift[2], dof_shift[2];
+  int view;              /* stencil kinds only: 0 = apply_stencil_2d, 1..6 = the composite operator built on the
+                            stencil (numbering of include/glb200.h GLB_SV_*): 1 m2mdeodoe (operators_stencil.cpp:196),
+                            2 m2mdtbdbt, 3 normal_eo, 4 normal_tb, 5 dagger_eo, 6 dagger_tb (mg_complex.cpp:1228-1372).
+                            Reference library only.                                                       */
 } orc_op_desc;
 
 typedef struct orc_result {

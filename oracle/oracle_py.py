@@ -27,7 +27,8 @@ class OpDesc(C.Structure):
     _fields_ = [("kind", C.c_int), ("X", C.c_int), ("Y", C.c_int), ("Nc", C.c_int),
                 ("mass", C.c_double), ("links", C.c_void_p), ("clover", C.c_void_p),
                 ("hopping", C.c_void_p), ("two_link", C.c_void_p), ("has_two", C.c_int),
-                ("shift", C.c_double * 2), ("eo_shift", C.c_double * 2), ("dof_shift", C.c_double * 2)]
+                ("shift", C.c_double * 2), ("eo_shift", C.c_double * 2), ("dof_shift", C.c_double * 2),
+                ("view", C.c_int)]
 
 
 class Result(C.Structure):
@@ -46,9 +47,14 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
+VIEW = dict(NONE=0, M2MDEODOE=1, M2MDTBDBT=2, NORMAL_EO=3, NORMAL_TB=4, DAGGER_EO=5, DAGGER_TB=6)
+
+
 class Operator:
     def __init__(self, orc, kind, X, Y, mass=0.0, Nc=1, links=None, clover=None, hopping=None, two_link=None,
-                 shift=0j, eo_shift=0j, dof_shift=0j):
+                 shift=0j, eo_shift=0j, dof_shift=0j, view=0):
+        """view (stencil kinds, reference library only): VIEW name or number of the composite operator built on the
+        stencil -- M2MDEODOE, M2MDTBDBT, NORMAL_EO, NORMAL_TB, DAGGER_EO, DAGGER_TB"""
         self.orc = orc
         self._keep = (links, clover, hopping, two_link)
         d = OpDesc()
@@ -59,8 +65,11 @@ class Operator:
         for name, v in (("shift", shift), ("eo_shift", eo_shift), ("dof_shift", dof_shift)):
             getattr(d, name)[0] = complex(v).real
             getattr(d, name)[1] = complex(v).imag
+        d.view = VIEW[view] if isinstance(view, str) else view
         self.desc = d
         self.h = orc._f("op_prepare")(C.byref(d))
+        if not self.h:
+            raise RuntimeError("this oracle library cannot build the operator (composite stencil views need `ref`)")
         self.is_complex = bool(orc._f("op_is_complex")(self.h))
         self.size = orc._f("op_size")(self.h)
         self.dtype = np.complex128 if self.is_complex else np.float64
@@ -244,7 +253,7 @@ class RefMg:
         vp, ci, cd = C.c_void_p, C.c_int, C.c_double
         for name, res, args in (("refmg_create2", vp, [ci, ci, vp, cd, ci, vp, vp, vp, ci]),
                                 ("refmg_setup", vp, [ci, ci, vp, cd, ci, vp, vp, ci, cd, ci, vp, vp, ci, ci, ci, ci,
-                                                     C.c_uint, ci]),
+                                                     C.c_uint, ci, ci]),
                                 ("refmg_null_counts", None, [vp, vp]),
                                 ("refmg_level_dims", None, [vp, ci, vp, vp, vp]),
                                 ("refmg_get_null", None, [vp, ci, ci, vp]),
@@ -261,11 +270,12 @@ class RefMg:
     @classmethod
     def setup(cls, orc, X, Y, links, mass, blocks, nvecs, bstrat=1, null_mass=1e-2, null_gen="BICGSTAB", tol=5e-5,
               max_iter=500, restart_freq=0, bicgstab_l=-1, do_ortho_eo=False, do_global_ortho_conj=False, seed=1337,
-              verbosity=0):
+              verbosity=0, null_prec=0):
         """The reference driver's complete set-up (aa_mg_square_staggered_u1.cpp:716-1143; oracle/ref_mg_shim.cpp
         refmg_setup): null vectors from null_generate_random_smooth with a std::mt19937(seed), block_orthonormalize,
         generate_coarse_from_fine_stencil(ignore_shifts=true) with the shift copied down.  nvecs[l] = total vectors
-        of refinement l (after the partition); bstrat 0 = BLOCK_NONE, 1 = BLOCK_EO."""
+        of refinement l (after the partition); bstrat 0 = BLOCK_NONE, 1 = BLOCK_EO; null_prec 0 = none, 1 = even/odd
+        (top/bottom below the top level), 2 = normal equations (null_gen.h:24-29)."""
         self = cls.__new__(cls)
         self._bind(orc)
         self.n_refine = len(blocks)
@@ -277,7 +287,7 @@ class RefMg:
         self._keep = (blocks_a, nvecs_a, tol_a, it_a)
         self.h = self.L.refmg_setup(X, Y, _ptr(self.links), mass, self.n_refine, _ptr(blocks_a), _ptr(nvecs_a), bstrat,
                                     null_mass, self.SMOOTH[null_gen], _ptr(tol_a), _ptr(it_a), restart_freq, bicgstab_l,
-                                    int(do_ortho_eo), int(do_global_ortho_conj), seed, verbosity)
+                                    int(do_ortho_eo), int(do_global_ortho_conj), seed, verbosity, null_prec)
         return self
 
     def null_counts(self):
@@ -365,6 +375,22 @@ def ref_solve_multi(orc, which, op, b, shifts, resid_freq_check=10, max_iter=100
       C.byref(res))
     by_addr = {x.ctypes.data: x for x in xs}
     return [by_addr[ptrs[i]] for i in range(n)], res.as_dict(), shifts
+
+
+def ref_stencil_prec(orc, op, top_bottom, a, b=None):
+    """apply_square_staggered_{eo,tb}prec_prepare_stencil (b is None) / _reconstruct_stencil (a = lhs_part,
+    b = rhs_other) of the reference on a stencil operator (`ref` library only)"""
+    f = orc.lib.ref_stencil_prec
+    f.restype = None
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    a = np.ascontiguousarray(a, dtype=np.complex128)
+    out = np.zeros_like(a)
+    if b is None:
+        f(op.h, int(top_bottom), 0, _ptr(out), _ptr(a), None)
+    else:
+        b = np.ascontiguousarray(b, dtype=np.complex128)
+        f(op.h, int(top_bottom), 1, _ptr(out), _ptr(a), _ptr(b))
+    return out
 
 
 def ref_solve_relax(orc, which, op, b, x0=None, max_iter=10000, eps=1e-10, omega=1.0):

@@ -1030,6 +1030,7 @@ double port_diffnorm2sq(int is_complex, const double* a, const double* b, int n)
 }
 
 void* port_op_prepare(const orc_op_desc* d) {
+  if (d->view != 0) return 0;  // the composite stencil operators exist in the reference library only
   PortOp* op = new PortOp();
   op->d = *d;
   op->nc = d->Nc > 0 ? d->Nc : 1;

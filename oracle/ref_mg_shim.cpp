@@ -27,6 +27,7 @@ using namespace std;
 #include "coarse_stencil.h"
 #include "null_gen.h"
 #include <random>
+#include <malloc.h>
 
 namespace {
 
@@ -179,15 +180,16 @@ void* refmg_create(int X, int Y, const double* links, double mass, int n_refine,
 //   null_gen      minv_inverter of the smoothing solve; tol[l], max_iter[l] per refinement
 //   restart_freq  > 0: restarted solver;  bicgstab_l: l of BiCGStab-l
 //   seed          std::mt19937 seed of the gaussian sources
+//   null_prec     null_precond_strategy (null_gen.h:24-29): 0 none, 1 even/odd (top/bottom below the top level), 2 normal
 void* refmg_setup(int X, int Y, const double* links, double mass, int n_refine, const int* block, const int* nvec,
                   int bstrat, double null_mass, int null_gen, const double* tol, const int* max_iter, int restart_freq,
-                  int bicgstab_l, int do_ortho_eo, int do_global_ortho_conj, unsigned seed, int verbosity) {
+                  int bicgstab_l, int do_ortho_eo, int do_global_ortho_conj, unsigned seed, int verbosity, int null_prec) {
   RefMg* h = make_struct(X, Y, links, mass, n_refine, block, nvec, 0);
   mg_operator_struct_complex& mg = h->mg;
   null_vector_params nv;
   nv.opt_null = STAGGERED;
   nv.null_gen = (minv_inverter)null_gen;
-  nv.null_prec = NULL_PRECOND_NONE;
+  nv.null_prec = (null_precond_strategy)null_prec;
   nv.null_restart = restart_freq > 0;
   nv.null_restart_freq = restart_freq;
   nv.null_bicgstab_l = bicgstab_l;
@@ -212,6 +214,10 @@ void* refmg_setup(int X, int Y, const double* links, double mass, int n_refine, 
   get_square_staggered_u1_stencil(mg.stencils[0], &h->stagif);
   h->stagif.mass = mass;
   mg.stencils[0]->shift = null_mass;
+  // null_gen.cpp:214,266: with NULL_PRECOND_EO the reference hands a new[]-ed, never initialised array to the solver
+  // as its initial guess.  Make that read defined for the comparison: glibc fills fresh allocations with the
+  // complement of M_PERTURB's low byte, so 0xFF gives the zero-filled memory a fresh mmap would have given.
+  if (null_prec == NULL_PRECOND_EO) mallopt(M_PERTURB, 0xFF);
   for (int n = 0; n < n_refine; n++) {
     verb.verb_prefix = "[L" + to_string(mg.curr_level + 1) + "_NULLVEC]: ";
     null_generate_random_smooth(&mg, &nv, &verb, &generator);
@@ -222,6 +228,7 @@ void* refmg_setup(int X, int Y, const double* links, double mass, int n_refine, 
       level_down(&mg);
     }
   }
+  if (null_prec == NULL_PRECOND_EO) mallopt(M_PERTURB, 0);
   for (int n = 1; n < n_refine; n++) level_up(&mg);
   // final stencils with the true mass (:982-1143)
   for (int n = 0; n <= n_refine; n++) mg.stencils[n]->clear_stencils();

@@ -29,6 +29,7 @@
 #include "lattice.h"
 #include "coarse_stencil.h"
 #include "operators_stencil.h"
+#include "mg_complex.h"
 
 using std::complex;
 typedef complex<double> cplx;
@@ -86,7 +87,17 @@ void apply_c(RefOp* op, cplx* lhs, cplx* rhs) {
     case ORC_OP_STAG_DOE_U1: square_staggered_doe_u1(lhs, rhs, e); break;
     case ORC_OP_STAG_M2MDEODOE_U1: square_staggered_m2mdeodoe_u1(lhs, rhs, e); break;
     case ORC_OP_STENCIL:
-    case ORC_OP_STENCIL_FROM_STAG: apply_stencil_2d(lhs, rhs, (void*)op->stenc); break;
+    case ORC_OP_STENCIL_FROM_STAG:
+      switch (op->d.view) {
+        case 1: apply_square_staggered_m2mdeodoe_stencil(lhs, rhs, (void*)op->stenc); break;
+        case 2: apply_square_staggered_m2mdtbdbt_stencil(lhs, rhs, (void*)op->stenc); break;
+        case 3: apply_square_staggered_normal_eo_stencil(lhs, rhs, (void*)op->stenc); break;
+        case 4: apply_square_staggered_normal_tb_stencil(lhs, rhs, (void*)op->stenc); break;
+        case 5: apply_square_staggered_dagger_eo_stencil(lhs, rhs, (void*)op->stenc); break;
+        case 6: apply_square_staggered_dagger_tb_stencil(lhs, rhs, (void*)op->stenc); break;
+        default: apply_stencil_2d(lhs, rhs, (void*)op->stenc); break;
+      }
+      break;
     default: break;
   }
 }
@@ -237,6 +248,23 @@ void ref_op_apply(void* opv, double* lhs, const double* rhs) {
     apply_c(op, (cplx*)lhs, (cplx*)rhs);
   else
     apply_r(op, lhs, (double*)rhs);
+}
+
+// apply_square_staggered_{eo,tb}prec_{prepare,reconstruct}_stencil (operators_stencil.cpp:179,217; mg_complex.cpp:1211,1252)
+// prepare: out = f(a); reconstruct: out = f(a = lhs_part, b = rhs_other)
+void ref_stencil_prec(void* opv, int top_bottom, int reconstruct, double* out, const double* a, const double* b) {
+  RefOp* op = (RefOp*)opv;
+  if (!reconstruct) {
+    if (top_bottom)
+      apply_square_staggered_tbprec_prepare_stencil((cplx*)out, (cplx*)a, op->stenc);
+    else
+      apply_square_staggered_eoprec_prepare_stencil((cplx*)out, (cplx*)a, op->stenc);
+  } else {
+    if (top_bottom)
+      apply_square_staggered_tbprec_reconstruct_stencil((cplx*)out, (cplx*)a, (cplx*)b, op->stenc);
+    else
+      apply_square_staggered_eoprec_reconstruct_stencil((cplx*)out, (cplx*)a, (cplx*)b, op->stenc);
+  }
 }
 
 void ref_stencil_apply_part(void* opv, int part, double* lhs, const double* rhs) {

@@ -19,6 +19,10 @@ struct glb_operator {
   PortOp* op;
   int dtype;
   std::vector<cplx> links;
+  int composite;          // GLB_SV_* view of `base` (op is then the base's PortOp)
+  glb_operator* base;
+  bool owns_base;
+  glb_operator() : ctx(0), op(0), dtype(0), composite(0), base(0), owns_base(false) {}
 };
 
 static std::string g_err;
@@ -142,7 +146,54 @@ int glb_op_create_stencil2d(glb_context*, const void* cl, const void* hp, const 
   *op = o;
   return GLB_OK;
 }
-int glb_op_destroy(glb_operator* o) { if (o) { port_op_free(o->op); delete o; } return GLB_OK; }
+int glb_op_destroy(glb_operator* o) {
+  if (!o) return GLB_OK;
+  if (o->base) {
+    if (o->owns_base) glb_op_destroy(o->base);
+  } else {
+    port_op_free(o->op);
+  }
+  delete o;
+  return GLB_OK;
+}
+int glb_op_create_stencil_view(glb_operator* base, int kind, int adopt, glb_operator** out) {
+  if (!base || base->base || kind < GLB_SV_M2MDEODOE || kind > GLB_SV_DAGGER_TB) return GLB_ERR_ARG;
+  glb_operator* v = new glb_operator();
+  v->ctx = base->ctx; v->op = base->op; v->dtype = base->dtype;
+  v->composite = kind; v->base = base; v->owns_base = adopt != 0;
+  *out = v;
+  return GLB_OK;
+}
+// operators_stencil.cpp:179-193 / mg_complex.cpp:1211-1225
+int glb_stencil_prec_prepare(glb_operator* o, int tb, void* rhs_part, const void* rhs_orig) {
+  g_calls++;
+  PortOp* st = o->op;
+  const int n = st->size, X = st->d.X, nc = st->nc;
+  cplx* out = (cplx*)rhs_part; const cplx* orig = (const cplx*)rhs_orig;
+  port_stencil_apply_part(st, tb ? GLB_PART_TB : GLB_PART_EO, (double*)out, (const double*)orig);
+  for (int i = 0; i < n; i++) {
+    const int site = i / nc;
+    const bool sel = tb ? (i % nc) < nc / 2 : ((site % X + site / X) % 2 == 0);
+    if (sel) out[i] = st->shift * orig[i] - out[i];
+  }
+  return GLB_OK;
+}
+// operators_stencil.cpp:217-236 / mg_complex.cpp:1252-1272
+int glb_stencil_prec_reconstruct(glb_operator* o, int tb, void* lhs_full, const void* lhs_part, const void* rhs_other) {
+  g_calls++;
+  PortOp* st = o->op;
+  const int n = st->size, X = st->d.X, nc = st->nc;
+  cplx* out = (cplx*)lhs_full; const cplx* part = (const cplx*)lhs_part; const cplx* other = (const cplx*)rhs_other;
+  const double inv_mass = 1.0 / real(st->shift);
+  port_stencil_apply_part(st, tb ? GLB_PART_BT : GLB_PART_OE, (double*)out, (const double*)part);
+  for (int i = 0; i < n; i++) {
+    const int site = i / nc;
+    const bool sel = tb ? (i % nc) < nc / 2 : ((site % X + site / X) % 2 == 0);
+    if (!sel) out[i] = inv_mass * (other[i] - out[i]);
+    else out[i] = part[i];
+  }
+  return GLB_OK;
+}
 int glb_op_set_mass(glb_operator* o, double m) { o->op->d.mass = m; return GLB_OK; }
 int glb_op_dtype(const glb_operator* o) { return o->dtype; }
 size_t glb_op_local_size(const glb_operator* o) { return o->op->size; }
@@ -164,9 +215,48 @@ int glb_stag_eoprec_reconstruct(glb_operator* o, void* lhs_full, const void* lhs
   port_eoprec_reconstruct(o->op, (double*)lhs_full, (const double*)lhs_e, (const double*)rhs_o);
   return GLB_OK;
 }
+// the composite stencil operators in the reference's statement order (operators_stencil.cpp:196-214,
+// mg_complex.cpp:1228-1372)
+static void mock_composite(glb_operator* o, cplx* lhs, const cplx* rhs) {
+  PortOp* st = o->op;
+  const int n = st->size, X = st->d.X, nc = st->nc;
+  std::vector<cplx> tmp(n), tmp2(n);
+  const int kind = o->composite;
+  const bool tb = (kind == GLB_SV_M2MDTBDBT || kind == GLB_SV_NORMAL_TB || kind == GLB_SV_DAGGER_TB);
+  const int A = tb ? GLB_PART_TB : GLB_PART_EO, B = tb ? GLB_PART_BT : GLB_PART_OE;
+  if (kind == GLB_SV_M2MDEODOE || kind == GLB_SV_M2MDTBDBT) {
+    port_stencil_apply_part(st, B, (double*)tmp.data(), (const double*)rhs);
+    port_stencil_apply_part(st, A, (double*)lhs, (const double*)tmp.data());
+    for (int i = 0; i < n; i++) {
+      const int site = i / nc;
+      const bool sel = tb ? (i % nc) < nc / 2 : ((site % X + site / X) % 2 == 0);
+      if (sel) lhs[i] = st->shift * st->shift * rhs[i] - lhs[i];
+    }
+  } else if (kind == GLB_SV_NORMAL_EO || kind == GLB_SV_NORMAL_TB) {
+    port_stencil_apply_part(st, A, (double*)tmp2.data(), (const double*)rhs);
+    port_stencil_apply_part(st, B, (double*)lhs, (const double*)tmp2.data());
+    port_stencil_apply_part(st, B, (double*)tmp2.data(), (const double*)rhs);
+    port_stencil_apply_part(st, A, (double*)tmp.data(), (const double*)tmp2.data());
+    for (int i = 0; i < n; i++) lhs[i] = st->shift * st->shift * rhs[i] - lhs[i] - tmp[i];
+  } else {
+    auto sign = [&](cplx* out, const cplx* in) {
+      for (int i = 0; i < n; i++) {
+        const int site = i / nc;
+        const bool flip = tb ? (nc % 2 == 0 && (i % nc) >= nc / 2) : ((site % X + site / X) % 2 != 0);
+        out[i] = flip ? -in[i] : in[i];
+      }
+    };
+    sign(lhs, rhs);
+    port_op_apply(st, (double*)tmp.data(), (const double*)lhs);
+    sign(lhs, tmp.data());
+  }
+}
 int glb_op_apply(glb_operator* o, void* out, const void* in) {
   g_calls++;
-  port_op_apply(o->op, (double*)out, (const double*)in);
+  if (o->composite)
+    mock_composite(o, (cplx*)out, (const cplx*)in);
+  else
+    port_op_apply(o->op, (double*)out, (const double*)in);
   return GLB_OK;
 }
 int glb_dot(glb_context*, int dt, size_t n, const void* x, const void* y, double out[2]) {

@@ -1,4 +1,4 @@
-"""The Python side of the multigrid set-up GPU tests (tests/test_mg_setup_gpu.py) run against the CPU mock of the C ABI
+"""The Python side of some GPU test modules (multigrid set-up, preconditioned stencil paths) run against the CPU mock of the C ABI
 in a child process (tests/mock/run_gpu_tests_on_mock.py): bindings, argument orders, shapes and assertions of the
 `-m gpu` tests are exercised here, where no GPU exists, so that GPU minutes are spent on the kernels only.  Says
 nothing about the CUDA code."""
@@ -15,7 +15,7 @@ pytestmark = pytest.mark.skipif("ref" not in oracle_py.available(),
                                 reason="the reference's multigrid is only in oracle/_ref/libref_oracle.so")
 
 
-@pytest.mark.parametrize("module", ["test_mg_setup_gpu"])
+@pytest.mark.parametrize("module", ["test_mg_setup_gpu", "test_stencil_prec_gpu"])
 def test_gpu_test_logic_runs_on_the_mock(module):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "mock", "run_gpu_tests_on_mock.py"), module],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)

