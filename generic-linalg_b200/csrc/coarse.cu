@@ -446,61 +446,127 @@ static bool ring_enabled() {
 //   2: coef.re*(aux - s) | in             *prec_reconstruct (coef.re = 1/Re shift; the other half is copied from in)
 //   3: coef*aux - s on EVERY dof          first half of m^2 - D_ab D_ba - D_ba D_ab (s = 0 off the live half)
 //   4: out - s on EVERY dof               second half of the same (out is read and rewritten)
+//
+// Thread mapping.  Half of the dofs are dead in every partial apply.  PAIRED = true gives each thread one LIVE dof and
+// its dead partner (e/o: the x-neighbour inside the same pair of sites, needs an even X; t/b: the same row in the
+// other half of the colour index, needs an even nc), so that no lane idles while the matrices stream in; the sum for
+// the live dof runs in the reference's order either way.  PAIRED = false is the one-thread-per-dof form for odd X / nc.
+// WIDE: the colour range is even and every array 32-byte aligned -> matrix rows and input sites are read two
+// complex numbers at a time (LDG.256); the additions keep their order.
+template <bool WIDE>
+__device__ __forceinline__ cplx part_sum(const CoarseArgs& a, const int part, const size_t i, const int x, const int y,
+                                         const size_t plane) {
+  const int nc = a.nc, X = a.X;
+  const size_t site = i / nc;
+  cplx s = mk(0.0, 0.0);
+  int c0 = 0, c1 = nc;
+  const bool colour_split = (part == GLB_PART_TB || part == GLB_PART_BT);
+  if (colour_split) {
+    c0 = (part == GLB_PART_TB) ? nc / 2 : 0;
+    c1 = (part == GLB_PART_TB) ? nc : nc / 2;
+  }
+  (void)site;
+  const int xp = (x + 1 == X) ? 0 : x + 1, xm = (x == 0) ? X - 1 : x - 1;
+  auto term = [&](const cplx* M, const cplx* v) {
+    if (WIDE) {
+      for (int c = c0; c < c1; c += 2) {
+        cplx m2[2], v2[2];
+        ldv_nc<2>(M + c, m2);
+        ldv_nc<2>(v + c, v2);
+        s = fadd(s, fmul(m2[0], v2[0]));
+        s = fadd(s, fmul(m2[1], v2[1]));
+      }
+    } else {
+      for (int c = c0; c < c1; c++) s = fadd(s, fmul(__ldg(M + c), v[c]));
+    }
+  };
+  if (colour_split) term(a.clover + i * nc, site_ptr(a, x, y));
+  const cplx* H = a.hopping + i * nc;
+  term(H, site_ptr(a, xp, y));
+  term(H + plane, site_ptr(a, x, y + 1));
+  term(H + 2 * plane, site_ptr(a, xm, y));
+  term(H + 3 * plane, site_ptr(a, x, y - 1));
+  if (a.has_two && colour_split) {
+    const int xpp = (x + 2) % X, xmm = (x - 2 + 2 * X) % X;
+    const cplx* T = a.two_link + i * nc;
+    term(T, site_ptr(a, xpp, y));
+    term(T + plane, site_ptr(a, xp, y + 1));
+    term(T + 2 * plane, site_ptr(a, x, y + 2));
+    term(T + 3 * plane, site_ptr(a, xm, y + 1));
+    term(T + 4 * plane, site_ptr(a, xmm, y));
+    term(T + 5 * plane, site_ptr(a, xm, y - 1));
+    term(T + 6 * plane, site_ptr(a, x, y - 2));
+    term(T + 7 * plane, site_ptr(a, xp, y - 1));
+  }
+  return s;
+}
+
+__device__ __forceinline__ void part_store(const CoarseArgs& a, const int post, const bool live, const cplx s, const cplx coef,
+                                           const cplx* __restrict__ aux, const size_t i) {
+  cplx r;
+  switch (post) {
+    case 1: r = live ? fsub(fmul(coef, aux[i]), s) : mk(0.0, 0.0); break;
+    case 2: r = live ? fscale(coef.x, fsub(aux[i], s)) : a.in[i]; break;
+    case 3: r = fsub(fmul(coef, aux[i]), s); break;
+    case 4:
+      if (!live) return;  // out - 0 = out
+      r = fsub(a.out[i], s);
+      break;
+    default: r = s; break;
+  }
+  a.out[i] = r;
+}
+
+template <bool PAIRED, bool WIDE>
 __global__ void __launch_bounds__(256) coarse_part_kernel(const CoarseArgs a, const int part, const int post, const cplx coef,
                                                           const cplx* __restrict__ aux) {
   const int nc = a.nc;
   const int X = a.X;
   const size_t L = (size_t)X * a.Yloc * nc;
   const size_t plane = L * nc;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < L; i += (size_t)gridDim.x * blockDim.x) {
-    const int row = (int)(i % nc);
-    const size_t site = i / nc;
-    const int x = (int)(site % X), y = (int)(site / X);
-    cplx s = mk(0.0, 0.0);
-    int c0 = 0, c1 = nc;
-    bool live;
-    if (part == GLB_PART_EO || part == GLB_PART_OE) {
-      const bool even = (((x + y + a.y0) & 1) == 0);
-      live = (part == GLB_PART_EO) ? even : !even;
-    } else {
-      const bool top = row < nc / 2;
-      live = (part == GLB_PART_TB) ? top : !top;
-      c0 = (part == GLB_PART_TB) ? nc / 2 : 0;
-      c1 = (part == GLB_PART_TB) ? nc : nc / 2;
-    }
-    if (live) {
-      const int xp = (x + 1 == X) ? 0 : x + 1, xm = (x == 0) ? X - 1 : x - 1;
-      auto term = [&](const cplx* M, const cplx* v) {
-        for (int c = c0; c < c1; c++) s = fadd(s, fmul(__ldg(M + c), v[c]));
-      };
-      if (part == GLB_PART_TB || part == GLB_PART_BT) term(a.clover + i * nc, site_ptr(a, x, y));
-      const cplx* H = a.hopping + i * nc;
-      term(H, site_ptr(a, xp, y));
-      term(H + plane, site_ptr(a, x, y + 1));
-      term(H + 2 * plane, site_ptr(a, xm, y));
-      term(H + 3 * plane, site_ptr(a, x, y - 1));
-      if (a.has_two && (part == GLB_PART_TB || part == GLB_PART_BT)) {
-        const int xpp = (x + 2) % X, xmm = (x - 2 + 2 * X) % X;
-        const cplx* T = a.two_link + i * nc;
-        term(T, site_ptr(a, xpp, y));
-        term(T + plane, site_ptr(a, xp, y + 1));
-        term(T + 2 * plane, site_ptr(a, x, y + 2));
-        term(T + 3 * plane, site_ptr(a, xm, y + 1));
-        term(T + 4 * plane, site_ptr(a, xmm, y));
-        term(T + 5 * plane, site_ptr(a, xm, y - 1));
-        term(T + 6 * plane, site_ptr(a, x, y - 2));
-        term(T + 7 * plane, site_ptr(a, xp, y - 1));
+  const bool site_split = (part == GLB_PART_EO || part == GLB_PART_OE);
+  if (PAIRED) {
+    const int h = nc / 2, Xh = X / 2;
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < L / 2; j += (size_t)gridDim.x * blockDim.x) {
+      size_t i_live, i_dead;
+      int x, y;
+      if (site_split) {
+        const int row = (int)(j % nc);
+        const size_t ps = j / nc;
+        y = (int)(ps / Xh);
+        const int k = (int)(ps % Xh);
+        const int b = (y + a.y0) & 1;                               // parity of the row offset
+        x = 2 * k + ((part == GLB_PART_EO) ? b : 1 - b);            // the site of the pair with the wanted parity
+        i_live = ((size_t)y * X + x) * nc + row;
+        i_dead = ((size_t)y * X + (x ^ 1)) * nc + row;
+      } else {
+        const int r = (int)(j % h);
+        const size_t site = j / h;
+        x = (int)(site % X);
+        y = (int)(site / X);
+        i_live = site * nc + ((part == GLB_PART_TB) ? r : r + h);
+        i_dead = site * nc + ((part == GLB_PART_TB) ? r + h : r);
       }
+      const cplx s = part_sum<WIDE>(a, part, i_live, x, y, plane);
+      part_store(a, post, true, s, coef, aux, i_live);
+      part_store(a, post, false, mk(0.0, 0.0), coef, aux, i_dead);
     }
-    cplx r;
-    switch (post) {
-      case 1: r = live ? fsub(fmul(coef, aux[i]), s) : mk(0.0, 0.0); break;
-      case 2: r = live ? fscale(coef.x, fsub(aux[i], s)) : a.in[i]; break;
-      case 3: r = fsub(fmul(coef, aux[i]), s); break;
-      case 4: r = fsub(a.out[i], s); break;
-      default: r = s; break;
+  } else {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < L; i += (size_t)gridDim.x * blockDim.x) {
+      const int row = (int)(i % nc);
+      const size_t site = i / nc;
+      const int x = (int)(site % X), y = (int)(site / X);
+      bool live;
+      if (site_split) {
+        const bool even = (((x + y + a.y0) & 1) == 0);
+        live = (part == GLB_PART_EO) ? even : !even;
+      } else {
+        const bool top = row < nc / 2;
+        live = (part == GLB_PART_TB) ? top : !top;
+      }
+      const cplx s = live ? part_sum<false>(a, part, i, x, y, plane) : mk(0.0, 0.0);
+      part_store(a, post, live, s, coef, aux, i);
     }
-    a.out[i] = r;
   }
 }
 
@@ -553,10 +619,22 @@ int launch_stencil2d_part(glb_operator* op, void* out, const void* in, int part,
   a.nc = op->nc;
   a.has_two = op->has_two ? 1 : 0;
   const size_t L = rowlen * op->Yloc;
-  const int grid = blas_grid(ctx, L, 256, 1);
+  const bool site_split = (part == GLB_PART_EO || part == GLB_PART_OE);
+  const bool paired = site_split ? (op->X % 2 == 0) : (op->nc % 2 == 0);
+  const cplx cf = coef ? make_double2(coef[0], coef[1]) : make_double2(0.0, 0.0);
   ProfScope prof(ctx, PROF_COARSE);
-  coarse_part_kernel<<<grid, 256, 0, ctx->stream>>>(a, part, post, coef ? make_double2(coef[0], coef[1]) : make_double2(0.0, 0.0),
-                                                    (const cplx*)aux);
+  // two complex numbers per load: the summed colour range [c0, c1) must start and end on an even colour
+  // (e/o: nc even; t/b: nc a multiple of 4) and every array must be 32-byte aligned
+  const bool even_range = site_split ? (op->nc % 2 == 0) : (op->nc % 4 == 0);
+  const uintptr_t addrs = (uintptr_t)a.in | (uintptr_t)a.in_lo | (uintptr_t)a.in_hi | (uintptr_t)a.clover |
+                          (uintptr_t)a.hopping | (uintptr_t)a.two_link;
+  const bool wide = paired && even_range && (addrs & 31u) == 0 && ring_enabled();
+  if (paired && wide)
+    coarse_part_kernel<true, true><<<blas_grid(ctx, L / 2, 256, 1), 256, 0, ctx->stream>>>(a, part, post, cf, (const cplx*)aux);
+  else if (paired)
+    coarse_part_kernel<true, false><<<blas_grid(ctx, L / 2, 256, 1), 256, 0, ctx->stream>>>(a, part, post, cf, (const cplx*)aux);
+  else
+    coarse_part_kernel<false, false><<<blas_grid(ctx, L, 256, 1), 256, 0, ctx->stream>>>(a, part, post, cf, (const cplx*)aux);
   GLB_LAUNCH_CHECK();
   return GLB_OK;
 }
