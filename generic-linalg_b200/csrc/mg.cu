@@ -114,22 +114,32 @@ __global__ void __launch_bounds__(128) mg_block_orthonormalize_kernel(const MgNu
   }
 }
 
-// null_partition_staggered / null_partition_coarse, BLOCK_EO (null_gen.cpp:26-35, :109-126): the odd part of `even_io`
-// (odd sites on the top level; below it the elements whose index modulo colour_period lies in the upper half of the
-// period) moves to `odd_out` and is zeroed in place.
-__global__ void mg_partition_kernel(cplx* __restrict__ even_io, cplx* __restrict__ odd_out, size_t n, int X, int dof, int y0,
-                                    int colour_period) {
+// null_partition_staggered / null_partition_coarse (null_gen.cpp:13-160): the elements of class `which` move from
+// `src_io` to `dst_out` and are zeroed in place.  Classes: BLOCK_EO (nparts = 2) -- 1 = odd sites on the top level, below
+// it the elements whose index modulo colour_period lies in the upper half of the period; BLOCK_CORNER (nparts = 4) --
+// top level: 1 = (x odd, y odd), 2 = (x odd, y even), 3 = (x even, y odd) (null_gen.cpp:74-88); below it the quarters
+// of the period with the reference's integer bounds p/4, 2p/4, 3p/4 (:132-152).
+__global__ void mg_partition_kernel(cplx* __restrict__ src_io, cplx* __restrict__ dst_out, size_t n, int X, int dof, int y0,
+                                    int colour_period, int nparts, int which) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    bool odd;
+    int cls;
     if (colour_period > 0) {
-      odd = (int)(i % colour_period) >= colour_period / 2;
+      const int c = (int)(i % colour_period), p = colour_period;
+      if (nparts == 2)
+        cls = (c >= p / 2) ? 1 : 0;
+      else
+        cls = (c >= p / 4 && c < 2 * p / 4) ? 1 : (c >= 2 * p / 4 && c < 3 * p / 4) ? 2 : (c >= 3 * p / 4) ? 3 : 0;
     } else {
       const size_t site = i / dof;
-      odd = ((site % X + site / X + y0) & 1) != 0;
+      const int xo = (int)(site % X) & 1, yo = ((int)(site / X) + y0) & 1;
+      if (nparts == 2)
+        cls = xo ^ yo;
+      else
+        cls = (xo && yo) ? 1 : (xo && !yo) ? 2 : (!xo && yo) ? 3 : 0;
     }
-    if (odd) {
-      odd_out[i] = even_io[i];
-      even_io[i] = mk(0.0, 0.0);
+    if (cls == which) {
+      dst_out[i] = src_io[i];
+      src_io[i] = mk(0.0, 0.0);
     }
   }
 }
@@ -289,9 +299,21 @@ int glb_mg_transfer_create_dev(glb_context* ctx, int Xf, int Yf, int dof_f, int 
     return fail(GLB_ERR_CUDA, "glb_mg_transfer_create_dev: out of device memory");
   }
   const int grid = blas_grid(ctx, nf, 256, 1);
-  for (int v = 0; v < nvec; v++)
+  for (int v = 0; v < nvec; v++) {
+    if (!d_null_vectors[v]) {
+      cudaFree(t->null);
+      delete t;
+      return fail(GLB_ERR_ARG, "glb_mg_transfer_create_dev: null vector pointer is null");
+    }
     mg_interleave_kernel<<<grid, 256, 0, ctx->stream>>>(t->null, (const cplx*)d_null_vectors[v], nf, nvec, v);
-  GLB_LAUNCH_CHECK();
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    cudaFree(t->null);
+    delete t;
+    return fail(GLB_ERR_CUDA, std::string("glb_mg_transfer_create_dev: ") + cudaGetErrorString(e));
+  }
   *out = t;
   return GLB_OK;
 }
@@ -310,14 +332,26 @@ int glb_mg_block_orthonormalize(glb_context* ctx, int Xf, int Yf, int dof_f, int
   return GLB_OK;
 }
 
-int glb_mg_partition(glb_context* ctx, int X, int Y, int dof, int colour_period, void* d_even_io, void* d_odd_out) {
-  if (!ctx || !d_even_io || !d_odd_out) return fail(GLB_ERR_ARG, "glb_mg_partition: null argument");
-  if (X < 1 || Y < 1 || dof < 1 || colour_period < 0) return fail(GLB_ERR_ARG, "glb_mg_partition: bad extents");
+static int partition_launch(glb_context* ctx, int X, int Y, int dof, int colour_period, int nparts, int which, void* d_src_io,
+                            void* d_dst_out, const char* who) {
+  if (!ctx || !d_src_io || !d_dst_out) return fail(GLB_ERR_ARG, std::string(who) + ": null argument");
+  if (X < 1 || Y < 1 || dof < 1 || colour_period < 0 || which < 1 || which >= nparts)
+    return fail(GLB_ERR_ARG, std::string(who) + ": bad extents or class");
+  if (d_src_io == d_dst_out) return fail(GLB_ERR_ARG, std::string(who) + ": source and target must differ");
   const size_t n = (size_t)X * Y * dof;
   const int grid = blas_grid(ctx, n, 256, 1);
-  mg_partition_kernel<<<grid, 256, 0, ctx->stream>>>((cplx*)d_even_io, (cplx*)d_odd_out, n, X, dof, 0, colour_period);
+  mg_partition_kernel<<<grid, 256, 0, ctx->stream>>>((cplx*)d_src_io, (cplx*)d_dst_out, n, X, dof, 0, colour_period, nparts, which);
   GLB_LAUNCH_CHECK();
   return GLB_OK;
+}
+
+int glb_mg_partition(glb_context* ctx, int X, int Y, int dof, int colour_period, void* d_even_io, void* d_odd_out) {
+  return partition_launch(ctx, X, Y, dof, colour_period, 2, 1, d_even_io, d_odd_out, "glb_mg_partition");
+}
+
+int glb_mg_partition_corner(glb_context* ctx, int X, int Y, int dof, int colour_period, int which, void* d_src_io,
+                            void* d_dst_out) {
+  return partition_launch(ctx, X, Y, dof, colour_period, 4, which, d_src_io, d_dst_out, "glb_mg_partition_corner");
 }
 
 int glb_mg_galerkin(glb_mg_transfer* t, glb_operator* fine, int ignore_shifts, glb_operator** coarse) {
@@ -347,7 +381,13 @@ int glb_mg_galerkin(glb_mg_transfer* t, glb_operator* fine, int ignore_shifts, g
   fs.use_dof = !ignore_shifts && (fine->dof_shift[0] != 0.0 || fine->dof_shift[1] != 0.0);
   const int grid = blas_grid(ctx, per, 128, 1);
   mg_galerkin_kernel<<<grid, 128, 0, ctx->stream>>>(mg_args(t), fs, cl, hp);
-  GLB_LAUNCH_CHECK();
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    cudaFree(cl);
+    cudaFree(hp);
+    return fail(GLB_ERR_CUDA, std::string("glb_mg_galerkin: ") + cudaGetErrorString(e));
+  }
   int rc = op_adopt_stencil2d(ctx, t->Xc, t->Yc, nv, cl, hp, coarse);
   if (rc) {
     cudaFree(cl);

@@ -535,11 +535,12 @@ void glbx_mg_destroy(glbx_mg* h) {
 // :1066-1093 gives the same matrices).
 //   nvec[l]   total null vectors of refinement l (after the partition);  bstrat: 0 none, 1 even/odd
 //   null_gen  minv_inverter;  tol[l], max_iter[l] per refinement;  seed of the std::mt19937 behind the sources
+//   do_free   free-field null vectors (null_generate_free_dev) instead of smoothed random ones
 //   null_prec null_precond_strategy: 0 plain solve, 1 even/odd (top/bottom below the top level), 2 normal equations
 glbx_mg* glbx_mg_setup(glb_operator* fine, int X, int Y, int n_refine, const int* block, const int* nvec, int bstrat,
                        double null_mass, int null_gen, const double* tol, const int* max_iter, int restart_freq,
                        int bicgstab_l, int do_ortho_eo, int do_global_ortho_conj, unsigned seed, int verbosity,
-                       int null_prec) {
+                       int null_prec, int do_free) {
   if (!fine || n_refine < 1 || !block || !nvec || !tol || !max_iter) return 0;
   glbx_mg* h = new glbx_mg();
   double mass_shift[2] = {0.0, 0.0};
@@ -585,7 +586,7 @@ glbx_mg* glbx_mg_setup(glb_operator* fine, int X, int Y, int n_refine, const int
     nv.null_bicgstab_l = bicgstab_l;
     nv.null_mass = null_mass;
     nv.bstrat = (blocking_strategy)bstrat;
-    nv.null_partitions = (bstrat == BLOCK_EO) ? 2 : 1;  // :412-427
+    nv.null_partitions = (bstrat == BLOCK_EO) ? 2 : (bstrat == BLOCK_CORNER) ? 4 : 1;  // :412-427
     nv.do_ortho_eo = do_ortho_eo != 0;
     nv.do_global_ortho_conj = do_global_ortho_conj != 0;
     nv.quiet = verbosity == 0;
@@ -607,7 +608,10 @@ glbx_mg* glbx_mg_setup(glb_operator* fine, int X, int Y, int n_refine, const int
     for (int n = 0; n < n_refine; n++) {
       verb.verb_prefix = "[L" + std::to_string(h->mg.curr_level + 1) + "_NULLVEC]: ";
       clk::time_point t0 = clk::now();
-      null_generate_random_smooth_dev(&h->mg, &nv, &verb, &generator);
+      if (do_free)  // :792-795
+        null_generate_free_dev(&h->mg, &nv, false, 0);
+      else
+        null_generate_random_smooth_dev(&h->mg, &nv, &verb, &generator);
       GLBX(glb_synchronize(ctx));
       clk::time_point t1 = clk::now();
       block_orthonormalize_dev(&h->mg);

@@ -18,7 +18,7 @@
 enum blocking_strategy {
   BLOCK_NONE = 0,    // block fully
   BLOCK_EO = 1,      // even/odd
-  BLOCK_CORNER = 2,  // corners        (not on the accelerated path)
+  BLOCK_CORNER = 2,  // corners
   BLOCK_TOPO = 3     // taste singlet  (not on the accelerated path)
 };
 
@@ -64,11 +64,17 @@ struct null_vector_params {
 };
 
 // null_gen.cpp:13-103: partition null vector `num_null_vec` of the top level (BLOCK_EO: its odd sites move to vector
-// num_null_vec + n_vectors[0]/2).  BLOCK_NONE: nothing.  Other strategies throw.
+// num_null_vec + n_vectors[0]/2; BLOCK_CORNER: the three odd corners move to num_null_vec + k*n_vectors[0]/4).
+// BLOCK_NONE: nothing.  BLOCK_TOPO throws.
 void null_partition_staggered_dev(mg_operator_struct_complex_dev* mgstruct, int num_null_vec, blocking_strategy bstrat);
 
 // null_gen.cpp:106-160: the same below the top level (BLOCK_EO: the upper half of the colour index moves).
 void null_partition_coarse_dev(mg_operator_struct_complex_dev* mgstruct, int num_null_vec, blocking_strategy bstrat);
+
+// null_gen.cpp:162-191: free-field null vectors -- the constant vector (times the HOST array gauge_trans on the top
+// level when do_gauge_transform), partitioned and normalised part by part.
+void null_generate_free_dev(mg_operator_struct_complex_dev* mgstruct, null_vector_params* nvec_params,
+                            bool do_gauge_transform = false, std::complex<double>* gauge_trans = 0);
 
 // null_gen.cpp:193-400: for each of n_vectors[curr_level]/null_partitions vectors draw a gaussian x0, orthogonalise it
 // against the vectors found so far, solve A x = -A x0 from a zero guess with `null_gen` on stencils[curr_level]

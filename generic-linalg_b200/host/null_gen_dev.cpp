@@ -84,17 +84,23 @@ struct StencilView {
 void partition(mg_operator_struct_complex_dev* mg, int num_null_vec, blocking_strategy bstrat, bool by_colour) {
   const Level L = level_of(mg);
   const int lvl = mg->curr_level;
+  // null_gen.cpp:114: below the top level the colour index is taken modulo n_vectors[curr_level] (the number of
+  // vectors being built on this level, not the dofs per site of this level -- kept as the reference has it)
+  const int period = by_colour ? mg->n_vectors[lvl] : 0;
+  zcplx** null = mg->null_vectors[lvl];
   switch (bstrat) {
     case BLOCK_NONE:
       return;
     case BLOCK_EO:
-      // null_gen.cpp:114: below the top level the colour index is taken modulo n_vectors[curr_level] (the number
-      // of vectors being built on this level, not the dofs per site of this level -- kept as the reference has it)
-      GLBX(glb_mg_partition(L.ctx, L.X, L.Y, L.dof, by_colour ? mg->n_vectors[lvl] : 0, mg->null_vectors[lvl][num_null_vec],
-                            mg->null_vectors[lvl][num_null_vec + mg->n_vectors[lvl] / 2]));
+      GLBX(glb_mg_partition(L.ctx, L.X, L.Y, L.dof, period, null[num_null_vec], null[num_null_vec + mg->n_vectors[lvl] / 2]));
+      return;
+    case BLOCK_CORNER:  // null_gen.cpp:74-88, :132-152: class k goes to vector num_null_vec + k*n_vectors/4
+      for (int k = 1; k < 4; k++)
+        GLBX(glb_mg_partition_corner(L.ctx, L.X, L.Y, L.dof, period, k, null[num_null_vec],
+                                     null[num_null_vec + k * mg->n_vectors[lvl] / 4]));
       return;
     default:
-      throw Error("null_partition: only BLOCK_NONE and BLOCK_EO are on the accelerated path");
+      throw Error("null_partition: BLOCK_TOPO is not on the accelerated path (it needs the symmetric-shift operators)");
   }
 }
 
@@ -109,12 +115,39 @@ void null_partition_coarse_dev(mg_operator_struct_complex_dev* mg, int num_null_
   partition(mg, num_null_vec, bstrat == BLOCK_TOPO ? BLOCK_EO : bstrat, true);
 }
 
+// null_gen.cpp:162-191: one constant vector (times a gauge transformation on the top level), partitioned and
+// normalised part by part.  gauge_trans is a HOST array of the top-level lattice size.
+void null_generate_free_dev(mg_operator_struct_complex_dev* mg, null_vector_params* nv, bool do_gauge_transform,
+                            std::complex<double>* gauge_trans) {
+  const Level L = level_of(mg);
+  const int lvl = mg->curr_level;
+  if (nv->null_partitions < 1 || (int)nv->n_null_vectors.size() <= lvl)
+    throw Error("null_generate_free_dev: null_partitions / n_null_vectors are not filled in");
+  std::vector<zcplx> host(L.size);
+  for (int i = 0; i < L.size; i++) {
+    host[i] = 1;
+    if (do_gauge_transform && lvl == 0) host[i] *= gauge_trans[i];
+  }
+  zcplx** null = mg->null_vectors[lvl];
+  Blas<zcplx> B = {L.ctx, (size_t)L.size};
+  GLBX(glb_vec_upload(L.ctx, GLB_COMPLEX, B.n, null[0], host.data()));
+  if (lvl == 0)
+    null_partition_staggered_dev(mg, 0, nv->bstrat);
+  else
+    null_partition_coarse_dev(mg, 0, nv->bstrat);
+  for (int k = 0; k < nv->null_partitions; k++) normalize_dev(B, null[k * nv->n_null_vectors[lvl]]);
+}
+
 void null_generate_random_smooth_dev(mg_operator_struct_complex_dev* mg, null_vector_params* nv,
                                      inversion_verbose_struct* verb, std::mt19937* generator) {
   const Level L = level_of(mg);
   const int lvl = mg->curr_level;
   if (nv->null_partitions < 1 || mg->n_vectors[lvl] % nv->null_partitions != 0)
     throw Error("null_generate_random_smooth_dev: n_vectors must be a multiple of null_partitions");
+  if ((int)nv->n_null_vectors.size() <= lvl || (int)nv->null_precisions.size() <= lvl || (int)nv->null_max_iters.size() <= lvl)
+    throw Error("null_generate_random_smooth_dev: n_null_vectors / null_precisions / null_max_iters need one entry per level");
+  if (nv->null_prec != NULL_PRECOND_NONE && nv->null_prec != NULL_PRECOND_EO && nv->null_prec != NULL_PRECOND_NORMAL)
+    throw Error("null_generate_random_smooth_dev: unknown null_precond_strategy");
   glb_operator* op = mg->stencils[lvl];
   zcplx** null = mg->null_vectors[lvl];
   const int n_gen = mg->n_vectors[lvl] / nv->null_partitions;

@@ -313,6 +313,11 @@ int glb_mg_block_orthonormalize(glb_context* ctx, int Xf, int Yf, int dof_f, int
  * null_partition_staggered, null_gen.cpp:26-35).  colour_period = m > 0: elements with (index % m) >= m/2
  * (null_partition_coarse, null_gen.cpp:109-126, where m = n_vectors[curr_level]). */
 int glb_mg_partition(glb_context* ctx, int X, int Y, int dof, int colour_period, void* d_even_io, void* d_odd_out);
+/* BLOCK_CORNER partition (null_gen.cpp:74-88, :132-152): the elements of corner class `which` (1..3) move to dst_out
+ * and are zeroed in src_io.  colour_period = 0: sites by (x odd, y odd) = 1, (x odd, y even) = 2, (x even, y odd) = 3;
+ * colour_period = p > 0: index % p in [p/4, 2p/4) = 1, [2p/4, 3p/4) = 2, [3p/4, p) = 3 (integer divisions). */
+int glb_mg_partition_corner(glb_context* ctx, int X, int Y, int dof, int colour_period, int which, void* d_src_io,
+                            void* d_dst_out);
 /* Galerkin coarse operator P^dag A P of a five-point stencil2d fine operator (what generate_coarse_from_fine_stencil,
  * mg_complex.cpp:827-1026, assembles by probing with 1 + 8 applies per coarse colour): a new stencil2d operator on
  * the coarse lattice of the transfer, nc = nvec, all three coarse shifts zero.  ignore_shifts = 0: the fine shifts

@@ -253,7 +253,7 @@ class RefMg:
         vp, ci, cd = C.c_void_p, C.c_int, C.c_double
         for name, res, args in (("refmg_create2", vp, [ci, ci, vp, cd, ci, vp, vp, vp, ci]),
                                 ("refmg_setup", vp, [ci, ci, vp, cd, ci, vp, vp, ci, cd, ci, vp, vp, ci, ci, ci, ci,
-                                                     C.c_uint, ci, ci]),
+                                                     C.c_uint, ci, ci, ci]),
                                 ("refmg_null_counts", None, [vp, vp]),
                                 ("refmg_level_dims", None, [vp, ci, vp, vp, vp]),
                                 ("refmg_get_null", None, [vp, ci, ci, vp]),
@@ -270,11 +270,12 @@ class RefMg:
     @classmethod
     def setup(cls, orc, X, Y, links, mass, blocks, nvecs, bstrat=1, null_mass=1e-2, null_gen="BICGSTAB", tol=5e-5,
               max_iter=500, restart_freq=0, bicgstab_l=-1, do_ortho_eo=False, do_global_ortho_conj=False, seed=1337,
-              verbosity=0, null_prec=0):
+              verbosity=0, null_prec=0, do_free=False):
         """The reference driver's complete set-up (aa_mg_square_staggered_u1.cpp:716-1143; oracle/ref_mg_shim.cpp
         refmg_setup): null vectors from null_generate_random_smooth with a std::mt19937(seed), block_orthonormalize,
         generate_coarse_from_fine_stencil(ignore_shifts=true) with the shift copied down.  nvecs[l] = total vectors
-        of refinement l (after the partition); bstrat 0 = BLOCK_NONE, 1 = BLOCK_EO; null_prec 0 = none, 1 = even/odd
+        of refinement l (after the partition); bstrat 0 = BLOCK_NONE, 1 = BLOCK_EO, 2 = BLOCK_CORNER; do_free: null_generate_free instead of
+        the smoothing solves; null_prec 0 = none, 1 = even/odd
         (top/bottom below the top level), 2 = normal equations (null_gen.h:24-29)."""
         self = cls.__new__(cls)
         self._bind(orc)
@@ -287,7 +288,8 @@ class RefMg:
         self._keep = (blocks_a, nvecs_a, tol_a, it_a)
         self.h = self.L.refmg_setup(X, Y, _ptr(self.links), mass, self.n_refine, _ptr(blocks_a), _ptr(nvecs_a), bstrat,
                                     null_mass, self.SMOOTH[null_gen], _ptr(tol_a), _ptr(it_a), restart_freq, bicgstab_l,
-                                    int(do_ortho_eo), int(do_global_ortho_conj), seed, verbosity, null_prec)
+                                    int(do_ortho_eo), int(do_global_ortho_conj), seed, verbosity, null_prec,
+                                    int(do_free))
         return self
 
     def null_counts(self):

@@ -180,10 +180,12 @@ void* refmg_create(int X, int Y, const double* links, double mass, int n_refine,
 //   null_gen      minv_inverter of the smoothing solve; tol[l], max_iter[l] per refinement
 //   restart_freq  > 0: restarted solver;  bicgstab_l: l of BiCGStab-l
 //   seed          std::mt19937 seed of the gaussian sources
+//   do_free       free-field null vectors (null_generate_free, null_gen.cpp:162) instead of smoothed random ones
 //   null_prec     null_precond_strategy (null_gen.h:24-29): 0 none, 1 even/odd (top/bottom below the top level), 2 normal
 void* refmg_setup(int X, int Y, const double* links, double mass, int n_refine, const int* block, const int* nvec,
                   int bstrat, double null_mass, int null_gen, const double* tol, const int* max_iter, int restart_freq,
-                  int bicgstab_l, int do_ortho_eo, int do_global_ortho_conj, unsigned seed, int verbosity, int null_prec) {
+                  int bicgstab_l, int do_ortho_eo, int do_global_ortho_conj, unsigned seed, int verbosity, int null_prec,
+                  int do_free) {
   RefMg* h = make_struct(X, Y, links, mass, n_refine, block, nvec, 0);
   mg_operator_struct_complex& mg = h->mg;
   null_vector_params nv;
@@ -195,7 +197,7 @@ void* refmg_setup(int X, int Y, const double* links, double mass, int n_refine, 
   nv.null_bicgstab_l = bicgstab_l;
   nv.null_mass = null_mass;
   nv.bstrat = (blocking_strategy)bstrat;
-  nv.null_partitions = (bstrat == BLOCK_EO) ? 2 : 1;  // aa_mg_square_staggered_u1.cpp:412-427
+  nv.null_partitions = (bstrat == BLOCK_EO) ? 2 : (bstrat == BLOCK_CORNER) ? 4 : 1;  // aa_mg_square_staggered_u1.cpp:412-427
   nv.do_global_ortho_conj = do_global_ortho_conj != 0;
   nv.do_ortho_eo = do_ortho_eo != 0;
   for (int i = 0; i < n_refine; i++) {
@@ -220,7 +222,10 @@ void* refmg_setup(int X, int Y, const double* links, double mass, int n_refine, 
   if (null_prec == NULL_PRECOND_EO) mallopt(M_PERTURB, 0xFF);
   for (int n = 0; n < n_refine; n++) {
     verb.verb_prefix = "[L" + to_string(mg.curr_level + 1) + "_NULLVEC]: ";
-    null_generate_random_smooth(&mg, &nv, &verb, &generator);
+    if (do_free)  // aa_mg_square_staggered_u1.cpp:792-795
+      null_generate_free(&mg, &nv, false, 0);
+    else
+      null_generate_random_smooth(&mg, &nv, &verb, &generator);
     block_orthonormalize(&mg);
     if (n != n_refine - 1) {
       generate_coarse_from_fine_stencil(mg.stencils[mg.curr_level + 1], mg.stencils[mg.curr_level], &mg, true);

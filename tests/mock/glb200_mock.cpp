@@ -526,6 +526,29 @@ int glb_mg_partition(glb_context*, int X, int Y, int dof, int colour_period, voi
   }
   return GLB_OK;
 }
+// null_gen.cpp:74-88 (colour_period = 0) / :132-152 (colour_period = n_vectors[curr_level])
+int glb_mg_partition_corner(glb_context*, int X, int Y, int dof, int colour_period, int which, void* src_io, void* dst_out) {
+  g_calls++;
+  cplx* e = (cplx*)src_io; cplx* o = (cplx*)dst_out;
+  const size_t n = (size_t)X * Y * dof;
+  for (size_t i = 0; i < n; i++) {
+    int cls = 0;
+    if (colour_period > 0) {
+      const int c = (int)(i % colour_period), p = colour_period;
+      if (c >= p / 4 && c < 2 * p / 4) cls = 1;
+      else if (c >= 2 * p / 4 && c < 3 * p / 4) cls = 2;
+      else if (c >= 3 * p / 4) cls = 3;
+    } else {
+      const size_t site = i / dof;
+      const int x = (int)(site % X), y = (int)(site / X);
+      if (x % 2 == 1 && y % 2 == 0) cls = 2;
+      else if (x % 2 == 0 && y % 2 == 1) cls = 3;
+      else if (x % 2 == 1 && y % 2 == 1) cls = 1;
+    }
+    if (cls == which) { o[i] = e[i]; e[i] = 0.0; }
+  }
+  return GLB_OK;
+}
 // P^dag A P summed directly (the device kernel's formulation of mg_complex.cpp:827-1026)
 int glb_mg_galerkin(glb_mg_transfer* t, glb_operator* fine, int ignore_shifts, glb_operator** coarse) {
   g_calls++;

@@ -16,6 +16,8 @@ import subprocess
 import sys
 import traceback
 
+import pytest
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 for p in (os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tools"), ROOT):
@@ -81,6 +83,8 @@ def main():
             try:
                 fn(**kw)
                 print("PASS", name, c)
+            except pytest.skip.Exception as e:     # e.g. argument-error tests: the mock does no argument checking
+                print("SKIP", name, c, str(e)[:120])
             except Exception as e:
                 traceback.print_exc()
                 print("FAIL", name, c, repr(e)[:200])

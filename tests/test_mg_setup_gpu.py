@@ -122,6 +122,65 @@ def test_partition_exact(ctx, X, Y, dof, period):
     assert np.array_equal(b.download(), np.where(odd, v, tgt))
 
 
+@pytest.mark.parametrize("X,Y,dof,period", [(16, 16, 1, 0), (12, 20, 2, 0), (8, 8, 8, 8), (8, 8, 4, 8), (6, 10, 6, 6)])
+def test_partition_corner_exact(ctx, X, Y, dof, period):
+    """BLOCK_CORNER: the three moves of null_gen.cpp:74-88 (sites) / :132-152 (colour quarters, integer bounds)"""
+    rg = np.random.default_rng(X + dof)
+    n = X * Y * dof
+    v = rg.standard_normal(n) + 1j * rg.standard_normal(n)
+    idx = np.arange(n)
+    if period:
+        c, p = idx % period, period
+        cls = np.where((c >= p // 4) & (c < 2 * p // 4), 1, np.where((c >= 2 * p // 4) & (c < 3 * p // 4), 2,
+                                                                    np.where(c >= 3 * p // 4, 3, 0)))
+    else:
+        site = idx // dof
+        xo, yo = (site % X) % 2, (site // X) % 2
+        cls = np.where((xo == 1) & (yo == 1), 1, np.where((xo == 1) & (yo == 0), 2, np.where((xo == 0) & (yo == 1), 3, 0)))
+    src = ctx.vector(n).upload(v)
+    for k in (1, 2, 3):
+        tgt = rg.standard_normal(n) + 1j * rg.standard_normal(n)
+        dst = ctx.vector(n).upload(tgt)
+        ctx.mg_partition_corner(X, Y, dof, period, k, src, dst)
+        assert np.array_equal(dst.download(), np.where(cls == k, v, tgt))
+    assert np.array_equal(src.download(), np.where(cls == 0, v, 0))
+
+
+def test_setup_argument_errors(ctx, glb):
+    """the set-up entry points refuse what they cannot do, with a message, and leave nothing behind"""
+    if ctx.cu.glb_device(ctx.h) < 0:
+        pytest.skip("argument checking is the CUDA library's; the CPU mock of the C ABI has none")
+    orc = oracle_py.load("ref")
+    L = 16
+    U = orc.rng(7).gauss_gauge_u1(L, L, 6.0)
+    fine, _ = _fine_stencil(ctx, orc, U, L, 0.05)
+    D = ctx.staggered(U, L, L, 0.05, 0)
+    vecs = [ctx.vector(L * L).upload(v) for v in _raw_vectors(orc, L, 1)]
+    with pytest.raises(glb.GlbError):                      # block size does not divide the lattice
+        glb.MgTransfer(ctx, L, L, 1, 3, 3, vecs)
+    tr = glb.MgTransfer(ctx, L, L, 1, 4, 4, vecs)
+    with pytest.raises(glb.GlbError):                      # the Galerkin kernel needs a stencil2d operator
+        tr.galerkin(D)
+    tr5 = glb.MgTransfer(ctx, 20, 20, 1, 4, 4, [ctx.vector(400).upload(np.ones(400)), ctx.vector(400).upload(np.ones(400))])
+    cl, hp, _ = __import__("mg_setup").staggered_stencil(orc.rng(3).gauss_gauge_u1(20, 20, 6.0), 20, 20, 0.0)
+    with pytest.raises(glb.GlbError):                      # 5 x 5 coarse sites: the reference's even/odd probing needs an even extent
+        tr5.galerkin(ctx.stencil2d(cl, hp, None, 20, 20, 1, shift=0.1))
+    with pytest.raises(glb.GlbError):                      # views exist on stencil2d operators only ...
+        D.view("M2MDEODOE")
+    with pytest.raises(glb.GlbError):                      # ... and not on other views
+        fine.view("NORMAL_EO").view("DAGGER_EO")
+    odd = ctx.stencil2d(np.zeros(64 * 9, complex), np.zeros(4 * 64 * 9, complex), None, 8, 8, 3, shift=0.1)
+    with pytest.raises(glb.GlbError):                      # top/bottom needs an even number of colours
+        odd.view("M2MDTBDBT")
+    with pytest.raises(glb.GlbError):
+        odd.prec_prepare(1, ctx.vector(192), ctx.vector(192))
+    with pytest.raises(glb.GlbError):                      # BLOCK_TOPO is refused (stderr carries the reason)
+        ctx.multigrid_setup(fine, L, L, [4], [4], bstrat=3, max_iter=2)
+    assert fine.get_shifts()[0] == complex(0.05)           # and the caller's shift is back
+    with pytest.raises(glb.GlbError):
+        ctx.mg_partition_corner(8, 8, 1, 0, 4, vecs[0], vecs[1])
+
+
 def _fine_stencil(ctx, orc, U, L, mass):
     import mg_setup
     cl0, hp0, sh0 = mg_setup.staggered_stencil(U, L, L, 0.0)
@@ -169,7 +228,10 @@ def test_setup_handle_outlives_its_fine_operator(ctx, glb):
                                                  # (t/b below the top level) system, and the normal equations
                                                  (64, [4], [8], dict(null_prec=1, null_gen="CG")),
                                                  (64, [4, 2], [4, 4], dict(null_prec=1)),
-                                                 (64, [4], [8], dict(null_prec=2, null_gen="CG", tol=1e-3))])
+                                                 (64, [4], [8], dict(null_prec=2, null_gen="CG", tol=1e-3)),
+                                                 # BLOCK_CORNER (four parts per smoothed vector), free-field vectors
+                                                 (64, [4], [8], dict(bstrat=2)),
+                                                 (32, [4], [2], dict(do_free=True))])
 def test_setup_defaults_hierarchy_and_solve(ctx, glb, L, blocks, nvecs, opts):
     """the driver's defaults (BiCGStab to 5e-5, at most 500 iterations, null mass 1e-2, BLOCK_EO): structural
     properties of the device-built hierarchy and the outer solve VPGCR(64) + V cycle next to the reference's own
@@ -195,8 +257,9 @@ def test_setup_defaults_hierarchy_and_solve(ctx, glb, L, blocks, nvecs, opts):
     # BLOCK_EO: the first half lives on even sites, the second half on odd sites
     idx = np.arange(L * L)
     even = ((idx % L + idx // L) % 2) == 0
-    for v in range(nvecs[0]):
-        assert np.all(vecs[v][~even if v < nvecs[0] // 2 else even] == 0)
+    if opts.get("bstrat", 1) == 1:
+        for v in range(nvecs[0]):
+            assert np.all(vecs[v][~even if v < nvecs[0] // 2 else even] == 0)
     # the level-1 operator is P^dag A P of the device's own vectors (numpy restatement checked against the
     # reference in tests/test_mg_setup_cpu.py), with the mass in the shift
     cl, hp, sh = mg.level_stencil(1)
