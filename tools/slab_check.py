@@ -16,6 +16,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 
 def main():
@@ -81,6 +82,48 @@ def main():
         want = orc.op("STENCIL", X, Y, Nc=nc, clover=cl, hopping=hp, two_link=two, shift=0.3, eo_shift=0.2j,
                       dof_shift=0.1).apply(v)
         check("apply STENCIL nc=4 two_link=%s" % (two is not None), np.array_equal(got, want))
+
+    # ---- partial applies, composite views and the prepare / reconstruct passes on slabs (reference
+    # library only).  The paired thread mapping keys on the GLOBAL row parity, so y0 matters here.
+    if orc.kind == "reference":
+        slc = slice(y0 * X * nc, (y0 + Yloc) * X * nc)
+        sop = ctx.stencil2d(cl, hp, None, X, Y, nc, shift=0.3)
+        oop = orc.op("STENCIL", X, Y, Nc=nc, clover=cl, hopping=hp, shift=0.3)
+        w = rc(V * nc)
+        dv, dw, out = ctx.vector(Yloc * X * nc).upload(v[slc]), ctx.vector(Yloc * X * nc).upload(w[slc]), ctx.vector(Yloc * X * nc)
+        for part in ("EO", "OE", "TB", "BT"):
+            sop.apply_part(part, out, dv)
+            check("stencil part %s" % part, np.array_equal(gather(out.download()), oop.apply_part(part, v)))
+        for view in ("M2MDEODOE", "M2MDTBDBT", "NORMAL_EO", "NORMAL_TB", "DAGGER_EO", "DAGGER_TB"):
+            vo = sop.view(view)
+            vo.apply(out, dv)
+            want = orc.op("STENCIL", X, Y, Nc=nc, clover=cl, hopping=hp, shift=0.3, view=view).apply(v)
+            check("stencil view %s" % view, np.array_equal(gather(out.download()), want))
+            vo.destroy()
+        for tb in (0, 1):
+            sop.prec_prepare(tb, out, dv)
+            check("stencil prec_prepare tb=%d" % tb, np.array_equal(gather(out.download()), oracle_py.ref_stencil_prec(orc, oop, tb, v)))
+            sop.prec_reconstruct(tb, out, dv, dw)
+            check("stencil prec_reconstruct tb=%d" % tb,
+                  np.array_equal(gather(out.download()), oracle_py.ref_stencil_prec(orc, oop, tb, v, w)))
+        # e/o-preconditioned solve of D x = b through the nc = 1 stencil of the staggered operator
+        import mg_setup
+        cl0, hp0, _ = mg_setup.staggered_stencil(U, X, Y, 0.0)
+        st = ctx.stencil2d(cl0, hp0, None, X, Y, 1, shift=0.1)
+        ost = orc.op("STENCIL_FROM_STAG", X, Y, mass=0.1, links=U)
+        ostm = orc.op("STENCIL_FROM_STAG", X, Y, mass=0.1, links=U, view="M2MDEODOE")
+        db, be, xe, xf = (ctx.vector(Yloc * X) for _ in range(4))
+        db.upload(b[sl])
+        st.prec_prepare(0, be, db)
+        xe.zero()
+        stm = st.view("M2MDEODOE")
+        info = ctx.solve("CG", stm, xe, be, max_iter=5000, eps=1e-10)
+        st.prec_reconstruct(0, xf, xe, db)
+        _, want = orc.solve("CG", ostm, oracle_py.ref_stencil_prec(orc, ost, 0, b), max_iter=5000, eps=1e-10)
+        xg = gather(xf.download())
+        rr = np.linalg.norm(orc.op("STAG_U1", X, Y, mass=0.1, links=U).apply(xg) - b) / np.linalg.norm(b)
+        check("solve e/o-preconditioned CG through the stencil", abs(info["iter"] - want["iter"]) <= max(1, round(0.02 * want["iter"]))
+              and rr < 1e-8, "iter %d (oracle %d) true rel res %.2e" % (info["iter"], want["iter"], rr))
 
     # ---- reductions
     xv = ctx.vector(Yloc * X).upload(b[sl])
