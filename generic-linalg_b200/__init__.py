@@ -442,9 +442,16 @@ class Multigrid:
             X, Y, dof = X // self.blocks[l], Y // self.blocks[l], self.nvecs[l]
         return X, Y, dof
 
+    def _local_dims(self, level):
+        """(X, Yloc, dof) of this rank's slab of level `level` (the whole lattice on one rank)"""
+        X, Y, dof = self.level_dims(level)
+        y0, yloc = self.ctx.slab_bounds(Y)
+        return X, yloc, dof
+
     def level_stencil(self, level):
-        """(clover, hopping, shifts) of level `level` of a hierarchy built by setup()"""
-        X, Y, nc = self.level_dims(level)
+        """(clover, hopping, shifts) of level `level` of a hierarchy built by setup(); on y-slabs this rank's rows of
+        every plane"""
+        X, Y, nc = self._local_dims(level)
         h = self.ctx.ho.glbx_mg_level_op(self.h, level)
         cl = np.empty(X * Y * nc * nc, dtype=np.complex128)
         hp = np.empty(4 * X * Y * nc * nc, dtype=np.complex128)
@@ -454,8 +461,8 @@ class Multigrid:
         return cl, hp, tuple(complex(v[0], v[1]) for v in a)
 
     def null_vector(self, level, v):
-        """block-orthonormalised null vector v of refinement `level` (downloaded)"""
-        X, Y, dof = self.level_dims(level)
+        """block-orthonormalised null vector v of refinement `level` (downloaded; on y-slabs this rank's rows)"""
+        X, Y, dof = self._local_dims(level)
         out = np.empty(X * Y * dof, dtype=np.complex128)
         p = self.ctx.ho.glbx_mg_null_vector(self.h, level, v)
         if not p:

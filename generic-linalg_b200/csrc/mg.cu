@@ -21,12 +21,18 @@ struct glb_mg_transfer {
   int Xf = 0, Yf = 0, dof_f = 1, bx = 1, by = 1, nvec = 1;
   int Xc = 0, Yc = 0;
   glb::cplx* null = nullptr;  // [fine dof][v]
+  // y-slabs: the neighbours' boundary rows of the null vectors in the same [dof][v] layout (one row each), filled by
+  // glb_mg_galerkin -- the only consumer: hops across the slab edge
+  glb::cplx* null_lo = nullptr;
+  glb::cplx* null_hi = nullptr;
 };
 
 namespace glb {
 
 struct MgArgs {
   const cplx* null;
+  const cplx* null_lo;  // row -1 / row Yf of the slab (nullptr on a single rank: periodic wrap inside the array)
+  const cplx* null_hi;
   int Xf, Yf, dof_f, bx, by, nvec, Xc, Yc;
 };
 
@@ -124,7 +130,8 @@ __global__ void mg_partition_kernel(cplx* __restrict__ src_io, cplx* __restrict_
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     int cls;
     if (colour_period > 0) {
-      const int c = (int)(i % colour_period), p = colour_period;
+      // the reference takes the GLOBAL index modulo the period (null_gen.cpp:114); y0 rows precede this slab
+      const int c = (int)((i + (size_t)y0 * X * dof) % colour_period), p = colour_period;
       if (nparts == 2)
         cls = (c >= p / 2) ? 1 : 0;
       else
@@ -184,9 +191,16 @@ __global__ void __launch_bounds__(128) mg_galerkin_kernel(const MgArgs a, const 
           if (fs.use_dof) row = fadd(row, fmul(r < df / 2 ? fs.dof_shift : fneg(fs.dof_shift), self));
           acc_c = fadd(acc_c, fcmul(ci, row));
           for (int d = 0; d < 4; d++) {
-            const size_t g = ((size_t)yn[d] * a.Xf + xn[d]) * df;
+            // the neighbour's null-vector entries: inside the slab, or (y-slabs) in the neighbour rank's boundary row
+            const cplx* nb;
+            if (a.null_lo && d == 1 && y + 1 == a.Yf)
+              nb = a.null_hi + (size_t)xn[d] * df * nv;
+            else if (a.null_lo && d == 3 && y == 0)
+              nb = a.null_lo + (size_t)xn[d] * df * nv;
+            else
+              nb = a.null + ((size_t)yn[d] * a.Xf + xn[d]) * df * nv;
             cplx h = mk(0.0, 0.0);
-            for (int c = 0; c < df; c++) h = fadd(h, fmul(fs.hopping[c + df * f + d * df * Lf], a.null[(g + c) * nv + j]));
+            for (int c = 0; c < df; c++) h = fadd(h, fmul(fs.hopping[c + df * f + d * df * Lf], nb[(size_t)c * nv + j]));
             if (inside[d])
               acc_c = fadd(acc_c, fcmul(ci, h));
             else
@@ -202,6 +216,16 @@ __global__ void __launch_bounds__(128) mg_galerkin_kernel(const MgArgs a, const 
   }
 }
 
+// y-slabs: boundary rows of null vector v out of / into the [dof][v] layout (row = X*dof_f consecutive fine dofs)
+__global__ void mg_row_gather_kernel(cplx* __restrict__ row_out, const cplx* __restrict__ null_row, size_t rowlen, int nvec, int v) {
+  for (size_t f = (size_t)blockIdx.x * blockDim.x + threadIdx.x; f < rowlen; f += (size_t)gridDim.x * blockDim.x)
+    row_out[f] = null_row[f * nvec + v];
+}
+__global__ void mg_row_scatter_kernel(cplx* __restrict__ null_row, const cplx* __restrict__ row_in, size_t rowlen, int nvec, int v) {
+  for (size_t f = (size_t)blockIdx.x * blockDim.x + threadIdx.x; f < rowlen; f += (size_t)gridDim.x * blockDim.x)
+    null_row[f * nvec + v] = row_in[f];
+}
+
 // host arrays null_vectors[v][f] -> device null[f*nvec + v]
 __global__ void mg_interleave_kernel(cplx* __restrict__ dst, const cplx* __restrict__ src, size_t nf, int nvec, int v) {
   for (size_t f = (size_t)blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += (size_t)gridDim.x * blockDim.x)
@@ -215,6 +239,8 @@ using namespace glb;
 static MgArgs mg_args(const glb_mg_transfer* t) {
   MgArgs a;
   a.null = t->null;
+  a.null_lo = t->null_lo;
+  a.null_hi = t->null_hi;
   a.Xf = t->Xf;
   a.Yf = t->Yf;
   a.dof_f = t->dof_f;
@@ -338,9 +364,11 @@ static int partition_launch(glb_context* ctx, int X, int Y, int dof, int colour_
   if (X < 1 || Y < 1 || dof < 1 || colour_period < 0 || which < 1 || which >= nparts)
     return fail(GLB_ERR_ARG, std::string(who) + ": bad extents or class");
   if (d_src_io == d_dst_out) return fail(GLB_ERR_ARG, std::string(who) + ": source and target must differ");
-  const size_t n = (size_t)X * Y * dof;
+  int y0 = 0, Yloc = Y;  // Y is the GLOBAL extent; on y-slabs the vectors hold this rank's rows
+  if (glb_slab_bounds(ctx, Y, &y0, &Yloc) != GLB_OK) return GLB_ERR_ARG;
+  const size_t n = (size_t)X * Yloc * dof;
   const int grid = blas_grid(ctx, n, 256, 1);
-  mg_partition_kernel<<<grid, 256, 0, ctx->stream>>>((cplx*)d_src_io, (cplx*)d_dst_out, n, X, dof, 0, colour_period, nparts, which);
+  mg_partition_kernel<<<grid, 256, 0, ctx->stream>>>((cplx*)d_src_io, (cplx*)d_dst_out, n, X, dof, y0, colour_period, nparts, which);
   GLB_LAUNCH_CHECK();
   return GLB_OK;
 }
@@ -359,10 +387,38 @@ int glb_mg_galerkin(glb_mg_transfer* t, glb_operator* fine, int ignore_shifts, g
   glb_context* ctx = t->ctx;
   if (fine->kind != OPK_STENCIL || fine->has_two)
     return fail(GLB_ERR_ARG, "glb_mg_galerkin: the fine operator must be a five-point stencil2d operator");
-  if (fine->X != t->Xf || fine->Yloc != t->Yf || fine->nc != t->dof_f || ctx->nranks != 1)
-    return fail(GLB_ERR_ARG, "glb_mg_galerkin: transfer and fine operator disagree (single rank only)");
-  if (t->Xc < 2 || t->Yc < 2 || (t->Xc & 1) || (t->Yc & 1))
+  if (fine->X != t->Xf || fine->Yloc != t->Yf || fine->nc != t->dof_f)
+    return fail(GLB_ERR_ARG, "glb_mg_galerkin: transfer and fine operator disagree (on y-slabs the transfer holds the local rows)");
+  if (fine->Y % t->by != 0 || fine->y0 % t->by != 0)
+    return fail(GLB_ERR_ARG, "glb_mg_galerkin: slab boundaries must coincide with block boundaries");
+  const int Yc_global = fine->Y / t->by;
+  if (t->Xc < 2 || Yc_global < 2 || (t->Xc & 1) || (Yc_global & 1))
     return fail(GLB_ERR_ARG, "glb_mg_galerkin: the coarse lattice needs an even number (>= 2) of sites per direction");
+  if (ctx->nranks > 1) {
+    // the neighbours' boundary rows of every null vector, through the fine operator's halo path (one row per side)
+    const size_t rowlen = (size_t)t->Xf * t->dof_f;
+    if (!t->null_lo) {
+      if (cudaMalloc(&t->null_lo, rowlen * t->nvec * sizeof(cplx)) != cudaSuccess ||
+          cudaMalloc(&t->null_hi, rowlen * t->nvec * sizeof(cplx)) != cudaSuccess)
+        return fail(GLB_ERR_CUDA, "glb_mg_galerkin: out of device memory");
+    }
+    if (!fine->send_lo || !fine->send_hi) return fail(GLB_ERR_STATE, "glb_mg_galerkin: the fine operator has no halo staging");
+    const int g1 = blas_grid(ctx, rowlen, 256, 1);
+    const cplx* first = t->null;
+    const cplx* last = t->null + (size_t)(t->Yf - 1) * rowlen * t->nvec;
+    for (int v = 0; v < t->nvec; v++) {
+      mg_row_gather_kernel<<<g1, 256, 0, ctx->stream>>>((cplx*)fine->send_lo, first, rowlen, t->nvec, v);
+      mg_row_gather_kernel<<<g1, 256, 0, ctx->stream>>>((cplx*)fine->send_hi, last, rowlen, t->nvec, v);
+      GLB_LAUNCH_CHECK();
+      int rc = halo_exchange_ptrs(fine, fine->send_lo, fine->send_hi, 1);
+      if (rc) return rc;
+      // ghost_lo holds ghost_depth rows, the nearest one (row -1) last; ghost_hi starts with row Yloc
+      const cplx* glo = (const cplx*)fine->ghost_lo + (size_t)(fine->ghost_depth - 1) * rowlen;
+      mg_row_scatter_kernel<<<g1, 256, 0, ctx->stream>>>(t->null_lo, glo, rowlen, t->nvec, v);
+      mg_row_scatter_kernel<<<g1, 256, 0, ctx->stream>>>(t->null_hi, (const cplx*)fine->ghost_hi, rowlen, t->nvec, v);
+      GLB_LAUNCH_CHECK();
+    }
+  }
   const int nv = t->nvec;
   const size_t per = (size_t)t->Xc * t->Yc * nv * nv;
   cplx *cl = nullptr, *hp = nullptr;
@@ -388,7 +444,7 @@ int glb_mg_galerkin(glb_mg_transfer* t, glb_operator* fine, int ignore_shifts, g
     cudaFree(hp);
     return fail(GLB_ERR_CUDA, std::string("glb_mg_galerkin: ") + cudaGetErrorString(e));
   }
-  int rc = op_adopt_stencil2d(ctx, t->Xc, t->Yc, nv, cl, hp, coarse);
+  int rc = op_adopt_stencil2d(ctx, t->Xc, Yc_global, t->Yc, nv, cl, hp, coarse);
   if (rc) {
     cudaFree(cl);
     cudaFree(hp);
@@ -400,6 +456,8 @@ int glb_mg_transfer_destroy(glb_mg_transfer* t) {
   if (!t) return GLB_OK;
   cudaStreamSynchronize(t->ctx->stream);
   cudaFree(t->null);
+  cudaFree(t->null_lo);
+  cudaFree(t->null_hi);
   delete t;
   return GLB_OK;
 }

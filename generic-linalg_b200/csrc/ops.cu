@@ -219,16 +219,27 @@ int glb_op_create_stencil2d(glb_context* ctx, const void* clover, const void* ho
 
 namespace glb {
 // a five-point stencil2d operator around matrices that already live on the device (ownership passes to the
-// operator): used by the Galerkin set-up in mg.cu.  Single rank only.
-int op_adopt_stencil2d(glb_context* ctx, int X, int Y, int nc, cplx* d_clover, cplx* d_hopping, glb_operator** out) {
-  if (ctx->nranks != 1) return fail(GLB_ERR_STATE, "device-side stencil set-up is single-rank");
+// operator): used by the Galerkin set-up in mg.cu.  Y is the GLOBAL extent; the arrays hold this rank's Yloc rows
+// in the slab-local plane layout of glb_op_create_stencil2d.
+int op_adopt_stencil2d(glb_context* ctx, int X, int Y, int Yloc, int nc, cplx* d_clover, cplx* d_hopping, glb_operator** out) {
   int rc = new_op(ctx, OPK_STENCIL, GLB_COMPLEX, X, Y, nc, out);
   if (rc) return rc;
   glb_operator* op = *out;
+  if (op->Yloc != Yloc) {
+    delete op;
+    *out = nullptr;
+    return fail(GLB_ERR_ARG, "device-side stencil set-up: the coarse slab does not match this rank's share of the coarse lattice");
+  }
   op->has_two = false;
+  rc = alloc_ghosts(op, 1);
+  if (rc) {
+    glb_op_destroy(op);   // clover / hopping are still null: the caller keeps its arrays
+    *out = nullptr;
+    return rc;
+  }
   op->clover = d_clover;
   op->hopping = d_hopping;
-  return alloc_ghosts(op, 1);
+  return GLB_OK;
 }
 }  // namespace glb
 
@@ -291,11 +302,11 @@ int glb_op_get_shifts(const glb_operator* op, double shift[2], double eo_shift[2
 }
 int glb_op_stencil_download(glb_operator* op, void* h_clover, void* h_hopping) {
   if (!op || op->kind != OPK_STENCIL) return fail(GLB_ERR_ARG, "glb_op_stencil_download: not a stencil2d operator");
-  if (op->ctx->nranks != 1) return fail(GLB_ERR_STATE, "glb_op_stencil_download: single rank only");
+  const glb_operator* src = op->base ? op->base : op;  // a view shows its base's matrices
   GLB_CUDA(cudaSetDevice(op->ctx->device));
-  const size_t per = (size_t)op->X * op->Y * op->nc * op->nc * sizeof(cplx);
-  if (h_clover) GLB_CUDA(cudaMemcpyAsync(h_clover, op->clover, per, cudaMemcpyDeviceToHost, op->ctx->stream));
-  if (h_hopping) GLB_CUDA(cudaMemcpyAsync(h_hopping, op->hopping, 4 * per, cudaMemcpyDeviceToHost, op->ctx->stream));
+  const size_t per = (size_t)op->X * op->Yloc * op->nc * op->nc * sizeof(cplx);  // this rank's rows of every plane
+  if (h_clover) GLB_CUDA(cudaMemcpyAsync(h_clover, src->clover, per, cudaMemcpyDeviceToHost, op->ctx->stream));
+  if (h_hopping) GLB_CUDA(cudaMemcpyAsync(h_hopping, src->hopping, 4 * per, cudaMemcpyDeviceToHost, op->ctx->stream));
   GLB_CUDA(cudaStreamSynchronize(op->ctx->stream));
   return GLB_OK;
 }

@@ -190,7 +190,7 @@ int launch_stencil2d_part(glb_operator* op, void* out, const void* in, int part,
 int launch_stencil2d_sign(glb_operator* op, void* out, const void* in, int mode);  // 0: epsilon(x), 1: sigma_3
 
 // ops.cu : stencil2d operator around device-resident matrices (ownership passes to the operator)
-int op_adopt_stencil2d(glb_context* ctx, int X, int Y, int nc, cplx* d_clover, cplx* d_hopping, glb_operator** out);
+int op_adopt_stencil2d(glb_context* ctx, int X, int Y, int Yloc, int nc, cplx* d_clover, cplx* d_hopping, glb_operator** out);
 
 // comm.cu : fills op->ghost_lo / ghost_hi from the neighbouring ranks' boundary rows of `in`
 int halo_exchange(glb_operator* op, const void* in, int nrows);

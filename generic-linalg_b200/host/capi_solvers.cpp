@@ -537,6 +537,7 @@ void glbx_mg_destroy(glbx_mg* h) {
 //   null_gen  minv_inverter;  tol[l], max_iter[l] per refinement;  seed of the std::mt19937 behind the sources
 //   do_free   free-field null vectors (null_generate_free_dev) instead of smoothed random ones
 //   null_prec null_precond_strategy: 0 plain solve, 1 even/odd (top/bottom below the top level), 2 normal equations
+// On y-slabs X, Y are the GLOBAL extents and `fine` the slab operator; every rank calls with the same arguments.
 glbx_mg* glbx_mg_setup(glb_operator* fine, int X, int Y, int n_refine, const int* block, const int* nvec, int bstrat,
                        double null_mass, int null_gen, const double* tol, const int* max_iter, int restart_freq,
                        int bicgstab_l, int do_ortho_eo, int do_global_ortho_conj, unsigned seed, int verbosity,
@@ -564,9 +565,10 @@ glbx_mg* glbx_mg_setup(glb_operator* fine, int X, int Y, int n_refine, const int
     h->null_dev.resize(n_refine);
     h->null_tab.resize(n_refine);
     for (int l = 0; l < n_refine; l++) {  // aa_mg_square_staggered_u1.cpp:607-616: allocated and zeroed
-      int lx, ly, ld;
+      int lx, ly, ld, ly0, lyloc;
       mg_level_dims(&h->mg, l, &lx, &ly, &ld);
-      const size_t sz = (size_t)lx * ly * ld;
+      GLBX(glb_slab_bounds(ctx, ly, &ly0, &lyloc));
+      const size_t sz = (size_t)lx * lyloc * ld;  // this rank's rows
       h->null_dev[l].assign(nvec[l], (zc*)0);
       for (int v = 0; v < nvec[l]; v++) {
         void* p = 0;

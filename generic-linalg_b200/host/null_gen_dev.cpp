@@ -31,7 +31,10 @@ namespace {
 
 struct Level {
   glb_context* ctx;
-  int X, Y, dof, size;
+  int X, Y, dof;   // the GLOBAL lattice of the level
+  int y0, Yloc;    // this rank's rows (y-slabs; the whole lattice on one rank)
+  int size;        // local vector length X*Yloc*dof
+  int global_size;
 };
 
 Level level_of(const mg_operator_struct_complex_dev* mg) {
@@ -42,7 +45,9 @@ Level level_of(const mg_operator_struct_complex_dev* mg) {
   Level L;
   L.ctx = glb_op_context(op);
   mg_level_dims(mg, mg->curr_level, &L.X, &L.Y, &L.dof);
-  L.size = L.X * L.Y * L.dof;
+  GLBX(glb_slab_bounds(L.ctx, L.Y, &L.y0, &L.Yloc));
+  L.size = L.X * L.Yloc * L.dof;
+  L.global_size = L.X * L.Y * L.dof;
   if ((size_t)L.size != glb_op_local_size(op)) throw Error("multigrid set-up: operator and level sizes disagree");
   return L;
 }
@@ -124,9 +129,10 @@ void null_generate_free_dev(mg_operator_struct_complex_dev* mg, null_vector_para
   if (nv->null_partitions < 1 || (int)nv->n_null_vectors.size() <= lvl)
     throw Error("null_generate_free_dev: null_partitions / n_null_vectors are not filled in");
   std::vector<zcplx> host(L.size);
+  const size_t slab_off = (size_t)L.y0 * L.X * L.dof;  // gauge_trans is a global array
   for (int i = 0; i < L.size; i++) {
     host[i] = 1;
-    if (do_gauge_transform && lvl == 0) host[i] *= gauge_trans[i];
+    if (do_gauge_transform && lvl == 0) host[i] *= gauge_trans[slab_off + i];
   }
   zcplx** null = mg->null_vectors[lvl];
   Blas<zcplx> B = {L.ctx, (size_t)L.size};
@@ -172,12 +178,15 @@ void null_generate_random_smooth_dev(mg_operator_struct_complex_dev* mg, null_ve
   zcplx* prep = (nv->null_prec != NULL_PRECOND_NONE) ? W.get() : 0;      // Arand_guess_prep (:213)
   zcplx* prec_soln = (nv->null_prec == NULL_PRECOND_EO) ? W.get() : 0;   // Arand_guess_prec_soln (:214)
   if (prec_soln) B.zero(prec_soln);  // the reference hands this new[]-ed array to the solver as its initial guess
-  std::vector<zcplx> host(L.size);
+  // the reference draws one global vector per source; every rank draws all of it and keeps its rows, so that the
+  // random numbers do not depend on the number of ranks
+  std::vector<zcplx> host(L.global_size);
+  const size_t slab_off = (size_t)L.y0 * L.X * L.dof;
 
   for (int i = 0; i < n_gen; i++) {
     // a gaussian source (:219), orthogonal to the vectors found so far (:222-238)
     gaussian_host(host, *generator);
-    GLBX(glb_vec_upload(L.ctx, GLB_COMPLEX, B.n, rand_guess, host.data()));
+    GLBX(glb_vec_upload(L.ctx, GLB_COMPLEX, B.n, rand_guess, host.data() + slab_off));
     for (int j = 0; j < i; j++) {
       for (int k = 0; k < n_split; k++) {
         zcplx* prev = null[j + k * stride];
@@ -268,7 +277,9 @@ void null_generate_random_smooth_dev(mg_operator_struct_complex_dev* mg, null_ve
 void block_orthonormalize_dev(mg_operator_struct_complex_dev* mg) {
   const Level L = level_of(mg);
   const int lvl = mg->curr_level;
-  GLBX(glb_mg_block_orthonormalize(L.ctx, L.X, L.Y, L.dof, mg->blocksize_x[lvl], mg->blocksize_y[lvl], mg->n_vectors[lvl],
+  if (L.Yloc % mg->blocksize_y[lvl] != 0 || L.y0 % mg->blocksize_y[lvl] != 0)
+    throw Error("block_orthonormalize_dev: slab boundaries must coincide with block boundaries");
+  GLBX(glb_mg_block_orthonormalize(L.ctx, L.X, L.Yloc, L.dof, mg->blocksize_x[lvl], mg->blocksize_y[lvl], mg->n_vectors[lvl],
                                    (void* const*)mg->null_vectors[lvl]));
 }
 
@@ -280,7 +291,7 @@ void generate_coarse_from_fine_stencil_dev(mg_operator_struct_complex_dev* mg, b
     glb_mg_transfer_destroy(mg->transfers[lvl]);
     mg->transfers[lvl] = 0;
   }
-  GLBX(glb_mg_transfer_create_dev(L.ctx, L.X, L.Y, L.dof, mg->blocksize_x[lvl], mg->blocksize_y[lvl], mg->n_vectors[lvl],
+  GLBX(glb_mg_transfer_create_dev(L.ctx, L.X, L.Yloc, L.dof, mg->blocksize_x[lvl], mg->blocksize_y[lvl], mg->n_vectors[lvl],
                                   (const void* const*)mg->null_vectors[lvl], &mg->transfers[lvl]));
   if (mg->stencils[lvl + 1]) {
     glb_op_destroy(mg->stencils[lvl + 1]);

@@ -150,8 +150,9 @@ int glb_op_set_mass(glb_operator* op, double mass);
  * generation and the final build (aa_mg_square_staggered_u1.cpp:757, :933, :996, :1086); NULL leaves one unchanged. */
 int glb_op_set_shifts(glb_operator* op, const double shift[2], const double eo_shift[2], const double dof_shift[2]);
 int glb_op_get_shifts(const glb_operator* op, double shift[2], double eo_shift[2], double dof_shift[2]);
-/* stencil2d operators, single rank: copy the matrices back to host arrays in the reference layout
- * (clover nc*nc*V, hopping 4*nc*nc*V complex; either may be NULL) -- what stencil_2d::clover / ::hopping hold */
+/* stencil2d operators: copy the matrices back to host arrays in the reference layout (clover nc*nc*V, hopping
+ * 4*nc*nc*V complex; either may be NULL) -- what stencil_2d::clover / ::hopping hold.  On y-slabs V is this rank's
+ * X*Yloc sites: every plane holds the local rows only. */
 int glb_op_stencil_download(glb_operator* op, void* h_clover, void* h_hopping);
 int glb_op_dtype(const glb_operator* op);
 size_t glb_op_local_size(const glb_operator* op);   /* elements held by this rank              */
@@ -308,7 +309,8 @@ int glb_mg_transfer_create_dev(glb_context* ctx, int Xf, int Yf, int dof_f, int 
 /* block_orthonormalize + block_normalize (mg_complex.cpp:191-370) in place on nvec device vectors */
 int glb_mg_block_orthonormalize(glb_context* ctx, int Xf, int Yf, int dof_f, int bx, int by, int nvec,
                                 void* const* d_null_vectors);
-/* BLOCK_EO partition of one null vector of X*Y*dof elements: its "odd" part moves to odd_out (only those elements
+/* BLOCK_EO partition of one null vector on the X x Y lattice (Y GLOBAL; on y-slabs the arrays hold this rank's rows,
+ * and site parity counts global rows) with dof values per site: its "odd" part moves to odd_out (only those elements
  * of odd_out are written) and is zeroed in even_io.  colour_period = 0: odd SITES (x+y odd; top level,
  * null_partition_staggered, null_gen.cpp:26-35).  colour_period = m > 0: elements with (index % m) >= m/2
  * (null_partition_coarse, null_gen.cpp:109-126, where m = n_vectors[curr_level]). */
@@ -322,8 +324,10 @@ int glb_mg_partition_corner(glb_context* ctx, int X, int Y, int dof, int colour_
  * mg_complex.cpp:827-1026, assembles by probing with 1 + 8 applies per coarse colour): a new stencil2d operator on
  * the coarse lattice of the transfer, nc = nvec, all three coarse shifts zero.  ignore_shifts = 0: the fine shifts
  * are folded into the coarse clover; != 0: they are left out (the caller then sets the coarse shifts with
- * glb_op_set_shifts, aa_mg_square_staggered_u1.cpp:1080-1093).  Single rank; the coarse lattice needs an even
- * number (>= 2) of sites per direction, as the reference's even/odd probing does. */
+ * glb_op_set_shifts, aa_mg_square_staggered_u1.cpp:1080-1093).  The coarse lattice needs an even number (>= 2) of
+ * sites per direction, as the reference's even/odd probing does.  On y-slabs (slab boundaries on block boundaries)
+ * the neighbours' boundary rows of the null vectors travel once through the fine operator's halo path and the
+ * result is the slab of the coarse operator. */
 int glb_mg_galerkin(glb_mg_transfer* t, glb_operator* fine, int ignore_shifts, glb_operator** coarse);
 size_t glb_mg_fine_size(const glb_mg_transfer* t);
 size_t glb_mg_coarse_size(const glb_mg_transfer* t);

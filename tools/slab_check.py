@@ -125,6 +125,55 @@ def main():
         check("solve e/o-preconditioned CG through the stencil", abs(info["iter"] - want["iter"]) <= max(1, round(0.02 * want["iter"]))
               and rr < 1e-8, "iter %d (oracle %d) true rel res %.2e" % (info["iter"], want["iter"], rr))
 
+    # ---- multigrid on slabs: set-up on the device (null vectors, block orthonormalisation, Galerkin product with the
+    # neighbours' boundary rows) and the V-cycle-preconditioned outer solve, next to the reference's own set-up + solve
+    if orc.kind == "reference" and Y % (8 * world) == 0:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from mg_common import quiet_stdout
+        import mg_setup
+        mass_mg = 0.05
+        cl0, hp0, _ = mg_setup.staggered_stencil(U, X, Y, 0.0)
+        fine = ctx.stencil2d(cl0, hp0, None, X, Y, 1, shift=mass_mg)
+
+        def rel(a, bb):
+            return float(np.linalg.norm(a - bb) / max(np.linalg.norm(bb), 1e-300))
+
+        def gather_planes(local, nplanes):
+            per = local.size // nplanes
+            return np.concatenate([gather(local[d * per:(d + 1) * per]) for d in range(nplanes)])
+
+        for blocks, nvecs in (([4], [4]), ([4, 2], [4, 4])):
+            tag = "blocks %s" % blocks
+            # (a) three smoothing iterations: the hierarchy itself can be compared (see tests/test_mg_setup_gpu.py)
+            kw = dict(seed=17, max_iter=3)
+            with quiet_stdout():
+                ref = oracle_py.RefMg.setup(orc, X, Y, U, mass_mg, blocks, nvecs, **kw)
+            mg = ctx.multigrid_setup(fine, X, Y, blocks, nvecs, **kw)
+            worst = max(rel(gather(mg.null_vector(0, v)), ref.null(0, v)) for v in range(nvecs[0]))
+            check("MG set-up on slabs, %s: top-level null vectors" % tag, worst < 1e-5, "max rel err %.1e" % worst)
+            cl, hp, sh = mg.level_stencil(1)
+            clr, hpr, shr = ref.stencil(1)
+            e1, e2 = rel(gather(cl), clr), rel(gather_planes(hp, 4), hpr)
+            check("MG set-up on slabs, %s: Galerkin coarse stencil" % tag, e1 < 1e-5 and e2 < 1e-5 and sh[0] == complex(mass_mg),
+                  "clover %.1e hopping %.1e" % (e1, e2))
+            check("MG set-up on slabs, %s: null-vector applies" % tag, mg.counts()["nullvectors"] == ref.null_counts())
+            mg.destroy()
+            # (b) the driver's defaults: outer VPGCR(64) + V cycle
+            with quiet_stdout():
+                ref = oracle_py.RefMg.setup(orc, X, Y, U, mass_mg, blocks, nvecs, seed=23)
+                ref.set_precond()
+                xo, want = ref.vpgcr(b, max_iter=1000, eps=5e-7, restart_freq=64)
+            mg = ctx.multigrid_setup(fine, X, Y, blocks, nvecs, seed=23)
+            mg.set()
+            x = ctx.vector(Yloc * X).zero()
+            got = mg.vpgcr(x, ctx.vector(Yloc * X).upload(b[sl]), max_iter=1000, eps=5e-7, restart_freq=64)
+            xg = gather(x.download())
+            rr = np.linalg.norm(orc.op("STAG_U1", X, Y, mass=mass_mg, links=U).apply(xg) - b) / np.linalg.norm(b)
+            check("MG solve on slabs, %s: VPGCR(64) + V cycle" % tag,
+                  got["success"] and abs(got["iter"] - want["iter"]) <= max(2, 0.25 * want["iter"]) and rr < 5e-7 * 1.0001,
+                  "iter %d (reference %d) true rel res %.2e" % (got["iter"], want["iter"], rr))
+            mg.destroy()
+
     # ---- reductions
     xv = ctx.vector(Yloc * X).upload(b[sl])
     d = ctx.dot(xv, xv)
