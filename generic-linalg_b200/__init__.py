@@ -27,7 +27,8 @@ STAG_DEO, STAG_DOE, STAG_M2MDEODOE = 8, 16, 32   # even/odd pieces (operators.cp
 OP = dict(LAPLACE_REAL=0, LAPLACE_IMAG=1, LAPLACE_NC=2, LAPLACE_U1=3, STAG_FREE=4, STAG_U1=5,
           STAG_GAMMA5_U1=6, STAG_DAGGER_U1=7, STAG_NORMAL_U1=8, GAMMA5=9, STENCIL=10,
           STENCIL_FROM_STAG=11, STAG_GAMMA5_FREE=12, LAPLACE_REAL_NC=13, STAG_FREE_REAL=14,
-          STAG_DEO_U1=15, STAG_DOE_U1=16, STAG_M2MDEODOE_U1=17)
+          STAG_DEO_U1=15, STAG_DOE_U1=16, STAG_M2MDEODOE_U1=17, SYMMSHIFT_X=18, SYMMSHIFT_Y=19,
+          STAG_2LINK_U1=20, STAG_INDEX=21)
 SOLVER = dict(CG=0, CG_RESTART=1, CR=2, CR_RESTART=3, GCR=4, GCR_RESTART=5, BICGSTAB=6,
               BICGSTAB_RESTART=7, BICGSTAB_L=8, BICGSTAB_L_RESTART=9, GMRES=10, GMRES_RESTART=11)
 
@@ -41,7 +42,7 @@ class OpDesc(C.Structure):
                 ("mass", C.c_double), ("links", C.c_void_p), ("clover", C.c_void_p),
                 ("hopping", C.c_void_p), ("two_link", C.c_void_p), ("has_two", C.c_int),
                 ("shift", C.c_double * 2), ("eo_shift", C.c_double * 2), ("dof_shift", C.c_double * 2),
-                ("view", C.c_int)]
+                ("view", C.c_int), ("wilson_coeff", C.c_double)]
 
 
 class Result(C.Structure):
@@ -724,8 +725,9 @@ class Context:
 
     # ---- the reference's own calls: HOST vectors + reference-named callbacks ----
     def _desc(self, kind, X, Y, mass=0.0, Nc=1, links=None, clover=None, hopping=None, two_link=None, shift=0j,
-              eo_shift=0j, dof_shift=0j, view=0):
+              eo_shift=0j, dof_shift=0j, view=0, wilson_coeff=0.0):
         d = OpDesc()
+        d.wilson_coeff = wilson_coeff
         d.view = STENCIL_VIEW[view] if isinstance(view, str) else view
         d.kind = OP[kind] if isinstance(kind, str) else kind
         d.X, d.Y, d.Nc, d.mass = X, Y, Nc, mass

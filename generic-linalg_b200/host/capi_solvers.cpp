@@ -36,7 +36,8 @@ enum {
   GX_LAPLACE_REAL = 0, GX_LAPLACE_IMAG = 1, GX_LAPLACE_NC = 2, GX_LAPLACE_U1 = 3, GX_STAG_FREE = 4, GX_STAG_U1 = 5,
   GX_STAG_GAMMA5_U1 = 6, GX_STAG_DAGGER_U1 = 7, GX_STAG_NORMAL_U1 = 8, GX_GAMMA5 = 9, GX_STENCIL = 10,
   GX_STENCIL_FROM_STAG = 11, GX_STAG_GAMMA5_FREE = 12, GX_LAPLACE_REAL_NC = 13, GX_STAG_FREE_REAL = 14,
-  GX_STAG_DEO_U1 = 15, GX_STAG_DOE_U1 = 16, GX_STAG_M2MDEODOE_U1 = 17
+  GX_STAG_DEO_U1 = 15, GX_STAG_DOE_U1 = 16, GX_STAG_M2MDEODOE_U1 = 17, GX_SYMMSHIFT_X = 18, GX_SYMMSHIFT_Y = 19,
+  GX_STAG_2LINK_U1 = 20, GX_STAG_INDEX = 21
 };
 enum {
   GX_CG = 0, GX_CG_RESTART = 1, GX_CR = 2, GX_CR_RESTART = 3, GX_GCR = 4, GX_GCR_RESTART = 5, GX_BICGSTAB = 6,
@@ -54,6 +55,7 @@ typedef struct glbx_opdesc {
   int has_two;
   double shift[2], eo_shift[2], dof_shift[2];
   int view;  // stencil kinds: 0 apply_stencil_2d, GLB_SV_* the composite callback on the stencil
+  double wilson_coeff;  // staggered_u1_op::wilson_coeff (square_staggered_2linklaplace_u1)
 } glbx_opdesc;
 
 }  // extern "C"
@@ -102,7 +104,7 @@ bool build_host_op(const glbx_opdesc* d, HostOp* h) {
   h->stag.x_fine = d->X;
   h->stag.y_fine = d->Y;
   h->stag.Nc = d->Nc > 0 ? d->Nc : 1;
-  h->stag.wilson_coeff = 0.0;
+  h->stag.wilson_coeff = d->wilson_coeff;
   h->lap.N = d->X;
   h->lap.mass_sq = d->mass;
   h->extra = &h->stag;
@@ -124,6 +126,10 @@ bool build_host_op(const glbx_opdesc* d, HostOp* h) {
     case GX_STAG_DEO_U1: h->cz = &square_staggered_deo_u1; break;
     case GX_STAG_DOE_U1: h->cz = &square_staggered_doe_u1; break;
     case GX_STAG_M2MDEODOE_U1: h->cz = &square_staggered_m2mdeodoe_u1; break;
+    case GX_SYMMSHIFT_X: h->cz = &staggered_symmshift_x; break;
+    case GX_SYMMSHIFT_Y: h->cz = &staggered_symmshift_y; break;
+    case GX_STAG_2LINK_U1: h->cz = &square_staggered_2linklaplace_u1; break;
+    case GX_STAG_INDEX: h->cz = &staggered_index_operator; break;
     case GX_STENCIL:
     case GX_STENCIL_FROM_STAG: {
       int dims[2] = {d->X, d->Y};

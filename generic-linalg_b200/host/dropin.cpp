@@ -30,7 +30,10 @@ enum Builtin {
   B_STAG_G5_U1, B_STAG_DAGGER_U1, B_STAG_NORMAL_U1, B_STAG_DEO_U1, B_STAG_DOE_U1, B_STAG_M2MDEODOE_U1, B_LAPLACIAN_REAL,
   B_LAPLACIAN_IMAG, B_STENCIL, B_STAG_FREE_REAL,
   // composite views of a stencil_2d (include/glb200.h GLB_SV_*), in that order
-  B_SV_M2MDEODOE, B_SV_M2MDTBDBT, B_SV_NORMAL_EO, B_SV_NORMAL_TB, B_SV_DAGGER_EO, B_SV_DAGGER_TB
+  B_SV_M2MDEODOE, B_SV_M2MDTBDBT, B_SV_NORMAL_EO, B_SV_NORMAL_TB, B_SV_DAGGER_EO, B_SV_DAGGER_TB,
+  // the rest of operators.h: stencils built on the host from the links (one upload), and the index operator,
+  // a composition of three device operators
+  B_SYMMSHIFT_X, B_SYMMSHIFT_Y, B_STAG_2LINK, B_STAG_INDEX
 };
 
 Builtin classify(void (*fn)(zcplx*, zcplx*, void*)) {
@@ -49,6 +52,10 @@ Builtin classify(void (*fn)(zcplx*, zcplx*, void*)) {
   if (fn == (F)&square_staggered_m2mdeodoe_u1) return B_STAG_M2MDEODOE_U1;
   if (fn == (F)&square_laplacian) return B_LAPLACIAN_IMAG;
   if (fn == (F)&apply_stencil_2d) return B_STENCIL;
+  if (fn == (F)&staggered_symmshift_x) return B_SYMMSHIFT_X;
+  if (fn == (F)&staggered_symmshift_y) return B_SYMMSHIFT_Y;
+  if (fn == (F)&square_staggered_2linklaplace_u1) return B_STAG_2LINK;
+  if (fn == (F)&staggered_index_operator) return B_STAG_INDEX;
   if (fn == (F)&apply_square_staggered_m2mdeodoe_stencil) return B_SV_M2MDEODOE;
   if (fn == (F)&apply_square_staggered_m2mdtbdbt_stencil) return B_SV_M2MDTBDBT;
   if (fn == (F)&apply_square_staggered_normal_eo_stencil) return B_SV_NORMAL_EO;
@@ -124,6 +131,46 @@ glb_operator* build(Builtin kind, void* extra) {
                                    st->lat->get_nc(), sh, eo, df, &op));
       break;
     }
+    case B_SYMMSHIFT_X:
+    case B_SYMMSHIFT_Y:
+    case B_STAG_2LINK: {
+      // nc = 1 stencils of operators.cpp:625-778, entries computed on the host with the reference's products
+      // (scaling by 1/2 is exact, so (U/2) psi = (U psi)/2 bit for bit).  Plane order: +x, +y, -x, -y;
+      // two-link: +2x, +x+y, +2y, -x+y, -2x, -x-y, -2y, +x-y (coarse_stencil.h:46-60).
+      staggered_u1_op* s = (staggered_u1_op*)extra;
+      const int X = s->x_fine, Y = s->y_fine, V = X * Y;
+      const zcplx* U = s->lattice;
+      std::vector<zcplx> cl(V, zcplx(0.0)), hp(4 * (size_t)V, zcplx(0.0)), tl;
+      const bool two = (kind == B_STAG_2LINK);
+      if (two) tl.assign(8 * (size_t)V, zcplx(0.0));
+      for (int i = 0; i < V; i++) {
+        const int x = i % X, y = i / X;
+        const int xm = (x + X - 1) % X, ym = (y + Y - 1) % Y, xp = (x + 1) % X, yp = (y + 1) % Y;
+        const int xmm = (x + X - 2) % X, ymm = (y + Y - 2) % Y;
+        const double eta1 = 1 - 2 * (x % 2);
+        if (kind == B_SYMMSHIFT_X) {
+          hp[i] = 0.5 * U[y * X * 2 + x * 2];
+          hp[i + 2 * (size_t)V] = 0.5 * conj(U[y * X * 2 + xm * 2]);
+        } else if (kind == B_SYMMSHIFT_Y) {
+          hp[i + (size_t)V] = 0.5 * (eta1 * U[y * X * 2 + x * 2 + 1]);
+          hp[i + 3 * (size_t)V] = 0.5 * (eta1 * conj(U[ym * X * 2 + x * 2 + 1]));
+        } else {
+          hp[i] = -0.5 * U[y * X * 2 + x * 2];
+          hp[i + (size_t)V] = -0.5 * (eta1 * U[y * X * 2 + x * 2 + 1]);
+          hp[i + 2 * (size_t)V] = 0.5 * conj(U[y * X * 2 + xm * 2]);
+          hp[i + 3 * (size_t)V] = 0.5 * (eta1 * conj(U[ym * X * 2 + x * 2 + 1]));
+          const double w = s->wilson_coeff;
+          cl[i] = w * 4.0;
+          tl[i] = -(w * U[y * X * 2 + x * 2] * U[y * X * 2 + xp * 2]);                              // +2x
+          tl[i + 2 * (size_t)V] = -(w * U[y * X * 2 + x * 2 + 1] * U[yp * X * 2 + x * 2 + 1]);      // +2y
+          tl[i + 4 * (size_t)V] = -(w * conj(U[y * X * 2 + xm * 2]) * conj(U[y * X * 2 + xmm * 2]));            // -2x
+          tl[i + 6 * (size_t)V] = -(w * conj(U[ym * X * 2 + x * 2 + 1]) * conj(U[ymm * X * 2 + x * 2 + 1]));    // -2y
+        }
+      }
+      const double sh[2] = {two ? s->mass : 0.0, 0.0}, z[2] = {0.0, 0.0};
+      GLBX(glb_op_create_stencil2d(ctx, cl.data(), hp.data(), two ? tl.data() : 0, X, Y, 1, sh, z, z, &op));
+      break;
+    }
     case B_SV_M2MDEODOE:
     case B_SV_M2MDTBDBT:
     case B_SV_NORMAL_EO:
@@ -160,16 +207,80 @@ std::map<CacheKey, glb_operator*> g_cache;
 
 bool cacheable(Builtin k) { return k >= B_LAPLACE_NC && k <= B_STAG_M2MDEODOE_U1; }
 
+// staggered_index_operator (operators.cpp:782-835) on the device: lhs = i D_0 rhs - (m i/2) S_x S_y rhs
+// + (m i/2) S_y S_x rhs with D_0 the massless staggered operator and S the symmetric shifts -- five applies and
+// three axpys of existing kernels, in the reference's order.  Usable as a device callback (extra = IndexOp*).
+struct IndexOp {
+  glb_context* ctx;
+  glb_operator *D0, *Sx, *Sy;
+  zcplx *t1, *t2;
+  double mass;
+  size_t n;
+};
+void index_apply_dev(zcplx* lhs, zcplx* rhs, void* e) {
+  IndexOp* o = (IndexOp*)e;
+  Blas<zcplx> B = {o->ctx, o->n};
+  GLBX(glb_op_apply(o->D0, o->t1, rhs));
+  B.zero(lhs);
+  B.axpy(zcplx(0.0, 1.0), o->t1, lhs);               // lhs = i D_0 rhs
+  const zcplx c = o->mass * zcplx(0.0, 0.5);          // mass*cplxId2
+  GLBX(glb_op_apply(o->Sy, o->t1, rhs));
+  GLBX(glb_op_apply(o->Sx, o->t2, o->t1));
+  B.axpy(-c, o->t2, lhs);                             // lhs -= c S_x S_y rhs
+  GLBX(glb_op_apply(o->Sx, o->t1, rhs));
+  GLBX(glb_op_apply(o->Sy, o->t2, o->t1));
+  B.axpy(c, o->t2, lhs);                              // lhs += c S_y S_x rhs
+}
+
 struct OpLease {  // operator for the duration of one call
   glb_operator* op;
   bool owned;
-  OpLease() : op(0), owned(false) {}
+  IndexOp* comp;  // set for the index operator: `op` is then its D_0 (sizes), the callback is index_apply_dev
+  OpLease() : op(0), owned(false), comp(0) {}
   ~OpLease() {
+    if (comp) {
+      glb_op_destroy(comp->Sx);
+      glb_op_destroy(comp->Sy);
+      if (comp->t1) glb_vec_free(comp->ctx, comp->t1);
+      if (comp->t2) glb_vec_free(comp->ctx, comp->t2);
+      delete comp;
+    }
     if (op && owned) glb_op_destroy(op);
   }
 };
+// the device callback of a composite lease (complex only)
+template <typename T>
+struct CompositeCallback {
+  static void (*get())(T*, T*, void*) { return 0; }
+};
+template <>
+struct CompositeCallback<zcplx> {
+  static void (*get())(zcplx*, zcplx*, void*) { return &index_apply_dev; }
+};
 
 void lease(Builtin kind, void* extra, OpLease* out) {
+  if (kind == B_STAG_INDEX) {
+    staggered_u1_op* s = (staggered_u1_op*)extra;
+    staggered_u1_op nomass = *s;
+    nomass.mass = 0.0;  // operators.cpp:803-808: a massless kernel for i D_st
+    IndexOp* c = new IndexOp();
+    c->ctx = glb200_default_context();
+    c->D0 = c->Sx = c->Sy = 0;
+    c->t1 = c->t2 = 0;
+    c->mass = s->mass;
+    out->comp = c;
+    out->op = c->D0 = build(B_STAG_U1, &nomass);
+    out->owned = true;
+    c->Sx = build(B_SYMMSHIFT_X, extra);
+    c->Sy = build(B_SYMMSHIFT_Y, extra);
+    c->n = glb_op_local_size(c->D0);
+    void* p = 0;
+    GLBX(glb_vec_alloc(c->ctx, GLB_COMPLEX, c->n, &p));
+    c->t1 = (zcplx*)p;
+    GLBX(glb_vec_alloc(c->ctx, GLB_COMPLEX, c->n, &p));
+    c->t2 = (zcplx*)p;
+    return;
+  }
   if (g_cache_ops && cacheable(kind)) {
     staggered_u1_op* s = (staggered_u1_op*)extra;
     CacheKey key = {(int)kind, (const void*)s->lattice, s->x_fine, s->y_fine, s->Nc};
@@ -222,6 +333,10 @@ inversion_info host_solve(const char* alg, T* phi, T* phi0, int size, void (*mv)
         throw Error("`size` does not match the operator's lattice");
       cb = &glb200_apply_dev;
       cb_extra = L.op;
+      if (L.comp) {  // the index operator: a composition of device operators behind a device callback
+        cb = CompositeCallback<T>::get();
+        cb_extra = L.comp;
+      }
     } else if (g_allow_shim) {
       shim.fn = mv;
       shim.extra = extra;
@@ -263,7 +378,10 @@ void direct_apply(Builtin kind, T* lhs, T* rhs, void* extra) {
     T* d_in = W.get();
     T* d_out = W.get();
     GLBX(glb_vec_upload(ctx, Traits<T>::dtype, n, d_in, rhs));
-    GLBX(glb_op_apply(L.op, d_out, d_in));
+    if (L.comp)
+      CompositeCallback<T>::get()(d_out, d_in, L.comp);
+    else
+      GLBX(glb_op_apply(L.op, d_out, d_in));
     GLBX(glb_vec_download(ctx, Traits<T>::dtype, n, lhs, d_out));
   } catch (const std::exception& e) {
     std::cerr << "[glb200] operator apply failed: " << e.what() << std::endl;
@@ -335,6 +453,10 @@ void square_staggered_dagger_u1(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<
 void square_staggered_normal_u1(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_STAG_NORMAL_U1, lhs, rhs, e); }
 void square_staggered_deo_u1(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_STAG_DEO_U1, lhs, rhs, e); }
 void square_staggered_doe_u1(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_STAG_DOE_U1, lhs, rhs, e); }
+void square_staggered_2linklaplace_u1(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_STAG_2LINK, lhs, rhs, e); }
+void staggered_symmshift_x(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_SYMMSHIFT_X, lhs, rhs, e); }
+void staggered_symmshift_y(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_SYMMSHIFT_Y, lhs, rhs, e); }
+void staggered_index_operator(zcplx* lhs, zcplx* rhs, void* e) { direct_apply<zcplx>(B_STAG_INDEX, lhs, rhs, e); }
 void square_staggered_m2mdeodoe_u1(zcplx* lhs, zcplx* rhs, void* e) {
   direct_apply<zcplx>(B_STAG_M2MDEODOE_U1, lhs, rhs, e);
 }
@@ -582,8 +704,12 @@ static inversion_info multi_host(const char* alg, typename MultiDev<T>::fn dev, 
     for (int s = 0; s < n_shift; s++) d_phi[s] = W.get();
     GLBX(glb_vec_upload(ctx, Traits<T>::dtype, size, d_b, phi0));
     void (*cb)(T*, T*, void*) = &glb200_apply_dev;
-    inversion_info inf = dev(d_phi.data(), d_b, n_shift, size, rfc, max_iter, eps, shifts, cb, (void*)L.op, worst_first,
-                             verb);
+    void* cb_extra = (void*)L.op;
+    if (L.comp) {
+      cb = CompositeCallback<T>::get();
+      cb_extra = (void*)L.comp;
+    }
+    inversion_info inf = dev(d_phi.data(), d_b, n_shift, size, rfc, max_iter, eps, shifts, cb, cb_extra, worst_first, verb);
     for (int s = 0; s < n_shift; s++) GLBX(glb_vec_download(ctx, Traits<T>::dtype, size, phi[s], d_phi[s]));
     return inf;
   } catch (const std::exception& e) {
@@ -671,6 +797,10 @@ struct PrecondMap {
       gcr.rel_res = g->rel_res;
       gcr.matrix_vector = &glb200_apply_dev;
       gcr.matrix_extra_data = L.op;
+      if (L.comp) {
+        gcr.matrix_vector = CompositeCallback<T>::get();
+        gcr.matrix_extra_data = L.comp;
+      }
       dev = &gcr_preconditioner_dev;
       info = &gcr;
     } else if (g_allow_shim) {

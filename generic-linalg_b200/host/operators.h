@@ -16,7 +16,7 @@ struct staggered_u1_op {
   int x_fine;
   int y_fine;
   int Nc;               // only relevant for square_laplace
-  double wilson_coeff;  // unused on this path
+  double wilson_coeff;  // two-link Laplace coefficient of square_staggered_2linklaplace_u1
 };
 
 // operator_utils/operators.h:17-25
@@ -69,5 +69,13 @@ struct laplace_op {
 };
 void square_laplacian(double* lhs, double* rhs, void* extra_data);                    // extra: laplace_op*
 void square_laplacian(complex<double>* lhs, complex<double>* rhs, void* extra_data);  // extra: laplace_op*
+
+// operators.cpp:625   staggered D plus a two-link Laplace term scaled by wilson_coeff (a 13-point stencil)
+void square_staggered_2linklaplace_u1(complex<double>* lhs, complex<double>* rhs, void* extra_data);
+// operators.cpp:688 / :728   symmetric shifts (1/2)(U psi(x+mu) + U^* psi(x-mu)), eta_1 in the y direction
+void staggered_symmshift_x(complex<double>* lhs, complex<double>* rhs, void* extra_data);
+void staggered_symmshift_y(complex<double>* lhs, complex<double>* rhs, void* extra_data);
+// operators.cpp:782   staggered index operator i D_st - m Gamma_5, Gamma_5 = (i/2)(S_x S_y - S_y S_x) of the symmetric shifts
+void staggered_index_operator(complex<double>* lhs, complex<double>* rhs, void* extra_data);
 
 #endif

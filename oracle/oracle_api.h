@@ -47,7 +47,11 @@ enum orc_op_kind {
   ORC_OP_STAG_FREE_REAL = 14,   /* tests/multishift/multishift.cpp:677 square_staggered (double)            */
   ORC_OP_STAG_DEO_U1 = 15,      /* operators.cpp:456  square_staggered_deo_u1   (hop term, even sites)      */
   ORC_OP_STAG_DOE_U1 = 16,      /* operators.cpp:494  square_staggered_doe_u1   (hop term, odd sites)       */
-  ORC_OP_STAG_M2MDEODOE_U1 = 17 /* operators.cpp:549  square_staggered_m2mdeodoe_u1 (m^2 - D_eo D_oe)       */
+  ORC_OP_STAG_M2MDEODOE_U1 = 17,/* operators.cpp:549  square_staggered_m2mdeodoe_u1 (m^2 - D_eo D_oe)       */
+  ORC_OP_SYMMSHIFT_X = 18,      /* operators.cpp:688  staggered_symmshift_x                 (reference only) */
+  ORC_OP_SYMMSHIFT_Y = 19,      /* operators.cpp:728  staggered_symmshift_y                 (reference only) */
+  ORC_OP_STAG_2LINK_U1 = 20,    /* operators.cpp:625  square_staggered_2linklaplace_u1      (reference only) */
+  ORC_OP_STAG_INDEX = 21        /* operators.cpp:782  staggered_index_operator              (reference only) */
 };
 
 /* Description of one operator.  Arrays are host pointers owned by the caller
@@ -66,6 +70,7 @@ typedef struct orc_op_desc {
                             stencil (numbering of include/glb200.h GLB_SV_*): 1 m2mdeodoe (operators_stencil.cpp:196),
                             2 m2mdtbdbt, 3 normal_eo, 4 normal_tb, 5 dagger_eo, 6 dagger_tb (mg_complex.cpp:1228-1372).
                             Reference library only.                                                       */
+  double wilson_coeff;   /* staggered_u1_op::wilson_coeff (ORC_OP_STAG_2LINK_U1)                             */
 } orc_op_desc;
 
 typedef struct orc_result {

@@ -1030,7 +1030,8 @@ double port_diffnorm2sq(int is_complex, const double* a, const double* b, int n)
 }
 
 void* port_op_prepare(const orc_op_desc* d) {
-  if (d->view != 0) return 0;  // the composite stencil operators exist in the reference library only
+  if (d->view != 0 || d->kind > ORC_OP_STAG_M2MDEODOE_U1) return 0;  // composite stencil operators, symmetric shifts, 2-link
+                                                                      // Laplace and the index operator: reference library only
   PortOp* op = new PortOp();
   op->d = *d;
   op->nc = d->Nc > 0 ? d->Nc : 1;

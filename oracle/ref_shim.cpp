@@ -86,6 +86,10 @@ void apply_c(RefOp* op, cplx* lhs, cplx* rhs) {
     case ORC_OP_STAG_DEO_U1: square_staggered_deo_u1(lhs, rhs, e); break;
     case ORC_OP_STAG_DOE_U1: square_staggered_doe_u1(lhs, rhs, e); break;
     case ORC_OP_STAG_M2MDEODOE_U1: square_staggered_m2mdeodoe_u1(lhs, rhs, e); break;
+    case ORC_OP_SYMMSHIFT_X: staggered_symmshift_x(lhs, rhs, e); break;
+    case ORC_OP_SYMMSHIFT_Y: staggered_symmshift_y(lhs, rhs, e); break;
+    case ORC_OP_STAG_2LINK_U1: square_staggered_2linklaplace_u1(lhs, rhs, e); break;
+    case ORC_OP_STAG_INDEX: staggered_index_operator(lhs, rhs, e); break;
     case ORC_OP_STENCIL:
     case ORC_OP_STENCIL_FROM_STAG:
       switch (op->d.view) {
@@ -213,7 +217,7 @@ void* ref_op_prepare(const orc_op_desc* d) {
   op->stagif.x_fine = d->X;
   op->stagif.y_fine = d->Y;
   op->stagif.Nc = d->Nc > 0 ? d->Nc : 1;
-  op->stagif.wilson_coeff = 0.0;
+  op->stagif.wilson_coeff = d->wilson_coeff;
   const int V = d->X * d->Y;
   op->size = V;
   op->is_complex = !(d->kind == ORC_OP_LAPLACE_REAL || d->kind == ORC_OP_LAPLACE_REAL_NC ||

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.skipif("ref" not in oracle_py.available(),
                                 reason="the reference's multigrid is only in oracle/_ref/libref_oracle.so")
 
 
-@pytest.mark.parametrize("module", ["test_mg_setup_gpu", "test_stencil_prec_gpu"])
+@pytest.mark.parametrize("module", ["test_mg_setup_gpu", "test_stencil_prec_gpu", "test_operators_rest_gpu"])
 def test_gpu_test_logic_runs_on_the_mock(module):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "mock", "run_gpu_tests_on_mock.py"), module],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)

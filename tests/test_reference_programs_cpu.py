@@ -1,0 +1,66 @@
+"""Source-level drop-in: the reference's OWN test programs, unmodified, compiled against this repository's headers
+(generic-linalg_b200/host) and linked with its solver shells, must print what the reference build prints.
+
+Three programs of /root/reference/tests are built twice here -- (a) as their Makefiles say, from the reference's
+sources; (b) the same .cpp against `-I generic-linalg_b200/host -I include` and the shells, which run on the
+host-memory mock of the C ABI in this GPU-less container (tests/mock: serial reductions, so the arithmetic is the
+reference's) -- and run from the reference's directory (they load gauge configurations by relative path).  Everything
+but the "Time" lines must be identical: operator names, plaquette, iteration / ops counts, residuals to the printed
+digits.  The only reference sources compiled into (b) are its gauge-field I/O (u1_utils.cpp) and its header-only
+host utilities (generic_vector.h), which are not on the accelerated path.  Skipped where /root/reference is absent."""
+import os
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+REF = "/root/reference"
+MOCK_DIR = os.path.join(ROOT, "tests", "mock")
+CXX = "/usr/bin/g++"
+
+PROGRAMS = {
+    # tests/bicgstab_l/Makefile:6
+    "bicgstab_l": dict(src="tests/bicgstab_l/bicgstab_l.cpp",
+                       ref_srcs=["generic_cg.cpp", "generic_bicgstab.cpp", "generic_bicgstab_l.cpp", "generic_gcr.cpp",
+                                 "u1_utils/u1_utils.cpp", "operator_utils/operators.cpp"],
+                       args=["--mass", "1e-2", "--beta", "6.0", "--lattice-size", "32"]),
+    # tests/staggered_stencil/Makefile:6
+    "staggered_stencil": dict(src="tests/staggered_stencil/staggered_stencil.cpp",
+                              ref_srcs=["u1_utils/u1_utils.cpp", "operator_utils/operators.cpp",
+                                        "operator_utils/operators_stencil.cpp", "stencil_2d/coarse_stencil.cpp"],
+                              args=[]),
+    # tests/staggered_w_laplace/Makefile:6
+    "staggered_w_laplace": dict(src="tests/staggered_w_laplace/staggered_w_laplace.cpp",
+                                ref_srcs=["u1_utils/u1_utils.cpp", "operator_utils/operators.cpp", "generic_gcr.cpp",
+                                          "generic_minres.cpp", "generic_gcr_var_precond.cpp", "generic_precond.cpp"],
+                                args=[]),
+}
+
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "tests")), reason="needs the reference tree")
+
+
+def _run(exe, args, cwd):
+    r = subprocess.run([exe] + args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:]
+    return [l for l in r.stdout.splitlines() if not l.startswith("Time")]
+
+
+@pytest.mark.parametrize("name", sorted(PROGRAMS))
+def test_unmodified_reference_program_prints_the_same(name, tmp_path):
+    subprocess.check_call(["make", "-C", MOCK_DIR], stdout=subprocess.DEVNULL)
+    p = PROGRAMS[name]
+    src = os.path.join(REF, p["src"])
+    ref_exe, our_exe = str(tmp_path / "ref_prog"), str(tmp_path / "our_prog")
+    ref_inc = ["-I" + os.path.join(REF, d) for d in ("", "u1_utils", "operator_utils", "stencil_2d", "lattice")]
+    subprocess.check_call([CXX, "-O2", "-std=c++11"] + ref_inc + [src] + [os.path.join(REF, s) for s in p["ref_srcs"]] +
+                          ["-o", ref_exe, "-lrt"], stderr=subprocess.DEVNULL)
+    our_inc = ["-I" + os.path.join(ROOT, "generic-linalg_b200", "host"), "-I" + os.path.join(ROOT, "include"),
+               "-I" + REF, "-I" + os.path.join(REF, "u1_utils")]                  # ours first: they shadow the reference's
+    subprocess.check_call([CXX, "-O2", "-std=c++11"] + our_inc + [src, os.path.join(REF, "u1_utils", "u1_utils.cpp"),
+                           "-o", our_exe, "-L" + MOCK_DIR, "-l:libglb200_inverters_mock.so", "-Wl,-rpath," + MOCK_DIR, "-lrt"],
+                          stderr=subprocess.DEVNULL)
+    cwd = os.path.dirname(src)
+    want, got = _run(ref_exe, p["args"], cwd), _run(our_exe, p["args"], cwd)
+    assert len(want) > 5
+    assert got == want
