@@ -107,6 +107,11 @@ inversion_info minv_vector_minres(complex<double>* phi, complex<double>* phi0, i
 // Gauss-Jordan elimination used by GMRES; stays on the host (generic_gelim.h)
 int gaussian_elimination(double* x, double* b, double** matrix, int size);
 int gaussian_elimination(complex<double>* x, complex<double>* b, complex<double>** matrix, int size);
+// several right-hand sides (x[k], b[k] of length size) and the matrix inverse (minv may alias matrix); generic_gelim.h:19-24
+int gaussian_elimination_multi_rhs(double** x, double** b, double** matrix, int n_rhs, int size);
+int gaussian_elimination_multi_rhs(complex<double>** x, complex<double>** b, complex<double>** matrix, int n_rhs, int size);
+int gaussian_elimination_matrix_inverse(double** minv, double** matrix, int size);
+int gaussian_elimination_matrix_inverse(complex<double>** minv, complex<double>** matrix, int size);
 
 // Solver selection by enum (generic_inverters.h:70-111)
 enum minv_inverter {

@@ -87,3 +87,35 @@ def test_missing_library_is_an_error(tmp_path, monkeypatch):
     monkeypatch.setattr(glb, "LIB_CUDA", str(tmp_path / "nope.so"))
     with pytest.raises(glb.GlbError):
         glb.libs()
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/glb200.h is what a cgo / JNI / ctypes host binds: it must compile as C99, no C++ types in it"""
+    src = tmp_path / "t.c"
+    src.write_text('#include "glb200.h"\nint main(void) { return GLB_OK; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           "-fsyntax-only", str(src)])
+
+
+@needs_build
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="needs the reference tree")
+def test_every_reference_solver_and_operator_entry_point_has_a_drop_in():
+    """every function the reference declares in its solver / operator / stencil headers on the path is exported by
+    libglb200_inverters.so with the same C++ signature (nm -DC of both sides, compared by demangled prototype)"""
+    ref = "/root/reference"
+    headers = ["generic_cg.h", "generic_cr.h", "generic_gcr.h", "generic_bicgstab.h", "generic_bicgstab_l.h",
+               "generic_gmres.h", "generic_cg_m.h", "generic_cr_m.h", "generic_bicgstab_m.h", "generic_sor.h",
+               "generic_minres.h", "generic_cg_precond.h", "generic_cg_flex_precond.h", "generic_gcr_var_precond.h",
+               "generic_bicgstab_precond.h", "generic_inverters.h", "generic_inverters_precond.h", "generic_gelim.h",
+               "operator_utils/operators.h", "operator_utils/operators_stencil.h"]
+    names = set()
+    for h in headers:
+        txt = open(os.path.join(ref, h)).read()
+        txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+        txt = re.sub(r"//[^\n]*", "", txt)
+        names.update(re.findall(r"^\s*(?:inversion_info|void|int)\s+(\w+)\s*\(", txt, flags=re.M))
+    assert len(names) > 40
+    out = subprocess.check_output(["nm", "-DC", "--defined-only", os.path.join(PKG, "libglb200_inverters.so")]).decode()
+    exported = set(re.findall(r" T (\w+)\(", out))
+    missing = sorted(n for n in names if n not in exported)
+    assert not missing, missing

@@ -64,3 +64,21 @@ def test_unmodified_reference_program_prints_the_same(name, tmp_path):
     want, got = _run(ref_exe, p["args"], cwd), _run(our_exe, p["args"], cwd)
     assert len(want) > 5
     assert got == want
+
+
+def test_dense_elimination_routines_match_the_reference_bit_for_bit(tmp_path):
+    """gaussian_elimination_multi_rhs / _matrix_inverse (generic_gelim.cpp:228-641; host-side dense helpers): the same
+    17-digit output from the reference's sources and from host/gelim.cpp (the reference prints its work on stdout)"""
+    subprocess.check_call(["make", "-C", MOCK_DIR], stdout=subprocess.DEVNULL)
+    drv = os.path.join(MOCK_DIR, "gelim_driver.cpp")
+    ref_exe, our_exe = str(tmp_path / "gelim_ref"), str(tmp_path / "gelim_ours")
+    subprocess.check_call([CXX, "-O2", "-std=c++11", "-I" + REF, drv, os.path.join(REF, "generic_gelim.cpp"), "-o", ref_exe])
+    subprocess.check_call([CXX, "-O2", "-std=c++11", drv, "-o", our_exe, "-L" + MOCK_DIR, "-l:libglb200_inverters_mock.so",
+                           "-Wl,-rpath," + MOCK_DIR])
+    outs = []
+    for exe in (ref_exe, our_exe):
+        r = subprocess.run([exe], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, timeout=120)
+        assert r.returncode == 0
+        outs.append(r.stderr.splitlines())
+    assert len(outs[0]) == 71 and outs[0][0] == "1 1"
+    assert outs[0] == outs[1]
