@@ -29,22 +29,25 @@ enum null_precond_strategy {
   NULL_PRECOND_NORMAL = 2,  // not on the accelerated path
 };
 
-// null_gen.h:31-64 (opt_null dropped: the operator is whatever stencils[curr_level] holds)
+// How the null vectors of every refinement are made (null_gen.h:31-64).  Filled by the driver from its command line in
+// the reference; here any caller of the _dev set-up routines fills it.  Per-level entries are indexed by the
+// refinement (0 = top).  `opt_null` of the reference is dropped: the operator the vectors are smoothed with is
+// whatever stencils[curr_level] holds when the routine is called.
 struct null_vector_params {
-  std::vector<int> n_null_vectors;  // per refinement, BEFORE the partition doubles them
-  minv_inverter null_gen;
-  null_precond_strategy null_prec;
-  std::vector<double> null_precisions;
-  std::vector<int> null_max_iters;
-  bool null_restart;
+  std::vector<int> n_null_vectors;      // per refinement: smoothed vectors BEFORE the partition multiplies them
+  minv_inverter null_gen;               // solver of the smoothing solve A x = -A x0 (default BiCGStab)
+  null_precond_strategy null_prec;      // plain, even/odd (top/bottom below the top level) or normal equations
+  std::vector<double> null_precisions;  // per refinement: relative tolerance of the smoothing solve (driver: 5e-5)
+  std::vector<int> null_max_iters;      // per refinement: its iteration cap (driver: 500)
+  bool null_restart;                    // restarted solver, every null_restart_freq iterations
   int null_restart_freq;
-  int null_bicgstab_l;
-  double null_relaxation;
-  double null_mass;
-  int null_partitions;
+  int null_bicgstab_l;                  // l of BiCGStab-l
+  double null_relaxation;               // omega of SOR / MinRes
+  double null_mass;                     // mass (stencil shift) used while generating, driver default 1e-2
+  int null_partitions;                  // 1 (BLOCK_NONE), 2 (BLOCK_EO, BLOCK_TOPO) or 4 (BLOCK_CORNER)
   blocking_strategy bstrat;
-  bool do_global_ortho_conj;
-  bool do_ortho_eo;
+  bool do_global_ortho_conj;            // also orthogonalise against the complex conjugates of earlier vectors
+  bool do_ortho_eo;                     // partition every vector right after its solve instead of at the end
   bool quiet;  // true: skip the reference's "[L*_NULLVEC]: Pre-orthog cosines ..." lines (and their three reductions each)
 
   null_vector_params() {

@@ -55,11 +55,9 @@ def test_unmodified_reference_program_prints_the_same(name, tmp_path):
     ref_inc = ["-I" + os.path.join(REF, d) for d in ("", "u1_utils", "operator_utils", "stencil_2d", "lattice")]
     subprocess.check_call([CXX, "-O2", "-std=c++11"] + ref_inc + [src] + [os.path.join(REF, s) for s in p["ref_srcs"]] +
                           ["-o", ref_exe, "-lrt"], stderr=subprocess.DEVNULL)
-    our_inc = ["-I" + os.path.join(ROOT, "generic-linalg_b200", "host"), "-I" + os.path.join(ROOT, "include"),
-               "-I" + REF, "-I" + os.path.join(REF, "u1_utils")]                  # ours first: they shadow the reference's
-    subprocess.check_call([CXX, "-O2", "-std=c++11"] + our_inc + [src, os.path.join(REF, "u1_utils", "u1_utils.cpp"),
-                           "-o", our_exe, "-L" + MOCK_DIR, "-l:libglb200_inverters_mock.so", "-Wl,-rpath," + MOCK_DIR, "-lrt"],
-                          stderr=subprocess.DEVNULL)
+    our_inc = ["-I" + os.path.join(ROOT, "generic-linalg_b200", "host"), "-I" + os.path.join(ROOT, "include")]
+    subprocess.check_call([CXX, "-O2", "-std=c++11"] + our_inc + [src, "-o", our_exe, "-L" + MOCK_DIR,
+                           "-l:libglb200_inverters_mock.so", "-Wl,-rpath," + MOCK_DIR, "-lrt"], stderr=subprocess.DEVNULL)
     cwd = os.path.dirname(src)
     want, got = _run(ref_exe, p["args"], cwd), _run(our_exe, p["args"], cwd)
     assert len(want) > 5
@@ -82,3 +80,23 @@ def test_dense_elimination_routines_match_the_reference_bit_for_bit(tmp_path):
         outs.append(r.stderr.splitlines())
     assert len(outs[0]) == 71 and outs[0][0] == "1 1"
     assert outs[0] == outs[1]
+
+
+def test_gauge_field_utilities_and_host_vector_helpers_match_the_reference(tmp_path):
+    """u1_utils.h (generators, gauge transformation, APE smearing, plaquette, topological charge, file round trip) and
+    generic_vector.h (every helper, real and complex): 17-digit output of the same driver built both ways"""
+    subprocess.check_call(["make", "-C", MOCK_DIR], stdout=subprocess.DEVNULL)
+    drv = os.path.join(MOCK_DIR, "u1_driver.cpp")
+    ref_exe, our_exe = str(tmp_path / "u1_ref"), str(tmp_path / "u1_ours")
+    subprocess.check_call([CXX, "-O2", "-std=c++11", "-I" + REF, "-I" + os.path.join(REF, "u1_utils"), drv,
+                           os.path.join(REF, "u1_utils", "u1_utils.cpp"), "-o", ref_exe])
+    subprocess.check_call([CXX, "-O2", "-std=c++11", "-I" + os.path.join(ROOT, "generic-linalg_b200", "host"), drv, "-o", our_exe,
+                           "-L" + MOCK_DIR, "-l:libglb200_inverters_mock.so", "-Wl,-rpath," + MOCK_DIR])
+    outs = []
+    for exe, f in ((ref_exe, "cfg_ref.dat"), (our_exe, "cfg_ours.dat")):
+        r = subprocess.run([exe, str(tmp_path / f)], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, timeout=120)
+        assert r.returncode == 0
+        outs.append(r.stderr.splitlines())
+    assert len(outs[0]) == 18 and outs[0][0].startswith("unit ") and outs[0][-1].startswith("real ")
+    assert outs[0] == outs[1]
+    assert open(tmp_path / "cfg_ref.dat").read() == open(tmp_path / "cfg_ours.dat").read()      # the file format itself
