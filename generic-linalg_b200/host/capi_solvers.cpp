@@ -429,9 +429,10 @@ inversion_info run_host_precond(int solver, T* phi, T* b, int size, int max_iter
   g.matrix_vector = cb;
   g.matrix_extra_data = extra;
   typedef void (*pfn)(T*, T*, int, void*, inversion_verbose_struct*);
-  pfn pc_gcr = &gcr_preconditioner, pc_id = &identity_preconditioner;
-  pfn pc = (precond == 1) ? pc_gcr : pc_id;
-  void* pci = (precond == 1) ? (void*)&g : 0;
+  // precond 2: minres_preconditioner; its struct has the layout of the GCR one (generic_precond.h:27-70)
+  pfn pc_gcr = &gcr_preconditioner, pc_id = &identity_preconditioner, pc_mr = &minres_preconditioner;
+  pfn pc = (precond == 1) ? pc_gcr : (precond == 2) ? pc_mr : pc_id;
+  void* pci = (precond != 0) ? (void*)&g : 0;
   switch (solver) {
     case 0: return minv_vector_cg_precond(phi, b, size, max_iter, eps, cb, extra, pc, pci, v);
     case 1: return minv_vector_cg_flex_precond(phi, b, size, max_iter, eps, cb, extra, pc, pci, v);

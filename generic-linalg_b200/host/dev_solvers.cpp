@@ -1523,6 +1523,16 @@ void gcr_preconditioner_dev(zcplx* lhs, zcplx* rhs, int size, void* extra_data, 
   minv_vector_gcr_dev(lhs, rhs, size, g->n_step, g->rel_res, g->matrix_vector, g->matrix_extra_data, verb);
 }
 
+// generic_precond.cpp:45-59 : n_step MinRes iterations (no relaxation) on the operator named by the struct
+void minres_preconditioner_dev(double* lhs, double* rhs, int size, void* extra_data, inversion_verbose_struct* verb) {
+  minres_precond_struct_real* m = (minres_precond_struct_real*)extra_data;
+  minv_vector_minres_dev(lhs, rhs, size, m->n_step, m->rel_res, m->matrix_vector, m->matrix_extra_data, verb);
+}
+void minres_preconditioner_dev(zcplx* lhs, zcplx* rhs, int size, void* extra_data, inversion_verbose_struct* verb) {
+  minres_precond_struct_complex* m = (minres_precond_struct_complex*)extra_data;
+  minv_vector_minres_dev(lhs, rhs, size, m->n_step, m->rel_res, m->matrix_vector, m->matrix_extra_data, verb);
+}
+
 // generic_inverter_precond.cpp:18-114
 template <typename T>
 static inversion_info dispatch_precond_dev(T* lhs, T* rhs, int size, minv_inverter_precond type,

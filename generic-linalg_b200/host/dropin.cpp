@@ -786,9 +786,10 @@ struct PrecondMap {
   PrecondMap(pfn host, void* host_info) : dev(0), info(0) {
     pfn ident = &identity_preconditioner;
     pfn gcrp = &gcr_preconditioner;
+    pfn mrp = &minres_preconditioner;
     if (host == ident) {
       dev = &identity_preconditioner_dev;
-    } else if (host == gcrp) {
+    } else if (host == gcrp || host == mrp) {  // the two structs have the same layout (generic_precond.h:27-70)
       typename GcrStruct<T>::type* g = (typename GcrStruct<T>::type*)host_info;
       const Builtin kind = classify(g->matrix_vector);
       if (kind == B_NONE) throw Error("gcr_preconditioner: its operator callback is not a known device operator");
@@ -801,7 +802,7 @@ struct PrecondMap {
         gcr.matrix_vector = CompositeCallback<T>::get();
         gcr.matrix_extra_data = L.comp;
       }
-      dev = &gcr_preconditioner_dev;
+      dev = (host == gcrp) ? (pfn)&gcr_preconditioner_dev : (pfn)&minres_preconditioner_dev;
       info = &gcr;
     } else if (g_allow_shim) {
       shim.fn = host;
@@ -809,7 +810,7 @@ struct PrecondMap {
       dev = &precond_shim_cb<T>;
       info = &shim;
     } else {
-      throw Error("preconditioner callback is not one of generic_precond.h (identity_preconditioner, gcr_preconditioner); "
+      throw Error("preconditioner callback is not one of generic_precond.h (identity_, gcr_, minres_preconditioner); "
                   "use the _dev entry points with a device preconditioner");
     }
   }
@@ -859,6 +860,15 @@ void gcr_preconditioner(double* lhs, double* rhs, int size, void* extra_data, in
 void gcr_preconditioner(zcplx* lhs, zcplx* rhs, int size, void* extra_data, inversion_verbose_struct* verb) {
   gcr_precond_struct_complex* g = (gcr_precond_struct_complex*)extra_data;
   minv_vector_gcr(lhs, rhs, size, g->n_step, g->rel_res, g->matrix_vector, g->matrix_extra_data, verb);
+}
+
+void minres_preconditioner(double* lhs, double* rhs, int size, void* extra_data, inversion_verbose_struct* verb) {
+  minres_precond_struct_real* m = (minres_precond_struct_real*)extra_data;
+  minv_vector_minres(lhs, rhs, size, m->n_step, m->rel_res, m->matrix_vector, m->matrix_extra_data, verb);
+}
+void minres_preconditioner(zcplx* lhs, zcplx* rhs, int size, void* extra_data, inversion_verbose_struct* verb) {
+  minres_precond_struct_complex* m = (minres_precond_struct_complex*)extra_data;
+  minv_vector_minres(lhs, rhs, size, m->n_step, m->rel_res, m->matrix_vector, m->matrix_extra_data, verb);
 }
 
 // generic_inverter_precond.cpp:18-114

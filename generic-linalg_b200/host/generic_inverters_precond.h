@@ -39,7 +39,8 @@
                                         void* extra_info, bool worst_first = false,                                 \
                                         inversion_verbose_struct* verbosity = 0);                                   \
   void identity_preconditioner(T* lhs, T* rhs, int size, void* extra_data, inversion_verbose_struct* verb = 0);     \
-  void gcr_preconditioner(T* lhs, T* rhs, int size, void* extra_data, inversion_verbose_struct* verb = 0);
+  void gcr_preconditioner(T* lhs, T* rhs, int size, void* extra_data, inversion_verbose_struct* verb = 0);     \
+  void minres_preconditioner(T* lhs, T* rhs, int size, void* extra_data, inversion_verbose_struct* verb = 0);
 GLB200_DECL_PRECOND(double)
 GLB200_DECL_PRECOND(complex<double>)
 
@@ -51,6 +52,20 @@ struct gcr_precond_struct_real {
   void* matrix_extra_data;
 };
 struct gcr_precond_struct_complex {
+  int n_step;
+  double rel_res;
+  void (*matrix_vector)(complex<double>*, complex<double>*, void*);
+  void* matrix_extra_data;
+};
+
+// generic_precond.h:27-43 : `extra_data` of minres_preconditioner (n_step MinRes iterations on matrix_vector)
+struct minres_precond_struct_real {
+  int n_step;
+  double rel_res;
+  void (*matrix_vector)(double*, double*, void*);
+  void* matrix_extra_data;
+};
+struct minres_precond_struct_complex {
   int n_step;
   double rel_res;
   void (*matrix_vector)(complex<double>*, complex<double>*, void*);

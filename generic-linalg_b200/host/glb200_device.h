@@ -148,7 +148,8 @@ GLB200_DECL_VPGCR(std::complex<double>)
   /* generic_precond.cpp:23-77 on device vectors: lhs = rhs; n_step GCR iterations on gps->matrix_vector (a device   \
      callback with its extra_info) from the lhs handed in */                                                        \
   void identity_preconditioner_dev(T* d_lhs, T* d_rhs, int size, void* extra_data, inversion_verbose_struct* verb = 0); \
-  void gcr_preconditioner_dev(T* d_lhs, T* d_rhs, int size, void* extra_data, inversion_verbose_struct* verb = 0);
+  void gcr_preconditioner_dev(T* d_lhs, T* d_rhs, int size, void* extra_data, inversion_verbose_struct* verb = 0); \
+  void minres_preconditioner_dev(T* d_lhs, T* d_rhs, int size, void* extra_data, inversion_verbose_struct* verb = 0);
 GLB200_DECL_DEV_PRECOND(double)
 GLB200_DECL_DEV_PRECOND(std::complex<double>)
 

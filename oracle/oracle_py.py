@@ -360,7 +360,7 @@ class RefMg:
 
 MULTI = dict(CG_M=0, CR_M=1, BICGSTAB_M=2)
 PRECOND_SOLVER = dict(PCG=0, FPCG=1, FPCG_RESTART=2, VPGCR=3, VPGCR_RESTART=4, PBICGSTAB=5, PBICGSTAB_RESTART=6)
-PRECOND = dict(IDENTITY=0, GCR=1)
+PRECOND = dict(IDENTITY=0, GCR=1, MINRES=2)
 
 
 def ref_solve_multi(orc, which, op, b, shifts, resid_freq_check=10, max_iter=10000, eps=1e-10, worst_first=False):

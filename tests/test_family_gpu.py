@@ -68,6 +68,8 @@ def test_multishift_family(ctx, glb, which, kind, shifts):
     ("FPCG_RESTART", "STAG_NORMAL_U1", dict(precond="GCR", n_step=2, restart_freq=12)),
     ("VPGCR", "STAG_U1", dict(precond="GCR", n_step=4)),
     ("VPGCR_RESTART", "STAG_U1", dict(precond="GCR", n_step=3, restart_freq=16)),
+    ("VPGCR", "STAG_U1", dict(precond="MINRES", n_step=4)),
+    ("FPCG", "STAG_NORMAL_U1", dict(precond="MINRES", n_step=3)),
     # BiCGStab on the light staggered operator is chaotic (the reference itself: 218..463 iterations over 1e-15
     # perturbations at m = 0.1), so these two run at m = 0.3 where the unrestarted count is stable
     ("PBICGSTAB", "STAG_U1", dict(precond="GCR", n_step=3, mass=0.3)),

@@ -96,6 +96,9 @@ PRECOND_CASES = [
     ("PBICGSTAB", "LAPLACE_REAL", dict(precond="IDENTITY")),
     ("PBICGSTAB", "STAG_U1", dict(precond="IDENTITY", max_iter=9)),                  # fails: k == max_iter quirk
     ("PBICGSTAB_RESTART", "STAG_U1", dict(precond="GCR", n_step=2, restart_freq=7)),
+    ("VPGCR", "STAG_U1", dict(precond="MINRES", n_step=4)),                          # minres_preconditioner
+    ("FPCG", "STAG_NORMAL_U1", dict(precond="MINRES", n_step=3)),
+    ("VPGCR_RESTART", "LAPLACE_REAL", dict(precond="MINRES", n_step=2, restart_freq=6)),
 ]
 
 
