@@ -119,3 +119,16 @@ def test_every_reference_solver_and_operator_entry_point_has_a_drop_in():
     exported = set(re.findall(r" T (\w+)\(", out))
     missing = sorted(n for n in names if n not in exported)
     assert not missing, missing
+
+
+def test_library_never_uses_the_host_vector_helpers():
+    """host/generic_vector.h and host/u1_utils.h exist for DRIVER programs (fill / check host arrays, gauge-field files).
+    No translation unit of the two libraries includes generic_vector.h: all vector work of the path is device work."""
+    for sub in ("host", "csrc"):
+        for f in os.listdir(os.path.join(PKG, sub)):
+            if f.endswith((".cpp", ".hpp", ".cu", ".cuh")) or (f.endswith(".h") and f != "generic_vector.h"):
+                txt = open(os.path.join(PKG, sub, f)).read()
+                assert not re.search(r"#include\s+[\"<]generic_vector\.h", txt), f
+    out = subprocess.check_output(["nm", "-DC", "--defined-only", os.path.join(PKG, "libglb200_inverters.so")]).decode() \
+        if _built() else ""
+    assert "glb200_hostvec" not in out
