@@ -1,9 +1,9 @@
 """Host-side (numpy) set-up of a two-level adaptive-multigrid hierarchy for the 2-D U(1) staggered operator:
 what the reference does in null_generate_random_smooth / block_orthonormalize /
 generate_coarse_from_fine_stencil (multigrid/aa_mg/null_gen.cpp:193, mg_complex.cpp:259, :827), vectorised so
-that it is usable at 2048^2.  MEASUREMENT TOOLING: the product takes the hierarchy as arrays; moving
-the set-up itself onto the device is the next row (8f-2).  tests/test_mg_setup_cpu.py checks these functions
-against the reference's own set-up on a small lattice."""
+that it is usable at 2048^2.  TEST / MEASUREMENT TOOLING: an independent restatement that both the reference's set-up
+(tests/test_mg_setup_cpu.py) and the device set-up of the product (glbx_mg_setup, tests/test_mg_setup_gpu.py)
+are checked against, and the host-side timing the device set-up is compared with (tools/bench_mg.py --numpy-setup)."""
 import numpy as np
 
 
