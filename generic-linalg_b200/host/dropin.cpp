@@ -407,6 +407,17 @@ glb_context* glb200_default_context() {
 }
 void glb200_set_default_context(glb_context* ctx) { g_default_ctx = ctx; }
 void glb200_allow_host_callback_shim(bool allow) { g_allow_shim = allow; }
+namespace {
+// GLB200_HOST_CALLBACKS=1 in the environment switches the shim on without a source change: programs whose operator is
+// their OWN host function (typically a composition of the operators of operators.h, e.g. level_crossing.cpp:366) then
+// run unmodified -- the solver's vectors stay on the device and every apply goes download -> user function -> upload.
+struct ShimFromEnv {
+  ShimFromEnv() {
+    const char* e = std::getenv("GLB200_HOST_CALLBACKS");
+    if (e && e[0] == '1') g_allow_shim = true;
+  }
+} g_shim_from_env;
+}  // namespace
 extern "C" void glb200_cache_operators(int on) {
   g_cache_ops = on != 0;
   if (!on) {
