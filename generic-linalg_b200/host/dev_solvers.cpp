@@ -12,6 +12,7 @@
 #include <utility>
 
 #include "dev_internal.hpp"
+#include "generic_eigenvalues.h"
 
 using namespace glbx;
 
@@ -893,6 +894,41 @@ inversion_info minres_dev(T* x, T* b, int size, int max_iter, double eps, double
   }
 GLB200_DEF_RELAX(double)
 GLB200_DEF_RELAX(zcplx)
+
+// ------------------------------------------------------------------------------------------ power iteration
+// generic_poweriter.cpp:23-88
+eigenvalue_info eig_vector_poweriter_dev(double* eig, double* phi0, int size, int max_iter, double relres,
+                                         void (*fn)(double*, double*, void*), void* extra) {
+  eigenvalue_info eigif;
+  eigif.relative_diff = 0.0;
+  eigif.iter = 0;
+  eigif.success = false;
+  eigif.name = "Power Iteration";
+  try {
+    DevOp<double> A = make_op<double>(fn, extra, size);
+    Blas<double> B = {A.ctx, (size_t)size};
+    Work<double> W(B);
+    double *x = W.get(), *q = W.get();
+    B.copy(x, phi0);
+    double beta = 0.0, beta_new = sqrt(B.norm2sq(x));
+    B.rdiv(x, beta_new, q);
+    int k;
+    for (k = 0; k < max_iter; k++) {
+      beta = beta_new;
+      A.apply(x, q);
+      beta_new = sqrt(B.norm2sq(x));
+      if (fabs(beta - beta_new) < relres) break;
+      B.rdiv(x, beta_new, q);
+    }
+    eigif.success = (k != max_iter);
+    *eig = beta_new;
+    eigif.relative_diff = fabs(beta - beta_new);
+    eigif.iter = k;
+  } catch (const std::exception& e) {
+    std::cerr << "[glb200] Power Iteration aborted: " << e.what() << std::endl;
+  }
+  return eigif;
+}
 
 // generic_inverter.cpp:18-190 on device vectors: the enum dispatch the MG smoother uses
 template <typename T>

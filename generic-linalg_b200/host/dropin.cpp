@@ -13,6 +13,7 @@
 
 #include "coarse_stencil.h"
 #include "dev_internal.hpp"
+#include "generic_eigenvalues.h"
 #include "generic_inverters_precond.h"
 #include "operators.h"
 #include "operators_stencil.h"
@@ -660,6 +661,23 @@ void get_square_staggered_dagger_u1_stencil(stencil_2d* st, staggered_u1_op* s) 
 GLB200_HOST_RELAX(double)
 GLB200_HOST_RELAX(zcplx)
 
+// generic_poweriter.cpp:23 with host vectors: phi0 goes up, the estimate comes back
+eigenvalue_info eig_vector_poweriter(double* eig, double* phi0, int size, int max_iter, double relres,
+                                     void (*mv)(double*, double*, void*), void* extra) {
+  eigenvalue_info out;
+  out.relative_diff = 0.0;
+  out.iter = 0;
+  out.success = false;
+  out.name = "Power Iteration";
+  std::vector<double> unused(size, 0.0);  // host_solve moves an in/out vector and a rhs: the start vector is the rhs
+  host_solve<double>("Power Iteration", unused.data(), phi0, size, mv, extra,
+                     [&](double*, double* d_phi0, void (*cb)(double*, double*, void*), void* ce) {
+                       out = eig_vector_poweriter_dev(eig, d_phi0, size, max_iter, relres, cb, ce);
+                       return inversion_info();
+                     });
+  return out;
+}
+
 GLB200_HOST_BASIC(minv_vector_cg, minv_vector_cg_dev, "CG")
 GLB200_HOST_RESTART(minv_vector_cg_restart, minv_vector_cg_restart_dev, "CG")
 GLB200_HOST_BASIC(minv_vector_cr, minv_vector_cr_dev, "CR")
@@ -794,7 +812,8 @@ struct PrecondMap {
   OpLease L;
   typename GcrStruct<T>::type gcr;
   PrecondShim<T> shim;
-  PrecondMap(pfn host, void* host_info) : dev(0), info(0) {
+  Shim<T> opshim;  // the stock preconditioner's own operator when that is a user host function (shim enabled)
+  PrecondMap(pfn host, void* host_info, int size) : dev(0), info(0) {
     pfn ident = &identity_preconditioner;
     pfn gcrp = &gcr_preconditioner;
     pfn mrp = &minres_preconditioner;
@@ -803,15 +822,26 @@ struct PrecondMap {
     } else if (host == gcrp || host == mrp) {  // the two structs have the same layout (generic_precond.h:27-70)
       typename GcrStruct<T>::type* g = (typename GcrStruct<T>::type*)host_info;
       const Builtin kind = classify(g->matrix_vector);
-      if (kind == B_NONE) throw Error("gcr_preconditioner: its operator callback is not a known device operator");
-      lease(kind, g->matrix_extra_data, &L);
       gcr.n_step = g->n_step;
       gcr.rel_res = g->rel_res;
-      gcr.matrix_vector = &glb200_apply_dev;
-      gcr.matrix_extra_data = L.op;
-      if (L.comp) {
-        gcr.matrix_vector = CompositeCallback<T>::get();
-        gcr.matrix_extra_data = L.comp;
+      if (kind != B_NONE) {
+        lease(kind, g->matrix_extra_data, &L);
+        gcr.matrix_vector = &glb200_apply_dev;
+        gcr.matrix_extra_data = L.op;
+        if (L.comp) {
+          gcr.matrix_vector = CompositeCallback<T>::get();
+          gcr.matrix_extra_data = L.comp;
+        }
+      } else if (g_allow_shim) {
+        opshim.fn = g->matrix_vector;
+        opshim.extra = g->matrix_extra_data;
+        opshim.n = size;
+        opshim.in.resize(size);
+        opshim.out.resize(size);
+        gcr.matrix_vector = &shim_cb<T>;
+        gcr.matrix_extra_data = &opshim;
+      } else {
+        throw Error("gcr_ / minres_preconditioner: its operator callback is not a known device operator");
       }
       dev = (host == gcrp) ? (pfn)&gcr_preconditioner_dev : (pfn)&minres_preconditioner_dev;
       info = &gcr;
@@ -832,7 +862,7 @@ struct PrecondMap {
                       void (*pc)(T*, T*, int, void*, inversion_verbose_struct*), void* pci,                         \
                       inversion_verbose_struct* verb) {                                                             \
     return host_solve<T>(ALG, phi, phi0, size, mv, extra, [&](T* dp, T* db, void (*cb)(T*, T*, void*), void* ce) {  \
-      PrecondMap<T> pm(pc, pci);                                                                                    \
+      PrecondMap<T> pm(pc, pci, size);                                                                              \
       return DEVNAME(dp, db, size, max_iter, eps, cb, ce, pm.dev, pm.info, verb);                                   \
     });                                                                                                             \
   }
@@ -841,7 +871,7 @@ struct PrecondMap {
                       void* extra, void (*pc)(T*, T*, int, void*, inversion_verbose_struct*), void* pci,            \
                       inversion_verbose_struct* verb) {                                                             \
     return host_solve<T>(ALG, phi, phi0, size, mv, extra, [&](T* dp, T* db, void (*cb)(T*, T*, void*), void* ce) {  \
-      PrecondMap<T> pm(pc, pci);                                                                                    \
+      PrecondMap<T> pm(pc, pci, size);                                                                              \
       return DEVNAME(dp, db, size, max_iter, res, rf, cb, ce, pm.dev, pm.info, verb);                               \
     });                                                                                                             \
   }

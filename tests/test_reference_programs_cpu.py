@@ -19,6 +19,11 @@ REF = "/root/reference"
 MOCK_DIR = os.path.join(ROOT, "tests", "mock")
 CXX = "/usr/bin/g++"
 
+ROOT_SRCS = [f + ".cpp" for f in (
+    "generic_cg generic_cr generic_bicgstab generic_bicgstab_l generic_gcr generic_gmres generic_gelim generic_sor "
+    "generic_minres generic_cg_precond generic_cg_flex_precond generic_gcr_var_precond generic_bicgstab_precond "
+    "generic_poweriter generic_precond generic_inverter generic_inverter_precond").split()]
+
 PROGRAMS = {
     # tests/bicgstab_l/Makefile:6
     "bicgstab_l": dict(src="tests/bicgstab_l/bicgstab_l.cpp",
@@ -43,6 +48,13 @@ PROGRAMS = {
     "level_crossing": dict(src="level_crossing/level_crossing.cpp", ref_srcs=None, args=[], env={"GLB200_HOST_CALLBACKS": "1"}),
     "meas_pion": dict(src="staggered_goldstone/meas_pion.cpp", ref_srcs="drivers_without_operators", args=[],
                       env={"GLB200_HOST_CALLBACKS": "1"}),
+    # the examples of the reference's top directory (Makefile:6): their operator is an in-file Laplacian with #define'd
+    # size and mass, so they run through the host-callback shim.  unit_test.cpp exercises EVERY solver of the library
+    # verbosely: ~30 000 lines of per-iteration residuals, all of which have to agree.  (Compiled from a copy in the
+    # test's scratch directory: next to its original a quoted #include would find the reference's own headers first.)
+    "square_laplace": dict(src="square_laplace.cpp", ref_srcs=ROOT_SRCS, args=[], env={"GLB200_HOST_CALLBACKS": "1"}, copy=True),
+    "imag_laplace": dict(src="imag_laplace.cpp", ref_srcs=ROOT_SRCS, args=[], env={"GLB200_HOST_CALLBACKS": "1"}, copy=True),
+    "unit_test": dict(src="unit_test.cpp", ref_srcs=ROOT_SRCS, args=[], env={"GLB200_HOST_CALLBACKS": "1"}, copy=True),
 }
 DRIVER_SRCS = ["generic_cg.cpp", "generic_cr.cpp", "generic_bicgstab.cpp", "generic_gcr.cpp", "generic_gmres.cpp",
                "generic_gelim.cpp", "generic_sor.cpp", "generic_minres.cpp", "generic_precond.cpp", "generic_cg_precond.cpp",
@@ -96,6 +108,10 @@ def test_unmodified_reference_program_prints_the_same(name, tmp_path, ref_object
     subprocess.check_call(["make", "-C", MOCK_DIR], stdout=subprocess.DEVNULL)
     p = PROGRAMS[name]
     src = os.path.join(REF, p["src"])
+    cwd = os.path.dirname(src)
+    if p.get("copy"):
+        import shutil
+        src = shutil.copy(src, str(tmp_path / os.path.basename(src)))
     ref_exe, our_exe = str(tmp_path / "ref_prog"), str(tmp_path / "our_prog")
     ref_inc = ["-I" + os.path.join(REF, d) for d in ("", "u1_utils", "operator_utils", "stencil_2d", "lattice")]
     b1 = subprocess.Popen([CXX, "-O2", "-std=c++11"] + ref_inc + [src] + [ref_objects[s] for s in _ref_sources(p)] +
@@ -104,10 +120,9 @@ def test_unmodified_reference_program_prints_the_same(name, tmp_path, ref_object
     b2 = subprocess.Popen([CXX, "-O2", "-std=c++11"] + our_inc + [src, "-o", our_exe, "-L" + MOCK_DIR,
                            "-l:libglb200_inverters_mock.so", "-Wl,-rpath," + MOCK_DIR, "-lrt"], stderr=subprocess.DEVNULL)
     assert b1.wait() == 0 and b2.wait() == 0
-    cwd = os.path.dirname(src)
     r1, r2 = _start(ref_exe, p["args"], cwd), _start(our_exe, p["args"], cwd, p.get("env"))   # side by side
     want, got = _finish(r1), _finish(r2)
-    assert len(want) > 5 and any("Success Y" in l or "difference" in l for l in want)
+    assert len(want) > 3 and any("Success Y" in l or "difference" in l or "esid" in l for l in want)
     assert got == want
 
 
