@@ -723,27 +723,41 @@ static inversion_info multi_host(const char* alg, typename MultiDev<T>::fn dev, 
   try {
     glb_context* ctx = glb200_default_context();
     const Builtin kind = classify(mv);
-    if (kind == B_NONE) throw Error("operator callback is not a known device operator");
     OpLease L;
-    lease(kind, extra, &L);
+    Shim<T> shim;
+    void (*cb)(T*, T*, void*) = &glb200_apply_dev;
+    void* cb_extra = 0;
+    if (kind != B_NONE) {
+      lease(kind, extra, &L);
+      cb_extra = (void*)L.op;
+      if (L.comp) {
+        cb = CompositeCallback<T>::get();
+        cb_extra = (void*)L.comp;
+      }
+    } else if (g_allow_shim) {  // the caller's own host function (tests/multishift/multishift.cpp:634)
+      shim.fn = mv;
+      shim.extra = extra;
+      shim.n = size;
+      shim.in.resize(size);
+      shim.out.resize(size);
+      cb = &shim_cb<T>;
+      cb_extra = &shim;
+    } else {
+      throw Error("operator callback is not a known device operator");
+    }
     Blas<T> B = {ctx, (size_t)size};
     Work<T> W(B);
     T* d_b = W.get();
     std::vector<T*> d_phi(n_shift);
     for (int s = 0; s < n_shift; s++) d_phi[s] = W.get();
     GLBX(glb_vec_upload(ctx, Traits<T>::dtype, size, d_b, phi0));
-    void (*cb)(T*, T*, void*) = &glb200_apply_dev;
-    void* cb_extra = (void*)L.op;
-    if (L.comp) {
-      cb = CompositeCallback<T>::get();
-      cb_extra = (void*)L.comp;
-    }
     inversion_info inf = dev(d_phi.data(), d_b, n_shift, size, rfc, max_iter, eps, shifts, cb, cb_extra, worst_first, verb);
     for (int s = 0; s < n_shift; s++) GLBX(glb_vec_download(ctx, Traits<T>::dtype, size, phi[s], d_phi[s]));
     return inf;
   } catch (const std::exception& e) {
     std::cerr << "[glb200] " << alg << " aborted: " << e.what() << std::endl;
-    inversion_info inf;
+    inversion_info inf(n_shift > 0 ? n_shift : 1);  // callers index resSqmrhs[] without looking at `success`
+    for (int s = 0; s < inf.n_rhs; s++) inf.resSqmrhs[s] = 0.0;
     inf.name = alg;
     return inf;
   }
