@@ -81,4 +81,13 @@ void apply_stencil_2d_oe(complex<double>* lhs, complex<double>* rhs, void* extra
 void apply_stencil_2d_tb(complex<double>* lhs, complex<double>* rhs, void* extra_data);
 void apply_stencil_2d_bt(complex<double>* lhs, complex<double>* rhs, void* extra_data);
 
+// coarse_stencil.cpp:1515-1640: fill an allocated, not yet generated stencil (stencil_size 1 or 2) from ANY operator
+// callback by probing it.  The reference applies the operator once per lattice dof; here unit sources that are further
+// apart than the stencil reaches share one apply (a comb with period >= 2*stencil_size+1 in each direction, when such a
+// period divides the lattice -- otherwise one source per row / column as in the reference), which gives the same
+// entries bit for bit with nc * period_x * period_y applies.  Host vectors; the callback is one of this library's
+// (each apply then runs on the device) or the caller's own.
+void generate_stencil_2d(stencil_2d* stenc, void (*matrix_vector)(complex<double>*, complex<double>*, void*),
+                         void* extra_data);
+
 #endif

@@ -6,6 +6,7 @@
 // operators.h / coarse_stencil.h, when called directly, do upload -> device apply -> download.
 // There is no CPU compute path: an unrecognised callback is an error unless the explicit parity
 // shim (glb200_allow_host_callback_shim) is switched on.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -552,6 +553,56 @@ void apply_square_staggered_tbprec_prepare_stencil(zcplx* rhs_t, zcplx* rhs_orig
 void apply_square_staggered_tbprec_reconstruct_stencil(zcplx* lhs_full, zcplx* lhs_t, zcplx* rhs_b, stencil_2d* st) {
   stencil_prec(1, true, lhs_full, lhs_t, rhs_b, st);
 }
+// coarse_stencil.cpp:1515-1640 by comb probing (see coarse_stencil.h)
+void generate_stencil_2d(stencil_2d* st, void (*mv)(zcplx*, zcplx*, void*), void* extra) {
+  if (st->generated || st->stencil_size > 2) return;
+  Lattice* lat = st->lat;
+  const int X = lat->get_lattice_dimension(0), Y = lat->get_lattice_dimension(1), nc = lat->get_nc();
+  const int L = lat->get_lattice_size();
+  const int reach = 2 * st->stencil_size + 1;
+  // smallest period >= reach that divides the extent; the whole extent (one source per row / column) otherwise
+  struct Period {
+    static int of(int n, int reach) {
+      for (int p = reach; p < n; p++)
+        if (n % p == 0) return p;
+      return n;
+    }
+  };
+  const int px = Period::of(X, reach), py = Period::of(Y, reach);
+  std::vector<zcplx> rhs(L), lhs(L);
+  const size_t plane = (size_t)nc * L;
+  // where the operator's row of the target site t = s - offset picks up the source s: plane index and offset
+  static const int hop[4][2] = {{1, 0}, {0, 1}, {-1, 0}, {0, -1}};
+  static const int two[8][2] = {{2, 0}, {1, 1}, {0, 2}, {-1, 1}, {-2, 0}, {-1, -1}, {0, -2}, {1, -1}};
+  for (int color = 0; color < nc; color++)
+    for (int cy = 0; cy < py; cy++)
+      for (int cx = 0; cx < px; cx++) {
+        std::fill(rhs.begin(), rhs.end(), zcplx(0.0));
+        for (int y = cy; y < Y; y += py)
+          for (int x = cx; x < X; x += px) rhs[((size_t)y * X + x) * nc + color] = 1.0;
+        std::fill(lhs.begin(), lhs.end(), zcplx(0.0));
+        mv(lhs.data(), rhs.data(), extra);
+        for (int y = cy; y < Y; y += py)
+          for (int x = cx; x < X; x += px)
+            for (int c = 0; c < nc; c++) {
+              const size_t self = ((size_t)y * X + x) * nc + c;
+              st->clover[color + nc * self] += lhs[self];
+              for (int d = 0; d < 4; d++) {  // the site whose direction-d neighbour is the source
+                const int tx = ((x - hop[d][0]) % X + X) % X, ty = ((y - hop[d][1]) % Y + Y) % Y;
+                const size_t t = ((size_t)ty * X + tx) * nc + c;
+                st->hopping[color + nc * t + d * plane] += lhs[t];
+              }
+              if (st->has_two)
+                for (int d = 0; d < 8; d++) {
+                  const int tx = ((x - two[d][0]) % X + X) % X, ty = ((y - two[d][1]) % Y + Y) % Y;
+                  const size_t t = ((size_t)ty * X + tx) * nc + c;
+                  st->two_link[color + nc * t + d * plane] += lhs[t];
+                }
+            }
+      }
+  st->generated = true;
+}
+
 static void stencil_part(zcplx* lhs, zcplx* rhs, void* e, int part) {
   try {
     glb_context* ctx = glb200_default_context();

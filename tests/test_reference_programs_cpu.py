@@ -169,3 +169,25 @@ def test_gauge_field_utilities_and_host_vector_helpers_match_the_reference(tmp_p
     assert len(outs[0]) == 18 and outs[0][0].startswith("unit ") and outs[0][-1].startswith("real ")
     assert outs[0] == outs[1]
     assert open(tmp_path / "cfg_ref.dat").read() == open(tmp_path / "cfg_ours.dat").read()      # the file format itself
+
+
+def test_generate_stencil_2d_matches_the_reference(tmp_path):
+    """generate_stencil_2d (coarse_stencil.cpp:1515): the reference probes with one apply per lattice dof, ours with
+    combs of well-separated unit sources -- every entry of the stencils generated from four operators on four lattices
+    (even, odd and degenerate extents; one- and two-link) has to be the same 17 digits"""
+    subprocess.check_call(["make", "-C", MOCK_DIR], stdout=subprocess.DEVNULL)
+    drv = os.path.join(MOCK_DIR, "genstencil_driver.cpp")
+    ref_exe, our_exe = str(tmp_path / "gs_ref"), str(tmp_path / "gs_ours")
+    ref_inc = ["-I" + os.path.join(REF, d) for d in ("", "u1_utils", "operator_utils", "stencil_2d", "lattice")]
+    subprocess.check_call([CXX, "-O2", "-std=c++11"] + ref_inc + [drv] + [os.path.join(REF, s) for s in (
+        "u1_utils/u1_utils.cpp", "operator_utils/operators.cpp", "stencil_2d/coarse_stencil.cpp")] + ["-o", ref_exe])
+    subprocess.check_call([CXX, "-O2", "-std=c++11", "-I" + os.path.join(ROOT, "generic-linalg_b200", "host"),
+                           "-I" + os.path.join(ROOT, "include"), drv, "-o", our_exe, "-L" + MOCK_DIR,
+                           "-l:libglb200_inverters_mock.so", "-Wl,-rpath," + MOCK_DIR])
+    outs = []
+    for exe in (ref_exe, our_exe):
+        r = subprocess.run([exe], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, timeout=300)
+        assert r.returncode == 0
+        outs.append(r.stderr.splitlines())
+    assert len(outs[0]) > 5000 and sum(l.endswith("generated 1") for l in outs[0]) == 15
+    assert outs[0] == outs[1]
