@@ -132,3 +132,34 @@ def test_library_never_uses_the_host_vector_helpers():
     out = subprocess.check_output(["nm", "-DC", "--defined-only", os.path.join(PKG, "libglb200_inverters.so")]).decode() \
         if _built() else ""
     assert "glb200_hostvec" not in out
+
+
+def _build_c_example(tmp_path):
+    exe = str(tmp_path / "c_abi_cgne")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "c_abi_cgne.c"), "-L", PKG, "-lglb200", "-lm",
+                           "-Wl,-rpath," + PKG, "-o", exe])
+    return exe
+
+
+@needs_build
+def test_plain_c_program_links_against_the_c_abi_and_refuses_to_run_without_a_gpu(tmp_path):
+    """examples/c_abi_cgne.c: what a foreign-language binding does, in C99; on this GPU-less machine it must stop at
+    glb_create with the library's message -- no CPU path takes over"""
+    exe = _build_c_example(tmp_path)
+    import shutil
+    if shutil.which("nvidia-smi") and subprocess.run(["nvidia-smi", "-L"], capture_output=True).returncode == 0:
+        pytest.skip("a GPU is present: covered by the gpu-marked test")
+    r = subprocess.run([exe, "32"], capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+@needs_build
+@pytest.mark.gpu
+def test_plain_c_program_runs_on_the_gpu(tmp_path):
+    exe = _build_c_example(tmp_path)
+    r = subprocess.run([exe, "64"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "CGNE on 64 x 64" in r.stdout and "iterations" in r.stdout
+    resid = float(r.stdout.split("|Dx-b|/|b| = ")[1].split(",")[0])
+    assert resid < 1e-8
