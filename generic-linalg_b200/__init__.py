@@ -164,7 +164,7 @@ def libs():
         "glbx_mg_vpgcr": (ci, [vp, vp, vp, ci, cd, ci, ci, C.POINTER(Result)]),
         "glbx_mg_counts": (None, [vp, C.POINTER(ci)]),
         "glbx_mg_setup": (vp, [vp, ci, ci, ci, C.POINTER(ci), C.POINTER(ci), ci, cd, ci, pd, C.POINTER(ci), ci, ci, ci,
-                               ci, C.c_uint, ci, ci, ci]),
+                               ci, C.c_uint, ci, ci, ci, vp]),
         "glbx_mg_level_op": (vp, [vp, ci]), "glbx_mg_level_transfer": (vp, [vp, ci]),
         "glbx_mg_null_vector": (vp, [vp, ci, ci]), "glbx_mg_setup_seconds": (None, [vp, pd]),
     }
@@ -413,11 +413,12 @@ class Multigrid:
     @classmethod
     def setup(cls, ctx, fine_op, X, Y, blocks, nvecs, bstrat=1, null_mass=1e-2, null_gen="BICGSTAB", tol=5e-5,
               max_iter=500, restart_freq=0, bicgstab_l=-1, do_ortho_eo=False, do_global_ortho_conj=False, seed=1337,
-              verbosity=0, null_prec=0, do_free=False):
+              verbosity=0, null_prec=0, do_free=False, links=None):
         """glbx_mg_setup: the reference driver's set-up sequence on the device (null_generate_random_smooth_dev,
         block_orthonormalize_dev, generate_coarse_from_fine_stencil_dev; aa_mg_square_staggered_u1.cpp:716-1143).
         fine_op: the level-0 stencil2d operator with the mass in its shift.  nvecs[l]: vectors of refinement l after
-        the partition; bstrat 0 = BLOCK_NONE, 1 = BLOCK_EO, 2 = BLOCK_CORNER; do_free: free-field vectors
+        the partition; bstrat 0 = BLOCK_NONE, 1 = BLOCK_EO, 2 = BLOCK_CORNER, 3 = BLOCK_TOPO (pass the host
+        gauge field as `links`: the chiral projectors are built from its symmetric shifts); do_free: free-field vectors
         (null_generate_free_dev) instead of the smoothing solves; null_prec 0 = plain solves, 1 = even/odd (top/bottom below the
         top level), 2 = normal equations (null_gen.h:24-29)."""
         n = len(blocks)
@@ -429,7 +430,7 @@ class Multigrid:
         mi = (C.c_int * n)(*([max_iter] * n if np.isscalar(max_iter) else max_iter))
         self.h = ctx.ho.glbx_mg_setup(fine_op.h, X, Y, n, bl, nv, bstrat, null_mass, cls.SMOOTH[null_gen], tl, mi,
                                       restart_freq, bicgstab_l, int(do_ortho_eo), int(do_global_ortho_conj), seed,
-                                      verbosity, null_prec, int(do_free))
+                                      verbosity, null_prec, int(do_free), _p(links) if links is not None else None)
         if not self.h:
             raise GlbError("glbx_mg_setup failed (see stderr)")
         self.ops, self.transfers = [fine_op], []

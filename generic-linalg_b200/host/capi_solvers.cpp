@@ -480,7 +480,8 @@ typedef struct glbx_mg {
   std::vector<std::vector<zc*> > null_dev;
   std::vector<zc**> null_tab;
   double setup_seconds[4];  // null vectors, block orthonormalisation, transfers + Galerkin products, total
-  glbx_mg() : owns_hierarchy(false), ctx(0) { setup_seconds[0] = setup_seconds[1] = setup_seconds[2] = setup_seconds[3] = 0.0; }
+  // mg(), pc(): every pointer of the two structs starts null
+  glbx_mg() : mg(), pc(), owns_hierarchy(false), ctx(0) { setup_seconds[0] = setup_seconds[1] = setup_seconds[2] = setup_seconds[3] = 0.0; }
 } glbx_mg;
 
 static void mg_defaults(glbx_mg* h, int n_refine) {
@@ -525,6 +526,8 @@ void glbx_mg_destroy(glbx_mg* h) {
       if (h->ops[i]) glb_op_destroy(h->ops[i]);
     for (size_t i = 0; i < h->trs.size(); i++)
       if (h->trs[i]) glb_mg_transfer_destroy(h->trs[i]);
+    if (h->mg.symmshift_x) glb_op_destroy(h->mg.symmshift_x);
+    if (h->mg.symmshift_y) glb_op_destroy(h->mg.symmshift_y);
     for (size_t l = 0; l < h->null_dev.size(); l++)
       for (size_t v = 0; v < h->null_dev[l].size(); v++)
         if (h->null_dev[l][v] && ctx) glb_vec_free(ctx, h->null_dev[l][v]);
@@ -543,12 +546,13 @@ void glbx_mg_destroy(glbx_mg* h) {
 //   nvec[l]   total null vectors of refinement l (after the partition);  bstrat: 0 none, 1 even/odd
 //   null_gen  minv_inverter;  tol[l], max_iter[l] per refinement;  seed of the std::mt19937 behind the sources
 //   do_free   free-field null vectors (null_generate_free_dev) instead of smoothed random ones
+//   links     BLOCK_TOPO (bstrat 3) only: the host gauge field (reference layout) the symmetric shifts are built from
 //   null_prec null_precond_strategy: 0 plain solve, 1 even/odd (top/bottom below the top level), 2 normal equations
 // On y-slabs X, Y are the GLOBAL extents and `fine` the slab operator; every rank calls with the same arguments.
 glbx_mg* glbx_mg_setup(glb_operator* fine, int X, int Y, int n_refine, const int* block, const int* nvec, int bstrat,
                        double null_mass, int null_gen, const double* tol, const int* max_iter, int restart_freq,
                        int bicgstab_l, int do_ortho_eo, int do_global_ortho_conj, unsigned seed, int verbosity,
-                       int null_prec, int do_free) {
+                       int null_prec, int do_free, const void* links) {
   if (!fine || n_refine < 1 || !block || !nvec || !tol || !max_iter) return 0;
   glbx_mg* h = new glbx_mg();
   double mass_shift[2] = {0.0, 0.0};
@@ -586,6 +590,21 @@ glbx_mg* glbx_mg_setup(glb_operator* fine, int X, int Y, int n_refine, const int
       h->null_tab[l] = h->null_dev[l].data();
     }
     h->mg.null_vectors = h->null_tab.data();
+    if (bstrat == BLOCK_TOPO) {  // null_gen.cpp:36-71 needs the symmetric shifts of the gauge field
+      if (!links) throw glbx::Error("BLOCK_TOPO needs the gauge links");
+      staggered_u1_op st;
+      st.lattice = (zc*)links;
+      st.mass = 0.0;
+      st.x_fine = X;
+      st.y_fine = Y;
+      st.Nc = 1;
+      st.wilson_coeff = 0.0;
+      void (*sx)(zc*, zc*, void*) = &staggered_symmshift_x;
+      void (*sy)(zc*, zc*, void*) = &staggered_symmshift_y;
+      h->mg.symmshift_x = glb200_operator_from_callback(sx, (void*)&st);
+      h->mg.symmshift_y = glb200_operator_from_callback(sy, (void*)&st);
+      if (!h->mg.symmshift_x || !h->mg.symmshift_y) throw glbx::Error("BLOCK_TOPO: cannot build the symmetric shifts");
+    }
 
     null_vector_params nv;
     nv.null_gen = (minv_inverter)null_gen;
@@ -595,7 +614,7 @@ glbx_mg* glbx_mg_setup(glb_operator* fine, int X, int Y, int n_refine, const int
     nv.null_bicgstab_l = bicgstab_l;
     nv.null_mass = null_mass;
     nv.bstrat = (blocking_strategy)bstrat;
-    nv.null_partitions = (bstrat == BLOCK_EO) ? 2 : (bstrat == BLOCK_CORNER) ? 4 : 1;  // :412-427
+    nv.null_partitions = (bstrat == BLOCK_EO || bstrat == BLOCK_TOPO) ? 2 : (bstrat == BLOCK_CORNER) ? 4 : 1;  // :412-427
     nv.do_ortho_eo = do_ortho_eo != 0;
     nv.do_global_ortho_conj = do_global_ortho_conj != 0;
     nv.quiet = verbosity == 0;

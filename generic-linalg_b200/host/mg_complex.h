@@ -49,6 +49,11 @@ struct mg_operator_struct_complex_dev {
   int* blocksize_y;                        // [n_refine]
   int* n_vectors;                          // [n_refine] null vectors per refinement = coarse dofs per site
   std::complex<double>*** null_vectors;    // DEVICE arrays null_vectors[level][v], level-l lattice size each
+  // BLOCK_TOPO only (null_gen.cpp:36-71 builds the taste-singlet projectors from the symmetric shifts of the gauge
+  // field in matrix_extra_data): the two shift operators on the top level, e.g. from
+  // glb200_operator_from_callback(staggered_symmshift_x / _y, &stagif)
+  glb_operator* symmshift_x;
+  glb_operator* symmshift_y;
 };
 
 // lattice of level l (mg_complex.h: latt[l]): sites and dofs per site

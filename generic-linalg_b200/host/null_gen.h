@@ -19,7 +19,7 @@ enum blocking_strategy {
   BLOCK_NONE = 0,    // block fully
   BLOCK_EO = 1,      // even/odd
   BLOCK_CORNER = 2,  // corners
-  BLOCK_TOPO = 3     // taste singlet  (not on the accelerated path)
+  BLOCK_TOPO = 3     // taste singlet: (1 +- Gamma_5)/2 from the symmetric shifts (needs mgstruct->symmshift_x/_y)
 };
 
 // null_gen.h:24-29
@@ -68,7 +68,7 @@ struct null_vector_params {
 
 // null_gen.cpp:13-103: partition null vector `num_null_vec` of the top level (BLOCK_EO: its odd sites move to vector
 // num_null_vec + n_vectors[0]/2; BLOCK_CORNER: the three odd corners move to num_null_vec + k*n_vectors[0]/4).
-// BLOCK_NONE: nothing.  BLOCK_TOPO throws.
+// BLOCK_NONE: nothing.  BLOCK_TOPO: v and Gamma_5 v combined into the two chiral projections (null_gen.cpp:36-71).
 void null_partition_staggered_dev(mg_operator_struct_complex_dev* mgstruct, int num_null_vec, blocking_strategy bstrat);
 
 // null_gen.cpp:106-160: the same below the top level (BLOCK_EO: the upper half of the colour index moves).

@@ -104,8 +104,30 @@ void partition(mg_operator_struct_complex_dev* mg, int num_null_vec, blocking_st
         GLBX(glb_mg_partition_corner(L.ctx, L.X, L.Y, L.dof, period, k, null[num_null_vec],
                                      null[num_null_vec + k * mg->n_vectors[lvl] / 4]));
       return;
+    case BLOCK_TOPO: {
+      // null_gen.cpp:36-71 (top level; below it null_partition_coarse treats BLOCK_TOPO like BLOCK_EO): with
+      // Gamma_5 = (i/2)(S_x S_y - S_y S_x) of the symmetric shifts, v -> (1 +- Gamma_5)/2 v
+      if (by_colour) throw Error("null_partition: BLOCK_TOPO below the top level is the BLOCK_EO split");
+      if (!mg->symmshift_x || !mg->symmshift_y)
+        throw Error("null_partition: BLOCK_TOPO needs mgstruct->symmshift_x / symmshift_y (the symmetric shifts of the gauge field)");
+      zcplx* v = null[num_null_vec];
+      zcplx* g5v = null[num_null_vec + mg->n_vectors[lvl] / 2];
+      Blas<zcplx> B = {L.ctx, (size_t)L.size};
+      Work<zcplx> W(B);
+      zcplx *tmp = W.get(), *tmp2 = W.get();
+      GLBX(glb_op_apply(mg->symmshift_y, tmp, v));
+      GLBX(glb_op_apply(mg->symmshift_x, tmp2, tmp));
+      B.axpy(zcplx(0.0, 0.5), tmp2, g5v);    // += (i/2) S_x S_y v
+      GLBX(glb_op_apply(mg->symmshift_x, tmp, v));
+      GLBX(glb_op_apply(mg->symmshift_y, tmp2, tmp));
+      B.axpy(-zcplx(0.0, 0.5), tmp2, g5v);   // -= (i/2) S_y S_x v
+      B.add(v, g5v, v);                      // v <- 0.5 (v + Gamma_5 v)
+      GLBX(glb_rscale(L.ctx, GLB_COMPLEX, B.n, v, 0.5, v));
+      B.sub(v, g5v, g5v);                    // Gamma_5 slot <- v_new - Gamma_5 v
+      return;
+    }
     default:
-      throw Error("null_partition: BLOCK_TOPO is not on the accelerated path (it needs the symmetric-shift operators)");
+      throw Error("null_partition: unknown blocking strategy");
   }
 }
 

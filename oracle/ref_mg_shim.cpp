@@ -197,7 +197,7 @@ void* refmg_setup(int X, int Y, const double* links, double mass, int n_refine, 
   nv.null_bicgstab_l = bicgstab_l;
   nv.null_mass = null_mass;
   nv.bstrat = (blocking_strategy)bstrat;
-  nv.null_partitions = (bstrat == BLOCK_EO) ? 2 : (bstrat == BLOCK_CORNER) ? 4 : 1;  // aa_mg_square_staggered_u1.cpp:412-427
+  nv.null_partitions = (bstrat == BLOCK_EO || bstrat == BLOCK_TOPO) ? 2 : (bstrat == BLOCK_CORNER) ? 4 : 1;  // aa_mg_square_staggered_u1.cpp:412-427
   nv.do_global_ortho_conj = do_global_ortho_conj != 0;
   nv.do_ortho_eo = do_ortho_eo != 0;
   for (int i = 0; i < n_refine; i++) {

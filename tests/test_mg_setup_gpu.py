@@ -174,7 +174,7 @@ def test_setup_argument_errors(ctx, glb):
         odd.view("M2MDTBDBT")
     with pytest.raises(glb.GlbError):
         odd.prec_prepare(1, ctx.vector(192), ctx.vector(192))
-    with pytest.raises(glb.GlbError):                      # BLOCK_TOPO is refused (stderr carries the reason)
+    with pytest.raises(glb.GlbError):                      # BLOCK_TOPO without the gauge links is refused (stderr says why)
         ctx.multigrid_setup(fine, L, L, [4], [4], bstrat=3, max_iter=2)
     assert fine.get_shifts()[0] == complex(0.05)           # and the caller's shift is back
     with pytest.raises(glb.GlbError):
@@ -231,7 +231,9 @@ def test_setup_handle_outlives_its_fine_operator(ctx, glb):
                                                  (64, [4], [8], dict(null_prec=2, null_gen="CG", tol=1e-3)),
                                                  # BLOCK_CORNER (four parts per smoothed vector), free-field vectors
                                                  (64, [4], [8], dict(bstrat=2)),
-                                                 (32, [4], [2], dict(do_free=True))])
+                                                 (32, [4], [2], dict(do_free=True)),
+                                                 # BLOCK_TOPO: chiral projectors from the symmetric shifts of the links
+                                                 (64, [4], [8], dict(bstrat=3))])
 def test_setup_defaults_hierarchy_and_solve(ctx, glb, L, blocks, nvecs, opts):
     """the driver's defaults (BiCGStab to 5e-5, at most 500 iterations, null mass 1e-2, BLOCK_EO): structural
     properties of the device-built hierarchy and the outer solve VPGCR(64) + V cycle next to the reference's own
@@ -246,7 +248,7 @@ def test_setup_defaults_hierarchy_and_solve(ctx, glb, L, blocks, nvecs, opts):
     with quiet_stdout():
         ref = oracle_py.RefMg.setup(orc, L, L, U, mass, blocks, nvecs, **kw)
     fine, hp0 = _fine_stencil(ctx, orc, U, L, mass)
-    mg = ctx.multigrid_setup(fine, L, L, blocks, nvecs, **kw)
+    mg = ctx.multigrid_setup(fine, L, L, blocks, nvecs, links=(U if opts.get("bstrat") == 3 else None), **kw)
     secs = mg.setup_seconds()
     assert secs["total"] > 0
     # block orthonormality of the top-level vectors: <v_i, v_j> = delta_ij inside every block

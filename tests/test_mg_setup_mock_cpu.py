@@ -40,7 +40,7 @@ def lib():
     L.glb_op_get_shifts.argtypes = [vp, pd, pd, pd]
     L.glbx_mg_setup.restype = vp
     L.glbx_mg_setup.argtypes = [vp, ci, ci, ci, C.POINTER(ci), C.POINTER(ci), ci, cd, ci, pd, C.POINTER(ci), ci, ci, ci, ci,
-                                C.c_uint, ci, ci, ci]
+                                C.c_uint, ci, ci, ci, vp]
     L.glbx_mg_level_op.restype = vp
     L.glbx_mg_level_op.argtypes = [vp, ci]
     L.glbx_mg_null_vector.restype = vp
@@ -75,7 +75,7 @@ def _mock_setup(lib, ref, X, Y, blocks, nvecs, **kw):
                           (C.c_double * n)(*[kw.get("tol", 5e-5)] * n), (C.c_int * n)(*[kw.get("max_iter", 500)] * n),
                           kw.get("restart_freq", 0), kw.get("bicgstab_l", -1), int(kw.get("do_ortho_eo", False)),
                           int(kw.get("do_global_ortho_conj", False)), kw.get("seed", 1337), 0, kw.get("null_prec", 0),
-                          int(kw.get("do_free", False)))
+                          int(kw.get("do_free", False)), _p(ref.links) if kw.get("bstrat", 1) == 3 else None)
     assert h, "glbx_mg_setup failed"
     return h, fine, keep
 
@@ -119,6 +119,9 @@ CASES = [
     dict(L=16, blocks=[4], nvecs=[4], kw=dict(seed=12, bstrat=2, do_ortho_eo=True, null_gen="GCR", max_iter=30)),
     dict(L=16, blocks=[4], nvecs=[2], kw=dict(do_free=True)),
     dict(L=16, blocks=[4], nvecs=[4], kw=dict(do_free=True, bstrat=2)),
+    # BLOCK_TOPO: the chiral projectors (1 +- Gamma_5)/2 from the symmetric shifts (null_gen.cpp:36-71)
+    dict(L=16, blocks=[4], nvecs=[4], kw=dict(seed=14, bstrat=3, max_iter=60)),
+    dict(L=16, blocks=[4], nvecs=[2], kw=dict(do_free=True, bstrat=3)),
 ]
 
 
@@ -174,7 +177,7 @@ def test_three_level_setup_and_solve(lib):
     assert lib.glb_op_create_stencil2d(None, _p(cl), _p(hp), None, L, L, 1, c2[0], c2[1], c2[2], C.byref(fine)) == 0
     two = C.c_int * 2
     h = lib.glbx_mg_setup(fine, L, L, 2, two(*blocks), two(*nvecs), 1, 1e-2, glb.Multigrid.SMOOTH["BICGSTAB"],
-                          (C.c_double * 2)(5e-5, 5e-5), two(500, 4), 0, -1, 0, 0, 21, 0, 0, 0)
+                          (C.c_double * 2)(5e-5, 5e-5), two(500, 4), 0, -1, 0, 0, 21, 0, 0, 0, None)
     assert h
     try:
         for v in range(nvecs[0]):
@@ -233,7 +236,7 @@ def test_preconditioned_null_solves_below_the_top_level(lib, null_prec):
     assert lib.glb_op_create_stencil2d(None, _p(cl), _p(hp), None, L, L, 1, c2[0], c2[1], c2[2], C.byref(fine)) == 0
     two = C.c_int * 2
     h = lib.glbx_mg_setup(fine, L, L, 2, two(*blocks), two(*nvecs), 1, 1e-2, lib._glb.Multigrid.SMOOTH["CG"],
-                          (C.c_double * 2)(5e-5, 5e-5), two(500, 3), 0, -1, 0, 0, 13, 0, null_prec, 0)
+                          (C.c_double * 2)(5e-5, 5e-5), two(500, 3), 0, -1, 0, 0, 13, 0, null_prec, 0, None)
     assert h
     try:
         for v in range(nvecs[0]):
@@ -261,7 +264,7 @@ def test_coarse_partition_uses_the_reference_colour_period(lib):
     assert lib.glb_op_create_stencil2d(None, _p(cl), _p(hp), None, L, L, 1, c2[0], c2[1], c2[2], C.byref(fine)) == 0
     two = C.c_int * 2
     h = lib.glbx_mg_setup(fine, L, L, 2, two(*blocks), two(*nvecs), 1, 1e-2, lib._glb.Multigrid.SMOOTH["BICGSTAB"],
-                          (C.c_double * 2)(5e-5, 5e-5), two(500, 3), 0, -1, 1, 0, 4, 0, 0, 0)
+                          (C.c_double * 2)(5e-5, 5e-5), two(500, 3), 0, -1, 1, 0, 4, 0, 0, 0, None)
     assert h
     try:
         X1, Y1, d1 = ref.dims(1)
@@ -277,7 +280,7 @@ def test_coarse_partition_uses_the_reference_colour_period(lib):
 
 
 def test_unsupported_strategies_fail_loudly(lib):
-    """BLOCK_TOPO is not on the accelerated path: the set-up refuses instead of doing something else"""
+    """BLOCK_TOPO without the gauge links cannot build its projectors: the set-up refuses instead of doing something else"""
     L = 16
     orc = oracle_py.load("ref")
     U = orc.rng(7).gauss_gauge_u1(L, L, 6.0)
@@ -293,7 +296,7 @@ def test_unsupported_strategies_fail_loudly(lib):
     null = os.open(os.devnull, os.O_WRONLY)
     os.dup2(null, 2)
     try:
-        h = lib.glbx_mg_setup(fine, L, L, 1, one(4), one(4), 3, 1e-2, 3, (C.c_double * 1)(5e-5), one(5), 0, -1, 0, 0, 1, 0, 0, 0)
+        h = lib.glbx_mg_setup(fine, L, L, 1, one(4), one(4), 3, 1e-2, 3, (C.c_double * 1)(5e-5), one(5), 0, -1, 0, 0, 1, 0, 0, 0, None)
     finally:
         os.dup2(saved, 2)
         os.close(null)
