@@ -16,6 +16,7 @@
 #include "dev_internal.hpp"
 #include "generic_eigenvalues.h"
 #include "generic_inverters_precond.h"
+#include "mg_complex.h"
 #include "operators.h"
 #include "operators_stencil.h"
 
@@ -35,7 +36,9 @@ enum Builtin {
   B_SV_M2MDEODOE, B_SV_M2MDTBDBT, B_SV_NORMAL_EO, B_SV_NORMAL_TB, B_SV_DAGGER_EO, B_SV_DAGGER_TB,
   // the rest of operators.h: stencils built on the host from the links (one upload), and the index operator,
   // a composition of three device operators
-  B_SYMMSHIFT_X, B_SYMMSHIFT_Y, B_STAG_2LINK, B_STAG_INDEX
+  B_SYMMSHIFT_X, B_SYMMSHIFT_Y, B_STAG_2LINK, B_STAG_INDEX,
+  // the level operators of a host multigrid struct (mg_complex.h): extra_info is a mg_operator_struct_complex*
+  B_MG_FINE, B_MG_COARSE
 };
 
 Builtin classify(void (*fn)(zcplx*, zcplx*, void*)) {
@@ -58,6 +61,8 @@ Builtin classify(void (*fn)(zcplx*, zcplx*, void*)) {
   if (fn == (F)&staggered_symmshift_y) return B_SYMMSHIFT_Y;
   if (fn == (F)&square_staggered_2linklaplace_u1) return B_STAG_2LINK;
   if (fn == (F)&staggered_index_operator) return B_STAG_INDEX;
+  if (fn == (F)&fine_square_staggered) return B_MG_FINE;
+  if (fn == (F)&coarse_square_staggered) return B_MG_COARSE;
   if (fn == (F)&apply_square_staggered_m2mdeodoe_stencil) return B_SV_M2MDEODOE;
   if (fn == (F)&apply_square_staggered_m2mdtbdbt_stencil) return B_SV_M2MDTBDBT;
   if (fn == (F)&apply_square_staggered_normal_eo_stencil) return B_SV_NORMAL_EO;
@@ -131,6 +136,23 @@ glb_operator* build(Builtin kind, void* extra) {
       GLBX(glb_op_create_stencil2d(ctx, st->clover, st->hopping, st->has_two ? st->two_link : 0,
                                    st->lat->get_lattice_dimension(0), st->lat->get_lattice_dimension(1),
                                    st->lat->get_nc(), sh, eo, df, &op));
+      break;
+    }
+    case B_MG_FINE:
+    case B_MG_COARSE: {  // mg_complex.cpp:28-92: the stencil of the current level / of the level below it
+      mg_operator_struct_complex* mg = (mg_operator_struct_complex*)extra;
+      const int level = mg->curr_level + (kind == B_MG_COARSE ? 1 : 0);
+      stencil_2d* st = mg->stencils ? mg->stencils[level] : 0;
+      if (st && st->generated) {
+        op = glb200_mg_host::upload_stencil(ctx, st);
+      } else if (level == 0 && mg->matrix_vector) {  // no stencil on the top level: its function operator (:80-84)
+        const Builtin inner = classify(mg->matrix_vector);
+        if (inner == B_NONE || inner == B_MG_FINE || inner == B_MG_COARSE || inner == B_STAG_INDEX)
+          throw Error("fine_square_staggered: the top-level operator is not a known device operator");
+        op = build(inner, mg->matrix_extra_data);
+      } else {
+        throw Error("fine_/coarse_square_staggered: the level has no generated stencil");
+      }
       break;
     }
     case B_SYMMSHIFT_X:
@@ -869,6 +891,22 @@ void precond_shim_cb(T* d_lhs, T* d_rhs, int size, void* e, inversion_verbose_st
   s->fn(s->out.data(), s->in.data(), size, s->extra, verb);
   GLBX(glb_vec_upload(ctx, Traits<T>::dtype, size, d_lhs, s->out.data()));
 }
+// mg_preconditioner exists for complex vectors only
+template <typename T>
+struct MgPrecond {
+  typedef void (*pfn)(T*, T*, int, void*, inversion_verbose_struct*);
+  static bool is(pfn) { return false; }
+  static pfn dev() { return 0; }
+};
+template <>
+struct MgPrecond<zcplx> {
+  typedef void (*pfn)(zcplx*, zcplx*, int, void*, inversion_verbose_struct*);
+  static bool is(pfn f) {
+    pfn mgp = &mg_preconditioner;
+    return f == mgp;
+  }
+  static pfn dev() { return &mg_preconditioner_dev; }
+};
 template <typename T>
 struct PrecondMap {
   typedef void (*pfn)(T*, T*, int, void*, inversion_verbose_struct*);
@@ -878,7 +916,17 @@ struct PrecondMap {
   typename GcrStruct<T>::type gcr;
   PrecondShim<T> shim;
   Shim<T> opshim;  // the stock preconditioner's own operator when that is a user host function (shim enabled)
-  PrecondMap(pfn host, void* host_info, int size) : dev(0), info(0) {
+  glb200_mg_host::Hierarchy* mgh;  // mg_preconditioner: the host hierarchy uploaded once for the whole solve
+  ~PrecondMap() { delete mgh; }
+  PrecondMap(pfn host, void* host_info, int size) : dev(0), info(0), mgh(0) {
+    if (MgPrecond<T>::is(host)) {
+      mg_precond_struct_complex* p = (mg_precond_struct_complex*)host_info;
+      mgh = new glb200_mg_host::Hierarchy(p->mgstruct);
+      mgh->set_precond(p);
+      dev = MgPrecond<T>::dev();
+      info = &mgh->pc;
+      return;
+    }
     pfn ident = &identity_preconditioner;
     pfn gcrp = &gcr_preconditioner;
     pfn mrp = &minres_preconditioner;

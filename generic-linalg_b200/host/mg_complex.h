@@ -96,4 +96,104 @@ void level_up(mg_operator_struct_complex_dev* mgstruct);
 void mg_preconditioner_dev(std::complex<double>* d_lhs, std::complex<double>* d_rhs, int size, void* extra_data,
                            inversion_verbose_struct* verb = 0);
 
+// =====================================================================================================================
+// The reference's HOST-pointer multigrid interface (multigrid/aa_mg/mg_complex.h:22-236), kept so that a driver written
+// against it compiles and runs: the structs with the reference's members, and the routines on plain host arrays.  Each
+// routine ships its operands to the device, runs the device kernel / cycle above, and ships the result back, so values
+// agree with the _dev forms; inside a drop-in solve (minv_vector_gcr_var_precond(_restart) with fine_square_staggered
+// and mg_preconditioner as its callbacks) the hierarchy is uploaded ONCE and the whole solve stays on the device.
+// Every level needs a generated stencil (the reference's explicit-projection fall-back for stencil-less levels is not
+// carried over).
+// =====================================================================================================================
+#include "coarse_stencil.h"
+
+// mg_complex.h:139-182
+struct mg_operator_struct_complex {
+  int x_fine;
+  int y_fine;
+  int n_refine;       // 1 = two levels, 2 = three levels, ...
+  int* blocksize_x;   // per refinement
+  int* blocksize_y;
+  unsigned int Nc;    // colours on the top level (square_laplace only)
+  Lattice** latt;     // one per level (n_refine + 1)
+  stencil_2d** stencils;
+  bool have_dagger_stencil;
+  stencil_2d** dagger_stencils;
+  int* n_vectors;                         // null vectors per refinement = dofs per site of the next level
+  std::complex<double>*** null_vectors;   // [refinement][vector][fine dof of that level], host arrays
+  void (*matrix_vector)(std::complex<double>*, std::complex<double>*, void*);         // top-level operator
+  void (*matrix_vector_dagger)(std::complex<double>*, std::complex<double>*, void*);
+  void* matrix_extra_data;
+  int curr_level;
+  int curr_dof_fine, curr_x_fine, curr_y_fine, curr_fine_size;
+  int curr_dof_coarse, curr_x_coarse, curr_y_coarse, curr_coarse_size;
+  dslash_tracker* dslash_count;
+};
+
+// mg_complex.h:185-236
+struct mg_precond_struct_complex {
+  minv_inverter in_smooth_type;
+  double omega_smooth;
+  int* n_pre_smooth;
+  int* n_post_smooth;
+  bool normal_eqn_mg;
+  bool normal_eqn_smooth;
+  mg_multilevel_type mlevel_type;
+  inner_solver in_solve_type;
+  int n_max;
+  int n_restart;
+  double* rel_res;
+  mg_operator_struct_complex* mgstruct;
+  void (*fine_matrix_vector)(std::complex<double>*, std::complex<double>*, void*);
+  void (*coarse_matrix_vector)(std::complex<double>*, std::complex<double>*, void*);
+  void (*fine_matrix_vector_dagger)(std::complex<double>*, std::complex<double>*, void*);
+  void (*coarse_matrix_vector_dagger)(std::complex<double>*, std::complex<double>*, void*);
+  void (*fine_matrix_vector_normal)(std::complex<double>*, std::complex<double>*, void*);
+  void (*coarse_matrix_vector_normal)(std::complex<double>*, std::complex<double>*, void*);
+  void* matrix_extra_data;
+};
+
+// mg_complex.h:24-44: the operator of the current level / of the level below it (extra_data: mg_operator_struct_complex*);
+// the daggered forms use dagger_stencils when present and epsilon / sigma_3 conjugation of the stencil otherwise
+void coarse_square_staggered(std::complex<double>* lhs, std::complex<double>* rhs, void* extra_data);
+void fine_square_staggered(std::complex<double>* lhs, std::complex<double>* rhs, void* extra_data);
+void coarse_square_staggered_dagger(std::complex<double>* lhs, std::complex<double>* rhs, void* extra_data);
+void fine_square_staggered_dagger(std::complex<double>* lhs, std::complex<double>* rhs, void* extra_data);
+void coarse_square_staggered_normal(std::complex<double>* lhs, std::complex<double>* rhs, void* extra_data);
+void fine_square_staggered_normal(std::complex<double>* lhs, std::complex<double>* rhs, void* extra_data);
+// mg_complex.h:50-68
+void block_orthonormalize(mg_operator_struct_complex* mgstruct);  // ends with block_normalize, which is not offered on its own
+void prolong(std::complex<double>* x_fine, std::complex<double>* x_coarse, mg_operator_struct_complex* mgstruct);
+void restrict(std::complex<double>* x_coarse, std::complex<double>* x_fine, mg_operator_struct_complex* mgstruct);
+void level_down(mg_operator_struct_complex* mgstruct);
+void level_up(mg_operator_struct_complex* mgstruct);
+void generate_coarse_from_fine_stencil(stencil_2d* stenc_coarse, stencil_2d* stenc_fine, mg_operator_struct_complex* mgstruct,
+                                       bool ignore_shifts);
+void generate_coarse_from_fine_stencil(stencil_2d* stenc_coarse, stencil_2d* stenc_fine, mg_operator_struct_complex* mgstruct);
+// mg_complex.h:238: one cycle, lhs = M^-1 rhs from the current level down; extra_data: mg_precond_struct_complex*
+void mg_preconditioner(std::complex<double>* lhs, std::complex<double>* rhs, int size, void* extra_data,
+                       inversion_verbose_struct* verb = 0);
+
+// the device image of a host hierarchy (used by mg_preconditioner above and by the drop-in solvers, which keep one for
+// the duration of a solve)
+#include <vector>
+namespace glb200_mg_host {
+struct Hierarchy {
+  glb_context* ctx;
+  std::vector<glb_operator*> ops;
+  std::vector<glb_mg_transfer*> trs;
+  mg_operator_struct_complex_dev mg;
+  mg_precond_struct_complex_dev pc;
+  explicit Hierarchy(mg_operator_struct_complex* host);
+  void set_precond(const mg_precond_struct_complex* p);
+  void release();
+  ~Hierarchy();
+
+ private:
+  Hierarchy(const Hierarchy&);
+  Hierarchy& operator=(const Hierarchy&);
+};
+glb_operator* upload_stencil(glb_context* ctx, stencil_2d* st);
+}  // namespace glb200_mg_host
+
 #endif

@@ -13,6 +13,7 @@
 #include "generic_inverters.h"
 #include "inverter_struct.h"
 #include "mg_complex.h"
+#include "operators.h"
 
 // null_gen.h:14-21
 enum blocking_strategy {
@@ -34,6 +35,7 @@ enum null_precond_strategy {
 // refinement (0 = top).  `opt_null` of the reference is dropped: the operator the vectors are smoothed with is
 // whatever stencils[curr_level] holds when the routine is called.
 struct null_vector_params {
+  op_type opt_null;                     // kept for source compatibility (null_gen.h:33); the set-up smooths with stencils[curr_level]
   std::vector<int> n_null_vectors;      // per refinement: smoothed vectors BEFORE the partition multiplies them
   minv_inverter null_gen;               // solver of the smoothing solve A x = -A x0 (default BiCGStab)
   null_precond_strategy null_prec;      // plain, even/odd (top/bottom below the top level) or normal equations
@@ -51,6 +53,7 @@ struct null_vector_params {
   bool quiet;  // true: skip the reference's "[L*_NULLVEC]: Pre-orthog cosines ..." lines (and their three reductions each)
 
   null_vector_params() {
+    opt_null = STAGGERED;
     null_gen = MINV_BICGSTAB;
     null_prec = NULL_PRECOND_NONE;
     null_restart = false;
@@ -84,5 +87,14 @@ void null_generate_free_dev(mg_operator_struct_complex_dev* mgstruct, null_vecto
 // (tolerance / iteration cap of this level), keep x + x0, partition, normalise, orthogonalise, normalise.
 void null_generate_random_smooth_dev(mg_operator_struct_complex_dev* mgstruct, null_vector_params* nvec_params,
                                      inversion_verbose_struct* verb, std::mt19937* generator);
+
+// ---- the reference's HOST-pointer forms (null_gen.h:66-80) on mg_operator_struct_complex: the vectors of the current
+// level go to the device, the _dev routine above runs, the vectors come back
+void null_partition_staggered(mg_operator_struct_complex* mgstruct, int num_null_vec, blocking_strategy bstrat, Lattice* Lat);
+void null_partition_coarse(mg_operator_struct_complex* mgstruct, int num_null_vec, blocking_strategy bstrat);
+void null_generate_free(mg_operator_struct_complex* mgstruct, null_vector_params* nvec_params, bool do_gauge_transform = false,
+                        std::complex<double>* gauge_trans = 0);
+void null_generate_random_smooth(mg_operator_struct_complex* mgstruct, null_vector_params* nvec_params,
+                                 inversion_verbose_struct* verb, std::mt19937* generator);
 
 #endif

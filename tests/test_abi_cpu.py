@@ -107,14 +107,20 @@ def test_every_reference_solver_and_operator_entry_point_has_a_drop_in():
                "generic_gmres.h", "generic_cg_m.h", "generic_cr_m.h", "generic_bicgstab_m.h", "generic_sor.h",
                "generic_minres.h", "generic_cg_precond.h", "generic_cg_flex_precond.h", "generic_gcr_var_precond.h",
                "generic_bicgstab_precond.h", "generic_inverters.h", "generic_inverters_precond.h", "generic_gelim.h",
-               "operator_utils/operators.h", "operator_utils/operators_stencil.h"]
+               "operator_utils/operators.h", "operator_utils/operators_stencil.h", "stencil_2d/coarse_stencil.h",
+               "multigrid/aa_mg/mg_complex.h", "multigrid/aa_mg/null_gen.h", "u1_utils/u1_utils.h", "generic_eigenvalues.h",
+               "generic_precond.h"]
+    # not offered: block_normalize on its own (block_orthonormalize ends with it); clear_stencils is a member function
+    not_offered = {"block_normalize", "clear_stencils"}
     names = set()
     for h in headers:
         txt = open(os.path.join(ref, h)).read()
         txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
         txt = re.sub(r"//[^\n]*", "", txt)
-        names.update(re.findall(r"^\s*(?:inversion_info|void|int)\s+(\w+)\s*\(", txt, flags=re.M))
-    assert len(names) > 40
+        names.update(re.findall(r"^\s*(?:inversion_info|eigenvalue_info|void|int|double|complex<double>)\s+(\w+)\s*\(", txt,
+                                flags=re.M))
+    names -= not_offered
+    assert len(names) > 80
     out = subprocess.check_output(["nm", "-DC", "--defined-only", os.path.join(PKG, "libglb200_inverters.so")]).decode()
     exported = set(re.findall(r" T (\w+)\(", out))
     missing = sorted(n for n in names if n not in exported)
