@@ -4,6 +4,7 @@
 
 #include <cmath>
 #include <fstream>
+#include <iostream>
 #include <vector>
 
 namespace {
@@ -32,7 +33,8 @@ complex<double> plaquette_at(const Links& L, int x, int y) {
 void read_gauge_u1(complex<double>* gauge_field, int x_len, int y_len, string input_file) {
   const Links L = {gauge_field, x_len, y_len};
   std::ifstream in(input_file.c_str());
-  double phase;
+  if (!in) std::cerr << "[glb200] read_gauge_u1: cannot open " << input_file << " (the field is left undefined, as in the reference)\n";
+  double phase = 0.0;
   for (int x = 0; x < x_len; x++)        // the file is x-major (its writer had y as the fast coordinate)
     for (int y = 0; y < y_len; y++)
       for (int mu = 0; mu < 2; mu++) {
