@@ -1,4 +1,4 @@
-// TEST INFRASTRUCTURE: exercises every routine of u1_utils.h and generic_vector.h on seeded inputs and prints the results
+// TEST INFRASTRUCTURE: exercises every routine of u1_utils.h, generic_vector.h and lattice_functions.h on seeded inputs and prints the results
 // with 17 digits on stderr; tests/test_reference_programs_cpu.py builds it against the reference's headers / sources and
 // against generic-linalg_b200/host and compares the two outputs line by line.
 #include <complex>
@@ -6,7 +6,10 @@
 #include <random>
 #include <vector>
 
+using namespace std;  // the reference's lattice_functions.h says complex<double> unqualified, as its programs do
+
 #include "generic_vector.h"
+#include "lattice_functions.h"
 #include "u1_utils.h"
 
 static void show(const char* what, const std::complex<double>* v, int n) {
@@ -61,6 +64,22 @@ int main(int argc, char** argv) {
   zero<double>(a.data(), V);
   show("copy", b.data(), V);
   show("zero", a.data(), V);
+  {  // lattice_functions.h: epsilon on a one-colour and sigma3 on a 4- and a 3-colour lattice, in place and out of place
+    int dims[2] = {X, Y};
+    Lattice l1(2, dims, 1), l4(2, dims, 4), l3(2, dims, 3);
+    std::vector<std::complex<double> > w(4 * V), z(4 * V);
+    gaussian<double>(w.data(), 4 * V, gen);
+    lattice_epsilon(z.data(), w.data(), &l1);
+    show("epsilon", z.data(), V);
+    lattice_epsilon(z.data(), w.data(), &l4);
+    show("epsilon4", z.data(), 4 * V);
+    lattice_sigma3(z.data(), w.data(), &l4);
+    show("sigma3", z.data(), 4 * V);
+    lattice_sigma3(w.data(), w.data(), &l4);
+    lattice_sigma3(w.data(), w.data(), &l3);
+    lattice_epsilon(w.data(), w.data(), &l3);
+    show("inplace", w.data(), 3 * V);
+  }
   std::vector<double> r(V), q(V);
   gaussian<double>(r.data(), V, gen);
   gaussian<double>(q.data(), V, gen);
