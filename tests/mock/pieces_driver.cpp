@@ -21,6 +21,8 @@ using namespace std;
 #include "coarse_stencil.h"
 #include "generic_bicgstab_l.h"
 #include "generic_cg.h"
+#include "generic_gcr.h"
+#include "generic_gmres.h"
 #include "generic_vector.h"
 #include "lattice.h"
 #ifdef PIECES_DECLARE_LATTICE_FUNCTIONS  // reference build: lattice_functions.h DEFINES its two functions non-inline and
@@ -267,6 +269,29 @@ int main(int argc, char** argv) {
     prolong(x.data(), xi.data(), &mg);
     prolong(y.data(), yi.data(), &mg);
     report(19, x, y, a.iter, c.iter);
+  }
+
+  // ---- tests/staggered_gcr_cgne_equiv/gcr_cgne_equiv.cpp:243-289 (stale in the reference tree as well): a source
+  // projected on the even sites, solved by GCR(inf), GMRES(inf), CG on D^dag D with D^dag b and with b itself.  The
+  // second column of these lines is |x_solver - x_GCR|^2 / |x_GCR|^2 (not an identity: 23 solves another system).
+  {
+    gamma_5(t.data(), b.data(), Dv);
+    for (int i = 0; i < n; i++) bp[i] = 0.5 * (b[i] + t[i]);
+    zero<double>(x.data(), n);
+    inversion_info a = minv_vector_gcr(x.data(), bp.data(), n, 100000, tol, square_staggered_u1, Dv, &verb);
+    report(20, x, x, a.iter, a.ops_count);
+    zero<double>(y.data(), n);
+    a = minv_vector_gmres(y.data(), bp.data(), n, 100000, tol, square_staggered_u1, Dv, &verb);
+    report(21, y, x, a.iter, a.ops_count);
+    gamma_5(t.data(), bp.data(), Dv);
+    square_staggered_u1(t2.data(), t.data(), Dv);
+    gamma_5(t.data(), t2.data(), Dv);
+    zero<double>(y.data(), n);
+    a = minv_vector_cg(y.data(), t.data(), n, 100000, tol, square_staggered_normal_u1, Dv, &verb);
+    report(22, y, x, a.iter, a.ops_count);
+    zero<double>(y.data(), n);
+    a = minv_vector_cg(y.data(), bp.data(), n, 100000, tol, square_staggered_normal_u1, Dv, &verb);
+    report(23, y, x, a.iter, a.ops_count);
   }
   return 0;
 }
