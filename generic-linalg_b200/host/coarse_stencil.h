@@ -4,8 +4,8 @@
 //   hopping  [c + nc*i + dir*nc*L]           dir = +x, +y, -x, -y ; L = lattice_size
 //   two_link [c + nc*i + dir*nc*L]           dir = +2x, +x+y, +2y, -x+y, -2x, -x-y, -2y, +x-y
 // apply_stencil_2d computes lhs = clover + hopping (+ two_link) + shift + eo_shift + dof_shift terms
-// for sdir == DIR_ALL (stencil_2d/coarse_stencil.cpp:29-172); single-direction applications are
-// outside the accelerated path.
+// (stencil_2d/coarse_stencil.cpp:29-172).  sdir != DIR_ALL applies one direction only (:173-393; the reference's
+// set-up probes with it, no solver uses it): served by the same kernels on a copy that keeps that one plane.
 #ifndef GLB200_COARSE_STENCIL_H
 #define GLB200_COARSE_STENCIL_H
 

@@ -128,14 +128,32 @@ glb_operator* build(Builtin kind, void* extra) {
     }
     case B_STENCIL: {
       stencil_2d* st = (stencil_2d*)extra;
-      if (st->sdir != DIR_ALL) throw Error("apply_stencil_2d: only sdir == DIR_ALL is on the accelerated path");
       if (st->lat->get_nd() != 2) throw Error("apply_stencil_2d: 2-d lattices only");
+      const int X = st->lat->get_lattice_dimension(0), Y = st->lat->get_lattice_dimension(1), nc = st->lat->get_nc();
+      if (st->sdir != DIR_ALL) {
+        // one direction of the stencil (coarse_stencil.cpp:173-393 and the same switch in the partial applies): the
+        // reference's set-up and tests use it, no solver does.  Same kernels on a copy that keeps only that plane --
+        // the site term DIR_0 carries the three shifts, a hopping / two-link direction none -- so every other term
+        // contributes an exact zero.
+        const int d = (int)st->sdir;
+        if (d < (int)DIR_0 || d > (int)DIR_XP1YM1) throw Error("apply_stencil_2d: unknown stencil direction");
+        if (d >= (int)DIR_XP2 && !st->has_two) throw Error("apply_stencil_2d: two-link direction of a one-link stencil");
+        const size_t plane = (size_t)nc * nc * X * Y;
+        std::vector<zcplx> cl(plane), hp(4 * plane), tw(st->has_two ? 8 * plane : 0);
+        if (d == (int)DIR_0) std::copy(st->clover, st->clover + plane, cl.begin());
+        else if (d < (int)DIR_XP2) std::copy(st->hopping + (d - (int)DIR_XP1) * plane, st->hopping + (d - (int)DIR_XP1 + 1) * plane, hp.begin() + (d - (int)DIR_XP1) * plane);
+        else std::copy(st->two_link + (d - (int)DIR_XP2) * plane, st->two_link + (d - (int)DIR_XP2 + 1) * plane, tw.begin() + (d - (int)DIR_XP2) * plane);
+        const bool site = d == (int)DIR_0;
+        const double sh[2] = {site ? st->shift.real() : 0.0, site ? st->shift.imag() : 0.0};
+        const double eo[2] = {site ? st->eo_shift.real() : 0.0, site ? st->eo_shift.imag() : 0.0};
+        const double df[2] = {site ? st->dof_shift.real() : 0.0, site ? st->dof_shift.imag() : 0.0};
+        GLBX(glb_op_create_stencil2d(ctx, cl.data(), hp.data(), st->has_two ? tw.data() : 0, X, Y, nc, sh, eo, df, &op));
+        break;
+      }
       const double sh[2] = {st->shift.real(), st->shift.imag()};
       const double eo[2] = {st->eo_shift.real(), st->eo_shift.imag()};
       const double df[2] = {st->dof_shift.real(), st->dof_shift.imag()};
-      GLBX(glb_op_create_stencil2d(ctx, st->clover, st->hopping, st->has_two ? st->two_link : 0,
-                                   st->lat->get_lattice_dimension(0), st->lat->get_lattice_dimension(1),
-                                   st->lat->get_nc(), sh, eo, df, &op));
+      GLBX(glb_op_create_stencil2d(ctx, st->clover, st->hopping, st->has_two ? st->two_link : 0, X, Y, nc, sh, eo, df, &op));
       break;
     }
     case B_MG_FINE:

@@ -293,5 +293,37 @@ int main(int argc, char** argv) {
     a = minv_vector_cg(y.data(), bp.data(), n, 100000, tol, square_staggered_normal_u1, Dv, &verb);
     report(23, y, x, a.iter, a.ops_count);
   }
+
+  // ---- one direction of a stencil at a time (stencil_2d::sdir; multigrid/aa_mg/tests.cpp:520-622 "piece" test): the
+  // pieces add up to the full apply -- for the full and the four partial applies, on the 4-colour one-link stencil
+  // (24.x) and on a two-link stencil of D^dag D generated by probing (25.x: 13 directions)
+  {
+    typedef void (*apply_fn)(zc*, zc*, void*);
+    const apply_fn variants[5] = {apply_stencil_2d, apply_stencil_2d_eo, apply_stencil_2d_oe, apply_stencil_2d_tb, apply_stencil_2d_bt};
+    stencil_2d S2(&lat0, get_stencil_size(STAGGERED_NORMAL));
+    generate_stencil_2d(&S2, square_staggered_normal_u1, Dv);
+    for (int which = 0; which < 2; which++) {
+      stencil_2d* st = which == 0 ? &S1 : &S2;
+      const zvec& src = which == 0 ? bi : b;
+      const int last = which == 0 ? (int)DIR_YM1 : (int)DIR_XP1YM1;
+      for (int v = 0; v < (which == 0 ? 5 : 3); v++) {
+        st->sdir = DIR_ALL;
+        variants[v](x.data(), const_cast<zc*>(src.data()), st);
+        zero<double>(y.data(), n);
+        zc piece_sum = 0.0;
+        for (int d = (int)DIR_0; d <= last; d++) {
+          st->sdir = (stencil_dir)d;
+          variants[v](t.data(), const_cast<zc*>(src.data()), st);
+          for (int i = 0; i < n; i++) {
+            y[i] += t[i];
+            piece_sum += t[i] * (double)(d + i % 3);
+          }
+        }
+        st->sdir = DIR_ALL;
+        printf("T%d.%d %.17g %.17g %.17g %.17g %.17g\n", 24 + which, v, diffnorm2sq<double>(x.data(), y.data(), n) / norm2sq<double>(b.data(), n),
+               piece_sum.real(), piece_sum.imag(), x[1].real(), x[n - 2].imag());
+      }
+    }
+  }
   return 0;
 }

@@ -151,7 +151,8 @@ def test_the_checks_of_the_two_stale_reference_programs(L, mass, tmp_path, ref_o
     interface: gamma5 / dagger / even-odd pieces of the staggered operator as functions and as stencils, e/o and t/b
     preconditioned solves against direct ones, and the 2x2-hypercube rotation into 4 internal dofs built from
     null_generate_free(BLOCK_CORNER) + block_orthonormalize + generate_coarse_from_fine_stencil + restrict / prolong.
-    Then the solver comparison of tests/staggered_gcr_cgne_equiv (:243-289): GCR, GMRES, CGNE on an even-site source.
+    Then the solver comparison of tests/staggered_gcr_cgne_equiv (:243-289): GCR, GMRES, CGNE on an even-site source,
+    and the direction-by-direction applies (sdir != DIR_ALL) of the full and the e/o, o/e, t/b, b/t stencil applies.
     Every identity holds, and both builds print the same 17-digit checksums and iteration counts"""
     subprocess.check_call(["make", "-C", MOCK_DIR], stdout=subprocess.DEVNULL)
     drv = os.path.join(MOCK_DIR, "pieces_driver.cpp")
@@ -168,12 +169,15 @@ def test_the_checks_of_the_two_stale_reference_programs(L, mass, tmp_path, ref_o
         r = subprocess.run([exe, str(L), str(mass)], capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr[-1000:]
         outs.append([l for l in r.stdout.splitlines() if l.startswith("T")])
-    assert [l.split()[0] for l in outs[1]] == ["T%d" % i for i in range(1, 24)]
+    assert [l.split()[0] for l in outs[1]] == ["T%d" % i for i in range(1, 24)] + \
+        ["T24.%d" % v for v in range(5)] + ["T25.%d" % v for v in range(3)]
     for l in outs[1][:19]:
         f = l.split()
         assert float(f[1]) < (1e-17 if f[0] in ("T5", "T13", "T19") else 1e-28), l     # the identity itself (solves: tol 1e-10)
     # the solver comparison of tests/staggered_gcr_cgne_equiv (T20-T23): GMRES and CGNE reach GCR's solution
     assert float(outs[1][20].split()[1]) < 1e-17 and float(outs[1][21].split()[1]) < 1e-15
+    # single-direction applies (stencil_2d::sdir; multigrid/aa_mg/tests.cpp:520): the pieces add up to the whole
+    assert all(float(l.split()[1]) < 1e-28 for l in outs[1][23:])
     assert outs[0] == outs[1]
 
 
