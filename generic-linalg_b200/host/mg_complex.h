@@ -162,7 +162,8 @@ void fine_square_staggered_dagger(std::complex<double>* lhs, std::complex<double
 void coarse_square_staggered_normal(std::complex<double>* lhs, std::complex<double>* rhs, void* extra_data);
 void fine_square_staggered_normal(std::complex<double>* lhs, std::complex<double>* rhs, void* extra_data);
 // mg_complex.h:50-68
-void block_orthonormalize(mg_operator_struct_complex* mgstruct);  // ends with block_normalize, which is not offered on its own
+void block_normalize(mg_operator_struct_complex* mgstruct);       // mg_complex.cpp:191
+void block_orthonormalize(mg_operator_struct_complex* mgstruct);  // mg_complex.cpp:259, ends with block_normalize
 void prolong(std::complex<double>* x_fine, std::complex<double>* x_coarse, mg_operator_struct_complex* mgstruct);
 void restrict(std::complex<double>* x_coarse, std::complex<double>* x_fine, mg_operator_struct_complex* mgstruct);
 void level_down(mg_operator_struct_complex* mgstruct);

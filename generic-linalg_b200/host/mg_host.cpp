@@ -275,6 +275,20 @@ void block_orthonormalize(mg_operator_struct_complex* mg) {
     fail_hard("block_orthonormalize", e);
   }
 }
+// mg_complex.cpp:191-256: every null vector of the current level scaled to unit norm on every block -- the
+// orthonormalisation kernel handed one vector at a time (nothing to project out, its closing normalisation remains)
+void block_normalize(mg_operator_struct_complex* mg) {
+  try {
+    glb_context* ctx = glb200_default_context();
+    DevNull N(ctx, mg);
+    for (int j = 0; j < mg->n_vectors[mg->curr_level]; j++)
+      GLBX(glb_mg_block_orthonormalize(ctx, mg->curr_x_fine, mg->curr_y_fine, mg->curr_dof_fine, mg->blocksize_x[mg->curr_level],
+                                       mg->blocksize_y[mg->curr_level], 1, (void* const*)(N.v.data() + j)));
+    N.sync_back(mg);
+  } catch (const std::exception& e) {
+    fail_hard("block_normalize", e);
+  }
+}
 // mg_complex.cpp:827-1026: P^dag A P of the fine stencil with the null vectors of the current level, written into the
 // (allocated, not yet generated) coarse stencil
 void generate_coarse_from_fine_stencil(stencil_2d* coarse, stencil_2d* fine, mg_operator_struct_complex* mg, bool ignore_shifts) {

@@ -9,6 +9,7 @@
 // (the checksum of the left-hand side, solver iteration counts) has to agree.
 //
 //   pieces_driver [L] [mass]      prints one line per identity:  T<n> <squared difference> <checksum re> <checksum im> [iters]
+#include <cmath>
 #include <complex>
 #include <cstdio>
 #include <cstdlib>
@@ -324,6 +325,27 @@ int main(int argc, char** argv) {
                piece_sum.real(), piece_sum.imag(), x[1].real(), x[n - 2].imag());
       }
     }
+  }
+
+  // ---- block_normalize on its own (mg_complex.cpp:191; the driver's PDAGP_TEST, aa_mg_square_staggered_u1.cpp:1388-1470):
+  // four gaussian vectors scaled to unit norm on every 2x2 block, then restrict -> prolong through them
+  {
+    for (int v = 0; v < 4; v++) gaussian<double>(corner[v].data(), n, gen);
+    block_normalize(&mg);
+    double worst = 0.0;
+    for (int v = 0; v < 4; v++)
+      for (int by = 0; by < L; by += 2)
+        for (int bx = 0; bx < L; bx += 2) {
+          const double nb = norm(corner[v][by * L + bx]) + norm(corner[v][by * L + bx + 1]) + norm(corner[v][(by + 1) * L + bx]) +
+                            norm(corner[v][(by + 1) * L + bx + 1]);
+          if (fabs(nb - 1.0) > worst) worst = fabs(nb - 1.0);
+        }
+    zc cs = 0.0;
+    for (int v = 0; v < 4; v++)
+      for (int i = 0; i < n; i++) cs += corner[v][i] * (double)(1 + v + i % 7);
+    restrict(xi.data(), b.data(), &mg);
+    prolong(y.data(), xi.data(), &mg);
+    printf("T26 %.3g %.17g %.17g %.17g %.17g\n", worst, cs.real(), cs.imag(), y[0].real(), y[n - 1].imag());
   }
   return 0;
 }

@@ -170,14 +170,15 @@ def test_the_checks_of_the_two_stale_reference_programs(L, mass, tmp_path, ref_o
         assert r.returncode == 0, r.stderr[-1000:]
         outs.append([l for l in r.stdout.splitlines() if l.startswith("T")])
     assert [l.split()[0] for l in outs[1]] == ["T%d" % i for i in range(1, 24)] + \
-        ["T24.%d" % v for v in range(5)] + ["T25.%d" % v for v in range(3)]
+        ["T24.%d" % v for v in range(5)] + ["T25.%d" % v for v in range(3)] + ["T26"]
     for l in outs[1][:19]:
         f = l.split()
         assert float(f[1]) < (1e-17 if f[0] in ("T5", "T13", "T19") else 1e-28), l     # the identity itself (solves: tol 1e-10)
     # the solver comparison of tests/staggered_gcr_cgne_equiv (T20-T23): GMRES and CGNE reach GCR's solution
     assert float(outs[1][20].split()[1]) < 1e-17 and float(outs[1][21].split()[1]) < 1e-15
     # single-direction applies (stencil_2d::sdir; multigrid/aa_mg/tests.cpp:520): the pieces add up to the whole
-    assert all(float(l.split()[1]) < 1e-28 for l in outs[1][23:])
+    assert all(float(l.split()[1]) < 1e-28 for l in outs[1][23:31])
+    assert float(outs[1][31].split()[1]) < 1e-14                     # block_normalize: unit norm on every block
     assert outs[0] == outs[1]
 
 
