@@ -54,6 +54,10 @@ struct mg_operator_struct_complex_dev {
   // glb200_operator_from_callback(staggered_symmshift_x / _y, &stagif)
   glb_operator* symmshift_x;
   glb_operator* symmshift_y;
+  // ---- normal-equation variants of the cycle only (mg_precond_struct_complex_dev::normal_eqn_smooth / _mg): D^dag of
+  // every level they touch -- level 0: e.g. glb200_operator_from_callback(square_staggered_dagger_u1, &stagif) (the
+  // reference applies matrix_vector_dagger there, mg_complex.cpp:119-123), below it the dagger stencils (:97-100)
+  glb_operator** dagger_stencils;
 };
 
 // lattice of level l (mg_complex.h: latt[l]): sites and dofs per site
@@ -69,7 +73,8 @@ void block_orthonormalize_dev(mg_operator_struct_complex_dev* mgstruct);
 void generate_coarse_from_fine_stencil_dev(mg_operator_struct_complex_dev* mgstruct, bool ignore_shifts);
 
 // mg_precond_struct_complex (mg_complex.h:185-236) without the function pointers: the operators are
-// the device operators of the hierarchy.  normal_eqn_smooth / normal_eqn_mg must be false.
+// the device operators of the hierarchy.  normal_eqn_smooth (the smoother runs on D^dag D z = D^dag r, CGNR) and
+// normal_eqn_mg (the whole cycle runs on D^dag D: fine, coarse and smoothing operator) need mgstruct->dagger_stencils.
 struct mg_precond_struct_complex_dev {
   minv_inverter in_smooth_type;
   double omega_smooth;
@@ -182,6 +187,7 @@ namespace glb200_mg_host {
 struct Hierarchy {
   glb_context* ctx;
   std::vector<glb_operator*> ops;
+  std::vector<glb_operator*> dag;  // D^dag per level when the host struct has them (normal-equation variants), else empty
   std::vector<glb_mg_transfer*> trs;
   mg_operator_struct_complex_dev mg;
   mg_precond_struct_complex_dev pc;

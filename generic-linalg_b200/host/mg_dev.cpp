@@ -38,12 +38,29 @@ void level_up(mg_operator_struct_complex_dev* mg) {
 
 namespace {
 
+// D^dag D of one level as a device callback (fine_ / coarse_square_staggered_normal, mg_complex.cpp:147-172: the
+// operator into a temporary, its dagger out of it)
+struct NormalOp {
+  glb_operator* d;
+  glb_operator* ddag;
+  zcplx* tmp;
+};
+void normal_apply_dev(zcplx* lhs, zcplx* rhs, void* e) {
+  NormalOp* n = (NormalOp*)e;
+  GLBX(glb_op_apply(n->d, n->tmp, rhs));
+  GLBX(glb_op_apply(n->ddag, lhs, n->tmp));
+}
+glb_operator* dagger_of_level(mg_operator_struct_complex_dev* mg, int level) {
+  glb_operator* d = mg->dagger_stencils ? mg->dagger_stencils[level] : 0;
+  if (!d) throw Error("mg_preconditioner_dev: the normal-equation variants need mgstruct->dagger_stencils on every level they touch");
+  return d;
+}
+
 void cycle(zcplx* lhs, zcplx* rhs, int size, mg_precond_struct_complex_dev* pc, inversion_verbose_struct* verb) {
   mg_operator_struct_complex_dev* mg = pc->mgstruct;
   const int lvl = mg->curr_level;
   const bool say = !pc->quiet;
-  if (pc->normal_eqn_smooth || pc->normal_eqn_mg)
-    throw Error("mg_preconditioner_dev: the normal-equation variants are not on the accelerated path");
+  const bool normal_mg = pc->normal_eqn_mg, normal_any = pc->normal_eqn_smooth || pc->normal_eqn_mg;
   if (say) std::cout << "[MG]: Entered mg_preconditioner.\n";
   glb_operator* fine = mg->stencils[lvl];
   glb_operator* coarse = mg->stencils[lvl + 1];
@@ -60,6 +77,37 @@ void cycle(zcplx* lhs, zcplx* rhs, int size, mg_precond_struct_complex_dev* pc, 
   Work<zcplx> W(B);
   Work<zcplx> Wc(Bc);
   inversion_info invif;
+  // The operators of this level (mg_complex.cpp:531-545 and the driver's wiring, aa_mg_square_staggered_u1.cpp:552-577):
+  //   A        fine_matrix_vector    D of the level, D^dag D with normal_eqn_mg
+  //   Acoarse  coarse_matrix_vector  the same one level down
+  //   S        smoothing operator    A, or D^dag D with normal_eqn_smooth (then on the right-hand side D^dag r)
+  void (*A)(zcplx*, zcplx*, void*) = apply;
+  void* A_extra = (void*)fine;
+  void (*Acoarse)(zcplx*, zcplx*, void*) = apply;
+  void* Acoarse_extra = (void*)coarse;
+  void (*S)(zcplx*, zcplx*, void*) = apply;
+  void* S_extra = (void*)fine;
+  NormalOp Nf = {fine, 0, 0}, Nc = {coarse, 0, 0};
+  glb_operator* fine_dagger = 0;
+  zcplx* rhs_smooth = 0;  // D^dag r of the CGNR smoother
+  if (normal_any) {
+    fine_dagger = dagger_of_level(mg, lvl);
+    Nf.ddag = fine_dagger;
+    Nf.tmp = W.get();
+    S = &normal_apply_dev;
+    S_extra = (void*)&Nf;
+    if (normal_mg) {
+      A = S;
+      A_extra = S_extra;
+      Nc.ddag = dagger_of_level(mg, lvl + 1);
+      Nc.tmp = Wc.get();
+      Acoarse = &normal_apply_dev;
+      Acoarse_extra = (void*)&Nc;
+    } else {
+      rhs_smooth = W.get();
+    }
+  }
+  const int smooth_ops = normal_any ? 2 : 1, coarse_ops = normal_mg ? 2 : 1;  // dslash counting, :580, :646, :803
 
   // 1. pre-smooth: z1 ~ A^-1 rhs from a zero guess, r1 = rhs - A z1   (mg_complex.cpp:548-595)
   zcplx* z1 = W.get();
@@ -74,14 +122,19 @@ void cycle(zcplx* lhs, zcplx* rhs, int size, mg_precond_struct_complex_dev* pc, 
     pre_solve.sor_omega = 1.0;
     pre_solve.minres_omega = 1.0;
     pre_solve.bicgstabl_l = pc->n_pre_smooth[lvl];
-    invif = minv_unpreconditioned_dev(z1, rhs, fine_size, pc->in_smooth_type, pre_solve, apply, (void*)fine);
+    zcplx* b_smooth = rhs;
+    if (rhs_smooth) {  // :556-560
+      GLBX(glb_op_apply(fine_dagger, rhs_smooth, rhs));
+      b_smooth = rhs_smooth;
+    }
+    invif = minv_unpreconditioned_dev(z1, b_smooth, fine_size, pc->in_smooth_type, pre_solve, S, S_extra);
     if (say) {
       printf("[L%d Presmooth]: Iterations %d Res %.8e Err N Algorithm %s\n", lvl + 1, invif.iter, sqrt(invif.resSq),
              invif.name.c_str());
       fflush(stdout);
     }
-    mg->dslash_count->presmooth[lvl] += invif.ops_count;
-    GLBX(glb_op_apply(fine, r1, z1));
+    mg->dslash_count->presmooth[lvl] += smooth_ops * invif.ops_count;
+    A(r1, z1, A_extra);
     mg->dslash_count->residual[lvl]++;
     B.sub(rhs, r1, r1);
   } else {
@@ -100,20 +153,20 @@ void cycle(zcplx* lhs, zcplx* rhs, int size, mg_precond_struct_complex_dev* pc, 
       const double tol = pc->rel_res[lvl];
       switch (pc->in_solve_type) {
         case CG:
-          invif = minv_vector_cg_dev(lhs_coarse, rhs_coarse, coarse_length, pc->n_max, tol, apply, (void*)coarse, verb);
+          invif = minv_vector_cg_dev(lhs_coarse, rhs_coarse, coarse_length, pc->n_max, tol, Acoarse, Acoarse_extra, verb);
           break;
         case GCR:
-          invif = minv_vector_gcr_restart_dev(lhs_coarse, rhs_coarse, coarse_length, pc->n_max, tol, pc->n_restart, apply,
-                                              (void*)coarse, verb);
+          invif = minv_vector_gcr_restart_dev(lhs_coarse, rhs_coarse, coarse_length, pc->n_max, tol, pc->n_restart, Acoarse,
+                                              Acoarse_extra, verb);
           break;
         case BICGSTAB:
         case BICGSTAB_L:
-          invif = minv_vector_bicgstab_dev(lhs_coarse, rhs_coarse, coarse_length, pc->n_max, tol, apply, (void*)coarse,
+          invif = minv_vector_bicgstab_dev(lhs_coarse, rhs_coarse, coarse_length, pc->n_max, tol, Acoarse, Acoarse_extra,
                                            verb);
           break;
         case CR:
-          invif = minv_vector_cr_restart_dev(lhs_coarse, rhs_coarse, coarse_length, pc->n_max, tol, pc->n_restart, apply,
-                                             (void*)coarse, verb);
+          invif = minv_vector_cr_restart_dev(lhs_coarse, rhs_coarse, coarse_length, pc->n_max, tol, pc->n_restart, Acoarse,
+                                             Acoarse_extra, verb);
           break;
         default:
           throw Error("mg_preconditioner_dev: MinRes is not on the accelerated path (use CG, GCR, BiCGStab or CR)");
@@ -121,7 +174,7 @@ void cycle(zcplx* lhs, zcplx* rhs, int size, mg_precond_struct_complex_dev* pc, 
       if (say)
         printf("[L%d]: Iterations %d RelRes %.8e Err N Algorithm %s\n", lvl + 2, invif.iter,
                sqrt(invif.resSq) / sqrt(Bc.norm2sq(rhs_coarse)), invif.name.c_str());
-      mg->dslash_count->krylov[lvl + 1] += invif.ops_count;
+      mg->dslash_count->krylov[lvl + 1] += coarse_ops * invif.ops_count;
     } else {
       // not on the coarsest level: the level below is preconditioned by its own cycle
       if (say) {
@@ -137,8 +190,8 @@ void cycle(zcplx* lhs, zcplx* rhs, int size, mg_precond_struct_complex_dev* pc, 
           throw Error("mg_preconditioner_dev: the recursive cycle is accelerated for GCR / CR (VPGCR) only");
         void (*self)(zcplx*, zcplx*, int, void*, inversion_verbose_struct*) = &mg_preconditioner_dev;
         invif = minv_vector_gcr_var_precond_restart_dev(lhs_coarse, rhs_coarse, coarse_length, pc->n_max,
-                                                        pc->rel_res[mg->curr_level - 1], pc->n_restart, apply,
-                                                        (void*)coarse, self, (void*)pc, verb);
+                                                        pc->rel_res[mg->curr_level - 1], pc->n_restart, Acoarse,
+                                                        Acoarse_extra, self, (void*)pc, verb);
         if (say)
           printf("[L%d]: Iterations %d RelRes %.8e Err N Algorithm %s\n", mg->curr_level + 1, invif.iter,
                  sqrt(invif.resSq) / sqrt(Bc.norm2sq(rhs_coarse)), invif.name.c_str());
@@ -160,9 +213,14 @@ void cycle(zcplx* lhs, zcplx* rhs, int size, mg_precond_struct_complex_dev* pc, 
   if (pc->n_post_smooth[lvl] > 0 && pc->in_smooth_type != MINV_INVALID) {
     zcplx* r2 = W.get();
     zcplx* z3 = W.get();
-    GLBX(glb_op_apply(fine, r2, lhs));
+    A(r2, lhs, A_extra);
     mg->dslash_count->residual[lvl]++;
     B.sub(rhs, r2, r2);
+    zcplx* b_smooth = r2;
+    if (rhs_smooth) {  // :779-783
+      GLBX(glb_op_apply(fine_dagger, rhs_smooth, r2));
+      b_smooth = rhs_smooth;
+    }
     minv_inverter_params post_solve;
     post_solve.tol = 1e-20;
     post_solve.max_iters = pc->n_post_smooth[lvl];
@@ -172,11 +230,11 @@ void cycle(zcplx* lhs, zcplx* rhs, int size, mg_precond_struct_complex_dev* pc, 
     post_solve.minres_omega = 1.0;
     post_solve.bicgstabl_l = pc->n_post_smooth[lvl];
     B.zero(z3);
-    invif = minv_unpreconditioned_dev(z3, r2, fine_size, pc->in_smooth_type, post_solve, apply, (void*)fine);
+    invif = minv_unpreconditioned_dev(z3, b_smooth, fine_size, pc->in_smooth_type, post_solve, S, S_extra);
     if (say)
       printf("[L%d Postsmooth]: Iterations %d Res %.8e Err N Algorithm %s\n", lvl + 1, invif.iter, sqrt(invif.resSq),
              invif.name.c_str());
-    mg->dslash_count->postsmooth[lvl] += invif.ops_count;
+    mg->dslash_count->postsmooth[lvl] += smooth_ops * invif.ops_count;
     B.add(lhs, z3, lhs);
   }
   if (say) std::cout << "[MG]: Exited mg_preconditioner.\n";

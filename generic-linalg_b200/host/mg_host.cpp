@@ -69,6 +69,15 @@ Hierarchy::Hierarchy(mg_operator_struct_complex* host) : ctx(glb200_default_cont
   try {
     for (int l = 0; l <= n; l++) ops[l] = upload_stencil(ctx, host->stencils[l]);
     for (int l = 0; l < n; l++) trs[l] = upload_transfer(ctx, host, l);
+    if (host->have_dagger_stencil && host->dagger_stencils) {
+      // D^dag per level for the normal-equation variants: on the top level the reference applies the FUNCTION
+      // matrix_vector_dagger (mg_complex.cpp:119-123), below it the dagger stencil (:97-100).  A level without either
+      // stays empty; the cycle refuses only if it needs it.
+      dag.assign(n + 1, (glb_operator*)0);
+      if (host->matrix_vector_dagger) dag[0] = glb200_operator_from_callback(host->matrix_vector_dagger, host->matrix_extra_data);
+      for (int l = dag[0] ? 1 : 0; l <= n; l++)
+        if (host->dagger_stencils[l] && host->dagger_stencils[l]->generated) dag[l] = upload_stencil(ctx, host->dagger_stencils[l]);
+    }
   } catch (...) {
     release();
     throw;
@@ -77,20 +86,19 @@ Hierarchy::Hierarchy(mg_operator_struct_complex* host) : ctx(glb200_default_cont
   mg.n_refine = n;
   mg.stencils = ops.data();
   mg.transfers = trs.data();
+  mg.dagger_stencils = dag.empty() ? 0 : dag.data();
   mg.curr_level = host->curr_level;
   mg.dslash_count = host->dslash_count;  // the caller's counters keep counting
   pc = mg_precond_struct_complex_dev();
   pc.mgstruct = &mg;
 }
 void Hierarchy::set_precond(const mg_precond_struct_complex* p) {
-  if (p->normal_eqn_mg || p->normal_eqn_smooth)
-    throw Error("mg_preconditioner: the normal-equation variants are not on the accelerated path");
   pc.in_smooth_type = p->in_smooth_type;
   pc.omega_smooth = p->omega_smooth;
   pc.n_pre_smooth = p->n_pre_smooth;
   pc.n_post_smooth = p->n_post_smooth;
-  pc.normal_eqn_mg = false;
-  pc.normal_eqn_smooth = false;
+  pc.normal_eqn_mg = p->normal_eqn_mg;
+  pc.normal_eqn_smooth = p->normal_eqn_smooth;
   pc.mlevel_type = p->mlevel_type;
   pc.in_solve_type = p->in_solve_type;
   pc.n_max = p->n_max;
@@ -102,6 +110,9 @@ void Hierarchy::set_precond(const mg_precond_struct_complex* p) {
 void Hierarchy::release() {
   for (size_t i = 0; i < ops.size(); i++)
     if (ops[i]) glb_op_destroy(ops[i]);
+  for (size_t i = 0; i < dag.size(); i++)
+    if (dag[i]) glb_op_destroy(dag[i]);
+  dag.clear();
   for (size_t i = 0; i < trs.size(); i++)
     if (trs[i]) glb_mg_transfer_destroy(trs[i]);
   ops.clear();

@@ -263,6 +263,9 @@ class RefMg:
                                 ("refmg_prolong", None, [vp, ci, vp, vp]), ("refmg_restrict", None, [vp, ci, vp, vp]),
                                 ("refmg_apply_level", None, [vp, ci, vp, vp]),
                                 ("refmg_set_precond", None, [vp, ci, ci, ci, ci, ci, ci, cd, ci]),
+                                ("refmg_apply_level_variant", None, [vp, ci, ci, vp, vp]),
+                                ("refmg_set_normal", None, [vp, ci, ci, ci]),
+                                ("refmg_counts", None, [vp, vp]),
                                 ("refmg_vcycle", None, [vp, vp, vp]),
                                 ("refmg_vpgcr", None, [vp, vp, vp, ci, cd, ci, ci, vp])):
             f = getattr(L, name)
@@ -339,10 +342,29 @@ class RefMg:
         self.L.refmg_apply_level(self.h, level, _ptr(out), _ptr(v))
         return out
 
+    def apply_level_variant(self, level, v, which):
+        """which = "dagger" / "normal": fine_ / coarse_square_staggered_dagger / _normal at that level"""
+        v = np.ascontiguousarray(v, dtype=np.complex128)
+        out = np.zeros_like(v)
+        self.L.refmg_apply_level_variant(self.h, level, dict(plain=0, dagger=1, normal=2)[which], _ptr(out), _ptr(v))
+        return out
+
     def set_precond(self, smooth="GCR", n_pre=6, n_post=6, inner="GCR", n_max=1024, n_restart=64, rel_res=1e-2,
                     recursive=False):
         self.L.refmg_set_precond(self.h, self.SMOOTH[smooth], n_pre, n_post, self.INNER[inner], n_max, n_restart,
                                  rel_res, 1 if recursive else 0)
+
+    def set_normal(self, normal_smooth, normal_mg, ignore_shifts=False):
+        """normal-equation variants of the cycle (mg_precond_struct_complex::normal_eqn_smooth / normal_eqn_mg) with
+        dagger stencils on every level, as the reference's driver wires them"""
+        self.L.refmg_set_normal(self.h, int(normal_smooth), int(normal_mg), int(ignore_shifts))
+
+    def counts(self):
+        n = self.n_refine + 1
+        out = np.zeros(4 * n, dtype=np.int32)
+        self.L.refmg_counts(self.h, _ptr(out))
+        return dict(krylov=out[:n].tolist(), presmooth=out[n:2 * n].tolist(), postsmooth=out[2 * n:3 * n].tolist(),
+                    residual=out[3 * n:].tolist())
 
     def vcycle(self, rhs):
         rhs = np.ascontiguousarray(rhs, dtype=np.complex128)

@@ -316,6 +316,23 @@ void refmg_apply_level(void* hv, int level, double* lhs, const double* rhs) {
   goto_level(h, 0);
 }
 
+// the same for the daggered (which = 1) and the normal (which = 2) operator of level l (mg_complex.cpp:93-172)
+void refmg_apply_level_variant(void* hv, int level, int which, double* lhs, const double* rhs) {
+  RefMg* h = (RefMg*)hv;
+  goto_level(h, level < h->n_refine ? level : h->n_refine - 1);
+  void* e = (void*)&h->mg;
+  if (level < h->n_refine) {
+    if (which == 1) fine_square_staggered_dagger((zc*)lhs, (zc*)rhs, e);
+    else if (which == 2) fine_square_staggered_normal((zc*)lhs, (zc*)rhs, e);
+    else fine_square_staggered((zc*)lhs, (zc*)rhs, e);
+  } else {
+    if (which == 1) coarse_square_staggered_dagger((zc*)lhs, (zc*)rhs, e);
+    else if (which == 2) coarse_square_staggered_normal((zc*)lhs, (zc*)rhs, e);
+    else coarse_square_staggered((zc*)lhs, (zc*)rhs, e);
+  }
+  goto_level(h, 0);
+}
+
 // mg_precond_struct_complex settings (mg_complex.h:185-236); smoother / inner solver enums are the reference's
 void refmg_set_precond(void* hv, int in_smooth_type, int n_pre, int n_post, int in_solve_type, int n_max, int n_restart,
                        double rel_res, int mlevel_type) {
@@ -329,6 +346,60 @@ void refmg_set_precond(void* hv, int in_smooth_type, int n_pre, int n_post, int 
     h->n_pre[i] = n_pre;
     h->n_post[i] = n_post;
     h->rel_res[i] = rel_res;
+  }
+}
+
+// The normal-equation variants of the cycle, wired as the reference's driver does (aa_mg_square_staggered_u1.cpp:550-577,
+// :656-681, :990-1116): dagger stencils on every level -- the daggered staggered stencil on top, its Galerkin products
+// below, with the same treatment of the mass as the stencils of this handle (ignore_shifts of refmg_create2) -- and
+//   normal_smooth  the smoother runs on D^dag D z = D^dag r (CGNR)
+//   normal_mg      fine, coarse and smoothing operator are D^dag D of their level
+void refmg_set_normal(void* hv, int normal_smooth, int normal_mg, int ignore_shifts) {
+  RefMg* h = (RefMg*)hv;
+  mg_operator_struct_complex& mg = h->mg;
+  goto_level(h, 0);
+  if (!mg.have_dagger_stencil) {
+    mg.have_dagger_stencil = true;
+    mg.dagger_stencils = new stencil_2d*[h->n_refine + 1];
+    for (int i = 0; i <= h->n_refine; i++) mg.dagger_stencils[i] = new stencil_2d(mg.latt[i], 1);
+    const double mass = h->stagif.mass;
+    if (ignore_shifts) h->stagif.mass = 0.0;
+    get_square_staggered_dagger_u1_stencil(mg.dagger_stencils[0], &h->stagif);
+    h->stagif.mass = mass;
+    if (ignore_shifts) mg.dagger_stencils[0]->shift = mass;
+    for (int n = 0; n < h->n_refine; n++) {
+      generate_coarse_from_fine_stencil(mg.dagger_stencils[n + 1], mg.dagger_stencils[n], &mg, ignore_shifts != 0);
+      if (ignore_shifts) mg.dagger_stencils[n + 1]->shift = mg.dagger_stencils[n]->shift;
+      if (n != h->n_refine - 1) level_down(&mg);
+    }
+    goto_level(h, 0);
+  }
+  mg_precond_struct_complex& p = h->pre;
+  p.normal_eqn_smooth = normal_smooth != 0;
+  p.normal_eqn_mg = normal_mg != 0;
+  if (normal_mg) {
+    p.coarse_matrix_vector = coarse_square_staggered_normal;
+    p.fine_matrix_vector = fine_square_staggered_normal;
+    p.coarse_matrix_vector_dagger = coarse_square_staggered_normal;
+    p.fine_matrix_vector_dagger = fine_square_staggered_normal;
+  } else {
+    p.coarse_matrix_vector = coarse_square_staggered;
+    p.fine_matrix_vector = fine_square_staggered;
+    p.coarse_matrix_vector_dagger = coarse_square_staggered_dagger;
+    p.fine_matrix_vector_dagger = fine_square_staggered_dagger;
+  }
+  p.coarse_matrix_vector_normal = coarse_square_staggered_normal;
+  p.fine_matrix_vector_normal = fine_square_staggered_normal;
+}
+// dslash_tracker of the handle (mg_complex.h:104-136): out[4][n_refine+1] = krylov, presmooth, postsmooth, residual
+void refmg_counts(void* hv, int* out) {
+  RefMg* h = (RefMg*)hv;
+  const int n = h->n_refine + 1;
+  for (int i = 0; i < n; i++) {
+    out[i] = h->mg.dslash_count->krylov[i];
+    out[n + i] = h->mg.dslash_count->presmooth[i];
+    out[2 * n + i] = h->mg.dslash_count->postsmooth[i];
+    out[3 * n + i] = h->mg.dslash_count->residual[i];
   }
 }
 

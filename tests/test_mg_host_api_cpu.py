@@ -98,6 +98,62 @@ def test_hierarchy_from_given_null_vectors(ours, ignore_shifts):
         assert rel_err(xo, xr) < 1e-10 and abs(io["resSq"] - ir["resSq"]) <= 1e-6 * ir["resSq"]
 
 
+@pytest.mark.parametrize("normal_smooth,normal_mg", [(True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("levels", [1, 2])
+def test_normal_equation_variants_of_the_cycle(ours, normal_smooth, normal_mg, levels):
+    """mg_precond_struct_complex::normal_eqn_smooth (CGNR smoother: D^dag D z = D^dag r) and normal_eqn_mg (the cycle on
+    D^dag D, fine and coarse) with dagger stencils on every level, wired as the reference's driver does
+    (aa_mg_square_staggered_u1.cpp:550-577, :656-681, :990-1116; mg_complex.cpp:537-580, :779-803): the cycle, the
+    operator counts it books, and -- for the CGNR smoother -- the preconditioned solve"""
+    orc = oracle_py.load("ref")
+    L, mass = 16, 0.05
+    U, b, vecs = _raw_null_vectors(orc, L, mass, 2)
+    blocks, nvecs, nulls = [4], [4], [vecs]
+    if levels == 2:
+        rng = np.random.default_rng(3)
+        lvl1 = [rng.standard_normal(4 * 4 * 4) + 1j * rng.standard_normal(4 * 4 * 4) for _ in range(2)]
+        idx = np.arange(4 * 4 * 4)
+        top = (idx % 4) < 2
+        blocks, nvecs, nulls = [4, 2], [4, 4], [vecs, [np.where(top, v, 0) for v in lvl1] + [np.where(~top, v, 0) for v in lvl1]]
+    with quiet_stdout():
+        mo = oracle_py.RefMg(ours, L, L, U, mass, blocks, nvecs, nulls)
+        mr = oracle_py.RefMg(orc, L, L, U, mass, blocks, nvecs, nulls)
+        for m in (mo, mr):
+            m.set_normal(normal_smooth, normal_mg)
+    rng = np.random.default_rng(1)
+    for lvl in range(levels + 1):                                   # fine_ / coarse_square_staggered_dagger / _normal
+        X, Y, nc = mr.dims(lvl)
+        f = rng.standard_normal(X * Y * nc) + 1j * rng.standard_normal(X * Y * nc)
+        for which in ("dagger", "normal"):
+            assert rel_err(mo.apply_level_variant(lvl, f, which), mr.apply_level_variant(lvl, f, which)) < 1e-13
+    # With normal_eqn_mg the cycle solves on D^dag D (condition number ~ 1/m^2 squared) and amplifies rounding: the
+    # REFERENCE run twice with null vectors that differ by 1e-15 relative gives cycles that differ by 3e-8 (GCR) to 1e-7
+    # (CG inside); the level operators above agree to 1e-16, the operator counts exactly.
+    tol = 5e-6 if normal_mg else 1e-10
+    # CG as the coarse solver only where the coarse operator is D^dag D
+    for cfg in (dict(smooth="CG", n_pre=3, n_post=3, inner="CG" if normal_mg else "GCR", rel_res=1e-3),
+                dict(smooth="GCR", n_pre=2, n_post=4, inner="GCR", rel_res=1e-2),
+                dict(smooth="CG", n_pre=2, n_post=2, inner="GCR", rel_res=1e-2, recursive=True)):
+        if cfg.get("recursive") and levels == 1:
+            continue
+        mo.set_precond(**cfg)
+        mr.set_precond(**cfg)
+        before_o, before_r = mo.counts(), mr.counts()
+        with quiet_stdout():
+            vo, vr = mo.vcycle(b), mr.vcycle(b)
+        assert rel_err(vo, vr) < tol, cfg
+        delta = lambda a, z: {k: [y - x for x, y in zip(a[k], z[k])] for k in a}
+        assert delta(before_o, mo.counts()) == delta(before_r, mr.counts()), cfg
+    if not normal_mg:
+        mo.set_precond(smooth="CG", n_pre=3, n_post=3, inner="GCR", rel_res=1e-2)
+        mr.set_precond(smooth="CG", n_pre=3, n_post=3, inner="GCR", rel_res=1e-2)
+        with quiet_stdout():
+            xo, io = mo.vpgcr(b, max_iter=1000, eps=5e-7, restart_freq=64)
+            xr, ir = mr.vpgcr(b, max_iter=1000, eps=5e-7, restart_freq=64)
+        assert io["success"] and (io["iter"], io["ops_count"]) == (ir["iter"], ir["ops_count"])
+        assert rel_err(xo, xr) < 1e-9
+
+
 @pytest.mark.parametrize("kw", [dict(seed=11), dict(seed=5, do_ortho_eo=True), dict(seed=8, null_prec=2, null_gen="CG", tol=1e-3),
                                 dict(seed=12, bstrat=2, max_iter=60), dict(seed=14, bstrat=3, max_iter=60), dict(do_free=True)])
 def test_null_vector_generation_through_the_host_interface(ours, kw):
