@@ -38,7 +38,7 @@ enum Builtin {
   // a composition of three device operators
   B_SYMMSHIFT_X, B_SYMMSHIFT_Y, B_STAG_2LINK, B_STAG_INDEX,
   // the level operators of a host multigrid struct (mg_complex.h): extra_info is a mg_operator_struct_complex*
-  B_MG_FINE, B_MG_COARSE
+  B_MG_FINE, B_MG_COARSE, B_MG_FINE_DAGGER, B_MG_COARSE_DAGGER, B_MG_FINE_NORMAL, B_MG_COARSE_NORMAL
 };
 
 Builtin classify(void (*fn)(zcplx*, zcplx*, void*)) {
@@ -63,6 +63,10 @@ Builtin classify(void (*fn)(zcplx*, zcplx*, void*)) {
   if (fn == (F)&staggered_index_operator) return B_STAG_INDEX;
   if (fn == (F)&fine_square_staggered) return B_MG_FINE;
   if (fn == (F)&coarse_square_staggered) return B_MG_COARSE;
+  if (fn == (F)&fine_square_staggered_dagger) return B_MG_FINE_DAGGER;
+  if (fn == (F)&coarse_square_staggered_dagger) return B_MG_COARSE_DAGGER;
+  if (fn == (F)&fine_square_staggered_normal) return B_MG_FINE_NORMAL;
+  if (fn == (F)&coarse_square_staggered_normal) return B_MG_COARSE_NORMAL;
   if (fn == (F)&apply_square_staggered_m2mdeodoe_stencil) return B_SV_M2MDEODOE;
   if (fn == (F)&apply_square_staggered_m2mdtbdbt_stencil) return B_SV_M2MDTBDBT;
   if (fn == (F)&apply_square_staggered_normal_eo_stencil) return B_SV_NORMAL_EO;
@@ -165,7 +169,7 @@ glb_operator* build(Builtin kind, void* extra) {
         op = glb200_mg_host::upload_stencil(ctx, st);
       } else if (level == 0 && mg->matrix_vector) {  // no stencil on the top level: its function operator (:80-84)
         const Builtin inner = classify(mg->matrix_vector);
-        if (inner == B_NONE || inner == B_MG_FINE || inner == B_MG_COARSE || inner == B_STAG_INDEX)
+        if (inner == B_NONE || (inner >= B_MG_FINE && inner <= B_MG_COARSE_NORMAL) || inner == B_STAG_INDEX)
           throw Error("fine_square_staggered: the top-level operator is not a known device operator");
         op = build(inner, mg->matrix_extra_data);
       } else {
@@ -173,6 +177,26 @@ glb_operator* build(Builtin kind, void* extra) {
       }
       break;
     }
+    case B_MG_FINE_DAGGER:
+    case B_MG_COARSE_DAGGER: {  // mg_complex.cpp:93-133: the top level applies the FUNCTION matrix_vector_dagger, the levels
+                                // below it their dagger stencil (the prolong / restrict fall-back of :101-111 is not offered)
+      mg_operator_struct_complex* mg = (mg_operator_struct_complex*)extra;
+      const int level = mg->curr_level + (kind == B_MG_COARSE_DAGGER ? 1 : 0);
+      if (level == 0) {
+        const Builtin inner = mg->matrix_vector_dagger ? classify(mg->matrix_vector_dagger) : B_NONE;
+        if (inner == B_NONE || (inner >= B_MG_FINE && inner <= B_MG_COARSE_NORMAL) || inner == B_STAG_INDEX)
+          throw Error("fine_square_staggered_dagger: matrix_vector_dagger is not a known device operator");
+        op = build(inner, mg->matrix_extra_data);
+      } else {
+        stencil_2d* st = (mg->have_dagger_stencil && mg->dagger_stencils) ? mg->dagger_stencils[level] : 0;
+        if (!st || !st->generated) throw Error("fine_/coarse_square_staggered_dagger: the level has no generated dagger stencil");
+        op = glb200_mg_host::upload_stencil(ctx, st);
+      }
+      break;
+    }
+    case B_MG_FINE_NORMAL:
+    case B_MG_COARSE_NORMAL:
+      throw Error("fine_/coarse_square_staggered_normal is a composition of two device operators (lease)");
     case B_SYMMSHIFT_X:
     case B_SYMMSHIFT_Y:
     case B_STAG_2LINK: {
@@ -252,15 +276,41 @@ bool cacheable(Builtin k) { return k >= B_LAPLACE_NC && k <= B_STAG_M2MDEODOE_U1
 // staggered_index_operator (operators.cpp:782-835) on the device: lhs = i D_0 rhs - (m i/2) S_x S_y rhs
 // + (m i/2) S_y S_x rhs with D_0 the massless staggered operator and S the symmetric shifts -- five applies and
 // three axpys of existing kernels, in the reference's order.  Usable as a device callback (extra = IndexOp*).
-struct IndexOp {
+struct Composite {  // a composition of device operators behind ONE device callback (index_apply_dev)
+  virtual void apply(zcplx* lhs, zcplx* rhs) = 0;
+  virtual ~Composite() {}
+};
+struct IndexOp : Composite {
   glb_context* ctx;
-  glb_operator *D0, *Sx, *Sy;
+  glb_operator *D0, *Sx, *Sy;  // D0 belongs to the lease
   zcplx *t1, *t2;
   double mass;
   size_t n;
+  void apply(zcplx* lhs, zcplx* rhs);
+  ~IndexOp() {
+    glb_op_destroy(Sx);
+    glb_op_destroy(Sy);
+    if (t1) glb_vec_free(ctx, t1);
+    if (t2) glb_vec_free(ctx, t2);
+  }
 };
-void index_apply_dev(zcplx* lhs, zcplx* rhs, void* e) {
-  IndexOp* o = (IndexOp*)e;
+// fine_ / coarse_square_staggered_normal (mg_complex.cpp:135-172): the level operator into a temporary, its dagger out
+struct ChainOp : Composite {
+  glb_context* ctx;
+  glb_operator *first, *second;  // `first` belongs to the lease
+  zcplx* tmp;
+  void apply(zcplx* lhs, zcplx* rhs) {
+    GLBX(glb_op_apply(first, tmp, rhs));
+    GLBX(glb_op_apply(second, lhs, tmp));
+  }
+  ~ChainOp() {
+    glb_op_destroy(second);
+    if (tmp) glb_vec_free(ctx, tmp);
+  }
+};
+void index_apply_dev(zcplx* lhs, zcplx* rhs, void* e) { ((Composite*)e)->apply(lhs, rhs); }
+void IndexOp::apply(zcplx* lhs, zcplx* rhs) {
+  IndexOp* o = this;
   Blas<zcplx> B = {o->ctx, o->n};
   GLBX(glb_op_apply(o->D0, o->t1, rhs));
   B.zero(lhs);
@@ -277,16 +327,10 @@ void index_apply_dev(zcplx* lhs, zcplx* rhs, void* e) {
 struct OpLease {  // operator for the duration of one call
   glb_operator* op;
   bool owned;
-  IndexOp* comp;  // set for the index operator: `op` is then its D_0 (sizes), the callback is index_apply_dev
+  Composite* comp;  // set for a composition: `op` is then its first operator (sizes), the callback is index_apply_dev
   OpLease() : op(0), owned(false), comp(0) {}
   ~OpLease() {
-    if (comp) {
-      glb_op_destroy(comp->Sx);
-      glb_op_destroy(comp->Sy);
-      if (comp->t1) glb_vec_free(comp->ctx, comp->t1);
-      if (comp->t2) glb_vec_free(comp->ctx, comp->t2);
-      delete comp;
-    }
+    delete comp;
     if (op && owned) glb_op_destroy(op);
   }
 };
@@ -301,6 +345,21 @@ struct CompositeCallback<zcplx> {
 };
 
 void lease(Builtin kind, void* extra, OpLease* out) {
+  if (kind == B_MG_FINE_NORMAL || kind == B_MG_COARSE_NORMAL) {
+    const bool fine = (kind == B_MG_FINE_NORMAL);
+    ChainOp* c = new ChainOp();
+    c->ctx = glb200_default_context();
+    c->first = c->second = 0;
+    c->tmp = 0;
+    out->comp = c;
+    out->op = c->first = build(fine ? B_MG_FINE : B_MG_COARSE, extra);
+    out->owned = true;
+    c->second = build(fine ? B_MG_FINE_DAGGER : B_MG_COARSE_DAGGER, extra);
+    void* p = 0;
+    GLBX(glb_vec_alloc(c->ctx, GLB_COMPLEX, glb_op_local_size(c->first), &p));
+    c->tmp = (zcplx*)p;
+    return;
+  }
   if (kind == B_STAG_INDEX) {
     staggered_u1_op* s = (staggered_u1_op*)extra;
     staggered_u1_op nomass = *s;

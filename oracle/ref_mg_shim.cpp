@@ -424,11 +424,13 @@ void refmg_vpgcr(void* hv, double* phi, const double* phi0, int max_iter, double
   verb.precond_verb_prefix = "";
   const int n = h->mg.curr_fine_size;
   inversion_info inf;
+  // aa_mg_square_staggered_u1.cpp:1696-1705: with normal_eqn_mg the outer operator is D^dag D as well
+  void (*fine_op)(zc*, zc*, void*) = h->pre.normal_eqn_mg ? fine_square_staggered_normal : fine_square_staggered;
   if (restart_freq > 0)
-    inf = minv_vector_gcr_var_precond_restart((zc*)phi, (zc*)phi0, n, max_iter, res, restart_freq, fine_square_staggered,
+    inf = minv_vector_gcr_var_precond_restart((zc*)phi, (zc*)phi0, n, max_iter, res, restart_freq, fine_op,
                                               (void*)&h->mg, mg_preconditioner, (void*)&h->pre, &verb);
   else
-    inf = minv_vector_gcr_var_precond((zc*)phi, (zc*)phi0, n, max_iter, res, fine_square_staggered, (void*)&h->mg,
+    inf = minv_vector_gcr_var_precond((zc*)phi, (zc*)phi0, n, max_iter, res, fine_op, (void*)&h->mg,
                                       mg_preconditioner, (void*)&h->pre, &verb);
   out[0] = inf.resSq;
   out[1] = inf.iter;

@@ -144,14 +144,18 @@ def test_normal_equation_variants_of_the_cycle(ours, normal_smooth, normal_mg, l
         assert rel_err(vo, vr) < tol, cfg
         delta = lambda a, z: {k: [y - x for x, y in zip(a[k], z[k])] for k in a}
         assert delta(before_o, mo.counts()) == delta(before_r, mr.counts()), cfg
-    if not normal_mg:
-        mo.set_precond(smooth="CG", n_pre=3, n_post=3, inner="GCR", rel_res=1e-2)
-        mr.set_precond(smooth="CG", n_pre=3, n_post=3, inner="GCR", rel_res=1e-2)
-        with quiet_stdout():
-            xo, io = mo.vpgcr(b, max_iter=1000, eps=5e-7, restart_freq=64)
-            xr, ir = mr.vpgcr(b, max_iter=1000, eps=5e-7, restart_freq=64)
-        assert io["success"] and (io["iter"], io["ops_count"]) == (ir["iter"], ir["ops_count"])
-        assert rel_err(xo, xr) < 1e-9
+    # the preconditioned solve; with normal_eqn_mg its operator is fine_square_staggered_normal (driver :1696-1705),
+    # which the drop-in runs as a composition of the level operator and its dagger on the device
+    mo.set_precond(smooth="CG", n_pre=3, n_post=3, inner="GCR", rel_res=1e-2)
+    mr.set_precond(smooth="CG", n_pre=3, n_post=3, inner="GCR", rel_res=1e-2)
+    with quiet_stdout():
+        xo, io = mo.vpgcr(b, max_iter=1000, eps=5e-7, restart_freq=64)
+        xr, ir = mr.vpgcr(b, max_iter=1000, eps=5e-7, restart_freq=64)
+    assert io["success"] and ir["success"]
+    if normal_mg:
+        assert abs(io["iter"] - ir["iter"]) <= 1 and rel_err(xo, xr) < 1e-4
+    else:
+        assert (io["iter"], io["ops_count"]) == (ir["iter"], ir["ops_count"]) and rel_err(xo, xr) < 1e-9
 
 
 @pytest.mark.parametrize("kw", [dict(seed=11), dict(seed=5, do_ortho_eo=True), dict(seed=8, null_prec=2, null_gen="CG", tol=1e-3),
