@@ -157,6 +157,10 @@ void fail_hard(const char* what, const std::exception& e) {
 
 void apply_level_stencil(zcplx* lhs, zcplx* rhs, mg_operator_struct_complex* mg, int level, bool dagger) {
   stencil_2d* st = 0;
+  if (dagger && level == 0 && mg->matrix_vector_dagger) {  // mg_complex.cpp:119-123: the top level daggers by FUNCTION
+    mg->matrix_vector_dagger(lhs, rhs, mg->matrix_extra_data);
+    return;
+  }
   if (dagger && mg->have_dagger_stencil && mg->dagger_stencils && mg->dagger_stencils[level] && mg->dagger_stencils[level]->generated)
     st = mg->dagger_stencils[level];
   if (st) {
