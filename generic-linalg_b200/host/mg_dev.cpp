@@ -168,8 +168,11 @@ void cycle(zcplx* lhs, zcplx* rhs, int size, mg_precond_struct_complex_dev* pc, 
           invif = minv_vector_cr_restart_dev(lhs_coarse, rhs_coarse, coarse_length, pc->n_max, tol, pc->n_restart, Acoarse,
                                              Acoarse_extra, verb);
           break;
+        case MINRES:  // mg_complex.cpp:622-624
+          invif = minv_vector_minres_dev(lhs_coarse, rhs_coarse, coarse_length, pc->n_max, tol, Acoarse, Acoarse_extra, verb);
+          break;
         default:
-          throw Error("mg_preconditioner_dev: MinRes is not on the accelerated path (use CG, GCR, BiCGStab or CR)");
+          throw Error("mg_preconditioner_dev: unknown coarse solver");
       }
       if (say)
         printf("[L%d]: Iterations %d RelRes %.8e Err N Algorithm %s\n", lvl + 2, invif.iter,

@@ -82,7 +82,8 @@ def test_hierarchy_from_given_null_vectors(ours, ignore_shifts):
     assert np.array_equal(mo.restrict(0, f), mr.restrict(0, f))
     assert np.array_equal(mo.apply_level(0, f), mr.apply_level(0, f))   # fine_square_staggered
     assert rel_err(mo.apply_level(1, c), mr.apply_level(1, c)) < 1e-13  # coarse_square_staggered
-    for cfg in (dict(), dict(smooth="BICGSTAB", n_pre=3, n_post=2, inner="CG", rel_res=1e-3)):
+    for cfg in (dict(), dict(smooth="BICGSTAB", n_pre=3, n_post=2, inner="CG", rel_res=1e-3),
+                dict(smooth="MINRES", n_pre=4, n_post=4, inner="MINRES", rel_res=1e-1)):
         mo.set_precond(**cfg)
         mr.set_precond(**cfg)
         with quiet_stdout():
