@@ -189,12 +189,21 @@ void cycle(zcplx* lhs, zcplx* rhs, int size, mg_precond_struct_complex_dev* pc, 
       if (pc->in_solve_type == NONE || pc->mlevel_type == MLEVEL_SMOOTH || pc->in_solve_type == MINRES) {
         cycle(lhs_coarse, rhs_coarse, coarse_length, pc, verb);
       } else {
-        if (pc->in_solve_type != GCR && pc->in_solve_type != CR)
-          throw Error("mg_preconditioner_dev: the recursive cycle is accelerated for GCR / CR (VPGCR) only");
+        // mg_complex.cpp:672-695: the level below solved by a flexible Krylov method preconditioned by its own cycle --
+        // flexible CG, VPGCR (also standing in for CR) or preconditioned BiCGStab (also for BiCGStab-l)
         void (*self)(zcplx*, zcplx*, int, void*, inversion_verbose_struct*) = &mg_preconditioner_dev;
-        invif = minv_vector_gcr_var_precond_restart_dev(lhs_coarse, rhs_coarse, coarse_length, pc->n_max,
-                                                        pc->rel_res[mg->curr_level - 1], pc->n_restart, Acoarse,
-                                                        Acoarse_extra, self, (void*)pc, verb);
+        const double tol_rec = pc->rel_res[mg->curr_level - 1];
+        if (pc->in_solve_type == CG)
+          invif = minv_vector_cg_flex_precond_restart_dev(lhs_coarse, rhs_coarse, coarse_length, pc->n_max, tol_rec,
+                                                          pc->n_restart, Acoarse, Acoarse_extra, self, (void*)pc, verb);
+        else if (pc->in_solve_type == GCR || pc->in_solve_type == CR)
+          invif = minv_vector_gcr_var_precond_restart_dev(lhs_coarse, rhs_coarse, coarse_length, pc->n_max, tol_rec,
+                                                          pc->n_restart, Acoarse, Acoarse_extra, self, (void*)pc, verb);
+        else if (pc->in_solve_type == BICGSTAB || pc->in_solve_type == BICGSTAB_L)
+          invif = minv_vector_bicgstab_precond_dev(lhs_coarse, rhs_coarse, coarse_length, pc->n_max, tol_rec, Acoarse,
+                                                   Acoarse_extra, self, (void*)pc, verb);
+        else
+          throw Error("mg_preconditioner_dev: unknown inner solver of the recursive cycle");
         if (say)
           printf("[L%d]: Iterations %d RelRes %.8e Err N Algorithm %s\n", mg->curr_level + 1, invif.iter,
                  sqrt(invif.resSq) / sqrt(Bc.norm2sq(rhs_coarse)), invif.name.c_str());

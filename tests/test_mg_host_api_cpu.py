@@ -111,8 +111,10 @@ def test_normal_equation_variants_of_the_cycle(ours, normal_smooth, normal_mg, l
     U, b, vecs = _raw_null_vectors(orc, L, mass, 2)
     blocks, nvecs, nulls = [4], [4], [vecs]
     if levels == 2:
-        rng = np.random.default_rng(3)
-        lvl1 = [rng.standard_normal(4 * 4 * 4) + 1j * rng.standard_normal(4 * 4 * 4) for _ in range(2)]
+        with quiet_stdout():
+            one = oracle_py.RefMg(orc, L, L, U, mass, [4], [4], [vecs])
+        _, _, more = _raw_null_vectors(orc, L, mass, 2, seed=99)      # level-1 null vectors: restricted smooth vectors
+        lvl1 = [one.restrict(0, more[0] + more[2]), one.restrict(0, more[1] + more[3])]
         idx = np.arange(4 * 4 * 4)
         top = (idx % 4) < 2
         blocks, nvecs, nulls = [4, 2], [4, 4], [vecs, [np.where(top, v, 0) for v in lvl1] + [np.where(~top, v, 0) for v in lvl1]]
@@ -135,14 +137,31 @@ def test_normal_equation_variants_of_the_cycle(ours, normal_smooth, normal_mg, l
     # CG as the coarse solver only where the coarse operator is D^dag D
     for cfg in (dict(smooth="CG", n_pre=3, n_post=3, inner="CG" if normal_mg else "GCR", rel_res=1e-3),
                 dict(smooth="GCR", n_pre=2, n_post=4, inner="GCR", rel_res=1e-2),
-                dict(smooth="CG", n_pre=2, n_post=2, inner="GCR", rel_res=1e-2, recursive=True)):
+                dict(smooth="CG", n_pre=2, n_post=2, inner="GCR", rel_res=1e-2, recursive=True),
+                # the other recursions of mg_complex.cpp:672-695: flexible CG (on D^dag D only), preconditioned BiCGStab
+                dict(smooth="CG", n_pre=2, n_post=2, inner="CG", rel_res=1e-2, recursive=True, only_normal_mg=True),
+                dict(smooth="CG", n_pre=2, n_post=2, inner="BICGSTAB", rel_res=1e-3, recursive=True, erratic=True)):
+        cfg = dict(cfg)
+        if cfg.pop("only_normal_mg", False) and not normal_mg:
+            continue
         if cfg.get("recursive") and levels == 1:
             continue
+        if cfg.get("erratic") and normal_mg:        # BiCGStab on D^dag D runs into n_max on both sides
+            continue
+        erratic = cfg.pop("erratic", False)
         mo.set_precond(**cfg)
         mr.set_precond(**cfg)
         before_o, before_r = mo.counts(), mr.counts()
         with quiet_stdout():
             vo, vr = mo.vcycle(b), mr.vcycle(b)
+        if erratic:
+            # BiCGStab preconditioned by a cycle that itself stops on a tolerance: the REFERENCE run twice with null vectors
+            # 1e-15 apart differs by 1e-3 relative here (5e-2 at rel_res = 0.1) and books different operator counts.  What
+            # can be held: both are equally good approximate inverses, and they agree to the accuracy of the inner solves.
+            A = (lambda m, v: m.apply_level_variant(0, v, "normal")) if normal_mg else (lambda m, v: m.apply_level(0, v))
+            ro, rr = rel_err(A(mo, vo), b), rel_err(A(mr, vr), b)
+            assert ro < 1.0 and ro < 3 * rr + 1e-3 and rel_err(vo, vr) < 5e-2, (cfg, ro, rr)
+            continue
         assert rel_err(vo, vr) < tol, cfg
         delta = lambda a, z: {k: [y - x for x, y in zip(a[k], z[k])] for k in a}
         assert delta(before_o, mo.counts()) == delta(before_r, mr.counts()), cfg
