@@ -998,7 +998,7 @@ struct PrecondMap {
   PrecondMap(pfn host, void* host_info, int size) : dev(0), info(0), mgh(0) {
     if (MgPrecond<T>::is(host)) {
       mg_precond_struct_complex* p = (mg_precond_struct_complex*)host_info;
-      mgh = new glb200_mg_host::Hierarchy(p->mgstruct);
+      mgh = new glb200_mg_host::Hierarchy(p->mgstruct, p->normal_eqn_smooth || p->normal_eqn_mg);
       mgh->set_precond(p);
       dev = MgPrecond<T>::dev();
       info = &mgh->pc;

@@ -191,7 +191,8 @@ struct Hierarchy {
   std::vector<glb_mg_transfer*> trs;
   mg_operator_struct_complex_dev mg;
   mg_precond_struct_complex_dev pc;
-  explicit Hierarchy(mg_operator_struct_complex* host);
+  // with_dagger: also D^dag of every level (the normal-equation variants of the cycle need them)
+  explicit Hierarchy(mg_operator_struct_complex* host, bool with_dagger = false);
   void set_precond(const mg_precond_struct_complex* p);
   void release();
   ~Hierarchy();

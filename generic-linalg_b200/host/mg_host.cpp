@@ -53,6 +53,41 @@ glb_operator* upload_stencil(glb_context* ctx, stencil_2d* st) {
   return op;
 }
 
+// The adjoint of a generated stencil as a device operator: entry ((x,r),(x+d,c)) of D^dag is the conjugate of entry
+// ((x+d,c),(x,r)) of D, i.e. of the opposite direction's matrix at the neighbour, transposed; the three shifts are
+// diagonal and conjugate.  Stands in for a level's dagger stencil where the host struct has none: in exact arithmetic
+// it is what the reference's fall-back computes (prolong -> dagger above -> restrict = P^dag D^dag P, mg_complex.cpp:101-111).
+static glb_operator* upload_adjoint_stencil(glb_context* ctx, stencil_2d* st) {
+  if (!st || !st->generated) throw Error("multigrid (host interface): every level needs a generated stencil");
+  const int X = st->lat->get_lattice_dimension(0), Y = st->lat->get_lattice_dimension(1), nc = st->lat->get_nc();
+  const size_t V = (size_t)X * Y, plane = V * nc * nc;
+  std::vector<zcplx> cl(plane), hp(4 * plane), tw(st->has_two ? 8 * plane : 0);
+  static const int hop[4][2] = {{1, 0}, {0, 1}, {-1, 0}, {0, -1}};
+  static const int two[8][2] = {{2, 0}, {1, 1}, {0, 2}, {-1, 1}, {-2, 0}, {-1, -1}, {0, -2}, {1, -1}};
+  for (int y = 0; y < Y; y++)
+    for (int x = 0; x < X; x++) {
+      const size_t site = (size_t)y * X + x;
+      for (int r = 0; r < nc; r++)
+        for (int c = 0; c < nc; c++) {
+          cl[(site * nc + r) * nc + c] = conj(st->clover[(site * nc + c) * nc + r]);
+          for (int d = 0; d < 4; d++) {
+            const size_t nb = (size_t)((y + hop[d][1] + Y) % Y) * X + (size_t)((x + hop[d][0] + X) % X);
+            hp[d * plane + (site * nc + r) * nc + c] = conj(st->hopping[((d + 2) % 4) * plane + (nb * nc + c) * nc + r]);
+          }
+          if (st->has_two)
+            for (int d = 0; d < 8; d++) {
+              const size_t nb = (size_t)((y + two[d][1] + 2 * Y) % Y) * X + (size_t)((x + two[d][0] + 2 * X) % X);
+              tw[d * plane + (site * nc + r) * nc + c] = conj(st->two_link[((d + 4) % 8) * plane + (nb * nc + c) * nc + r]);
+            }
+        }
+    }
+  const double sh[2] = {st->shift.real(), -st->shift.imag()}, eo[2] = {st->eo_shift.real(), -st->eo_shift.imag()},
+               df[2] = {st->dof_shift.real(), -st->dof_shift.imag()};
+  glb_operator* op = 0;
+  GLBX(glb_op_create_stencil2d(ctx, cl.data(), hp.data(), st->has_two ? tw.data() : 0, X, Y, nc, sh, eo, df, &op));
+  return op;
+}
+
 glb_mg_transfer* upload_transfer(glb_context* ctx, mg_operator_struct_complex* mg, int level) {
   Lattice* f = mg->latt[level];
   glb_mg_transfer* t = 0;
@@ -62,21 +97,23 @@ glb_mg_transfer* upload_transfer(glb_context* ctx, mg_operator_struct_complex* m
 }
 
 // the device image of a host hierarchy: operators of every level, transfers of every refinement
-Hierarchy::Hierarchy(mg_operator_struct_complex* host) : ctx(glb200_default_context()) {
+Hierarchy::Hierarchy(mg_operator_struct_complex* host, bool with_dagger) : ctx(glb200_default_context()) {
   const int n = host->n_refine;
   ops.assign(n + 1, (glb_operator*)0);
   trs.assign(n, (glb_mg_transfer*)0);
   try {
     for (int l = 0; l <= n; l++) ops[l] = upload_stencil(ctx, host->stencils[l]);
     for (int l = 0; l < n; l++) trs[l] = upload_transfer(ctx, host, l);
-    if (host->have_dagger_stencil && host->dagger_stencils) {
+    if (with_dagger) {
       // D^dag per level for the normal-equation variants: on the top level the reference applies the FUNCTION
-      // matrix_vector_dagger (mg_complex.cpp:119-123), below it the dagger stencil (:97-100).  A level without either
-      // stays empty; the cycle refuses only if it needs it.
+      // matrix_vector_dagger (mg_complex.cpp:119-123), below it the dagger stencil (:97-100) and without one
+      // P^dag D^dag P by prolong / restrict (:101-111) -- here the adjoint of the level's stencil.
+      const bool have = host->have_dagger_stencil && host->dagger_stencils;
       dag.assign(n + 1, (glb_operator*)0);
       if (host->matrix_vector_dagger) dag[0] = glb200_operator_from_callback(host->matrix_vector_dagger, host->matrix_extra_data);
       for (int l = dag[0] ? 1 : 0; l <= n; l++)
-        if (host->dagger_stencils[l] && host->dagger_stencils[l]->generated) dag[l] = upload_stencil(ctx, host->dagger_stencils[l]);
+        dag[l] = (have && host->dagger_stencils[l] && host->dagger_stencils[l]->generated) ? upload_stencil(ctx, host->dagger_stencils[l])
+                                                                                          : upload_adjoint_stencil(ctx, host->stencils[l]);
     }
   } catch (...) {
     release();
@@ -200,13 +237,30 @@ void coarse_square_staggered(zcplx* lhs, zcplx* rhs, void* e) {
   mg_operator_struct_complex* mg = (mg_operator_struct_complex*)e;
   apply_level_stencil(lhs, rhs, mg, mg->curr_level + 1, false);
 }
+// mg_complex.cpp:93-133.  The top level daggers by function (or, without one, through its dagger stencil / epsilon D epsilon);
+// a level below it through its dagger stencil, and without one as the reference does: prolong, dagger one level up,
+// restrict -- P^dag D^dag P, the adjoint of the Galerkin operator whatever the null vectors look like.
 void fine_square_staggered_dagger(zcplx* lhs, zcplx* rhs, void* e) {
   mg_operator_struct_complex* mg = (mg_operator_struct_complex*)e;
-  apply_level_stencil(lhs, rhs, mg, mg->curr_level, true);
+  if (mg->curr_level == 0) {
+    apply_level_stencil(lhs, rhs, mg, 0, true);
+  } else {
+    level_up(mg);
+    coarse_square_staggered_dagger(lhs, rhs, e);
+    level_down(mg);
+  }
 }
 void coarse_square_staggered_dagger(zcplx* lhs, zcplx* rhs, void* e) {
   mg_operator_struct_complex* mg = (mg_operator_struct_complex*)e;
-  apply_level_stencil(lhs, rhs, mg, mg->curr_level + 1, true);
+  const int level = mg->curr_level + 1;
+  if (mg->have_dagger_stencil && mg->dagger_stencils && mg->dagger_stencils[level] && mg->dagger_stencils[level]->generated) {
+    apply_stencil_2d(lhs, rhs, (void*)mg->dagger_stencils[level]);
+    return;
+  }
+  std::vector<zcplx> fine_in(mg->curr_fine_size), fine_out(mg->curr_fine_size);
+  prolong(fine_in.data(), rhs, mg);
+  fine_square_staggered_dagger(fine_out.data(), fine_in.data(), e);
+  restrict(lhs, fine_out.data(), mg);
 }
 void fine_square_staggered_normal(zcplx* lhs, zcplx* rhs, void* e) {
   mg_operator_struct_complex* mg = (mg_operator_struct_complex*)e;
@@ -342,7 +396,7 @@ void generate_coarse_from_fine_stencil(stencil_2d* coarse, stencil_2d* fine, mg_
 void mg_preconditioner(zcplx* lhs, zcplx* rhs, int size, void* extra_data, inversion_verbose_struct* verb) {
   try {
     mg_precond_struct_complex* p = (mg_precond_struct_complex*)extra_data;
-    Hierarchy H(p->mgstruct);
+    Hierarchy H(p->mgstruct, p->normal_eqn_smooth || p->normal_eqn_mg);
     H.set_precond(p);
     DevVec l(H.ctx, (size_t)size, lhs), r(H.ctx, (size_t)size, rhs);
     mg_preconditioner_dev(l.d, r.d, size, (void*)&H.pc, verb);

@@ -354,10 +354,10 @@ class RefMg:
         self.L.refmg_set_precond(self.h, self.SMOOTH[smooth], n_pre, n_post, self.INNER[inner], n_max, n_restart,
                                  rel_res, 1 if recursive else 0)
 
-    def set_normal(self, normal_smooth, normal_mg, ignore_shifts=False):
+    def set_normal(self, normal_smooth, normal_mg, ignore_shifts=False, dagger_stencils=True):
         """normal-equation variants of the cycle (mg_precond_struct_complex::normal_eqn_smooth / normal_eqn_mg) with
-        dagger stencils on every level, as the reference's driver wires them"""
-        self.L.refmg_set_normal(self.h, int(normal_smooth), int(normal_mg), int(ignore_shifts))
+        dagger stencils on every level, as the reference's driver wires them; dagger_stencils=False leaves them out"""
+        self.L.refmg_set_normal(self.h, int(normal_smooth), int(normal_mg), int(ignore_shifts) if dagger_stencils else -1)
 
     def counts(self):
         n = self.n_refine + 1

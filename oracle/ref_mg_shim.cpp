@@ -354,11 +354,12 @@ void refmg_set_precond(void* hv, int in_smooth_type, int n_pre, int n_post, int 
 // below, with the same treatment of the mass as the stencils of this handle (ignore_shifts of refmg_create2) -- and
 //   normal_smooth  the smoother runs on D^dag D z = D^dag r (CGNR)
 //   normal_mg      fine, coarse and smoothing operator are D^dag D of their level
+//   ignore_shifts < 0: no dagger stencils at all (the levels below the top dagger by prolong / restrict, mg_complex.cpp:101-111)
 void refmg_set_normal(void* hv, int normal_smooth, int normal_mg, int ignore_shifts) {
   RefMg* h = (RefMg*)hv;
   mg_operator_struct_complex& mg = h->mg;
   goto_level(h, 0);
-  if (!mg.have_dagger_stencil) {
+  if (!mg.have_dagger_stencil && ignore_shifts >= 0) {
     mg.have_dagger_stencil = true;
     mg.dagger_stencils = new stencil_2d*[h->n_refine + 1];
     for (int i = 0; i <= h->n_refine; i++) mg.dagger_stencils[i] = new stencil_2d(mg.latt[i], 1);

@@ -179,6 +179,47 @@ def test_normal_equation_variants_of_the_cycle(ours, normal_smooth, normal_mg, l
         assert (io["iter"], io["ops_count"]) == (ir["iter"], ir["ops_count"]) and rel_err(xo, xr) < 1e-9
 
 
+def test_dagger_of_a_level_without_dagger_stencils(ours):
+    """coarse_square_staggered_dagger with no dagger stencil falls back to prolong -> dagger one level up -> restrict
+    (mg_complex.cpp:101-111), recursively: the exact adjoint of the Galerkin operator for ANY null vectors -- here
+    unpartitioned ones, for which sigma_3 D sigma_3 would not be the adjoint"""
+    orc = oracle_py.load("ref")
+    L, mass = 16, 0.05
+    U, b, vecs = _raw_null_vectors(orc, L, mass, 2)
+    whole = [vecs[0] + vecs[2], vecs[1] + vecs[3]]
+    rng = np.random.default_rng(5)
+    lvl1 = [rng.standard_normal(4 * 4 * 2) + 1j * rng.standard_normal(4 * 4 * 2) for _ in range(2)]
+    with quiet_stdout():
+        mo = oracle_py.RefMg(ours, L, L, U, mass, [4, 2], [2, 2], [whole, lvl1])
+        mr = oracle_py.RefMg(orc, L, L, U, mass, [4, 2], [2, 2], [whole, lvl1])
+        for m in (mo, mr):
+            m.set_normal(False, False, dagger_stencils=False)
+    for lvl in (0, 1, 2):
+        X, Y, nc = mr.dims(lvl)
+        f = rng.standard_normal(X * Y * nc) + 1j * rng.standard_normal(X * Y * nc)
+        g = rng.standard_normal(X * Y * nc) + 1j * rng.standard_normal(X * Y * nc)
+        for which in ("dagger", "normal"):
+            vo, vr = mo.apply_level_variant(lvl, f, which), mr.apply_level_variant(lvl, f, which)
+            assert np.array_equal(vo, vr) if lvl == 0 else rel_err(vo, vr) < 1e-13
+        lhs, rhs = np.vdot(g, mo.apply_level(lvl, f)), np.vdot(mo.apply_level_variant(lvl, g, "dagger"), f)
+        assert abs(lhs - rhs) < 1e-12 * abs(lhs)                      # <g, D f> = <D^dag g, f>
+    # the CGNR-smoothed cycle and solve on this hierarchy: the device cycle gets D^dag of the lower levels as the
+    # adjoint of their stencils where the reference projects
+    for m in (mo, mr):
+        m.set_normal(True, False, dagger_stencils=False)
+        m.set_precond(smooth="CG", n_pre=3, n_post=3, inner="GCR", rel_res=1e-2)
+    before_o, before_r = mo.counts(), mr.counts()
+    with quiet_stdout():
+        vo, vr = mo.vcycle(b), mr.vcycle(b)
+    assert rel_err(vo, vr) < 1e-10
+    assert {k: [y - x for x, y in zip(before_o[k], mo.counts()[k])] for k in before_o} == \
+           {k: [y - x for x, y in zip(before_r[k], mr.counts()[k])] for k in before_r}
+    with quiet_stdout():
+        xo, io = mo.vpgcr(b, max_iter=1000, eps=5e-7, restart_freq=64)
+        xr, ir = mr.vpgcr(b, max_iter=1000, eps=5e-7, restart_freq=64)
+    assert io["success"] and (io["iter"], io["ops_count"]) == (ir["iter"], ir["ops_count"]) and rel_err(xo, xr) < 1e-9
+
+
 @pytest.mark.parametrize("kw", [dict(seed=11), dict(seed=5, do_ortho_eo=True), dict(seed=8, null_prec=2, null_gen="CG", tol=1e-3),
                                 dict(seed=12, bstrat=2, max_iter=60), dict(seed=14, bstrat=3, max_iter=60), dict(do_free=True)])
 def test_null_vector_generation_through_the_host_interface(ours, kw):
