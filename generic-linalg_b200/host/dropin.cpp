@@ -179,7 +179,7 @@ glb_operator* build(Builtin kind, void* extra) {
     }
     case B_MG_FINE_DAGGER:
     case B_MG_COARSE_DAGGER: {  // mg_complex.cpp:93-133: the top level applies the FUNCTION matrix_vector_dagger, the levels
-                                // below it their dagger stencil (the prolong / restrict fall-back of :101-111 is not offered)
+                                // below it their dagger stencil, else the adjoint of their stencil
       mg_operator_struct_complex* mg = (mg_operator_struct_complex*)extra;
       const int level = mg->curr_level + (kind == B_MG_COARSE_DAGGER ? 1 : 0);
       if (level == 0) {
@@ -189,8 +189,10 @@ glb_operator* build(Builtin kind, void* extra) {
         op = build(inner, mg->matrix_extra_data);
       } else {
         stencil_2d* st = (mg->have_dagger_stencil && mg->dagger_stencils) ? mg->dagger_stencils[level] : 0;
-        if (!st || !st->generated) throw Error("fine_/coarse_square_staggered_dagger: the level has no generated dagger stencil");
-        op = glb200_mg_host::upload_stencil(ctx, st);
+        if (st && st->generated)
+          op = glb200_mg_host::upload_stencil(ctx, st);
+        else  // the reference projects P^dag D^dag P here (:101-111): the adjoint of the level's stencil
+          op = glb200_mg_host::upload_adjoint_stencil(ctx, mg->stencils ? mg->stencils[level] : 0);
       }
       break;
     }

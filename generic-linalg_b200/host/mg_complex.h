@@ -202,6 +202,7 @@ struct Hierarchy {
   Hierarchy& operator=(const Hierarchy&);
 };
 glb_operator* upload_stencil(glb_context* ctx, stencil_2d* st);
+glb_operator* upload_adjoint_stencil(glb_context* ctx, stencil_2d* st);  // D^dag of a generated stencil
 }  // namespace glb200_mg_host
 
 #endif

@@ -57,7 +57,7 @@ glb_operator* upload_stencil(glb_context* ctx, stencil_2d* st) {
 // ((x+d,c),(x,r)) of D, i.e. of the opposite direction's matrix at the neighbour, transposed; the three shifts are
 // diagonal and conjugate.  Stands in for a level's dagger stencil where the host struct has none: in exact arithmetic
 // it is what the reference's fall-back computes (prolong -> dagger above -> restrict = P^dag D^dag P, mg_complex.cpp:101-111).
-static glb_operator* upload_adjoint_stencil(glb_context* ctx, stencil_2d* st) {
+glb_operator* upload_adjoint_stencil(glb_context* ctx, stencil_2d* st) {
   if (!st || !st->generated) throw Error("multigrid (host interface): every level needs a generated stencil");
   const int X = st->lat->get_lattice_dimension(0), Y = st->lat->get_lattice_dimension(1), nc = st->lat->get_nc();
   const size_t V = (size_t)X * Y, plane = V * nc * nc;

@@ -218,6 +218,12 @@ def test_dagger_of_a_level_without_dagger_stencils(ours):
         xo, io = mo.vpgcr(b, max_iter=1000, eps=5e-7, restart_freq=64)
         xr, ir = mr.vpgcr(b, max_iter=1000, eps=5e-7, restart_freq=64)
     assert io["success"] and (io["iter"], io["ops_count"]) == (ir["iter"], ir["ops_count"]) and rel_err(xo, xr) < 1e-9
+    for m in (mo, mr):                                                 # and the cycle on D^dag D of every level
+        m.set_normal(False, True, dagger_stencils=False)
+        m.set_precond(smooth="CG", n_pre=3, n_post=3, inner="CG", rel_res=1e-2)
+    with quiet_stdout():
+        vo, vr = mo.vcycle(b), mr.vcycle(b)
+    assert rel_err(vo, vr) < 5e-6
 
 
 @pytest.mark.parametrize("kw", [dict(seed=11), dict(seed=5, do_ortho_eo=True), dict(seed=8, null_prec=2, null_gen="CG", tol=1e-3),
