@@ -198,7 +198,7 @@ glb_operator* build(Builtin kind, void* extra) {
     }
     case B_MG_FINE_NORMAL:
     case B_MG_COARSE_NORMAL:
-      throw Error("fine_/coarse_square_staggered_normal is a composition of two device operators (lease)");
+      break;  // a composition of two device operators, like the index operator: no single operator (lease() builds it)
     case B_SYMMSHIFT_X:
     case B_SYMMSHIFT_Y:
     case B_STAG_2LINK: {
