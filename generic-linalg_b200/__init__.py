@@ -119,6 +119,7 @@ def libs():
         "glb_cgm_update_x": (ci, [vp, ci, sz, ci, pd, C.POINTER(vp), C.POINTER(vp)]),
         "glb_cgm_update_p": (ci, [vp, ci, sz, ci, pd, pd, vp, C.POINTER(vp)]),
         "glb_cg_solve_supported": (ci, [vp]),
+        "glb_cg_last_pred_err": (cd, []), "glb_cg_step_mode": (ci, [ci, ci]),
         "glb_cg_solve": (ci, [vp, vp, vp, ci, cd, C.POINTER(CgReport), pd, ci]),
         "glb_op_apply_part": (ci, [vp, vp, vp, ci]),
         "glb_stag_eoprec_prepare": (ci, [vp, vp, vp]), "glb_stag_eoprec_reconstruct": (ci, [vp, vp, vp, vp]),
@@ -143,6 +144,7 @@ def libs():
         "glbx_default_context": (vp, []), "glbx_set_default_context": (None, [vp]),
         "glbx_force_host_scalars": (None, [ci]), "glbx_allow_host_callback_shim": (None, [ci]),
         "glbx_cache_operators": (None, [ci]),
+        "glbx_synthetic_inputs": (ci, [C.c_uint, ci, ci, cd, vp, vp]),
         "glbx_host_apply": (ci, [C.POINTER(OpDesc), vp, vp]),
         "glbx_host_solve": (ci, [ci, C.POINTER(OpDesc), vp, vp, ci, cd, ci, ci, ci, C.POINTER(Result)]),
         "glbx_host_solve_cg_m": (ci, [C.POINTER(OpDesc), C.POINTER(vp), vp, ci, ci, ci, cd, vp, ci, ci,
@@ -723,6 +725,21 @@ class Context:
         if want_history:
             out["history"] = hist[:rep.iterations]
         return out
+
+    def synthetic_inputs(self, X, Y, seed=1337, beta=6.0, want_rhs=True):
+        """BASELINE.md section 3 inputs from the drop-in's host helpers: mt19937(seed) -> gauss_gauge_u1 -> gaussian"""
+        links = np.empty(2 * X * Y, dtype=np.complex128)
+        rhs = np.empty(X * Y, dtype=np.complex128) if want_rhs else None
+        _chk(self.ho.glbx_synthetic_inputs(seed, X, Y, beta, _p(links), _p(rhs) if want_rhs else None),
+             "glbx_synthetic_inputs")
+        return links, rhs
+
+    def cg_step_mode(self, on=True, variant=0):
+        """glb_cg_step_mode: single-kernel CG iteration on/off (+ kernel shape); returns the previous setting"""
+        return bool(self.cu.glb_cg_step_mode(1 if on else 0, int(variant)))
+
+    def cg_last_pred_err(self):
+        return float(self.cu.glb_cg_last_pred_err())
 
     # ---- the reference's own calls: HOST vectors + reference-named callbacks ----
     def _desc(self, kind, X, Y, mass=0.0, Nc=1, links=None, clover=None, hopping=None, two_link=None, shift=0j,

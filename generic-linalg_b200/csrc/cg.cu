@@ -15,9 +15,12 @@
 #include <vector>
 
 #include "cg_state.cuh"
+#include "cgstep.cuh"
 #include "runtime.hpp"
 
 namespace glb {
+
+static double g_last_pred_err = 0.0;  // diagnostic of the last single-kernel solve (glb_cg_last_pred_err)
 
 int launch_cg_update(glb_context* ctx, int dtype, void* st, double* hist, const void* p, void* x, const void* Ap,
                      void* r, size_t n, int defer);
@@ -121,6 +124,177 @@ static int direction_and_apply(glb_operator* op, CgState* d_st, const void* r, v
   return op_apply_fused(op, Ap, p_cur, g);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// The single-kernel iteration (cgstep.cu): one launch and one rank-wide reduction per CG iteration, 160 B/site.
+// Arena layout of an operator's ghost area on slabs: [parity 0: lo | hi][parity 1: lo | hi][flags + counters],
+// each of lo / hi = 3 vectors x 2 rows x X complex.
+static int cs_prepare_slab(glb_operator* op) {
+  if (op->cs_ready) return GLB_OK;
+  const size_t gbytes = (size_t)3 * 2 * op->X * sizeof(cplx);
+  size_t off = 0;
+  if (!comm_arena_alloc(op->ctx, 4 * gbytes + 256, &off))
+    return fail(GLB_ERR_STATE, "peer-memory arena exhausted (GLB_P2P_ARENA_MB)");
+  op->cs_off = off;
+  op->cs_ready = true;
+  return GLB_OK;
+}
+
+// pointers of step number `seq` (it pushes into parity seq&1 and raises the flags to seq; it reads what step seq-1 pushed)
+static void cs_slab_args(glb_operator* op, unsigned long long seq, CgStepArgs* a) {
+  glb_context* ctx = op->ctx;
+  const int G = ctx->nranks, g = ctx->rank;
+  const int up = (g + 1) % G, down = (g + G - 1) % G;
+  const size_t gbytes = (size_t)3 * 2 * op->X * sizeof(cplx);
+  const size_t off_flag = op->cs_off + 4 * gbytes;
+  char* mine = comm_peer(ctx, g);
+  const size_t wr = op->cs_off + (size_t)(seq & 1) * 2 * gbytes;        // parity written by this step
+  const size_t rd = op->cs_off + (size_t)((seq - 1) & 1) * 2 * gbytes;  // parity written by the previous one
+  a->g_lo = (const cplx*)(mine + rd);
+  a->g_hi = (const cplx*)(mine + rd + gbytes);
+  a->push_down = (cplx*)(comm_peer(ctx, down) + wr + gbytes);  // my rows 0,1 are its rows Y, Y+1
+  a->push_up = (cplx*)(comm_peer(ctx, up) + wr);               // my rows Y-2, Y-1 are its rows -2, -1
+  a->flag_down = (unsigned long long*)(comm_peer(ctx, down) + off_flag + 8);
+  a->flag_up = (unsigned long long*)(comm_peer(ctx, up) + off_flag);
+  a->push_count = (unsigned int*)(mine + off_flag + 16);
+  a->push_seq = seq;
+  a->wait.flag_lo = (const unsigned long long*)(mine + off_flag);
+  a->wait.flag_hi = (const unsigned long long*)(mine + off_flag + 8);
+  a->wait.seq = seq - 1;
+  a->wait.budget = comm_spin_budget(ctx);
+}
+
+static int cg_solve_step(glb_operator* op, void* d_x, const void* d_b, int max_iter, double eps, glb_cg_report* rep,
+                         double* rsq_hist, int hist_cap) {
+  glb_context* ctx = op->ctx;
+  const int dt = op->dtype;
+  const size_t n = glb_op_local_size(op);
+  const bool slab = ctx->nranks > 1;
+  int rc = GLB_OK;
+  void* v[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // r0 r1 p0 p1 q0 q1
+  CgState* d_st = nullptr;
+  double* d_hist = nullptr;
+  CgState* h_st = (CgState*)ctx->h_table;
+#define CS_TRY(x)      \
+  do {                 \
+    rc = (x);          \
+    if (rc) goto done; \
+  } while (0)
+  if (slab) CS_TRY(cs_prepare_slab(op));
+  for (int i = 0; i < 6; i++) CS_TRY(glb_vec_alloc(ctx, dt, n, &v[i]));
+  if (cudaMallocAsync((void**)&d_st, sizeof(CgState), ctx->stream) != cudaSuccess) {
+    rc = fail(GLB_ERR_CUDA, "cudaMallocAsync(CgState)");
+    goto done;
+  }
+  if (hist_cap > 0 && rsq_hist) {
+    if (cudaMallocAsync((void**)&d_hist, sizeof(double) * hist_cap, ctx->stream) != cudaSuccess) {
+      rc = fail(GLB_ERR_CUDA, "cudaMallocAsync(hist)");
+      goto done;
+    }
+  }
+  {
+    // set-up of generic_cg.cpp:304-321: bnorm, r = b - A x; the first apply (Ap = A p with p = r) and rsq = |r|^2
+    // are step 0 of the kernel (alpha = beta = 0, p_old = q_old = 0)
+    double bsq = 0.0;
+    CS_TRY(glb_norm2sq(ctx, dt, n, d_b, &bsq));
+    CS_TRY(glb_op_apply(op, v[2], d_x));
+    CS_TRY(glb_sub(ctx, dt, n, d_b, v[2], v[0]));
+    CS_TRY(glb_vec_zero(ctx, dt, n, v[2]));
+    CS_TRY(glb_vec_zero(ctx, dt, n, v[4]));
+    CgState init{};
+    init.bnorm = sqrt(bsq);
+    init.eps = eps;
+    init.max_iter = max_iter;
+    init.hist_cap = d_hist ? hist_cap : 0;
+    h_st[0] = init;
+    if (cudaMemcpyAsync(d_st, &h_st[0], sizeof(CgState), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+      rc = fail(GLB_ERR_CUDA, "upload CgState");
+      goto done;
+    }
+    rep->bnorm = init.bnorm;
+
+    CgStepArgs a{};
+    a.x = (cplx*)d_x;
+    a.Ux = op->Ux;
+    a.Uy = op->Uy;
+    a.X = op->X;
+    a.Y = op->Yloc;
+    a.mass = op->mass;
+    a.st = d_st;
+    a.hist = d_hist;
+    a.red = ctx->red;
+    a.red.result_host = nullptr;
+    int cur = 0;
+    if (slab) {  // boundary rows of (r, 0, 0) to the neighbours: what step 0 reads as ghost rows
+      cs_slab_args(op, ++op->cs_seq, &a);
+      CS_TRY(launch_cg_step_halo_init(op, v[0], v[4], v[2], a, comm_ticket(ctx)));
+    }
+    const int BATCH = 8;
+    int enq = 0;
+    bool finished = false, have_pending = false;
+    while (!finished) {
+      for (int b = 0; b < BATCH; b++) {
+        a.r_in = (const cplx*)v[0 + cur];
+        a.p_in = (const cplx*)v[2 + cur];
+        a.q_in = (const cplx*)v[4 + cur];
+        a.r_out = (cplx*)v[0 + (cur ^ 1)];
+        a.p_out = (cplx*)v[2 + (cur ^ 1)];
+        a.q_out = (cplx*)v[4 + (cur ^ 1)];
+        if (slab) {
+          cs_slab_args(op, ++op->cs_seq, &a);
+          a.pr = comm_p2p_red(ctx);
+        }
+        CS_TRY(launch_cg_step(op, a));
+        cur ^= 1;
+        enq++;
+      }
+      const int slot = (enq / BATCH) & 1;
+      if (have_pending) {
+        if (cudaEventSynchronize(ctx->ev_a) != cudaSuccess) {
+          rc = fail(GLB_ERR_CUDA, "cudaEventSynchronize");
+          goto done;
+        }
+        if (h_st[slot ^ 1].done) finished = true;
+      }
+      if (cudaMemcpyAsync(&h_st[slot], d_st, sizeof(CgState), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+          cudaEventRecord(ctx->ev_a, ctx->stream) != cudaSuccess) {
+        rc = fail(GLB_ERR_CUDA, "state readback");
+        goto done;
+      }
+      have_pending = true;
+      if (finished) break;
+      if (enq >= max_iter + 1 + BATCH) finished = true;  // everything that could run has been enqueued
+    }
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+      rc = fail(GLB_ERR_CUDA, "cudaStreamSynchronize");
+      goto done;
+    }
+    if (cudaMemcpy(&h_st[0], d_st, sizeof(CgState), cudaMemcpyDeviceToHost) != cudaSuccess) {
+      rc = fail(GLB_ERR_CUDA, "final state readback");
+      goto done;
+    }
+    const CgState fin = h_st[0];
+    rep->iterations = fin.iter;
+    rep->ops = 2 + (fin.iter > 0 ? fin.iter - 1 : 0);  // the reference's count (generic_cg.cpp:362)
+    rep->hit_max_iter = fin.hit_max;
+    rep->rsq = fin.rsq_new;
+    g_last_pred_err = fin.pred_err;
+    if (d_hist) {
+      const int m = fin.iter < hist_cap ? fin.iter : hist_cap;
+      if (m > 0 && cudaMemcpy(rsq_hist, d_hist, sizeof(double) * m, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        rc = fail(GLB_ERR_CUDA, "history readback");
+        goto done;
+      }
+    }
+  }
+done:
+  if (d_hist) cudaFreeAsync(d_hist, ctx->stream);
+  if (d_st) cudaFreeAsync(d_st, ctx->stream);
+  for (int i = 5; i >= 0; i--) glb_vec_free(ctx, v[i]);
+  return rc;
+#undef CS_TRY
+}
+
 }  // namespace glb
 
 using namespace glb;
@@ -138,6 +312,7 @@ extern "C" int glb_cg_solve(glb_operator* op, void* d_x, const void* d_b, int ma
   glb_context* ctx = op->ctx;
   if (ctx->nranks > 1 && !normal_fused_ok(op))
     return fail(GLB_ERR_STATE, "glb_cg_solve on slabs needs the one-pass D^dag D operator (see glb_cg_solve_supported)");
+  if (cg_step_ok(op)) return cg_solve_step(op, d_x, d_b, max_iter, eps, rep, rsq_hist, hist_cap);
   const int dt = op->dtype;
   const size_t n = glb_op_local_size(op);
   int rc;
@@ -271,3 +446,7 @@ done:
   return rc;
 #undef CG_TRY
 }
+
+// largest relative deviation |predicted - exact| / exact of |r|^2 during the last single-kernel CG solve of this
+// process (0 when the two-kernel loop ran); measurement aid for the parity tests
+extern "C" double glb_cg_last_pred_err(void) { return glb::g_last_pred_err; }

@@ -23,6 +23,13 @@ struct CgState {
   // slab runs: this rank's partial sums, summed over ranks in place (ncclAllReduce on the stream)
   // before a one-thread kernel folds them into the recurrence: [0] |r|^2, [1..2] <p,Ap>
   double partial[4];
+  // single-kernel iteration (cgstep.cu): the scalars the NEXT step starts from
+  double alpha_re, alpha_im;  // alpha_i = |r_i|^2 / <p_i, q_i>
+  double beta;                // beta_{i+1} = rsq_pred / |r_i|^2
+  double rsq_pred;            // predicted |r_{i+1}|^2 = |r_i|^2 - 2 Re(alpha <r_i,q_i>) + |alpha|^2 |q_i|^2
+  double pred_err;            // largest relative deviation of a prediction from the exact sum one step later
+  int step;                   // steps completed (step 0 is the set-up pass)
+  int pad2;
 };
 
 }  // namespace glb

@@ -89,6 +89,7 @@ struct Comm {
   char* peer[P2P_MAX_RANKS] = {nullptr};
   unsigned long long red_seq = 0;
   unsigned int* ticket = nullptr;
+  long long spin_budget = 0;  // clock64() ticks a kernel waits for a peer (GLB_P2P_TIMEOUT_S; 0 = for ever)
 };
 
 void comm_destroy(glb_context* ctx) {
@@ -129,9 +130,9 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const uint4* send_lo, co
 }
 // spin until both neighbours have delivered exchange number `seq`
 __global__ void halo_wait_kernel(const unsigned long long* flag_lo, const unsigned long long* flag_hi,
-                                 unsigned long long seq) {
-  spin_until(flag_lo, seq);
-  spin_until(flag_hi, seq);
+                                 unsigned long long seq, long long budget) {
+  spin_until(flag_lo, seq, budget);
+  spin_until(flag_hi, seq, budget);
 }
 // stand-alone one-shot allreduce (used when no producing kernel can finish the sum itself)
 __global__ void p2p_allreduce_kernel(double* vals, int n, P2PRed pr) {  // one warp
@@ -143,6 +144,9 @@ __global__ void p2p_allreduce_kernel(double* vals, int n, P2PRed pr) {  // one w
 }
 
 bool comm_p2p(const glb_context* ctx) { return ctx->comm && ctx->comm->p2p; }
+char* comm_peer(glb_context* ctx, int g) { return ctx->comm->peer[g]; }
+long long comm_spin_budget(const glb_context* ctx) { return ctx->comm ? ctx->comm->spin_budget : 0; }
+unsigned int* comm_ticket(glb_context* ctx) { return ctx->comm->ticket; }
 
 // descriptor of the NEXT rank-wide reduction (bumps the sequence number: one per reduction, same order on all ranks)
 P2PRed comm_p2p_red(glb_context* ctx) {
@@ -152,6 +156,7 @@ P2PRed comm_p2p_red(glb_context* ctx) {
   pr.rank = ctx->rank;
   pr.nranks = ctx->nranks;
   pr.seq = ++c->red_seq;
+  pr.budget = c->spin_budget;
   return pr;
 }
 
@@ -178,6 +183,7 @@ int halo_p2p_begin(glb_operator* op, int nrows, HaloTargets* t) {
   t->wait.flag_lo = (const unsigned long long*)(c->arena + off_flag);
   t->wait.flag_hi = (const unsigned long long*)(c->arena + off_flag + 8);
   t->wait.seq = seq;
+  t->wait.budget = c->spin_budget;
   t->ticket = c->ticket;
   t->bytes = rowb * nrows;
   op->ghost_lo = c->arena + off_lo;
@@ -209,7 +215,7 @@ static int halo_exchange_p2p(glb_operator* op, const void* send_lo, const void* 
                                                   (uint4*)t.dst_up_lo, n16, t.flag_down_hi, t.flag_up_lo, t.wait.seq,
                                                   t.ticket);
   GLB_LAUNCH_CHECK();
-  halo_wait_kernel<<<1, 1, 0, ctx->stream>>>(t.wait.flag_lo, t.wait.flag_hi, t.wait.seq);
+  halo_wait_kernel<<<1, 1, 0, ctx->stream>>>(t.wait.flag_lo, t.wait.flag_hi, t.wait.seq, t.wait.budget);
   GLB_LAUNCH_CHECK();
   return GLB_OK;
 }
@@ -303,6 +309,14 @@ int glb_comm_init(glb_context* ctx, int rank, int nranks, const char id[GLB_COMM
   if (rc) return rc;
   GLB_CUDA(cudaSetDevice(ctx->device));
   Comm* c = new Comm();
+  {
+    // how long a kernel spins for a peer before it traps: seconds -> clock64() ticks at the SM's maximum clock
+    const char* et = getenv("GLB_P2P_TIMEOUT_S");
+    const double secs = et ? atof(et) : 600.0;
+    int khz = 2000000;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
+    c->spin_budget = secs > 0.0 ? (long long)(secs * 1e3 * (double)khz) : 0;
+  }
   ncclUniqueId_t u;
   std::memcpy(u.internal, id, GLB_COMM_ID_BYTES);
   GLB_NCCL(g_nccl.CommInitRank(&c->nccl, nranks, u, rank));

@@ -42,7 +42,8 @@ enum ProfClass {
   PROF_CG_UPDATE = 3,     // cg_update_kernel (96 B/site)
   PROF_STAG = 4,          // stag_kernel, any flavour
   PROF_COARSE = 5,        // coarse_kernel / coarse_ring_kernel
-  PROF_LAPLACE = 6
+  PROF_LAPLACE = 6,
+  PROF_CG_STEP = 7         // cg_step_kernel: the whole CG iteration in one pass (160 B/site)
 };
 struct ProfRec {
   cudaEvent_t a, b;
@@ -116,6 +117,10 @@ struct glb_operator {
   unsigned long long halo_seq = 0;
   void* send_lo = nullptr;     // staging for boundary rows produced on the fly (device CG)
   void* send_hi = nullptr;
+  // single-kernel CG iteration on slabs (cgstep.cu): ghost rows of (r, q, p), two parities, in the peer arena
+  bool cs_ready = false;
+  size_t cs_off = 0;           // [parity 0: lo | hi][parity 1: lo | hi][flag_lo, flag_hi, count0, count1]
+  unsigned long long cs_seq = 0;
   // stencil data (slab-local, device)
   glb::cplx* clover = nullptr;
   glb::cplx* hopping = nullptr;   // 4 planes of nc*nc*Vloc
@@ -200,6 +205,9 @@ int allreduce_device(glb_context* ctx, double* d_vals, int n);
 int allreduce_sum(glb_context* ctx, double* host_vals, int n);
 void comm_destroy(glb_context* ctx);
 bool comm_p2p(const glb_context* ctx);
+char* comm_peer(glb_context* ctx, int g);        // rank g's arena as mapped here (peer-memory path only)
+long long comm_spin_budget(const glb_context* ctx);
+unsigned int* comm_ticket(glb_context* ctx);     // self-resetting block counter for small push kernels
 P2PRed comm_p2p_red(glb_context* ctx);
 struct HaloTargets {
   char* dst_down_hi;

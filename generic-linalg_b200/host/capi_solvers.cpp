@@ -16,6 +16,8 @@
 #include "null_gen.h"
 #include "operators.h"
 #include "operators_stencil.h"
+#include "generic_vector.h"
+#include "u1_utils.h"
 
 typedef std::complex<double> zc;
 
@@ -226,6 +228,18 @@ void glbx_set_default_context(glb_context* ctx) { glb200_set_default_context(ctx
 void glbx_force_host_scalars(int on) { glb200_force_host_scalars(on != 0); }
 void glbx_allow_host_callback_shim(int on) { glb200_allow_host_callback_shim(on != 0); }
 void glbx_cache_operators(int on) { glb200_cache_operators(on); }
+
+// The synthetic inputs BASELINE.md section 3 prescribes, drawn with the drop-in's own host helpers the way the
+// reference's drivers do it (one std::mt19937(seed) stream: gauss_gauge_u1(beta) of u1_utils.h, then gaussian() of
+// generic_vector.h).  links: 2*X*Y complex (lattice[y*X*2 + x*2 + mu]), rhs: X*Y complex.  Host-side input
+// preparation for bench.py and the examples; not on the solver path.
+int glbx_synthetic_inputs(unsigned seed, int X, int Y, double beta, void* links, void* rhs) {
+  if (X < 1 || Y < 1 || !links) return GLB_ERR_ARG;
+  std::mt19937 gen(seed);
+  gauss_gauge_u1((zc*)links, X, Y, gen, beta);
+  if (rhs) gaussian<double>((zc*)rhs, X * Y, gen);
+  return GLB_OK;
+}
 
 // lhs = A rhs through the reference-named host callback (upload, device apply, download)
 int glbx_host_apply(const glbx_opdesc* d, void* lhs, const void* rhs) {

@@ -242,6 +242,18 @@ typedef struct glb_cg_report {
 int glb_cg_solve_supported(const glb_operator* op);
 int glb_cg_solve(glb_operator* op, void* d_x, const void* d_b, int max_iter, double eps, glb_cg_report* rep,
                  double* rsq_hist, int hist_cap);
+/* On the one-pass staggered D^dag D operator (complex, gauged, even X; slabs over peer memory) glb_cg_solve runs
+ * the whole iteration as ONE kernel with ONE rank-wide reduction (cgstep.cu): r, x and p updates, the operator and
+ * the four inner products |r|^2, <p,Ap>, <r,Ap>, |Ap|^2 in a single pass (160 B/site instead of 192).  beta's
+ * numerator |r_new|^2 is predicted from those sums one step ahead (|r - a q|^2 = |r|^2 - 2 Re(a <r,q>) + |a|^2 |q|^2)
+ * and replaced by the exact sum for alpha and for the stopping test of generic_cg.cpp:339.  This returns the
+ * largest relative |predicted - exact| / exact seen in the last such solve (0 if the two-kernel loop ran);
+ * GLB_CGSTEP=0 in the environment selects the two-kernel loop. */
+double glb_cg_last_pred_err(void);
+/* measurement / test aid: on = 0 makes glb_cg_solve use the two-kernel loop on that operator too, on = 1 (default)
+ * the single-kernel iteration; variant > 0 selects a kernel shape (100*consumer warps + 10*stages + blocks per SM).
+ * Returns the previous on/off value. */
+int glb_cg_step_mode(int on, int variant);
 
 /* ----------------------------------------------- partial stencil applies */
 /* apply_stencil_2d_eo / _oe / _tb / _bt (coarse_stencil.cpp:395, 560, 725, 1120; DIR_ALL) on a stencil2d operator:
