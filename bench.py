@@ -435,16 +435,23 @@ def main():
     info_p = solve_resident()
     ctx.prof_enable(False)
     it_p = info_p["iter"]
-    t_step = ctx.prof_read(7)[:it_p + 1]
+    t_step = ctx.prof_read(7)
     single_kernel = len(t_step) > 0
     step_ms = ms_total / args.steps
     if single_kernel:
+        persistent = (len(t_step) == 1)     # one launch ran all it_p + 1 steps of the solve
+        if not persistent:
+            t_step = t_step[:it_p + 1]
+        steps_per_launch = (it_p + 1) if persistent else 1
         dom_ms = max_over_ranks(sum(t_step) / len(t_step))
-        dom_bytes = 160.0 * V_local
+        dom_bytes = 160.0 * V_local * steps_per_launch
         dom_share = sum(t_step) / step_ms
-        dom_name = ("cg_step_kernel (one CG iteration in one pass: r -= a q ; x += a p ; p = r + b p ; q = D^dag D p ; "
-                    "|r|^2, <p,q>, <r,q>, |q|^2 ; R r,q,p,x,Ux,Uy 96 + W r,p,q,x 64 = 160 B/site): the step's dominant kernel")
+        dom_name = ("cg_step_kernel (%s; per CG step, in one pass: r -= a q ; x += a p ; p = r + b p ; q = D^dag D p ; "
+                    "|r|^2, <p,q>, <r,q>, |q|^2 ; R r,q,p,x,Ux,Uy 96 + W r,p,q,x 64 = 160 B/site): the step's dominant kernel"
+                    % ("persistent: ONE launch runs all %d CG steps of the solve, meeting at one grid-wide reduction per "
+                       "step" % steps_per_launch if persistent else "one launch per CG step"))
         dom_key, dom_n = "cg_step_kernel", len(t_step)
+        dom_extra = {"cg_steps_per_launch": steps_per_launch, "ms_per_cg_step": dom_ms / steps_per_launch}
     # the two-kernel loop (glb_cg_step_mode(0)): its kernels are timed the same way on one more solve
     ctx.cg_step_mode(False)
     solve_resident()
@@ -466,6 +473,7 @@ def main():
         dom_ms, dom_bytes, dom_share = fused_ms, 96.0 * V_local, sum(t_fused) / step_ms
         dom_name = "normal_kernel<fused> (p = r + beta p ; Ap = D^dag D p ; <p,Ap> in one pass, 96 B/site)"
         dom_key, dom_n = "normal_kernel_fused", len(t_fused)
+        dom_extra = {}
     dom_gbps = dom_bytes / (dom_ms * 1e-3) / 1e9
 
     # ---- end to end: the reference-facing call with host (pinned) buffers, on every rank (slab form: the rank's
@@ -577,7 +585,7 @@ def main():
                      "achieved": dom_gbps, "peak": peak, "unit": "GB/s", "frac": dom_gbps / peak,
                      "traffic": ncu_traffic(dom_key, L), "ms_per_launch": dom_ms,
                      "algorithmic_bytes_per_launch": dom_bytes, "launches_timed": dom_n,
-                     "share_of_step": dom_share, "peak_source": peak_src, "per_gpu": True,
+                     "share_of_step": dom_share, "peak_source": peak_src, "per_gpu": True, **dom_extra,
                      "how": "CUDA events around every launch inside one more solve right after the timed region "
                             "(slab runs: includes waiting for the slowest rank in the reduction)",
                      "other_kernels": [
@@ -689,8 +697,10 @@ def strong_case(ctx, glb, torch, dist, stream, barrier, max_over_ranks, Lg, worl
     x.zero()
     ip = ctx.solve("CG", opN, x, bp, max_iter=5000, eps=TOL)
     ctx.prof_enable(False)
-    ts = ctx.prof_read(7)[:ip["iter"] + 1]
-    k_ms = max_over_ranks(sum(ts) / max(len(ts), 1))
+    ts = ctx.prof_read(7)
+    if len(ts) != 1:
+        ts = ts[:ip["iter"] + 1]
+    k_ms = max_over_ranks(sum(ts) / (ip["iter"] + 1))   # per CG step, whether one launch per step or one per solve
     true_rel = float(np.sqrt(info["resSq"]) / np.sqrt(ctx.norm2sq(bp)))
     for o in (opN, opDd):
         o.destroy()
@@ -734,7 +744,7 @@ def strong_case(ctx, glb, torch, dist, stream, barrier, max_over_ranks, Lg, worl
     barrier()
     ms_1 = max_over_ranks(ms_1)
     out.update({"ms_per_solve_1gpu": ms_1, "efficiency": ms_1 / (world * ms_n),
-                "limiting": "cg_step_kernel %.1f us per launch at %d rows per GPU against %.1f us = (1-GPU solve / "
+                "limiting": "cg_step_kernel %.1f us per CG step at %d rows per GPU against %.1f us = (1-GPU solve / "
                             "iterations / N): launch + grid tail + one rank-wide reduction per iteration"
                             % (1e3 * k_ms, Yloc, 1e3 * ms_1 / max(info["iter"], 1) / world)})
     ref = golden_large().get(str(Lg), {}).get("CGNE", {}).get("iter")

@@ -140,28 +140,23 @@ static int cs_prepare_slab(glb_operator* op) {
   return GLB_OK;
 }
 
-// pointers of step number `seq` (it pushes into parity seq&1 and raises the flags to seq; it reads what step seq-1 pushed)
-static void cs_slab_args(glb_operator* op, unsigned long long seq, CgStepArgs* a) {
+// the slab part of the kernel arguments: this rank's ghost buffers, the neighbours', flags and counters
+static void cs_slab_args(glb_operator* op, CgStepArgs* a) {
   glb_context* ctx = op->ctx;
   const int G = ctx->nranks, g = ctx->rank;
   const int up = (g + 1) % G, down = (g + G - 1) % G;
   const size_t gbytes = (size_t)3 * 2 * op->X * sizeof(cplx);
   const size_t off_flag = op->cs_off + 4 * gbytes;
   char* mine = comm_peer(ctx, g);
-  const size_t wr = op->cs_off + (size_t)(seq & 1) * 2 * gbytes;        // parity written by this step
-  const size_t rd = op->cs_off + (size_t)((seq - 1) & 1) * 2 * gbytes;  // parity written by the previous one
-  a->g_lo = (const cplx*)(mine + rd);
-  a->g_hi = (const cplx*)(mine + rd + gbytes);
-  a->push_down = (cplx*)(comm_peer(ctx, down) + wr + gbytes);  // my rows 0,1 are its rows Y, Y+1
-  a->push_up = (cplx*)(comm_peer(ctx, up) + wr);               // my rows Y-2, Y-1 are its rows -2, -1
-  a->flag_down = (unsigned long long*)(comm_peer(ctx, down) + off_flag + 8);
-  a->flag_up = (unsigned long long*)(comm_peer(ctx, up) + off_flag);
+  a->ghost = (const cplx*)(mine + op->cs_off);
+  a->peer_down = (cplx*)(comm_peer(ctx, down) + op->cs_off);
+  a->peer_up = (cplx*)(comm_peer(ctx, up) + op->cs_off);
+  a->flag_down = (unsigned long long*)(comm_peer(ctx, down) + off_flag + 8);  // its flag_hi
+  a->flag_up = (unsigned long long*)(comm_peer(ctx, up) + off_flag);          // its flag_lo
   a->push_count = (unsigned int*)(mine + off_flag + 16);
-  a->push_seq = seq;
   a->wait.flag_lo = (const unsigned long long*)(mine + off_flag);
   a->wait.flag_hi = (const unsigned long long*)(mine + off_flag + 8);
-  a->wait.seq = seq - 1;
-  a->wait.budget = comm_spin_budget(ctx);
+  a->wait.seq = 0;
 }
 
 static int cg_solve_step(glb_operator* op, void* d_x, const void* d_b, int max_iter, double eps, glb_cg_report* rep,
@@ -214,6 +209,11 @@ static int cg_solve_step(glb_operator* op, void* d_x, const void* d_b, int max_i
     rep->bnorm = init.bnorm;
 
     CgStepArgs a{};
+    for (int c = 0; c < 2; c++) {
+      a.r[c] = (cplx*)v[0 + c];
+      a.p[c] = (cplx*)v[2 + c];
+      a.q[c] = (cplx*)v[4 + c];
+    }
     a.x = (cplx*)d_x;
     a.Ux = op->Ux;
     a.Uy = op->Uy;
@@ -224,46 +224,50 @@ static int cg_solve_step(glb_operator* op, void* d_x, const void* d_b, int max_i
     a.hist = d_hist;
     a.red = ctx->red;
     a.red.result_host = nullptr;
-    int cur = 0;
-    if (slab) {  // boundary rows of (r, 0, 0) to the neighbours: what step 0 reads as ghost rows
-      cs_slab_args(op, ++op->cs_seq, &a);
-      CS_TRY(launch_cg_step_halo_init(op, v[0], v[4], v[2], a, comm_ticket(ctx)));
+    a.wait.budget = comm_spin_budget(ctx);
+    if (a.wait.budget == 0 && !slab) a.wait.budget = 0;  // single rank: the step spin never gives up on its own grid
+    const long long max_steps = (long long)max_iter + 1;  // step 0 is the set-up pass
+    if (slab) {
+      // boundary rows of (r, 0, 0) to the neighbours: what step 0 reads as ghost rows.  Exchange numbers: the set-up
+      // push is seq0, step s is seq0 + 1 + s; a range is reserved so that every rank counts alike whatever happens
+      cs_slab_args(op, &a);
+      const unsigned long long seq0 = op->cs_seq + 1;
+      op->cs_seq += 1 + (unsigned long long)max_steps;
+      a.seq_base = seq0 + 1;
+      CS_TRY(launch_cg_step_halo_init(op, v[0], v[4], v[2], a, seq0, comm_ticket(ctx)));
+      a.pr = comm_p2p_red_range(ctx, (unsigned long long)max_steps);
     }
-    const int BATCH = 8;
-    int enq = 0;
-    bool finished = false, have_pending = false;
-    while (!finished) {
-      for (int b = 0; b < BATCH; b++) {
-        a.r_in = (const cplx*)v[0 + cur];
-        a.p_in = (const cplx*)v[2 + cur];
-        a.q_in = (const cplx*)v[4 + cur];
-        a.r_out = (cplx*)v[0 + (cur ^ 1)];
-        a.p_out = (cplx*)v[2 + (cur ^ 1)];
-        a.q_out = (cplx*)v[4 + (cur ^ 1)];
-        if (slab) {
-          cs_slab_args(op, ++op->cs_seq, &a);
-          a.pr = comm_p2p_red(ctx);
+    if (cg_step_persistent()) {
+      // ONE launch for the whole solve: the CTAs stay resident and meet at the reduction of every step
+      a.nsteps = max_steps > 0x7fffffffLL ? 0x7fffffff : (int)max_steps;
+      CS_TRY(launch_cg_step(op, a));
+    } else {
+      a.nsteps = 1;
+      const int BATCH = 8;
+      long long enq = 0;
+      bool finished = false, have_pending = false;
+      while (!finished) {
+        for (int b = 0; b < BATCH; b++) {
+          CS_TRY(launch_cg_step(op, a));
+          enq++;
         }
-        CS_TRY(launch_cg_step(op, a));
-        cur ^= 1;
-        enq++;
-      }
-      const int slot = (enq / BATCH) & 1;
-      if (have_pending) {
-        if (cudaEventSynchronize(ctx->ev_a) != cudaSuccess) {
-          rc = fail(GLB_ERR_CUDA, "cudaEventSynchronize");
+        const int slot = (int)((enq / BATCH) & 1);
+        if (have_pending) {
+          if (cudaEventSynchronize(ctx->ev_a) != cudaSuccess) {
+            rc = fail(GLB_ERR_CUDA, "cudaEventSynchronize");
+            goto done;
+          }
+          if (h_st[slot ^ 1].done) finished = true;
+        }
+        if (cudaMemcpyAsync(&h_st[slot], d_st, sizeof(CgState), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaEventRecord(ctx->ev_a, ctx->stream) != cudaSuccess) {
+          rc = fail(GLB_ERR_CUDA, "state readback");
           goto done;
         }
-        if (h_st[slot ^ 1].done) finished = true;
+        have_pending = true;
+        if (finished) break;
+        if (enq >= max_steps + BATCH) finished = true;  // everything that could run has been enqueued
       }
-      if (cudaMemcpyAsync(&h_st[slot], d_st, sizeof(CgState), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
-          cudaEventRecord(ctx->ev_a, ctx->stream) != cudaSuccess) {
-        rc = fail(GLB_ERR_CUDA, "state readback");
-        goto done;
-      }
-      have_pending = true;
-      if (finished) break;
-      if (enq >= max_iter + 1 + BATCH) finished = true;  // everything that could run has been enqueued
     }
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
       rc = fail(GLB_ERR_CUDA, "cudaStreamSynchronize");

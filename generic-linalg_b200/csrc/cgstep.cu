@@ -30,8 +30,10 @@
 // row blocks wait for that flag before they read ghost rows -- interior row blocks never wait.  The
 // kernel's last block completes the sum of the six scalars over ranks itself (p2p_allreduce_warp):
 // one rank-wide synchronisation per CG iteration, no separate halo or reduction launch.
+#include <climits>
 #include <cstdlib>
 #include <type_traits>
+#include <vector>
 
 #include "cg_state.cuh"
 #include "cgstep.cuh"
@@ -98,6 +100,15 @@ __device__ __forceinline__ cplx cs_row(bool eta_neg, cplx below, cplx centre, cp
 // arrays of one stage, in this order
 enum { CS_R = 0, CS_Q = 1, CS_P = 2, CS_XV = 3, CS_UX = 4, CS_UY = 5, CS_NARR = 6 };
 
+__device__ __forceinline__ int ld_acquire_gpu_s32(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu_s32(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 template <int CW, int STAGES, int MINB>
 __global__ void __launch_bounds__((CW + 1) * 32, MINB) cg_step_kernel(const CgStepArgs a) {
   constexpr int OUT_W = 28;           // sites a consumer warp produces per row (32 loaded - 2 halo sites per side)
@@ -109,13 +120,14 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) cg_step_kernel(const CgSt
   cplx* const tiles = reinterpret_cast<cplx*>(cs_smem);
   unsigned long long* const full = reinterpret_cast<unsigned long long*>(cs_smem + (size_t)STAGES * STAGE_BYTES);
   unsigned long long* const empty = full + STAGES;
+  // Stage headers: the producer is also the scheduler.  Every stage carries {row L, ya, yb, x_lo} of the item it
+  // belongs to (L = INT_MIN: end of this CG step), so the consumers are a uniform stream processor whatever item
+  // the rows come from -- items follow each other in the ring without draining it.
+  int4* const hdr = reinterpret_cast<int4*>(empty + STAGES);
+  __shared__ double s_scal[3];  // alpha.re, alpha.im, beta of the current step
+  __shared__ int s_ctl[2];      // step number, done
 
   CgState* const st = a.st;
-  if (st->done) return;  // (uniform: every thread reads the same word; rank-summed scalars are equal on all ranks)
-  const cplx alpha = mk(st->alpha_re, st->alpha_im);
-  const cplx nalpha = fneg(alpha);
-  const double beta = st->beta;
-
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; s++) {
@@ -124,97 +136,173 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) cg_step_kernel(const CgSt
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();
 
   const int X = a.X, Y = a.Y;
   const int nstrips = a.nstrips, nrb = a.nrb;
   const int nitems = nstrips * nrb;
-  const bool slab = (a.g_lo != nullptr);
-  double acc[6];  // |r|^2, <p,q>.re, <p,q>.im, <r,q>.re, <r,q>.im, |q|^2
-#pragma unroll
-  for (int i = 0; i < 6; i++) acc[i] = 0.0;
-
+  const bool slab = (a.ghost != nullptr);
+  const size_t gvec = (size_t)2 * X;  // one vector's two ghost rows
   unsigned j = 0;  // running stage counter: the same sequence in the producer and in every consumer
-  if (warp == CW) {
-    // ================================================================== producer (one elected lane)
-    if (lane == 0) {
-      bool waited = false;
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const int strip = item % nstrips, rb = item / nstrips;
-        const int ya = (int)((long long)Y * rb / nrb), yb = (int)((long long)Y * (rb + 1) / nrb);
-        if (ya >= yb) continue;
-        const int x_lo = strip * OUT - 2;
-        const int pos0 = ((x_lo % X) + X) % X;
-        if (slab && !waited && (ya - 2 < 0 || yb + 2 > Y) && a.wait.seq != 0) {
-          // the neighbours' rows of the previous step must have landed before the TMA unit reads them
-          spin_until(a.wait.flag_lo, a.wait.seq, a.wait.budget);
-          spin_until(a.wait.flag_hi, a.wait.seq, a.wait.budget);
-          asm volatile("fence.proxy.async;" ::: "memory");
-          waited = true;
-        }
-        for (int L = ya - 2; L < yb + 2; L++, j++) {
-          const int s = j % STAGES;
-          mbar_wait(&empty[s], ((j / STAGES) & 1) ^ 1);
-          mbar_expect_tx(&full[s], STAGE_BYTES);
-          cplx* const dst = tiles + (size_t)s * (CS_NARR * TW);
-          // source rows: vectors at row L (periodic on one rank, ghost rows on slabs), links at row L-1
-          const cplx* src[CS_NARR];
-          if (slab && L < 0) {
-            const cplx* g = a.g_lo + (size_t)(L + 2) * X;
-            src[CS_R] = g;
-            src[CS_Q] = g + (size_t)2 * X;
-            src[CS_P] = g + (size_t)4 * X;
-            src[CS_XV] = a.x;  // never used on ghost rows
-          } else if (slab && L >= Y) {
-            const cplx* g = a.g_hi + (size_t)(L - Y) * X;
-            src[CS_R] = g;
-            src[CS_Q] = g + (size_t)2 * X;
-            src[CS_P] = g + (size_t)4 * X;
-            src[CS_XV] = a.x;
-          } else {
-            const size_t o = (size_t)(((L % Y) + Y) % Y) * X;
-            src[CS_R] = a.r_in + o;
-            src[CS_Q] = a.q_in + o;
-            src[CS_P] = a.p_in + o;
-            src[CS_XV] = a.x + o;
-          }
-          const int lrow = (L - 1 < -LINK_GHOST) ? -LINK_GHOST : L - 1;  // row ya-3 is never used
-          src[CS_UX] = a.Ux + (ptrdiff_t)lrow * X;
-          src[CS_UY] = a.Uy + (ptrdiff_t)lrow * X;
-          // the tile is periodic in x: split at the seam (several times when the lattice is narrower than the tile)
-          int pos = pos0, rem = TW, d = 0;
-          while (rem > 0) {
-            const int seg = (rem < X - pos) ? rem : X - pos;
+  int have_step = -1;
+
+  // consumer state that lives across steps: three rotating register windows.  At a row step of phase K slot K2
+  // takes the new row L, K1 holds row L-1, K0 row L-2.  A new item (or CG step) may start at any phase: its first
+  // four rows only feed results that are predicated off (rows below ya), so nothing is carried over.
+  const bool eta_neg = (lane & 1);  // tiles and warp windows start on even x
+  const int idx = warp * OUT_W + lane;              // this lane's site inside the tile (consumers)
+  const int idx_l = idx > 0 ? idx - 1 : 0;          // its left neighbour (lane 0 of warp 0 never uses it)
+  const bool lane_in = (lane >= 2) && (lane < 30);
+  cplx p[3], r[3], t[3], ux[3], uy[3], uxl[3];
 #pragma unroll
-            for (int arr = 0; arr < CS_NARR; arr++)
-              bulk_g2s(dst + arr * TW + d, src[arr] + pos, (unsigned)seg * (unsigned)sizeof(cplx), &full[s]);
-            d += seg;
-            rem -= seg;
-            pos = 0;
-          }
+  for (int k = 0; k < 3; k++) p[k] = r[k] = t[k] = ux[k] = uy[k] = uxl[k] = mk(0.0, 0.0);
+
+#pragma unroll 1
+  for (int n = 0; n < a.nsteps; n++) {
+    // ---- the scalars of this step, published by the last block of the previous one (or by the host)
+    if (threadIdx.x == 0) {
+      int step = ld_acquire_gpu_s32(&st->step);
+      if (n > 0) {
+        const long long t0 = clock64();
+        while (step <= have_step) {
+          __nanosleep(32);
+          step = ld_acquire_gpu_s32(&st->step);
+          if (a.wait.budget > 0 && clock64() - t0 > a.wait.budget) __trap();
         }
       }
+      s_ctl[0] = step;
+      s_ctl[1] = __ldcg(&st->done);
+      s_scal[0] = __ldcg(&st->alpha_re);
+      s_scal[1] = __ldcg(&st->alpha_im);
+      s_scal[2] = __ldcg(&st->beta);
     }
-  } else {
-    // ================================================================== consumers
-    const bool eta_neg = (lane & 1);  // tiles and warp windows start on even x
-    const int idx = warp * OUT_W + lane;              // this lane's site inside the tile
-    const int idx_l = idx > 0 ? idx - 1 : 0;          // its left neighbour (lane 0 of warp 0 never uses it)
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-      const int strip = item % nstrips, rb = item / nstrips;
-      const int ya = (int)((long long)Y * rb / nrb), yb = (int)((long long)Y * (rb + 1) / nrb);
-      if (ya >= yb) continue;
-      const int x = strip * OUT - 2 + idx;
-      const bool active = (lane >= 2) && (lane < 30) && (x < X);
-      // register windows, slot = (L - (ya-2)) % 3 : at step L slot K2 takes row L, K1 holds L-1, K0 holds L-2
-      cplx p[3], r[3], t[3], ux[3], uy[3], uxl[3];
+    __syncthreads();
+    const int step = s_ctl[0];
+    if (s_ctl[1]) break;  // uniform over the grid: rank-summed scalars are equal on every block and every rank
+    have_step = step;
+    const cplx alpha = mk(s_scal[0], s_scal[1]);
+    const double beta = s_scal[2];
+    const int cur = step & 1;  // ping-pong buffers of the recurrence
+    const cplx* const r_in = a.r[cur];
+    const cplx* const q_in = a.q[cur];
+    const cplx* const p_in = a.p[cur];
+    cplx* const r_out = a.r[cur ^ 1];
+    cplx* const q_out = a.q[cur ^ 1];
+    cplx* const p_out = a.p[cur ^ 1];
+    // slabs: this step has exchange number seq; it reads the ghost rows of parity (seq-1)&1, stores its own boundary
+    // rows into the neighbours' buffers of parity seq&1 and raises their flags to seq
+    const unsigned long long seq = a.seq_base + (unsigned long long)step;
+    const cplx* g_lo = nullptr;
+    const cplx* g_hi = nullptr;
+    cplx* push_down = nullptr;
+    cplx* push_up = nullptr;
+    if (slab) {
+      const size_t rd = (size_t)((seq - 1) & 1) * 2 * (3 * gvec), wr = (size_t)(seq & 1) * 2 * (3 * gvec);
+      g_lo = a.ghost + rd;
+      g_hi = a.ghost + rd + 3 * gvec;
+      push_down = a.peer_down + wr + 3 * gvec;  // my rows 0, 1 are rows Y, Y+1 of the rank below
+      push_up = a.peer_up + wr;                 // my rows Y-2, Y-1 are rows -2, -1 of the rank above
+    }
+    double acc[6];  // |r|^2, <p,q>.re, <p,q>.im, <r,q>.re, <r,q>.im, |q|^2
 #pragma unroll
-      for (int k = 0; k < 3; k++) p[k] = r[k] = t[k] = ux[k] = uy[k] = uxl[k] = mk(0.0, 0.0);
+    for (int i = 0; i < 6; i++) acc[i] = 0.0;
+    const bool tracing = (a.trace != nullptr) && (step == a.trace_step);
+    unsigned long long t_start = 0;
+    int items_done = 0;
+    if (tracing && threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start));
 
-      auto row_step = [&](auto Kc, const int L) {
+    if (warp == CW) {
+      // ================================================================== producer (one elected lane)
+      if (lane == 0) {
+        // data written by the previous step's generic stores (any SM) is read by the TMA unit from here on
+        asm volatile("fence.proxy.async;" ::: "memory");
+        bool waited = false;
+        int item = blockIdx.x;
+        for (;;) {
+          if (a.queue != nullptr) item = (int)atomicAdd(a.queue, 1u);  // dynamic schedule: first come, first served
+          if (item >= nitems) break;
+          // item -> (strip, row block); on slabs the two boundary row blocks come first so that their rows are on
+          // their way to the neighbours while the interior is still being worked on
+          const int strip = item % nstrips;
+          int rb = item / nstrips;
+          if (slab && nrb > 2) rb = (rb == 0) ? 0 : (rb == 1 ? nrb - 1 : rb - 1);
+          if (a.queue == nullptr) item += gridDim.x;
+          const int ya = a.rb_rows ? a.rb_rows[rb] : (int)((long long)Y * rb / nrb);
+          const int yb = a.rb_rows ? a.rb_rows[rb + 1] : (int)((long long)Y * (rb + 1) / nrb);
+          if (ya >= yb) continue;
+          items_done++;
+          const int x_lo = strip * OUT - 2;
+          const int pos0 = ((x_lo % X) + X) % X;
+          if (slab && !waited && (ya - 2 < 0 || yb + 2 > Y)) {
+            // the neighbours' rows of the previous step must have landed before the TMA unit reads them
+            spin_until(a.wait.flag_lo, seq - 1, a.wait.budget);
+            spin_until(a.wait.flag_hi, seq - 1, a.wait.budget);
+            asm volatile("fence.proxy.async;" ::: "memory");
+            waited = true;
+          }
+          for (int L = ya - 2; L < yb + 2; L++, j++) {
+            const int s = j % STAGES;
+            mbar_wait(&empty[s], ((j / STAGES) & 1) ^ 1);
+            hdr[s] = make_int4(L, ya, yb, x_lo);
+            mbar_expect_tx(&full[s], STAGE_BYTES);
+            cplx* const dst = tiles + (size_t)s * (CS_NARR * TW);
+            // source rows: vectors at row L (periodic on one rank, ghost rows on slabs), links at row L-1
+            const cplx* src[CS_NARR];
+            if (slab && L < 0) {
+              const cplx* g = g_lo + (size_t)(L + 2) * X;
+              src[CS_R] = g;
+              src[CS_Q] = g + gvec;
+              src[CS_P] = g + 2 * gvec;
+              src[CS_XV] = a.x;  // never used on ghost rows
+            } else if (slab && L >= Y) {
+              const cplx* g = g_hi + (size_t)(L - Y) * X;
+              src[CS_R] = g;
+              src[CS_Q] = g + gvec;
+              src[CS_P] = g + 2 * gvec;
+              src[CS_XV] = a.x;
+            } else {
+              const size_t o = (size_t)(((L % Y) + Y) % Y) * X;
+              src[CS_R] = r_in + o;
+              src[CS_Q] = q_in + o;
+              src[CS_P] = p_in + o;
+              src[CS_XV] = a.x + o;
+            }
+            const int lrow = (L - 1 < -LINK_GHOST) ? -LINK_GHOST : L - 1;  // row ya-3 is never used
+            src[CS_UX] = a.Ux + (ptrdiff_t)lrow * X;
+            src[CS_UY] = a.Uy + (ptrdiff_t)lrow * X;
+            // the tile is periodic in x: split at the seam (several times when the lattice is narrower than the tile)
+            int pos = pos0, rem = TW, d = 0;
+            while (rem > 0) {
+              const int seg = (rem < X - pos) ? rem : X - pos;
+#pragma unroll
+              for (int arr = 0; arr < CS_NARR; arr++)
+                bulk_g2s(dst + arr * TW + d, src[arr] + pos, (unsigned)seg * (unsigned)sizeof(cplx), &full[s]);
+              d += seg;
+              rem -= seg;
+              pos = 0;
+            }
+          }
+        }
+        // end of this step: one header-only stage sends the consumers to the reduction
+        const int s = j % STAGES;
+        mbar_wait(&empty[s], ((j / STAGES) & 1) ^ 1);
+        hdr[s] = make_int4(INT_MIN, 0, 0, 0);
+        mbar_arrive(&full[s]);
+        j++;
+      }
+    } else {
+      // ================================================================== consumers
+      auto row_step = [&](auto Kc) -> bool {
         constexpr int K0 = decltype(Kc)::value % 3, K1 = (K0 + 1) % 3, K2 = (K0 + 2) % 3;
         const int s = j % STAGES;
         mbar_wait(&full[s], (j / STAGES) & 1);
+        const int4 h = hdr[s];
+        const int L = h.x, ya = h.y, yb = h.z;
+        if (L == INT_MIN) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[s]);
+          j++;
+          return false;
+        }
         const cplx* const tile = tiles + (size_t)s * (CS_NARR * TW);
         const cplx ro = tile[CS_R * TW + idx];
         const cplx qo = tile[CS_Q * TW + idx];
@@ -226,28 +314,30 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) cg_step_kernel(const CgSt
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
         j++;
+        const int x = h.w + idx;
+        const bool active = lane_in && (x < X);
         // the streaming part of the iteration at row L (generic_cg.cpp:328-351)
-        const cplx rn = fadd(ro, fmul(nalpha, qo));       // r = r - alpha*Ap
+        const cplx rn = fsub(ro, fmul(alpha, qo));        // r = r - alpha*Ap
         const cplx pn = fadd(rn, fscale(beta, po));       // p = r + beta*p
         r[K2] = rn;
         p[K2] = pn;
         const bool own = active && (L >= ya) && (L < yb);
         if (own) {
           const size_t o = (size_t)L * X + x;
-          a.r_out[o] = rn;
-          a.p_out[o] = pn;
+          r_out[o] = rn;
+          p_out[o] = pn;
           a.x[o] = fadd(xo, fmul(alpha, po));             // phi = phi + alpha*p
           acc[0] += fnorm(rn);
           if (slab) {
             if (L < 2) {
-              cplx* g = a.push_down + (size_t)L * X + x;
+              cplx* g = push_down + (size_t)L * X + x;
               g[0] = rn;
-              g[(size_t)4 * X] = pn;
+              g[2 * gvec] = pn;
             }
             if (L >= Y - 2) {
-              cplx* g = a.push_up + (size_t)(L - (Y - 2)) * X + x;
+              cplx* g = push_up + (size_t)(L - (Y - 2)) * X + x;
               g[0] = rn;
-              g[(size_t)4 * X] = pn;
+              g[2 * gvec] = pn;
             }
           }
         }
@@ -257,90 +347,117 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) cg_step_kernel(const CgSt
         const int y = L - 2;
         if (active && y >= ya) {
           const size_t o = (size_t)y * X + x;
-          a.q_out[o] = res;
+          q_out[o] = res;
           Field<cplx>::dot_acc(acc + 1, p[K0], res);
           Field<cplx>::dot_acc(acc + 3, r[K0], res);
           acc[5] += fnorm(res);
           if (slab) {
-            if (y < 2) a.push_down[(size_t)(2 + y) * X + x] = res;
-            if (y >= Y - 2) a.push_up[(size_t)(2 + y - (Y - 2)) * X + x] = res;
+            if (y < 2) push_down[gvec + (size_t)y * X + x] = res;
+            if (y >= Y - 2) push_up[gvec + (size_t)(y - (Y - 2)) * X + x] = res;
           }
         }
+        if (slab && L == yb + 1 && (ya < 2 || yb > Y - 2)) {
+          // last row of an item that owns boundary rows of the slab: this warp's share of them is on its way to the
+          // neighbours -- make it visible system-wide, then the last warp to get here raises the neighbours' flags
+          __threadfence_system();
+          __syncwarp();
+          if (lane == 0) {
+            const unsigned need = (unsigned)(nstrips * CW);
+            if (ya < 2) {
+              if (atomicAdd(&a.push_count[0], 1u) == need - 1) {
+                a.push_count[0] = 0;
+                __threadfence_system();
+                st_release_sys(a.flag_down, seq);
+              }
+            }
+            if (yb > Y - 2) {
+              if (atomicAdd(&a.push_count[1], 1u) == need - 1) {
+                a.push_count[1] = 0;
+                __threadfence_system();
+                st_release_sys(a.flag_up, seq);
+              }
+            }
+          }
+        }
+        return true;
       };
-      int L = ya - 2;
 #pragma unroll 1
-      for (; L + 3 <= yb + 2; L += 3) {
-        row_step(std::integral_constant<int, 0>(), L);
-        row_step(std::integral_constant<int, 1>(), L + 1);
-        row_step(std::integral_constant<int, 2>(), L + 2);
+      for (;;) {
+        if (!row_step(std::integral_constant<int, 0>())) break;
+        if (!row_step(std::integral_constant<int, 1>())) break;
+        if (!row_step(std::integral_constant<int, 2>())) break;
       }
-      if (L < yb + 2) row_step(std::integral_constant<int, 0>(), L);
-      if (L + 1 < yb + 2) row_step(std::integral_constant<int, 1>(), L + 1);
+    }
+    if (tracing) {
+      // per CTA: [0] SM, [1] producer out of work, [2] items, [3] stages, [4] start, [5] consumers done, [6] after the
+      // grid-wide sum (last block only: the step's effective end)
+      unsigned long long* tr = a.trace + 8 * (size_t)blockIdx.x;
+      unsigned long long tn;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tn));
+      if (threadIdx.x == CW * 32) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        tr[0] = smid;
+        tr[1] = tn;
+        tr[2] = (unsigned long long)items_done;
+        tr[3] = (unsigned long long)j;
+      }
+      if (threadIdx.x == 0) {
+        tr[4] = t_start;
+        tr[5] = tn;
+      }
+    }
 
-      if (slab && (ya < 2 || yb > Y - 2)) {
-        // this warp's share of the slab's boundary rows is on its way to the neighbours: make it visible
-        // system-wide, then the last warp to get here raises the neighbours' flags
-        __threadfence_system();
-        __syncwarp();
-        if (lane == 0) {
-          const unsigned need = (unsigned)(nstrips * CW);
-          if (ya < 2) {
-            if (atomicAdd(&a.push_count[0], 1u) == need - 1) {
-              a.push_count[0] = 0;
-              __threadfence_system();
-              st_release_sys(a.flag_down, a.push_seq);
-            }
+    // ---- the six sums: block -> grid (last block) -> ranks (its first warp, peer memory) -> recurrence
+    double total[6];
+    if (grid_sum<6>(acc, a.red, total)) {
+      if (a.pr.seq != 0 && threadIdx.x < 32) {
+        P2PRed pr = a.pr;
+        pr.seq += (unsigned long long)step;
+        p2p_allreduce_warp(pr, total, 6);
+      }
+      if (threadIdx.x == 0) {
+        unsigned long long tn = 0;
+        if (tracing || a.step_ns != nullptr) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tn));
+        if (tracing) a.trace[8 * (size_t)blockIdx.x + 6] = tn;
+        if (a.step_ns != nullptr && step < a.step_ns_cap) a.step_ns[step] = tn;
+        if (a.queue != nullptr) *a.queue = 0;  // every block has claimed its last item: ready for the next step
+        const double rr = total[0];
+        // step 0: the set-up pass (alpha = beta = 0), step i >= 1: reference iteration k = i-1
+        if (step > 0) {
+          const int k = step - 1;
+          st->rsq_new = rr;
+          st->iter = k + 1;
+          if (a.hist != nullptr && k < st->hist_cap) a.hist[k] = rr;
+          const double want = st->rsq_pred;  // how good was the prediction that went into beta (diagnostic)
+          if (rr > 0.0) {
+            const double e = fabs(want - rr) / rr;
+            if (e > st->pred_err) st->pred_err = e;
           }
-          if (yb > Y - 2) {
-            if (atomicAdd(&a.push_count[1], 1u) == need - 1) {
-              a.push_count[1] = 0;
-              __threadfence_system();
-              st_release_sys(a.flag_up, a.push_seq);
-            }
+          const bool conv = sqrt(rr) < st->eps * st->bnorm;  // generic_cg.cpp:339
+          const bool last = (k == st->max_iter - 1);
+          if (conv || last) {
+            st->done = 1;
+            st->hit_max = last ? 1 : 0;  // generic_cg.cpp:356 tests k alone
           }
         }
+        // scalars of the next step: alpha = rsq/<p,Ap> (generic_cg.cpp:326), beta = rsqNew/rsq (:344) with the
+        // numerator predicted:  |r - alpha q|^2 = |r|^2 - 2 Re(alpha <r,q>) + |alpha|^2 |q|^2
+        const cplx al = cdiv(mk(rr, 0.0), mk(total[1], total[2]));
+        const cplx arq = fmul(al, mk(total[3], total[4]));
+        double pred = rr - 2.0 * arq.x + (al.x * al.x + al.y * al.y) * total[5];
+        if (!(pred > 0.0)) pred = 0.0;  // converged to rounding: restart the direction (beta = 0)
+        st->alpha_re = al.x;
+        st->alpha_im = al.y;
+        st->beta = (rr > 0.0) ? pred / rr : 0.0;
+        st->rsq_pred = pred;
+        st->rsq_old = rr;
+        st->pAp_re = total[1];
+        st->pAp_im = total[2];
+        __threadfence();
+        st_release_gpu_s32(&st->step, step + 1);  // every block of this launch is waiting for this word
       }
     }
-  }
-
-  // ---- the six sums: block -> grid (last block) -> ranks (its first warp, peer memory) -> recurrence
-  double total[6];
-  if (!grid_sum<6>(acc, a.red, total)) return;
-  if (a.pr.seq != 0 && threadIdx.x < 32) p2p_allreduce_warp(a.pr, total, 6);
-  if (threadIdx.x == 0) {
-    const double rr = total[0];
-    const int step = st->step;  // 0: the set-up pass (alpha = beta = 0), i >= 1: reference iteration k = i-1
-    if (step > 0) {
-      const int k = step - 1;
-      st->rsq_new = rr;
-      st->iter = k + 1;
-      if (a.hist != nullptr && k < st->hist_cap) a.hist[k] = rr;
-      const double want = st->rsq_pred;  // how good was the prediction that went into beta (diagnostic)
-      if (rr > 0.0) {
-        const double e = fabs(want - rr) / rr;
-        if (e > st->pred_err) st->pred_err = e;
-      }
-      const bool conv = sqrt(rr) < st->eps * st->bnorm;  // generic_cg.cpp:339
-      const bool last = (k == st->max_iter - 1);
-      if (conv || last) {
-        st->done = 1;
-        st->hit_max = last ? 1 : 0;  // generic_cg.cpp:356 tests k alone
-      }
-    }
-    // scalars of the next step: alpha = rsq/<p,Ap> (generic_cg.cpp:326), beta = rsqNew/rsq (:344) with the
-    // numerator predicted:  |r - alpha q|^2 = |r|^2 - 2 Re(alpha <r,q>) + |alpha|^2 |q|^2
-    const cplx al = cdiv(mk(rr, 0.0), mk(total[1], total[2]));
-    const cplx arq = fmul(al, mk(total[3], total[4]));
-    double pred = rr - 2.0 * arq.x + (al.x * al.x + al.y * al.y) * total[5];
-    if (!(pred > 0.0)) pred = 0.0;  // converged to rounding: restart the direction (beta = 0)
-    st->alpha_re = al.x;
-    st->alpha_im = al.y;
-    st->beta = (rr > 0.0) ? pred / rr : 0.0;
-    st->rsq_pred = pred;
-    st->rsq_old = rr;
-    st->pAp_re = total[1];
-    st->pAp_im = total[2];
-    st->step = step + 1;
   }
 }
 
@@ -370,12 +487,49 @@ __global__ void __launch_bounds__(256) cg_step_halo_init_kernel(const cplx* r, c
   }
 }
 
+static unsigned int* g_cs_queue = nullptr;  // item counter of the dynamic schedule (one per process / device)
+static int g_cgstep_enabled = -1;
+static int g_cgstep_variant = -1;   // rows_per_item * 1000 + 100 * CW + 10 * STAGES + MINB
+static int g_cgstep_persist = 1;     // GLB_CGSTEP_PERSIST=0: one launch per CG iteration instead of one per solve
+static const char* g_trace_path = nullptr;
+static int g_trace_launch = 0;
+
+static double g_gfac = 1.0;  // GLB_CGSTEP_GFAC: guided schedule, first item height = rows / (CTAs per strip * gfac)
+struct RowTable {
+  int Y, hmin;
+  double per_strip;
+  int nrb;
+  int* d_rows;
+};
+static std::vector<RowTable> g_row_tables;
+static const RowTable* row_table(int Y, int hmin, double per_strip) {
+  for (const RowTable& t : g_row_tables)
+    if (t.Y == Y && t.hmin == hmin && t.per_strip == per_strip) return &t;
+  std::vector<int> rows;
+  rows.push_back(0);
+  int y = 0;
+  while (y < Y) {
+    int h = (int)((Y - y) / per_strip);
+    if (h < hmin) h = hmin;
+    if (Y - y - h < hmin / 2) h = Y - y;  // do not leave a sliver
+    if (h > Y - y) h = Y - y;
+    y += h;
+    rows.push_back(y);
+  }
+  RowTable t{Y, hmin, per_strip, (int)rows.size() - 1, nullptr};
+  if (cudaMalloc((void**)&t.d_rows, sizeof(int) * rows.size()) != cudaSuccess) return nullptr;
+  if (cudaMemcpy(t.d_rows, rows.data(), sizeof(int) * rows.size(), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+  g_row_tables.push_back(t);
+  return &g_row_tables.back();
+}
+
 template <int CW, int STAGES, int MINB>
-static int launch_cg_step_t(glb_operator* op, CgStepArgs a) {
+static int launch_cg_step_t(glb_operator* op, CgStepArgs a, int rows_per_item) {
   glb_context* ctx = op->ctx;
   constexpr int OUT = CW * 28, TW = OUT + 4;
   auto kern = cg_step_kernel<CW, STAGES, MINB>;
-  const size_t smem = (size_t)STAGES * CS_NARR * TW * sizeof(cplx) + 2 * STAGES * sizeof(unsigned long long);
+  const size_t smem = (size_t)STAGES * CS_NARR * TW * sizeof(cplx) + 2 * STAGES * sizeof(unsigned long long) +
+                      STAGES * sizeof(int4);
   static int per_sm = 0;
   if (per_sm == 0) {
     if (smem + 4096 > 48 * 1024)
@@ -385,61 +539,135 @@ static int launch_cg_step_t(glb_operator* op, CgStepArgs a) {
   }
   const long long nstrips = (a.X + OUT - 1) / OUT;
   const long long max_ctas = (long long)ctx->sm_count * per_sm;
-  long long nrb = max_ctas / nstrips;
-  const long long nrb_cap = a.Y >= 16 ? a.Y / 8 : 1;  // at least 8 rows per item (4 halo rows each)
-  if (nrb > nrb_cap) nrb = nrb_cap;
+  long long nrb;
+  a.rb_rows = nullptr;
+  if (rows_per_item >= 500) {
+    // guided schedule: row blocks shrink from (rows left) / (CTAs per strip * gfac) down to hmin as the sweep nears
+    // the top, so the last items are short (small tail) while most rows are in tall items (little halo re-reading)
+    const int hmin = rows_per_item - 500 > 4 ? rows_per_item - 500 : 4;
+    const double per_strip = (double)max_ctas / (double)nstrips * g_gfac;
+    const RowTable* t = row_table(a.Y, hmin, per_strip);
+    if (!t) return fail(GLB_ERR_CUDA, "cg_step: row table allocation failed");
+    a.rb_rows = t->d_rows;
+    nrb = t->nrb;
+  } else if (rows_per_item > 0) {
+    // dynamic schedule: many more items than CTAs, claimed from a counter as CTAs run out of work
+    nrb = (a.Y + rows_per_item - 1) / rows_per_item;
+  } else {
+    nrb = 0;
+  }
+  if (rows_per_item > 0) {
+    if (g_cs_queue == nullptr) {
+      GLB_CUDA(cudaMalloc((void**)&g_cs_queue, sizeof(unsigned int)));
+      GLB_CUDA(cudaMemset(g_cs_queue, 0, sizeof(unsigned int)));
+    }
+    a.queue = g_cs_queue;
+  }
+  if (rows_per_item <= 0) {
+    nrb = max_ctas / nstrips;  // static: one item per resident CTA
+    const long long nrb_cap = a.Y >= 16 ? a.Y / 8 : 1;  // at least 8 rows per item (4 halo rows each)
+    if (nrb > nrb_cap) nrb = nrb_cap;
+    a.queue = nullptr;
+  }
   if (nrb < 1) nrb = 1;
   a.nstrips = (int)nstrips;
   a.nrb = (int)nrb;
   long long blocks = nstrips * nrb;
   if (blocks > max_ctas) blocks = max_ctas;
   if (blocks > MAX_PARTIAL_BLOCKS) blocks = MAX_PARTIAL_BLOCKS;
-  ProfScope prof(ctx, PROF_CG_STEP);
-  kern<<<(unsigned)blocks, (CW + 1) * 32, smem, ctx->stream>>>(a);
-  GLB_LAUNCH_CHECK();
+  // GLB_CGSTEP_TRACE=<file>: per-CTA record (SM, start, end, items) of step 20 -- where does the tail go?
+  unsigned long long* d_trace = nullptr;
+  a.trace = nullptr;
+  a.trace_step = -1;
+  if (g_trace_path != nullptr && (a.nsteps > 1 ? g_trace_launch++ == 0 : ++g_trace_launch == 20)) {
+    GLB_CUDA(cudaMalloc((void**)&d_trace, sizeof(unsigned long long) * 8 * blocks));
+    GLB_CUDA(cudaMemset(d_trace, 0, sizeof(unsigned long long) * 8 * blocks));
+    a.trace = d_trace;
+    a.trace_step = 20;
+  }
+  {
+    ProfScope prof(ctx, PROF_CG_STEP);
+    if (a.nsteps > 1) {
+      // persistent: every CTA waits for the last block of each step, so all of them must be resident
+      void* kargs[] = {(void*)&a};
+      GLB_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)blocks), dim3((CW + 1) * 32), kargs, smem,
+                                           ctx->stream));
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+    } else {
+      kern<<<(unsigned)blocks, (CW + 1) * 32, smem, ctx->stream>>>(a);
+      GLB_LAUNCH_CHECK();
+    }
+  }
+  if (d_trace != nullptr) {
+    std::vector<unsigned long long> h(8 * blocks);
+    GLB_CUDA(cudaStreamSynchronize(ctx->stream));
+    GLB_CUDA(cudaMemcpy(h.data(), d_trace, sizeof(unsigned long long) * 8 * blocks, cudaMemcpyDeviceToHost));
+    cudaFree(d_trace);
+    if (FILE* f = fopen(g_trace_path, "w")) {
+      fprintf(f, "# block smid t_start_ns t_producer_end_ns items stages t_consumers_end_ns t_after_gridsum_ns"
+                 "   (X=%d Y=%d nstrips=%d nrb=%d blocks=%lld)\n", a.X, a.Y, a.nstrips, a.nrb, blocks);
+      for (long long b = 0; b < blocks; b++)
+        fprintf(f, "%lld %llu %llu %llu %llu %llu %llu %llu\n", b, h[8 * b], h[8 * b + 4], h[8 * b + 1], h[8 * b + 2],
+                h[8 * b + 3], h[8 * b + 5], h[8 * b + 6]);
+      fclose(f);
+    }
+  }
   return GLB_OK;
 }
 
-// GLB_CGSTEP=0 switches the single-kernel iteration off (the two-kernel loop of cg.cu runs instead);
-// GLB_CGSTEP_VARIANT = 100*CW + 10*STAGES + MINB picks an instantiated shape (default 443).
-static int g_cgstep_enabled = -1;
-static int g_cgstep_variant = -1;
-bool cg_step_ok(const glb_operator* op) {
+static void cg_step_env() {
   if (g_cgstep_enabled < 0) {
     const char* e = getenv("GLB_CGSTEP");
     g_cgstep_enabled = (e && atoi(e) == 0) ? 0 : 1;
+    const char* v = getenv("GLB_CGSTEP_VARIANT");
+    g_cgstep_variant = v ? atoi(v) : 433;
+    g_trace_path = getenv("GLB_CGSTEP_TRACE");
+    const char* pe = getenv("GLB_CGSTEP_PERSIST");
+    g_cgstep_persist = (pe && atoi(pe) == 0) ? 0 : 1;
+    if (const char* gf = getenv("GLB_CGSTEP_GFAC")) g_gfac = atof(gf) > 0.0 ? atof(gf) : 1.0;
   }
+}
+
+// GLB_CGSTEP=0 switches the single-kernel iteration off (the two-kernel loop of cg.cu runs instead);
+// GLB_CGSTEP_VARIANT = 1000*rows_per_item + 100*CW + 10*STAGES + MINB picks the schedule (rows_per_item = 0: static,
+// one item per resident CTA) and an instantiated shape.
+bool cg_step_ok(const glb_operator* op) {
+  cg_step_env();
   if (!g_cgstep_enabled || !normal_fused_ok(op) || op->dtype != GLB_COMPLEX) return false;
   if (op->ctx->nranks > 1 && (!comm_p2p(op->ctx) || op->Yloc < 4)) return false;
   return true;
 }
 
+bool cg_step_persistent() {
+  cg_step_env();
+  return g_cgstep_persist != 0;
+}
+
 int launch_cg_step(glb_operator* op, const CgStepArgs& a) {
-  if (g_cgstep_variant < 0) {
-    const char* e = getenv("GLB_CGSTEP_VARIANT");
-    g_cgstep_variant = e ? atoi(e) : 443;
-  }
-  switch (g_cgstep_variant) {
-    case 433: return launch_cg_step_t<4, 3, 3>(op, a);
-    case 453: return launch_cg_step_t<4, 5, 3>(op, a);
-    case 463: return launch_cg_step_t<4, 6, 3>(op, a);
-    case 444: return launch_cg_step_t<4, 4, 4>(op, a);
-    case 442: return launch_cg_step_t<4, 4, 2>(op, a);
-    case 842: return launch_cg_step_t<8, 4, 2>(op, a);
-    case 841: return launch_cg_step_t<8, 4, 1>(op, a);
-    case 243: return launch_cg_step_t<2, 4, 3>(op, a);
-    case 246: return launch_cg_step_t<2, 4, 6>(op, a);
-    default: return launch_cg_step_t<4, 4, 3>(op, a);
+  cg_step_env();
+  const int rows = g_cgstep_variant / 1000;
+  switch (g_cgstep_variant % 1000) {
+    case 423: return launch_cg_step_t<4, 2, 3>(op, a, rows);
+    case 443: return launch_cg_step_t<4, 4, 3>(op, a, rows);
+    case 632: return launch_cg_step_t<6, 3, 2>(op, a, rows);
+    case 642: return launch_cg_step_t<6, 4, 2>(op, a, rows);
+    case 532: return launch_cg_step_t<5, 3, 2>(op, a, rows);
+    case 732: return launch_cg_step_t<7, 3, 2>(op, a, rows);
+    case 333: return launch_cg_step_t<3, 3, 3>(op, a, rows);
+    case 334: return launch_cg_step_t<3, 3, 4>(op, a, rows);
+    default: return launch_cg_step_t<4, 3, 3>(op, a, rows);
   }
 }
 
 int launch_cg_step_halo_init(glb_operator* op, const void* r, const void* q, const void* p, const CgStepArgs& a,
-                             unsigned int* ticket) {
+                             unsigned long long seq, unsigned int* ticket) {
   glb_context* ctx = op->ctx;
+  const size_t gvec = (size_t)2 * op->X;
+  const size_t wr = (size_t)(seq & 1) * 2 * (3 * gvec);
   const int grid = 16;
   cg_step_halo_init_kernel<<<grid, 256, 0, ctx->stream>>>((const cplx*)r, (const cplx*)q, (const cplx*)p, op->X, op->Yloc,
-                                                          a.push_down, a.push_up, a.flag_down, a.flag_up, a.push_seq,
-                                                          ticket);
+                                                          a.peer_down + wr + 3 * gvec, a.peer_up + wr, a.flag_down,
+                                                          a.flag_up, seq, ticket);
   GLB_LAUNCH_CHECK();
   return GLB_OK;
 }
@@ -450,12 +678,10 @@ int launch_cg_step_halo_init(glb_operator* op, const void* r, const void* q, con
 // iteration (default), 0 the two-kernel loop; variant > 0 picks an instantiated kernel shape (100*consumer warps +
 // 10*stages + blocks per SM), 0 keeps the current one.  Returns the previous on/off setting.
 extern "C" int glb_cg_step_mode(int on, int variant) {
-  if (glb::g_cgstep_enabled < 0) {
-    const char* e = getenv("GLB_CGSTEP");
-    glb::g_cgstep_enabled = (e && atoi(e) == 0) ? 0 : 1;
-  }
+  glb::cg_step_env();
   const int prev = glb::g_cgstep_enabled;
   glb::g_cgstep_enabled = on ? 1 : 0;
+  glb::g_cgstep_persist = (on == 2) ? 0 : 1;  // on = 2: single-kernel iteration, one launch per iteration
   if (variant > 0) glb::g_cgstep_variant = variant;
   return prev;
 }

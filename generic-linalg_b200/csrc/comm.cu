@@ -160,6 +160,13 @@ P2PRed comm_p2p_red(glb_context* ctx) {
   return pr;
 }
 
+// the same for a kernel that performs up to `count` reductions of its own (step s uses seq + s): reserves the range
+P2PRed comm_p2p_red_range(glb_context* ctx, unsigned long long count) {
+  P2PRed pr = comm_p2p_red(ctx);
+  if (count > 1) ctx->comm->red_seq += count - 1;
+  return pr;
+}
+
 // Start halo exchange number op->halo_seq+1 on the peer-memory path: where this rank's boundary rows go
 // (remote pointers), which flags to raise there, which local flags to wait on.  Also points
 // op->ghost_lo/hi at the buffers of this exchange's parity.

@@ -209,6 +209,7 @@ char* comm_peer(glb_context* ctx, int g);        // rank g's arena as mapped her
 long long comm_spin_budget(const glb_context* ctx);
 unsigned int* comm_ticket(glb_context* ctx);     // self-resetting block counter for small push kernels
 P2PRed comm_p2p_red(glb_context* ctx);
+P2PRed comm_p2p_red_range(glb_context* ctx, unsigned long long count);
 struct HaloTargets {
   char* dst_down_hi;
   char* dst_up_lo;

@@ -251,7 +251,8 @@ int glb_cg_solve(glb_operator* op, void* d_x, const void* d_b, int max_iter, dou
  * GLB_CGSTEP=0 in the environment selects the two-kernel loop. */
 double glb_cg_last_pred_err(void);
 /* measurement / test aid: on = 0 makes glb_cg_solve use the two-kernel loop on that operator too, on = 1 (default)
- * the single-kernel iteration; variant > 0 selects a kernel shape (100*consumer warps + 10*stages + blocks per SM).
+ * the single-kernel iteration; variant > 0 selects schedule and kernel shape (1000*rows per work item [0 = static partition] + 100*consumer
+ * warps + 10*stages + blocks per SM).
  * Returns the previous on/off value. */
 int glb_cg_step_mode(int on, int variant);
 

@@ -3,7 +3,7 @@
 
     python tools/tune_cgstep.py [L] [variant ...]
 
-For every variant (100*consumer warps + 10*stages + blocks per SM) one CGNE solve at L^2 is timed per launch with
+For every variant (1000*rows per item [0 = static partition] + 100*consumer warps + 10*stages + blocks per SM) one CGNE solve at L^2 is timed per launch with
 CUDA events (glb_prof_*); prints one JSON object per variant, and the two-kernel loop for comparison."""
 import json
 import os
@@ -18,7 +18,7 @@ from __graft_entry__ import _load_pkg  # noqa: E402
 glb = _load_pkg()
 ctx = glb.Context(device=0)
 L = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-variants = [int(v) for v in sys.argv[2:]] or [443, 433, 453, 463, 444, 442, 842, 841, 243, 246]
+variants = [int(v) for v in sys.argv[2:]] or [433, 423, 432, 64433, 32433, 128433]
 try:
     PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
 except Exception:
@@ -42,11 +42,16 @@ def one(label):
     info = ctx.solve("CG", N, x, bp, max_iter=5000, eps=1e-10)
     ctx.prof_enable(False)
     it = info["iter"]
-    ts = ctx.prof_read(7)[:it + 1]
+    ts = ctx.prof_read(7)
     rec = {"variant": label, "L": L, "iterations": it}
-    if ts:
+    if len(ts) == 1:     # persistent kernel: one launch ran all it + 1 steps
+        ms = ts[0] / (it + 1)
+        rec.update(launches=1, cg_step_ms=ms, GBps=160.0 * V / ms / 1e6, frac=160.0 * V / ms / 1e6 / PEAK,
+                   ms_per_iteration=ms)
+    elif ts:
+        ts = ts[:it + 1]
         ms = float(np.mean(ts[2:]))
-        rec.update(cg_step_ms=ms, GBps=160.0 * V / ms / 1e6, frac=160.0 * V / ms / 1e6 / PEAK,
+        rec.update(launches=len(ts), cg_step_ms=ms, GBps=160.0 * V / ms / 1e6, frac=160.0 * V / ms / 1e6 / PEAK,
                    ms_min=float(np.min(ts[2:])), ms_max=float(np.max(ts[2:])), ms_per_iteration=ms)
     else:
         f, u = ctx.prof_read(1)[:it - 1], ctx.prof_read(3)[:it]
@@ -62,4 +67,3 @@ for v in variants:
         print(json.dumps({"variant": v, "error": str(e)}), flush=True)
 ctx.cg_step_mode(False)
 one("two-kernel loop")
-ctx.cg_step_mode(True, 443)
