@@ -97,6 +97,52 @@ __device__ __forceinline__ cplx cs_row(bool eta_neg, cplx below, cplx centre, cp
   return fadd(fscale(0.5, h), fscale(mass, centre));
 }
 
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// grid_sum of common.cuh with optional time stamps (tr != nullptr): where does the tail of a step go?
+template <int NRED>
+__device__ __forceinline__ bool grid_sum_tr(double (&v)[NRED], const ReduceWs& ws, double (&total)[NRED],
+                                            unsigned long long* tr) {
+  __shared__ double s_red[NRED * 32];
+  __shared__ bool s_last;
+  block_sum<NRED>(v, s_red);
+  if (threadIdx.x == 0) {
+    if (tr) tr[8] = gtime();
+#pragma unroll
+    for (int r = 0; r < NRED; r++) ws.partials[r * MAX_PARTIAL_BLOCKS + blockIdx.x] = v[r];
+    __threadfence();
+    if (tr) tr[9] = gtime();
+    const unsigned int t = atomicInc(ws.ticket, gridDim.x - 1);  // wraps to 0 after the last block
+    s_last = (t == gridDim.x - 1);
+    if (tr) tr[10] = gtime();
+  }
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+  double acc[NRED];
+#pragma unroll
+  for (int r = 0; r < NRED; r++) acc[r] = 0.0;
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+#pragma unroll
+    for (int r = 0; r < NRED; r++) acc[r] += __ldcg(&ws.partials[r * MAX_PARTIAL_BLOCKS + b]);
+  }
+  if (tr && threadIdx.x == 0) tr[11] = gtime();
+  __syncthreads();  // s_red reuse
+  block_sum<NRED>(acc, s_red);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int r = 0; r < NRED; r++) {
+      total[r] = acc[r];
+      ws.result_dev[r] = acc[r];
+    }
+  }
+  return true;
+}
+
 // arrays of one stage, in this order
 enum { CS_R = 0, CS_Q = 1, CS_P = 2, CS_XV = 3, CS_UX = 4, CS_UY = 5, CS_NARR = 6 };
 
@@ -208,7 +254,10 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) cg_step_kernel(const CgSt
     const bool tracing = (a.trace != nullptr) && (step == a.trace_step);
     unsigned long long t_start = 0;
     int items_done = 0;
-    if (tracing && threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start));
+    if (a.trace != nullptr && threadIdx.x == 0) {
+      t_start = gtime();
+      if (step == a.trace_step + 1) a.trace[16 * (size_t)blockIdx.x + 13] = t_start;  // when the next step began here
+    }
 
     if (warp == CW) {
       // ================================================================== producer (one elected lane)
@@ -391,7 +440,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) cg_step_kernel(const CgSt
     if (tracing) {
       // per CTA: [0] SM, [1] producer out of work, [2] items, [3] stages, [4] start, [5] consumers done, [6] after the
       // grid-wide sum (last block only: the step's effective end)
-      unsigned long long* tr = a.trace + 8 * (size_t)blockIdx.x;
+      unsigned long long* tr = a.trace + 16 * (size_t)blockIdx.x;
       unsigned long long tn;
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tn));
       if (threadIdx.x == CW * 32) {
@@ -410,7 +459,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) cg_step_kernel(const CgSt
 
     // ---- the six sums: block -> grid (last block) -> ranks (its first warp, peer memory) -> recurrence
     double total[6];
-    if (grid_sum<6>(acc, a.red, total)) {
+    if (grid_sum_tr<6>(acc, a.red, total, tracing ? a.trace + 16 * (size_t)blockIdx.x : nullptr)) {
       if (a.pr.seq != 0 && threadIdx.x < 32) {
         P2PRed pr = a.pr;
         pr.seq += (unsigned long long)step;
@@ -419,7 +468,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) cg_step_kernel(const CgSt
       if (threadIdx.x == 0) {
         unsigned long long tn = 0;
         if (tracing || a.step_ns != nullptr) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tn));
-        if (tracing) a.trace[8 * (size_t)blockIdx.x + 6] = tn;
+        if (tracing) a.trace[16 * (size_t)blockIdx.x + 6] = tn;
         if (a.step_ns != nullptr && step < a.step_ns_cap) a.step_ns[step] = tn;
         if (a.queue != nullptr) *a.queue = 0;  // every block has claimed its last item: ready for the next step
         const double rr = total[0];
@@ -454,8 +503,10 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) cg_step_kernel(const CgSt
         st->rsq_old = rr;
         st->pAp_re = total[1];
         st->pAp_im = total[2];
+        if (tracing) a.trace[16 * (size_t)blockIdx.x + 12] = gtime();
         __threadfence();
         st_release_gpu_s32(&st->step, step + 1);  // every block of this launch is waiting for this word
+        if (tracing) a.trace[16 * (size_t)blockIdx.x + 14] = gtime();
       }
     }
   }
@@ -580,10 +631,15 @@ static int launch_cg_step_t(glb_operator* op, CgStepArgs a, int rows_per_item) {
   a.trace = nullptr;
   a.trace_step = -1;
   if (g_trace_path != nullptr && (a.nsteps > 1 ? g_trace_launch++ == 0 : ++g_trace_launch == 20)) {
-    GLB_CUDA(cudaMalloc((void**)&d_trace, sizeof(unsigned long long) * 8 * blocks));
-    GLB_CUDA(cudaMemset(d_trace, 0, sizeof(unsigned long long) * 8 * blocks));
+    GLB_CUDA(cudaMalloc((void**)&d_trace, sizeof(unsigned long long) * 16 * blocks));
+    GLB_CUDA(cudaMemset(d_trace, 0, sizeof(unsigned long long) * 16 * blocks));
     a.trace = d_trace;
     a.trace_step = 20;
+    if (a.nsteps > 1) {  // and when every step of this launch ended
+      a.step_ns_cap = 4096;
+      GLB_CUDA(cudaMalloc((void**)&a.step_ns, sizeof(unsigned long long) * a.step_ns_cap));
+      GLB_CUDA(cudaMemset(a.step_ns, 0, sizeof(unsigned long long) * a.step_ns_cap));
+    }
   }
   {
     ProfScope prof(ctx, PROF_CG_STEP);
@@ -599,16 +655,28 @@ static int launch_cg_step_t(glb_operator* op, CgStepArgs a, int rows_per_item) {
     }
   }
   if (d_trace != nullptr) {
-    std::vector<unsigned long long> h(8 * blocks);
+    std::vector<unsigned long long> h(16 * blocks);
     GLB_CUDA(cudaStreamSynchronize(ctx->stream));
-    GLB_CUDA(cudaMemcpy(h.data(), d_trace, sizeof(unsigned long long) * 8 * blocks, cudaMemcpyDeviceToHost));
+    GLB_CUDA(cudaMemcpy(h.data(), d_trace, sizeof(unsigned long long) * 16 * blocks, cudaMemcpyDeviceToHost));
     cudaFree(d_trace);
+    if (a.step_ns != nullptr) {
+      std::vector<unsigned long long> hs(a.step_ns_cap);
+      GLB_CUDA(cudaMemcpy(hs.data(), a.step_ns, sizeof(unsigned long long) * a.step_ns_cap, cudaMemcpyDeviceToHost));
+      cudaFree(a.step_ns);
+      if (FILE* f = fopen((std::string(g_trace_path) + ".steps").c_str(), "w")) {
+        for (int i = 0; i < a.step_ns_cap && hs[i] != 0; i++) fprintf(f, "%d %llu\n", i, hs[i]);
+        fclose(f);
+      }
+    }
     if (FILE* f = fopen(g_trace_path, "w")) {
-      fprintf(f, "# block smid t_start_ns t_producer_end_ns items stages t_consumers_end_ns t_after_gridsum_ns"
-                 "   (X=%d Y=%d nstrips=%d nrb=%d blocks=%lld)\n", a.X, a.Y, a.nstrips, a.nrb, blocks);
-      for (long long b = 0; b < blocks; b++)
-        fprintf(f, "%lld %llu %llu %llu %llu %llu %llu %llu\n", b, h[8 * b], h[8 * b + 4], h[8 * b + 1], h[8 * b + 2],
-                h[8 * b + 3], h[8 * b + 5], h[8 * b + 6]);
+      fprintf(f, "# block smid t_start t_producer_end items stages t_consumers_end t_after_gridsum t_blocksum t_fence "
+                 "t_ticket t_partials t_updated t_next_start t_published   (ns; X=%d Y=%d nstrips=%d nrb=%d blocks=%lld)\n",
+              a.X, a.Y, a.nstrips, a.nrb, blocks);
+      for (long long b = 0; b < blocks; b++) {
+        const unsigned long long* t = &h[16 * b];
+        fprintf(f, "%lld %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu\n", b, t[0], t[4], t[1], t[2],
+                t[3], t[5], t[6], t[8], t[9], t[10], t[11], t[12], t[13], t[14]);
+      }
       fclose(f);
     }
   }

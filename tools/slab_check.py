@@ -199,6 +199,29 @@ def main():
         tol_it = 0.10 if solver.startswith("BICGSTAB") else 0.02   # BiCGStab is chaotic (see tests/test_solvers_gpu.py)
         ok = abs(info["iter"] - want["iter"]) <= max(1, round(tol_it * want["iter"])) and rr < kw["eps"] * 1.000001
         check("solve %s" % name, ok, "iter %d (oracle %d) true rel res %.2e" % (info["iter"], want["iter"], rr))
+    # ---- the single-kernel CG iteration on slabs (cgstep.cu): the iterate after m = 1..5 iterations equals the
+    # reference's to rounding -- every row of r, p, q next to a slab edge has then crossed NVLink m times -- on the
+    # square lattice and on a thin one (four rows per rank and a partial strip in x)
+    for (Xc, Yc) in ((X, Y), (132, 4 * world), (16, 8 * world)):
+        rr_ = orc.rng(5)
+        Uc = rr_.gauss_gauge_u1(Xc, Yc, 6.0)
+        bc = rr_.gaussian(Xc * Yc)
+        x0c = rr_.gaussian(Xc * Yc)
+        oNc = orc.op("STAG_NORMAL_U1", Xc, Yc, mass=0.1, links=Uc)
+        Nc_ = ctx.staggered(Uc, Xc, Yc, 0.1, glb.STAG_NORMAL)
+        y0c, Ylc = ctx.slab_bounds(Yc)
+        slc_ = slice(y0c * Xc, (y0c + Ylc) * Xc)
+        worst, its = 0.0, []
+        for m in (1, 2, 3, 5):
+            want_x, winfo = orc.solve("CG", oNc, bc, x0=x0c, max_iter=m, eps=1e-30)
+            xd = ctx.vector(Ylc * Xc).upload(x0c[slc_])
+            rep = ctx.cg_device(Nc_, xd, ctx.vector(Ylc * Xc).upload(bc[slc_]), max_iter=m, eps=1e-30)
+            xg = gather(xd.download())
+            worst = max(worst, float(np.linalg.norm(xg - want_x) / np.linalg.norm(want_x)))
+            its.append(rep["iterations"])
+        check("single-kernel CG on slabs, %dx%d: first iterations" % (Xc, Yc), worst < 1e-13 and its == [1, 2, 3, 5],
+              "max rel err %.1e, beta prediction err %.1e" % (worst, ctx.cg_last_pred_err()))
+        Nc_.destroy()
     shifts = [0.0, 0.01, 0.05, 0.25]
     xs = [ctx.vector(Yloc * X) for _ in shifts]
     info, _ = ctx.solve_cg_m(N, xs, ctx.vector(Yloc * X).upload(bprime[sl]), shifts, max_iter=5000, eps=1e-10)
