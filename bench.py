@@ -300,7 +300,8 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
 
-    numa_note = bind_to_gpu_numa_node(local) if world > 1 else "single GPU: not bound"
+    numa_note = (bind_to_gpu_numa_node(local) if world > 1 and not os.environ.get("BENCH_NO_BIND")
+                 else "not bound")
     import torch
     import torch.distributed as dist
     from __graft_entry__ import _load_pkg

@@ -283,6 +283,16 @@ int glbx_host_solve(int solver, const glbx_opdesc* d, void* phi, const void* phi
                     int restart_freq, int l, int verbosity, glbx_result* out) {
   HostOp h;
   if (!build_host_op(d, &h)) return GLB_ERR_ARG;
+  {
+    // slab form of the reference call: with a communicator attached to the default context every rank passes ITS rows
+    // of phi / phi0 (size = X * Yloc * Nc) together with the global operator description, of which it reads its rows
+    glb_context* ctx = glb200_default_context();
+    if (glb_comm_size(ctx) > 1) {
+      int y0 = 0, yl = 0;
+      if (glb_slab_bounds(ctx, d->Y, &y0, &yl) != GLB_OK) return GLB_ERR_ARG;
+      h.size = (int)((long long)h.size / d->Y * yl);
+    }
+  }
   inversion_verbose_struct v;
   make_verb(verbosity, &v);
   inversion_info inf;

@@ -432,8 +432,10 @@ inversion_info host_solve(const char* alg, T* phi, T* phi0, int size, void (*mv)
     void* cb_extra = 0;
     if (kind != B_NONE) {
       lease(kind, extra, &L);
-      if (glb_comm_size(ctx) == 1 && (size_t)size != glb_op_local_size(L.op))
-        throw Error("`size` does not match the operator's lattice");
+      if ((size_t)size != glb_op_local_size(L.op))
+        throw Error(glb_comm_size(ctx) == 1 ? "`size` does not match the operator's lattice"
+                                            : "`size` must be this rank's share of the lattice (X * Yloc * Nc): with a "
+                                              "communicator every rank passes its own rows of the vectors");
       cb = &glb200_apply_dev;
       cb_extra = L.op;
       if (L.comp) {  // the index operator: a composition of device operators behind a device callback
