@@ -545,7 +545,7 @@ static int g_cgstep_persist = 1;     // GLB_CGSTEP_PERSIST=0: one launch per CG 
 static const char* g_trace_path = nullptr;
 static int g_trace_launch = 0;
 
-static double g_gfac = 1.0;  // GLB_CGSTEP_GFAC: guided schedule, first item height = rows / (CTAs per strip * gfac)
+static double g_gfac = 0.0;  // GLB_CGSTEP_GFAC: guided schedule, first item height = rows / (CTAs per strip * gfac); 0 = by slab height
 struct RowTable {
   int Y, hmin;
   double per_strip;
@@ -596,7 +596,10 @@ static int launch_cg_step_t(glb_operator* op, CgStepArgs a, int rows_per_item) {
     // guided schedule: row blocks shrink from (rows left) / (CTAs per strip * gfac) down to hmin as the sweep nears
     // the top, so the last items are short (small tail) while most rows are in tall items (little halo re-reading)
     const int hmin = rows_per_item - 500 > 4 ? rows_per_item - 500 : 4;
-    const double per_strip = (double)max_ctas / (double)nstrips * g_gfac;
+    // measured on the B200 (profiles/r02_tune_cgstep.md): gfac 1.0 is best up to 2048 rows, 1.25 - 1.5 at 4096
+    double gfac = g_gfac;
+    if (gfac <= 0.0) gfac = a.Y <= 2048 ? 1.0 : (a.Y >= 4096 ? 1.25 : 1.0 + 0.25 * (a.Y - 2048) / 2048.0);
+    const double per_strip = (double)max_ctas / (double)nstrips * gfac;
     const RowTable* t = row_table(a.Y, hmin, per_strip);
     if (!t) return fail(GLB_ERR_CUDA, "cg_step: row table allocation failed");
     a.rb_rows = t->d_rows;
@@ -688,11 +691,11 @@ static void cg_step_env() {
     const char* e = getenv("GLB_CGSTEP");
     g_cgstep_enabled = (e && atoi(e) == 0) ? 0 : 1;
     const char* v = getenv("GLB_CGSTEP_VARIANT");
-    g_cgstep_variant = v ? atoi(v) : 433;
+    g_cgstep_variant = v ? atoi(v) : 508433;  // guided schedule down to 8-row items, 4 consumer warps, 3 stages, 3 CTAs/SM
     g_trace_path = getenv("GLB_CGSTEP_TRACE");
     const char* pe = getenv("GLB_CGSTEP_PERSIST");
     g_cgstep_persist = (pe && atoi(pe) == 0) ? 0 : 1;
-    if (const char* gf = getenv("GLB_CGSTEP_GFAC")) g_gfac = atof(gf) > 0.0 ? atof(gf) : 1.0;
+    if (const char* gf = getenv("GLB_CGSTEP_GFAC")) g_gfac = atof(gf) > 0.0 ? atof(gf) : 0.0;
   }
 }
 

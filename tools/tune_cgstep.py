@@ -17,16 +17,19 @@ from __graft_entry__ import _load_pkg  # noqa: E402
 
 glb = _load_pkg()
 ctx = glb.Context(device=0)
-L = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-variants = [int(v) for v in sys.argv[2:]] or [433, 423, 432, 64433, 32433, 128433]
+# first argument: L (square lattice) or XxY
+_a = sys.argv[1] if len(sys.argv) > 1 else "4096"
+X, Y = (int(_a.split("x")[0]), int(_a.split("x")[1])) if "x" in _a else (int(_a), int(_a))
+L = X
+variants = [int(v) for v in sys.argv[2:]] or [433, 508433, 32433]
 try:
     PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
 except Exception:
     PEAK = 6650.0
-links, b_h = ctx.synthetic_inputs(L, L)
-N = ctx.staggered(links, L, L, 0.1, glb.STAG_NORMAL)
-Dd = ctx.staggered(links, L, L, 0.1, glb.STAG_DAGGER)
-V = L * L
+links, b_h = ctx.synthetic_inputs(X, Y)
+N = ctx.staggered(links, X, Y, 0.1, glb.STAG_NORMAL)
+Dd = ctx.staggered(links, X, Y, 0.1, glb.STAG_DAGGER)
+V = X * Y
 b = ctx.vector(V).upload(b_h)
 bp = ctx.vector(V)
 Dd.apply(bp, b)
@@ -43,7 +46,7 @@ def one(label):
     ctx.prof_enable(False)
     it = info["iter"]
     ts = ctx.prof_read(7)
-    rec = {"variant": label, "L": L, "iterations": it}
+    rec = {"variant": label, "lattice": [X, Y], "iterations": it}
     if len(ts) == 1:     # persistent kernel: one launch ran all it + 1 steps
         ms = ts[0] / (it + 1)
         rec.update(launches=1, cg_step_ms=ms, GBps=160.0 * V / ms / 1e6, frac=160.0 * V / ms / 1e6 / PEAK,
