@@ -460,6 +460,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) cg_step_kernel(const CgSt
     // ---- the six sums: block -> grid (last block) -> ranks (its first warp, peer memory) -> recurrence
     double total[6];
     if (grid_sum_tr<6>(acc, a.red, total, tracing ? a.trace + 16 * (size_t)blockIdx.x : nullptr)) {
+      if (a.step_ns != nullptr && threadIdx.x == 0 && 2 * step + 1 < a.step_ns_cap) a.step_ns[2 * step] = gtime();
       if (a.pr.seq != 0 && threadIdx.x < 32) {
         P2PRed pr = a.pr;
         pr.seq += (unsigned long long)step;
@@ -469,7 +470,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) cg_step_kernel(const CgSt
         unsigned long long tn = 0;
         if (tracing || a.step_ns != nullptr) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tn));
         if (tracing) a.trace[16 * (size_t)blockIdx.x + 6] = tn;
-        if (a.step_ns != nullptr && step < a.step_ns_cap) a.step_ns[step] = tn;
+        if (a.step_ns != nullptr && 2 * step + 1 < a.step_ns_cap) a.step_ns[2 * step + 1] = tn;  // after the rank sum
         if (a.queue != nullptr) *a.queue = 0;  // every block has claimed its last item: ready for the next step
         const double rr = total[0];
         // step 0: the set-up pass (alpha = beta = 0), step i >= 1: reference iteration k = i-1
@@ -639,7 +640,7 @@ static int launch_cg_step_t(glb_operator* op, CgStepArgs a, int rows_per_item) {
     a.trace = d_trace;
     a.trace_step = 20;
     if (a.nsteps > 1) {  // and when every step of this launch ended
-      a.step_ns_cap = 4096;
+      a.step_ns_cap = 8192;  // two stamps per step: local sums done, sum over ranks done
       GLB_CUDA(cudaMalloc((void**)&a.step_ns, sizeof(unsigned long long) * a.step_ns_cap));
       GLB_CUDA(cudaMemset(a.step_ns, 0, sizeof(unsigned long long) * a.step_ns_cap));
     }
@@ -667,7 +668,9 @@ static int launch_cg_step_t(glb_operator* op, CgStepArgs a, int rows_per_item) {
       GLB_CUDA(cudaMemcpy(hs.data(), a.step_ns, sizeof(unsigned long long) * a.step_ns_cap, cudaMemcpyDeviceToHost));
       cudaFree(a.step_ns);
       if (FILE* f = fopen((std::string(g_trace_path) + ".steps").c_str(), "w")) {
-        for (int i = 0; i < a.step_ns_cap && hs[i] != 0; i++) fprintf(f, "%d %llu\n", i, hs[i]);
+        fprintf(f, "# step t_local_sums_done_ns t_rank_sum_done_ns\n");
+        for (int i = 0; 2 * i + 1 < a.step_ns_cap && hs[2 * i + 1] != 0; i++)
+          fprintf(f, "%d %llu %llu\n", i, hs[2 * i], hs[2 * i + 1]);
         fclose(f);
       }
     }
@@ -692,7 +695,7 @@ static void cg_step_env() {
     g_cgstep_enabled = (e && atoi(e) == 0) ? 0 : 1;
     const char* v = getenv("GLB_CGSTEP_VARIANT");
     g_cgstep_variant = v ? atoi(v) : 508433;  // guided schedule down to 8-row items, 4 consumer warps, 3 stages, 3 CTAs/SM
-    g_trace_path = getenv("GLB_CGSTEP_TRACE");
+    g_trace_path = getenv("GLB_CGSTEP_TRACE");  // on slabs give every rank its own file (the launcher's job)
     const char* pe = getenv("GLB_CGSTEP_PERSIST");
     g_cgstep_persist = (pe && atoi(pe) == 0) ? 0 : 1;
     if (const char* gf = getenv("GLB_CGSTEP_GFAC")) g_gfac = atof(gf) > 0.0 ? atof(gf) : 0.0;
