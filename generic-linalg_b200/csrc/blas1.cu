@@ -317,7 +317,7 @@ cg_update_kernel(CgState* st, double* hist, const T* p, T* x, const T* Ap, T* r,
   }
   double total[1];
   if (!grid_sum<1>(acc, red, total)) return;  // only the block that arrived last goes on
-  if (defer == 2 && threadIdx.x < 32) p2p_allreduce_warp(pr, total, 1);  // slabs over peer memory: finish the sum here
+  if (defer == 2) p2p_allreduce_block(pr, total, 1);  // slabs over peer memory: finish the sum here
   if (threadIdx.x == 0) {
     if (defer == 1) {  // slab run over NCCL: the sum over ranks and the recurrence step follow on the stream
       st->partial[0] = total[0];

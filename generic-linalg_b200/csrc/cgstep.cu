@@ -28,7 +28,7 @@
 // those rows straight into the neighbours' ghost rows (remote stores over NVLink) while the rest of the
 // kernel runs; the last of them raises the neighbour's flag.  The next step's producers of boundary
 // row blocks wait for that flag before they read ghost rows -- interior row blocks never wait.  The
-// kernel's last block completes the sum of the six scalars over ranks itself (p2p_allreduce_warp):
+// kernel's last block completes the sum of the six scalars over ranks itself (p2p_allreduce_block):
 // one rank-wide synchronisation per CG iteration, no separate halo or reduction launch.
 #include <climits>
 #include <cstdlib>
@@ -461,10 +461,10 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) cg_step_kernel(const CgSt
     double total[6];
     if (grid_sum_tr<6>(acc, a.red, total, tracing ? a.trace + 16 * (size_t)blockIdx.x : nullptr)) {
       if (a.step_ns != nullptr && threadIdx.x == 0 && 2 * step + 1 < a.step_ns_cap) a.step_ns[2 * step] = gtime();
-      if (a.pr.seq != 0 && threadIdx.x < 32) {
+      if (a.pr.seq != 0) {  // every thread of the last block: one warp per peer
         P2PRed pr = a.pr;
         pr.seq += (unsigned long long)step;
-        p2p_allreduce_warp(pr, total, 6);
+        p2p_allreduce_block(pr, total, 6);
       }
       if (threadIdx.x == 0) {
         unsigned long long tn = 0;

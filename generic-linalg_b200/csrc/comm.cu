@@ -90,6 +90,7 @@ struct Comm {
   unsigned long long red_seq = 0;
   unsigned int* ticket = nullptr;
   long long spin_budget = 0;  // clock64() ticks a kernel waits for a peer (GLB_P2P_TIMEOUT_S; 0 = for ever)
+  int flush = 1;              // GLB_P2P_FLUSH: fence.sys after the sends of a reduction
 };
 
 void comm_destroy(glb_context* ctx) {
@@ -134,12 +135,219 @@ __global__ void halo_wait_kernel(const unsigned long long* flag_lo, const unsign
   spin_until(flag_lo, seq, budget);
   spin_until(flag_hi, seq, budget);
 }
-// stand-alone one-shot allreduce (used when no producing kernel can finish the sum itself)
-__global__ void p2p_allreduce_kernel(double* vals, int n, P2PRed pr) {  // one warp
-  for (int t = 0; t < n; t++) {
-    double v[1] = {vals[t]};
-    p2p_allreduce_warp(pr, v, 1, t);
-    if (threadIdx.x == 0) vals[t] = v[0];
+// stand-alone one-shot allreduce (used when no producing kernel can finish the sum itself): one warp per peer
+__global__ void p2p_allreduce_kernel(double* vals, int n, P2PRed pr) {
+  __shared__ double s_v[P2P_RED_WIDTH];
+  if (threadIdx.x == 0)
+    for (int t = 0; t < n; t++) s_v[t] = vals[t];
+  p2p_allreduce_block(pr, s_v, n);  // reads and writes through thread 0
+  if (threadIdx.x == 0)
+    for (int t = 0; t < n; t++) vals[t] = s_v[t];
+}
+
+// ---- measurement aid: how long does the rank-wide sum take when every rank arrives at (nearly) the same time?
+// One warp per rank: [busy-wait busy_cycles] -> [sum of 6 doubles over ranks] -> record the time spent in the sum.
+//   variant = 10 * send + recv
+//   send 0: st.relaxed.sys words, lane g -> rank g (the first protocol)   1: + fence.sys after the sends   2: st.release.sys last word
+//        3: atom.exch.sys words (not posted)
+//   recv 0: ld.relaxed.sys poll   1: ld.acquire.sys   2: atom.add.sys(+0) poll (read at the home L2)   3: ld.cv
+//        4: ld.relaxed.sys with __nanosleep(200) between polls   5: ld.volatile
+__device__ __forceinline__ unsigned long long poll_word(const unsigned long long* w, int recv) {
+  unsigned long long v;
+  switch (recv) {
+    case 1: return ld_acquire_sys(w);
+    case 2: return atomicAdd_system((unsigned long long*)w, 0ull);
+    case 3: asm volatile("ld.global.cv.u64 %0, [%1];" : "=l"(v) : "l"(w) : "memory"); return v;
+    case 5: asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(w) : "memory"); return v;
+    default: return ld_relaxed_sys(w);
+  }
+}
+__global__ void p2p_bench_kernel(P2PRed pr, int iters, long long busy_cycles, int variant, float* wait_us) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  __shared__ double s_got[8][6];
+  if ((variant / 10) % 10 != 7 && warp > 0) return;  // only variant 7x uses the other warps
+  const int send = (variant / 10) % 10, recv = variant % 10;
+  if (variant >= 100) {  // only the first `active` ranks take part (the others leave at once)
+    const int active = variant / 100;
+    if (pr.rank >= active) return;
+    pr.nranks = active;
+  }
+  Mailbox* mine = pr.mb[pr.rank];
+  Mailbox* peer = pr.mb[lane < pr.nranks ? lane : pr.rank];
+  for (int it = 0; it < iters; it++, pr.seq++) {
+    const long long c0 = clock64();
+    while (clock64() - c0 < busy_cycles) {
+    }
+    __syncwarp();
+    unsigned long long ta, tb;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ta));
+    const int slot = (int)(pr.seq % P2P_RED_SLOTS);
+    const unsigned long long tag = ((pr.seq % 0xffffffffull) + 1ull) << 32;
+    double vals[6];
+    for (int t = 0; t < 6; t++) vals[t] = 1.0 + t + pr.rank;
+    double sum[6];
+    if (send == 7) {
+      // one warp per peer: warp g sends this rank's 12 words to rank g with ONE store instruction (lane = word), then
+      // polls the 12 words rank g sent here; the sums are formed through shared memory
+      __syncthreads();
+      if (warp < pr.nranks && lane < 12) {
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(vals[lane / 2]);
+        const unsigned long long word = tag | ((lane & 1) ? (bits >> 32) : (bits & 0xffffffffull));
+        st_relaxed_sys(&pr.mb[warp]->ll[slot][pr.rank][lane], word);
+        const unsigned long long* w = &mine->ll[slot][warp][lane];
+        unsigned long long v;
+        const long long t0 = clock64();
+        for (;;) {
+          v = ld_relaxed_sys(w);
+          if ((v & 0xffffffff00000000ull) == tag) break;
+          if (pr.budget > 0 && clock64() - t0 > pr.budget) __trap();
+        }
+        const unsigned long long other = __shfl_xor_sync(0xfffu, v, 1);
+        if (!(lane & 1))
+          s_got[warp][lane / 2] = __longlong_as_double((long long)((v & 0xffffffffull) | (other << 32)));
+      }
+      __syncthreads();
+      for (int t = 0; t < 6; t++) {
+        double sacc = 0.0;
+        for (int r = 0; r < pr.nranks; r++) sacc += s_got[r][t];
+        sum[t] = sacc;
+      }
+    } else if (send == 8) {
+      // recursive doubling: log2(ranks) rounds, one partner per round; lane = word (12 words = 6 values).  Rows 8..11
+      // of the mailbox (sending-rank index) serve as the rounds' receive buffers.
+      double cur = (lane < 12) ? vals[lane / 2] : 0.0;
+      int round = 0;
+      for (int d = 1; d < pr.nranks; d <<= 1, round++) {
+        const int partner = pr.rank ^ d;
+        if (lane < 12) {
+          const unsigned long long bits = (unsigned long long)__double_as_longlong(cur);
+          const unsigned long long word = tag | ((lane & 1) ? (bits >> 32) : (bits & 0xffffffffull));
+          st_relaxed_sys(&pr.mb[partner]->ll[slot][8 + round][lane], word);
+          const unsigned long long* w = &mine->ll[slot][8 + round][lane];
+          unsigned long long v;
+          const long long t0 = clock64();
+          for (;;) {
+            v = ld_relaxed_sys(w);
+            if ((v & 0xffffffff00000000ull) == tag) break;
+            if (pr.budget > 0 && clock64() - t0 > pr.budget) __trap();
+          }
+          const unsigned long long other = __shfl_xor_sync(0xfffu, v, 1);
+          const unsigned long long lo = (lane & 1) ? other : v, hi = (lane & 1) ? v : other;
+          const double theirs = __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
+          // the lower rank's partial goes first: both partners form the same sum bit for bit
+          cur = (pr.rank & d) ? (theirs + cur) : (cur + theirs);
+        }
+      }
+      for (int t = 0; t < 6; t++) sum[t] = __shfl_sync(full, cur, 2 * t);
+    } else if (send >= 5) {
+      // spread over the warp: lane = part * 8 + peer (up to 8 ranks); every lane sends / polls only its share of the
+      // six values, so no thread issues more than two or three system-scope stores in a row
+      const int g = lane & 7, part = lane >> 3;  // 4 parts
+      Mailbox* pg = pr.mb[g < pr.nranks ? g : pr.rank];
+      if (g < pr.nranks) {
+        for (int t = part; t < 6; t += 4) {
+          const unsigned long long bits = (unsigned long long)__double_as_longlong(vals[t]);
+          const unsigned long long w0 = tag | (bits & 0xffffffffull), w1 = tag | (bits >> 32);
+          unsigned long long* dst = &pg->ll[slot][pr.rank][2 * t];
+          if (send == 6) {
+            asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(w0), "l"(w1) : "memory");
+          } else {
+            st_relaxed_sys(dst, w0);
+            st_relaxed_sys(dst + 1, w1);
+          }
+        }
+      }
+      double got[2] = {0.0, 0.0};
+      if (g < pr.nranks) {
+        int k = 0;
+        for (int t = part; t < 6; t += 4, k++) {
+          const unsigned long long* w = &mine->ll[slot][g][2 * t];
+          unsigned long long lo, hi;
+          const long long t0 = clock64();
+          for (;;) {
+            if (send == 6) {
+              asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(w) : "memory");
+            } else {
+              lo = ld_relaxed_sys(w);
+              hi = ld_relaxed_sys(w + 1);
+            }
+            if ((lo & 0xffffffff00000000ull) == tag && (hi & 0xffffffff00000000ull) == tag) break;
+            if (pr.budget > 0 && clock64() - t0 > pr.budget) __trap();
+          }
+          got[k] = __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
+        }
+      }
+      for (int t = 0; t < 6; t++) {
+        double sacc = 0.0;
+        for (int r = 0; r < pr.nranks; r++) sacc += __shfl_sync(full, got[t / 4], (t % 4) * 8 + r);  // rank order
+        sum[t] = sacc;
+      }
+    } else {
+    if (lane < pr.nranks) {
+      for (int w = 0; w < 12; w++) {
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(vals[w / 2]);
+        const unsigned long long word = tag | ((w & 1) ? (bits >> 32) : (bits & 0xffffffffull));
+        unsigned long long* dst = &peer->ll[slot][pr.rank][w];
+        if (send == 3)
+          atomicExch_system(dst, word);
+        else if (send == 2 && w == 11)
+          st_release_sys(dst, word);
+        else
+          st_relaxed_sys(dst, word);
+      }
+    }
+    if (send == 1) __threadfence_system();
+    for (int t = 0; t < 6; t++) {
+      double got = 0.0;
+      if (lane < pr.nranks) {
+        const unsigned long long* w = &mine->ll[slot][lane][2 * t];
+        unsigned long long lo, hi;
+        const long long t0 = clock64();
+        for (;;) {
+          lo = poll_word(w, recv);
+          hi = poll_word(w + 1, recv);
+          if ((lo & 0xffffffff00000000ull) == tag && (hi & 0xffffffff00000000ull) == tag) break;
+          if (recv == 4) __nanosleep(200);
+          if (pr.budget > 0 && clock64() - t0 > pr.budget) __trap();
+        }
+        got = __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
+      }
+      double s = 0.0;
+      for (int g = 0; g < pr.nranks; g++) s += __shfl_sync(full, got, g);
+      sum[t] = s;
+    }
+    }
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tb));
+    if (lane == 0) wait_us[it] = (float)(tb - ta) * 1e-3f + (sum[0] < 0.0 ? 1.0f : 0.0f);
+  }
+}
+
+// ping-pong between rank 0 and rank `peer`: one 8-byte word each way per round trip; rtt_us[i] on rank 0
+__global__ void p2p_pingpong_kernel(P2PRed pr, int peer, int iters, float* rtt_us) {
+  if (pr.rank != 0 && pr.rank != peer) return;
+  const int other = pr.rank == 0 ? peer : 0;
+  unsigned long long* out = &pr.mb[other]->ll[0][pr.rank][0];
+  const unsigned long long* in = &pr.mb[pr.rank]->ll[0][other][0];
+  for (int it = 0; it < iters; it++) {
+    const unsigned long long word = ((pr.seq + it) << 8) | 1ull;
+    unsigned long long ta, tb;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ta));
+    if (pr.rank == 0) {
+      st_relaxed_sys(out, word);
+      while (ld_relaxed_sys(in) != word) {
+      }
+    } else {
+      while (ld_relaxed_sys(in) != word) {
+      }
+      st_relaxed_sys(out, word);
+    }
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tb));
+    if (pr.rank == 0) rtt_us[it] = (float)(tb - ta) * 1e-3f;
+    const long long c0 = clock64();
+    while (clock64() - c0 < 20000) {
+    }
   }
 }
 
@@ -157,6 +365,7 @@ P2PRed comm_p2p_red(glb_context* ctx) {
   pr.nranks = ctx->nranks;
   pr.seq = ++c->red_seq;
   pr.budget = c->spin_budget;
+  pr.flush = c->flush;
   return pr;
 }
 
@@ -283,7 +492,7 @@ int allreduce_device(glb_context* ctx, double* d_vals, int n) {
   if (!ctx->comm) return fail(GLB_ERR_STATE, "reduction before glb_comm_init");
   Comm* c = ctx->comm;
   if (c->p2p && n <= P2P_RED_WIDTH) {
-    p2p_allreduce_kernel<<<1, 32, 0, ctx->stream>>>(d_vals, n, comm_p2p_red(ctx));
+    p2p_allreduce_kernel<<<1, 32 * (ctx->nranks < 16 ? ctx->nranks : 16), 0, ctx->stream>>>(d_vals, n, comm_p2p_red(ctx));
     GLB_LAUNCH_CHECK();
     return GLB_OK;
   }
@@ -323,6 +532,8 @@ int glb_comm_init(glb_context* ctx, int rank, int nranks, const char id[GLB_COMM
     int khz = 2000000;
     cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
     c->spin_budget = secs > 0.0 ? (long long)(secs * 1e3 * (double)khz) : 0;
+    const char* ef = getenv("GLB_P2P_FLUSH");
+    c->flush = ef ? atoi(ef) : 1;
   }
   ncclUniqueId_t u;
   std::memcpy(u.internal, id, GLB_COMM_ID_BYTES);
@@ -394,6 +605,36 @@ int glb_comm_init(glb_context* ctx, int rank, int nranks, const char id[GLB_COMM
 }
 
 int glb_comm_p2p_enabled(glb_context* ctx) { return comm_p2p(ctx) ? 1 : 0; }
+
+// measurement aid (tools/p2p_bench.py): see p2p_bench_kernel.  Collective: every rank calls it with equal arguments.
+int glb_dbg_p2p_pingpong(glb_context* ctx, int peer, int iters, float* rtt_us_host) {
+  if (!comm_p2p(ctx)) return fail(GLB_ERR_STATE, "glb_dbg_p2p_pingpong needs the peer-memory communicator");
+  float* d = nullptr;
+  GLB_CUDA(cudaMalloc((void**)&d, sizeof(float) * iters));
+  GLB_CUDA(cudaMemset(d, 0, sizeof(float) * iters));
+  P2PRed pr = comm_p2p_red_range(ctx, (unsigned long long)iters);
+  p2p_pingpong_kernel<<<1, 1, 0, ctx->stream>>>(pr, peer, iters, d);
+  GLB_LAUNCH_CHECK();
+  GLB_CUDA(cudaStreamSynchronize(ctx->stream));
+  GLB_CUDA(cudaMemcpy(rtt_us_host, d, sizeof(float) * iters, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  return GLB_OK;
+}
+
+int glb_dbg_p2p_bench(glb_context* ctx, int variant, int iters, double busy_us, float* wait_us_host) {
+  if (!comm_p2p(ctx)) return fail(GLB_ERR_STATE, "glb_dbg_p2p_bench needs the peer-memory communicator");
+  float* d = nullptr;
+  GLB_CUDA(cudaMalloc((void**)&d, sizeof(float) * iters));
+  int khz = 2000000;
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
+  P2PRed pr = comm_p2p_red_range(ctx, (unsigned long long)iters);
+  p2p_bench_kernel<<<1, 256, 0, ctx->stream>>>(pr, iters, (long long)(busy_us * 1e-3 * khz), variant, d);
+  GLB_LAUNCH_CHECK();
+  GLB_CUDA(cudaStreamSynchronize(ctx->stream));
+  GLB_CUDA(cudaMemcpy(wait_us_host, d, sizeof(float) * iters, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  return GLB_OK;
+}
 int glb_comm_rank(glb_context* ctx) { return ctx->rank; }
 int glb_comm_size(glb_context* ctx) { return ctx->nranks; }
 

@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(NORM_THREADS, 3) normal_kernel(const NormArgs 
     double total[NRED];
     if (grid_sum<NRED>(acc, a.red, total)) {  // the block that arrived last
       // slab run over peer memory: its first warp finishes the sum over ranks
-      if (a.cg != nullptr && a.cg_role == 3 && threadIdx.x < 32) p2p_allreduce_warp(a.pr, total, 2);
+      if (a.cg != nullptr && a.cg_role == 3) p2p_allreduce_block(a.pr, total, 2);
       if (threadIdx.x == 0 && a.cg != nullptr) {
         if (a.cg_role == 1 || a.cg_role == 3) {  // <p,Ap> ready: generic_cg.cpp:326 / :345
           a.cg->pAp_re = total[0];

@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(N1_THREADS, MINB) normal1_kernel(const NormArg
   if (NDOT > 0) {
     double total[NRED];
     if (grid_sum<NRED>(acc, a.red, total)) {
-      if (a.cg != nullptr && a.cg_role == 3 && threadIdx.x < 32) p2p_allreduce_warp(a.pr, total, 2);
+      if (a.cg != nullptr && a.cg_role == 3) p2p_allreduce_block(a.pr, total, 2);
       if (threadIdx.x == 0 && a.cg != nullptr) {
         if (a.cg_role == 1 || a.cg_role == 3) {
           a.cg->pAp_re = total[0];

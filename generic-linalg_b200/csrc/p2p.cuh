@@ -1,9 +1,9 @@
 // p2p.cuh -- device side of the NVLink peer-memory communication (see comm.cu).
 //
 // Every rank maps every peer's arena; a Mailbox sits at offset 0 of each.  A kernel whose last block
-// has just finished this rank's partial sums can complete the sum over ranks ITSELF: lane g of one warp
-// stores the values into slot [seq % 4][rank] of peer g's mailbox and polls the words rank g sent here,
-// then the warp adds the G contributions in rank order.  All ranks obtain the bit-identical result; no
+// has just finished this rank's partial sums can complete the sum over ranks ITSELF: one warp per peer
+// stores the values into slot [seq % 4][rank] of that peer's mailbox and polls the words it sent here,
+// then the block adds the G contributions in rank order.  All ranks obtain the bit-identical result; no
 // library call, no extra kernel.  The words travel NCCL-LL style: every 8-byte store carries 32 bits of
 // payload and a 32-bit tag derived from the sequence number, so data and flag arrive in one atomic
 // store -- no fence, no second round trip, and the G peers are served in parallel by G lanes.
@@ -26,6 +26,7 @@ struct P2PRed {  // by-value kernel argument; seq == 0 means "not used"
   int rank, nranks;
   unsigned long long seq;
   long long budget;  // spin budget in clock64() ticks before the kernel gives up on a peer; 0 = wait for ever
+  int flush;         // 1: a system-scope fence after the sends pushes the posted 8-byte stores out at once (GLB_P2P_FLUSH)
 };
 
 struct HaloWait {  // by-value kernel argument; seq == 0 means "nothing to wait for"
@@ -62,41 +63,55 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long
   asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-// Sum vals[0..n) over all ranks, in place.  Call from all 32 lanes of exactly ONE warp per rank; vals is
-// read from lane 0 and valid in every lane on return.  `base` offsets the word index when one reduction
-// (one seq) is fed through several calls.
-__device__ __forceinline__ void p2p_allreduce_warp(const P2PRed& pr, double* vals, int n, int base = 0) {
-  const unsigned full = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
+// Sum vals[0..n) over all ranks, in place.  Call from EVERY thread of exactly one block per rank (block size a
+// multiple of 32); vals is read from thread 0 and valid in thread 0 on return (n <= P2P_RED_WIDTH).
+//
+// One WARP per peer, one LANE per word: warp w serves ranks w, w + W, ...; its lanes 0 .. 2m-1 store the 2m tagged
+// words of this rank's values into that peer's mailbox with ONE store instruction and then poll, again one lane per
+// word, the words that peer sent here.  Measured on 8 B200s (tools/p2p_bench.py, profiles/r02_p2p_allreduce.md): a
+// single warp that stores to all peers itself -- lane g sending 12 words to rank g one after the other -- takes
+// 18 us per sum of six doubles (the stores to different GPUs leave the SM one destination after the other, about one
+// NVLink round trip each), this shape 1.9 us (NCCL's all-reduce of the same six doubles: 22 us).
+__device__ __forceinline__ void p2p_allreduce_block(const P2PRed& pr, double* vals, int n) {
+  __shared__ double s_vals[P2P_RED_WIDTH];
+  __shared__ double s_got[P2P_MAX_RANKS][P2P_RED_WIDTH];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int slot = (int)(pr.seq % P2P_RED_SLOTS);
   const unsigned long long tag = ((pr.seq % 0xffffffffull) + 1ull) << 32;  // never 0: fresh mailboxes are zero
   Mailbox* mine = pr.mb[pr.rank];
-  Mailbox* peer = pr.mb[lane < pr.nranks ? lane : pr.rank];
-  for (int t = 0; t < n; t++) {
-    const unsigned long long bits = (unsigned long long)__double_as_longlong(__shfl_sync(full, vals[t], 0));
-    if (lane < pr.nranks) {
-      st_relaxed_sys(&peer->ll[slot][pr.rank][2 * (base + t)], tag | (bits & 0xffffffffull));
-      st_relaxed_sys(&peer->ll[slot][pr.rank][2 * (base + t) + 1], tag | (bits >> 32));
-    }
-  }
-  for (int t = 0; t < n; t++) {
-    double got = 0.0;
-    if (lane < pr.nranks) {
-      const unsigned long long* w = &mine->ll[slot][lane][2 * (base + t)];
-      const long long t0 = clock64();
-      unsigned long long lo, hi;
-      for (;;) {
-        lo = ld_relaxed_sys(w);
-        hi = ld_relaxed_sys(w + 1);
-        if ((lo & 0xffffffff00000000ull) == tag && (hi & 0xffffffff00000000ull) == tag) break;
-        if (pr.budget > 0 && clock64() - t0 > pr.budget) __trap();  // a peer that never shows up must not hang the GPU
+  if (threadIdx.x == 0)
+    for (int t = 0; t < n; t++) s_vals[t] = vals[t];
+  __syncthreads();
+  for (int c = 0; c < n; c += 16) {  // 16 values = 32 words = one warp-wide store
+    const int m = (n - c < 16) ? n - c : 16;
+    if (lane < 2 * m) {
+      const unsigned mask = (m == 16) ? 0xffffffffu : ((1u << (2 * m)) - 1u);
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(s_vals[c + lane / 2]);
+      const unsigned long long word = tag | ((lane & 1) ? (bits >> 32) : (bits & 0xffffffffull));
+      for (int g = warp; g < pr.nranks; g += nwarp) st_relaxed_sys(&pr.mb[g]->ll[slot][pr.rank][2 * c + lane], word);
+      for (int g = warp; g < pr.nranks; g += nwarp) {
+        const unsigned long long* w = &mine->ll[slot][g][2 * c + lane];
+        const long long t0 = clock64();
+        unsigned long long v;
+        for (;;) {
+          v = ld_relaxed_sys(w);
+          if ((v & 0xffffffff00000000ull) == tag) break;
+          if (pr.budget > 0 && clock64() - t0 > pr.budget) __trap();  // a peer that never shows up must not hang the GPU
+        }
+        const unsigned long long other = __shfl_xor_sync(mask, v, 1);
+        if (!(lane & 1)) s_got[g][c + lane / 2] = __longlong_as_double((long long)((v & 0xffffffffull) | (other << 32)));
       }
-      got = __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
     }
-    double s = 0.0;
-    for (int g = 0; g < pr.nranks; g++) s += __shfl_sync(full, got, g);  // rank order: same bits everywhere
-    vals[t] = s;
   }
+  __syncthreads();
+  if (threadIdx.x < n) {
+    double s = 0.0;
+    for (int g = 0; g < pr.nranks; g++) s += s_got[g][threadIdx.x];  // rank order: the same bits on every rank
+    s_vals[threadIdx.x] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int t = 0; t < n; t++) vals[t] = s_vals[t];
 }
 // block-wide wait for the neighbours' ghost rows (thread 0 spins, everybody syncs)
 __device__ __forceinline__ void halo_wait_block(const HaloWait& hw) {
