@@ -133,9 +133,11 @@ static int cs_prepare_slab(glb_operator* op) {
   if (op->cs_ready) return GLB_OK;
   const size_t gbytes = (size_t)3 * 2 * op->X * sizeof(cplx);
   size_t off = 0;
-  if (!comm_arena_alloc(op->ctx, 4 * gbytes + 256, &off))
+  unsigned long long seq0 = 0;
+  if (!comm_arena_alloc(op->ctx, 4 * gbytes + 256, &off, &seq0))
     return fail(GLB_ERR_STATE, "peer-memory arena exhausted (GLB_P2P_ARENA_MB)");
   op->cs_off = off;
+  op->cs_seq = seq0;
   op->cs_ready = true;
   return GLB_OK;
 }
@@ -306,6 +308,7 @@ using namespace glb;
 extern "C" int glb_cg_solve_supported(const glb_operator* op) {
   if (!op) return 0;
   if (op->composite) return 0;  // multi-pass stencil views: no fused epilogue, the host-scalar shell runs them
+  if (op->kind == OPK_GAMMA5) return 0;  // gamma_5 alone has no fused reductions either
   return (op->ctx->nranks == 1 || normal_fused_ok(op)) ? 1 : 0;
 }
 

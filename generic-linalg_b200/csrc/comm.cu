@@ -22,6 +22,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <utility>
 #include <vector>
 
 #include "p2p.cuh"
@@ -89,6 +90,11 @@ struct Comm {
   char* peer[P2P_MAX_RANKS] = {nullptr};
   unsigned long long red_seq = 0;
   unsigned int* ticket = nullptr;
+  struct FreeRegion {
+    size_t off, bytes;
+    unsigned long long seq;
+  };
+  std::vector<FreeRegion> arena_free;  // regions returned by destroyed operators, with their last exchange number
   long long spin_budget = 0;  // clock64() ticks a kernel waits for a peer (GLB_P2P_TIMEOUT_S; 0 = for ever)
   int flush = 1;              // GLB_P2P_FLUSH: fence.sys after the sends of a reduction
 };
@@ -408,15 +414,41 @@ int halo_p2p_begin(glb_operator* op, int nrows, HaloTargets* t) {
 }
 
 // carve `bytes` (256-byte aligned) out of the arena; identical call sequences on all ranks give
-// identical offsets.  Returns nullptr when the arena is exhausted (caller falls back to NCCL buffers).
-void* comm_arena_alloc(glb_context* ctx, size_t bytes, size_t* offset) {
+// identical offsets.  Regions of destroyed operators are reused (exact size match: operators of one lattice
+// size come and go, e.g. a new gauge field per configuration or a multigrid set-up per solve).  A reused region is
+// NOT cleared -- ranks are not synchronised here, a slower peer may still be storing the old operator's last rows
+// into it -- instead the new operator continues the old one's exchange numbering (*seq_start): flags only ever
+// grow, and ghost rows are read only after the flag of their own exchange has arrived.  Returns nullptr when the
+// arena is exhausted (the caller falls back to NCCL buffers).
+void* comm_arena_alloc(glb_context* ctx, size_t bytes, size_t* offset, unsigned long long* seq_start) {
   Comm* c = ctx->comm;
+  if (seq_start) *seq_start = 0;
   if (!c || !c->p2p) return nullptr;
   const size_t need = (bytes + 255) & ~(size_t)255;
-  if (c->arena_used + need > c->arena_bytes) return nullptr;
+  for (size_t i = 0; i < c->arena_free.size(); i++) {
+    if (c->arena_free[i].bytes == need) {
+      *offset = c->arena_free[i].off;
+      if (seq_start) *seq_start = c->arena_free[i].seq;
+      c->arena_free.erase(c->arena_free.begin() + i);
+      return c->arena + *offset;
+    }
+  }
+  if (c->arena_used + need > c->arena_bytes) {
+    if (getenv("GLB_VERBOSE"))
+      fprintf(stderr, "[glb200] rank %d: peer-memory arena exhausted (%zu MB, GLB_P2P_ARENA_MB): this operator's halos "
+                      "go through NCCL\n", ctx->rank, c->arena_bytes >> 20);
+    return nullptr;
+  }
   *offset = c->arena_used;
   c->arena_used += need;
   return c->arena + *offset;
+}
+// give a region back (same order on every rank, so the free lists stay identical); seq = its last exchange number
+void comm_arena_free(glb_context* ctx, size_t offset, size_t bytes, unsigned long long seq) {
+  Comm* c = ctx->comm;
+  if (!c || !c->p2p) return;
+  Comm::FreeRegion f = {offset, (bytes + 255) & ~(size_t)255, seq};
+  c->arena_free.push_back(f);
 }
 
 static int halo_exchange_p2p(glb_operator* op, const void* send_lo, const void* send_hi, int nrows) {

@@ -146,12 +146,6 @@ __device__ __forceinline__ void stv(cplx* p, const cplx (&v)[SPT]) {
   }
 }
 
-// L2 prefetch of a contiguous byte range by the TMA unit (no registers, no completion tracking):
-// cp.async.bulk.prefetch.L2 (SASS UBLKPF).  addr 16-byte aligned, bytes a multiple of 16.
-__device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-
 // cp.async (LDGSTS): 16-byte global -> shared copies that bypass the register file; a per-thread
 // queue of commit groups gives deep prefetch without spending registers on staging.
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {

@@ -46,10 +46,13 @@ static int alloc_ghosts(glb_operator* op, int depth) {
   GLB_CUDA(cudaMalloc(&op->send_hi, bytes));
   // peer-memory path: [parity 0: lo|hi][parity 1: lo|hi][flag_lo, flag_hi] at the same offset on every rank
   size_t off = 0;
-  char* area = (char*)comm_arena_alloc(op->ctx, 4 * bytes + 256, &off);
+  unsigned long long seq0 = 0;
+  char* area = (char*)comm_arena_alloc(op->ctx, 4 * bytes + 256, &off, &seq0);
   if (area) {
     op->ghost_p2p = true;
     op->ghost_off = off;
+    op->ghost_arena_bytes = 4 * bytes + 256;
+    op->halo_seq = seq0;  // a reused region: carry on counting where its previous owner stopped
     op->ghost_lo = area;
     op->ghost_hi = area + bytes;
     return GLB_OK;
@@ -104,9 +107,11 @@ static int upload_links(glb_operator* op, const void* h_links, bool local = fals
 
 using namespace glb;
 
-extern "C" {
+// The constructors proper.  A failure part-way (upload, ghost rows, temporaries) leaves a half-built operator in
+// *out; the extern "C" wrappers below destroy it and hand back a null handle.
+namespace {
 
-int glb_op_create_laplace(glb_context* ctx, int dtype, int X, int Y, int Nc, double diag_re, double diag_im,
+int create_laplace_impl(glb_context* ctx, int dtype, int X, int Y, int Nc, double diag_re, double diag_im,
                           glb_operator** out) {
   if (dtype != GLB_REAL && dtype != GLB_COMPLEX) return fail(GLB_ERR_ARG, "bad dtype");
   if (dtype == GLB_REAL && diag_im != 0.0) return fail(GLB_ERR_ARG, "real Laplacian with complex diagonal");
@@ -119,7 +124,7 @@ int glb_op_create_laplace(glb_context* ctx, int dtype, int X, int Y, int Nc, dou
 
 // real free staggered operator of tests/multishift/multishift.cpp:677 (served by the simple
 // nearest-neighbour kernel; flag 0x100 selects the staggered signs, diag carries the mass)
-int glb_op_create_staggered_free_real(glb_context* ctx, int X, int Y, double mass, glb_operator** out) {
+int create_staggered_free_real_impl(glb_context* ctx, int X, int Y, double mass, glb_operator** out) {
   int rc = new_op(ctx, OPK_LAPLACE, GLB_REAL, X, Y, 1, out);
   if (rc) return rc;
   (*out)->diag_re = mass;
@@ -129,7 +134,7 @@ int glb_op_create_staggered_free_real(glb_context* ctx, int X, int Y, double mas
   return alloc_ghosts(*out, 1);
 }
 
-int glb_op_create_laplace_u1(glb_context* ctx, const void* h_links, int X, int Y, double mass, glb_operator** out) {
+int create_laplace_u1_impl(glb_context* ctx, const void* h_links, int X, int Y, double mass, glb_operator** out) {
   if (!h_links) return fail(GLB_ERR_ARG, "gauged Laplacian needs links");
   int rc = new_op(ctx, OPK_LAPLACE_U1, GLB_COMPLEX, X, Y, 1, out);
   if (rc) return rc;
@@ -139,7 +144,7 @@ int glb_op_create_laplace_u1(glb_context* ctx, const void* h_links, int X, int Y
   return alloc_ghosts(*out, 1);
 }
 
-int glb_op_create_staggered(glb_context* ctx, const void* h_links, int X, int Y, double mass, unsigned flags,
+int create_staggered_impl(glb_context* ctx, const void* h_links, int X, int Y, double mass, unsigned flags,
                             glb_operator** out) {
   if ((flags & GLB_STAG_NORMAL) && (flags & (GLB_STAG_DAGGER | GLB_STAG_GAMMA5)))
     return fail(GLB_ERR_ARG, "NORMAL cannot be combined with DAGGER/GAMMA5");
@@ -160,7 +165,7 @@ int glb_op_create_staggered(glb_context* ctx, const void* h_links, int X, int Y,
   return alloc_ghosts(op, 2);
 }
 
-int glb_op_create_staggered_local(glb_context* ctx, const void* h_links_local, int X, int Y, double mass,
+int create_staggered_local_impl(glb_context* ctx, const void* h_links_local, int X, int Y, double mass,
                                     unsigned flags, glb_operator** out) {
   if (!h_links_local) return fail(GLB_ERR_ARG, "glb_op_create_staggered_local needs links");
   if ((flags & GLB_STAG_NORMAL) && (flags & (GLB_STAG_DAGGER | GLB_STAG_GAMMA5)))
@@ -178,11 +183,11 @@ int glb_op_create_staggered_local(glb_context* ctx, const void* h_links_local, i
   return alloc_ghosts(op, 2);
 }
 
-int glb_op_create_gamma5(glb_context* ctx, int X, int Y, glb_operator** out) {
+int create_gamma5_impl(glb_context* ctx, int X, int Y, glb_operator** out) {
   return new_op(ctx, OPK_GAMMA5, GLB_COMPLEX, X, Y, 1, out);
 }
 
-int glb_op_create_stencil2d(glb_context* ctx, const void* clover, const void* hopping, const void* two_link, int X,
+int create_stencil2d_impl(glb_context* ctx, const void* clover, const void* hopping, const void* two_link, int X,
                             int Y, int nc, const double shift[2], const double eo_shift[2],
                             const double dof_shift[2], glb_operator** out) {
   if (!clover || !hopping) return fail(GLB_ERR_ARG, "stencil2d needs clover and hopping arrays");
@@ -213,6 +218,52 @@ int glb_op_create_stencil2d(glb_context* ctx, const void* clover, const void* ho
   }
   GLB_CUDA(cudaStreamSynchronize(ctx->stream));
   return alloc_ghosts(op, op->has_two ? 2 : 1);
+}
+
+}  // namespace
+
+// on any error path the half-built operator is destroyed and *out set to null (a caller that checks the return
+// code and then frees the handle must not be handed a leaked object)
+template <typename F>
+static int guarded_create(glb_operator** out, F body) {
+  if (out) *out = nullptr;
+  const int rc = body();
+  if (rc != GLB_OK && out && *out) {
+    glb_op_destroy(*out);
+    *out = nullptr;
+  }
+  return rc;
+}
+
+extern "C" {
+
+int glb_op_create_laplace(glb_context* ctx, int dtype, int X, int Y, int Nc, double diag_re, double diag_im,
+                          glb_operator** out) {
+  return guarded_create(out, [&] { return create_laplace_impl(ctx, dtype, X, Y, Nc, diag_re, diag_im, out); });
+}
+int glb_op_create_staggered_free_real(glb_context* ctx, int X, int Y, double mass, glb_operator** out) {
+  return guarded_create(out, [&] { return create_staggered_free_real_impl(ctx, X, Y, mass, out); });
+}
+int glb_op_create_laplace_u1(glb_context* ctx, const void* h_links, int X, int Y, double mass, glb_operator** out) {
+  return guarded_create(out, [&] { return create_laplace_u1_impl(ctx, h_links, X, Y, mass, out); });
+}
+int glb_op_create_staggered(glb_context* ctx, const void* h_links, int X, int Y, double mass, unsigned flags,
+                            glb_operator** out) {
+  return guarded_create(out, [&] { return create_staggered_impl(ctx, h_links, X, Y, mass, flags, out); });
+}
+int glb_op_create_staggered_local(glb_context* ctx, const void* h_links_local, int X, int Y, double mass,
+                                  unsigned flags, glb_operator** out) {
+  return guarded_create(out, [&] { return create_staggered_local_impl(ctx, h_links_local, X, Y, mass, flags, out); });
+}
+int glb_op_create_gamma5(glb_context* ctx, int X, int Y, glb_operator** out) {
+  return guarded_create(out, [&] { return create_gamma5_impl(ctx, X, Y, out); });
+}
+int glb_op_create_stencil2d(glb_context* ctx, const void* clover, const void* hopping, const void* two_link, int X,
+                            int Y, int nc, const double shift[2], const double eo_shift[2],
+                            const double dof_shift[2], glb_operator** out) {
+  return guarded_create(out, [&] {
+    return create_stencil2d_impl(ctx, clover, hopping, two_link, X, Y, nc, shift, eo_shift, dof_shift, out);
+  });
 }
 
 }  // extern "C"
@@ -260,7 +311,10 @@ int glb_op_destroy(glb_operator* op) {
   if (!op->ghost_p2p) {
     cudaFree(op->ghost_lo);
     cudaFree(op->ghost_hi);
+  } else {
+    comm_arena_free(op->ctx, op->ghost_off, op->ghost_arena_bytes, op->halo_seq);  // every rank in the same order
   }
+  if (op->cs_ready) comm_arena_free(op->ctx, op->cs_off, 4 * ((size_t)3 * 2 * op->X * sizeof(cplx)) + 256, op->cs_seq);
   cudaFree(op->send_lo);
   cudaFree(op->send_hi);
   cudaFree(op->tmp2);
@@ -545,9 +599,8 @@ int glb_stag_eoprec_reconstruct(glb_operator* op, void* d_lhs_full, const void* 
 
 int glb_op_apply_dot(glb_operator* op, void* d_out, const void* d_in, const void* d_w, int want_norm, double dots[3]) {
   glb_context* ctx = op->ctx;
-  if (op->kind == OPK_GAMMA5) return fail(GLB_ERR_ARG, "gamma5 has no fused reductions");
-  if (op->composite) {  // several passes: the reductions follow as their own passes
-    int rc0 = apply_composite(op, d_out, d_in);
+  if (op->composite || op->kind == OPK_GAMMA5) {  // no fused epilogue: the reductions follow as their own passes
+    int rc0 = op->composite ? apply_composite(op, d_out, d_in) : launch_gamma5(op, d_out, d_in);
     if (rc0) return rc0;
     const size_t n = glb_op_local_size(op);
     rc0 = glb_dot(ctx, op->dtype, n, d_w ? d_w : d_in, d_out, dots);

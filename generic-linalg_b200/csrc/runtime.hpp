@@ -114,6 +114,7 @@ struct glb_operator {
   int ghost_depth = 0;
   bool ghost_p2p = false;      // ghost rows live in the peer-mapped arena (NVLink stores + flags)
   size_t ghost_off = 0;        // offset of this operator's ghost area inside every rank's arena
+  size_t ghost_arena_bytes = 0;
   unsigned long long halo_seq = 0;
   void* send_lo = nullptr;     // staging for boundary rows produced on the fly (device CG)
   void* send_hi = nullptr;
@@ -220,6 +221,7 @@ struct HaloTargets {
   size_t bytes;
 };
 int halo_p2p_begin(glb_operator* op, int nrows, HaloTargets* t);
-void* comm_arena_alloc(glb_context* ctx, size_t bytes, size_t* offset);
+void* comm_arena_alloc(glb_context* ctx, size_t bytes, size_t* offset, unsigned long long* seq_start);
+void comm_arena_free(glb_context* ctx, size_t offset, size_t bytes, unsigned long long seq);
 
 }  // namespace glb

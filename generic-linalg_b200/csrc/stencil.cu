@@ -56,7 +56,6 @@ struct StagArgs {
   ReduceWs red;
   CgState* cg;
   int cg_role;   // 1: epilogue publishes <p,Ap> into the CG state
-  int pf_rows;   // L2 prefetch distance in rows (0 = off)
   int nrb;       // number of row blocks per strip
   // FAM_STAG_EO: the even/odd pieces of operators.cpp:456-616
   int eo_parity;    // 0: update even sites (D_eo), 1: update odd sites (D_oe); the other parity gets the `else` value
@@ -175,29 +174,7 @@ __global__ void __launch_bounds__(STAG_THREADS) stag_kernel(const StagArgs a) {
     for (int k = 0; k < PF; k++)
       if (ya + k < yb) fetch(ya + k, st[k]);
 
-    // TMA L2 prefetch of this warp's row segment pf_rows steps ahead (one lane, one request per array)
-    const int pf_x = strip * strip_w + (threadIdx.x & ~31) * SPT;
-    const int pf_w = min(X, pf_x + 32 * SPT) - pf_x;
-    auto prefetch_rows = [&](int y) {  // data needed when row y is the centre: psi(y+1), U(y)
-      if (lane == 0 && pf_w > 0 && y + 1 <= Yloc) {
-        const unsigned bytes = (unsigned)pf_w * 16u;
-        if (FUSE_XPAY) {
-          prefetch_l2_bulk(rowp(a.r, a.r_lo, a.r_hi, y + 1) + pf_x, bytes);
-          prefetch_l2_bulk(rowp(a.pold, a.pold_lo, a.pold_hi, y + 1) + pf_x, bytes);
-        } else {
-          prefetch_l2_bulk(rowp(a.in, a.in_lo, a.in_hi, y + 1) + pf_x, bytes);
-        }
-        if (HAS_U && y < Yloc) {
-          prefetch_l2_bulk(a.Ux + (size_t)y * X + pf_x, bytes);
-          prefetch_l2_bulk(a.Uy + (size_t)y * X + pf_x, bytes);
-        }
-      }
-    };
-    if (a.pf_rows > 0)
-      for (int k = 1; k < a.pf_rows; k++) prefetch_rows(ya + k);
-
     auto row_body = [&](const int y, const RowLoad<SPT>& cur) {
-      if (a.pf_rows > 0) prefetch_rows(y + a.pf_rows);
       // edge lanes: x neighbours that live in another warp / across the periodic seam
       cplx cl, cr, uxl;
       if (edge_l) {
@@ -413,10 +390,6 @@ static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
 }
-static int env_int_cached_pf() {
-  static int v = env_int("GLB_PF_L2", 0);  // measured slower with L2 bulk prefetch (profiles/): off
-  return v < 0 ? 0 : v;
-}
 static int stag_pf() {
   static int v = env_int("GLB_STAG_PF", 1);
   return v == 2 ? 2 : 1;
@@ -516,7 +489,6 @@ int launch_staggered(glb_operator* op, void* out, const void* in, bool dagger, c
   if (!f.to_host) a.red.result_host = nullptr;
   a.cg = (CgState*)f.cg_state;
   a.cg_role = f.cg_role;
-  a.pf_rows = env_int_cached_pf();
   const int ndot = (f.w != nullptr || f.w_is_input) ? (f.want_norm ? 2 : 1) : 0;
   if (ndot == 0 && f.want_norm) return fail(GLB_ERR_ARG, "want_norm requires a dot partner");
   const bool spt2 = (op->X % 2 == 0) && stag_spt() == 2;
@@ -560,7 +532,6 @@ int launch_staggered_eo(glb_operator* op, void* out, const void* in, int parity,
   if (!f.to_host) a.red.result_host = nullptr;
   a.cg = (CgState*)f.cg_state;
   a.cg_role = f.cg_role;
-  a.pf_rows = 0;
   a.eo_parity = parity;
   a.eo_post = post;
   a.eo_coef = coef;

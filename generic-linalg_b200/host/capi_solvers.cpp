@@ -16,7 +16,6 @@
 #include "null_gen.h"
 #include "operators.h"
 #include "operators_stencil.h"
-#include "generic_vector.h"
 #include "u1_utils.h"
 
 typedef std::complex<double> zc;
@@ -237,7 +236,17 @@ int glbx_synthetic_inputs(unsigned seed, int X, int Y, double beta, void* links,
   if (X < 1 || Y < 1 || !links) return GLB_ERR_ARG;
   std::mt19937 gen(seed);
   gauss_gauge_u1((zc*)links, X, Y, gen, beta);
-  if (rhs) gaussian<double>((zc*)rhs, X * Y, gen);
+  if (rhs) {
+    // gaussian() of generic_vector.h:48-60 (the library itself never includes that driver-side header): unit normal
+    // entries, the imaginary part drawn first
+    std::normal_distribution<> unit_normal(0.0, 1.0);
+    zc* v = (zc*)rhs;
+    for (long long i = 0; i < (long long)X * Y; i++) {
+      const double im = unit_normal(gen);
+      const double re = unit_normal(gen);
+      v[i] = zc(re, im);
+    }
+  }
   return GLB_OK;
 }
 

@@ -26,6 +26,7 @@ namespace {
 
 glb_context* g_default_ctx = 0;
 bool g_allow_shim = false;
+bool g_shim_from_env_used = false;  // the shim was switched on by GLB200_HOST_CALLBACKS, not by the program
 bool g_cache_ops = false;
 
 enum Builtin {
@@ -443,6 +444,11 @@ inversion_info host_solve(const char* alg, T* phi, T* phi0, int size, void (*mv)
         cb_extra = L.comp;
       }
     } else if (g_allow_shim) {
+      if (g_shim_from_env_used)
+        std::cerr << "[glb200] WARNING: " << alg << ": the operator callback is an unknown HOST function and "
+                     "GLB200_HOST_CALLBACKS=1 is set: every apply goes device -> host function -> device (a parity aid, "
+                     "not a GPU path; call glb200_allow_host_callback_shim() from the program instead, or use the "
+                     "operators of operators.h / a device callback)" << std::endl;
       shim.fn = mv;
       shim.extra = extra;
       shim.n = size;
@@ -519,7 +525,10 @@ namespace {
 struct ShimFromEnv {
   ShimFromEnv() {
     const char* e = std::getenv("GLB200_HOST_CALLBACKS");
-    if (e && e[0] == '1') g_allow_shim = true;
+    if (e && e[0] == '1') {
+      g_allow_shim = true;
+      g_shim_from_env_used = true;  // every solve that falls back on it says so on stderr
+    }
   }
 } g_shim_from_env;
 }  // namespace
@@ -889,6 +898,10 @@ static inversion_info multi_host(const char* alg, typename MultiDev<T>::fn dev, 
         cb_extra = (void*)L.comp;
       }
     } else if (g_allow_shim) {  // the caller's own host function (tests/multishift/multishift.cpp:634)
+      if (g_shim_from_env_used)
+        std::cerr << "[glb200] WARNING: " << alg << ": unknown HOST operator callback served through the "
+                     "GLB200_HOST_CALLBACKS=1 shim (device -> host function -> device per apply): a parity aid, not a "
+                     "GPU path" << std::endl;
       shim.fn = mv;
       shim.extra = extra;
       shim.n = size;

@@ -3,6 +3,7 @@
 // The control flow, the parameters handed to the smoother and the inner solvers, the printed lines and
 // the dslash bookkeeping follow the reference statement by statement; vectors are device arrays and
 // every operation is a C-ABI call (operator applies, BLAS-1, glb_mg_prolong / glb_mg_restrict).
+#include <cstdlib>
 #include <cmath>
 #include <cstdio>
 #include <iostream>
@@ -185,7 +186,18 @@ void cycle(zcplx* lhs, zcplx* rhs, int size, mg_precond_struct_complex_dev* pc, 
                lvl + 1);
         fflush(stdout);
       }
-      level_down(mg);
+      // the level counter is restored whatever happens below (a throw in the recursive solve would otherwise leave
+      // every later preconditioner call on the wrong level)
+      struct LevelGuard {
+        mg_operator_struct_complex_dev* m;
+        bool armed;
+        explicit LevelGuard(mg_operator_struct_complex_dev* mm) : m(mm), armed(true) { level_down(m); }
+        void release() {
+          if (armed) level_up(m);
+          armed = false;
+        }
+        ~LevelGuard() { release(); }
+      } guard(mg);
       if (pc->in_solve_type == NONE || pc->mlevel_type == MLEVEL_SMOOTH || pc->in_solve_type == MINRES) {
         cycle(lhs_coarse, rhs_coarse, coarse_length, pc, verb);
       } else {
@@ -209,7 +221,7 @@ void cycle(zcplx* lhs, zcplx* rhs, int size, mg_precond_struct_complex_dev* pc, 
                  sqrt(invif.resSq) / sqrt(Bc.norm2sq(rhs_coarse)), invif.name.c_str());
         mg->dslash_count->krylov[mg->curr_level] += invif.ops_count;
       }
-      level_up(mg);
+      guard.release();
       if (say) {
         printf(pc->in_solve_type != NONE ? "Exited coarser solve.\n" : "[L%d]: Exited coarse solve.\n", lvl + 1);
         fflush(stdout);
@@ -259,7 +271,10 @@ void mg_preconditioner_dev(zcplx* d_lhs, zcplx* d_rhs, int size, void* extra_dat
   try {
     cycle(d_lhs, d_rhs, size, pc, verb);
   } catch (const std::exception& e) {
-    // the preconditioner contract has no error channel (generic_gcr_var_precond.h:16): report and leave lhs as is
-    std::cerr << "[glb200] mg_preconditioner aborted: " << e.what() << std::endl;
+    // The preconditioner contract has no error channel (generic_gcr_var_precond.h:16), and lhs may be half written
+    // or not written at all: an outer flexible solver that kept iterating on it would silently return garbage.  Same
+    // policy as the operator callback (dropin.cpp direct_apply): report and stop.
+    std::cerr << "[glb200] mg_preconditioner failed: " << e.what() << std::endl;
+    std::abort();
   }
 }

@@ -11,7 +11,7 @@ timeout 600 $TR --master-port 29511 tools/slab_check.py 64 > $OUT/slab_check.log
 grep -E "FAIL|SLAB|single-kernel|solve CGNE" $OUT/slab_check.log | tee -a $OUT/summary.txt; tail -5 $OUT/slab_check.log >> $OUT/summary.txt
 echo "== per-step wait traces" | tee -a $OUT/summary.txt
 nvidia-smi nvlink -gt d -i 0 > $OUT/nvlink_before.txt 2>&1
-for shape in "4096 $((4096*NG))" "4096 4096" "8192 8192"; do
+for shape in "4096 $((4096*NG))" "4096 4096"; do
   timeout 300 $TR --master-port 29512 tools/slab_trace.py $shape $OUT/traces 2>/dev/null | grep "^rank" | tee -a $OUT/summary.txt
 done
 nvidia-smi nvlink -gt d -i 0 > $OUT/nvlink_after.txt 2>&1
