@@ -256,6 +256,15 @@ double glb_cg_last_pred_err(void);
  * Returns the previous on/off value. */
 int glb_cg_step_mode(int on, int variant);
 
+/* ----------------------------------------------- measurement aids of the peer-memory communicator */
+/* tools/p2p_bench.py.  Collective over the communicator's ranks (every rank calls with equal arguments).
+ * glb_dbg_p2p_bench: iters x [busy-wait busy_us, then sum 6 doubles over ranks with protocol `variant`]; wait_us[i] =
+ * time rank-locally spent in sum i (variant 70 = the protocol of the library: one warp per peer; 0 = one warp for all
+ * peers; 80 = recursive doubling; 100*k + v = only the first k ranks take part).
+ * glb_dbg_p2p_pingpong: one 8-byte word each way between rank 0 and `peer`; rtt_us[i] on rank 0. */
+int glb_dbg_p2p_bench(glb_context* ctx, int variant, int iters, double busy_us, float* wait_us);
+int glb_dbg_p2p_pingpong(glb_context* ctx, int peer, int iters, float* rtt_us);
+
 /* ----------------------------------------------- partial stencil applies */
 /* apply_stencil_2d_eo / _oe / _tb / _bt (coarse_stencil.cpp:395, 560, 725, 1120; DIR_ALL) on a stencil2d operator:
  *   EO, OE: hopping term only, output on even / odd sites, the other parity zeroed;

@@ -397,6 +397,8 @@ int glb_cgm_update_p(glb_context*, int dt, size_t n, int ns, const double* zeta,
 int glb_cg_solve_supported(const glb_operator*) { return 0; }
 double glb_cg_last_pred_err(void) { return 0.0; }
 int glb_cg_step_mode(int, int) { return 0; }
+int glb_dbg_p2p_bench(glb_context*, int, int, double, float*) { return GLB_ERR_STATE; }
+int glb_dbg_p2p_pingpong(glb_context*, int, int, float*) { return GLB_ERR_STATE; }
 int glb_cg_solve(glb_operator*, void*, const void*, int, double, glb_cg_report*, double*, int) {
   g_err = "glb_cg_solve is not available in the CPU mock";
   return GLB_ERR_STATE;
