@@ -103,52 +103,17 @@ __device__ __forceinline__ unsigned long long gtime() {
   return t;
 }
 
-// grid_sum of common.cuh with optional time stamps (tr != nullptr): where does the tail of a step go?
-template <int NRED>
-__device__ __forceinline__ bool grid_sum_tr(double (&v)[NRED], const ReduceWs& ws, double (&total)[NRED],
-                                            unsigned long long* tr) {
-  __shared__ double s_red[NRED * 32];
-  __shared__ bool s_last;
-  block_sum<NRED>(v, s_red);
-  if (threadIdx.x == 0) {
-    if (tr) tr[8] = gtime();
-#pragma unroll
-    for (int r = 0; r < NRED; r++) ws.partials[r * MAX_PARTIAL_BLOCKS + blockIdx.x] = v[r];
-    __threadfence();
-    if (tr) tr[9] = gtime();
-    const unsigned int t = atomicInc(ws.ticket, gridDim.x - 1);  // wraps to 0 after the last block
-    s_last = (t == gridDim.x - 1);
-    if (tr) tr[10] = gtime();
-  }
-  __syncthreads();
-  if (!s_last) return false;
-  __threadfence();
-  double acc[NRED];
-#pragma unroll
-  for (int r = 0; r < NRED; r++) acc[r] = 0.0;
-  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
-#pragma unroll
-    for (int r = 0; r < NRED; r++) acc[r] += __ldcg(&ws.partials[r * MAX_PARTIAL_BLOCKS + b]);
-  }
-  if (tr && threadIdx.x == 0) tr[11] = gtime();
-  __syncthreads();  // s_red reuse
-  block_sum<NRED>(acc, s_red);
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int r = 0; r < NRED; r++) {
-      total[r] = acc[r];
-      ws.result_dev[r] = acc[r];
-    }
-  }
-  return true;
-}
-
 // arrays of one stage, in this order
 enum { CS_R = 0, CS_Q = 1, CS_P = 2, CS_XV = 3, CS_UX = 4, CS_UY = 5, CS_NARR = 6 };
 
 __device__ __forceinline__ int ld_acquire_gpu_s32(const int* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void st_release_gpu_s32(int* p, int v) {
@@ -171,7 +136,11 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) cg_step_kernel(const CgSt
   // the rows come from -- items follow each other in the ring without draining it.
   int4* const hdr = reinterpret_cast<int4*>(empty + STAGES);
   __shared__ double s_scal[3];  // alpha.re, alpha.im, beta of the current step
-  __shared__ int s_ctl[2];      // step number, done
+  __shared__ int s_ctl[3];      // step number, done, "this block finishes the step"
+  __shared__ double s_wpart[CW][6];   // the consumer warps' sums of the step
+  __shared__ double s_red[6 * 32];
+  __shared__ unsigned long long s_rbar;  // mbarrier: all consumer warps have posted their sums
+  unsigned long long* const rbar = &s_rbar;
 
   CgState* const st = a.st;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -180,6 +149,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) cg_step_kernel(const CgSt
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], CW);
     }
+    mbar_init(rbar, CW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
 
@@ -256,7 +226,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) cg_step_kernel(const CgSt
     int items_done = 0;
     if (a.trace != nullptr && threadIdx.x == 0) {
       t_start = gtime();
-      if (step == a.trace_step + 1) a.trace[16 * (size_t)blockIdx.x + 13] = t_start;  // when the next step began here
+      if (step == a.trace_step + 1) a.trace[24 * (size_t)blockIdx.x + 13] = t_start;  // when the next step began here
     }
 
     if (warp == CW) {
@@ -440,7 +410,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) cg_step_kernel(const CgSt
     if (tracing) {
       // per CTA: [0] SM, [1] producer out of work, [2] items, [3] stages, [4] start, [5] consumers done, [6] after the
       // grid-wide sum (last block only: the step's effective end)
-      unsigned long long* tr = a.trace + 16 * (size_t)blockIdx.x;
+      unsigned long long* tr = a.trace + 24 * (size_t)blockIdx.x;
       unsigned long long tn;
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tn));
       if (threadIdx.x == CW * 32) {
@@ -455,37 +425,92 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) cg_step_kernel(const CgSt
         tr[4] = t_start;
         tr[5] = tn;
       }
+      if (lane == 0) tr[16 + warp] = tn;  // when each warp left its loop
     }
 
-    // ---- the six sums: block -> grid (last block) -> ranks (its first warp, peer memory) -> recurrence
-    double total[6];
-    if (grid_sum_tr<6>(acc, a.red, total, tracing ? a.trace + 16 * (size_t)blockIdx.x : nullptr)) {
-      if (a.step_ns != nullptr && threadIdx.x == 0 && 2 * step + 1 < a.step_ns_cap) a.step_ns[2 * step] = gtime();
-      if (a.pr.seq != 0) {  // every thread of the last block: one warp per peer
+    // ---- end of the step.  Two things have to happen before anybody starts the next one: the six sums must be
+    // known on every rank, and every CTA's stores must have landed.  A block barrier waits for the CTA's outstanding
+    // stores (~6 us at the end of a step: the memory system is draining at full write bandwidth), so the sums do NOT
+    // go through one: consumer warps reduce by shuffles, hand their six numbers to the producer's lane through shared
+    // memory and an mbarrier, and that lane -- which has no stores of its own in flight -- posts the block's partials
+    // and takes a ticket.  The block that took the step's FIRST ticket (long finished, its stores long drained) collects
+    // all partials, completes the sum over ranks and evaluates the recurrence while the late blocks drain; it publishes
+    // once both counters are full.  Fixed shuffle tree, fixed warp / block / rank order: run-to-run reproducible.
+    const unsigned tgt = (unsigned)(n + 1) * gridDim.x;  // both counters are zeroed by the host before the launch
+    if (warp < CW) {
+#pragma unroll
+      for (int i = 0; i < 6; i++) {
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) acc[i] += shfl_xor_d(acc[i], m);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) s_wpart[warp][i] = acc[i];
+        mbar_arrive(rbar);
+      }
+    } else if (lane == 0) {
+      mbar_wait(rbar, n & 1);
+      double bsum[6];
+#pragma unroll
+      for (int i = 0; i < 6; i++) {
+        bsum[i] = 0.0;
+        for (int w = 0; w < CW; w++) bsum[i] += s_wpart[w][i];
+      }
+#pragma unroll
+      for (int i = 0; i < 6; i++) a.red.partials[i * MAX_PARTIAL_BLOCKS + blockIdx.x] = bsum[i];
+      __threadfence();
+      const unsigned tA = atomicAdd(a.counters + 1, 1u);
+      s_ctl[2] = (tA == (unsigned)n * gridDim.x) ? 1 : 0;  // the first block to get here finishes the step
+    }
+    __syncthreads();  // every thread of this CTA is past its last store of the step
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(a.counters + 2, 1u);  // ... and they are visible device-wide
+    }
+    if (s_ctl[2]) {
+      if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        while (ld_acquire_gpu_u32(a.counters + 1) < tgt) {
+          __nanosleep(20);
+          if (a.wait.budget > 0 && clock64() - t0 > a.wait.budget) __trap();
+        }
+      }
+      __syncthreads();
+      double fin[6];
+#pragma unroll
+      for (int i = 0; i < 6; i++) fin[i] = 0.0;
+      for (int bb = threadIdx.x; bb < (int)gridDim.x; bb += blockDim.x) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) fin[i] += __ldcg(&a.red.partials[i * MAX_PARTIAL_BLOCKS + bb]);
+      }
+      block_sum<6>(fin, s_red);
+      double total[6];
+      if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) total[i] = fin[i];
+        if (a.step_ns != nullptr && 2 * step + 1 < a.step_ns_cap) a.step_ns[2 * step] = gtime();
+      }
+      if (a.pr.seq != 0) {  // every thread of this block: one warp per peer
         P2PRed pr = a.pr;
         pr.seq += (unsigned long long)step;
         p2p_allreduce_block(pr, total, 6);
       }
       if (threadIdx.x == 0) {
-        unsigned long long tn = 0;
-        if (tracing || a.step_ns != nullptr) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tn));
-        if (tracing) a.trace[16 * (size_t)blockIdx.x + 6] = tn;
-        if (a.step_ns != nullptr && 2 * step + 1 < a.step_ns_cap) a.step_ns[2 * step + 1] = tn;  // after the rank sum
-        if (a.queue != nullptr) *a.queue = 0;  // every block has claimed its last item: ready for the next step
+        if (a.step_ns != nullptr && 2 * step + 1 < a.step_ns_cap) a.step_ns[2 * step + 1] = gtime();  // after the rank sum
         const double rr = total[0];
         // step 0: the set-up pass (alpha = beta = 0), step i >= 1: reference iteration k = i-1
         if (step > 0) {
           const int k = step - 1;
           st->rsq_new = rr;
           st->iter = k + 1;
-          if (a.hist != nullptr && k < st->hist_cap) a.hist[k] = rr;
-          const double want = st->rsq_pred;  // how good was the prediction that went into beta (diagnostic)
+          if (a.hist != nullptr && k < __ldcg(&st->hist_cap)) a.hist[k] = rr;
+          const double want = __ldcg(&st->rsq_pred);  // how good was the prediction that went into beta (diagnostic)
           if (rr > 0.0) {
             const double e = fabs(want - rr) / rr;
-            if (e > st->pred_err) st->pred_err = e;
+            if (e > __ldcg(&st->pred_err)) st->pred_err = e;
           }
-          const bool conv = sqrt(rr) < st->eps * st->bnorm;  // generic_cg.cpp:339
-          const bool last = (k == st->max_iter - 1);
+          const bool conv = sqrt(rr) < __ldcg(&st->eps) * __ldcg(&st->bnorm);  // generic_cg.cpp:339
+          const bool last = (k == __ldcg(&st->max_iter) - 1);
           if (conv || last) {
             st->done = 1;
             st->hit_max = last ? 1 : 0;  // generic_cg.cpp:356 tests k alone
@@ -504,10 +529,15 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) cg_step_kernel(const CgSt
         st->rsq_old = rr;
         st->pAp_re = total[1];
         st->pAp_im = total[2];
-        if (tracing) a.trace[16 * (size_t)blockIdx.x + 12] = gtime();
+        // every block's stores of this step must be in before anybody reads them
+        const long long t0 = clock64();
+        while (ld_acquire_gpu_u32(a.counters + 2) < tgt) {
+          if (a.wait.budget > 0 && clock64() - t0 > a.wait.budget) __trap();
+        }
+        if (a.queue != nullptr) *a.queue = 0;  // every block has claimed its last item: ready for the next step
+        if (tracing) a.trace[24 * (size_t)blockIdx.x + 6] = gtime();
         __threadfence();
         st_release_gpu_s32(&st->step, step + 1);  // every block of this launch is waiting for this word
-        if (tracing) a.trace[16 * (size_t)blockIdx.x + 14] = gtime();
       }
     }
   }
@@ -539,7 +569,8 @@ __global__ void __launch_bounds__(256) cg_step_halo_init_kernel(const cplx* r, c
   }
 }
 
-static unsigned int* g_cs_queue = nullptr;  // item counter of the dynamic schedule (one per process / device)
+static unsigned int* g_cs_counters = nullptr;  // [0] item counter of the dynamic schedule, [1] blocks whose sums are
+                                               // posted, [2] blocks whose stores are in (one set per process / device)
 static int g_cgstep_enabled = -1;
 static int g_cgstep_variant = -1;   // rows_per_item * 1000 + 100 * CW + 10 * STAGES + MINB
 static int g_cgstep_persist = 1;     // GLB_CGSTEP_PERSIST=0: one launch per CG iteration instead of one per solve
@@ -612,11 +643,7 @@ static int launch_cg_step_t(glb_operator* op, CgStepArgs a, int rows_per_item) {
     nrb = 0;
   }
   if (rows_per_item > 0) {
-    if (g_cs_queue == nullptr) {
-      GLB_CUDA(cudaMalloc((void**)&g_cs_queue, sizeof(unsigned int)));
-      GLB_CUDA(cudaMemset(g_cs_queue, 0, sizeof(unsigned int)));
-    }
-    a.queue = g_cs_queue;
+    a.queue = (unsigned int*)1;  // set below
   }
   if (rows_per_item <= 0) {
     nrb = max_ctas / nstrips;  // static: one item per resident CTA
@@ -625,6 +652,10 @@ static int launch_cg_step_t(glb_operator* op, CgStepArgs a, int rows_per_item) {
     a.queue = nullptr;
   }
   if (nrb < 1) nrb = 1;
+  if (g_cs_counters == nullptr) GLB_CUDA(cudaMalloc((void**)&g_cs_counters, 4 * sizeof(unsigned int)));
+  GLB_CUDA(cudaMemsetAsync(g_cs_counters, 0, 4 * sizeof(unsigned int), ctx->stream));  // counted up from 0 by every launch
+  a.counters = g_cs_counters;
+  if (a.queue != nullptr) a.queue = g_cs_counters;
   a.nstrips = (int)nstrips;
   a.nrb = (int)nrb;
   long long blocks = nstrips * nrb;
@@ -635,8 +666,8 @@ static int launch_cg_step_t(glb_operator* op, CgStepArgs a, int rows_per_item) {
   a.trace = nullptr;
   a.trace_step = -1;
   if (g_trace_path != nullptr && (a.nsteps > 1 ? g_trace_launch++ == 0 : ++g_trace_launch == 20)) {
-    GLB_CUDA(cudaMalloc((void**)&d_trace, sizeof(unsigned long long) * 16 * blocks));
-    GLB_CUDA(cudaMemset(d_trace, 0, sizeof(unsigned long long) * 16 * blocks));
+    GLB_CUDA(cudaMalloc((void**)&d_trace, sizeof(unsigned long long) * 24 * blocks));
+    GLB_CUDA(cudaMemset(d_trace, 0, sizeof(unsigned long long) * 24 * blocks));
     a.trace = d_trace;
     a.trace_step = 20;
     if (a.nsteps > 1) {  // and when every step of this launch ended
@@ -659,9 +690,9 @@ static int launch_cg_step_t(glb_operator* op, CgStepArgs a, int rows_per_item) {
     }
   }
   if (d_trace != nullptr) {
-    std::vector<unsigned long long> h(16 * blocks);
+    std::vector<unsigned long long> h(24 * blocks);
     GLB_CUDA(cudaStreamSynchronize(ctx->stream));
-    GLB_CUDA(cudaMemcpy(h.data(), d_trace, sizeof(unsigned long long) * 16 * blocks, cudaMemcpyDeviceToHost));
+    GLB_CUDA(cudaMemcpy(h.data(), d_trace, sizeof(unsigned long long) * 24 * blocks, cudaMemcpyDeviceToHost));
     cudaFree(d_trace);
     if (a.step_ns != nullptr) {
       std::vector<unsigned long long> hs(a.step_ns_cap);
@@ -676,12 +707,13 @@ static int launch_cg_step_t(glb_operator* op, CgStepArgs a, int rows_per_item) {
     }
     if (FILE* f = fopen(g_trace_path, "w")) {
       fprintf(f, "# block smid t_start t_producer_end items stages t_consumers_end t_after_gridsum t_blocksum t_fence "
-                 "t_ticket t_partials t_updated t_next_start t_published   (ns; X=%d Y=%d nstrips=%d nrb=%d blocks=%lld)\n",
+                 "t_ticket t_partials t_updated t_next_start t_published t_warp0..4_left_loop   (ns; X=%d Y=%d nstrips=%d nrb=%d blocks=%lld)\n",
               a.X, a.Y, a.nstrips, a.nrb, blocks);
       for (long long b = 0; b < blocks; b++) {
-        const unsigned long long* t = &h[16 * b];
-        fprintf(f, "%lld %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu\n", b, t[0], t[4], t[1], t[2],
-                t[3], t[5], t[6], t[8], t[9], t[10], t[11], t[12], t[13], t[14]);
+        const unsigned long long* t = &h[24 * b];
+        fprintf(f, "%lld %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu\n", b,
+                t[0], t[4], t[1], t[2], t[3], t[5], t[6], t[8], t[9], t[10], t[11], t[12], t[13], t[14], t[16], t[17],
+                t[18], t[19], t[20]);
       }
       fclose(f);
     }

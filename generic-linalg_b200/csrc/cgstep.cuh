@@ -35,6 +35,7 @@ struct CgStepArgs {
   ReduceWs red;
   P2PRed pr;                  // seq = number of step 0's rank-wide reduction (step s uses seq + s); 0 on a single rank
   const int* rb_rows;         // guided schedule: first row of every row block (nrb + 1 entries), else nullptr
+  unsigned int* counters;     // [1] blocks that posted the step's sums, [2] blocks whose stores are in; zero at launch
   unsigned int* queue;        // dynamic schedule: item counter (nullptr = static partition), reset by the last block
   unsigned long long* step_ns;  // optional: %globaltimer at the end of every step (measurement), step_ns_cap entries
   int step_ns_cap;
