@@ -451,7 +451,7 @@ void comm_arena_free(glb_context* ctx, size_t offset, size_t bytes, unsigned lon
   c->arena_free.push_back(f);
 }
 
-static int halo_exchange_p2p(glb_operator* op, const void* send_lo, const void* send_hi, int nrows) {
+static int halo_exchange_p2p(glb_operator* op, const void* send_lo, const void* send_hi, int nrows, HaloWait* defer) {
   glb_context* ctx = op->ctx;
   HaloTargets t;
   int rc = halo_p2p_begin(op, nrows, &t);
@@ -463,17 +463,22 @@ static int halo_exchange_p2p(glb_operator* op, const void* send_lo, const void* 
                                                   (uint4*)t.dst_up_lo, n16, t.flag_down_hi, t.flag_up_lo, t.wait.seq,
                                                   t.ticket);
   GLB_LAUNCH_CHECK();
+  if (defer != nullptr) {  // the consuming kernel waits itself, and only where it reads a ghost row
+    *defer = t.wait;
+    return GLB_OK;
+  }
   halo_wait_kernel<<<1, 1, 0, ctx->stream>>>(t.wait.flag_lo, t.wait.flag_hi, t.wait.seq, t.wait.budget);
   GLB_LAUNCH_CHECK();
   return GLB_OK;
 }
 
-int halo_exchange_ptrs(glb_operator* op, const void* send_lo, const void* send_hi, int nrows) {
+int halo_exchange_ptrs(glb_operator* op, const void* send_lo, const void* send_hi, int nrows, HaloWait* defer) {
   glb_context* ctx = op->ctx;
+  if (defer != nullptr) *defer = HaloWait{};
   if (ctx->nranks == 1) return GLB_OK;
   if (!ctx->comm) return fail(GLB_ERR_STATE, "slab operator used before glb_comm_init");
   if (nrows < 1 || nrows > op->ghost_depth) return fail(GLB_ERR_ARG, "halo deeper than the operator's ghost rows");
-  if (op->ghost_p2p) return halo_exchange_p2p(op, send_lo, send_hi, nrows);
+  if (op->ghost_p2p) return halo_exchange_p2p(op, send_lo, send_hi, nrows, defer);
   const int G = ctx->nranks, g = ctx->rank;
   const int up = (g + 1) % G, down = (g + G - 1) % G;
   const size_t rowb = (size_t)op->X * op->nc * elem_bytes(op->dtype);
@@ -492,12 +497,13 @@ int halo_exchange_ptrs(glb_operator* op, const void* send_lo, const void* send_h
   return GLB_OK;
 }
 
-int halo_exchange(glb_operator* op, const void* in, int nrows) {
+int halo_exchange(glb_operator* op, const void* in, int nrows, HaloWait* defer) {
+  if (defer != nullptr) *defer = HaloWait{};
   if (op->ctx->nranks == 1) return GLB_OK;
   if (nrows > op->Yloc) return fail(GLB_ERR_ARG, "slab thinner than the halo");
   const size_t rowb = (size_t)op->X * op->nc * elem_bytes(op->dtype);
   const char* base = (const char*)in;
-  return halo_exchange_ptrs(op, base, base + rowb * (op->Yloc - nrows), nrows);
+  return halo_exchange_ptrs(op, base, base + rowb * (op->Yloc - nrows), nrows, defer);
 }
 
 int allreduce_device(glb_context* ctx, double* d_vals, int n);

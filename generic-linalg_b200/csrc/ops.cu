@@ -476,14 +476,15 @@ static int apply_impl(glb_operator* op, void* out, const void* in, const ApplyFu
     case OPK_STAGGERED: {
       if (op->flags & GLB_STAG_NORMAL) {  // operators.cpp:444-453 : tmp = D in ; out = D^dag tmp
         if (normal_fused_ok(op)) {        // one pass, tmp stays on the SM; slabs exchange two rows once
-          if ((rc = halo_exchange(op, in, 2))) return rc;
-          return launch_normal(op, out, in, f);
+          ApplyFusion g1 = f;
+          if ((rc = halo_exchange(op, in, 2, &g1.wait))) return rc;  // the kernel waits for the flags in its prologue
+          return launch_normal(op, out, in, g1);
         }
         ApplyFusion none;
-        if ((rc = halo_exchange(op, in, 1))) return rc;
+        if ((rc = halo_exchange(op, in, 1, &none.wait))) return rc;
         if ((rc = launch_staggered(op, op->tmp, in, false, none))) return rc;
-        if ((rc = halo_exchange(op, op->tmp, 1))) return rc;
         ApplyFusion g = f;
+        if ((rc = halo_exchange(op, op->tmp, 1, &g.wait))) return rc;
         if (g.w_is_input) {  // the dot partner is the ORIGINAL input, not tmp
           g.w_is_input = false;
           g.w = in;
@@ -502,10 +503,11 @@ static int apply_impl(glb_operator* op, void* out, const void* in, const ApplyFu
         }
         return launch_staggered_eo(op, out, op->tmp, 0, 1, op->mass * op->mass, in, g);
       }
-      if ((rc = halo_exchange(op, in, 1))) return rc;
-      if (op->flags & GLB_STAG_DEO) return launch_staggered_eo(op, out, in, 0, 0, 0.0, nullptr, f);
-      if (op->flags & GLB_STAG_DOE) return launch_staggered_eo(op, out, in, 1, 0, 0.0, nullptr, f);
-      return launch_staggered(op, out, in, (op->flags & GLB_STAG_DAGGER) != 0, f);
+      ApplyFusion g2 = f;
+      if ((rc = halo_exchange(op, in, 1, &g2.wait))) return rc;  // only the boundary row blocks wait, inside the kernel
+      if (op->flags & GLB_STAG_DEO) return launch_staggered_eo(op, out, in, 0, 0, 0.0, nullptr, g2);
+      if (op->flags & GLB_STAG_DOE) return launch_staggered_eo(op, out, in, 1, 0, 0.0, nullptr, g2);
+      return launch_staggered(op, out, in, (op->flags & GLB_STAG_DAGGER) != 0, g2);
     }
   }
   (void)ctx;

@@ -199,9 +199,11 @@ int launch_stencil2d_sign(glb_operator* op, void* out, const void* in, int mode)
 int op_adopt_stencil2d(glb_context* ctx, int X, int Y, int Yloc, int nc, cplx* d_clover, cplx* d_hopping, glb_operator** out);
 
 // comm.cu : fills op->ghost_lo / ghost_hi from the neighbouring ranks' boundary rows of `in`
-int halo_exchange(glb_operator* op, const void* in, int nrows);
+// defer != nullptr (peer-memory path): no wait kernel is launched; *defer receives the flags and the consuming kernel
+// waits itself where it reads a ghost row (seq == 0 when there is nothing to wait for: one rank, NCCL transport)
+int halo_exchange(glb_operator* op, const void* in, int nrows, HaloWait* defer = nullptr);
 // same, boundary rows taken from explicit buffers (nrows lowest rows in send_lo, nrows highest in send_hi)
-int halo_exchange_ptrs(glb_operator* op, const void* send_lo, const void* send_hi, int nrows);
+int halo_exchange_ptrs(glb_operator* op, const void* send_lo, const void* send_hi, int nrows, HaloWait* defer = nullptr);
 int allreduce_device(glb_context* ctx, double* d_vals, int n);
 int allreduce_sum(glb_context* ctx, double* host_vals, int n);
 void comm_destroy(glb_context* ctx);

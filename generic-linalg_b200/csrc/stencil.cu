@@ -57,6 +57,7 @@ struct StagArgs {
   CgState* cg;
   int cg_role;   // 1: epilogue publishes <p,Ap> into the CG state
   int nrb;       // number of row blocks per strip
+  HaloWait wait; // slabs over peer memory: the ghost rows' flags; only row blocks that touch a ghost row wait for them
   // FAM_STAG_EO: the even/odd pieces of operators.cpp:456-616
   int eo_parity;    // 0: update even sites (D_eo), 1: update odd sites (D_oe); the other parity gets the `else` value
   int eo_post;      // 0: out = h/2 | 0          (square_staggered_deo_u1 / _doe_u1)
@@ -125,7 +126,23 @@ __global__ void __launch_bounds__(STAG_THREADS) stag_kernel(const StagArgs a) {
       yb = (int)((long long)Yloc * (rb + 1) / a.nrb);
       it += gridDim.x;
       if (ya >= yb) continue;
+      if (a.wait.seq != 0 && (ya == 0 || yb == Yloc)) {
+        // this row block reads a ghost row: the neighbour's push of this exchange must have landed (interior row
+        // blocks never wait -- the exchange overlaps with their work)
+        if (threadIdx.x == 0) {
+          if (ya == 0) spin_until(a.wait.flag_lo, a.wait.seq, a.wait.budget);
+          if (yb == Yloc) spin_until(a.wait.flag_hi, a.wait.seq, a.wait.budget);
+        }
+        __syncthreads();
+      }
     } else {
+      if (a.wait.seq != 0) {  // contiguous partition: any block may touch a ghost row
+        if (threadIdx.x == 0) {
+          spin_until(a.wait.flag_lo, a.wait.seq, a.wait.budget);
+          spin_until(a.wait.flag_hi, a.wait.seq, a.wait.budget);
+        }
+        __syncthreads();
+      }
       strip = (int)(it / Yloc);
       ya = (int)(it - (long long)strip * Yloc);
       yb = (int)min((long long)Yloc, (long long)ya + (u_end - it));
@@ -487,6 +504,7 @@ int launch_staggered(glb_operator* op, void* out, const void* in, bool dagger, c
   a.gamma5 = (op->flags & GLB_STAG_GAMMA5) ? 1 : 0;
   a.red = ctx->red;
   if (!f.to_host) a.red.result_host = nullptr;
+  a.wait = f.wait;
   a.cg = (CgState*)f.cg_state;
   a.cg_role = f.cg_role;
   const int ndot = (f.w != nullptr || f.w_is_input) ? (f.want_norm ? 2 : 1) : 0;
@@ -530,6 +548,7 @@ int launch_staggered_eo(glb_operator* op, void* out, const void* in, int parity,
   a.mass = op->mass;
   a.red = ctx->red;
   if (!f.to_host) a.red.result_host = nullptr;
+  a.wait = f.wait;
   a.cg = (CgState*)f.cg_state;
   a.cg_role = f.cg_role;
   a.eo_parity = parity;
