@@ -85,6 +85,7 @@ def libs():
         "glb_last_error": (C.c_char_p, []), "glb_synchronize": (ci, [vp]), "glb_stream": (vp, [vp]),
         "glb_device": (ci, [vp]), "glb_sm_count": (ci, [vp]), "glb_kernel_launches": (C.c_ulonglong, []),
         "glb_prof_enable": (ci, [vp, ci]), "glb_prof_read": (ci, [vp, ci, ci, C.POINTER(C.c_float), C.POINTER(ci)]),
+        "glb_prof_summary": (ci, [vp, ci, C.POINTER(ci), pd, pd]),
         "glb_comm_unique_id": (ci, [C.c_char_p]), "glb_comm_init": (ci, [vp, ci, ci, C.c_char_p]),
         "glb_comm_p2p_enabled": (ci, [vp]), "glb_comm_rank": (ci, [vp]), "glb_comm_size": (ci, [vp]), "glb_comm_barrier": (ci, [vp]),
         "glb_vec_alloc": (ci, [vp, ci, sz, C.POINTER(vp)]), "glb_vec_free": (ci, [vp, vp]),
@@ -121,6 +122,9 @@ def libs():
         "glb_cg_solve_supported": (ci, [vp]),
         "glb_cg_last_pred_err": (cd, []), "glb_cg_step_mode": (ci, [ci, ci]),
         "glb_cg_solve": (ci, [vp, vp, vp, ci, cd, C.POINTER(CgReport), pd, ci]),
+        "glb_krylov_solve_supported": (ci, [vp, ci]),
+        "glb_krylov_solve": (ci, [vp, ci, vp, vp, ci, cd, C.POINTER(CgReport), pd, ci]),
+        "glb_krylov_graph_mode": (ci, [ci]), "glb_krylov_last_used_graph": (ci, []),
         "glb_op_apply_part": (ci, [vp, vp, vp, ci]),
         "glb_stag_eoprec_prepare": (ci, [vp, vp, vp]), "glb_stag_eoprec_reconstruct": (ci, [vp, vp, vp, vp]),
         "glb_mg_transfer_create": (ci, [vp, ci, ci, ci, ci, ci, ci, C.POINTER(vp), C.POINTER(vp)]),
@@ -578,6 +582,22 @@ class Context:
         _chk(self.cu.glb_prof_read(self.h, cls, n.value, buf, C.byref(n)), "glb_prof_read")
         return [float(buf[i]) for i in range(n.value)]
 
+    PROF_CLASSES = {1: "normal_kernel<fused>", 2: "normal_kernel / normal1_kernel (D^dag D, one pass)", 3: "cg_update_kernel",
+                    4: "stag_kernel (staggered / gauged Laplace apply)", 5: "coarse stencil kernels (apply_stencil_2d)",
+                    6: "laplace_kernel", 7: "cg_step_kernel", 8: "streaming BLAS-1 kernels (ew_kernel / ews_kernel)",
+                    9: "multi_dot_kernel (batched <Ap_i, Ar>)", 10: "lincomb_kernel (p, Ap = z + sum beta_i p_i)",
+                    11: "mg_prolong / mg_restrict"}
+
+    def prof_summary(self):
+        """{class name: (launches, total ms, algorithmic bytes)} of everything recorded since prof_enable"""
+        out = {}
+        for cls, name in self.PROF_CLASSES.items():
+            n, ms, by = C.c_int(0), C.c_double(0.0), C.c_double(0.0)
+            _chk(self.cu.glb_prof_summary(self.h, cls, C.byref(n), C.byref(ms), C.byref(by)), "glb_prof_summary")
+            if n.value:
+                out[name] = (n.value, ms.value, by.value)
+        return out
+
     def vector(self, n, dtype=np.complex128):
         return DeviceVector(self, n, dtype)
 
@@ -725,6 +745,28 @@ class Context:
         if want_history:
             out["history"] = hist[:rep.iterations]
         return out
+
+    KRYLOV = dict(BICGSTAB=1, CR=2)
+
+    def krylov_device(self, alg, op, x, b, max_iter=10000, eps=1e-10, want_history=False):
+        """glb_krylov_solve: the device-resident BiCGStab / CR loop (no final true-residual apply)."""
+        rep = CgReport()
+        hist = np.zeros(max_iter if want_history else 0)
+        _chk(self.cu.glb_krylov_solve(op.h, self.KRYLOV[alg], x.ptr, b.ptr, max_iter, eps, C.byref(rep),
+                                      hist.ctypes.data_as(C.POINTER(C.c_double)) if want_history else None,
+                                      max_iter if want_history else 0), "glb_krylov_solve")
+        out = dict(iterations=rep.iterations, ops=rep.ops, hit_max_iter=bool(rep.hit_max_iter), rsq=rep.rsq,
+                   bnorm=rep.bnorm, used_graph=bool(self.cu.glb_krylov_last_used_graph()))
+        if want_history:
+            out["history"] = hist[:rep.iterations]
+        return out
+
+    def krylov_supported(self, alg, op):
+        return bool(self.cu.glb_krylov_solve_supported(op.h, self.KRYLOV[alg]))
+
+    def krylov_graph_mode(self, on):
+        """batches of the device-resident BiCGStab / CR loop as CUDA graphs (True, default) or direct launches"""
+        return bool(self.cu.glb_krylov_graph_mode(1 if on else 0))
 
     def synthetic_inputs(self, X, Y, seed=1337, beta=6.0, want_rhs=True):
         """BASELINE.md section 3 inputs from the drop-in's host helpers: mt19937(seed) -> gauss_gauge_u1 -> gaussian"""

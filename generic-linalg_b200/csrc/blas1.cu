@@ -68,6 +68,7 @@ static int run_ew(glb_context* ctx, const F& f, const VecPtrs<F::NV>& ptrs, size
   for (int k = 0; k < F::NV; k++) wide = wide && (((uintptr_t)ptrs.p[k] & 31u) == 0);
   ReduceWs red = ctx->red;
   if (!to_host) red.result_host = nullptr;
+  ProfScope prof(ctx, PROF_EW, (double)n * sizeof(T) * (__builtin_popcount(F::RD) + __builtin_popcount(F::WR)));
   if (wide) {
     const int grid = blas_grid(ctx, n / WMAX, 256, 2);
     ew_kernel<T, F, WMAX><<<grid, 256, 0, ctx->stream>>>(f, ptrs, n, red);
@@ -563,6 +564,7 @@ int glb_multi_dot(glb_context* ctx, int dtype, size_t n, int k, const void* cons
       a.k = kk;
       for (int j = 0; j < kk; j++) a.X[j] = (const T*)X[base + j];
       const int grid = blas_grid(ctx, n, 256, 4);
+      ProfScope prof(ctx, PROF_MULTI_DOT, (double)n * sizeof(T) * (kk + 1));
       multi_dot_kernel<T, MAXK><<<grid, 256, 0, ctx->stream>>>(a, (const T*)y, n, ctx->red);
       GLB_LAUNCH_CHECK();
       return GLB_OK;
@@ -693,6 +695,7 @@ int glb_lincomb(glb_context* ctx, int dtype, size_t n, int k, const double* coef
         a.c0[j] = coef<T>(coefs + 2 * (base + j));
       }
       const int grid = blas_grid(ctx, n, 256, 2);
+      ProfScope prof(ctx, PROF_LINCOMB, (double)n * sizeof(T) * (kk + (cur_init ? 1 : 0) + 1));
       lincomb_kernel<T><<<grid, 256, 0, ctx->stream>>>(a, (const T*)cur_init, (T*)out, n);
       GLB_LAUNCH_CHECK();
       return GLB_OK;

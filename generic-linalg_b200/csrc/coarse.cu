@@ -221,9 +221,12 @@ __global__ void __launch_bounds__(256) stencil1_pair_kernel(const CoarseArgs a) 
   }
 }
 
+// algorithmic bytes of one stencil apply over L dofs: (5 or 13) nc x nc matrices + in + out per site (SURVEY 8 d-bytes)
+static double coarse_bytes(const CoarseArgs& a, size_t L) { return (double)L * ((a.has_two ? 13.0 : 5.0) * a.nc + 2.0) * 16.0; }
+
 static int launch_stencil1_pair(glb_context* ctx, const CoarseArgs& a, int ndot, size_t L) {
   const int grid = blas_grid(ctx, L / 2, 256, 1);
-  ProfScope prof(ctx, PROF_COARSE);
+  ProfScope prof(ctx, PROF_COARSE, coarse_bytes(a, L));
   if (ndot == 0)
     stencil1_pair_kernel<0><<<grid, 256, 0, ctx->stream>>>(a);
   else if (ndot == 1)
@@ -404,7 +407,7 @@ static int launch_ring_t(glb_context* ctx, const CoarseArgs& a, size_t L) {
   if (blocks > (long long)ctx->sm_count * per_sm) blocks = (long long)ctx->sm_count * per_sm;
   if (blocks > MAX_PARTIAL_BLOCKS) blocks = MAX_PARTIAL_BLOCKS;
   if (blocks < 1) blocks = 1;
-  ProfScope prof(ctx, PROF_COARSE);
+  ProfScope prof(ctx, PROF_COARSE, coarse_bytes(a, L));
   kern<<<(unsigned)blocks, RING_THREADS, smem, ctx->stream>>>(a, ntiles);
   GLB_LAUNCH_CHECK();
   return GLB_OK;
@@ -642,7 +645,7 @@ int launch_stencil2d_part(glb_operator* op, void* out, const void* in, int part,
 template <int NC>
 static int launch_coarse_nc(glb_context* ctx, const CoarseArgs& a, int ndot, size_t L) {
   const int grid = blas_grid(ctx, L, 256, 1);
-  ProfScope prof(ctx, PROF_COARSE);
+  ProfScope prof(ctx, PROF_COARSE, coarse_bytes(a, L));
   if (ndot == 0)
     coarse_kernel<NC, 0><<<grid, 256, 0, ctx->stream>>>(a);
   else if (ndot == 1)

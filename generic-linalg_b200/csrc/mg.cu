@@ -471,6 +471,8 @@ int glb_mg_prolong(glb_mg_transfer* t, void* d_fine, const void* d_coarse) {
   glb_context* ctx = t->ctx;
   const MgArgs a = mg_args(t);
   const int grid = blas_grid(ctx, glb_mg_fine_size(t), 256, 1);
+  // null vectors (nvec per fine dof) + the fine vector + the coarse vector
+  ProfScope prof(ctx, PROF_MG_TRANSFER, 16.0 * ((double)glb_mg_fine_size(t) * (t->nvec + 1) + (double)glb_mg_coarse_size(t)));
   if (t->nvec == 8)
     mg_prolong_kernel<8><<<grid, 256, 0, ctx->stream>>>(a, (cplx*)d_fine, (const cplx*)d_coarse);
   else if (t->nvec == 4)
@@ -486,6 +488,7 @@ int glb_mg_restrict(glb_mg_transfer* t, void* d_coarse, const void* d_fine) {
   glb_context* ctx = t->ctx;
   const MgArgs a = mg_args(t);
   const int grid = blas_grid(ctx, glb_mg_coarse_size(t), 256, 1);
+  ProfScope prof(ctx, PROF_MG_TRANSFER, 16.0 * ((double)glb_mg_fine_size(t) * (t->nvec + 1) + (double)glb_mg_coarse_size(t)));
   mg_restrict_kernel<<<grid, 256, 0, ctx->stream>>>(a, (cplx*)d_coarse, (const cplx*)d_fine);
   GLB_LAUNCH_CHECK();
   return GLB_OK;

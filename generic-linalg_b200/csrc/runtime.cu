@@ -114,6 +114,25 @@ int glb_prof_read(glb_context* ctx, int cls, int cap, float* ms, int* n) {
   return GLB_OK;
 }
 
+int glb_prof_summary(glb_context* ctx, int cls, int* launches, double* ms_total, double* bytes_total) {
+  if (!ctx || !launches || !ms_total || !bytes_total) return fail(GLB_ERR_ARG, "glb_prof_summary: null argument");
+  GLB_CUDA(cudaStreamSynchronize(ctx->stream));
+  int k = 0;
+  double ms = 0.0, by = 0.0;
+  for (auto& r : ctx->prof) {
+    if (r.cls != cls) continue;
+    float t = 0.f;
+    GLB_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    ms += t;
+    by += r.bytes;
+    k++;
+  }
+  *launches = k;
+  *ms_total = ms;
+  *bytes_total = by;
+  return GLB_OK;
+}
+
 int glb_vec_alloc(glb_context* ctx, int dtype, size_t n, void** dptr) {
   if (!dptr) return fail(GLB_ERR_ARG, "glb_vec_alloc: null output");
   size_t bytes = n * elem_bytes(dtype);

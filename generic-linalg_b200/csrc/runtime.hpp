@@ -43,11 +43,17 @@ enum ProfClass {
   PROF_STAG = 4,          // stag_kernel, any flavour
   PROF_COARSE = 5,        // coarse_kernel / coarse_ring_kernel
   PROF_LAPLACE = 6,
-  PROF_CG_STEP = 7         // cg_step_kernel: the whole CG iteration in one pass (160 B/site)
+  PROF_CG_STEP = 7,        // cg_step_kernel: the whole CG iteration in one pass (160 B/site)
+  PROF_EW = 8,             // streaming BLAS-1 kernels (ew_kernel functors of blas1.cu, ews_kernel of krylov.cu)
+  PROF_MULTI_DOT = 9,      // multi_dot_kernel: <X_i, y> for up to 16 stored vectors in one pass (GCR / VPGCR sweeps)
+  PROF_LINCOMB = 10,       // lincomb_kernel: out = init + sum_i c_i X_i
+  PROF_MG_TRANSFER = 11,   // mg_prolong_kernel / mg_restrict_kernel
+  PROF_NCLASS = 12
 };
 struct ProfRec {
   cudaEvent_t a, b;
   int cls;
+  double bytes;  // algorithmic bytes of the launch (every distinct element read once / written once), 0 if not known
 };
 
 }  // namespace glb
@@ -143,10 +149,11 @@ namespace glb {
 struct ProfScope {
   glb_context* ctx;
   cudaEvent_t b = nullptr;
-  ProfScope(glb_context* c, int cls) : ctx(c) {
+  ProfScope(glb_context* c, int cls, double bytes = 0.0) : ctx(c) {
     if (!c->prof_on) return;
     ProfRec r{};
     r.cls = cls;
+    r.bytes = bytes;
     if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
     cudaEventRecord(r.a, c->stream);
     b = r.b;

@@ -440,7 +440,8 @@ static int launch_stag_t(glb_operator* op, const StagArgs& a) {
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   if (blocks > MAX_PARTIAL_BLOCKS) blocks = MAX_PARTIAL_BLOCKS;
-  ProfScope prof(ctx, PROF_STAG);
+  // in + out (+ the link pair) per site; the fused direction update adds r, p_old in and p_new out
+  ProfScope prof(ctx, PROF_STAG, (double)a.X * a.Yloc * ((HAS_U ? 64.0 : 32.0) + (FUSE ? 32.0 : 0.0)));
   kern<<<(unsigned)blocks, STAG_THREADS, 0, ctx->stream>>>(b);
   GLB_LAUNCH_CHECK();
   return GLB_OK;
@@ -598,7 +599,7 @@ static int launch_laplace_t(glb_operator* op, void* out, const void* in, const A
   a.cg_role = f.cg_role;
   const int ndot = (f.w != nullptr || f.w_is_input) ? (f.want_norm ? 2 : 1) : 0;
   const int grid = blas_grid(ctx, RX * op->Yloc, 256, 1);
-  ProfScope prof(ctx, PROF_LAPLACE);
+  ProfScope prof(ctx, PROF_LAPLACE, (double)RX * op->Yloc * sizeof(T) * 2);
   if (ndot == 0)
     laplace_kernel<T, 0><<<grid, 256, 0, ctx->stream>>>(a);
   else if (ndot == 1)

@@ -131,6 +131,29 @@ inversion_info cr_dev(T* x, T* b, int size, int max_iter, double eps, void (*fn)
   DevOp<T> A = make_op<T>(fn, extra, size);
   Blas<T> B = {A.ctx, (size_t)size};
   Work<T> W(B);
+  if (A.native && !g_force_host_scalars && max_iter >= 1 && glb_krylov_solve_supported(A.native, GLB_KRYLOV_CR)) {
+    // device-resident loop (csrc/krylov.cu): alpha, beta and the stopping test never leave the GPU
+    std::vector<double> hist;
+    const bool detail = (verb != 0 && verb->verbosity == VERB_DETAIL);
+    if (detail) hist.resize(max_iter);
+    glb_cg_report rep;
+    GLBX(glb_krylov_solve(A.native, GLB_KRYLOV_CR, x, b, max_iter, eps, &rep, detail ? hist.data() : 0,
+                          detail ? max_iter : 0));
+    if (detail)
+      for (int i = 0; i < rep.iterations; i++) print_verbosity_resid(verb, "CR", i + 1, 2 + i, sqrt(hist[i]) / rep.bnorm);
+    A.ops = rep.ops;
+    // the complex overload tests k == max_iter after the loop and so never reports failure (generic_cr.cpp:288 vs :117)
+    inf.success = IsComplex<T>::value ? true : !rep.hit_max_iter;
+    T* t = W.get();
+    A.apply(t, x);
+    const double truersq = B.diffnorm2sq(t, b);
+    inf.ops_count = A.ops;
+    print_verbosity_summary(verb, "CR", inf.success, rep.iterations, inf.ops_count, sqrt(truersq) / rep.bnorm);
+    inf.resSq = truersq;
+    inf.iter = rep.iterations;
+    inf.name = "CR";
+    return inf;
+  }
   T *r = W.get(), *Ar = W.get(), *p = W.get(), *Ap = W.get();
   const double bsqrt = sqrt(B.norm2sq(b));
   A.apply(p, x);
@@ -302,6 +325,29 @@ inversion_info bicgstab_dev(T* x, T* b, int size, int max_iter, double eps, void
   DevOp<T> A = make_op<T>(fn, extra, size);
   Blas<T> B = {A.ctx, (size_t)size};
   Work<T> W(B);
+  if (A.native && !g_force_host_scalars && max_iter >= 1 && glb_krylov_solve_supported(A.native, GLB_KRYLOV_BICGSTAB)) {
+    // device-resident loop (csrc/krylov.cu): alpha, omega, beta and the stopping test never leave the GPU
+    std::vector<double> hist;
+    const bool detail = (verb != 0 && verb->verbosity == VERB_DETAIL);
+    if (detail) hist.resize(max_iter);
+    glb_cg_report rep;
+    GLBX(glb_krylov_solve(A.native, GLB_KRYLOV_BICGSTAB, x, b, max_iter, eps, &rep, detail ? hist.data() : 0,
+                          detail ? max_iter : 0));
+    if (detail)  // ops at the time of the print: 2 set-up applies, As of every iteration, Ap of the earlier ones
+      for (int i = 0; i < rep.iterations; i++)
+        print_verbosity_resid(verb, "BiCGStab", i + 1, 2 * i + 3, sqrt(hist[i]) / rep.bnorm);
+    A.ops = rep.ops;
+    inf.success = !rep.hit_max_iter;
+    T* t = W.get();
+    A.apply(t, x);
+    const double truersq = B.diffnorm2sq(t, b);
+    inf.ops_count = A.ops;
+    print_verbosity_summary(verb, "BiCGStab", inf.success, rep.iterations, inf.ops_count, sqrt(truersq) / rep.bnorm);
+    inf.resSq = truersq;
+    inf.iter = rep.iterations;
+    inf.name = "BiCGStab";
+    return inf;
+  }
   T *r = W.get(), *r0 = W.get(), *p = W.get(), *Ap = W.get(), *s = W.get(), *As = W.get();
   const double bsqrt = sqrt(B.norm2sq(b));
   A.apply(Ap, x);

@@ -79,6 +79,11 @@ unsigned long long glb_kernel_launches(void);
    order (at most cap of them; *n = how many were recorded). */
 int glb_prof_enable(glb_context* ctx, int on);
 int glb_prof_read(glb_context* ctx, int cls, int cap, float* ms, int* n);
+/* classes 8-11: 8 streaming BLAS-1 kernels, 9 multi_dot (batched inner products of the GCR sweeps), 10 lincomb,
+   11 multigrid prolong / restrict.  glb_prof_summary: number of launches of class `cls` since glb_prof_enable(ctx,1),
+   their summed duration (ms) and their summed algorithmic bytes (tools/bench_mg.py: where a multigrid solve spends
+   its time, GB/s per kernel class). */
+int glb_prof_summary(glb_context* ctx, int cls, int* launches, double* ms_total, double* bytes_total);
 
 /* ------------------------------------------------------ slab communicator (y-slabs) */
 /* One process per GPU.  Rank g of G owns rows [g*Y/G, (g+1)*Y/G) of every lattice
@@ -255,6 +260,26 @@ double glb_cg_last_pred_err(void);
  * warps + 10*stages + blocks per SM).
  * Returns the previous on/off value. */
 int glb_cg_step_mode(int on, int variant);
+
+/* ----------------------------------------------- device-resident BiCGStab and CR (csrc/krylov.cu)
+ * The loops of minv_vector_bicgstab (generic_bicgstab.cpp:258-308 complex, :75-125 real) and minv_vector_cr
+ * (generic_cr.cpp:246-286, :76-116) with alpha / omega / beta and the stopping test kept on the GPU: every kernel
+ * forms the scalars it needs from the grid totals its predecessor on the stream left on the device, the host only
+ * polls the state once per batch of iterations (later batches are replayed as one CUDA graph).  Same vector kernels,
+ * launch geometry and reduction trees as the host-scalar shells: the iterates are bit-identical to theirs.
+ * x is in/out (initial guess), b the rhs; the report counts as the reference does, EXCLUDING the final
+ * true-residual apply (the shell performs it); rsq_hist (host, may be NULL) receives |r|^2 after each iteration.
+ * One rank, any native operator with fused reductions (not gamma5, not the composite stencil views). */
+#define GLB_KRYLOV_BICGSTAB 1
+#define GLB_KRYLOV_CR 2
+int glb_krylov_solve_supported(const glb_operator* op, int alg);
+int glb_krylov_solve(glb_operator* op, int alg, void* d_x, const void* d_b, int max_iter, double eps,
+                     glb_cg_report* rep, double* rsq_hist, int hist_cap);
+/* measurement / test aid: on = 1 (default; GLB_KRYLOV_GRAPH in the environment) replays batches as a CUDA graph,
+ * 0 launches every kernel directly, < 0 only queries.  Returns the previous setting.  glb_krylov_last_used_graph:
+ * 1 if the last glb_krylov_solve of this process replayed a graph. */
+int glb_krylov_graph_mode(int on);
+int glb_krylov_last_used_graph(void);
 
 /* ----------------------------------------------- measurement aids of the peer-memory communicator */
 /* tools/p2p_bench.py.  Collective over the communicator's ranks (every rank calls with equal arguments).

@@ -13,6 +13,7 @@ Recorded per size L:
   * config 3: minv_vector_cg_m, shifts {0, .01, .05, .25}, tol 1e-10  (generic_cg_m.cpp:312)
               minv_vector_gmres_restart(..., 1e-8, 20, ...) on D      (generic_gmres.cpp:778)
   * BiCGStab on D, tol 1e-10                                          (generic_bicgstab.cpp:228)
+  * CR: minv_vector_cr on D^dag D, rhs D^dag b, tol 1e-10            (generic_cr.cpp:198)   [--only CR adds it to an existing file]
 """
 import argparse
 import hashlib
@@ -56,11 +57,11 @@ def job(args):
         out["apply_g5D_sha"] = digest(ref.op("STAG_GAMMA5_U1", L, L, mass=MASS, links=U).apply(b))
         out["apply_DdagD_sha"] = digest(ref.op("STAG_NORMAL_U1", L, L, mass=MASS, links=U).apply(b))
         return what, out, time.time() - t0
-    if what in ("CGNE", "CG-M"):
+    if what in ("CGNE", "CG-M", "CR"):
         bprime = ref.op("STAG_DAGGER_U1", L, L, mass=MASS, links=U).apply(b)
         DdD = ref.op("STAG_NORMAL_U1", L, L, mass=MASS, links=U)
-        if what == "CGNE":
-            x, info = ref.solve("CG", DdD, bprime, max_iter=100000, eps=1e-10)
+        if what in ("CGNE", "CR"):
+            x, info = ref.solve("CG" if what == "CGNE" else "CR", DdD, bprime, max_iter=100000, eps=1e-10)
             info["x_sha"] = digest(x)
             info["true_rel_residual"] = float(np.linalg.norm(DdD.apply(x) - bprime) / np.linalg.norm(bprime))
         else:
@@ -87,6 +88,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--sizes", type=int, nargs="+", default=[1024, 4096])
     ap.add_argument("--jobs", type=int, default=3)
+    ap.add_argument("--only", nargs="+", default=None, help="run only these entries (e.g. CR) and merge them into the file")
     args = ap.parse_args()
     gold = {}
     if os.path.exists(OUT):
@@ -95,7 +97,7 @@ def main():
     gold["oracle_kind"] = O.load("ref").kind
     gold["inputs"] = "std::mt19937(1337): gauss_gauge_u1(L, L, beta=6) then gaussian(L*L); mass 0.1"
     for L in args.sizes:
-        todo = [(L, w) for w in ("GMRES(20)", "CG-M", "CGNE", "BiCGStab", "applies")]
+        todo = [(L, w) for w in ("GMRES(20)", "CG-M", "CGNE", "BiCGStab", "CR", "applies") if not args.only or w in args.only]
         entry = gold.get(str(L), {})
         with mp.get_context("fork").Pool(args.jobs) as pool:
             for what, info, dt in pool.imap_unordered(job, todo):

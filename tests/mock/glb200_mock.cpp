@@ -58,6 +58,12 @@ int glb_sm_count(glb_context*) { return 0; }
 unsigned long long glb_kernel_launches(void) { return g_calls; }
 int glb_prof_enable(glb_context*, int) { return GLB_OK; }
 int glb_prof_read(glb_context*, int, int, float*, int* n) { if (n) *n = 0; return GLB_OK; }
+int glb_prof_summary(glb_context*, int, int* launches, double* ms, double* bytes) {
+  if (launches) *launches = 0;
+  if (ms) *ms = 0.0;
+  if (bytes) *bytes = 0.0;
+  return GLB_OK;
+}
 int glb_comm_unique_id(char*) { return GLB_ERR_COMM; }
 int glb_comm_init(glb_context*, int, int, const char*) { return GLB_ERR_COMM; }
 int glb_comm_rank(glb_context*) { return 0; }
@@ -395,6 +401,13 @@ int glb_cgm_update_p(glb_context*, int dt, size_t n, int ns, const double* zeta,
 // the device-resident CG is a CUDA-only entry point: the shells fall back to the host-scalar loop
 // when forced (glb200_force_host_scalars), which is what the mock tests do.
 int glb_cg_solve_supported(const glb_operator*) { return 0; }
+int glb_krylov_solve_supported(const glb_operator*, int) { return 0; }
+int glb_krylov_solve(glb_operator*, int, void*, const void*, int, double, glb_cg_report*, double*, int) {
+  g_err = "glb_krylov_solve is not available in the CPU mock";
+  return GLB_ERR_STATE;
+}
+int glb_krylov_graph_mode(int) { return 0; }
+int glb_krylov_last_used_graph(void) { return 0; }
 double glb_cg_last_pred_err(void) { return 0.0; }
 int glb_cg_step_mode(int, int) { return 0; }
 int glb_dbg_p2p_bench(glb_context*, int, int, double, float*) { return GLB_ERR_STATE; }

@@ -1,7 +1,7 @@
 """GPU parity at the BASELINE lattice sizes (1024^2 and the headline 4096^2), against
 
   * tests/golden/golden_large.json -- produced by the UNMODIFIED reference here (oracle/gen_golden_large.py, ~25 CPU
-    minutes: digests of the applies, iteration counts and residuals of CGNE, CG-M, GMRES(20), BiCGStab), and
+    minutes: digests of the applies, iteration counts and residuals of CGNE, CG-M, GMRES(20), BiCGStab, CR), and
   * the CPU oracle itself for the applies (np.array_equal; one 4096^2 apply costs the CPU 0.25 s).
 
 Inputs: std::mt19937(1337) -> gauss_gauge_u1(beta = 6) -> gaussian rhs, drawn by the product's
@@ -135,5 +135,14 @@ def test_config3_cg_m_and_gmres(ctx, glb, orc, case):
     # BiCGStab is chaotic on this operator (the reference's own count moves by +-8 % under 1e-15 perturbations,
     # tests/test_solvers_gpu.py): the bar here is the envelope, the stable-mass case keeps the +-2 % bar
     assert info["success"] and close_iters(info["iter"], want["iter"], tol=0.10), (info["iter"], want["iter"])
+    rr = float(np.linalg.norm(orc.op("STAG_U1", L, L, mass=MASS, links=U).apply(x.download()) - b) / np.linalg.norm(b))
+    assert rr < 1.05e-10, rr
+    # minv_vector_cr on D^dag D (generic_cr.cpp:198) through the device-resident loop of csrc/krylov.cu
+    x.zero()
+    info = ctx.solve("CR", N, x, bp, max_iter=100000, eps=1e-10)
+    want = g["CR"]
+    assert info["success"] and close_iters(info["iter"], want["iter"]), (info["iter"], want["iter"])
+    rr = float(np.linalg.norm(oN.apply(x.download()) - rhs) / np.linalg.norm(rhs))
+    assert rr < 1.05e-10 and abs(rr - want["true_rel_residual"]) < 2e-11, (rr, want["true_rel_residual"])
     for o in (D, N, Dd):
         o.destroy()

@@ -93,6 +93,33 @@ def main():
          "device; fine level = nc=1 stencil (as the reference)", seconds=dt, iterations=info["iter"],
          outer_ops=info["ops_count"], success=info["success"], true_rel_residual=true_rel(x),
          kernel_launches=ctx.launches() - l0, dslash_counts=mgs.counts())
+    # ---- where the solve spends its time: the same solve once more with a CUDA-event pair around every classified
+    # launch (glb_prof_*); GB/s on the algorithmic bytes of each launch, share of the wall-clock time of THIS solve
+    x.zero()
+    ctx.sync()
+    ctx.prof_enable(True)
+    t0 = time.perf_counter()
+    info_p = mgs.vpgcr(x, b, max_iter=100000, eps=5e-7, restart_freq=64)
+    ctx.sync()
+    dt_p = time.perf_counter() - t0
+    summ = ctx.prof_summary()
+    ctx.prof_enable(False)
+    peak = 6543.7
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    table, covered = [], 0.0
+    for name, (n, ms, by) in sorted(summ.items(), key=lambda kv: -kv[1][1]):
+        covered += ms
+        table.append({"kernel": name, "launches": n, "ms_total": round(ms, 3), "us_per_launch": round(1e3 * ms / n, 2),
+                      "GBps": round(by / ms / 1e6, 1) if ms > 0 and by > 0 else None,
+                      "frac_of_hbm_peak": round(by / ms / 1e6 / peak, 3) if ms > 0 and by > 0 else None,
+                      "share_of_solve": round(ms / (1e3 * dt_p), 3)})
+    emit(kind="solve_profile", L=L, mass=mass, seconds_with_events=dt_p, iterations=info_p["iter"],
+         kernels=table, share_in_classified_kernels=round(covered / (1e3 * dt_p), 3),
+         note="rest = stream synchronisations of the host-scalar shells, event overhead, unclassified small kernels "
+              "(copies, memsets, vector subtraction inside glb_sub counts as BLAS-1)")
     mgs.destroy()
 
     # ---- the same system without the preconditioner
