@@ -237,29 +237,109 @@ struct MultiArgs {
   int k;
 };
 
-// out[2i..] = <X[i], y>
-template <typename T, int K>
-__global__ void __launch_bounds__(256) multi_dot_kernel(MultiArgs<T> a, const T* y, size_t n, ReduceWs red) {
+// out[NC*j ..] = <X[j], y> for up to MAXK stored vectors in ONE pass over y (the Gram-Schmidt sweeps of GCR / VPGCR /
+// the flexible solvers, generic_gcr.cpp:284-292).
+// Shape: the 8 warps of a block sweep the SAME elements, warp w owning the vectors [w*VPW, (w+1)*VPW) -- a thread
+// carries 2*VPW accumulators instead of 32, so the registers go to loads in flight (U elements x (VPW + 1) 16-byte
+// loads per thread) and not to sums: one thread summing all 16 vectors needs 102 registers, keeps ~4 loads in flight
+// and reaches 35 % of the HBM peak (profiles/r02/config5_profile_before_gs_kernels.jsonl).  y is fetched from DRAM once
+// per block (the other warps hit L1).  Warp sums -> per-block partials -> the block that arrives last adds the
+// partials of every vector in block order: fixed summation order, run-to-run reproducible.
+constexpr int MD_U = 4;  // elements per lane and chunk
+template <typename T, int VPW>
+__global__ void __launch_bounds__(256, 3) multi_dot_kernel(MultiArgs<T> a, const T* __restrict__ y, size_t n, ReduceWs red) {
   constexpr int NC = Field<T>::NCOMP;
-  double acc[K * NC];
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j0 = warp * VPW;
+  double acc[VPW * NC];
 #pragma unroll
-  for (int i = 0; i < K * NC; i++) acc[i] = 0.0;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const T yv = y[i];
+  for (int i = 0; i < VPW * NC; i++) acc[i] = 0.0;
+  if (j0 < a.k) {
+    const T* xp[VPW];
 #pragma unroll
-    for (int j = 0; j < K; j++)
-      if (j < a.k) Field<T>::dot_acc(acc + j * NC, a.X[j][i], yv);
+    for (int v = 0; v < VPW; v++) xp[v] = a.X[(j0 + v < a.k) ? j0 + v : j0];
+    const size_t chunk = (size_t)32 * MD_U;
+    for (size_t c0 = (size_t)blockIdx.x * chunk; c0 < n; c0 += (size_t)gridDim.x * chunk) {
+      T yv[MD_U], xv[VPW][MD_U];
+      if (c0 + chunk <= n) {
+        // full chunk: every load is issued (volatile asm keeps them ahead of the arithmetic) before the first use
+#pragma unroll
+        for (int u = 0; u < MD_U; u++) {
+          const size_t i = c0 + (size_t)u * 32 + lane;
+#pragma unroll
+          for (int v = 0; v < VPW; v++) xv[v][u] = ld_stream(xp[v] + i);
+          yv[u] = ld_keep(y + i);
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < MD_U; u++) {
+          const size_t i = c0 + (size_t)u * 32 + lane;
+          const bool in = i < n;
+          yv[u] = in ? y[i] : Field<T>::zero();
+#pragma unroll
+          for (int v = 0; v < VPW; v++) xv[v][u] = in ? xp[v][i] : Field<T>::zero();
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < MD_U; u++)
+#pragma unroll
+        for (int v = 0; v < VPW; v++) Field<T>::dot_acc(acc + v * NC, xv[v][u], yv[u]);
+    }
   }
-  double total[K * NC];
-  grid_sum<K * NC>(acc, red, total);
+#pragma unroll
+  for (int r = 0; r < VPW * NC; r++) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) acc[r] += shfl_xor_d(acc[r], m);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int v = 0; v < VPW; v++) {
+      const bool live = j0 + v < a.k;
+#pragma unroll
+      for (int c = 0; c < NC; c++)
+        red.partials[(size_t)((j0 + v) * NC + c) * MAX_PARTIAL_BLOCKS + blockIdx.x] = live ? acc[v * NC + c] : 0.0;
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicInc(red.ticket, gridDim.x - 1);  // wraps to 0 after the last block
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // final pass: warp w finishes the sums of its own vectors
+#pragma unroll
+  for (int r = 0; r < VPW * NC; r++) {
+    const int slot = j0 * NC + r;
+    double t = 0.0;
+    for (int b = lane; b < (int)gridDim.x; b += 32) t += __ldcg(&red.partials[(size_t)slot * MAX_PARTIAL_BLOCKS + b]);
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) t += shfl_xor_d(t, m);
+    if (lane == 0) {
+      red.result_dev[slot] = t;
+      if (red.result_host) red.result_host[slot] = t;
+    }
+  }
 }
 
-// out = init + c0[0]*X[0] + c0[1]*X[1] + ...   (sequential accumulation, generic_gcr.cpp:284-292)
+// out = init + c0[0]*X[0] + c0[1]*X[1] + ...   (sequential accumulation, generic_gcr.cpp:284-292).  The loop over the
+// vectors is unrolled over all MAXK slots so that every load of an element is in flight before the first multiply;
+// the sum still runs in the order j = 0, 1, ... (bit-identical to the serial loop).
 template <typename T>
-__global__ void __launch_bounds__(256) lincomb_kernel(MultiArgs<T> a, const T* init, T* out, size_t n) {
+__global__ void __launch_bounds__(256) lincomb_kernel(MultiArgs<T> a, const T* __restrict__ init, T* __restrict__ out,
+                                                      size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    T xv[MAXK];
+#pragma unroll
+    for (int j = 0; j < MAXK; j++)
+      if (j < a.k) xv[j] = ld_stream(a.X[j] + i);
     T v = init ? init[i] : Field<T>::zero();
-    for (int j = 0; j < a.k; j++) v = fadd(v, fmul(a.c0[j], a.X[j][i]));
+#pragma unroll
+    for (int j = 0; j < MAXK; j++)
+      if (j < a.k) v = fadd(v, fmul(a.c0[j], xv[j]));
     out[i] = v;
   }
 }
@@ -563,9 +643,15 @@ int glb_multi_dot(glb_context* ctx, int dtype, size_t n, int k, const void* cons
       MultiArgs<T> a{};
       a.k = kk;
       for (int j = 0; j < kk; j++) a.X[j] = (const T*)X[base + j];
-      const int grid = blas_grid(ctx, n, 256, 4);
+      // one 128-element chunk per block and step; 3 resident blocks per SM keep ~150 KB of loads in flight per SM
+      size_t want = (n + (size_t)32 * MD_U - 1) / ((size_t)32 * MD_U);
+      const size_t cap = (size_t)ctx->sm_count * 3;
+      const int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
       ProfScope prof(ctx, PROF_MULTI_DOT, (double)n * sizeof(T) * (kk + 1));
-      multi_dot_kernel<T, MAXK><<<grid, 256, 0, ctx->stream>>>(a, (const T*)y, n, ctx->red);
+      if (kk <= 8)
+        multi_dot_kernel<T, 1><<<grid, 256, 0, ctx->stream>>>(a, (const T*)y, n, ctx->red);
+      else
+        multi_dot_kernel<T, 2><<<grid, 256, 0, ctx->stream>>>(a, (const T*)y, n, ctx->red);
       GLB_LAUNCH_CHECK();
       return GLB_OK;
     });

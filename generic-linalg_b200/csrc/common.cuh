@@ -104,6 +104,17 @@ __device__ __forceinline__ double ld_stream(const double* p) {
   asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
   return r;
 }
+// same as a plain load (L1 allocating), but as volatile asm: keeps its place in a hand-ordered batch of loads
+__device__ __forceinline__ cplx ld_keep(const cplx* p) {
+  cplx r;
+  asm volatile("ld.global.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ double ld_keep(const double* p) {
+  double r;
+  asm volatile("ld.global.f64 %0, [%1];" : "=d"(r) : "l"(p));
+  return r;
+}
 __device__ __forceinline__ cplx ld_cached(const cplx* p) { return *p; }
 __device__ __forceinline__ double ld_cached(const double* p) { return *p; }
 __device__ __forceinline__ void st_stream(cplx* p, cplx v) {

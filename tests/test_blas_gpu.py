@@ -117,10 +117,12 @@ def test_elementwise_bit_exact(ctx, glb, n, dtype):
     assert abs(complex(o3[1], o3[2]) - np.vdot(r0_, r)) <= 1e-13 * np.sqrt(np.vdot(r, r).real * np.vdot(r0_, r0_).real)
 
 
-@pytest.mark.parametrize("k", [1, 3, 16, 17, 40])
+@pytest.mark.parametrize("k,n", [(1, 5000), (3, 5000), (8, 5000), (9, 5000), (16, 5000), (17, 5000), (40, 5000),
+                                 (5, 300001), (16, 300001), (7, 128)])
 @pytest.mark.parametrize("dtype", [np.float64, np.complex128])
-def test_multi_vector_ops(ctx, glb, k, dtype):
-    n = 5000
+def test_multi_vector_ops(ctx, glb, k, n, dtype):
+    """n = 5000: 39 full 128-element chunks + a ragged tail; 300001: several chunks per block; k <= 8 / > 8: one / two
+    vectors per warp of multi_dot_kernel; k > 16: several launches"""
     rg = np.random.default_rng(k)
     hs, ds = _vecs(ctx, rg, n, dtype, k + 2)
     cu, h = ctx.cu, ctx.h
@@ -132,6 +134,9 @@ def test_multi_vector_ops(ctx, glb, k, dtype):
     for j in range(k):
         want = np.vdot(hs[j], y_h)
         assert abs(complex(out[2 * j], out[2 * j + 1]) - want) <= 1e-12 * np.linalg.norm(hs[j]) * np.linalg.norm(y_h)
+    out2 = (C.c_double * (2 * k))()
+    assert cu.glb_multi_dot(h, dt, n, k, X, y_d.ptr, out2) == 0
+    assert list(out2) == list(out)  # fixed summation order: run-to-run reproducible
     coefs = rg.standard_normal(2 * k)
     if dtype == np.float64:
         coefs[1::2] = 0.0
