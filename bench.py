@@ -790,11 +790,12 @@ def other_configs(ctx, glb, L, peak):
             return timed(go)
 
         if which != "config 3":
-            # bytes the kernels move per iteration and site (csrc/krylov.cu): BiCGStab 48 + 64 + 112 + 48 + 80, CR 32 + 96 + 80 + 96
+            # bytes the kernels move per iteration and site (csrc/krylov.cu): BiCGStab 48 + 64 + 112 + 48 + 80 = 352,
+            # CR 96 + 80 + 96 = 272
             cases = [("CGNE (minv_vector_cg on D^dag D)", "CG", N, bp, dict(eps=1e-10), "CGNE", 160.0),
                      ("minv_vector_bicgstab on D", "BICGSTAB", D, b, dict(eps=1e-10), "BiCGStab", 352.0)]
             if Lc != 256:
-                cases.append(("minv_vector_cr on D^dag D", "CR", N, bp, dict(eps=1e-10), "CR", 304.0))
+                cases.append(("minv_vector_cr on D^dag D", "CR", N, bp, dict(eps=1e-10), "CR", 272.0))
             for name, solver, op, rhs, kw, key, bytes_it in cases:
                 info, dt = solve(solver, op, rhs, **kw)
                 rec = {"config": which, "L": Lc, "solver": name, "seconds": dt, "iterations": info["iter"],

@@ -32,4 +32,16 @@ struct CgState {
   int pad2;
 };
 
+// Device-resident BiCGStab / CR (krylov.cu).  `cg` first: the operator kernels take this object as their CgState
+// (early exit on cg.done).  The staggered kernel's fused BiCGStab inputs (stencil.cu, FUSE 2 / 3) read rho, beta and
+// omega here and leave alpha.
+struct KrylovState {
+  CgState cg;       // done, iter, max_iter, eps, bnorm, hit_max, hist_cap, rsq_new
+  double rho[2];    // BiCGStab: <r0,r> the current direction was built with ; CR: |Ap|^2 in rho[0]
+  double alpha[2];  // BiCGStab: alpha of the current iteration (formed where s is formed, used by the x/r update);
+                    // CR: <Ap,r> of the coming iteration
+  double omega[2];
+  double beta[2];
+};
+
 }  // namespace glb

@@ -12,7 +12,7 @@
 // iteration counts are the reference's.
 //
 // Per iteration (bytes per site, complex): BiCGStab 48 + 64 + 112 + 48 + 80 = 352 (SURVEY 8 d-bytes fused minimum: 336),
-// CR 32 + 96 + 80 + 96 = 304.  The host enqueues BATCH iterations at a time -- directly or as ONE CUDA-graph launch
+// CR 96 + 80 + 96 = 272 (<Ap,r> rides on the p / Ap update).  The host enqueues BATCH iterations at a time -- directly or as ONE CUDA-graph launch
 // (the kernel arguments never change between iterations) -- and polls the state of the previous batch while the next
 // one runs; kernels past the stopping point return at once, the operator applies through CgState::done.
 #include <cstdlib>
@@ -23,15 +23,6 @@
 namespace glb {
 
 int op_apply_fused(glb_operator* op, void* out, const void* in, const ApplyFusion& f);
-
-// `cg` first: the operator kernels take this object as their CgState (early exit on cg.done; cg_role 0)
-struct KrylovState {
-  CgState cg;       // done, iter, max_iter, eps, bnorm, hit_max, hist_cap, rsq_new
-  double rho[2];    // BiCGStab: <r0,r> the current direction was built with ; CR: |Ap|^2 in rho[0]
-  double alpha[2];  // BiCGStab: alpha of the current iteration (formed by the s kernel, used by the x/r update)
-  double omega[2];
-  double beta[2];
-};
 
 namespace {
 
@@ -136,24 +127,14 @@ struct FBicgP {
   __device__ void epilogue(const double*, KrylovState*, double*) const {}
 };
 
-// CR: <Ap,r> (generic_cr.cpp:249)                                                          vectors: Ap, r
-template <typename T>
-struct FCrDot {
-  static constexpr int NV = 2, RD = 3, WR = 0, NRED = Field<T>::NCOMP;
-  __device__ void prologue(const KrylovState*, const double*) {}
-  __device__ void persist(KrylovState*) const {}
-  __device__ void elem(T (&e)[NV], double* acc) const { Field<T>::dot_acc(acc, e[0], e[1]); }
-  __device__ void epilogue(const double*, KrylovState*, double*) const {}
-};
-
 // CR: alpha = <Ap,r>/|Ap|^2 ; x += alpha p ; r -= alpha Ap ; |r|^2 ; stopping test (generic_cr.cpp:249-265)
 //                                                                                          vectors: p, x, Ap, r
 template <typename T>
 struct FCrXR {
   static constexpr int NV = 4, RD = 15, WR = 10, NRED = 1;
   T a, b;
-  __device__ void prologue(const KrylovState* st, const double* res) {
-    a = frdiv(Field<T>::from(res), st->rho[0]);  // complex / double: component-wise
+  __device__ void prologue(const KrylovState* st, const double*) {
+    a = frdiv(Field<T>::from(st->alpha), st->rho[0]);  // <Ap,r> / |Ap|^2 ; complex / double: component-wise
     b = fneg(a);
   }
   __device__ void persist(KrylovState*) const {}
@@ -165,11 +146,12 @@ struct FCrXR {
   __device__ void epilogue(const double* total, KrylovState* st, double* hist) const { stop_test(st, hist, total[0]); }
 };
 
-// CR: beta = -<Ap,Ar>/|Ap|^2 ; p = r + beta p ; Ap = Ar + beta Ap ; |Ap|^2 (generic_cr.cpp:275-285)
-//                                                                                          vectors: r, Ar, p, Ap
+// CR: beta = -<Ap,Ar>/|Ap|^2 ; p = r + beta p ; Ap = Ar + beta Ap ; |Ap|^2 (generic_cr.cpp:275-285), and the next
+// iteration's <Ap,r> (:249) while Ap and r are in registers -- same elements per thread, same order and same
+// reduction tree as the separate dot kernel of the shell, so the same bits      vectors: r, Ar, p, Ap
 template <typename T>
 struct FCrPAp {
-  static constexpr int NV = 4, RD = 15, WR = 12, NRED = 1;
+  static constexpr int NV = 4, RD = 15, WR = 12, NRED = 1 + Field<T>::NCOMP;
   T beta;
   __device__ void prologue(const KrylovState* st, const double* res) {
     beta = frdiv(fneg(Field<T>::from(res)), st->rho[0]);
@@ -179,8 +161,12 @@ struct FCrPAp {
     e[2] = fadd(e[0], fmul(beta, e[2]));
     e[3] = fadd(e[1], fmul(beta, e[3]));
     acc[0] += fnorm(e[3]);
+    Field<T>::dot_acc(acc + 1, e[3], e[0]);
   }
-  __device__ void epilogue(const double* total, KrylovState* st, double*) const { st->rho[0] = total[0]; }
+  __device__ void epilogue(const double* total, KrylovState* st, double*) const {
+    st->rho[0] = total[0];
+    put(st->alpha, Field<T>::from(total + 1));
+  }
 };
 
 // The streaming kernel of blas1.cu (32 bytes per vector per thread and step, grid-stride loop, deterministic grid
@@ -265,7 +251,8 @@ bool graph_mode() {
 }
 
 // Enqueue iterations in batches until the state says the loop has ended (same protocol as glb_cg_solve): the state
-// after batch i is copied to a pinned slot asynchronously and looked at while batch i+1 runs.
+// after batch i is copied to a pinned slot asynchronously and looked at while batch i+1 runs.  enqueue_iteration(i)
+// gets the index of the iteration it enqueues (only its parity matters: BATCH is even, a captured batch starts even).
 template <typename Enq>
 int run_batches(glb_context* ctx, KrylovState* d_st, int max_iter, KrylovState* fin, Enq&& enqueue_iteration) {
   const int BATCH = 8;
@@ -289,7 +276,7 @@ int run_batches(glb_context* ctx, KrylovState* d_st, int max_iter, KrylovState* 
       enq += BATCH;
     } else {
       for (int b = 0; b < BATCH; b++) {
-        if ((rc = enqueue_iteration())) goto out;
+        if ((rc = enqueue_iteration(enq))) goto out;
         enq++;
       }
     }
@@ -316,7 +303,7 @@ int run_batches(glb_context* ctx, KrylovState* d_st, int max_iter, KrylovState* 
       cudaGraph_t graph = nullptr;
       if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
         int erc = GLB_OK;
-        for (int b = 0; b < BATCH && erc == GLB_OK; b++) erc = enqueue_iteration();
+        for (int b = 0; b < BATCH && erc == GLB_OK; b++) erc = enqueue_iteration(b);  // enq is a multiple of BATCH here
         const cudaError_t e1 = cudaStreamEndCapture(ctx->stream, &graph);
         if (erc != GLB_OK || e1 != cudaSuccess || graph == nullptr ||
             cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess)
@@ -395,7 +382,7 @@ int krylov_solve_t(glb_operator* op, int alg, void* d_x, const void* d_b, int ma
       const KPtrs<3> k1{{Ap, r, s}};
       const KPtrs<6> k3{{p, s, As, r0, d_x, r}};
       const KPtrs<3> k4{{r, Ap, p}};
-      KR_TRY(run_batches(ctx, d_st, max_iter, &fin, [&]() -> int {
+      KR_TRY(run_batches(ctx, d_st, max_iter, &fin, [&](int) -> int {
         int e;
         if ((e = run_ews<T, FBicgS<T>>(ctx, k1, n, d_st, nullptr))) return e;
         if ((e = apply_red(op, d_st, As, s, s, true))) return e;  // As = A s ; <s,As>, |As|^2
@@ -412,20 +399,21 @@ int krylov_solve_t(glb_operator* op, int alg, void* d_x, const void* d_b, int ma
       KR_TRY(glb_vec_copy(ctx, dt, n, p, r));
       KR_TRY(glb_op_apply(op, Ap, p));
       KR_TRY(glb_vec_copy(ctx, dt, n, Ar, Ap));
-      double apsq = 0.0;
+      double apsq = 0.0, apr[2] = {0.0, 0.0};
       KR_TRY(glb_norm2sq(ctx, dt, n, Ap, &apsq));
+      KR_TRY(glb_dot(ctx, dt, n, Ap, r, apr));  // <Ap,r> of the first iteration; later ones come from the p/Ap update
       init.rho[0] = apsq;
+      init.alpha[0] = apr[0];
+      init.alpha[1] = apr[1];
       h_st[0] = init;
       if (cudaMemcpyAsync(d_st, &h_st[0], sizeof(KrylovState), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
         rc = fail(GLB_ERR_CUDA, "upload KrylovState");
         goto done;
       }
-      const KPtrs<2> k0{{Ap, r}};
       const KPtrs<4> k1{{p, d_x, Ap, r}};
       const KPtrs<4> k3{{r, Ar, p, Ap}};
-      KR_TRY(run_batches(ctx, d_st, max_iter, &fin, [&]() -> int {
+      KR_TRY(run_batches(ctx, d_st, max_iter, &fin, [&](int) -> int {
         int e;
-        if ((e = run_ews<T, FCrDot<T>>(ctx, k0, n, d_st, nullptr))) return e;
         if ((e = run_ews<T, FCrXR<T>>(ctx, k1, n, d_st, d_hist))) return e;
         if ((e = apply_red(op, d_st, Ar, r, Ap, false))) return e;  // Ar = A r ; <Ap,Ar>
         return run_ews<T, FCrPAp<T>>(ctx, k3, n, d_st, nullptr);

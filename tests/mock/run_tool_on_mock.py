@@ -12,6 +12,7 @@ glb.C.CDLL = lambda path, mode=0: R._Tolerant(real(R.MOCK, mode=C.RTLD_LOCAL))
 glb._libs = None
 cu, ho = glb.libs()
 glb.C.CDLL = real
-mod = importlib.import_module(sys.argv[1])
-sys.argv = [sys.argv[1]] + sys.argv[2:]
+name = sys.argv[1]
+sys.argv = [name] + sys.argv[2:]
+mod = importlib.import_module(name)
 mod.main()
