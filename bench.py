@@ -287,6 +287,7 @@ def main():
                                                       "split over the GPUs); default L rows per GPU (weak)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling block")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the lattice sweep 256^2 ... 2048^2 (N=1)")
     ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configurations (N=1)")
     ap.add_argument("--strong-sizes", type=int, nargs="*", default=[4096, 8192])
     ap.add_argument("--apply-reps", type=int, default=50)
@@ -530,6 +531,15 @@ def main():
         except Exception as e:  # noqa: BLE001
             configs = [{"error": "%s: %s" % (type(e).__name__, e)}]
 
+    # ---- lattice sweep (north_star: stencil GB/s and iterations/s from 256^2 up, as a fraction of the HBM roofline);
+    # 4096^2 is the headline run, 8192^2 the strong block
+    sweep = None
+    if world == 1 and not args.no_sweep:
+        try:
+            sweep = lattice_sweep(ctx, glb, torch, stream, peak)
+        except Exception as e:  # noqa: BLE001
+            sweep = [{"error": "%s: %s" % (type(e).__name__, e)}]
+
     if rank != 0:
         return
 
@@ -617,6 +627,8 @@ def main():
         line["strong"] = strong
     if configs is not None:
         line["configs"] = configs
+    if sweep is not None:
+        line["sweep"] = sweep
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line))
@@ -752,6 +764,59 @@ def strong_case(ctx, glb, torch, dist, stream, barrier, max_over_ranks, Lg, worl
     if ref:
         out["reference_iterations"] = ref
     return out
+
+
+def lattice_sweep(ctx, glb, torch, stream, peak, sizes=(256, 512, 1024, 2048)):
+    """staggered D apply and CGNE solve per lattice size on one GPU (mt19937 inputs): GB/s on moved bytes, fraction of
+    the measured HBM peak, iterations/s.  Up to 1024^2 the working set fits the 126 MB L2: latency / launch bound."""
+    res = []
+    gold = golden_large()
+    for Ls in sizes:
+        V = Ls * Ls
+        links, b_h = ctx.synthetic_inputs(Ls, Ls, SEED, BETA)
+        D = ctx.staggered(links, Ls, Ls, MASS, 0)
+        N = ctx.staggered(links, Ls, Ls, MASS, glb.STAG_NORMAL)
+        Dd = ctx.staggered(links, Ls, Ls, MASS, glb.STAG_DAGGER)
+        b = ctx.vector(V).upload(b_h)
+        bp, x, out = ctx.vector(V), ctx.vector(V), ctx.vector(V)
+        Dd.apply(bp, b)
+
+        def events(fn, reps, warm):
+            for _ in range(warm):
+                fn()
+            ctx.sync()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            r = None
+            for _ in range(reps):
+                r = fn()
+            e1.record(stream)
+            ctx.sync()
+            torch.cuda.synchronize()
+            return r, e0.elapsed_time(e1) / reps
+
+        _, a_ms = events(lambda: D.apply(out, b), 200 if Ls <= 1024 else 50, 5)
+
+        def go():
+            x.zero()
+            return ctx.solve("CG", N, x, bp, max_iter=5000, eps=TOL)
+        info, s_ms = events(go, 5, 2)
+        it = info["iter"]
+        rec = {"lattice": [Ls, Ls], "apply_ms": a_ms, "apply_GBps": 64.0 * V / a_ms / 1e6,
+               "apply_frac_of_hbm_peak": 64.0 * V / a_ms / 1e6 / peak,
+               "cgne_ms_per_solve": s_ms, "cgne_iterations": it, "cgne_iterations_per_s": it / (s_ms * 1e-3),
+               "cgne_GBps": solve_bytes(V, it) / (s_ms * 1e-3) / 1e9,
+               "cgne_frac_of_hbm_peak": solve_bytes(V, it) / (s_ms * 1e-3) / 1e9 / peak}
+        ref = gold.get(str(Ls), {}).get("CGNE", {}).get("iter")
+        if ref:
+            rec["reference_iterations"] = ref
+        if V * 160 <= 126e6:
+            rec["note"] = "working set fits the L2: latency / launch bound"
+        res.append(rec)
+        for o in (D, N, Dd):
+            o.destroy()
+        del b, bp, x, out
+    return res
 
 
 def other_configs(ctx, glb, L, peak):
