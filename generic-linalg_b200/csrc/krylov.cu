@@ -260,6 +260,7 @@ int run_batches(glb_context* ctx, KrylovState* d_st, int max_iter, KrylovState* 
   static_assert(2 * sizeof(KrylovState) <= 4096, "pinned scratch of the context is 4 KiB");
   int rc = GLB_OK;
   cudaGraphExec_t exec = nullptr;
+  unsigned long long graph_kernels = 0;  // kernels one replay launches (glb_kernel_launches counts kernels, not graphs)
   g_last_used_graph = 0;
   // the first batch is launched directly (it also loads every kernel); later batches replay ONE graph
   bool try_graph = graph_mode() && !ctx->prof_on && max_iter > BATCH;
@@ -271,7 +272,7 @@ int run_batches(glb_context* ctx, KrylovState* d_st, int max_iter, KrylovState* 
         rc = fail(GLB_ERR_CUDA, "cudaGraphLaunch");
         goto out;
       }
-      g_launches.fetch_add(1, std::memory_order_relaxed);
+      g_launches.fetch_add(graph_kernels, std::memory_order_relaxed);
       g_last_used_graph = 1;
       enq += BATCH;
     } else {
@@ -301,6 +302,7 @@ int run_batches(glb_context* ctx, KrylovState* d_st, int max_iter, KrylovState* 
       // one batch as a graph: the arguments of the kernels do not change from one iteration to the next
       try_graph = false;
       cudaGraph_t graph = nullptr;
+      const unsigned long long l0 = g_launches.load(std::memory_order_relaxed);
       if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
         int erc = GLB_OK;
         for (int b = 0; b < BATCH && erc == GLB_OK; b++) erc = enqueue_iteration(b);  // enq is a multiple of BATCH here
@@ -310,6 +312,9 @@ int run_batches(glb_context* ctx, KrylovState* d_st, int max_iter, KrylovState* 
           exec = nullptr;
         if (graph) cudaGraphDestroy(graph);
       }
+      // the launches counted while capturing were recorded, not run
+      graph_kernels = g_launches.load(std::memory_order_relaxed) - l0;
+      g_launches.fetch_sub(graph_kernels, std::memory_order_relaxed);
       cudaGetLastError();  // a failed capture must not poison the direct path
     }
   }
