@@ -47,6 +47,97 @@ cplx cf<cplx>(const double a[2]) { return cplx(a[0], a[1]); }
     }                                          \
   } while (0)
 
+static void pk(double a, double o[2]) { o[0] = a; o[1] = 0.0; }
+static void pk(const cplx& a, double o[2]) { o[0] = a.real(); o[1] = a.imag(); }
+static double cj(double a) { return a; }
+static cplx cj(const cplx& a) { return std::conj(a); }
+
+template <typename T>
+static int mock_krylov(glb_operator* op, int alg, T* x, const T* b, int max_iter, double eps, glb_cg_report* rep,
+                       double* hist, int hist_cap) {
+  glb_context* c = op->ctx;
+  const int dt = op->dtype;
+  const size_t n = op->op->size;
+  std::vector<T> v[6];
+  for (int i = 0; i < 6; i++) v[i].assign(n, T(0));
+  double bsq = 0.0;
+  glb_norm2sq(c, dt, n, b, &bsq);
+  const double bnorm = std::sqrt(bsq);
+  int iter = 0, hit_max = 0;
+  double rsq = 0.0;
+  auto stop = [&](int k) {  // the epilogue of the x / r update kernel
+    iter = k + 1;
+    if (hist && k < hist_cap) hist[k] = rsq;
+    const bool conv = std::sqrt(rsq) < eps * bnorm, last = (k == max_iter - 1);
+    if (conv || last) hit_max = last ? 1 : 0;
+    return conv || last;
+  };
+  if (alg == GLB_KRYLOV_BICGSTAB) {
+    T *r = v[0].data(), *r0 = v[1].data(), *p = v[2].data(), *Ap = v[3].data(), *s = v[4].data(), *As = v[5].data();
+    double d[3], o3[3], ca[2], co[2], cb[2];
+    glb_op_apply(op, Ap, x);
+    glb_sub(c, dt, n, b, Ap, r);
+    glb_vec_copy(c, dt, n, r0, r);
+    glb_vec_copy(c, dt, n, p, r);
+    glb_dot(c, dt, n, r0, r, d);
+    T rho = cf<T>(d);
+    glb_op_apply_dot(op, Ap, p, r0, 0, d);
+    T r0Ap = cf<T>(d);
+    for (int k = 0; k < max_iter; k++) {
+      const T alpha = rho / r0Ap;                       // prologue of the s kernel
+      const T nalpha = -alpha;
+      pk(nalpha, ca);
+      glb_axpyz(c, dt, n, ca, Ap, r, s);                // s = r - alpha Ap
+      glb_op_apply_dot(op, As, s, s, 1, d);             // As = A s ; <s,As>, |As|^2
+      const T omega = cj(cf<T>(d)) / T(d[2]);           // prologue of the x / r update
+      pk(alpha, ca);
+      pk(omega, co);
+      glb_bicgstab_update(c, dt, n, ca, p, co, s, As, r0, x, r, o3);
+      rsq = o3[0];
+      if (stop(k)) break;
+      const T rhoNew = cf<T>(o3 + 1);                   // its epilogue
+      const T beta = rhoNew / rho * (alpha / omega);
+      rho = rhoNew;
+      pk(beta, cb);
+      glb_bicgstab_pupdate(c, dt, n, r, cb, co, Ap, p);
+      glb_op_apply_dot(op, Ap, p, r0, 0, d);            // Ap = A p ; <r0,Ap>
+      r0Ap = cf<T>(d);
+    }
+    rep->ops = 2 + iter + (iter > 0 ? iter - 1 : 0);
+  } else {
+    T *r = v[0].data(), *Ar = v[1].data(), *p = v[2].data(), *Ap = v[3].data();
+    double d[3], ca[2], cna[2], cb[2], apsq = 0.0;
+    glb_op_apply(op, p, x);
+    glb_sub(c, dt, n, b, p, r);
+    glb_vec_copy(c, dt, n, p, r);
+    glb_op_apply(op, Ap, p);
+    glb_vec_copy(c, dt, n, Ar, Ap);
+    glb_norm2sq(c, dt, n, Ap, &apsq);
+    glb_dot(c, dt, n, Ap, r, d);
+    T Apr = cf<T>(d);
+    for (int k = 0; k < max_iter; k++) {
+      const T alpha = Apr / apsq;                       // prologue of the x / r update
+      const T nalpha = -alpha;
+      pk(alpha, ca);
+      pk(nalpha, cna);
+      glb_update_xr_norm(c, dt, n, ca, p, x, cna, Ap, r, &rsq);
+      if (stop(k)) break;
+      glb_op_apply_dot(op, Ar, r, Ap, 0, d);            // Ar = A r ; <Ap,Ar>
+      const T beta = -cf<T>(d) / apsq;                  // prologue of the p / Ap update
+      pk(beta, cb);
+      glb_update_p_ap_norm(c, dt, n, r, Ar, cb, p, Ap, &apsq);
+      glb_dot(c, dt, n, Ap, r, d);                      // ... which also sums <Ap,r> for the next iteration
+      Apr = cf<T>(d);
+    }
+    rep->ops = 2 + (iter > 0 ? iter - 1 : 0);
+  }
+  rep->iterations = iter;
+  rep->hit_max_iter = hit_max;
+  rep->rsq = rsq;
+  rep->bnorm = bnorm;
+  return GLB_OK;
+}
+
 extern "C" {
 int glb_create(int, glb_context** ctx) { *ctx = &g_ctx; return GLB_OK; }
 int glb_destroy(glb_context*) { return GLB_OK; }
@@ -401,10 +492,33 @@ int glb_cgm_update_p(glb_context*, int dt, size_t n, int ns, const double* zeta,
 // the device-resident CG is a CUDA-only entry point: the shells fall back to the host-scalar loop
 // when forced (glb200_force_host_scalars), which is what the mock tests do.
 int glb_cg_solve_supported(const glb_operator*) { return 0; }
-int glb_krylov_solve_supported(const glb_operator*, int) { return 0; }
-int glb_krylov_solve(glb_operator*, int, void*, const void*, int, double, glb_cg_report*, double*, int) {
-  g_err = "glb_krylov_solve is not available in the CPU mock";
-  return GLB_ERR_STATE;
+// glb_krylov_solve (csrc/krylov.cu) restated on the host: the SAME sequence of vector operations and the SAME scalar
+// formulas the device loop evaluates in its kernel prologues / epilogues (alpha = rho / <r0,Ap>, omega =
+// conj(<s,As>) / T(|As|^2), beta = rhoNew/rho * (alpha/omega); CR: alpha = <Ap,r> / |Ap|^2, beta = -<Ap,Ar> / |Ap|^2,
+// <Ap,r> of the next iteration taken while p and Ap are updated), the stopping test, the iteration / operator counts
+// and the residual history.  With it the device-loop branches of bicgstab_dev / cr_dev (host/dev_solvers.cpp: history
+// replay for VERB_DETAIL, success flags, ops counts) run on the CPU and are compared with the reference line by line
+// (tests/test_krylov_mock_cpu.py, tests/test_reference_programs_cpu.py).  GLB200_MOCK_NO_KRYLOV=1 switches it off.
+static bool mock_krylov_on() {
+  const char* e = std::getenv("GLB200_MOCK_NO_KRYLOV");
+  return !(e && *e && std::atoi(e) != 0);
+}
+int glb_krylov_solve_supported(const glb_operator* o, int alg) {
+  if (!o || (alg != GLB_KRYLOV_BICGSTAB && alg != GLB_KRYLOV_CR)) return 0;
+  if (o->composite) return 0;  // as the CUDA library: no fused reductions on the composite views
+  return mock_krylov_on() ? 1 : 0;
+}
+static unsigned long long g_krylov_calls = 0;
+unsigned long long glb200_mock_krylov_calls(void) { return g_krylov_calls; }  // test aid: was the device-loop branch taken?
+int glb_krylov_solve(glb_operator* op, int alg, void* x, const void* b, int max_iter, double eps, glb_cg_report* rep,
+                     double* hist, int hist_cap) {
+  g_krylov_calls++;
+  if (!op || !x || !b || !rep || max_iter < 1 || !glb_krylov_solve_supported(op, alg)) {
+    g_err = "glb_krylov_solve: bad argument / not supported";
+    return GLB_ERR_ARG;
+  }
+  if (op->dtype == GLB_COMPLEX) return mock_krylov<cplx>(op, alg, (cplx*)x, (const cplx*)b, max_iter, eps, rep, hist, hist_cap);
+  return mock_krylov<double>(op, alg, (double*)x, (const double*)b, max_iter, eps, rep, hist, hist_cap);
 }
 int glb_krylov_graph_mode(int) { return 0; }
 int glb_krylov_last_used_graph(void) { return 0; }
