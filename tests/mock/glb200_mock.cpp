@@ -138,6 +138,51 @@ static int mock_krylov(glb_operator* op, int alg, T* x, const T* b, int max_iter
   return GLB_OK;
 }
 
+template <typename T>
+static int mock_cg(glb_operator* op, T* x, const T* b, int max_iter, double eps, glb_cg_report* rep, double* hist,
+                   int hist_cap) {
+  glb_context* c = op->ctx;
+  const int dt = op->dtype;
+  const size_t n = op->op->size;
+  std::vector<T> r(n), p(n), Ap(n);
+  double bsq = 0.0, rsq = 0.0, rsqNew = 0.0, d[3], ca[2], cna[2], cb[2];
+  glb_norm2sq(c, dt, n, b, &bsq);
+  const double bnorm = std::sqrt(bsq);
+  glb_op_apply(op, p.data(), x);
+  glb_sub(c, dt, n, b, p.data(), r.data());
+  glb_vec_copy(c, dt, n, p.data(), r.data());
+  glb_op_apply_dot(op, Ap.data(), p.data(), p.data(), 0, d);
+  T pAp = cf<T>(d);
+  glb_norm2sq(c, dt, n, r.data(), &rsq);
+  int iter = 0, hit_max = 0;
+  for (int k = 0; k < max_iter; k++) {
+    const T alpha = rsq / pAp;
+    const T nalpha = -alpha;
+    pk(alpha, ca);
+    pk(nalpha, cna);
+    glb_update_xr_norm(c, dt, n, ca, p.data(), x, cna, Ap.data(), r.data(), &rsqNew);
+    iter = k + 1;
+    if (hist && k < hist_cap) hist[k] = rsqNew;
+    const bool conv = std::sqrt(rsqNew) < eps * bnorm, last = (k == max_iter - 1);
+    if (conv || last) {
+      hit_max = last ? 1 : 0;
+      break;
+    }
+    const T beta = T(rsqNew / rsq);
+    rsq = rsqNew;
+    pk(beta, cb);
+    glb_xpay(c, dt, n, r.data(), cb, p.data());
+    glb_op_apply_dot(op, Ap.data(), p.data(), p.data(), 0, d);
+    pAp = cf<T>(d);
+  }
+  rep->iterations = iter;
+  rep->ops = 2 + (iter > 0 ? iter - 1 : 0);
+  rep->hit_max_iter = hit_max;
+  rep->rsq = rsqNew;
+  rep->bnorm = bnorm;
+  return GLB_OK;
+}
+
 extern "C" {
 int glb_create(int, glb_context** ctx) { *ctx = &g_ctx; return GLB_OK; }
 int glb_destroy(glb_context*) { return GLB_OK; }
@@ -491,7 +536,11 @@ int glb_cgm_update_p(glb_context*, int dt, size_t n, int ns, const double* zeta,
 }
 // the device-resident CG is a CUDA-only entry point: the shells fall back to the host-scalar loop
 // when forced (glb200_force_host_scalars), which is what the mock tests do.
-int glb_cg_solve_supported(const glb_operator*) { return 0; }
+static bool mock_krylov_on() {
+  const char* e = std::getenv("GLB200_MOCK_NO_KRYLOV");
+  return !(e && *e && std::atoi(e) != 0);
+}
+int glb_cg_solve_supported(const glb_operator* o) { return (o && !o->composite && mock_krylov_on()) ? 1 : 0; }
 // glb_krylov_solve (csrc/krylov.cu) restated on the host: the SAME sequence of vector operations and the SAME scalar
 // formulas the device loop evaluates in its kernel prologues / epilogues (alpha = rho / <r0,Ap>, omega =
 // conj(<s,As>) / T(|As|^2), beta = rhoNew/rho * (alpha/omega); CR: alpha = <Ap,r> / |Ap|^2, beta = -<Ap,Ar> / |Ap|^2,
@@ -499,10 +548,6 @@ int glb_cg_solve_supported(const glb_operator*) { return 0; }
 // and the residual history.  With it the device-loop branches of bicgstab_dev / cr_dev (host/dev_solvers.cpp: history
 // replay for VERB_DETAIL, success flags, ops counts) run on the CPU and are compared with the reference line by line
 // (tests/test_krylov_mock_cpu.py, tests/test_reference_programs_cpu.py).  GLB200_MOCK_NO_KRYLOV=1 switches it off.
-static bool mock_krylov_on() {
-  const char* e = std::getenv("GLB200_MOCK_NO_KRYLOV");
-  return !(e && *e && std::atoi(e) != 0);
-}
 int glb_krylov_solve_supported(const glb_operator* o, int alg) {
   if (!o || (alg != GLB_KRYLOV_BICGSTAB && alg != GLB_KRYLOV_CR)) return 0;
   if (o->composite) return 0;  // as the CUDA library: no fused reductions on the composite views
@@ -526,9 +571,19 @@ double glb_cg_last_pred_err(void) { return 0.0; }
 int glb_cg_step_mode(int, int) { return 0; }
 int glb_dbg_p2p_bench(glb_context*, int, int, double, float*) { return GLB_ERR_STATE; }
 int glb_dbg_p2p_pingpong(glb_context*, int, int, float*) { return GLB_ERR_STATE; }
-int glb_cg_solve(glb_operator*, void*, const void*, int, double, glb_cg_report*, double*, int) {
-  g_err = "glb_cg_solve is not available in the CPU mock";
-  return GLB_ERR_STATE;
+// glb_cg_solve restated on the host: the two-kernel device loop of csrc/cg.cu (= the reference's CG recurrence,
+// generic_cg.cpp:304-354), so that the device-loop branch of cg_dev (history replay, counts, success) runs on the CPU.
+// (The single-kernel iteration of cgstep.cu predicts beta's numerator one step ahead; that arithmetic is CUDA-only
+// and checked on the GPU.)
+int glb_cg_solve(glb_operator* op, void* x, const void* b, int max_iter, double eps, glb_cg_report* rep, double* hist,
+                 int hist_cap) {
+  g_krylov_calls++;
+  if (!op || !x || !b || !rep || max_iter < 1 || !glb_cg_solve_supported(op)) {
+    g_err = "glb_cg_solve: bad argument / not supported";
+    return GLB_ERR_ARG;
+  }
+  if (op->dtype == GLB_COMPLEX) return mock_cg<cplx>(op, (cplx*)x, (const cplx*)b, max_iter, eps, rep, hist, hist_cap);
+  return mock_cg<double>(op, (double*)x, (const double*)b, max_iter, eps, rep, hist, hist_cap);
 }
 
 // multigrid grid transfers: host loops in the reference's accumulation order (mg_complex.cpp:372-467)

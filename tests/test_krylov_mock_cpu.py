@@ -1,7 +1,7 @@
-"""The device-loop branches of the BiCGStab / CR shells (host/dev_solvers.cpp: glb_krylov_solve, history replay for
-VERB_DETAIL, success flags, operator counts) without a GPU.
+"""The device-loop branches of the CG / BiCGStab / CR shells (host/dev_solvers.cpp: glb_cg_solve, glb_krylov_solve,
+history replay for VERB_DETAIL, success flags, operator counts) without a GPU.
 
-tests/mock/glb200_mock.cpp restates glb_krylov_solve (csrc/krylov.cu) on the host: the same sequence of vector
+tests/mock/glb200_mock.cpp restates glb_krylov_solve (csrc/krylov.cu) and the two-kernel glb_cg_solve (csrc/cg.cu) on the host: the same sequence of vector
 operations and the same scalar formulas the CUDA loop evaluates in its kernel prologues / epilogues, with the mock's
 serial reductions.  Through it the branch a GPU run takes must reproduce the REFERENCE bit for bit -- solution,
 iteration / operator counts, success flags, residual -- and print, at VERB_DETAIL, exactly the lines the host-scalar
@@ -21,7 +21,7 @@ from conftest import ROOT, load_pkg, synthetic
 from test_oracle_cpu import SOLVES
 
 MOCK = os.path.join(ROOT, "tests", "mock", "libglb200_inverters_mock.so")
-KRYLOV = ("CR", "CR_RESTART", "BICGSTAB", "BICGSTAB_RESTART")
+KRYLOV = ("CG", "CG_RESTART", "CR", "CR_RESTART", "BICGSTAB", "BICGSTAB_RESTART")
 
 
 @pytest.fixture(scope="module")
@@ -100,6 +100,8 @@ def test_device_loop_branch_bit_identical_to_oracle(mock, kind, solver, kw):
 
 
 @pytest.mark.parametrize("kind,solver,kw", [("STAG_U1", "BICGSTAB", {}), ("STAG_NORMAL_U1", "CR", {}),
+                                            ("STAG_NORMAL_U1", "CG", {}), ("LAPLACE_REAL", "CG", dict(max_iter=7)),
+                                            ("STAG_NORMAL_U1", "CG_RESTART", dict(restart_freq=32)),
                                             ("LAPLACE_REAL", "BICGSTAB", {}), ("LAPLACE_REAL", "CR", dict(max_iter=7)),
                                             ("STAG_U1", "BICGSTAB", dict(max_iter=9)),
                                             ("STAG_NORMAL_U1", "CR_RESTART", dict(restart_freq=32)),
